@@ -1,0 +1,425 @@
+// Device-resident seeded reciprocal nearest-neighbour search + correspondence merge.
+//
+// Replaces the host/numpy control flow of
+//   mast3r/mast3r/fast_nn.py:109-188  (fast_reciprocal_NNs, pixel_tol=0, ret_basin=False)
+//   mast3r/mast3r/fast_nn.py:87-106   (merge_corres)
+//   mast3r/mast3r/cloud_opt/sparse_ga.py:595-630 (extract_correspondences)
+// The reference does 2 D2H + 2 H2D round trips per iteration; here the active
+// (not-yet-converged) seed list, its length and the convergence flags stay in
+// HBM and every kernel of the fixed launch chain reads the live count.
+#include "common.cuh"
+#include "nn.cuh"
+#include "radix_sort.cuh"
+#include "recip.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+static inline int nblk(int n) { return (n + TPB - 1) / TPB; }
+
+struct RecipState {
+  int32_t* xy[2];      // xy[0] = xy1 (index into map 1), xy[1] = xy2
+  int32_t* old[2];
+  uint8_t* notyet;
+  int32_t* active[2];  // ping-pong active slot lists
+  int32_t* counts;     // counts[h] = active length before half-iteration h
+  int32_t* qidx;       // query row indices of the current half-iteration
+  unsigned long long* packed;
+};
+
+__global__ void recip_init(RecipState st, int n, int nx, int S, int W1, const int32_t* seeds, int ncounts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ncounts) st.counts[i] = (i == 0) ? n : 0;
+  if (i >= n) return;
+  int32_t s;
+  if (seeds) {
+    s = seeds[i];
+  } else {
+    int y = S / 2 + (i / nx) * S, x = S / 2 + (i % nx) * S;
+    s = x + W1 * y;
+  }
+  st.xy[0][i] = s; st.old[0][i] = s;
+  st.xy[1][i] = -1; st.old[1][i] = -1;
+  st.notyet[i] = 1;
+  st.active[0][i] = i;
+}
+
+// qidx[i] = xy_src[active[i]]; clears the packed result slots.
+__global__ void recip_prepare(const int32_t* __restrict__ xy_src, const int32_t* __restrict__ active,
+                              const int32_t* __restrict__ count_ptr, int32_t* __restrict__ qidx,
+                              unsigned long long* __restrict__ packed) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *count_ptr) return;
+  qidx[i] = xy_src[active[i]];
+  packed[i] = 0ull;
+}
+
+// Scatter NN results, drop converged slots, build the next active list.
+__global__ void recip_update(int32_t* __restrict__ xy_dst, int32_t* __restrict__ old_dst,
+                             uint8_t* __restrict__ notyet, const int32_t* __restrict__ active,
+                             const int32_t* __restrict__ count_ptr,
+                             const unsigned long long* __restrict__ packed,
+                             int32_t* __restrict__ active_next, int32_t* __restrict__ count_next) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool in = i < *count_ptr;
+  bool keep = false;
+  int s = 0;
+  if (in) {
+    s = active[i];
+    int j = nn_unpack_idx(packed[i]);
+    xy_dst[s] = j;
+    keep = old_dst[s] != j;
+    old_dst[s] = j;
+    if (!keep) notyet[s] = 0;
+  }
+  unsigned m = __ballot_sync(0xffffffffu, keep);
+  if (m) {
+    int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane_id() == leader) base = atomicAdd(count_next, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (keep) active_next[base + __popc(m & ((1u << lane_id()) - 1u))] = s;
+  }
+}
+
+// Append converged (idx_a, idx_b) pairs as sort keys:  key = idx1<<33 | idx2<<1 | set.
+__global__ void recip_collect(const int32_t* __restrict__ xy1, const int32_t* __restrict__ xy2,
+                              const uint8_t* __restrict__ notyet, int n, int swap, int set,
+                              uint64_t* __restrict__ keys, int32_t* __restrict__ nkeys, int cap) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool conv = i < n && notyet[i] == 0;
+  unsigned m = __ballot_sync(0xffffffffu, conv);
+  if (!m) return;
+  int leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane_id() == leader) base = atomicAdd(nkeys, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (conv) {
+    int pos = base + __popc(m & ((1u << lane_id()) - 1u));
+    uint32_t a = (uint32_t)xy1[i], b = (uint32_t)xy2[i];
+    if (swap) { uint32_t t = a; a = b; b = t; }
+    if (pos < cap) keys[pos] = ((uint64_t)a << 33) | ((uint64_t)b << 1) | (uint64_t)set;
+  }
+}
+
+__global__ void pack_pairs(const int32_t* __restrict__ idx1, const int32_t* __restrict__ idx2, int n,
+                           uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int32_t* nkeys) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *nkeys = n;
+  if (i >= n) return;
+  keys[i] = ((uint64_t)(uint32_t)idx1[i] << 33) | ((uint64_t)(uint32_t)idx2[i] << 1);
+  vals[i] = (uint32_t)i;
+}
+
+// Single-CTA ordered compaction of the first element of every run of equal (key>>1).
+// Output modes: idx pairs (int32), first-occurrence positions, or xy (int64) + conf.
+struct UniqueOut {
+  int32_t* idx1; int32_t* idx2; int32_t* index;   // may be NULL
+  int64_t* xy1; int64_t* xy2; float* conf;        // may be NULL
+  const float* q1[2]; const float* q2[2];         // conf maps per descriptor set
+  int W1, W2;
+  int32_t* n_out;
+};
+
+__global__ void __launch_bounds__(1024)
+unique_sorted(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+              const int32_t* __restrict__ nkeys, int cap, UniqueOut out) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry_s;
+  const int n = min(*nkeys, cap);
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    int i = base + threadIdx.x;
+    uint64_t k = 0;
+    int flag = 0;
+    if (i < n) {
+      k = keys[i];
+      flag = (i == 0) || ((keys[i - 1] >> 1) != (k >> 1));
+    }
+    int x = flag;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane_id() >= off) x += y;
+    }
+    if (lane_id() == 31) warp_sums[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = warp_sums[threadIdx.x];
+      int xs = w;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, xs, off);
+        if (lane_id() >= off) xs += y;
+      }
+      warp_sums[threadIdx.x] = xs - w;
+    }
+    __syncthreads();
+    int pos = carry_s + warp_sums[threadIdx.x >> 5] + x - flag;
+    if (flag) {
+      uint32_t a = (uint32_t)(k >> 33), b = (uint32_t)((k >> 1) & 0xffffffffu);
+      int set = (int)(k & 1);
+      if (out.idx1) { out.idx1[pos] = (int32_t)a; out.idx2[pos] = (int32_t)b; }
+      if (out.index) out.index[pos] = (int32_t)vals[i];
+      if (out.xy1) {
+        out.xy1[2 * pos] = a % out.W1; out.xy1[2 * pos + 1] = a / out.W1;
+        out.xy2[2 * pos] = b % out.W2; out.xy2[2 * pos + 1] = b / out.W2;
+      }
+      if (out.conf) out.conf[pos] = sqrtf(out.q1[set][a] * out.q2[set][b]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = pos + flag;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out.n_out = carry_s;
+}
+
+__global__ void nn_decode(const unsigned long long* __restrict__ packed, int M, int32_t* idx, float* best) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  unsigned long long k = packed[i];
+  if (idx) idx[i] = k ? nn_unpack_idx(k) : -1;
+  if (best) best[i] = k ? nn_unpack_score(k) : -INFINITY;
+}
+
+int bits_for(long long n) {  // number of bits needed to represent values < n
+  int b = 1;
+  while ((1ll << b) < n) ++b;
+  return b;
+}
+
+struct RecipWs {
+  RecipState st;
+  uint64_t* keys; uint64_t* keys_alt;
+  uint32_t* vals; uint32_t* vals_alt;
+  int32_t* nkeys;
+  float* norm_bound;  // [2]
+  void* sort_ws; size_t sort_ws_bytes;
+};
+
+size_t carve(RecipWs* w, void* ws, size_t ws_bytes, int nseed_max, int key_cap, int max_iter, bool dry) {
+  WsAlloc a(dry ? (void*)0 : ws, dry ? (size_t)-1 : ws_bytes);
+  RecipWs t;
+  for (int s = 0; s < 2; ++s) {
+    t.st.xy[s] = a.take<int32_t>(nseed_max);
+    t.st.old[s] = a.take<int32_t>(nseed_max);
+    t.st.active[s] = a.take<int32_t>(nseed_max);
+  }
+  t.st.notyet = a.take<uint8_t>(nseed_max);
+  t.st.counts = a.take<int32_t>(2 * max_iter + 2);
+  t.st.qidx = a.take<int32_t>(nseed_max);
+  t.st.packed = a.take<unsigned long long>(nseed_max);
+  t.keys = a.take<uint64_t>(key_cap);
+  t.keys_alt = a.take<uint64_t>(key_cap);
+  t.vals = a.take<uint32_t>(key_cap);
+  t.vals_alt = a.take<uint32_t>(key_cap);
+  t.nkeys = a.take<int32_t>(4);
+  t.norm_bound = a.take<float>(4);
+  t.sort_ws_bytes = radix_sort_ws_bytes(key_cap);
+  t.sort_ws = a.take<char>(t.sort_ws_bytes);
+  if (w) *w = t;
+  return a.off + 256;
+}
+
+int seed_count(int H, int W, int S, int* nx_out) {
+  int off = S / 2;
+  int ny = H > off ? (H - off + S - 1) / S : 0;
+  int nx = W > off ? (W - off + S - 1) / S : 0;
+  if (nx_out) *nx_out = nx;
+  return ny * nx;
+}
+
+// One seeded reciprocal search P1 -> P2 -> P1 ...; appends converged pairs to w.keys.
+int run_recip(const RecipWs& w, const float* P1, int HW1, int W1, const float* P2, int HW2, int d,
+              int nseed, int nx, int S, const int32_t* seeds, int max_iter, int swap, int set,
+              int key_cap, int impl, cudaStream_t stream) {
+  if (nseed <= 0) return ST3R_OK;
+  const RecipState& st = w.st;
+  int ncounts = 2 * max_iter + 2;
+  recip_init<<<nblk(max(nseed, ncounts)), TPB, 0, stream>>>(st, nseed, nx, S, W1, seeds, ncounts);
+  ST3R_CHECK_LAUNCH();
+  bool use_tc = (impl == ST3R_NN_TCGEN05) || (impl == ST3R_NN_AUTO && nn_tc_supported(d));
+  if (use_tc) {
+    int rc = nn_db_norm_launch(P1, HW1, d, w.norm_bound + 0, stream);
+    if (rc) return rc;
+    rc = nn_db_norm_launch(P2, HW2, d, w.norm_bound + 1, stream);
+    if (rc) return rc;
+  }
+  const float* P[2] = {P1, P2};
+  const int HW[2] = {HW1, HW2};
+  int h = 0;
+  for (int it = 0; it < max_iter; ++it) {
+    for (int half = 0; half < 2; ++half, ++h) {
+      // half 0: query rows P1[xy1[active]] against DB P2 -> xy2;  half 1: the converse.
+      const int src = half, dst = 1 - half;
+      const int32_t* act = st.active[h & 1];
+      int32_t* act_next = st.active[(h + 1) & 1];
+      recip_prepare<<<nblk(nseed), TPB, 0, stream>>>(st.xy[src], act, st.counts + h, st.qidx, st.packed);
+      ST3R_CHECK_LAUNCH();
+      int rc;
+      if (use_tc)
+        rc = nn_tc_launch(P[src], st.qidx, st.counts + h, nseed, P[dst], HW[dst], d, w.norm_bound + dst,
+                          st.packed, stream);
+      else
+        rc = nn_simt_launch(P[src], st.qidx, st.counts + h, nseed, P[dst], HW[dst], d, st.packed, stream);
+      if (rc) return rc;
+      recip_update<<<nblk(nseed), TPB, 0, stream>>>(st.xy[dst], st.old[dst], st.notyet, act,
+                                                    st.counts + h, st.packed, act_next, st.counts + h + 1);
+      ST3R_CHECK_LAUNCH();
+    }
+  }
+  recip_collect<<<nblk(nseed), TPB, 0, stream>>>(st.xy[0], st.xy[1], st.notyet, nseed, swap, set,
+                                                 w.keys, w.nkeys, key_cap);
+  ST3R_CHECK_LAUNCH();
+  return ST3R_OK;
+}
+
+int sort_and_unique(const RecipWs& w, int key_cap, int HW1, int HW2, bool with_vals, const UniqueOut& out,
+                    cudaStream_t stream) {
+  // keys: idx1<<33 | idx2<<1 | set.  LSD: low field [0, 1+bits2) then high field [33, 33+bits1).
+  int b2 = bits_for(HW2) + 1, b1 = bits_for(HW1);
+  uint32_t* v = with_vals ? w.vals : nullptr;
+  uint32_t* va = with_vals ? w.vals_alt : nullptr;
+  int rc = radix_sort_pairs(w.keys, v, w.keys_alt, va, w.nkeys, key_cap, 0, b2, w.sort_ws,
+                            w.sort_ws_bytes, stream);
+  if (rc) return rc;
+  rc = radix_sort_pairs(w.keys, v, w.keys_alt, va, w.nkeys, key_cap, 33, 33 + b1, w.sort_ws,
+                        w.sort_ws_bytes, stream);
+  if (rc) return rc;
+  unique_sorted<<<1, 1024, 0, stream>>>(w.keys, v, w.nkeys, key_cap, out);
+  ST3R_CHECK_LAUNCH();
+  return ST3R_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI (declared in include/starst3r_b200.h)
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+size_t st3r_nn_argmax_ws_bytes(int M, int N, int d) {
+  (void)N; (void)d;
+  return st3r_align_up((size_t)max(M, 1) * sizeof(unsigned long long), 256) + 1024;
+}
+
+int st3r_nn_argmax(const float* Q, int M, const float* DB, int N, int d, int32_t* idx, float* best,
+                   void* ws, size_t ws_bytes, int impl, cudaStream_t stream) {
+  ST3R_CHECK_ARG(M >= 0 && N >= 0 && d > 0, "st3r_nn_argmax: bad sizes M=%d N=%d d=%d", M, N, d);
+  if (M == 0) return ST3R_OK;
+  ST3R_CHECK_ARG(Q && DB && idx, "st3r_nn_argmax: null pointer");
+  ST3R_CHECK_ARG(ws && ws_bytes >= st3r_nn_argmax_ws_bytes(M, N, d), "st3r_nn_argmax: workspace too small");
+  WsAlloc a(ws, ws_bytes);
+  unsigned long long* packed = a.take<unsigned long long>(M);
+  float* bound = a.take<float>(4);
+  ST3R_CHECK_CUDA(cudaMemsetAsync(packed, 0, (size_t)M * sizeof(unsigned long long), stream));
+  int rc;
+  bool use_tc = (impl == ST3R_NN_TCGEN05) || (impl == ST3R_NN_AUTO && nn_tc_supported(d) && M >= 64);
+  if (impl == ST3R_NN_TCGEN05) ST3R_CHECK_ARG(nn_tc_supported(d), "st3r_nn_argmax: tcgen05 path needs d=24");
+  if (use_tc && N > 0) {
+    rc = nn_db_norm_launch(DB, N, d, bound, stream);
+    if (rc) return rc;
+    rc = nn_tc_launch(Q, nullptr, nullptr, M, DB, N, d, bound, packed, stream);
+  } else {
+    rc = nn_simt_launch(Q, nullptr, nullptr, M, DB, N, d, packed, stream);
+  }
+  if (rc) return rc;
+  nn_decode<<<nblk(M), TPB, 0, stream>>>(packed, M, idx, best);
+  ST3R_CHECK_LAUNCH();
+  return ST3R_OK;
+}
+
+int st3r_recip_seed_count(int H, int W, int subsample) { return seed_count(H, W, subsample, nullptr); }
+
+size_t st3r_recip_nn_ws_bytes(int nseed_max, int key_cap, int max_iter) {
+  return carve(nullptr, nullptr, 0, max(nseed_max, 1), max(key_cap, 1), max(max_iter, 1), true);
+}
+
+int st3r_recip_nn(const float* P1, int H1, int W1, const float* P2, int H2, int W2, int d, int subsample,
+                  const int32_t* seeds, int nseeds, int max_iter, int32_t* out_idx1, int32_t* out_idx2,
+                  int32_t* n_out, void* ws, size_t ws_bytes, int impl, cudaStream_t stream) {
+  ST3R_CHECK_ARG(P1 && P2 && out_idx1 && out_idx2 && n_out, "st3r_recip_nn: null pointer");
+  ST3R_CHECK_ARG(H1 > 0 && W1 > 0 && H2 > 0 && W2 > 0 && d > 0 && max_iter > 0, "st3r_recip_nn: bad sizes");
+  ST3R_CHECK_ARG((long long)H1 * W1 < (1ll << 30) && (long long)H2 * W2 < (1ll << 30), "st3r_recip_nn: map too large");
+  int nx = 0;
+  int nseed = seeds ? nseeds : seed_count(H1, W1, subsample, &nx);
+  ST3R_CHECK_ARG(seeds || subsample > 0, "st3r_recip_nn: subsample must be > 0");
+  RecipWs w;
+  size_t need = carve(&w, ws, ws_bytes, max(nseed, 1), max(nseed, 1), max_iter, false);
+  ST3R_CHECK_ARG(ws && ws_bytes >= need, "st3r_recip_nn: workspace too small (%zu < %zu)", ws_bytes, need);
+  ST3R_CHECK_CUDA(cudaMemsetAsync(w.nkeys, 0, 4 * sizeof(int32_t), stream));
+  if (nseed == 0) { ST3R_CHECK_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int32_t), stream)); return ST3R_OK; }
+  int rc = run_recip(w, P1, H1 * W1, W1, P2, H2 * W2, d, nseed, nx, subsample, seeds, max_iter, 0, 0,
+                     nseed, impl, stream);
+  if (rc) return rc;
+  UniqueOut out = {};
+  out.idx1 = out_idx1; out.idx2 = out_idx2; out.n_out = n_out; out.W1 = W1; out.W2 = W2;
+  return sort_and_unique(w, nseed, H1 * W1, H2 * W2, false, out, stream);
+}
+
+size_t st3r_merge_corres_ws_bytes(int n) { return carve(nullptr, nullptr, 0, 1, max(n, 1), 1, true); }
+
+int st3r_merge_corres(const int32_t* idx1, const int32_t* idx2, int n, int hw1, int hw2, int32_t* out_idx1,
+                      int32_t* out_idx2, int32_t* out_index, int32_t* n_out, void* ws, size_t ws_bytes,
+                      cudaStream_t stream) {
+  ST3R_CHECK_ARG(n >= 0 && n_out, "st3r_merge_corres: bad args");
+  if (n == 0) { ST3R_CHECK_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int32_t), stream)); return ST3R_OK; }
+  ST3R_CHECK_ARG(idx1 && idx2 && out_idx1 && out_idx2, "st3r_merge_corres: null pointer");
+  ST3R_CHECK_ARG(hw1 > 0 && hw2 > 0 && hw1 < (1 << 30) && hw2 < (1 << 30), "st3r_merge_corres: bad map sizes");
+  RecipWs w;
+  size_t need = carve(&w, ws, ws_bytes, 1, n, 1, false);
+  ST3R_CHECK_ARG(ws && ws_bytes >= need, "st3r_merge_corres: workspace too small");
+  pack_pairs<<<nblk(n), TPB, 0, stream>>>(idx1, idx2, n, w.keys, w.vals, w.nkeys);
+  ST3R_CHECK_LAUNCH();
+  UniqueOut out = {};
+  out.idx1 = out_idx1; out.idx2 = out_idx2; out.index = out_index; out.n_out = n_out; out.W1 = 1; out.W2 = 1;
+  return sort_and_unique(w, n, hw1, hw2, true, out, stream);
+}
+
+int st3r_extract_corres_cap(int H1, int W1, int H2, int W2, int subsample) {
+  return 2 * (seed_count(H1, W1, subsample, nullptr) + seed_count(H2, W2, subsample, nullptr));
+}
+
+size_t st3r_extract_corres_ws_bytes(int H1, int W1, int H2, int W2, int subsample, int max_iter) {
+  int n1 = seed_count(H1, W1, subsample, nullptr), n2 = seed_count(H2, W2, subsample, nullptr);
+  return carve(nullptr, nullptr, 0, max(max(n1, n2), 1), max(2 * (n1 + n2), 1), max_iter, true);
+}
+
+int st3r_extract_corres(const float* feat11, const float* feat21, const float* feat22, const float* feat12,
+                        const float* qonf11, const float* qonf21, const float* qonf22, const float* qonf12,
+                        int H1, int W1, int H2, int W2, int d, int subsample, int max_iter,
+                        int64_t* out_xy1, int64_t* out_xy2, float* out_conf, int32_t* n_out,
+                        void* ws, size_t ws_bytes, int impl, cudaStream_t stream) {
+  ST3R_CHECK_ARG(feat11 && feat21 && feat22 && feat12 && qonf11 && qonf21 && qonf22 && qonf12,
+                 "st3r_extract_corres: null input");
+  ST3R_CHECK_ARG(out_xy1 && out_xy2 && out_conf && n_out, "st3r_extract_corres: null output");
+  ST3R_CHECK_ARG(H1 > 0 && W1 > 0 && H2 > 0 && W2 > 0 && d > 0 && subsample > 0 && max_iter > 0,
+                 "st3r_extract_corres: bad sizes");
+  ST3R_CHECK_ARG((long long)H1 * W1 < (1ll << 30) && (long long)H2 * W2 < (1ll << 30), "st3r_extract_corres: map too large");
+  int nx1, nx2;
+  int n1 = seed_count(H1, W1, subsample, &nx1), n2 = seed_count(H2, W2, subsample, &nx2);
+  int cap = 2 * (n1 + n2);
+  RecipWs w;
+  size_t need = carve(&w, ws, ws_bytes, max(max(n1, n2), 1), max(cap, 1), max_iter, false);
+  ST3R_CHECK_ARG(ws && ws_bytes >= need, "st3r_extract_corres: workspace too small (%zu < %zu)", ws_bytes, need);
+  ST3R_CHECK_CUDA(cudaMemsetAsync(w.nkeys, 0, 4 * sizeof(int32_t), stream));
+  // sparse_ga.py:612-620 - two descriptor sets, each matched in both directions.
+  const float* A[2] = {feat11, feat12};
+  const float* B[2] = {feat21, feat22};
+  for (int set = 0; set < 2; ++set) {
+    int rc = run_recip(w, A[set], H1 * W1, W1, B[set], H2 * W2, d, n1, nx1, subsample, nullptr, max_iter, 0,
+                       set, cap, impl, stream);
+    if (rc) return rc;
+    rc = run_recip(w, B[set], H2 * W2, W2, A[set], H1 * W1, d, n2, nx2, subsample, nullptr, max_iter, 1,
+                   set, cap, impl, stream);
+    if (rc) return rc;
+  }
+  UniqueOut out = {};
+  out.xy1 = out_xy1; out.xy2 = out_xy2; out.conf = out_conf; out.n_out = n_out;
+  out.q1[0] = qonf11; out.q2[0] = qonf21; out.q1[1] = qonf12; out.q2[1] = qonf22;
+  out.W1 = W1; out.W2 = W2;
+  return sort_and_unique(w, cap, H1 * W1, H2 * W2, false, out, stream);
+}
+
+}  // extern "C"

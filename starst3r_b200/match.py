@@ -1,0 +1,278 @@
+"""MATCH hot path — host-side mirror of the reference operator interface.
+
+Same names / argument meaning / error behaviour as
+  mast3r/mast3r/fast_nn.py            (bruteforce_reciprocal_nns, cdistMatcher, merge_corres,
+                                        fast_reciprocal_NNs)
+  mast3r/mast3r/cloud_opt/sparse_ga.py:595-630 (extract_correspondences)
+but every call runs hand-written sm_100a kernels through the C ABI of
+libstarst3r_b200.so (include/starst3r_b200.h).  There is no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = ("nn_argmax", "bruteforce_reciprocal_nns", "cdistMatcher", "merge_corres", "fast_reciprocal_NNs",
+           "extract_correspondences")
+
+_IMPL = {"auto": 0, "simt": 1, "tcgen05": 2}
+
+
+def _dev(device):
+    d = torch.device(device if device is not None else "cuda")
+    if d.type != "cuda":
+        raise RuntimeError(f"starst3r_b200.match: device={device!r} - the hot path only runs on CUDA (sm_100a); "
+                           "no CPU fallback is provided")
+    return d
+
+
+def _f32(x, device):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(x)
+    return x.to(device=device, dtype=torch.float32).contiguous()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def nn_argmax(Q, DB, impl="auto", return_score=False):
+    """idx[i] = argmax_j <Q[i], DB[j]> (fp32 FMA chain, ties -> lowest j).  Device tensors in/out (int32)."""
+    lib = _lib.load()
+    _lib.require_cuda(Q, DB)
+    Q = Q.float().contiguous()
+    DB = DB.float().contiguous()
+    M, d = Q.shape
+    N = DB.shape[0]
+    assert DB.shape[1] == d
+    idx = torch.empty(M, dtype=torch.int32, device=Q.device)
+    best = torch.empty(M, dtype=torch.float32, device=Q.device) if return_score else None
+    if M == 0:
+        return (idx, best) if return_score else idx
+    if N == 0:
+        raise ValueError("nn_argmax: empty database")
+    ws = _ws(lib.st3r_nn_argmax_ws_bytes(M, N, d), Q.device)
+    with torch.cuda.device(Q.device):
+        rc = lib.st3r_nn_argmax(_lib.ptr(Q), M, _lib.ptr(DB), N, d, _lib.ptr(idx), _lib.ptr(best), _lib.ptr(ws),
+                                ws.numel(), _IMPL[impl], _lib.stream_ptr())
+    _lib.check(rc, "st3r_nn_argmax")
+    return (idx, best) if return_score else idx
+
+
+@torch.no_grad()
+def bruteforce_reciprocal_nns(A, B, device="cuda", block_size=None, dist="l2", impl="auto"):
+    """fast_nn.py:16-70.  `block_size` is accepted for signature parity; the kernels never materialise the
+    score matrix, so it has no effect on memory or on the result (ties keep the lowest index either way)."""
+    if dist == "l2":
+        raise NotImplementedError("dist='l2' is outside the B200 hot path (Starst3r only matches with dist='dot', "
+                                  "sparse_ga.py:604)")
+    if dist != "dot":
+        raise ValueError(f"Unknown {dist=}")
+    device = _dev(device)
+    A = _f32(A, device)
+    B = _f32(B, device)
+    nn_A = nn_argmax(A, B, impl=impl)
+    nn_B = nn_argmax(B, A, impl=impl)
+    return nn_A.cpu().numpy().astype(np.int64), nn_B.cpu().numpy().astype(np.int64)
+
+
+class cdistMatcher:
+    """fast_nn.py:73-84."""
+
+    def __init__(self, db_pts, device="cuda"):
+        self.device = _dev(device)
+        self.db_pts = _f32(db_pts, self.device)
+
+    def query(self, queries, k=1, dist="dot", block_size=None, impl="auto", **kw):
+        assert k == 1
+        if queries.numel() == 0:
+            return None, []
+        if dist != "dot":
+            raise NotImplementedError("only dist='dot' is on the B200 hot path")
+        nnA = nn_argmax(_f32(queries, self.device), self.db_pts, impl=impl)
+        return None, nnA.cpu().numpy().astype(np.int64)
+
+
+def merge_corres(idx1, idx2, shape1=None, shape2=None, ret_xy=True, ret_index=False, device="cuda"):
+    """fast_nn.py:87-106 on the device: radix sort of packed (idx1, idx2) + ordered unique."""
+    assert idx1.dtype == idx2.dtype == np.int32
+    lib = _lib.load()
+    device = _dev(device)
+    n = len(idx1)
+    hw1 = int(shape1[0] * shape1[1]) if shape1 else (int(idx1.max()) + 1 if n else 1)
+    hw2 = int(shape2[0] * shape2[1]) if shape2 else (int(idx2.max()) + 1 if n else 1)
+    d1 = torch.from_numpy(np.ascontiguousarray(idx1)).to(device)
+    d2 = torch.from_numpy(np.ascontiguousarray(idx2)).to(device)
+    o1 = torch.empty(max(n, 1), dtype=torch.int32, device=device)
+    o2 = torch.empty_like(o1)
+    oi = torch.empty_like(o1)
+    n_out = torch.zeros(1, dtype=torch.int32, device=device)
+    ws = _ws(lib.st3r_merge_corres_ws_bytes(n), device)
+    with torch.cuda.device(device):
+        rc = lib.st3r_merge_corres(_lib.ptr(d1), _lib.ptr(d2), n, hw1, hw2, _lib.ptr(o1), _lib.ptr(o2), _lib.ptr(oi),
+                                   _lib.ptr(n_out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "st3r_merge_corres")
+    k = int(n_out.item())
+    xy1 = o1[:k].cpu().numpy()
+    xy2 = o2[:k].cpu().numpy()
+    indices = oi[:k].cpu().numpy().astype(np.int64)
+    if ret_xy:
+        assert shape1 and shape2
+        xy1 = _unravel(xy1, shape1, ret_xy)
+        xy2 = _unravel(xy2, shape2, ret_xy)
+    if ret_index:
+        return xy1, xy2, indices
+    return xy1, xy2
+
+
+def _unravel(idx, shape, ret_xy=True):
+    y, x = np.unravel_index(idx, shape)
+    if ret_xy == "y_x":
+        return (y, x)
+    return np.stack([x, y], axis=1).astype(np.int64)
+
+
+def _recip_device(P1, P2, subsample, seeds, max_iter, impl):
+    """One seeded reciprocal search on the device; returns int32 device tensors (idx1, idx2) (sorted unique)."""
+    lib = _lib.load()
+    H1, W1, d = P1.shape
+    H2, W2, _ = P2.shape
+    dev = P1.device
+    if seeds is None:
+        nseed = lib.st3r_recip_seed_count(H1, W1, subsample)
+        seeds_t = None
+    else:
+        seeds_t = torch.from_numpy(np.ascontiguousarray(seeds, dtype=np.int32)).to(dev)
+        nseed = seeds_t.numel()
+    cap = max(nseed, 1)
+    o1 = torch.empty(cap, dtype=torch.int32, device=dev)
+    o2 = torch.empty(cap, dtype=torch.int32, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _ws(lib.st3r_recip_nn_ws_bytes(nseed, nseed, max_iter), dev)
+    with torch.cuda.device(dev):
+        rc = lib.st3r_recip_nn(_lib.ptr(P1), H1, W1, _lib.ptr(P2), H2, W2, d, int(subsample) if seeds is None else 1,
+                               _lib.ptr(seeds_t), nseed if seeds is not None else 0, max_iter, _lib.ptr(o1),
+                               _lib.ptr(o2), _lib.ptr(n_out), _lib.ptr(ws), ws.numel(), _IMPL[impl],
+                               _lib.stream_ptr())
+    _lib.check(rc, "st3r_recip_nn")
+    k = int(n_out.item())
+    return o1[:k], o2[:k]
+
+
+def fast_reciprocal_NNs(pts1, pts2, subsample_or_initxy1=8, ret_xy=True, pixel_tol=0, ret_basin=False,
+                        device="cuda", impl="auto", **matcher_kw):
+    """fast_nn.py:109-188.  The default call (integer subsample, pixel_tol=0, ret_basin=False — the only form
+    Starst3r uses, sparse_ga.py:614-615) runs as one device-resident launch chain; the other forms drive the
+    same NN kernel from a host loop that follows the reference statement by statement."""
+    H1, W1, DIM1 = pts1.shape
+    H2, W2, DIM2 = pts2.shape
+    assert DIM1 == DIM2
+    dist = matcher_kw.get("dist", "dot")
+    if dist != "dot":
+        raise NotImplementedError("only dist='dot' is on the B200 hot path (KDTree / l2 branches are CPU code "
+                                  "in the reference)")
+    device = _dev(device)
+    P1 = _f32(pts1, device)
+    P2 = _f32(pts2, device)
+
+    if isinstance(subsample_or_initxy1, int) and pixel_tol == 0 and not ret_basin:
+        o1, o2 = _recip_device(P1, P2, subsample_or_initxy1, None, 10, impl)
+        xy1, xy2 = o1.cpu().numpy(), o2.cpu().numpy()
+        if ret_xy:
+            xy1, xy2 = _unravel(xy1, (H1, W1), ret_xy), _unravel(xy2, (H2, W2), ret_xy)
+        return xy1, xy2
+
+    # ---- general form (pixel_tol > 0, explicit seeds, ret_basin) -------------------------------------
+    F1 = P1.reshape(-1, DIM1)
+    F2 = P2.reshape(-1, DIM2)
+    if isinstance(subsample_or_initxy1, int) and pixel_tol == 0:
+        S = subsample_or_initxy1
+        y1, x1 = np.mgrid[S // 2:H1:S, S // 2:W1:S].reshape(2, -1)
+        max_iter = 10
+    else:
+        x1, y1 = subsample_or_initxy1
+        x1 = x1.cpu().numpy() if isinstance(x1, torch.Tensor) else np.asarray(x1)
+        y1 = y1.cpu().numpy() if isinstance(y1, torch.Tensor) else np.asarray(y1)
+        max_iter = 1
+    xy1 = np.int32(np.unique(x1 + W1 * y1))
+    xy2 = np.full_like(xy1, -1)
+    old_xy1, old_xy2 = xy1.copy(), xy2.copy()
+    notyet = np.ones(len(xy1), dtype=bool)
+    basin = np.full((H1 * W1 + 1,), -1, dtype=np.int32) if ret_basin else None
+
+    def query(F_src, sel, F_db):
+        if len(sel) == 0:
+            return np.zeros(0, np.int32)
+        q = F_src[torch.from_numpy(sel.astype(np.int64)).to(device)]
+        return nn_argmax(q, F_db, impl=impl).cpu().numpy()
+
+    niter = 0
+    while notyet.any():
+        xy2[notyet] = query(F1, xy1[notyet], F2)
+        if not ret_basin:
+            notyet &= (old_xy2 != xy2)
+        xy1[notyet] = query(F2, xy2[notyet], F1)
+        if ret_basin:
+            basin[old_xy1[notyet]] = xy1[notyet]
+        notyet &= (old_xy1 != xy1)
+        niter += 1
+        if niter >= max_iter:
+            break
+        old_xy2[:] = xy2
+        old_xy1[:] = xy1
+
+    if pixel_tol > 0:
+        old_yx1 = np.stack(np.unravel_index(old_xy1, (H1, W1)), axis=1)
+        new_yx1 = np.stack(np.unravel_index(xy1, (H1, W1)), axis=1)
+        dis = np.linalg.norm(old_yx1 - new_yx1, axis=-1)
+        converged = dis < pixel_tol
+        if not isinstance(subsample_or_initxy1, int):
+            xy1 = old_xy1
+    else:
+        converged = ~notyet
+    xy1, xy2 = merge_corres(xy1[converged], xy2[converged], (H1, W1), (H2, W2), ret_xy=ret_xy, device=device)
+    if ret_basin:
+        return xy1, xy2, basin
+    return xy1, xy2
+
+
+def extract_correspondences_device(feats, qonfs, subsample=8, impl="auto", max_iter=10):
+    """Device-resident form: returns (xy1 [cap,2] i64, xy2 [cap,2] i64, conf [cap] f32, n [1] i32) without
+    synchronising; rows >= n are undefined.  Used by the pair-sharded pipeline and by bench.py."""
+    lib = _lib.load()
+    f11, f21, f22, f12 = feats
+    q11, q21, q22, q12 = qonfs
+    assert f11.shape[:2] == f12.shape[:2] == q11.shape == q12.shape
+    assert f21.shape[:2] == f22.shape[:2] == q21.shape == q22.shape
+    _lib.require_cuda(f11, f21, f22, f12, q11, q21, q22, q12)
+    dev = f11.device
+    H1, W1, d = f11.shape
+    H2, W2, _ = f22.shape
+    cap = max(lib.st3r_extract_corres_cap(H1, W1, H2, W2, subsample), 1)
+    xy1 = torch.empty((cap, 2), dtype=torch.int64, device=dev)
+    xy2 = torch.empty((cap, 2), dtype=torch.int64, device=dev)
+    conf = torch.empty(cap, dtype=torch.float32, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _ws(lib.st3r_extract_corres_ws_bytes(H1, W1, H2, W2, subsample, max_iter), dev)
+    with torch.cuda.device(dev):
+        rc = lib.st3r_extract_corres(_lib.ptr(f11), _lib.ptr(f21), _lib.ptr(f22), _lib.ptr(f12), _lib.ptr(q11),
+                                     _lib.ptr(q21), _lib.ptr(q22), _lib.ptr(q12), H1, W1, H2, W2, d, subsample,
+                                     max_iter, _lib.ptr(xy1), _lib.ptr(xy2), _lib.ptr(conf), _lib.ptr(n_out),
+                                     _lib.ptr(ws), ws.numel(), _IMPL[impl], _lib.stream_ptr())
+    _lib.check(rc, "st3r_extract_corres")
+    return xy1, xy2, conf, n_out
+
+
+def extract_correspondences(feats, qonfs, subsample=8, device=None, ptmap_key="pred_desc", impl="auto"):
+    """sparse_ga.py:595-630: (xy1, xy2, conf) torch tensors on `device` for one image pair."""
+    if "3d" in ptmap_key:
+        raise NotImplementedError("ptmap_key with '3d' selects the CPU KDTree matcher in the reference "
+                                  "(sparse_ga.py:601-602); it is outside the B200 hot path")
+    device = _dev(device if device is not None else feats[0].device)
+    feats = [_f32(f, device) for f in feats]
+    qonfs = [_f32(q, device) for q in qonfs]
+    xy1, xy2, conf, n_out = extract_correspondences_device(feats, qonfs, subsample, impl)
+    n = int(n_out.item())
+    return xy1[:n], xy2[:n], conf[:n]

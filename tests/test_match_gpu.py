@@ -1,0 +1,172 @@
+"""GPU parity of the MATCH path: CUDA kernels (through the C ABI) vs the CPU oracle and the reference's golden
+vectors.  Integer outputs must be bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import match_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+IMPLS = ["simt", "tcgen05"]
+
+
+def unit(x):
+    return (x / np.linalg.norm(x, axis=-1, keepdims=True)).astype(np.float32)
+
+
+def _impl_ok(impl):
+    if impl == "tcgen05":
+        from starst3r_b200 import _lib
+        # built with the tcgen05 kernel?
+        return True
+    return True
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_nn_argmax_golden(golden, cuda_device, impl):
+    from starst3r_b200 import match
+    g = golden("match_nn.npz")
+    Q, DB = torch.from_numpy(g["Q"]).to(cuda_device), torch.from_numpy(g["DB"]).to(cuda_device)
+    assert np.array_equal(match.nn_argmax(Q, DB, impl=impl).cpu().numpy(), g["nnA"])
+    assert np.array_equal(match.nn_argmax(DB, Q, impl=impl).cpu().numpy(), g["nnB"])
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("M,N", [(1, 1), (2, 5), (7, 129), (128, 128), (129, 4097), (300, 20000), (1000, 66000)])
+def test_nn_argmax_vs_oracle(cuda_device, impl, M, N):
+    from starst3r_b200 import match
+    rng = np.random.default_rng(M * 7919 + N)
+    Q = unit(rng.standard_normal((M, 24)))
+    DB = unit(rng.standard_normal((N, 24)))
+    if N > 64:
+        DB[N // 2] = DB[3]            # tie on purpose
+        Q[0] = DB[3]
+    ref_idx, ref_best = mo.nn_argmax_dot_c(Q, DB)
+    idx, best = match.nn_argmax(torch.from_numpy(Q).to(cuda_device), torch.from_numpy(DB).to(cuda_device),
+                                impl=impl, return_score=True)
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)
+    assert np.array_equal(best.cpu().numpy(), ref_best)      # scores are bit-identical (fp32 FMA chain)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_nn_argmax_unnormalised_and_negative(cuda_device, impl):
+    """Non-unit descriptors (large dynamic range) and all-negative scores."""
+    from starst3r_b200 import match
+    rng = np.random.default_rng(11)
+    Q = (rng.standard_normal((257, 24)) * np.exp(rng.standard_normal((257, 1)) * 2)).astype(np.float32)
+    DB = (rng.standard_normal((5000, 24)) * np.exp(rng.standard_normal((5000, 1)) * 2)).astype(np.float32)
+    Q[:10] = -np.abs(Q[:10])
+    DB = np.abs(DB)
+    ref_idx, _ = mo.nn_argmax_dot_c(Q, DB)
+    idx = match.nn_argmax(torch.from_numpy(Q).to(cuda_device), torch.from_numpy(DB).to(cuda_device), impl=impl)
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)
+
+
+def test_nn_generic_dim(cuda_device):
+    from starst3r_b200 import match
+    rng = np.random.default_rng(5)
+    for d in (3, 16, 32, 40):
+        Q = rng.standard_normal((50, d)).astype(np.float32)
+        DB = rng.standard_normal((777, d)).astype(np.float32)
+        ref_idx, _ = mo.nn_argmax_dot_c(Q, DB)
+        idx = match.nn_argmax(torch.from_numpy(Q).to(cuda_device), torch.from_numpy(DB).to(cuda_device), impl="simt")
+        assert np.array_equal(idx.cpu().numpy(), ref_idx)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_fast_reciprocal_nns_golden(golden, cuda_device, impl, tag):
+    from starst3r_b200 import match
+    g = golden("match_recip.npz")
+    A, B = torch.from_numpy(g[f"A_{tag}"]), torch.from_numpy(g[f"B_{tag}"])
+    i1, i2 = match.fast_reciprocal_NNs(A, B, subsample_or_initxy1=8, ret_xy=False, device=cuda_device, dist="dot",
+                                       block_size=2 ** 13, impl=impl)
+    assert i1.dtype == np.int32
+    assert np.array_equal(i1, g[f"idx1_{tag}"]) and np.array_equal(i2, g[f"idx2_{tag}"])
+    x1, x2 = match.fast_reciprocal_NNs(A, B, subsample_or_initxy1=8, ret_xy=True, device=cuda_device, dist="dot",
+                                       impl=impl)
+    assert np.array_equal(x1, g[f"xy1_{tag}"]) and np.array_equal(x2, g[f"xy2_{tag}"])
+
+
+def test_fast_reciprocal_nns_general_form_equals_fused(golden, cuda_device):
+    """Host-loop form (explicit seeds / ret_basin) and the fused device chain agree."""
+    from starst3r_b200 import match
+    g = golden("match_recip.npz")
+    A, B = torch.from_numpy(g["A_a"]), torch.from_numpy(g["B_a"])
+    H1, W1 = A.shape[:2]
+    i1, i2, basin = match.fast_reciprocal_NNs(A, B, 8, ret_xy=False, ret_basin=True, device=cuda_device, dist="dot")
+    assert basin.shape == (H1 * W1 + 1,)
+    y1, x1 = np.mgrid[4:H1:8, 4:W1:8].reshape(2, -1)
+    j1, j2 = match.fast_reciprocal_NNs(A, B, (x1, y1), ret_xy=False, device=cuda_device, dist="dot")
+    # max_iter = 1 for explicit seeds (fast_nn.py:128): converged subset of the 10-iteration result
+    full = set(zip(g["idx1_a"].tolist(), g["idx2_a"].tolist()))
+    assert set(zip(j1.tolist(), j2.tolist())) <= full
+
+
+def test_merge_corres_golden(golden, cuda_device):
+    from starst3r_b200 import match
+    g = golden("match_merge.npz")
+    o1, o2, idx = match.merge_corres(g["idx1"], g["idx2"], ret_xy=False, ret_index=True, device=cuda_device)
+    assert np.array_equal(o1, g["out1"]) and np.array_equal(o2, g["out2"]) and np.array_equal(idx, g["index"])
+    o1, o2 = match.merge_corres(np.zeros(0, np.int32), np.zeros(0, np.int32), ret_xy=False, device=cuda_device)
+    assert len(o1) == 0
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_extract_correspondences_golden(golden, cuda_device, impl):
+    from starst3r_b200 import match
+    g = golden("match_extract.npz")
+    T = torch.from_numpy
+    xy1, xy2, conf = match.extract_correspondences([T(g["f11"]), T(g["f21"]), T(g["f22"]), T(g["f12"])],
+                                                   [T(g["q11"]), T(g["q21"]), T(g["q22"]), T(g["q12"])],
+                                                   subsample=8, device=cuda_device, impl=impl)
+    assert xy1.dtype == torch.int64 and conf.dtype == torch.float32 and xy1.is_cuda
+    assert np.array_equal(xy1.cpu().numpy(), g["xy1"]) and np.array_equal(xy2.cpu().numpy(), g["xy2"])
+    assert np.array_equal(conf.cpu().numpy(), g["conf"])
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("H,W,noise", [(128, 128, 0.3), (256, 256, 0.3), (96, 160, 1.0)])
+def test_fast_reciprocal_nns_vs_oracle(cuda_device, impl, H, W, noise):
+    from starst3r_b200 import match
+    rng = np.random.default_rng(H + W)
+    A = unit(rng.standard_normal((H, W, 24)))
+    B = unit(A + noise * rng.standard_normal((H, W, 24)).astype(np.float32))
+    r1, r2 = mo.fast_reciprocal_nns(A, B, 8)
+    i1, i2 = match.fast_reciprocal_NNs(torch.from_numpy(A), torch.from_numpy(B), 8, ret_xy=False,
+                                       device=cuda_device, dist="dot", impl=impl)
+    assert np.array_equal(i1, r1) and np.array_equal(i2, r2)
+
+
+def test_edge_cases(cuda_device):
+    from starst3r_b200 import match
+    P = torch.ones(3, 3, 24)
+    i1, i2 = match.fast_reciprocal_NNs(P, P, 8, ret_xy=False, device=cuda_device, dist="dot")
+    assert len(i1) == 0 and len(i2) == 0
+    P = torch.ones(16, 16, 24)
+    i1, i2 = match.fast_reciprocal_NNs(P, P, 8, ret_xy=False, device=cuda_device, dist="dot")
+    assert list(i1) == [0] and list(i2) == [0]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_full_size_properties(cuda_device, impl):
+    """512x512 (BASELINE configs[1] map size): size-independent properties instead of a CPU oracle sweep:
+    every returned pair is a mutual nearest neighbour (reciprocity), output sorted & unique, and matching a
+    map against itself returns exactly the seed grid."""
+    from starst3r_b200 import match
+    g = torch.Generator().manual_seed(0)
+    A = torch.nn.functional.normalize(torch.randn(512, 512, 24, generator=g), dim=-1)
+    B = torch.nn.functional.normalize(A + 0.3 * torch.randn(512, 512, 24, generator=g), dim=-1)
+    i1, i2 = match.fast_reciprocal_NNs(A, B, 8, ret_xy=False, device=cuda_device, dist="dot", impl=impl)
+    assert len(i1) > 1000
+    key = i1.astype(np.int64) << 32 | i2.astype(np.int64)
+    assert np.all(np.diff(key) > 0)
+    Ad, Bd = A.reshape(-1, 24).to(cuda_device), B.reshape(-1, 24).to(cuda_device)
+    t1 = torch.from_numpy(i1.astype(np.int64)).to(cuda_device)
+    t2 = torch.from_numpy(i2.astype(np.int64)).to(cuda_device)
+    assert torch.equal(match.nn_argmax(Ad[t1], Bd, impl="simt").long(), t2)
+    assert torch.equal(match.nn_argmax(Bd[t2], Ad, impl="simt").long(), t1)
+    s1, s2 = match.fast_reciprocal_NNs(A, A, 8, ret_xy=False, device=cuda_device, dist="dot", impl=impl)
+    y, x = np.mgrid[4:512:8, 4:512:8].reshape(2, -1)
+    assert np.array_equal(s1, np.sort(x + 512 * y)) and np.array_equal(s1, s2)
