@@ -1,10 +1,441 @@
-// placeholder until the tcgen05 kernel lands
+// Dot-product nearest neighbour on the 5th-gen tensor cores (tcgen05, sm_100a).
+//
+// Replaces the `A @ B.T` + torch.max of mast3r/mast3r/fast_nn.py:30-67.  The H*W x H*W x 24
+// descriptor correlation is a dense contraction, so it runs as kind::tf32 UMMA:
+//   TMA (cp.async.bulk.tensor, 128B swizzle, OOB zero-fill pads K 24 -> 32) -> smem ring
+//   -> tcgen05.mma (M=128, N=128, K=8 x3) -> fp32 accumulators in TMEM (2 stages)
+//   -> tcgen05.ld -> fused arg-max epilogue.  The score matrix never reaches HBM.
+//
+// Exactness.  The reference scores in true fp32 (sequential FMA chain).  TF32 drops 13
+// mantissa bits of each operand, so |approx - exact| <= eps = 2^-9 * |q| * max_j |db_j|.
+// The epilogue therefore keeps, per query row, every column whose approximate score is
+// within 2*eps of the running approximate maximum (a handful), and re-scores those
+// candidates with the exact fp32 FMA chain at the end.  The true arg-max (and all its
+// exact ties) is always among the candidates, so the result is bit-identical to the SIMT
+// kernel / the reference, ties -> lowest index.  Rows whose candidate list overflows
+// (degenerate inputs, e.g. constant descriptor maps) are re-done by an exact warp-per-row
+// kernel.
+#include <cuda.h>
 #include "common.cuh"
 #include "nn.cuh"
-bool nn_tc_supported(int d) { (void)d; return false; }
-int nn_db_norm_launch(const float*, int, int, float*, cudaStream_t) { return ST3R_OK; }
-int nn_tc_launch(const float*, const int32_t*, const int32_t*, int, const float*, int, int, const float*,
-                 unsigned long long*, cudaStream_t) {
-  st3r_set_error("tcgen05 NN kernel not built");
-  return ST3R_ERR_UNSUPPORTED;
+
+namespace {
+
+constexpr int BM = 128;            // query rows per CTA (UMMA M)
+constexpr int BN = 128;            // DB rows per MMA tile (UMMA N)
+constexpr int DK = 24;             // descriptor dim
+constexpr int ROWB = 128;          // smem bytes per operand row (32 floats, 24 real + 8 zero)
+constexpr int STAGES = 4;          // smem ring depth for DB tiles
+constexpr int ACC_STAGES = 2;      // TMEM accumulator stages
+constexpr int CAND_CAP = 12;       // candidates kept per row
+constexpr int NUM_THREADS = 192;   // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int TMEM_COLS = ACC_STAGES * BN;  // 256
+constexpr int MAX_TILES_PER_CHUNK = 64;
+constexpr float DELTA_COEF = 4.2e-3f;  // > 2 * 2^-9 (+ fp32 accumulation slack)
+
+constexpr int SMEM_A = 0;
+constexpr int SMEM_B = SMEM_A + BM * ROWB;
+constexpr int SMEM_CAND = SMEM_B + STAGES * BN * ROWB;
+constexpr int SMEM_BAR = SMEM_CAND + BM * CAND_CAP * 8;
+constexpr int SMEM_TOTAL = SMEM_BAR + 256;
+constexpr int SMEM_DYN = SMEM_TOTAL + 1024;  // slack for 1024-byte alignment
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a CUDA error (trap) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// K-major, 128-byte swizzle, dense 8-row groups (SBO = 1024 B), sm_100 descriptor version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fffu);  // start address
+  d |= (uint64_t)0 << 16;                   // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024u >> 4) << 32;        // stride byte offset
+  d |= (uint64_t)1 << 46;                   // version = 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                   // layout type SWIZZLE_128B
+  return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128.
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ float exact_score(const float* __restrict__ q, const float* __restrict__ b) {
+  float s = 0.f;
+#pragma unroll
+  for (int k4 = 0; k4 < DK / 4; ++k4) {
+    float4 qa = reinterpret_cast<const float4*>(q)[k4];
+    float4 bb = reinterpret_cast<const float4*>(b)[k4];
+    s = fmaf(qa.x, bb.x, s); s = fmaf(qa.y, bb.y, s); s = fmaf(qa.z, bb.z, s); s = fmaf(qa.w, bb.w, s);
+  }
+  return s;
+}
+
+struct Cand { int j; float s; };
+
+// Keeps only candidates that can still be the arg-max; returns the new count.
+__device__ __forceinline__ int cand_compact(Cand* list, int cnt, float thr) {
+  int w = 0;
+  for (int i = 0; i < cnt; ++i) {
+    Cand c = list[i];
+    if (c.s >= thr) list[w++] = c;
+  }
+  return w;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+nn_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const float* __restrict__ Qsrc,
+             const int32_t* __restrict__ qidx, const int32_t* __restrict__ count_ptr, int Mmax,
+             const float* __restrict__ DB, int N, int tiles_per_chunk, const float* __restrict__ db_norm2_max,
+             unsigned long long* __restrict__ packed, int32_t* __restrict__ ovf_flags) {
+  const int M = count_ptr ? min(*count_ptr, Mmax) : Mmax;
+  const int m0 = blockIdx.y * BM;
+  if (m0 >= M) return;
+  const int n_begin = blockIdx.x * tiles_per_chunk * BN;
+  if (n_begin >= N) return;
+  const int n_end = min(N, n_begin + tiles_per_chunk * BN);
+  const int ntiles = (n_end - n_begin + BN - 1) / BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sA = smem_u32(smem + SMEM_A);
+  const uint32_t sB = smem_u32(smem + SMEM_B);
+  Cand* cand_all = reinterpret_cast<Cand*>(smem + SMEM_CAND);
+  const uint32_t bar0 = smem_u32(smem + SMEM_BAR);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + ACC_STAGES + a); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 8 * (2 * STAGES + 2 * ACC_STAGES));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // A tile: gather query rows, write the 128B-swizzled K-major layout (chunk ^= row & 7), zero pad.
+  for (int e = threadIdx.x; e < BM * 8; e += NUM_THREADS) {
+    int r = e >> 3, c = e & 7;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int gm = m0 + r;
+    if (gm < M && c < DK / 4) {
+      size_t row = qidx ? (size_t)qidx[gm] : (size_t)gm;
+      v = *reinterpret_cast<const float4*>(Qsrc + row * DK + c * 4);
+    }
+    *reinterpret_cast<float4*>(smem + SMEM_A + r * ROWB + ((c ^ (r & 7)) << 4)) = v;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int t = 0; t < ntiles; ++t) {
+        int s = t % STAGES;
+        uint32_t ph = (uint32_t)(t / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_arrive_expect_tx(full_bar(s), BN * ROWB);
+        tma_load_2d(sB + s * BN * ROWB, &tmap_db, 0, n_begin + t * BN, full_bar(s));
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      for (int t = 0; t < ntiles; ++t) {
+        int s = t % STAGES;
+        uint32_t ph = (uint32_t)(t / STAGES) & 1u;
+        int a = t & 1;
+        uint32_t aph = (uint32_t)(t >> 1) & 1u;
+        mbar_wait(tempty_bar(a), aph ^ 1u);
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+#pragma unroll
+        for (int kk = 0; kk < DK / 8; ++kk) {
+          uint64_t da = make_smem_desc(sA + kk * 32);
+          uint64_t db = make_smem_desc(sB + s * BN * ROWB + kk * 32);
+          tc_mma_tf32(d_tmem, da, db, IDESC, kk > 0 ? 1u : 0u);
+        }
+        tc_commit(empty_bar(s));   // smem stage free once these MMAs retire
+        tc_commit(tfull_bar(a));   // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===== epilogue: fused arg-max over TMEM accumulators =====
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;     // accumulator row == TMEM lane
+    const int gm = m0 + row;
+    const bool row_ok = gm < M;
+    Cand* list = cand_all + row * CAND_CAP;
+    int cnt = 0;
+    bool overflow = false;
+    const float* qrow = Qsrc;
+    float delta = 0.f;
+    if (row_ok) {
+      qrow = Qsrc + (qidx ? (size_t)qidx[gm] : (size_t)gm) * DK;
+      float n2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < DK; ++k) n2 = fmaf(qrow[k], qrow[k], n2);
+      delta = DELTA_COEF * sqrtf(n2) * sqrtf(*db_norm2_max) + 1e-30f;
+    }
+    float run_max = row_ok ? -INFINITY : INFINITY;  // padded rows never trigger
+
+    for (int t = 0; t < ntiles; ++t) {
+      int a = t & 1;
+      uint32_t aph = (uint32_t)(t >> 1) & 1u;
+      mbar_wait(tfull_bar(a), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * BN);
+      const int col_base = n_begin + t * BN;
+      const bool ragged = col_base + BN > n_end;
+      float v[2][32];
+      tc_ld32(taddr, v[0]);
+      tc_wait_ld();
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        if (c + 1 < BN / 32) tc_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+        float* x = v[c & 1];
+        if (ragged) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col_base + c * 32 + i >= n_end) x[i] = -INFINITY;
+        }
+        float m01 = fmax3(x[0], x[1], x[2]), m02 = fmax3(x[3], x[4], x[5]), m03 = fmax3(x[6], x[7], x[8]);
+        float m04 = fmax3(x[9], x[10], x[11]), m05 = fmax3(x[12], x[13], x[14]), m06 = fmax3(x[15], x[16], x[17]);
+        float m07 = fmax3(x[18], x[19], x[20]), m08 = fmax3(x[21], x[22], x[23]), m09 = fmax3(x[24], x[25], x[26]);
+        float m10 = fmax3(x[27], x[28], x[29]), m11 = fmaxf(x[30], x[31]);
+        float cmax = fmax3(fmax3(m01, m02, m03), fmax3(m04, m05, m06), fmax3(fmax3(m07, m08, m09), m10, m11));
+        if (cmax >= run_max - delta) {
+          run_max = fmaxf(run_max, cmax);
+          const float thr = run_max - delta;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (x[i] >= thr) {
+              if (cnt == CAND_CAP) cnt = cand_compact(list, cnt, thr);
+              if (cnt == CAND_CAP) {
+                overflow = true;
+              } else {
+                list[cnt].j = col_base + c * 32 + i;
+                list[cnt].s = x[i];
+                ++cnt;
+              }
+            }
+          }
+        }
+        if (c + 1 < BN / 32) tc_wait_ld();
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(a));
+    }
+
+    if (row_ok) {
+      if (overflow) {
+        ovf_flags[gm] = 1;
+      } else {
+        const float thr = run_max - delta;
+        float bs = -INFINITY;
+        int bj = 0x7fffffff;
+        for (int i = 0; i < cnt; ++i) {
+          Cand c = list[i];
+          if (c.s < thr) continue;
+          float s = exact_score(qrow, DB + (size_t)c.j * DK);
+          if (s > bs || (s == bs && c.j < bj)) { bs = s; bj = c.j; }
+        }
+        if (bj != 0x7fffffff) atomicMax(packed + gm, nn_pack(bs, bj));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// Exact redo of rows whose candidate list overflowed: one warp per row.
+__global__ void nn_tc_overflow_kernel(const float* __restrict__ Qsrc, const int32_t* __restrict__ qidx,
+                                      const int32_t* __restrict__ count_ptr, int Mmax,
+                                      const float* __restrict__ DB, int N,
+                                      unsigned long long* __restrict__ packed, const int32_t* __restrict__ ovf_flags) {
+  const int M = count_ptr ? min(*count_ptr, Mmax) : Mmax;
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= M || !ovf_flags[r]) return;
+  const float* q = Qsrc + (qidx ? (size_t)qidx[r] : (size_t)r) * DK;
+  float bs = -INFINITY;
+  int bj = 0x7fffffff;
+  for (int j = lane_id(); j < N; j += 32) {
+    float s = exact_score(q, DB + (size_t)j * DK);
+    if (s > bs) { bs = s; bj = j; }
+  }
+  for (int off = 1; off < 32; off <<= 1) {
+    float so = __shfl_xor_sync(0xffffffffu, bs, off);
+    int jo = __shfl_xor_sync(0xffffffffu, bj, off);
+    if (so > bs || (so == bs && jo < bj)) { bs = so; bj = jo; }
+  }
+  if (lane_id() == 0 && bj != 0x7fffffff) atomicMax(packed + r, nn_pack(bs, bj));
+}
+
+__global__ void db_norm_kernel(const float* __restrict__ DB, int N, int d, uint32_t* __restrict__ out_bits) {
+  float m = 0.f;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+    const float* b = DB + (size_t)j * d;
+    float n2 = 0.f;
+    for (int k = 0; k < d; ++k) n2 = fmaf(b[k], b[k], n2);
+    m = fmaxf(m, n2);
+  }
+  for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if (lane_id() == 0) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order like uints
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+}  // namespace
+
+bool nn_tc_supported(int d) { return d == DK; }
+
+int nn_db_norm_launch(const float* DB, int N, int d, float* out_bound, cudaStream_t stream) {
+  ST3R_CHECK_CUDA(cudaMemsetAsync(out_bound, 0, sizeof(float), stream));
+  if (N <= 0) return ST3R_OK;
+  int blocks = min((N + 255) / 256, st3r_num_sms() * 4);
+  db_norm_kernel<<<blocks, 256, 0, stream>>>(DB, N, d, reinterpret_cast<uint32_t*>(out_bound));
+  ST3R_CHECK_LAUNCH();
+  return ST3R_OK;
+}
+
+int nn_tc_launch(const float* Qsrc, const int32_t* qidx, const int32_t* count_ptr, int Mmax, const float* DB,
+                 int N, int d, const float* db_norm_bound, unsigned long long* packed, int32_t* ovf_flags,
+                 cudaStream_t stream) {
+  if (Mmax <= 0 || N <= 0) return ST3R_OK;
+  ST3R_CHECK_ARG(d == DK, "nn_tc: only d == 24 is supported (got %d)", d);
+  ST3R_CHECK_ARG(((uintptr_t)DB % 16) == 0 && ((uintptr_t)Qsrc % 16) == 0, "nn_tc: operands must be 16-byte aligned");
+  ST3R_CHECK_ARG(ovf_flags && db_norm_bound, "nn_tc: missing scratch");
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) {
+    st3r_set_error("nn_tc: cuTensorMapEncodeTiled is unavailable in this driver");
+    return ST3R_ERR_CUDA;
+  }
+  // DB viewed as a [N, 24] fp32 tensor; the box is [128 rows, 32 floats]: the 8 out-of-bounds
+  // floats per row are zero-filled by TMA, which pads K to the 128-byte swizzle span for free.
+  CUtensorMap tmap;
+  cuuint64_t gdim[2] = {(cuuint64_t)DK, (cuuint64_t)N};
+  cuuint64_t gstride[1] = {(cuuint64_t)DK * sizeof(float)};
+  cuuint32_t box[2] = {32, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(DB), gdim, gstride, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    st3r_set_error("nn_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+    return ST3R_ERR_CUDA;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
+    attr_set = true;
+  }
+  ST3R_CHECK_CUDA(cudaMemsetAsync(ovf_flags, 0, (size_t)Mmax * sizeof(int32_t), stream));
+  const int mtiles = (Mmax + BM - 1) / BM;
+  const int ntiles_total = (N + BN - 1) / BN;
+  // Chunk the DB so that the grid covers every SM twice (2 CTAs/SM) when there is enough work.
+  int want_chunks = max(1, (2 * st3r_num_sms() + mtiles - 1) / mtiles);
+  int tiles_per_chunk = max(8, min(MAX_TILES_PER_CHUNK, (ntiles_total + want_chunks - 1) / want_chunks));
+  int nchunks = (ntiles_total + tiles_per_chunk - 1) / tiles_per_chunk;
+  dim3 grid(nchunks, mtiles);
+  nn_tc_kernel<<<grid, NUM_THREADS, SMEM_DYN, stream>>>(tmap, Qsrc, qidx, count_ptr, Mmax, DB, N, tiles_per_chunk,
+                                                        db_norm_bound, packed, ovf_flags);
+  ST3R_CHECK_LAUNCH();
+  int wpb = 8;
+  nn_tc_overflow_kernel<<<(Mmax + wpb - 1) / wpb, wpb * 32, 0, stream>>>(Qsrc, qidx, count_ptr, Mmax, DB, N, packed,
+                                                                         ovf_flags);
+  ST3R_CHECK_LAUNCH();
+  return ST3R_OK;
 }

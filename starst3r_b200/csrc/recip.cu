@@ -25,6 +25,7 @@ struct RecipState {
   int32_t* counts;     // counts[h] = active length before half-iteration h
   int32_t* qidx;       // query row indices of the current half-iteration
   unsigned long long* packed;
+  int32_t* ovf;        // tcgen05 candidate-overflow flags
 };
 
 __global__ void recip_init(RecipState st, int n, int nx, int S, int W1, const int32_t* seeds, int ncounts) {
@@ -210,6 +211,7 @@ size_t carve(RecipWs* w, void* ws, size_t ws_bytes, int nseed_max, int key_cap, 
   t.st.counts = a.take<int32_t>(2 * max_iter + 2);
   t.st.qidx = a.take<int32_t>(nseed_max);
   t.st.packed = a.take<unsigned long long>(nseed_max);
+  t.st.ovf = a.take<int32_t>(nseed_max);
   t.keys = a.take<uint64_t>(key_cap);
   t.keys_alt = a.take<uint64_t>(key_cap);
   t.vals = a.take<uint32_t>(key_cap);
@@ -260,7 +262,7 @@ int run_recip(const RecipWs& w, const float* P1, int HW1, int W1, const float* P
       int rc;
       if (use_tc)
         rc = nn_tc_launch(P[src], st.qidx, st.counts + h, nseed, P[dst], HW[dst], d, w.norm_bound + dst,
-                          st.packed, stream);
+                          st.packed, st.ovf, stream);
       else
         rc = nn_simt_launch(P[src], st.qidx, st.counts + h, nseed, P[dst], HW[dst], d, st.packed, stream);
       if (rc) return rc;
@@ -301,7 +303,8 @@ extern "C" {
 
 size_t st3r_nn_argmax_ws_bytes(int M, int N, int d) {
   (void)N; (void)d;
-  return st3r_align_up((size_t)max(M, 1) * sizeof(unsigned long long), 256) + 1024;
+  return st3r_align_up((size_t)max(M, 1) * sizeof(unsigned long long), 256) +
+         st3r_align_up((size_t)max(M, 1) * sizeof(int32_t), 256) + 1024;
 }
 
 int st3r_nn_argmax(const float* Q, int M, const float* DB, int N, int d, int32_t* idx, float* best,
@@ -313,6 +316,7 @@ int st3r_nn_argmax(const float* Q, int M, const float* DB, int N, int d, int32_t
   WsAlloc a(ws, ws_bytes);
   unsigned long long* packed = a.take<unsigned long long>(M);
   float* bound = a.take<float>(4);
+  int32_t* ovf = a.take<int32_t>(M);
   ST3R_CHECK_CUDA(cudaMemsetAsync(packed, 0, (size_t)M * sizeof(unsigned long long), stream));
   int rc;
   bool use_tc = (impl == ST3R_NN_TCGEN05) || (impl == ST3R_NN_AUTO && nn_tc_supported(d) && M >= 64);
@@ -320,7 +324,7 @@ int st3r_nn_argmax(const float* Q, int M, const float* DB, int N, int d, int32_t
   if (use_tc && N > 0) {
     rc = nn_db_norm_launch(DB, N, d, bound, stream);
     if (rc) return rc;
-    rc = nn_tc_launch(Q, nullptr, nullptr, M, DB, N, d, bound, packed, stream);
+    rc = nn_tc_launch(Q, nullptr, nullptr, M, DB, N, d, bound, packed, ovf, stream);
   } else {
     rc = nn_simt_launch(Q, nullptr, nullptr, M, DB, N, d, packed, stream);
   }
