@@ -30,7 +30,7 @@ constexpr int ACC_STAGES = 2;      // TMEM accumulator stages
 constexpr int CAND_CAP = 12;       // candidates kept per row
 constexpr int NUM_THREADS = 192;   // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-5: epilogue
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 256
-constexpr int MAX_TILES_PER_CHUNK = 64;
+constexpr int MAX_TILES_PER_CHUNK = 512;
 constexpr float DELTA_COEF = 4.2e-3f;  // > 2 * 2^-9 (+ fp32 accumulation slack)
 
 constexpr int SMEM_A = 0;
@@ -135,14 +135,31 @@ __device__ __forceinline__ float exact_score(const float* __restrict__ q, const 
 
 struct Cand { int j; float s; };
 
-// Keeps only candidates that can still be the arg-max; returns the new count.
-__device__ __forceinline__ int cand_compact(Cand* list, int cnt, float thr) {
-  int w = 0;
-  for (int i = 0; i < cnt; ++i) {
-    Cand c = list[i];
-    if (c.s >= thr) list[w++] = c;
+constexpr int CAND_OVERFLOW = 0x100;
+
+// Appends the columns flagged in `mask` (column = col0 + bit) to a row's candidate list.  The stored
+// score is an upper bound of the column's approximate score (the chunk maximum), which keeps the
+// later `score >= final_max - delta` filter conservative.  When the list is full it is first
+// compacted against the current threshold; if it is still full the row is flagged as overflowed.
+__device__ __noinline__ int push_candidates(Cand* list, int cnt, uint32_t mask, int col0, float score_ub, float thr) {
+  if (cnt & CAND_OVERFLOW) return cnt;
+  while (mask) {
+    int i = __ffs(mask) - 1;
+    mask &= mask - 1;
+    if (cnt == CAND_CAP) {
+      int w = 0;
+      for (int k = 0; k < CAND_CAP; ++k) {
+        Cand c = list[k];
+        if (c.s >= thr) list[w++] = c;
+      }
+      cnt = w;
+      if (cnt == CAND_CAP) return cnt | CAND_OVERFLOW;
+    }
+    list[cnt].j = col0 + i;
+    list[cnt].s = score_ub;
+    ++cnt;
   }
-  return w;
+  return cnt;
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 2)
@@ -240,8 +257,7 @@ nn_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const float* __restric
     const int gm = m0 + row;
     const bool row_ok = gm < M;
     Cand* list = cand_all + row * CAND_CAP;
-    int cnt = 0;
-    bool overflow = false;
+    int cnt = 0;  // bit 8 set => the list overflowed (row redone exactly afterwards)
     const float* qrow = Qsrc;
     float delta = 0.f;
     if (row_ok) {
@@ -279,21 +295,14 @@ nn_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const float* __restric
         float m10 = fmax3(x[27], x[28], x[29]), m11 = fmaxf(x[30], x[31]);
         float cmax = fmax3(fmax3(m01, m02, m03), fmax3(m04, m05, m06), fmax3(fmax3(m07, m08, m09), m10, m11));
         if (cmax >= run_max - delta) {
+          // Rare path (a few times per row): kept out of line and loop-based so that the hot
+          // epilogue stays small enough for the instruction cache.
           run_max = fmaxf(run_max, cmax);
           const float thr = run_max - delta;
+          uint32_t mask = 0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (x[i] >= thr) {
-              if (cnt == CAND_CAP) cnt = cand_compact(list, cnt, thr);
-              if (cnt == CAND_CAP) {
-                overflow = true;
-              } else {
-                list[cnt].j = col_base + c * 32 + i;
-                list[cnt].s = x[i];
-                ++cnt;
-              }
-            }
-          }
+          for (int i = 0; i < 32; ++i) mask |= (x[i] >= thr ? 1u : 0u) << i;
+          cnt = push_candidates(list, cnt, mask, col_base + c * 32, cmax, thr);
         }
         if (c + 1 < BN / 32) tc_wait_ld();
       }
@@ -302,7 +311,7 @@ nn_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const float* __restric
     }
 
     if (row_ok) {
-      if (overflow) {
+      if (cnt & CAND_OVERFLOW) {
         ovf_flags[gm] = 1;
       } else {
         const float thr = run_max - delta;
@@ -425,10 +434,13 @@ int nn_tc_launch(const float* Qsrc, const int32_t* qidx, const int32_t* count_pt
   ST3R_CHECK_CUDA(cudaMemsetAsync(ovf_flags, 0, (size_t)Mmax * sizeof(int32_t), stream));
   const int mtiles = (Mmax + BM - 1) / BM;
   const int ntiles_total = (N + BN - 1) / BN;
-  // Chunk the DB so that the grid covers every SM twice (2 CTAs/SM) when there is enough work.
-  int want_chunks = max(1, (2 * st3r_num_sms() + mtiles - 1) / mtiles);
-  int tiles_per_chunk = max(8, min(MAX_TILES_PER_CHUNK, (ntiles_total + want_chunks - 1) / want_chunks));
-  int nchunks = (ntiles_total + tiles_per_chunk - 1) / tiles_per_chunk;
+  // Chunk the DB so that the grid is (close to) a whole number of waves of 2 CTAs per SM: long chunks keep
+  // the per-row candidate restarts rare, and a partial last wave would idle most of the chip.
+  const int slots = 2 * st3r_num_sms();
+  int waves = max(1, (mtiles * ((ntiles_total + MAX_TILES_PER_CHUNK - 1) / MAX_TILES_PER_CHUNK) + slots - 1) / slots);
+  int nchunks = max(1, min(ntiles_total, (waves * slots) / mtiles));
+  int tiles_per_chunk = (ntiles_total + nchunks - 1) / nchunks;
+  nchunks = (ntiles_total + tiles_per_chunk - 1) / tiles_per_chunk;
   dim3 grid(nchunks, mtiles);
   nn_tc_kernel<<<grid, NUM_THREADS, SMEM_DYN, stream>>>(tmap, Qsrc, qidx, count_ptr, Mmax, DB, N, tiles_per_chunk,
                                                         db_norm_bound, packed, ovf_flags);
