@@ -95,6 +95,85 @@ ST3R_API int st3r_extract_corres(const float* feat11, const float* feat21, const
                         int64_t* out_xy1, int64_t* out_xy2, float* out_conf, int32_t* n_out,
                         void* ws, size_t ws_bytes, int impl, cudaStream_t stream);
 
+/* ------------------------------------------------------------------ RASTER + ADAM
+ * Replaces gsplat.rasterization(means, quats, scales, opacities, colors=shN, viewmats, Ks, width,
+ * height, sh_degree=1) as called at starster/gs.py:76-87 (gsplat 1.4 semantics, SURVEY.md
+ * Appendix A; packed=True, tile_size=16, eps2d=0.3, near=0.01, far=1e10, radius_clip=0, classic
+ * mode, no background), its backward (loss.backward(), gs.py:153), the loss of gs.py:126-136 and
+ * the six Adam optimisers of gs.py:37,159-161.
+ *
+ * Intermediate layout (dense, entry e = camera * N + gaussian):
+ *   radii int32 [C*N] (0 = culled); geomA float4 [C*N] = (mean2d.x, mean2d.y, opacity, depth);
+ *   geomB float4 [C*N] = (conic a, b, c, 0); rgb float4 [C*N] = (r, g, b, 0);
+ *   tiles int32 [C*N] = number of 16x16 tiles touched.
+ * `cams` is [C, st3r_gs_cam_floats()] fp32: R (9, row-major world->camera), t (3), fx, fy, cx, cy,
+ * camera centre (3).  Quaternions are wxyz.  shN is [N, sh_coeffs, 3]. */
+ST3R_API int st3r_gs_cam_floats(void);
+ST3R_API int st3r_gs_project(const float* means, const float* quats, const float* scales, const float* opacities,
+                    const float* shN, int sh_coeffs, const float* cams, int N, int C, int width, int height,
+                    int tile_size, float eps2d, float near_plane, float far_plane, float radius_clip,
+                    int32_t* radii, float* geomA, float* geomB, float* rgb, int32_t* tiles, cudaStream_t stream);
+
+/* Exclusive prefix sum (torch.cumsum of tiles_per_gauss); *total_out = sum (device). */
+ST3R_API size_t st3r_scan_ws_bytes(size_t n);
+ST3R_API int st3r_exclusive_scan_i32(const int32_t* in, int32_t* out, size_t n, int32_t* total_out, void* ws, size_t ws_bytes,
+                            cudaStream_t stream);
+
+/* isect_tiles: keys[i] = camera << (32 + tile_bits) | tile << 32 | bits(depth), vals[i] = entry e. */
+ST3R_API int st3r_gs_isect(const int32_t* radii, const float* geomA, const int32_t* cum_tiles, int N, int C, int width,
+                  int height, int tile_size, uint64_t* keys, uint32_t* vals, int n_cap, cudaStream_t stream);
+ST3R_API int st3r_gs_sort_bits(int C, int width, int height, int tile_size);
+
+/* Stable LSD radix sort of (key, value) pairs on bits [begin_bit, end_bit) (CUB SortPairs stand-in).
+ * n = n_ptr ? min(*n_ptr, n_cap) : n_cap.  vals / vals_alt may both be NULL (keys only). */
+ST3R_API size_t st3r_radix_sort_ws_bytes(int n_cap);
+ST3R_API int st3r_radix_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uint32_t* vals_alt,
+                          const int32_t* n_ptr, int n_cap, int begin_bit, int end_bit, void* ws, size_t ws_bytes,
+                          cudaStream_t stream);
+
+/* isect_offset_encode: offsets [C, tile_h, tile_w] int32. */
+ST3R_API int st3r_gs_offsets(const uint64_t* keys, const int32_t* n_isect, int n_cap, int C, int width, int height,
+                    int tile_size, int32_t* offsets, cudaStream_t stream);
+
+/* rasterize_to_pixels forward: render [C,H,W,3], alphas [C,H,W], last_ids [C,H,W] int32;
+ * n_blend (optional, uint64, accumulated) counts blended (pixel, Gaussian) pairs. */
+ST3R_API int st3r_gs_raster_fwd(const int32_t* offsets, const int32_t* n_isect, const uint32_t* flatten_ids,
+                       const float* geomA, const float* geomB, const float* rgb, int C, int width, int height,
+                       int tile_size, float* render, float* alphas, int32_t* last_ids, uint64_t* n_blend,
+                       cudaStream_t stream);
+/* rasterize_to_pixels backward: accumulates into v_geomA = (v_x, v_y, v_opacity, 0), v_geomB = v_conic,
+ * v_rgb (all float4 [C*N], zeroed by the caller).  v_alphas may be NULL. */
+ST3R_API int st3r_gs_raster_bwd(const int32_t* offsets, const int32_t* n_isect, const uint32_t* flatten_ids,
+                       const float* geomA, const float* geomB, const float* rgb, int C, int width, int height,
+                       int tile_size, const float* alphas, const int32_t* last_ids, const float* v_render,
+                       const float* v_alphas, float* v_geomA, float* v_geomB, float* v_rgb, cudaStream_t stream);
+/* projection + SH backward, summed over cameras, plus d/d(opacity, scale) of the regularisers
+ * (reg_opac = C * fac / N, reg_scale = C * fac / (3N)).  v_sh is [N, 4, 3] (the SH coefficients degree 1
+ * touches).  reg_sums (optional, float[2], accumulated): sum sigmoid(opacity), sum exp(scale). */
+ST3R_API int st3r_gs_project_bwd(const float* means, const float* quats, const float* scales, const float* opacities,
+                        const float* shN, int sh_coeffs, const float* cams, int N, int C, int width,
+                        int height, float eps2d, float near_plane, float far_plane, float radius_clip,
+                        const int32_t* radii, const float* v_geomA, const float* v_geomB,
+                        const float* v_rgb, float reg_opac, float reg_scale, float* v_means,
+                        float* v_quats, float* v_scales, float* v_opacities, float* v_sh, float* reg_sums,
+                        cudaStream_t stream);
+
+/* (1-f) * L1 + f * (1 - SSIM) per view (gs.py:126-131; SSIM = torchmetrics, data_range 1).
+ * render/truth [C,H,W,3]; dmaps [C,H,W,3,3] scratch; sums [C,2] (zeroed by caller) receives
+ * (sum of interior SSIM, sum |truth - render|).  bwd writes v_render = dLoss/d(render). */
+ST3R_API int st3r_gs_loss_fwd(const float* render, const float* truth, int C, int height, int width, float ssim_fac,
+                     float* dmaps, float* sums, cudaStream_t stream);
+ST3R_API int st3r_gs_loss_bwd(const float* render, const float* truth, const float* dmaps, int C, int height, int width,
+                     float ssim_fac, float* v_render, cudaStream_t stream);
+
+/* torch.optim.Adam step over up to 8 tensors in one launch.  Arrays are HOST arrays of device pointers /
+ * sizes; tensor i is rows[i] x cols[i] with leading dimensions ld_param[i] (param and both moments) and
+ * ld_grad[i].  step is 1-based. */
+ST3R_API int st3r_adam_step(int n_seg, float* const* h_params, const float* const* h_grads, float* const* h_exp_avg,
+                   float* const* h_exp_avg_sq, const int* h_rows, const int* h_cols, const int* h_ld_param,
+                   const int* h_ld_grad, float lr, float beta1, float beta2, float eps, int step,
+                   cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

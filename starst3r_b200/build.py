@@ -20,7 +20,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 # Files whose arithmetic must not be FMA-contracted (bit-exact tile/bin indices).
-NO_FMAD = {"gs_project.cu"}
+NO_FMAD = {"gs_project.cu", "gs_backward.cu"}
 
 
 def sources():

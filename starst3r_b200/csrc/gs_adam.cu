@@ -1,0 +1,66 @@
+// Fused per-Gaussian Adam (replaces the six torch.optim.Adam instances of starster/gs.py:37,159-161;
+// lr 1e-3, betas (0.9, 0.999), eps 1e-8, no weight decay, bias-corrected, non-amsgrad).
+// One launch updates every trainable tensor of the splat: segment s = (param, grad, exp_avg, exp_avg_sq)
+// viewed as `rows` x `cols` with independent leading dimensions, so the first 4 SH coefficients of shN
+// ([N,24,3], the only ones that ever receive a non-zero gradient: gs.py:81 renders with sh_degree=1)
+// are updated in place without touching the other 60 floats.  `sh0` never receives a gradient
+// (it is not passed to the renderer) and is skipped exactly like torch skips params with grad=None.
+// HBM-bound: 7 floats moved per element (read p, g, m, v; write p, m, v) = 28 B.
+#include "common.cuh"
+#include "gs.cuh"
+
+namespace {
+struct AdamSeg {
+  float* p; const float* g; float* m; float* v;
+  int rows, cols, ld_p, ld_g;
+};
+struct AdamSegs { AdamSeg s[8]; int n; };
+
+__global__ void __launch_bounds__(256)
+adam_kernel(AdamSegs segs, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps) {
+  const AdamSeg sg = segs.s[blockIdx.y];
+  const long long total = (long long)sg.rows * sg.cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / sg.cols), c = (int)(i - (long long)r * sg.cols);
+    const size_t ip = (size_t)r * sg.ld_p + c, ig = (size_t)r * sg.ld_g + c;
+    const float g = sg.g[ig];
+    float m = sg.m[ip], v = sg.v[ip];
+    m = m + (g - m) * (1.0f - b1);                 // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * b2 + (1.0f - b2) * g * g;              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
+    sg.p[ip] = sg.p[ip] - lr_over_bc1 * (m / denom);
+    sg.m[ip] = m;
+    sg.v[ip] = v;
+  }
+}
+}  // namespace
+
+extern "C" int st3r_adam_step(int n_seg, float* const* params, const float* const* grads, float* const* exp_avg,
+                              float* const* exp_avg_sq, const int* rows, const int* cols, const int* ld_param,
+                              const int* ld_grad, float lr, float beta1, float beta2, float eps, int step,
+                              cudaStream_t stream) {
+  ST3R_CHECK_ARG(n_seg >= 0 && n_seg <= 8 && step >= 1, "st3r_adam_step: bad args (n_seg <= 8, step >= 1)");
+  if (n_seg == 0) return ST3R_OK;
+  ST3R_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && rows && cols && ld_param && ld_grad, "st3r_adam_step: null");
+  AdamSegs segs;
+  segs.n = n_seg;
+  long long max_total = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    ST3R_CHECK_ARG(params[i] && grads[i] && exp_avg[i] && exp_avg_sq[i] && rows[i] >= 0 && cols[i] > 0,
+                   "st3r_adam_step: bad segment %d", i);
+    segs.s[i] = AdamSeg{params[i], grads[i], exp_avg[i], exp_avg_sq[i], rows[i], cols[i], ld_param[i], ld_grad[i]};
+    long long t = (long long)rows[i] * cols[i];
+    if (t > max_total) max_total = t;
+  }
+  if (max_total == 0) return ST3R_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float lr_over_bc1 = (float)((double)lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  int blocks = (int)((max_total + 255) / 256);
+  int cap = st3r_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  dim3 grid(blocks, n_seg);
+  adam_kernel<<<grid, 256, 0, stream>>>(segs, lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps);
+  ST3R_CHECK_LAUNCH();
+  return ST3R_OK;
+}

@@ -1,0 +1,243 @@
+// Per-tile alpha blending, forward and backward (gsplat rasterize_to_pixels_fwd / _bwd,
+// SURVEY.md Appendix A.6; called from starster/gs.py:76-87 and by loss.backward(), gs.py:153).
+//
+// One CTA of 16x16 threads per (camera, tile); the tile's depth-sorted Gaussians are staged
+// through shared memory in batches of 256 as three float4 records (xy+opacity, conic, rgb:
+// 48 B per intersection, read once per tile, coalesced 16-byte gathers), and every pixel
+// walks the batch with broadcast LDS.128 reads.  Backward walks the same list back to front,
+// re-derives the transmittance, reduces each Gaussian's nine partial derivatives across the
+// warp with shuffles, accumulates the eight warps of the CTA in shared memory and issues one
+// vector atomicAdd per (tile, Gaussian) record to HBM.
+// Algorithmic bytes: fwd 40 B per intersection + 20 B per pixel;
+// bwd 40 B per intersection + 24 B per pixel + 36 B of gradient per visible (Gaussian, view).
+#include "common.cuh"
+#include "gs.cuh"
+
+namespace {
+
+constexpr int TILE = 16;
+constexpr int BLOCK = TILE * TILE;
+constexpr float ALPHA_MIN = 1.0f / 255.0f;
+constexpr float ALPHA_MAX = 0.999f;
+constexpr float T_MIN = 1e-4f;
+
+struct TileRange { int lo, hi; };
+
+__device__ __forceinline__ TileRange tile_range(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
+                                                int t, int total_tiles) {
+  TileRange r;
+  r.lo = offsets[t];
+  r.hi = (t + 1 < total_tiles) ? offsets[t + 1] : *n_isect;
+  return r;
+}
+
+__global__ void __launch_bounds__(BLOCK)
+raster_fwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
+                  const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
+                  const float4* __restrict__ geomB, const float4* __restrict__ rgb, int C, int W, int H, int tile_w,
+                  int tile_h, float* __restrict__ render, float* __restrict__ alphas, int32_t* __restrict__ last_ids,
+                  unsigned long long* __restrict__ n_blend) {
+  __shared__ float4 sA[BLOCK], sB[BLOCK], sC[BLOCK];
+  const int c = blockIdx.y, tile = blockIdx.x;
+  const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
+  const int tr = threadIdx.x;
+  const int i = tyi * TILE + (tr >> 4), j = txi * TILE + (tr & 15);
+  const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+  const bool inside = i < H && j < W;
+  bool done = !inside;
+  const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
+  const int nb = (rg.hi - rg.lo + BLOCK - 1) / BLOCK;
+  float T = 1.0f, pr = 0.f, pg = 0.f, pb = 0.f;
+  int cur = 0, blends = 0;
+  for (int b = 0; b < nb; ++b) {
+    if (__syncthreads_count(done) == BLOCK) break;
+    const int start = rg.lo + b * BLOCK;
+    const int idx = start + tr;
+    if (idx < rg.hi) {
+      uint32_t e = flatten[idx];
+      sA[tr] = geomA[e];
+      sB[tr] = geomB[e];
+      sC[tr] = rgb[e];
+    }
+    __syncthreads();
+    const int bs = min(BLOCK, rg.hi - start);
+    for (int t = 0; t < bs && !done; ++t) {
+      const float4 A = sA[t], B = sB[t];
+      const float dx = A.x - px, dy = A.y - py;
+      const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
+      const float alpha = fminf(ALPHA_MAX, A.z * __expf(-sigma));
+      if (sigma < 0.f || alpha < ALPHA_MIN) continue;
+      const float nT = T * (1.0f - alpha);
+      if (nT <= T_MIN) { done = true; break; }
+      const float w = alpha * T;
+      const float4 col = sC[t];
+      pr += col.x * w; pg += col.y * w; pb += col.z * w;
+      cur = start + t;
+      T = nT;
+      ++blends;
+    }
+  }
+  if (inside) {
+    const size_t p = ((size_t)c * H + i) * W + j;
+    render[3 * p] = pr; render[3 * p + 1] = pg; render[3 * p + 2] = pb;
+    alphas[p] = 1.0f - T;
+    last_ids[p] = cur;
+  }
+  if (n_blend) {
+    for (int off = 16; off; off >>= 1) blends += __shfl_xor_sync(0xffffffffu, blends, off);
+    if (lane_id() == 0 && blends) atomicAdd(n_blend, (unsigned long long)blends);
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+__global__ void __launch_bounds__(BLOCK)
+raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
+                  const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
+                  const float4* __restrict__ geomB, const float4* __restrict__ rgb, int C, int W, int H, int tile_w,
+                  int tile_h, const float* __restrict__ alphas, const int32_t* __restrict__ last_ids,
+                  const float* __restrict__ v_render, const float* __restrict__ v_alphas,
+                  float4* __restrict__ v_geomA, float4* __restrict__ v_geomB, float4* __restrict__ v_rgb) {
+  __shared__ float4 sA[BLOCK], sB[BLOCK], sC[BLOCK];
+  __shared__ uint32_t sE[BLOCK];
+  __shared__ float acc[BLOCK][9];  // per-batch gradient accumulators (xy 2, opac 1, conic 3, rgb 3)
+  const int c = blockIdx.y, tile = blockIdx.x;
+  const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
+  const int tr = threadIdx.x;
+  const int i = tyi * TILE + (tr >> 4), j = txi * TILE + (tr & 15);
+  const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+  const bool inside = i < H && j < W;
+  const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
+  if (rg.hi <= rg.lo) return;
+  const size_t p = ((size_t)c * H + min(i, H - 1)) * W + min(j, W - 1);
+  const float T_final = 1.0f - alphas[p];
+  float T = T_final;
+  float br = 0.f, bg = 0.f, bb = 0.f;
+  const int bin_final = inside ? last_ids[p] : 0;
+  float vr = 0.f, vg = 0.f, vb = 0.f, va = 0.f;
+  if (inside) {
+    vr = v_render[3 * p]; vg = v_render[3 * p + 1]; vb = v_render[3 * p + 2];
+    va = v_alphas ? v_alphas[p] : 0.f;
+  }
+  int warp_bin_final = bin_final;
+  for (int off = 16; off; off >>= 1) warp_bin_final = max(warp_bin_final, __shfl_xor_sync(0xffffffffu, warp_bin_final, off));
+
+  const int nb = (rg.hi - rg.lo + BLOCK - 1) / BLOCK;
+  for (int b = 0; b < nb; ++b) {
+    __syncthreads();
+    const int batch_end = rg.hi - 1 - BLOCK * b;
+    const int bs = min(BLOCK, batch_end + 1 - rg.lo);
+    const int idx = batch_end - tr;
+    if (idx >= rg.lo) {
+      uint32_t e = flatten[idx];
+      sE[tr] = e;
+      sA[tr] = geomA[e];
+      sB[tr] = geomB[e];
+      sC[tr] = rgb[e];
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[tr][k] = 0.f;
+    __syncthreads();
+    for (int t = max(0, batch_end - warp_bin_final); t < bs; ++t) {
+      bool valid = inside && (batch_end - t <= bin_final);
+      float alpha = 0.f, opac = 0.f, vis = 0.f, dx = 0.f, dy = 0.f;
+      float4 B = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
+        const float4 A = sA[t];
+        B = sB[t];
+        opac = A.z;
+        dx = A.x - px; dy = A.y - py;
+        const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
+        vis = __expf(-sigma);
+        alpha = fminf(ALPHA_MAX, opac * vis);
+        if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
+      }
+      if (!__any_sync(0xffffffffu, valid)) continue;
+      float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (valid) {
+        const float ra = 1.0f / (1.0f - alpha);
+        T *= ra;
+        const float fac = alpha * T;
+        const float4 col = sC[t];
+        g[6] = fac * vr; g[7] = fac * vg; g[8] = fac * vb;
+        float v_alpha = (col.x * T - br * ra) * vr + (col.y * T - bg * ra) * vg + (col.z * T - bb * ra) * vb;
+        v_alpha += T_final * ra * va;
+        if (opac * vis <= ALPHA_MAX) {
+          const float v_sigma = -opac * vis * v_alpha;
+          g[3] = 0.5f * v_sigma * dx * dx;
+          g[4] = v_sigma * dx * dy;
+          g[5] = 0.5f * v_sigma * dy * dy;
+          g[0] = v_sigma * (B.x * dx + B.y * dy);
+          g[1] = v_sigma * (B.y * dx + B.z * dy);
+          g[2] = vis * v_alpha;
+        }
+        br += col.x * fac; bg += col.y * fac; bb += col.z * fac;
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) g[k] = warp_sum(g[k]);
+      if (lane_id() == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) atomicAdd(&acc[t][k], g[k]);
+      }
+    }
+    __syncthreads();
+    if (tr < bs) {
+      const uint32_t e = sE[tr];
+      const float* a = acc[tr];
+      if (a[0] != 0.f || a[1] != 0.f || a[2] != 0.f || a[3] != 0.f || a[4] != 0.f || a[5] != 0.f || a[6] != 0.f ||
+          a[7] != 0.f || a[8] != 0.f) {
+        atomicAdd(v_geomA + e, make_float4(a[0], a[1], a[2], 0.f));
+        atomicAdd(v_geomB + e, make_float4(a[3], a[4], a[5], 0.f));
+        atomicAdd(v_rgb + e, make_float4(a[6], a[7], a[8], 0.f));
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int st3r_gs_raster_fwd(const int32_t* offsets, const int32_t* n_isect, const uint32_t* flatten_ids,
+                       const float* geomA, const float* geomB, const float* rgb, int C, int width, int height,
+                       int tile_size, float* render, float* alphas, int32_t* last_ids, uint64_t* n_blend,
+                       cudaStream_t stream) {
+  ST3R_CHECK_ARG(tile_size == TILE, "st3r_gs_raster_fwd: tile_size must be 16 (gsplat default used by Starst3r)");
+  ST3R_CHECK_ARG(C >= 0 && width > 0 && height > 0, "st3r_gs_raster_fwd: bad sizes");
+  if (C == 0) return ST3R_OK;
+  ST3R_CHECK_ARG(offsets && n_isect && geomA && geomB && rgb && render && alphas && last_ids,
+                 "st3r_gs_raster_fwd: null pointer");
+  const int tile_w = (width + TILE - 1) / TILE, tile_h = (height + TILE - 1) / TILE;
+  dim3 grid(tile_w * tile_h, C);
+  raster_fwd_kernel<<<grid, BLOCK, 0, stream>>>(offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA),
+                                                reinterpret_cast<const float4*>(geomB),
+                                                reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h,
+                                                render, alphas, last_ids, reinterpret_cast<unsigned long long*>(n_blend));
+  ST3R_CHECK_LAUNCH();
+  return ST3R_OK;
+}
+
+int st3r_gs_raster_bwd(const int32_t* offsets, const int32_t* n_isect, const uint32_t* flatten_ids,
+                       const float* geomA, const float* geomB, const float* rgb, int C, int width, int height,
+                       int tile_size, const float* alphas, const int32_t* last_ids, const float* v_render,
+                       const float* v_alphas, float* v_geomA, float* v_geomB, float* v_rgb, cudaStream_t stream) {
+  ST3R_CHECK_ARG(tile_size == TILE, "st3r_gs_raster_bwd: tile_size must be 16");
+  ST3R_CHECK_ARG(C >= 0 && width > 0 && height > 0, "st3r_gs_raster_bwd: bad sizes");
+  if (C == 0) return ST3R_OK;
+  ST3R_CHECK_ARG(offsets && n_isect && geomA && geomB && rgb && alphas && last_ids && v_render && v_geomA &&
+                     v_geomB && v_rgb,
+                 "st3r_gs_raster_bwd: null pointer");
+  const int tile_w = (width + TILE - 1) / TILE, tile_h = (height + TILE - 1) / TILE;
+  dim3 grid(tile_w * tile_h, C);
+  raster_bwd_kernel<<<grid, BLOCK, 0, stream>>>(
+      offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
+      reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, alphas, last_ids, v_render, v_alphas,
+      reinterpret_cast<float4*>(v_geomA), reinterpret_cast<float4*>(v_geomB), reinterpret_cast<float4*>(v_rgb));
+  ST3R_CHECK_LAUNCH();
+  return ST3R_OK;
+}
+}

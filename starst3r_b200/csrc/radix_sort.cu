@@ -225,3 +225,16 @@ int radix_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uint32_
   }
   return ST3R_OK;
 }
+
+#include "../../include/starst3r_b200.h"
+extern "C" {
+size_t st3r_radix_sort_ws_bytes(int n_cap) { return radix_sort_ws_bytes(n_cap); }
+int st3r_radix_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uint32_t* vals_alt,
+                          const int32_t* n_ptr, int n_cap, int begin_bit, int end_bit, void* ws, size_t ws_bytes,
+                          cudaStream_t stream) {
+  ST3R_CHECK_ARG(n_cap >= 0 && begin_bit >= 0 && end_bit <= 64, "st3r_radix_sort_pairs: bad args");
+  if (n_cap == 0) return ST3R_OK;
+  ST3R_CHECK_ARG(keys && keys_alt && ws, "st3r_radix_sort_pairs: null pointer");
+  return radix_sort_pairs(keys, vals, keys_alt, vals_alt, n_ptr, n_cap, begin_bit, end_bit, ws, ws_bytes, stream);
+}
+}

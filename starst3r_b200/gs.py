@@ -1,0 +1,399 @@
+"""RASTER + ADAM hot path — host-side mirror of starster/gs.py (init_3dgs, render_3dgs, render_3dgs_original,
+run_3dgs_optim) and of the one gsplat entry point it calls (gsplat.rasterization, gs.py:76-87).
+
+Everything numeric runs in hand-written sm_100a kernels behind the C ABI (include/starst3r_b200.h):
+projection + SH -> tile count -> scan -> key emission -> radix sort -> tile offsets -> alpha blend, the blend /
+projection / SH backward, the fused L1+SSIM loss and a fused multi-tensor Adam.  No gsplat, no torchmetrics,
+no CPU fallback.  PyTorch only owns the memory and the stream.
+"""
+import ctypes
+import math
+
+import torch
+from tqdm import trange
+
+from . import _lib
+
+__all__ = ("init_3dgs", "render_3dgs", "render_3dgs_original", "run_3dgs_optim", "rasterization", "FusedAdam")
+
+TILE = 16
+EPS2D, NEAR, FAR, RADIUS_CLIP = 0.3, 0.01, 1e10, 0.0
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _f(x):
+    return ctypes.c_float(float(x))
+
+
+def make_cams(viewmats, Ks):
+    """[C, 19] fp32 camera records: R (9) | t (3) | fx fy cx cy | camera centre (3)."""
+    C = viewmats.shape[0]
+    V = viewmats.detach().float()
+    K = Ks.detach().float()
+    pos = torch.linalg.inv(V)[:, :3, 3]
+    cams = torch.cat([V[:, :3, :3].reshape(C, 9), V[:, :3, 3], K[:, 0, 0:1], K[:, 1, 1:2], K[:, 0, 2:3], K[:, 1, 2:3],
+                      pos], dim=1)
+    return cams.contiguous()
+
+
+class _Frame:
+    """Device state of one forward pass (kept for the backward)."""
+    pass
+
+
+def _forward(means, quats, scales, opacities, shN, cams, width, height, count_blends=False):
+    lib = _lib.load()
+    _lib.require_cuda(means, quats, scales, opacities, shN, cams)
+    dev = means.device
+    N, C = means.shape[0], cams.shape[0]
+    assert lib.st3r_gs_cam_floats() == cams.shape[1]
+    sh_coeffs = shN.shape[1]
+    fr = _Frame()
+    fr.N, fr.C, fr.W, fr.H, fr.sh_coeffs, fr.cams = N, C, int(width), int(height), sh_coeffs, cams
+    fr.tile_w, fr.tile_h = (fr.W + TILE - 1) // TILE, (fr.H + TILE - 1) // TILE
+    E = max(C * N, 1)
+    fr.radii = torch.empty(E, dtype=torch.int32, device=dev)
+    fr.geomA = torch.empty((E, 4), dtype=torch.float32, device=dev)
+    fr.geomB = torch.empty((E, 4), dtype=torch.float32, device=dev)
+    fr.rgb = torch.empty((E, 4), dtype=torch.float32, device=dev)
+    fr.tiles = torch.empty(E, dtype=torch.int32, device=dev)
+    fr.cum = torch.empty(E, dtype=torch.int32, device=dev)
+    fr.n_isect_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = _lib.stream_ptr()
+    with torch.cuda.device(dev):
+        _lib.check(lib.st3r_gs_project(_lib.ptr(means), _lib.ptr(quats), _lib.ptr(scales), _lib.ptr(opacities),
+                                       _lib.ptr(shN), sh_coeffs, _lib.ptr(cams), N, C, fr.W, fr.H, TILE, _f(EPS2D),
+                                       _f(NEAR), _f(FAR), _f(RADIUS_CLIP), _lib.ptr(fr.radii), _lib.ptr(fr.geomA),
+                                       _lib.ptr(fr.geomB), _lib.ptr(fr.rgb), _lib.ptr(fr.tiles), st), "st3r_gs_project")
+        ws = _ws(lib.st3r_scan_ws_bytes(C * N), dev)
+        _lib.check(lib.st3r_exclusive_scan_i32(_lib.ptr(fr.tiles), _lib.ptr(fr.cum), C * N, _lib.ptr(fr.n_isect_dev),
+                                               _lib.ptr(ws), ws.numel(), st), "st3r_exclusive_scan_i32")
+        # One host read per frame sizes the intersection buffers exactly (gsplat does the same).
+        n_isect = int(fr.n_isect_dev.item())
+        fr.n_isect = n_isect
+        cap = max(n_isect, 1)
+        fr.keys = torch.empty(cap, dtype=torch.int64, device=dev)
+        fr.vals = torch.empty(cap, dtype=torch.int32, device=dev)
+        keys_alt = torch.empty(cap, dtype=torch.int64, device=dev)
+        vals_alt = torch.empty(cap, dtype=torch.int32, device=dev)
+        _lib.check(lib.st3r_gs_isect(_lib.ptr(fr.radii), _lib.ptr(fr.geomA), _lib.ptr(fr.cum), N, C, fr.W, fr.H, TILE,
+                                     _lib.ptr(fr.keys), _lib.ptr(fr.vals), n_isect, st), "st3r_gs_isect")
+        ws = _ws(lib.st3r_radix_sort_ws_bytes(n_isect), dev)
+        bits = lib.st3r_gs_sort_bits(C, fr.W, fr.H, TILE)
+        _lib.check(lib.st3r_radix_sort_pairs(_lib.ptr(fr.keys), _lib.ptr(fr.vals), _lib.ptr(keys_alt),
+                                             _lib.ptr(vals_alt), _lib.ptr(fr.n_isect_dev), n_isect, 0, bits,
+                                             _lib.ptr(ws), ws.numel(), st), "st3r_radix_sort_pairs")
+        fr.offsets = torch.empty(max(C * fr.tile_w * fr.tile_h, 1), dtype=torch.int32, device=dev)
+        _lib.check(lib.st3r_gs_offsets(_lib.ptr(fr.keys), _lib.ptr(fr.n_isect_dev), n_isect, C, fr.W, fr.H, TILE,
+                                       _lib.ptr(fr.offsets), st), "st3r_gs_offsets")
+        fr.render = torch.empty((C, fr.H, fr.W, 3), dtype=torch.float32, device=dev)
+        fr.alphas = torch.empty((C, fr.H, fr.W), dtype=torch.float32, device=dev)
+        fr.last_ids = torch.empty((C, fr.H, fr.W), dtype=torch.int32, device=dev)
+        fr.n_blend = torch.zeros(1, dtype=torch.int64, device=dev) if count_blends else None
+        _lib.check(lib.st3r_gs_raster_fwd(_lib.ptr(fr.offsets), _lib.ptr(fr.n_isect_dev), _lib.ptr(fr.vals),
+                                          _lib.ptr(fr.geomA), _lib.ptr(fr.geomB), _lib.ptr(fr.rgb), C, fr.W, fr.H, TILE,
+                                          _lib.ptr(fr.render), _lib.ptr(fr.alphas), _lib.ptr(fr.last_ids),
+                                          _lib.ptr(fr.n_blend), st), "st3r_gs_raster_fwd")
+    return fr
+
+
+def _backward(fr, means, quats, scales, opacities, shN, v_render, v_alphas, reg_opac=0.0, reg_scale=0.0,
+              reg_sums=None):
+    """Blend backward + projection/SH backward.  Returns (v_means, v_quats, v_scales, v_opacities, v_sh [N,4,3])."""
+    lib = _lib.load()
+    dev = means.device
+    N, C = fr.N, fr.C
+    E = max(C * N, 1)
+    v_geom = torch.zeros((3, E, 4), dtype=torch.float32, device=dev)
+    v_means = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    v_quats = torch.empty((N, 4), dtype=torch.float32, device=dev)
+    v_scales = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    v_opac = torch.empty((N,), dtype=torch.float32, device=dev)
+    v_sh = torch.empty((N, 4, 3), dtype=torch.float32, device=dev)
+    st = _lib.stream_ptr()
+    with torch.cuda.device(dev):
+        _lib.check(lib.st3r_gs_raster_bwd(_lib.ptr(fr.offsets), _lib.ptr(fr.n_isect_dev), _lib.ptr(fr.vals),
+                                          _lib.ptr(fr.geomA), _lib.ptr(fr.geomB), _lib.ptr(fr.rgb), C, fr.W, fr.H, TILE,
+                                          _lib.ptr(fr.alphas), _lib.ptr(fr.last_ids), _lib.ptr(v_render),
+                                          _lib.ptr(v_alphas), _lib.ptr(v_geom[0]), _lib.ptr(v_geom[1]),
+                                          _lib.ptr(v_geom[2]), st), "st3r_gs_raster_bwd")
+        _lib.check(lib.st3r_gs_project_bwd(_lib.ptr(means), _lib.ptr(quats), _lib.ptr(scales), _lib.ptr(opacities),
+                                           _lib.ptr(shN), fr.sh_coeffs, _lib.ptr(fr.cams), N, C, fr.W, fr.H, _f(EPS2D),
+                                           _f(NEAR), _f(FAR), _f(RADIUS_CLIP), _lib.ptr(fr.radii), _lib.ptr(v_geom[0]),
+                                           _lib.ptr(v_geom[1]), _lib.ptr(v_geom[2]), _f(reg_opac), _f(reg_scale),
+                                           _lib.ptr(v_means), _lib.ptr(v_quats), _lib.ptr(v_scales), _lib.ptr(v_opac),
+                                           _lib.ptr(v_sh), _lib.ptr(reg_sums), st), "st3r_gs_project_bwd")
+    return v_means, v_quats, v_scales, v_opac, v_sh
+
+
+def _info(fr, opacities):
+    """The `info` dict of gsplat.rasterization (packed=True) assembled from the dense device state
+    (index plumbing only)."""
+    C, N = fr.C, fr.N
+    vis = fr.radii[:C * N] > 0
+    ids = torch.nonzero(vis).squeeze(1)
+    packed_index = torch.cumsum(vis.to(torch.int32), 0, dtype=torch.int32) - 1
+    gaussian_ids = ids % max(N, 1)
+    n = fr.n_isect
+    return {
+        "camera_ids": ids // max(N, 1), "gaussian_ids": gaussian_ids, "radii": fr.radii[ids],
+        "means2d": fr.geomA[ids, 0:2], "depths": fr.geomA[ids, 3], "conics": fr.geomB[ids, 0:3],
+        "opacities": opacities.detach()[gaussian_ids], "tile_width": fr.tile_w, "tile_height": fr.tile_h,
+        "tiles_per_gauss": fr.tiles[ids], "isect_ids": fr.keys[:n],
+        "flatten_ids": packed_index[fr.vals[:n].long()], "isect_offsets": fr.offsets.reshape(C, fr.tile_h, fr.tile_w),
+        "width": fr.W, "height": fr.H, "tile_size": TILE, "n_cameras": C, "last_ids": fr.last_ids,
+    }
+
+
+class _Rasterize(torch.autograd.Function):
+    last_frame = None   # device state of the most recent forward (read by rasterization() to build `info`)
+
+    @staticmethod
+    def forward(ctx, means, quats, scales, opacities, colors, cams, width, height):
+        args = [t.detach().float().contiguous() for t in (means, quats, scales, opacities, colors)]
+        fr = _forward(*args, cams, width, height)
+        ctx.fr, ctx.args = fr, args
+        _Rasterize.last_frame = fr
+        ctx.mark_non_differentiable(fr.last_ids)
+        return fr.render, fr.alphas.unsqueeze(-1), fr.last_ids
+
+    @staticmethod
+    def backward(ctx, v_render, v_alpha, _):
+        fr = ctx.fr
+        v_render = v_render.float().contiguous()
+        v_alpha = v_alpha.float().reshape(fr.C, fr.H, fr.W).contiguous()
+        vm, vq, vs, vo, vsh = _backward(fr, *ctx.args, v_render, v_alpha)
+        v_colors = torch.zeros((fr.N, fr.sh_coeffs, 3), dtype=torch.float32, device=vm.device)
+        v_colors[:, :4] = vsh
+        return vm, vq, vs, vo, v_colors, None, None, None
+
+
+def rasterization(means, quats, scales, opacities, colors, viewmats, Ks, width, height, sh_degree=1, **kw):
+    """gsplat.rasterization as Starst3r calls it (gs.py:76-87): returns (render [C,H,W,3], alpha [C,H,W,1], info).
+    Differentiable w.r.t. means / quats / scales / opacities / colors."""
+    if sh_degree != 1:
+        raise NotImplementedError("the Starst3r hot path renders with sh_degree=1 (gs.py:86); other degrees are "
+                                  "outside the B200 path")
+    if kw:
+        raise NotImplementedError(f"unsupported gsplat.rasterization options {sorted(kw)}: Starst3r uses the defaults")
+    if not means.is_cuda:
+        raise RuntimeError("starst3r_b200.gs.rasterization: tensors must live on a CUDA device (no CPU fallback)")
+    cams = make_cams(viewmats.to(means.device), Ks.to(means.device))
+    render, alpha, last_ids = _Rasterize.apply(means, quats, scales, opacities, colors, cams, int(width), int(height))
+    info = _info(_Rasterize.last_frame, opacities)
+    return render, alpha, info
+
+
+# ------------------------------------------------------------------------------------------- optimiser
+class FusedAdam:
+    """Optimizer-like handle for one splat tensor (what scene.optimizers[k] holds; gs.py:37).  Exposes
+    param_groups / state like torch.optim.Adam; step() runs the fused CUDA Adam on `param.grad`."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.param_groups = [dict(params=list(params), lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False)]
+        self.state = {}
+
+    def _st(self, p):
+        if p not in self.state:
+            self.state[p] = dict(step=torch.zeros((), dtype=torch.float32), exp_avg=torch.zeros_like(p.data),
+                                 exp_avg_sq=torch.zeros_like(p.data))
+        return self.state[p]
+
+    def zero_grad(self, set_to_none=True):
+        for g in self.param_groups:
+            for p in g["params"]:
+                p.grad = None if set_to_none else (p.grad.zero_() if p.grad is not None else None)
+
+    def step(self):
+        for g in self.param_groups:
+            for p in g["params"]:
+                if p.grad is None:
+                    continue
+                st = self._st(p)
+                st["step"] += 1
+                n = p.numel()
+                adam_step([(p.data.view(-1), p.grad.contiguous().view(-1), st["exp_avg"].view(-1),
+                            st["exp_avg_sq"].view(-1), 1, n, n, n)], g["lr"], g["betas"], g["eps"], int(st["step"].item()))
+
+
+def adam_step(segments, lr, betas, eps, step):
+    """segments: list of (param, grad, exp_avg, exp_avg_sq, rows, cols, ld_param, ld_grad) device tensors."""
+    lib = _lib.load()
+    n = len(segments)
+    PP = ctypes.c_void_p * n
+    II = ctypes.c_int * n
+    p = PP(*[s[0].data_ptr() for s in segments])
+    g = PP(*[s[1].data_ptr() for s in segments])
+    m = PP(*[s[2].data_ptr() for s in segments])
+    v = PP(*[s[3].data_ptr() for s in segments])
+    rows, cols = II(*[int(s[4]) for s in segments]), II(*[int(s[5]) for s in segments])
+    ldp, ldg = II(*[int(s[6]) for s in segments]), II(*[int(s[7]) for s in segments])
+    dev = segments[0][0].device
+    with torch.cuda.device(dev):
+        rc = lib.st3r_adam_step(n, p, g, m, v, rows, cols, ldp, ldg, _f(lr), _f(betas[0]), _f(betas[1]), _f(eps),
+                                int(step), _lib.stream_ptr())
+    _lib.check(rc, "st3r_adam_step")
+
+
+class MCMCStrategyStub:
+    """Placeholder for gsplat.MCMCStrategy (gs.py:43-45).  With gsplat's defaults relocation / densification only
+    fires for 500 < step < 25000 with step % 100 == 0 and `step` restarts at 0 on every run_3dgs_optim call
+    (gs.py:143), so the documented usage (<= 500 iterations per call) only ever applies the per-step position
+    noise, which is applied faithfully.  Relocation itself is on the §8f list."""
+    cap_max, noise_lr, refine_start_iter, refine_stop_iter, refine_every, min_opacity = 1_000_000, 5e5, 500, 25_000, 100, 0.005
+
+    def check_sanity(self, params, optimizers):
+        for k in ("means", "scales", "quats", "opacities"):
+            assert k in params and k in optimizers, f"{k} is required"
+
+    def initialize_state(self):
+        return {"binoms": None}
+
+    def step_pre_backward(self, params, optimizers, state, step, info):
+        pass
+
+    def step_post_backward(self, params, optimizers, state, step, info, lr):
+        if self.refine_start_iter < step < self.refine_stop_iter and step % self.refine_every == 0:
+            raise NotImplementedError("MCMC relocation / densification (gsplat.MCMCStrategy refine step) is not part of "
+                                      "the round-1 B200 hot path; run <= 500 iterations per call or enable_pruning=False")
+        with torch.no_grad():
+            opac = torch.sigmoid(params["opacities"].data)
+            sc = torch.exp(params["scales"].data)
+            R = _quat_to_rotmat(params["quats"].data)
+            M = R * sc[:, None, :]
+            cov = M @ M.transpose(1, 2)
+            w = 1.0 / (1.0 + torch.exp(-100.0 * ((1 - opac) - 0.995)))
+            noise = torch.randn_like(params["means"].data) * w[:, None] * lr * self.noise_lr
+            params["means"].data.add_(torch.einsum("nij,nj->ni", cov, noise))
+
+
+def _quat_to_rotmat(q):
+    q = torch.nn.functional.normalize(q, dim=-1)
+    w, x, y, z = q.unbind(-1)
+    return torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                        2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                        2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], dim=-1).reshape(-1, 3, 3)
+
+
+# ------------------------------------------------------------------------------------------- reference API
+def init_3dgs(scene, init_scale=3e-3, lr=1e-3):
+    """gs.py:14-45: splats from the dense MASt3R points (raw scales / opacities, wxyz identity quats, SH = 1 - colour)."""
+    pts = scene.dense_pts_flat
+    colors = scene.dense_cols_flat
+    n = pts.shape[0]
+    g = {
+        "means": pts.detach().clone().float(),
+        "scales": torch.full((n, 3), float(init_scale)),
+        "quats": torch.zeros(n, 4),
+        "opacities": torch.ones(n),
+        "sh0": torch.zeros(n, 1, 3),
+        "shN": torch.zeros(n, 24, 3),
+    }
+    g["quats"][:, 0] = 1.0
+    col = (1 - colors).float().cpu()
+    g["sh0"][:, 0] = col
+    g["shN"][:] = col[:, None, :]
+    scene.gaussians = {k: torch.nn.Parameter(v.to(scene.device).contiguous()) for k, v in g.items()}
+    scene.optimizers = {k: FusedAdam([v], lr=lr) for k, v in scene.gaussians.items()}
+    scene.ssim = None          # the SSIM term lives inside the fused loss kernel (st3r_gs_loss_fwd / _bwd)
+    scene.strategy = MCMCStrategyStub()
+    scene.strategy.check_sanity(scene.gaussians, scene.optimizers)
+    scene.strategy_state = scene.strategy.initialize_state()
+    scene._gs_truth = None
+
+
+def render_3dgs(scene, w2c, intrinsics, width, height):
+    """gs.py:47-88."""
+    gz = scene.gaussians
+    return rasterization(means=gz["means"], quats=gz["quats"], scales=gz["scales"], opacities=gz["opacities"],
+                         colors=gz["shN"], viewmats=w2c, Ks=intrinsics, width=width, height=height, sh_degree=1)
+
+
+def render_3dgs_original(scene, width, height):
+    """gs.py:90-95."""
+    return scene.render_3dgs(scene.w2c, scene.intrinsics, width, height)
+
+
+def _truth_images(scene, device):
+    """Ground-truth images as one [C,H,W,3] device tensor (the reference re-uploads them every step, gs.py:151)."""
+    cached = getattr(scene, "_gs_truth", None)
+    if cached is None or cached.shape[0] != len(scene.imgs):
+        imgs = [torch.as_tensor(im, dtype=torch.float32) for im in scene.imgs]
+        cached = torch.stack(imgs).to(device).contiguous()
+        scene._gs_truth = cached
+    return cached
+
+
+def train_step(params, states, truth, cams, width, height, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+               loss_ssim_fac=0.2, loss_opacity_fac=0.01, loss_scale_fac=0.01, count_blends=False):
+    """One fused iteration of gs.py:143-161 (without the strategy hooks): render all C views, loss, backward, Adam.
+    params: dict of contiguous fp32 device tensors (means, scales, quats, opacities, shN), updated in place;
+    states: dict name -> (exp_avg, exp_avg_sq).  Returns (loss tensor [] on device, frame)."""
+    lib = _lib.load()
+    means, quats, scales, opac, shN = (params[k] for k in ("means", "quats", "scales", "opacities", "shN"))
+    dev = means.device
+    fr = _forward(means, quats, scales, opac, shN, cams, width, height, count_blends)
+    C, N, H, W = fr.C, fr.N, fr.H, fr.W
+    dmaps = torch.empty((C, H, W, 3, 3), dtype=torch.float32, device=dev)
+    sums = torch.zeros((C, 2), dtype=torch.float32, device=dev)
+    reg = torch.zeros(2, dtype=torch.float32, device=dev)
+    v_render = torch.empty_like(fr.render)
+    st = _lib.stream_ptr()
+    with torch.cuda.device(dev):
+        _lib.check(lib.st3r_gs_loss_fwd(_lib.ptr(fr.render), _lib.ptr(truth), C, H, W, _f(loss_ssim_fac),
+                                        _lib.ptr(dmaps), _lib.ptr(sums), st), "st3r_gs_loss_fwd")
+        _lib.check(lib.st3r_gs_loss_bwd(_lib.ptr(fr.render), _lib.ptr(truth), _lib.ptr(dmaps), C, H, W,
+                                        _f(loss_ssim_fac), _lib.ptr(v_render), st), "st3r_gs_loss_bwd")
+    reg_o = C * loss_opacity_fac / max(N, 1)
+    reg_s = C * loss_scale_fac / max(3 * N, 1)
+    vm, vq, vs, vo, vsh = _backward(fr, means, quats, scales, opac, shN, v_render, None, reg_o, reg_s, reg)
+    segs = [(means, vm, *states["means"], N, 3, 3, 3), (scales, vs, *states["scales"], N, 3, 3, 3),
+            (quats, vq, *states["quats"], N, 4, 4, 4), (opac, vo, *states["opacities"], N, 1, 1, 1),
+            (shN, vsh, *states["shN"], N, 12, shN.shape[1] * 3, 12)]
+    adam_step(segs, lr, betas, eps, step)
+    l1 = sums[:, 1] / (3.0 * H * W)
+    ssim = sums[:, 0] / (3.0 * (H - 10) * (W - 10))
+    loss = (l1 * (1 - loss_ssim_fac) + (1 - ssim) * loss_ssim_fac).sum() + reg[0] * reg_o + reg[1] * reg_s
+    fr.grads = dict(means=vm, quats=vq, scales=vs, opacities=vo, sh=vsh)
+    return loss, fr
+
+
+def run_3dgs_optim(scene, iters, enable_pruning=False, loss_ssim_fac=0.2, loss_opacity_fac=0.01, loss_scale_fac=0.01,
+                   verbose=False):
+    """gs.py:97-166.  Returns the list of per-iteration losses (floats)."""
+    gz = scene.gaussians
+    dev = gz["means"].device
+    if dev.type != "cuda":
+        raise RuntimeError("starst3r_b200.gs.run_3dgs_optim needs the splats on a CUDA device (no CPU fallback)")
+    height, width = scene.imgs[0].shape[:2]
+    truth = _truth_images(scene, dev)
+    cams = make_cams(scene.w2c.to(dev), scene.intrinsics.to(dev))
+    names = ("means", "scales", "quats", "opacities", "shN")
+    params = {k: gz[k].data for k in names}
+    states = {}
+    for k in names:
+        opt = scene.optimizers[k]
+        st = opt._st(gz[k]) if isinstance(opt, FusedAdam) else opt.state.setdefault(gz[k], dict(
+            step=torch.zeros(()), exp_avg=torch.zeros_like(gz[k].data), exp_avg_sq=torch.zeros_like(gz[k].data)))
+        states[k] = (st["exp_avg"], st["exp_avg_sq"])
+    group = scene.optimizers["means"].param_groups[0]
+    losses_dev = []
+    pbar = trange(iters, disable=not verbose)
+    for step in pbar:
+        opt_step = int(scene.optimizers["means"]._st(gz["means"])["step"].item()) + 1
+        loss, fr = train_step(params, states, truth, cams, width, height, opt_step, lr=group["lr"],
+                              betas=group["betas"], eps=group["eps"], loss_ssim_fac=loss_ssim_fac,
+                              loss_opacity_fac=loss_opacity_fac, loss_scale_fac=loss_scale_fac)
+        for k in names:
+            scene.optimizers[k]._st(gz[k])["step"] += 1
+        losses_dev.append(loss)
+        if verbose:
+            pbar.set_description(f"Gsplat optimization: loss={loss.item()}")
+        if enable_pruning:
+            scene.strategy.step_post_backward(scene.gaussians, scene.optimizers, scene.strategy_state, step, None, 1e-3)
+    if not losses_dev:
+        return []
+    return torch.stack(losses_dev).cpu().tolist()
