@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the two Starst3r hot paths on B200 (contract: see the task statement / DESIGN.md §6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Headline line (`metric` = Gaussians/s rasterised): one *step* = one 3DGS training iteration of
+starster/gs.py:143-161 on BASELINE.json configs[1] (8 views of 512x512, 200 k Gaussians): render all views,
+L1+SSIM loss, backward, Adam.  `match` carries the second half of BASELINE.json's metric (512x512 image pairs
+matched per second, extract_correspondences of sparse_ga.py:595-630).  Inputs are synthetic.
+At N > 1 every rank renders its own 8 views of the replicated splat (weak scaling), the per-Gaussian gradients
+are all-reduced over NCCL and Adam is replicated; image pairs are independent and shard without a collective.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_GAUSS, N_VIEWS, W, H = 200_000, 8, 512, 512
+MATCH_HW = 512
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_workload(dev, seed):
+    from starst3r_b200 import gs, synth
+    viewmats, Ks = synth.look_at_cameras(N_VIEWS, W, H, device=dev)
+    target = synth.random_splats(N_GAUSS, seed=seed, scale_mode="init", device=dev)
+    with torch.no_grad():
+        truth, _, _ = gs.rasterization(target["means"], target["quats"], target["scales"], target["opacities"],
+                                       target["shN"], viewmats, Ks, W, H)
+    g = torch.Generator().manual_seed(seed + 1)
+    params = {k: v.clone().contiguous() for k, v in target.items()}
+    params["means"] += 0.01 * torch.randn(N_GAUSS, 3, generator=g).to(dev)        # start off the optimum
+    params["shN"] += 0.1 * torch.randn(N_GAUSS, 24, 3, generator=g).to(dev)
+    states = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in params.items()}
+    cams = gs.make_cams(viewmats, Ks)
+    return params, states, truth.clamp(0, 1).contiguous(), cams
+
+
+def allreduce_grads(fr, world):
+    import torch.distributed as dist
+    flat = torch.cat([fr.grads[k].reshape(-1) for k in ("means", "quats", "scales", "opacities", "sh")])
+    dist.all_reduce(flat)
+    off = 0
+    for k in ("means", "quats", "scales", "opacities", "sh"):
+        n = fr.grads[k].numel()
+        fr.grads[k].copy_(flat[off:off + n].view_as(fr.grads[k]))
+        off += n
+
+
+def run_ours(args):
+    from starst3r_b200 import _lib, gs, match, synth
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    hbm_peak, bf16_peak, peak_kind = peaks()
+
+    params, states, truth, cams = make_workload(dev, seed=rank)
+    if world > 1:   # replicated splat: every rank starts from rank 0's parameters
+        for v in params.values():
+            dist.broadcast(v, 0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step_fn(i, prof=False):
+        if world == 1:
+            return gs.train_step(params, states, truth, cams, W, H, i + 1, count_blends=prof)
+        return gs.train_step(params, states, truth, cams, W, H, i + 1, count_blends=prof,
+                             grad_hook=lambda fr: allreduce_grads(fr, world))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_fn(i)
+    barrier()
+    # ---- device-resident timing: K steps, L2 flushed between steps (flush not timed) -----------------
+    launches0 = lib.st3r_launch_count()
+    evs = []
+    gs.PROF = {}
+    with ClockSampler(local) as clk:
+        barrier()
+        for i in range(args.steps):
+            flush.fill_(i & 0xff)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss, fr = step_fn(args.warmup + i, prof=True)
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+    launches = lib.st3r_launch_count() - launches0
+    prof = gs.prof_summary()
+    gs.PROF = None
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = N_GAUSS * N_VIEWS * world / (ms_step * 1e-3)
+    n_isect, n_vis = fr.n_isect, int((fr.radii > 0).sum().item())
+    n_blend = int(fr.n_blend.item()) if fr.n_blend is not None else 0
+
+    # ---- roofline of the dominant kernel (live CUDA events on the launching stream) -------------------
+    px = N_VIEWS * H * W
+    alg_bytes = {   # SURVEY §8d algorithmic bytes per launch
+        "st3r_gs_project": 92 * N_GAUSS * N_VIEWS + 44 * n_vis,
+        "st3r_gs_isect": 12 * n_isect,
+        "st3r_radix_sort_pairs": 24 * n_isect,
+        "st3r_gs_raster_fwd": 40 * n_isect + 20 * px,
+        "st3r_gs_raster_bwd": 40 * n_isect + 24 * px + 36 * n_vis,
+        "st3r_gs_project_bwd": 92 * N_GAUSS * N_VIEWS + 92 * N_GAUSS,
+        "st3r_gs_loss_fwd": 24 * px, "st3r_gs_loss_bwd": 12 * px, "st3r_adam_step": 644 * N_GAUSS,
+    }
+    shares = {k: v[1] / max(v[0], 1) for k, v in prof.items()}
+    top = max(shares, key=shares.get)
+    top_ms = shares[top]
+    achieved = alg_bytes.get(top, 0) / (top_ms * 1e-3) / 1e9
+    roofline = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_kind": peak_kind,
+                "kernel_ms": round(top_ms, 4), "alg_bytes": alg_bytes.get(top, 0),
+                "step_breakdown_ms": {k: round(v, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])}}
+
+    # ---- end-to-end: truth images come from pinned host memory every step, the loss is read back -----
+    truth_host = truth.cpu().pin_memory()
+    truth_dev = torch.empty_like(truth)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        truth_dev.copy_(truth_host, non_blocking=True)
+        if world == 1:
+            loss, _ = gs.train_step(params, states, truth_dev, cams, W, H, args.warmup + args.steps + i + 1)
+        else:
+            loss, _ = gs.train_step(params, states, truth_dev, cams, W, H, args.warmup + args.steps + i + 1,
+                                    grad_hook=lambda fr: allreduce_grads(fr, world))
+        loss.item()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item() / args.steps
+    e2e = {"value": N_GAUSS * N_VIEWS * world / (e2e_ms * 1e-3), "unit": "Gaussians/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": truth_host.numel() * 4, "d2h_bytes_per_step": 4}
+
+    # ---- MATCH: 512x512 image pairs per second (each rank matches its own pairs) ---------------------
+    A, B = synth.descriptor_pair(MATCH_HW, MATCH_HW, seed=rank, device=dev)
+    A2, B2 = synth.descriptor_pair(MATCH_HW, MATCH_HW, seed=100 + rank, device=dev)
+    q = [1 + 9 * torch.rand(MATCH_HW, MATCH_HW, device=dev) for _ in range(4)]
+    feats = [A, B, B2, A2]
+    for _ in range(3):
+        match.extract_correspondences_device(feats, q, 8)
+    barrier()
+    n_pairs = max(4, args.steps)
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record()
+    for _ in range(n_pairs):
+        out = match.extract_correspondences_device(feats, q, 8)
+    m1.record()
+    barrier()
+    tm = torch.tensor([m0.elapsed_time(m1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    pair_ms = tm.item() / n_pairs
+    # e2e: descriptors + confidences from pinned host memory, correspondences read back
+    hfe = [f.cpu().pin_memory() for f in feats]
+    hq = [x.cpu().pin_memory() for x in q]
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    m0.record()
+    for _ in range(n_pairs):
+        xy1, xy2, conf = match.extract_correspondences([f.to(dev, non_blocking=True) for f in hfe],
+                                                       [x.to(dev, non_blocking=True) for x in hq], 8, device=dev)
+        xy1.cpu(), xy2.cpu(), conf.cpu()
+    m1.record()
+    barrier()
+    tm = torch.tensor([m0.elapsed_time(m1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    pair_e2e_ms = tm.item() / n_pairs
+    # algorithmic FLOPs of one pair = 2*M*N*24 summed over the NN calls the reference algorithm makes on this input
+    rows = match_rows(A, B, A2, B2)
+    flops = 2.0 * rows * MATCH_HW * MATCH_HW * 24
+    n_corr = int(out[3].item())
+    match_res = {"metric": "pairs_per_sec_matched_512x512", "value": 1000.0 / pair_ms * world, "unit": "pairs/s",
+                 "ms_per_pair": pair_ms, "correspondences": n_corr,
+                 "e2e": {"value": 1000.0 / pair_e2e_ms * world, "unit": "pairs/s",
+                         "h2d_bytes_per_step": sum(f.numel() for f in hfe + hq) * 4, "d2h_bytes_per_step": n_corr * 36},
+                 "roofline": {"kernel": "nn_tc_kernel (tcgen05 kind::tf32)", "bound": "tensor",
+                              "achieved": round(flops / (pair_ms * 1e-3) / 1e12, 1), "peak": round(bf16_peak / 2, 1),
+                              "unit": "TFLOP/s", "frac": round(flops / (pair_ms * 1e-3) / 1e12 / (bf16_peak / 2), 4),
+                              "peak_kind": peak_kind + " bf16 / 2 (TF32 dense runs at half the bf16 rate)",
+                              "alg_flops_per_pair": flops, "query_rows_per_pair": rows}}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- CPU baseline (oracle port, bounded sample) on rank 0 at N = 1 --------------------------------
+    cpu = cpu_baseline(sample_views=1) if world == 1 and not args.no_cpu else None
+    line = {"metric": "gaussians_per_sec_rasterized", "value": value, "unit": "Gaussians/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "8-view 512x512 synthetic scene, 200k Gaussians, 3DGS train step "
+                                   "(render fwd + L1/SSIM loss + bwd + Adam), BASELINE.json configs[1]",
+                       "views_per_gpu": N_VIEWS, "gaussians": N_GAUSS, "image": [H, W],
+                       "parallelism": f"views sharded dp{world}, gradient all-reduce" if world > 1 else "single GPU",
+                       "l2": "256 MiB flush between timed steps"},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "blends_per_sec": n_blend * world / (shares.get("st3r_gs_raster_fwd", float("nan")) * 1e-3),
+            "blends_per_frame": n_blend, "intersections": n_isect, "visible": n_vis, "loss": float(loss.item()),
+            "match": match_res}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def match_rows(A, B, A2, B2):
+    """Query rows the reference algorithm issues for one image pair (4 seeded searches, fast_nn.py:152-168)."""
+    from starst3r_b200 import match
+    return sum(sum(match.recip_query_rows(P1, P2, 8)) for P1, P2 in ((A, B), (B, A), (A2, B2), (B2, A2)))
+
+
+def cpu_baseline(sample_views=1):
+    """The oracle (CPU port of the reference algorithm: PyTorch fp32 restatement of gsplat 1.4 + torch Adam) timed on
+    the host cores on a bounded sample: `sample_views` of the 8 views, all 200k Gaussians, one full train step."""
+    from oracle import gs_oracle as go
+    from starst3r_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    viewmats, Ks = synth.look_at_cameras(N_VIEWS, W, H)
+    sp = synth.random_splats(N_GAUSS, seed=0, scale_mode="init")
+    params = {k: v.clone() for k, v in sp.items()}
+    states = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in params.items()}
+    truth = torch.rand(sample_views, H, W, 3)
+    t0 = time.time()
+    go.train_step(params, states, truth, viewmats[:sample_views], Ks[:sample_views], W, H, 1)
+    dt = time.time() - t0
+    return {"value": N_GAUSS * sample_views / dt, "unit": "Gaussians/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_views} of {N_VIEWS} views x {N_GAUSS} Gaussians, one train step "
+                      f"(oracle/gs_oracle.py, torch {torch.__version__} CPU), {dt:.1f} s",
+            "seconds": dt}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path for the same metric.  gsplat has no CPU backend and is not
+    installable here, so the oracle port (PyTorch restatement of the algorithm + torch Adam) stands in."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(max(1, min(args.steps, 2))):
+        vals.append(cpu_baseline(sample_views=1))
+    best = max(vals, key=lambda d: d["value"])
+    line = {"impl": "reference", "metric": "gaussians_per_sec_rasterized", "value": best["value"],
+            "unit": "Gaussians/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": len(vals), "warmup": 0,
+            "ms_per_step": best["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "8-view 512x512 synthetic scene, 200k Gaussians, 3DGS train step, BASELINE.json "
+                                   "configs[1]; each step = bounded sample of 1 view"},
+            "cpu_baseline": best,
+            "e2e": {"value": best["value"], "unit": "Gaussians/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback")
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

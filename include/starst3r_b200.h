@@ -47,6 +47,8 @@ typedef struct CUstream_st* cudaStream_t;
 ST3R_API const char* st3r_last_error(void);
 ST3R_API int st3r_abi_version(void);
 ST3R_API int st3r_device_sm_count(void);
+/* Number of CUDA kernels this library has launched in this process (all entry points). */
+ST3R_API uint64_t st3r_launch_count(void);
 
 /* ------------------------------------------------------------------ MATCH */
 
@@ -168,10 +170,11 @@ ST3R_API int st3r_gs_loss_bwd(const float* render, const float* truth, const flo
 
 /* torch.optim.Adam step over up to 8 tensors in one launch.  Arrays are HOST arrays of device pointers /
  * sizes; tensor i is rows[i] x cols[i] with leading dimensions ld_param[i] (param and both moments) and
- * ld_grad[i].  step is 1-based. */
+ * ld_grad[i].  step is 1-based; the hyper-parameters are doubles (torch keeps them as Python floats and rounds
+ * 1 - beta to fp32 once). */
 ST3R_API int st3r_adam_step(int n_seg, float* const* h_params, const float* const* h_grads, float* const* h_exp_avg,
                    float* const* h_exp_avg_sq, const int* h_rows, const int* h_cols, const int* h_ld_param,
-                   const int* h_ld_grad, float lr, float beta1, float beta2, float eps, int step,
+                   const int* h_ld_grad, double lr, double beta1, double beta2, double eps, int step,
                    cudaStream_t stream);
 
 #ifdef __cplusplus

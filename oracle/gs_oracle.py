@@ -153,17 +153,17 @@ def isect_tiles(means2d, radii, depths, tile_size, tile_w, tile_h):
     tiles_per_gauss = ((y1 - y0) * (x1 - x0)).astype(np.int32)
     tile_n_bits = int(math.floor(math.log2(tile_w * tile_h))) + 1 if tile_w * tile_h > 0 else 1
     depth_bits = d.view(np.int32).astype(np.int64) & 0xffffffff
-    ids, flat = [], []
     cam_np = cam.numpy()
-    for k in range(len(cam_np)):
-        if tiles_per_gauss[k] == 0:
-            continue
-        yy, xx = np.mgrid[y0[k]:y1[k], x0[k]:x1[k]]
-        tile_id = (yy * tile_w + xx).reshape(-1).astype(np.int64)
-        ids.append((np.int64(cam_np[k]) << (32 + tile_n_bits)) | (tile_id << 32) | depth_bits[k])
-        flat.append(np.full(tile_id.shape, k, np.int32))
-    ids = np.concatenate(ids) if ids else np.zeros(0, np.int64)
-    flat = np.concatenate(flat) if flat else np.zeros(0, np.int32)
+    # emit (row-major over y then x) every covered tile of every packed Gaussian, vectorised
+    n_t = tiles_per_gauss.astype(np.int64)
+    flat = np.repeat(np.arange(len(cam_np), dtype=np.int32), n_t)
+    first = np.cumsum(n_t) - n_t
+    local = np.arange(int(n_t.sum()), dtype=np.int64) - np.repeat(first, n_t)
+    wdt = np.repeat(x1 - x0, n_t)
+    yy = np.repeat(y0, n_t) + local // np.maximum(wdt, 1)
+    xx = np.repeat(x0, n_t) + local % np.maximum(wdt, 1)
+    tile_id = yy * tile_w + xx
+    ids = (np.repeat(cam_np.astype(np.int64), n_t) << (32 + tile_n_bits)) | (tile_id << 32) | np.repeat(depth_bits, n_t)
     order = np.argsort(ids, kind="stable")
     return dict(camera_ids=cam_np.astype(np.int64), gaussian_ids=gau.numpy().astype(np.int64),
                 tiles_per_gauss=tiles_per_gauss, isect_ids=ids[order], flatten_ids=flat[order],

@@ -5,6 +5,7 @@
 #include "../../include/starst3r_b200.h"
 
 static thread_local char g_err[512] = "";
+unsigned long long g_st3r_launches = 0;
 
 void st3r_set_error(const char* fmt, ...) {
   va_list ap;
@@ -27,4 +28,5 @@ extern "C" {
 const char* st3r_last_error(void) { return g_err; }
 int st3r_abi_version(void) { return ST3R_ABI_VERSION; }
 int st3r_device_sm_count(void) { return st3r_num_sms(); }
+uint64_t st3r_launch_count(void) { return g_st3r_launches; }
 }

@@ -31,7 +31,13 @@ void st3r_set_error(const char* fmt, ...);
     }                                                                                \
   } while (0)
 
-#define ST3R_CHECK_LAUNCH() ST3R_CHECK_CUDA(cudaGetLastError())
+// Counts every kernel this library launches (bench.py reports it as gpu_launches).
+extern unsigned long long g_st3r_launches;
+#define ST3R_CHECK_LAUNCH()                  \
+  do {                                       \
+    ++g_st3r_launches;                       \
+    ST3R_CHECK_CUDA(cudaGetLastError());     \
+  } while (0)
 
 static inline size_t st3r_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

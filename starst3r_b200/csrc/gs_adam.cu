@@ -17,7 +17,8 @@ struct AdamSeg {
 struct AdamSegs { AdamSeg s[8]; int n; };
 
 __global__ void __launch_bounds__(256)
-adam_kernel(AdamSegs segs, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps) {
+adam_kernel(AdamSegs segs, float lr_over_bc1, float inv_sqrt_bc2, float one_minus_b1, float b2, float one_minus_b2,
+            float eps) {
   const AdamSeg sg = segs.s[blockIdx.y];
   const long long total = (long long)sg.rows * sg.cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -25,8 +26,8 @@ adam_kernel(AdamSegs segs, float lr_over_bc1, float inv_sqrt_bc2, float b1, floa
     const size_t ip = (size_t)r * sg.ld_p + c, ig = (size_t)r * sg.ld_g + c;
     const float g = sg.g[ig];
     float m = sg.m[ip], v = sg.v[ip];
-    m = m + (g - m) * (1.0f - b1);                 // exp_avg.lerp_(grad, 1 - beta1)
-    v = v * b2 + (1.0f - b2) * g * g;              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    m = m + (g - m) * one_minus_b1;                  // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * b2 + one_minus_b2 * g * g;               // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
     const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
     sg.p[ip] = sg.p[ip] - lr_over_bc1 * (m / denom);
     sg.m[ip] = m;
@@ -37,7 +38,7 @@ adam_kernel(AdamSegs segs, float lr_over_bc1, float inv_sqrt_bc2, float b1, floa
 
 extern "C" int st3r_adam_step(int n_seg, float* const* params, const float* const* grads, float* const* exp_avg,
                               float* const* exp_avg_sq, const int* rows, const int* cols, const int* ld_param,
-                              const int* ld_grad, float lr, float beta1, float beta2, float eps, int step,
+                              const int* ld_grad, double lr, double beta1, double beta2, double eps, int step,
                               cudaStream_t stream) {
   ST3R_CHECK_ARG(n_seg >= 0 && n_seg <= 8 && step >= 1, "st3r_adam_step: bad args (n_seg <= 8, step >= 1)");
   if (n_seg == 0) return ST3R_OK;
@@ -53,14 +54,16 @@ extern "C" int st3r_adam_step(int n_seg, float* const* params, const float* cons
     if (t > max_total) max_total = t;
   }
   if (max_total == 0) return ST3R_OK;
-  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  const float lr_over_bc1 = (float)((double)lr / bc1);
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  const float lr_over_bc1 = (float)(lr / bc1);
   const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   int blocks = (int)((max_total + 255) / 256);
   int cap = st3r_num_sms() * 16;
   if (blocks > cap) blocks = cap;
   dim3 grid(blocks, n_seg);
-  adam_kernel<<<grid, 256, 0, stream>>>(segs, lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps);
+  // torch evaluates 1 - beta in double and rounds once to fp32
+  adam_kernel<<<grid, 256, 0, stream>>>(segs, lr_over_bc1, inv_sqrt_bc2, (float)(1.0 - beta1), (float)beta2,
+                                        (float)(1.0 - beta2), (float)eps);
   ST3R_CHECK_LAUNCH();
   return ST3R_OK;
 }

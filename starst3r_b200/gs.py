@@ -20,6 +20,36 @@ TILE = 16
 EPS2D, NEAR, FAR, RADIUS_CLIP = 0.3, 0.01, 1e10, 0.0
 
 
+class _Prof:
+    """Optional per-entry-point CUDA-event timing (bench.py's roofline leg): `gs.PROF = {}` turns it on; each C-ABI
+    call then appends (start, end) events on the launching stream under its name."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROF is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROF is not None:
+            self.e1.record()
+            PROF.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
+
+
+PROF = None
+
+
+def prof_summary():
+    """{name: (calls, total_ms)} of the events collected so far (synchronises)."""
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (PROF or {}).items()}
+
+
 def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -64,13 +94,15 @@ def _forward(means, quats, scales, opacities, shN, cams, width, height, count_bl
     fr.n_isect_dev = torch.zeros(1, dtype=torch.int32, device=dev)
     st = _lib.stream_ptr()
     with torch.cuda.device(dev):
-        _lib.check(lib.st3r_gs_project(_lib.ptr(means), _lib.ptr(quats), _lib.ptr(scales), _lib.ptr(opacities),
-                                       _lib.ptr(shN), sh_coeffs, _lib.ptr(cams), N, C, fr.W, fr.H, TILE, _f(EPS2D),
-                                       _f(NEAR), _f(FAR), _f(RADIUS_CLIP), _lib.ptr(fr.radii), _lib.ptr(fr.geomA),
-                                       _lib.ptr(fr.geomB), _lib.ptr(fr.rgb), _lib.ptr(fr.tiles), st), "st3r_gs_project")
+        with _Prof("st3r_gs_project"):
+            _lib.check(lib.st3r_gs_project(_lib.ptr(means), _lib.ptr(quats), _lib.ptr(scales), _lib.ptr(opacities),
+                                           _lib.ptr(shN), sh_coeffs, _lib.ptr(cams), N, C, fr.W, fr.H, TILE, _f(EPS2D),
+                                           _f(NEAR), _f(FAR), _f(RADIUS_CLIP), _lib.ptr(fr.radii), _lib.ptr(fr.geomA),
+                                           _lib.ptr(fr.geomB), _lib.ptr(fr.rgb), _lib.ptr(fr.tiles), st), "st3r_gs_project")
         ws = _ws(lib.st3r_scan_ws_bytes(C * N), dev)
-        _lib.check(lib.st3r_exclusive_scan_i32(_lib.ptr(fr.tiles), _lib.ptr(fr.cum), C * N, _lib.ptr(fr.n_isect_dev),
-                                               _lib.ptr(ws), ws.numel(), st), "st3r_exclusive_scan_i32")
+        with _Prof("st3r_exclusive_scan_i32"):
+            _lib.check(lib.st3r_exclusive_scan_i32(_lib.ptr(fr.tiles), _lib.ptr(fr.cum), C * N, _lib.ptr(fr.n_isect_dev),
+                                                   _lib.ptr(ws), ws.numel(), st), "st3r_exclusive_scan_i32")
         # One host read per frame sizes the intersection buffers exactly (gsplat does the same).
         n_isect = int(fr.n_isect_dev.item())
         fr.n_isect = n_isect
@@ -79,24 +111,28 @@ def _forward(means, quats, scales, opacities, shN, cams, width, height, count_bl
         fr.vals = torch.empty(cap, dtype=torch.int32, device=dev)
         keys_alt = torch.empty(cap, dtype=torch.int64, device=dev)
         vals_alt = torch.empty(cap, dtype=torch.int32, device=dev)
-        _lib.check(lib.st3r_gs_isect(_lib.ptr(fr.radii), _lib.ptr(fr.geomA), _lib.ptr(fr.cum), N, C, fr.W, fr.H, TILE,
-                                     _lib.ptr(fr.keys), _lib.ptr(fr.vals), n_isect, st), "st3r_gs_isect")
+        with _Prof("st3r_gs_isect"):
+            _lib.check(lib.st3r_gs_isect(_lib.ptr(fr.radii), _lib.ptr(fr.geomA), _lib.ptr(fr.cum), N, C, fr.W, fr.H, TILE,
+                                         _lib.ptr(fr.keys), _lib.ptr(fr.vals), n_isect, st), "st3r_gs_isect")
         ws = _ws(lib.st3r_radix_sort_ws_bytes(n_isect), dev)
         bits = lib.st3r_gs_sort_bits(C, fr.W, fr.H, TILE)
-        _lib.check(lib.st3r_radix_sort_pairs(_lib.ptr(fr.keys), _lib.ptr(fr.vals), _lib.ptr(keys_alt),
-                                             _lib.ptr(vals_alt), _lib.ptr(fr.n_isect_dev), n_isect, 0, bits,
-                                             _lib.ptr(ws), ws.numel(), st), "st3r_radix_sort_pairs")
+        with _Prof("st3r_radix_sort_pairs"):
+            _lib.check(lib.st3r_radix_sort_pairs(_lib.ptr(fr.keys), _lib.ptr(fr.vals), _lib.ptr(keys_alt),
+                                                 _lib.ptr(vals_alt), _lib.ptr(fr.n_isect_dev), n_isect, 0, bits,
+                                                 _lib.ptr(ws), ws.numel(), st), "st3r_radix_sort_pairs")
         fr.offsets = torch.empty(max(C * fr.tile_w * fr.tile_h, 1), dtype=torch.int32, device=dev)
-        _lib.check(lib.st3r_gs_offsets(_lib.ptr(fr.keys), _lib.ptr(fr.n_isect_dev), n_isect, C, fr.W, fr.H, TILE,
-                                       _lib.ptr(fr.offsets), st), "st3r_gs_offsets")
+        with _Prof("st3r_gs_offsets"):
+            _lib.check(lib.st3r_gs_offsets(_lib.ptr(fr.keys), _lib.ptr(fr.n_isect_dev), n_isect, C, fr.W, fr.H, TILE,
+                                           _lib.ptr(fr.offsets), st), "st3r_gs_offsets")
         fr.render = torch.empty((C, fr.H, fr.W, 3), dtype=torch.float32, device=dev)
         fr.alphas = torch.empty((C, fr.H, fr.W), dtype=torch.float32, device=dev)
         fr.last_ids = torch.empty((C, fr.H, fr.W), dtype=torch.int32, device=dev)
         fr.n_blend = torch.zeros(1, dtype=torch.int64, device=dev) if count_blends else None
-        _lib.check(lib.st3r_gs_raster_fwd(_lib.ptr(fr.offsets), _lib.ptr(fr.n_isect_dev), _lib.ptr(fr.vals),
-                                          _lib.ptr(fr.geomA), _lib.ptr(fr.geomB), _lib.ptr(fr.rgb), C, fr.W, fr.H, TILE,
-                                          _lib.ptr(fr.render), _lib.ptr(fr.alphas), _lib.ptr(fr.last_ids),
-                                          _lib.ptr(fr.n_blend), st), "st3r_gs_raster_fwd")
+        with _Prof("st3r_gs_raster_fwd"):
+            _lib.check(lib.st3r_gs_raster_fwd(_lib.ptr(fr.offsets), _lib.ptr(fr.n_isect_dev), _lib.ptr(fr.vals),
+                                              _lib.ptr(fr.geomA), _lib.ptr(fr.geomB), _lib.ptr(fr.rgb), C, fr.W, fr.H, TILE,
+                                              _lib.ptr(fr.render), _lib.ptr(fr.alphas), _lib.ptr(fr.last_ids),
+                                              _lib.ptr(fr.n_blend), st), "st3r_gs_raster_fwd")
     return fr
 
 
@@ -115,17 +151,19 @@ def _backward(fr, means, quats, scales, opacities, shN, v_render, v_alphas, reg_
     v_sh = torch.empty((N, 4, 3), dtype=torch.float32, device=dev)
     st = _lib.stream_ptr()
     with torch.cuda.device(dev):
-        _lib.check(lib.st3r_gs_raster_bwd(_lib.ptr(fr.offsets), _lib.ptr(fr.n_isect_dev), _lib.ptr(fr.vals),
-                                          _lib.ptr(fr.geomA), _lib.ptr(fr.geomB), _lib.ptr(fr.rgb), C, fr.W, fr.H, TILE,
-                                          _lib.ptr(fr.alphas), _lib.ptr(fr.last_ids), _lib.ptr(v_render),
-                                          _lib.ptr(v_alphas), _lib.ptr(v_geom[0]), _lib.ptr(v_geom[1]),
-                                          _lib.ptr(v_geom[2]), st), "st3r_gs_raster_bwd")
-        _lib.check(lib.st3r_gs_project_bwd(_lib.ptr(means), _lib.ptr(quats), _lib.ptr(scales), _lib.ptr(opacities),
-                                           _lib.ptr(shN), fr.sh_coeffs, _lib.ptr(fr.cams), N, C, fr.W, fr.H, _f(EPS2D),
-                                           _f(NEAR), _f(FAR), _f(RADIUS_CLIP), _lib.ptr(fr.radii), _lib.ptr(v_geom[0]),
-                                           _lib.ptr(v_geom[1]), _lib.ptr(v_geom[2]), _f(reg_opac), _f(reg_scale),
-                                           _lib.ptr(v_means), _lib.ptr(v_quats), _lib.ptr(v_scales), _lib.ptr(v_opac),
-                                           _lib.ptr(v_sh), _lib.ptr(reg_sums), st), "st3r_gs_project_bwd")
+        with _Prof("st3r_gs_raster_bwd"):
+            _lib.check(lib.st3r_gs_raster_bwd(_lib.ptr(fr.offsets), _lib.ptr(fr.n_isect_dev), _lib.ptr(fr.vals),
+                                              _lib.ptr(fr.geomA), _lib.ptr(fr.geomB), _lib.ptr(fr.rgb), C, fr.W, fr.H, TILE,
+                                              _lib.ptr(fr.alphas), _lib.ptr(fr.last_ids), _lib.ptr(v_render),
+                                              _lib.ptr(v_alphas), _lib.ptr(v_geom[0]), _lib.ptr(v_geom[1]),
+                                              _lib.ptr(v_geom[2]), st), "st3r_gs_raster_bwd")
+        with _Prof("st3r_gs_project_bwd"):
+            _lib.check(lib.st3r_gs_project_bwd(_lib.ptr(means), _lib.ptr(quats), _lib.ptr(scales), _lib.ptr(opacities),
+                                               _lib.ptr(shN), fr.sh_coeffs, _lib.ptr(fr.cams), N, C, fr.W, fr.H, _f(EPS2D),
+                                               _f(NEAR), _f(FAR), _f(RADIUS_CLIP), _lib.ptr(fr.radii), _lib.ptr(v_geom[0]),
+                                               _lib.ptr(v_geom[1]), _lib.ptr(v_geom[2]), _f(reg_opac), _f(reg_scale),
+                                               _lib.ptr(v_means), _lib.ptr(v_quats), _lib.ptr(v_scales), _lib.ptr(v_opac),
+                                               _lib.ptr(v_sh), _lib.ptr(reg_sums), st), "st3r_gs_project_bwd")
     return v_means, v_quats, v_scales, v_opac, v_sh
 
 
@@ -232,8 +270,9 @@ def adam_step(segments, lr, betas, eps, step):
     rows, cols = II(*[int(s[4]) for s in segments]), II(*[int(s[5]) for s in segments])
     ldp, ldg = II(*[int(s[6]) for s in segments]), II(*[int(s[7]) for s in segments])
     dev = segments[0][0].device
-    with torch.cuda.device(dev):
-        rc = lib.st3r_adam_step(n, p, g, m, v, rows, cols, ldp, ldg, _f(lr), _f(betas[0]), _f(betas[1]), _f(eps),
+    with torch.cuda.device(dev), _Prof("st3r_adam_step"):
+        rc = lib.st3r_adam_step(n, p, g, m, v, rows, cols, ldp, ldg, ctypes.c_double(lr), ctypes.c_double(betas[0]),
+                                ctypes.c_double(betas[1]), ctypes.c_double(eps),
                                 int(step), _lib.stream_ptr())
     _lib.check(rc, "st3r_adam_step")
 
@@ -328,7 +367,7 @@ def _truth_images(scene, device):
 
 
 def train_step(params, states, truth, cams, width, height, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
-               loss_ssim_fac=0.2, loss_opacity_fac=0.01, loss_scale_fac=0.01, count_blends=False):
+               loss_ssim_fac=0.2, loss_opacity_fac=0.01, loss_scale_fac=0.01, count_blends=False, grad_hook=None):
     """One fused iteration of gs.py:143-161 (without the strategy hooks): render all C views, loss, backward, Adam.
     params: dict of contiguous fp32 device tensors (means, scales, quats, opacities, shN), updated in place;
     states: dict name -> (exp_avg, exp_avg_sq).  Returns (loss tensor [] on device, frame)."""
@@ -343,13 +382,18 @@ def train_step(params, states, truth, cams, width, height, step, lr=1e-3, betas=
     v_render = torch.empty_like(fr.render)
     st = _lib.stream_ptr()
     with torch.cuda.device(dev):
-        _lib.check(lib.st3r_gs_loss_fwd(_lib.ptr(fr.render), _lib.ptr(truth), C, H, W, _f(loss_ssim_fac),
-                                        _lib.ptr(dmaps), _lib.ptr(sums), st), "st3r_gs_loss_fwd")
-        _lib.check(lib.st3r_gs_loss_bwd(_lib.ptr(fr.render), _lib.ptr(truth), _lib.ptr(dmaps), C, H, W,
-                                        _f(loss_ssim_fac), _lib.ptr(v_render), st), "st3r_gs_loss_bwd")
+        with _Prof("st3r_gs_loss_fwd"):
+            _lib.check(lib.st3r_gs_loss_fwd(_lib.ptr(fr.render), _lib.ptr(truth), C, H, W, _f(loss_ssim_fac),
+                                            _lib.ptr(dmaps), _lib.ptr(sums), st), "st3r_gs_loss_fwd")
+        with _Prof("st3r_gs_loss_bwd"):
+            _lib.check(lib.st3r_gs_loss_bwd(_lib.ptr(fr.render), _lib.ptr(truth), _lib.ptr(dmaps), C, H, W,
+                                            _f(loss_ssim_fac), _lib.ptr(v_render), st), "st3r_gs_loss_bwd")
     reg_o = C * loss_opacity_fac / max(N, 1)
     reg_s = C * loss_scale_fac / max(3 * N, 1)
     vm, vq, vs, vo, vsh = _backward(fr, means, quats, scales, opac, shN, v_render, None, reg_o, reg_s, reg)
+    fr.grads = dict(means=vm, quats=vq, scales=vs, opacities=vo, sh=vsh)
+    if grad_hook is not None:      # multi-GPU: all-reduce of the per-Gaussian gradients (views are sharded)
+        grad_hook(fr)
     segs = [(means, vm, *states["means"], N, 3, 3, 3), (scales, vs, *states["scales"], N, 3, 3, 3),
             (quats, vq, *states["quats"], N, 4, 4, 4), (opac, vo, *states["opacities"], N, 1, 1, 1),
             (shN, vsh, *states["shN"], N, 12, shN.shape[1] * 3, 12)]
@@ -357,7 +401,6 @@ def train_step(params, states, truth, cams, width, height, step, lr=1e-3, betas=
     l1 = sums[:, 1] / (3.0 * H * W)
     ssim = sums[:, 0] / (3.0 * (H - 10) * (W - 10))
     loss = (l1 * (1 - loss_ssim_fac) + (1 - ssim) * loss_ssim_fac).sum() + reg[0] * reg_o + reg[1] * reg_s
-    fr.grads = dict(means=vm, quats=vq, scales=vs, opacities=vo, sh=vsh)
     return loss, fr
 
 

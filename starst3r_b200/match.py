@@ -238,6 +238,35 @@ def fast_reciprocal_NNs(pts1, pts2, subsample_or_initxy1=8, ret_xy=True, pixel_t
     return xy1, xy2
 
 
+def recip_query_rows(pts1, pts2, subsample=8, max_iter=10, impl="auto"):
+    """Diagnostic: the number of query rows each NN call of fast_reciprocal_NNs issues on this input (the sizes
+    of the not-yet-converged set, fast_nn.py:152-168), measured by driving the CUDA NN kernel from the host loop.
+    bench.py uses the sum as the algorithmic FLOP count (2 * rows * H*W * d)."""
+    device = pts1.device
+    H1, W1, D = pts1.shape
+    F1, F2 = pts1.reshape(-1, D).float().contiguous(), pts2.reshape(-1, D).float().contiguous()
+    S = subsample
+    y1, x1 = np.mgrid[S // 2:H1:S, S // 2:W1:S].reshape(2, -1)
+    xy1 = torch.from_numpy(np.unique(x1 + W1 * y1).astype(np.int64)).to(device)
+    xy2 = torch.full_like(xy1, -1)
+    old1, old2 = xy1.clone(), xy2.clone()
+    notyet = torch.ones_like(xy1, dtype=torch.bool)
+    rows = []
+    for _ in range(max_iter):
+        if not bool(notyet.any()):
+            break
+        rows.append(int(notyet.sum()))
+        xy2[notyet] = nn_argmax(F1[xy1[notyet]], F2, impl=impl).long()
+        notyet &= old2 != xy2
+        rows.append(int(notyet.sum()))
+        if bool(notyet.any()):
+            xy1[notyet] = nn_argmax(F2[xy2[notyet]], F1, impl=impl).long()
+        notyet &= old1 != xy1
+        old2.copy_(xy2)
+        old1.copy_(xy1)
+    return rows
+
+
 def extract_correspondences_device(feats, qonfs, subsample=8, impl="auto", max_iter=10):
     """Device-resident form: returns (xy1 [cap,2] i64, xy2 [cap,2] i64, conf [cap] f32, n [1] i32) without
     synchronising; rows >= n are undefined.  Used by the pair-sharded pipeline and by bench.py."""

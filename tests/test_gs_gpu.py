@@ -184,8 +184,8 @@ def test_fused_adam_vs_torch(cuda_device):
         opt.step()
     assert torch.allclose(mine.data.cpu(), ref.data, atol=1e-7, rtol=1e-6)
     st = opt.state[mine]
-    assert torch.allclose(st["exp_avg"].cpu(), opt_ref.state[ref]["exp_avg"], rtol=1e-6, atol=1e-12)
-    assert torch.allclose(st["exp_avg_sq"].cpu(), opt_ref.state[ref]["exp_avg_sq"], rtol=1e-6, atol=1e-20)
+    assert torch.allclose(st["exp_avg"].cpu(), opt_ref.state[ref]["exp_avg"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(st["exp_avg_sq"].cpu(), opt_ref.state[ref]["exp_avg_sq"], rtol=1e-5, atol=1e-9)
 
 
 # ------------------------------------------------------------------------------------------ full train step
