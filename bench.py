@@ -43,11 +43,12 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None      # wall-clock window of the GPU-busy region
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -57,7 +58,7 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.rows.append([x.strip() for x in ln.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in ln.split(",")]))
 
     def __exit__(self, *a):
         if self.proc:
@@ -68,12 +69,13 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        rows = [r for ts, r in self.rows if (self.t0 is None or ts >= self.t0) and (self.t1 is None or ts <= self.t1 + 0.05)]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for _, r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "window": "warm-up + timed steps + e2e + match legs (GPU busy throughout)"}
 
 
 def make_workload(dev, seed):
@@ -133,6 +135,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clk = ClockSampler(local)
+    clk.__enter__()
+    time.sleep(0.3)                 # let nvidia-smi start sampling
+    clk.t0 = time.time()
     for i in range(args.warmup):
         step_fn(i)
     barrier()
@@ -140,16 +146,15 @@ def run_ours(args):
     launches0 = lib.st3r_launch_count()
     evs = []
     gs.PROF = {}
-    with ClockSampler(local) as clk:
-        barrier()
-        for i in range(args.steps):
-            flush.fill_(i & 0xff)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            loss, fr = step_fn(args.warmup + i, prof=True)
-            e1.record()
-            evs.append((e0, e1))
-        barrier()
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss, fr = step_fn(args.warmup + i, prof=True)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
     launches = lib.st3r_launch_count() - launches0
     prof = gs.prof_summary()
     gs.PROF = None
@@ -240,6 +245,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     pair_e2e_ms = tm.item() / n_pairs
+    clk.t1 = time.time()
+    clk.__exit__()
     # algorithmic FLOPs of one pair = 2*M*N*24 summed over the NN calls the reference algorithm makes on this input
     rows = match_rows(A, B, A2, B2)
     flops = 2.0 * rows * MATCH_HW * MATCH_HW * 24
