@@ -177,6 +177,72 @@ ST3R_API int st3r_adam_step(int n_seg, float* const* h_params, const float* cons
                    const int* h_ld_grad, double lr, double beta1, double beta2, double eps, int step,
                    cudaStream_t stream);
 
+/* ------------------------------------------------------------------ ALIGN
+ * Fused sparse-global-alignment optimiser: optimize_loop of starster/reconstruct.py:371-406 with
+ * make_K_cam_depth (:209-261), loss_3d / loss_2d / loss_dust3r (:311-369), make_pts3d / reproj2d
+ * (mast3r/cloud_opt/sparse_ga.py:469-501,977-981), gamma_loss and the Adam(lr=1, betas=(.9,.9)) step with
+ * quaternion re-normalisation (:373-395).  All arrays are device pointers; the problem description is the
+ * flattened form of the reference's condense_data output (sparse_ga.py:729-814). */
+typedef struct {
+  float W, H;            /* image size in pixels                                   (imsizes)          */
+  float base_focal;      /* Weiszfeld focal of the canonical point map             (base_focals)      */
+  float median;          /* median of the core depth map before normalisation      (median_depths)    */
+  float min_focal, max_focal; /* 0.25 / 10 x image diagonal                        (reconstruct.py:203-205) */
+  int32_t core_off, n_core;   /* slice of `core` owned by this image                                  */
+} St3rAlignImgConst;
+
+typedef struct {
+  int32_t n_img;
+  const St3rAlignImgConst* img_const;   /* [n_img] */
+  const float* core;                    /* concatenated core depth maps, each divided by its median */
+  int32_t n_core_total;
+  int32_t root;                         /* MST root and BFS edge list (parent, child), sparse_ga.py:991-1009 */
+  const int32_t* edges;                 /* [2 * (n_img - 1)] */
+  /* anchors (sparse_ga.py:770-779): pixel (u, v), core-depth index, depth-ratio offset */
+  int32_t n_anchor;
+  const int32_t* anc_img; const float* anc_uv; const int32_t* anc_k; const float* anc_off;
+  /* loss_3d entries: pairs of anchors + confidence; norm3 = sum of confidences */
+  int32_t n3; const int32_t* e3_a1; const int32_t* e3_a2; const float* e3_conf; float norm3;
+  /* loss_2d entries: pixel in image img1, the matching anchor in the other image; norm2 = sum conf */
+  int32_t n2; const int32_t* e2_img1; const float* e2_pix; const int32_t* e2_a2; const float* e2_conf; float norm2;
+  /* loss_dust3r entries: anchor of img1, regression target (in img2's camera frame), confidence */
+  int32_t nd; const int32_t* ed_a1; const int32_t* ed_img2; const float* ed_tgt; const float* ed_conf; float normd;
+} St3rAlignProblem;
+
+ST3R_API size_t st3r_align_ws_bytes(int n_img);
+ST3R_API int st3r_align_cam_floats(void);          /* floats per camera record in cam_out: R(9) t(3) f cx cy A B bf pad(2) */
+ST3R_API int st3r_align_img_const_bytes(void);
+/* Runs `niter` iterations (mode 0: loss_3d, mode 1: loss_2d; both + dust3r_w * loss_dust3r) on the raw parameters
+ * pp [N,2] (normalised principal points), log_focal [N], quat [N,4] (XYZW), trans [N,3], log_size [N]; Adam moments
+ * adam_m / adam_v are [N,11] in that parameter order (zero them to start a phase).  train_mask bits: 1 pp, 2
+ * log_focal, 4 quat, 8 trans, 16 log_size.  h_lr is a HOST array [niter] (cosine schedule).  Outputs (device,
+ * optional): loss_hist [niter]; cam_out [N, st3r_align_cam_floats()] = camera records of the LAST forward (the
+ * reference returns the state before the final step, reconstruct.py:379-380,405-406); pts3d_out [n_anchor,3];
+ * depth_out [n_core_total]; grad_out [N,11] = parameter gradients of the last iteration.  niter = 0 only evaluates. */
+ST3R_API int st3r_align_optimize(const St3rAlignProblem* prob, float* pp, float* log_focal, float* quat, float* trans,
+                        float* log_size, float* adam_m, float* adam_v, int mode, int train_mask, float gamma,
+                        float gamma_dust3r, float dust3r_w, const float* h_lr, int niter, double beta1,
+                        double beta2, double eps, float* loss_hist, float* cam_out, float* pts3d_out,
+                        float* depth_out, float* grad_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+/* canonical_view(ptmaps11, confs11, subsample, mode='avg-angle') (sparse_ga.py:817-855): ptmaps [P,H,W,3], confs
+ * [P,H,W] -> canon [H,W,3], canon2 [H,W] (relative depth w.r.t. the 8x8 block centre), cconf [H,W]. */
+ST3R_API int st3r_canonical_view(const float* ptmaps, const float* confs, int n_entries, int H, int W, int subsample,
+                        float* canon, float* canon2, float* cconf, cudaStream_t stream);
+/* estimate_focal_knowing_depth(canon, pp = image centre, 'weiszfeld', min_focal, max_focal) (dust3r/post_process.py:
+ * 12-60) for n_img stacked [H,W,3] point maps. */
+ST3R_API int st3r_focal_weiszfeld(const float* canon, int n_img, int H, int W, float min_focal, float max_focal, float* focal_out,
+                         cudaStream_t stream);
+/* SparseGA.get_dense_pts3d for one image (sparse_ga.py:70-93): every pixel anchored to its block's core depth.
+ * h_cam2w (16 floats) and h_K (9 floats) are HOST arrays. */
+ST3R_API int st3r_dense_points(const float* canon2, const float* core_depth, const float* h_cam2w, const float* h_K,
+                      float base_focal, int H, int W, int subsample, float* pts3d, float* depth, cudaStream_t stream);
+/* clean_pointcloud (dust3r/cloud_opt/base_opt.py:369-405) for n_img same-size views: pts3d [N,HW,3], confs [N,HW]
+ * (updated in place), depthmaps [N,HW], cams [N, st3r_clean_cam_floats()] = world->camera R (9), t (3), K (9). */
+ST3R_API int st3r_clean_cam_floats(void);
+ST3R_API int st3r_clean_pointcloud(const float* pts3d, float* confs, const float* depthmaps, const float* cams, int n_img, int H,
+                          int W, float tol, float bad_conf, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

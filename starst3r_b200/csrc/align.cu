@@ -1,0 +1,450 @@
+// Fused sparse global alignment optimiser (ALIGN hot loop).
+//
+// Replaces optimize_loop of starster/reconstruct.py:371-406 with its nested make_K_cam_depth (:209-261),
+// loss_3d (:325-353), loss_2d (:355-369), loss_dust3r (:311-323), make_pts3d / reproj2d
+// (mast3r/cloud_opt/sparse_ga.py:469-501,977-981), gamma_loss (cloud_opt/utils/losses.py:19-28) and the
+// torch.optim.Adam(lr=1, betas=(.9,.9)) step + quaternion re-normalisation (:373-395).
+// The reference spends ~200 tiny autograd kernels and one host sync per iteration; here one iteration is
+// three launches and the whole niter loop is enqueued without touching the host:
+//   align_cam_fwd   (1 CTA)  raw parameters -> per-image camera record (R, t', f, cx, cy, depth affine map)
+//   align_loss_*    (grid)   per-correspondence unproject -> transform -> gamma loss -> analytic gradient
+//                            w.r.t. the two images' camera records (warp-shuffle + shared-memory reduction)
+//   align_cam_bwd   (1 CTA)  camera-record gradients -> MST chain backward -> parameter gradients -> Adam
+// HBM traffic per iteration is the correspondence list (~40 B per correspondence slot); the
+// loop is latency-bound, so the figure of merit is iterations/s.
+#include "common.cuh"
+#include "align_math.cuh"
+#include "../../include/starst3r_b200.h"
+
+namespace {
+
+constexpr int CAM_THREADS = 256;
+constexpr int LOSS_THREADS = 256;
+constexpr int NG = ALIGN_CAM_GRADS;
+static_assert(sizeof(AlignImgConst) == sizeof(St3rAlignImgConst), "public / internal image record mismatch");
+
+struct Params { float* pp; float* log_focal; float* quat; float* trans; float* log_size; };
+struct AdamState { float* m; float* v; };   // laid out like the flat parameter vector [11 * N]
+
+struct Work {
+  AlignCam* cam; AlignCamTmp* tmp; AlignCamGrad* cgrad;
+  float* gcam;        // [N * 17]
+  float* sums;        // [4]: main loss numerator, dust3r numerator, spare, stop flag
+  float* gscal;       // [2]: g (global scaling), arg-min index as float
+};
+
+__global__ void __launch_bounds__(CAM_THREADS)
+align_cam_fwd_kernel(St3rAlignProblem pb, Params p, Work w) {
+  const int N = pb.n_img;
+  if (w.sums[3] != 0.f) return;   // NaN loss seen: the reference breaks out of the loop (reconstruct.py:398-399)
+  const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
+  __shared__ float s_min[CAM_THREADS];
+  __shared__ int s_arg[CAM_THREADS];
+  float best = INFINITY;
+  int arg = 0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    al_cam_local_fwd(ic[i], p.log_focal[i], p.log_size[i], p.quat + 4 * i, w.tmp[i]);
+    float s = w.tmp[i].s;
+    if (s < best) { best = s; arg = i; }
+  }
+  s_min[threadIdx.x] = best; s_arg[threadIdx.x] = arg;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = INFINITY; int a = 0;
+    for (int t = 0; t < blockDim.x; ++t)
+      if (s_min[t] < b || (s_min[t] == b && s_arg[t] < a)) { b = s_min[t]; a = s_arg[t]; }
+    w.gscal[0] = 1.0f / b;
+    w.gscal[1] = (float)a;
+    al_chain_fwd(N, pb.root, pb.edges, w.tmp, p.trans);
+  }
+  __syncthreads();
+  const float g = w.gscal[0];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) al_cam_final_fwd(ic[i], p.pp + 2 * i, g, w.tmp[i], w.cam[i]);
+}
+
+// Adds a thread's 17 camera-record gradients of image `img` into the CTA-wide shared table
+// (warp-shuffle reduction when the whole warp works on the same image, which is the common case:
+// correspondences of one image pair are contiguous).
+__device__ __forceinline__ void accum_image(float* table, int img, bool active, const float* g) {
+  const unsigned full = 0xffffffffu;
+  int key = active ? img : -1;
+  unsigned peers = __match_any_sync(full, key);
+  if (peers == full) {
+    if (key < 0) return;
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+      float v = g[k];
+      for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(full, v, off);
+      if (lane_id() == 0 && v != 0.f) atomicAdd(table + img * NG + k, v);
+    }
+  } else if (active) {
+#pragma unroll
+    for (int k = 0; k < NG; ++k)
+      if (g[k] != 0.f) atomicAdd(table + img * NG + k, g[k]);
+  }
+}
+
+__device__ __forceinline__ void flush_table(const float* table, int N, float* gcam, float loss, float* loss_out) {
+  __shared__ float red[LOSS_THREADS / 32];
+  __syncthreads();
+  for (int e = threadIdx.x; e < N * NG; e += blockDim.x) {
+    float v = table[e];
+    if (v != 0.f) atomicAdd(gcam + e, v);
+  }
+  for (int off = 16; off; off >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, off);
+  if (lane_id() == 0) red[threadIdx.x >> 5] = loss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < LOSS_THREADS / 32; ++k) s += red[k];
+    if (s != 0.f) atomicAdd(loss_out, s);
+  }
+}
+
+struct Anchor { int img; float u, v, core, off; };
+__device__ __forceinline__ Anchor load_anchor(const St3rAlignProblem& pb, const AlignImgConst* ic, int a) {
+  Anchor r;
+  r.img = pb.anc_img[a];
+  r.u = pb.anc_uv[2 * a];
+  r.v = pb.anc_uv[2 * a + 1];
+  r.core = pb.core[ic[r.img].core_off + pb.anc_k[a]];
+  r.off = pb.anc_off[a];
+  return r;
+}
+
+// loss_3d: sum conf * gamma(|P1 - P2|) / norm   (reconstruct.py:325-353)
+__global__ void __launch_bounds__(LOSS_THREADS)
+align_loss3d_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, float off_pow, float scale) {
+  extern __shared__ float table[];
+  if (w.sums[3] != 0.f) return;
+  const int N = pb.n_img;
+  const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
+  for (int e = threadIdx.x; e < N * NG; e += blockDim.x) table[e] = 0.f;
+  __syncthreads();
+  float loss = 0.f;
+  const int n = pb.n3;
+  const int n_round = (n + 31) / 32 * 32;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n_round; m += gridDim.x * blockDim.x) {
+    const bool active = m < n;
+    float g1[NG], g2[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) g1[k] = g2[k] = 0.f;
+    int i1 = 0, i2 = 0;
+    if (active) {
+      Anchor a1 = load_anchor(pb, ic, pb.e3_a1[m]), a2 = load_anchor(pb, ic, pb.e3_a2[m]);
+      i1 = a1.img; i2 = a2.img;
+      const AlignCam c1 = w.cam[i1], c2 = w.cam[i2];
+      float P1[3], P2[3], pc1[3], pc2[3], z1, z2, D1, D2, o1, o2;
+      al_anchor_point(c1, a1.u, a1.v, a1.core, a1.off, P1, pc1, &z1, &D1, &o1);
+      al_anchor_point(c2, a2.u, a2.v, a2.core, a2.off, P2, pc2, &z2, &D2, &o2);
+      float d[3] = {P1[0] - P2[0], P1[1] - P2[1], P1[2] - P2[2]};
+      float dist = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      float dl;
+      float l = al_gamma_loss(dist, gamma, offset, off_pow, &dl);
+      float cw = pb.e3_conf[m] * scale;
+      loss += cw * l;
+      float k = dist > 0.f ? cw * dl / dist : 0.f;
+      float GP1[3] = {k * d[0], k * d[1], k * d[2]}, GP2[3] = {-k * d[0], -k * d[1], -k * d[2]};
+      al_anchor_point_vjp(c1, a1.u, a1.v, a1.core, a1.off, pc1, z1, D1, o1, GP1, g1);
+      al_anchor_point_vjp(c2, a2.u, a2.v, a2.core, a2.off, pc2, z2, D2, o2, GP2, g2);
+    }
+    accum_image(table, i1, active, g1);
+    accum_image(table, i2, active, g2);
+  }
+  flush_table(table, N, w.gcam, loss, w.sums + 0);
+}
+
+// loss_2d: sum conf * gamma(|pix1 - reproj(K1 w2cam1, P2)|) / norm   (reconstruct.py:355-369)
+__global__ void __launch_bounds__(LOSS_THREADS)
+align_loss2d_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, float off_pow, float scale) {
+  extern __shared__ float table[];
+  if (w.sums[3] != 0.f) return;
+  const int N = pb.n_img;
+  const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
+  for (int e = threadIdx.x; e < N * NG; e += blockDim.x) table[e] = 0.f;
+  __syncthreads();
+  float loss = 0.f;
+  const int n = pb.n2;
+  const int n_round = (n + 31) / 32 * 32;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n_round; m += gridDim.x * blockDim.x) {
+    const bool active = m < n;
+    float g1[NG], g2[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) g1[k] = g2[k] = 0.f;
+    int i1 = 0, i2 = 0;
+    if (active) {
+      i1 = pb.e2_img1[m];
+      Anchor a2 = load_anchor(pb, ic, pb.e2_a2[m]);
+      i2 = a2.img;
+      const AlignCam c1 = w.cam[i1], c2 = w.cam[i2];
+      float P2[3], pc2[3], z2, D2, o2;
+      al_anchor_point(c2, a2.u, a2.v, a2.core, a2.off, P2, pc2, &z2, &D2, &o2);
+      float uv[2];
+      AlignReproj q;
+      al_reproj(c1, P2, uv, q);
+      float d[2] = {pb.e2_pix[2 * m] - uv[0], pb.e2_pix[2 * m + 1] - uv[1]};
+      float dist = sqrtf(d[0] * d[0] + d[1] * d[1]);
+      float dl;
+      float l = al_gamma_loss(dist, gamma, offset, off_pow, &dl);
+      float cw = pb.e2_conf[m] * scale;
+      loss += cw * l;
+      float k = dist > 0.f ? cw * dl / dist : 0.f;
+      float Guv[2] = {-k * d[0], -k * d[1]};
+      float GP[3];
+      al_reproj_vjp(c1, P2, q, Guv, g1, GP);
+      al_anchor_point_vjp(c2, a2.u, a2.v, a2.core, a2.off, pc2, z2, D2, o2, GP, g2);
+    }
+    accum_image(table, i1, active, g1);
+    accum_image(table, i2, active, g2);
+  }
+  flush_table(table, N, w.gcam, loss, w.sums + 0);
+}
+
+// loss_dust3r: sum conf * gamma(|P1 - cam2w[img2] tgt|) / norm   (reconstruct.py:311-323)
+__global__ void __launch_bounds__(LOSS_THREADS)
+align_lossd_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, float off_pow, float scale) {
+  extern __shared__ float table[];
+  if (w.sums[3] != 0.f) return;
+  const int N = pb.n_img;
+  const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
+  for (int e = threadIdx.x; e < N * NG; e += blockDim.x) table[e] = 0.f;
+  __syncthreads();
+  float loss = 0.f;
+  const int n = pb.nd;
+  const int n_round = (n + 31) / 32 * 32;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n_round; m += gridDim.x * blockDim.x) {
+    const bool active = m < n;
+    float g1[NG], g2[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) g1[k] = g2[k] = 0.f;
+    int i1 = 0, i2 = 0;
+    if (active) {
+      Anchor a1 = load_anchor(pb, ic, pb.ed_a1[m]);
+      i1 = a1.img;
+      i2 = pb.ed_img2[m];
+      const AlignCam c1 = w.cam[i1], c2 = w.cam[i2];
+      float P1[3], pc1[3], z1, D1, o1;
+      al_anchor_point(c1, a1.u, a1.v, a1.core, a1.off, P1, pc1, &z1, &D1, &o1);
+      const float tg[3] = {pb.ed_tgt[3 * m], pb.ed_tgt[3 * m + 1], pb.ed_tgt[3 * m + 2]};
+      float T[3];
+      al_mat3_vec(c2.R, tg, T);
+      T[0] += c2.t[0]; T[1] += c2.t[1]; T[2] += c2.t[2];
+      float d[3] = {P1[0] - T[0], P1[1] - T[1], P1[2] - T[2]};
+      float dist = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      float dl;
+      float l = al_gamma_loss(dist, gamma, offset, off_pow, &dl);
+      float cw = pb.ed_conf[m] * scale;
+      loss += cw * l;
+      float k = dist > 0.f ? cw * dl / dist : 0.f;
+      float GP1[3] = {k * d[0], k * d[1], k * d[2]};
+      al_anchor_point_vjp(c1, a1.u, a1.v, a1.core, a1.off, pc1, z1, D1, o1, GP1, g1);
+      for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) g2[3 * a + b] += -GP1[a] * tg[b];
+        g2[9 + a] += -GP1[a];
+      }
+    }
+    accum_image(table, i1, active, g1);
+    accum_image(table, i2, active, g2);
+  }
+  flush_table(table, N, w.gcam, loss, w.sums + 1);
+}
+
+__device__ __forceinline__ void adam_update(float* p, float g, float* m, float* v, float lr_over_bc1, float inv_sqrt_bc2,
+                                            float omb1, float b2, float omb2, float eps) {
+  float mm = *m + (g - *m) * omb1;
+  float vv = *v * b2 + omb2 * g * g;
+  *p = *p - lr_over_bc1 * (mm / (sqrtf(vv) * inv_sqrt_bc2 + eps));
+  *m = mm;
+  *v = vv;
+}
+
+// camera-record gradients -> parameter gradients -> Adam -> quaternion re-normalisation; also finalises the
+// iteration's loss and clears the accumulators for the next iteration.
+__global__ void __launch_bounds__(CAM_THREADS)
+align_cam_bwd_kernel(St3rAlignProblem pb, Params p, AdamState ad, Work w, int train_mask, float lr_over_bc1,
+                     float inv_sqrt_bc2, float omb1, float b2, float omb2, float eps, float dust3r_w,
+                     float* loss_hist, int iter, float* grad_out /* optional [11 N], for tests */) {
+  const int N = pb.n_img;
+  const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
+  __shared__ float s_gg[CAM_THREADS];
+  if (w.sums[3] != 0.f) return;
+  const float g = w.gscal[0];
+  const int jstar = (int)w.gscal[1];
+  float gg = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    al_cam_final_bwd(ic[i], p.pp + 2 * i, g, w.tmp[i], w.gcam + i * NG, w.cgrad[i]);
+    gg += w.cgrad[i].g_g;
+  }
+  s_gg[threadIdx.x] = gg;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < blockDim.x; ++k) t += s_gg[k];
+    s_gg[0] = t;
+    al_chain_bwd(N, pb.root, pb.edges, w.tmp, p.trans, w.cgrad);
+    float loss = w.sums[0] + dust3r_w * w.sums[1];
+    if (loss_hist) loss_hist[iter] = loss;
+    if (loss != loss) w.sums[3] = 1.0f;   // NaN -> stop flag (reconstruct.py:398-399)
+    w.sums[0] = 0.f; w.sums[1] = 0.f;
+  }
+  __syncthreads();
+  const float gg_total = s_gg[0];
+  const bool stop = false;  // the NaN iteration itself still steps, like the reference
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    float g_pp[2], g_lf, g_q[4], g_t[3], g_ls;
+    float extra = (i == jstar) ? -gg_total * g * g : 0.f;
+    al_cam_local_bwd(w.tmp[i], w.cgrad[i], extra, g_pp, &g_lf, g_q, g_t, &g_ls);
+    if (grad_out) {
+      float* o = grad_out + 11 * i;
+      o[0] = g_pp[0]; o[1] = g_pp[1]; o[2] = g_lf; o[3] = g_q[0]; o[4] = g_q[1]; o[5] = g_q[2]; o[6] = g_q[3];
+      o[7] = g_t[0]; o[8] = g_t[1]; o[9] = g_t[2]; o[10] = g_ls;
+    }
+    if (!stop) {
+      float* m = ad.m + 11 * i;
+      float* v = ad.v + 11 * i;
+      if (train_mask & 1) {
+        adam_update(p.pp + 2 * i, g_pp[0], m + 0, v + 0, lr_over_bc1, inv_sqrt_bc2, omb1, b2, omb2, eps);
+        adam_update(p.pp + 2 * i + 1, g_pp[1], m + 1, v + 1, lr_over_bc1, inv_sqrt_bc2, omb1, b2, omb2, eps);
+      }
+      if (train_mask & 2) adam_update(p.log_focal + i, g_lf, m + 2, v + 2, lr_over_bc1, inv_sqrt_bc2, omb1, b2, omb2, eps);
+      if (train_mask & 4) {
+        for (int k = 0; k < 4; ++k)
+          adam_update(p.quat + 4 * i + k, g_q[k], m + 3 + k, v + 3 + k, lr_over_bc1, inv_sqrt_bc2, omb1, b2, omb2, eps);
+      }
+      if (train_mask & 8) {
+        for (int k = 0; k < 3; ++k)
+          adam_update(p.trans + 3 * i + k, g_t[k], m + 7 + k, v + 7 + k, lr_over_bc1, inv_sqrt_bc2, omb1, b2, omb2, eps);
+      }
+      if (train_mask & 16) adam_update(p.log_size + i, g_ls, m + 10, v + 10, lr_over_bc1, inv_sqrt_bc2, omb1, b2, omb2, eps);
+      // quats[i].data[:] /= quats[i].data.norm()   (reconstruct.py:394-395)
+      float* q = p.quat + 4 * i;
+      float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+      q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+    }
+    for (int k = 0; k < NG; ++k) w.gcam[i * NG + k] = 0.f;
+  }
+}
+
+// pts3d of every anchor + dense depth maps from the last forward's camera records.
+__global__ void align_outputs_kernel(St3rAlignProblem pb, Work w, float* pts3d, float* depthmaps, int n_core_total) {
+  const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < pb.n_anchor) {
+    Anchor a = load_anchor(pb, ic, t);
+    float P[3], pc[3], z, D, o;
+    al_anchor_point(w.cam[a.img], a.u, a.v, a.core, a.off, P, pc, &z, &D, &o);
+    pts3d[3 * t] = P[0]; pts3d[3 * t + 1] = P[1]; pts3d[3 * t + 2] = P[2];
+  }
+  if (t < n_core_total) {
+    // find owning image (N is small)
+    int img = 0;
+    for (int i = 0; i < pb.n_img; ++i)
+      if (t >= ic[i].core_off && t < ic[i].core_off + ic[i].n_core) img = i;
+    depthmaps[t] = w.cam[img].A + w.cam[img].B * pb.core[t];
+  }
+}
+
+Work carve(void* ws, int N) {
+  WsAlloc a(ws, (size_t)-1);
+  Work w;
+  w.cam = a.take<AlignCam>(N);
+  w.tmp = a.take<AlignCamTmp>(N);
+  w.cgrad = a.take<AlignCamGrad>(N);
+  w.gcam = a.take<float>((size_t)N * NG);
+  w.sums = a.take<float>(4);
+  w.gscal = a.take<float>(2);
+  return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t st3r_align_ws_bytes(int n_img) {
+  size_t n = (size_t)(n_img > 0 ? n_img : 1);
+  return st3r_align_up(n * sizeof(AlignCam), 256) + st3r_align_up(n * sizeof(AlignCamTmp), 256) +
+         st3r_align_up(n * sizeof(AlignCamGrad), 256) + st3r_align_up(n * NG * sizeof(float), 256) + 4096;
+}
+int st3r_align_cam_floats(void) { return (int)(sizeof(AlignCam) / sizeof(float)); }
+int st3r_align_img_const_bytes(void) { return (int)sizeof(AlignImgConst); }
+
+int st3r_align_optimize(const St3rAlignProblem* prob, float* pp, float* log_focal, float* quat, float* trans,
+                        float* log_size, float* adam_m, float* adam_v, int mode, int train_mask, float gamma,
+                        float gamma_dust3r, float dust3r_w, const float* h_lr, int niter, double beta1,
+                        double beta2, double eps, float* loss_hist, float* cam_out, float* pts3d_out,
+                        float* depth_out, float* grad_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  ST3R_CHECK_ARG(prob && pp && log_focal && quat && trans && log_size && adam_m && adam_v, "st3r_align_optimize: null");
+  ST3R_CHECK_ARG(prob->n_img >= 1 && niter >= 0 && (mode == 0 || mode == 1), "st3r_align_optimize: bad sizes / mode");
+  ST3R_CHECK_ARG(ws && ws_bytes >= st3r_align_ws_bytes(prob->n_img), "st3r_align_optimize: workspace too small");
+  ST3R_CHECK_ARG(niter == 0 || h_lr, "st3r_align_optimize: missing lr schedule");
+  const St3rAlignProblem pb = *prob;
+  const int N = pb.n_img;
+  const size_t table_bytes = (size_t)N * NG * sizeof(float);
+  ST3R_CHECK_ARG(table_bytes <= 96 * 1024, "st3r_align_optimize: too many images for the shared-memory gradient table");
+  static bool attr = false;
+  if (!attr) {
+    ST3R_CHECK_CUDA(cudaFuncSetAttribute(align_loss3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    ST3R_CHECK_CUDA(cudaFuncSetAttribute(align_loss2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    ST3R_CHECK_CUDA(cudaFuncSetAttribute(align_lossd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  Work w = carve(ws, N);
+  Params p{pp, log_focal, quat, trans, log_size};
+  AdamState ad{adam_m, adam_v};
+  ST3R_CHECK_CUDA(cudaMemsetAsync(w.gcam, 0, (size_t)N * NG * sizeof(float), stream));
+  ST3R_CHECK_CUDA(cudaMemsetAsync(w.sums, 0, 4 * sizeof(float), stream));
+
+  auto gamma_consts = [](float gm, float* off, float* offpow) {
+    if (gm == 1.0f) { *off = 0.f; *offpow = 0.f; return; }
+    double o = pow(1.0 / (double)gm, 1.0 / ((double)gm - 1.0));
+    *off = (float)o;
+    *offpow = (float)pow(o, (double)gm);
+  };
+  float off_m, offp_m, off_d, offp_d;
+  gamma_consts(gamma, &off_m, &offp_m);
+  gamma_consts(gamma_dust3r, &off_d, &offp_d);
+  const int n_main = mode == 0 ? pb.n3 : pb.n2;
+  const float norm_main = mode == 0 ? pb.norm3 : pb.norm2;
+  const float scale_main = (n_main > 0 && norm_main != 0.f) ? 1.0f / norm_main : 0.f;
+  const float scale_d = (pb.nd > 0 && pb.normd != 0.f) ? 1.0f / pb.normd : 0.f;
+  auto blocks_for = [](int n) { int b = (n + LOSS_THREADS * 2 - 1) / (LOSS_THREADS * 2); return b < 1 ? 1 : (b > 1184 ? 1184 : b); };
+
+  const int iters = niter > 0 ? niter : 1;
+  for (int it = 0; it < iters; ++it) {
+    align_cam_fwd_kernel<<<1, CAM_THREADS, 0, stream>>>(pb, p, w);
+    ST3R_CHECK_LAUNCH();
+    if (niter == 0) break;
+    if (n_main > 0) {
+      if (mode == 0)
+        align_loss3d_kernel<<<blocks_for(n_main), LOSS_THREADS, table_bytes, stream>>>(pb, w, gamma, off_m, offp_m, scale_main);
+      else
+        align_loss2d_kernel<<<blocks_for(n_main), LOSS_THREADS, table_bytes, stream>>>(pb, w, gamma, off_m, offp_m, scale_main);
+      ST3R_CHECK_LAUNCH();
+    }
+    if (pb.nd > 0 && dust3r_w != 0.f) {
+      // the dust3r term enters the total loss with weight dust3r_w (reconstruct.py:389)
+      align_lossd_kernel<<<blocks_for(pb.nd), LOSS_THREADS, table_bytes, stream>>>(pb, w, gamma_dust3r, off_d, offp_d,
+                                                                                   scale_d * dust3r_w);
+      ST3R_CHECK_LAUNCH();
+    }
+    const int step = it + 1;
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    align_cam_bwd_kernel<<<1, CAM_THREADS, 0, stream>>>(pb, p, ad, w, train_mask, (float)((double)h_lr[it] / bc1),
+                                                        (float)(1.0 / sqrt(bc2)), (float)(1.0 - beta1), (float)beta2,
+                                                        (float)(1.0 - beta2), (float)eps, 1.0f, loss_hist, it,
+                                                        (it == iters - 1) ? grad_out : nullptr);
+    ST3R_CHECK_LAUNCH();
+  }
+  if (cam_out) ST3R_CHECK_CUDA(cudaMemcpyAsync(cam_out, w.cam, (size_t)N * sizeof(AlignCam), cudaMemcpyDeviceToDevice, stream));
+  if (pts3d_out || depth_out) {
+    ST3R_CHECK_ARG(pts3d_out && depth_out, "st3r_align_optimize: pts3d_out and depth_out go together");
+    int total = pb.n_anchor > pb.n_core_total ? pb.n_anchor : pb.n_core_total;
+    if (total > 0) {
+      align_outputs_kernel<<<(total + 255) / 256, 256, 0, stream>>>(pb, w, pts3d_out, depth_out, pb.n_core_total);
+      ST3R_CHECK_LAUNCH();
+    }
+  }
+  return ST3R_OK;
+}
+
+}  // extern "C"

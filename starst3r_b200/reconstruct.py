@@ -1,0 +1,649 @@
+"""MATCH + ALIGN pipeline — host-side mirror of starster/reconstruct.py (reconstruct_scene, run_sparse_ga,
+sparse_scene_optimizer_slam) and of the mast3r/cloud_opt/sparse_ga.py functions it star-imports.
+
+The numerics run in sm_100a kernels behind the C ABI: correspondences via st3r_extract_corres (match.py), the
+700-iteration global alignment via st3r_align_optimize (align.cu), canonical views / dense points / point-cloud
+cleaning via st3r_canonical_view, st3r_dense_points, st3r_clean_pointcloud (align_dense.cu).  Pair results stay in
+HBM (no torch.save round trip); `tmpdir` / `cache_dir` are accepted for signature parity.
+"""
+import ctypes
+import math
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _lib, match
+
+__all__ = ("reconstruct_scene", "run_sparse_ga", "sparse_scene_optimizer_slam", "gamma_loss", "cosine_schedule",
+           "linear_schedule", "make_pairs", "SparseGA", "PairOfSlices")
+
+PairOfSlices = namedtuple("ImgPair", "img1, slice1, pix1, anchor_idxs1, img2, slice2, pix2, anchor_idxs2, confs, confs_sum")
+
+
+# ------------------------------------------------------------------------------------------- small helpers
+class gamma_loss:
+    """cloud_opt/utils/losses.py:19-28 as a descriptor object: the fused kernel evaluates (d + o)^gamma - o^gamma
+    itself, so only `gamma` is carried; calling the object evaluates the same formula with torch (API parity)."""
+
+    def __init__(self, gamma, mul=1, offset=None, clip=np.inf):
+        if mul != 1 or offset is not None or clip != np.inf:
+            raise NotImplementedError("gamma_loss: only the default mul/offset/clip are used by Starst3r")
+        self.gamma = float(gamma)
+        self.offset = 0.0 if gamma == 1 else (1 / gamma) ** (1 / (gamma - 1))
+
+    def __call__(self, x, y):
+        d = torch.linalg.norm(x - y, dim=-1)
+        return d if self.gamma == 1 else (d + self.offset) ** self.gamma - self.offset ** self.gamma
+
+
+def linear_schedule(alpha, lr_base, lr_end=0):
+    return (1 - alpha) * lr_base + alpha * lr_end
+
+
+def cosine_schedule(alpha, lr_base, lr_end=0):
+    return lr_end + (lr_base - lr_end) * (1 + np.cos(alpha * np.pi)) / 2
+
+
+def _gamma_of(loss):
+    if isinstance(loss, (int, float)):
+        return float(loss)
+    if hasattr(loss, "gamma"):
+        return float(loss.gamma)
+    raise NotImplementedError("the fused ALIGN kernel needs a gamma_loss(gamma) descriptor (or a number) as pixel loss")
+
+
+def _sl(s):
+    return s if isinstance(s, slice) else slice(s[1], s[2])
+
+
+def make_pairs(imgs, scene_graph="complete", prefilter=None, symmetrize=True):
+    """dust3r/image_pairs.py:11-59, 'complete' graph (the only one Starst3r uses, reconstruct.py:51)."""
+    if scene_graph != "complete" or prefilter is not None:
+        raise NotImplementedError("only scene_graph='complete', prefilter=None is on the Starst3r path")
+    pairs = [(imgs[i], imgs[j]) for i in range(len(imgs)) for j in range(i)]
+    if symmetrize:
+        pairs += [(b, a) for a, b in pairs]
+    return pairs
+
+
+# ------------------------------------------------------------------------------------------- problem flattening
+class _ImgConst(ctypes.Structure):
+    _fields_ = [("W", ctypes.c_float), ("H", ctypes.c_float), ("base_focal", ctypes.c_float), ("median", ctypes.c_float),
+                ("min_focal", ctypes.c_float), ("max_focal", ctypes.c_float), ("core_off", ctypes.c_int32),
+                ("n_core", ctypes.c_int32)]
+
+
+class _Problem(ctypes.Structure):
+    _fields_ = [("n_img", ctypes.c_int32), ("img_const", ctypes.c_void_p), ("core", ctypes.c_void_p),
+                ("n_core_total", ctypes.c_int32), ("root", ctypes.c_int32), ("edges", ctypes.c_void_p),
+                ("n_anchor", ctypes.c_int32), ("anc_img", ctypes.c_void_p), ("anc_uv", ctypes.c_void_p),
+                ("anc_k", ctypes.c_void_p), ("anc_off", ctypes.c_void_p),
+                ("n3", ctypes.c_int32), ("e3_a1", ctypes.c_void_p), ("e3_a2", ctypes.c_void_p),
+                ("e3_conf", ctypes.c_void_p), ("norm3", ctypes.c_float),
+                ("n2", ctypes.c_int32), ("e2_img1", ctypes.c_void_p), ("e2_pix", ctypes.c_void_p),
+                ("e2_a2", ctypes.c_void_p), ("e2_conf", ctypes.c_void_p), ("norm2", ctypes.c_float),
+                ("nd", ctypes.c_int32), ("ed_a1", ctypes.c_void_p), ("ed_img2", ctypes.c_void_p),
+                ("ed_tgt", ctypes.c_void_p), ("ed_conf", ctypes.c_void_p), ("normd", ctypes.c_float)]
+
+
+def flatten_problem(imgs, imsizes, pps, base_focals, core_depth, anchors, corres, corres2d, preds_21, mst,
+                    matching_conf_thr=5.0, device="cpu"):
+    """condense_data output (sparse_ga.py:729-814) -> flat arrays for st3r_align_optimize (see St3rAlignProblem).
+    Follows reconstruct.py:141-309: pp normalisation (:170), median-normalised core depth (:176-177), focal bounds
+    (:203-205), matching_check (:283-290), loss3d / dust3r slice split and corres2d filtering (:291-309)."""
+    dev = torch.device(device)
+    N = len(imgs)
+    imsizes_f = imsizes.detach().float().cpu()
+    base_f = torch.as_tensor(base_focals).detach().float().cpu().reshape(-1)
+    core = [c.detach().float().cpu().reshape(-1) for c in core_depth]
+    median = torch.stack([c.median() for c in core])
+    core_n = [c / m for c, m in zip(core, median)]
+    diag = imsizes_f.norm(dim=1)
+    img_names = list(imgs)
+    ic_host = np.zeros(N, dtype=[("W", "f4"), ("H", "f4"), ("bf", "f4"), ("med", "f4"), ("minf", "f4"), ("maxf", "f4"),
+                                 ("off", "i4"), ("n", "i4")])
+    off = 0
+    for i in range(N):
+        ic_host[i] = (imsizes_f[i, 0], imsizes_f[i, 1], base_f[i], median[i], 0.25 * diag[i], 10 * diag[i], off,
+                      core_n[i].numel())
+        off += core_n[i].numel()
+    # anchors
+    aoff, a_img, a_uv, a_k, a_off = [0], [], [], [], []
+    for i in range(N):
+        pix, idx, offs = anchors[i]
+        n = len(idx)
+        aoff.append(aoff[-1] + n)
+        a_img.append(torch.full((n,), i, dtype=torch.int32))
+        a_uv.append(pix.detach().cpu().float()[:, :2])
+        a_k.append(idx.detach().cpu().to(torch.int32))
+        a_off.append(offs.detach().cpu().float())
+    n_anchor = aoff[-1]
+    _, _, slices = corres
+    ok = {(s[0], s[4]): bool(s[8].max() > matching_conf_thr) for s in slices}
+    e3a1, e3a2, e3c, eda1, edi2, edt, edc = [], [], [], [], [], [], []
+    for s in slices:
+        i1, sl1, i2, sl2, confs = s[0], _sl(s[1]), s[4], _sl(s[5]), s[8]
+        if ok[i1, i2]:
+            e3a1.append(aoff[i1] + torch.arange(sl1.start, sl1.stop, dtype=torch.int32))
+            e3a2.append(aoff[i2] + torch.arange(sl2.start, sl2.stop, dtype=torch.int32))
+            e3c.append(confs.detach().cpu().float())
+        else:
+            tgt, tc = preds_21[img_names[i2]][img_names[i1]]
+            n1 = aoff[i1 + 1] - aoff[i1]
+            eda1.append(aoff[i1] + torch.arange(n1, dtype=torch.int32))
+            edi2.append(torch.full((n1,), i2, dtype=torch.int32))
+            edt.append(tgt.detach().cpu().float())
+            edc.append(tc.detach().cpu().float())
+    e2i, e2p, e2a, e2c = [], [], [], []
+    for img1, pix1, confs, _, sls in corres2d:
+        cur = 0
+        for img2, sl2 in sls:
+            sl2 = _sl(sl2)
+            n = sl2.stop - sl2.start
+            if ok[img1, img2]:
+                e2i.append(torch.full((n,), img1, dtype=torch.int32))
+                e2p.append(pix1[cur:cur + n].detach().cpu().float())
+                e2c.append(confs[cur:cur + n].detach().cpu().float())
+                e2a.append(aoff[img2] + torch.arange(sl2.start, sl2.stop, dtype=torch.int32))
+            cur += n
+
+    def cat(xs, dtype, shape_tail=()):
+        if xs:
+            return torch.cat(xs).to(dtype).contiguous()
+        return torch.zeros((0,) + shape_tail, dtype=dtype)
+    t = dict(
+        img_const=torch.from_numpy(ic_host.view(np.uint8).reshape(N, -1).copy()),
+        core=torch.cat(core_n).contiguous(),
+        edges=torch.tensor([[int(a), int(b)] for a, b in mst[1]], dtype=torch.int32).reshape(-1).contiguous()
+        if len(mst[1]) else torch.zeros(0, dtype=torch.int32),
+        anc_img=cat(a_img, torch.int32), anc_uv=cat(a_uv, torch.float32, (2,)), anc_k=cat(a_k, torch.int32),
+        anc_off=cat(a_off, torch.float32),
+        e3_a1=cat(e3a1, torch.int32), e3_a2=cat(e3a2, torch.int32), e3_conf=cat(e3c, torch.float32),
+        e2_img1=cat(e2i, torch.int32), e2_pix=cat(e2p, torch.float32, (2,)), e2_a2=cat(e2a, torch.int32),
+        e2_conf=cat(e2c, torch.float32),
+        ed_a1=cat(eda1, torch.int32), ed_img2=cat(edi2, torch.int32), ed_tgt=cat(edt, torch.float32, (3,)),
+        ed_conf=cat(edc, torch.float32))
+    meta = dict(N=N, root=int(mst[0]), n_anchor=n_anchor, aoff=aoff, n_core=[c.numel() for c in core_n],
+                norm3=float(t["e3_conf"].sum()), norm2=float(t["e2_conf"].sum()), normd=float(t["ed_conf"].sum()),
+                median=median, imsizes=imsizes_f, base_focals=base_f)
+    t = {k: v.to(dev) for k, v in t.items()}
+    return t, meta
+
+
+def problem_struct(t, meta):
+    p = _Problem()
+    p.n_img, p.root, p.n_anchor = meta["N"], meta["root"], meta["n_anchor"]
+    p.n_core_total = int(t["core"].numel())
+    p.n3, p.n2, p.nd = int(t["e3_a1"].numel()), int(t["e2_img1"].numel()), int(t["ed_a1"].numel())
+    p.norm3, p.norm2, p.normd = meta["norm3"], meta["norm2"], meta["normd"]
+    for k in ("img_const", "core", "edges", "anc_img", "anc_uv", "anc_k", "anc_off", "e3_a1", "e3_a2", "e3_conf",
+              "e2_img1", "e2_pix", "e2_a2", "e2_conf", "ed_a1", "ed_img2", "ed_tgt", "ed_conf"):
+        setattr(p, k, t[k].data_ptr())
+    return p
+
+
+def _optimize_phase(t, meta, params, mode, train_mask, gamma, lr_base, niter, schedule, dust3r_w, lossd_gamma,
+                    want_grad=False):
+    """One optimize_loop call (reconstruct.py:371-406) on the device."""
+    lib = _lib.load()
+    dev = params["pps"].device
+    N = meta["N"]
+    prob = problem_struct(t, meta)
+    lr = np.array([schedule(it / niter, lr_base, 0) for it in range(niter)], dtype=np.float32) if niter else \
+        np.zeros(1, np.float32)
+    adam_m = torch.zeros(N, 11, device=dev)
+    adam_v = torch.zeros(N, 11, device=dev)
+    loss_hist = torch.zeros(max(niter, 1), device=dev)
+    camf = lib.st3r_align_cam_floats()
+    cam = torch.empty(N, camf, device=dev)
+    pts3d = torch.empty(max(meta["n_anchor"], 1), 3, device=dev)
+    depth = torch.empty(max(int(t["core"].numel()), 1), device=dev)
+    grad = torch.zeros(N, 11, device=dev) if want_grad else None
+    ws = torch.empty(lib.st3r_align_ws_bytes(N), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.st3r_align_optimize(ctypes.byref(prob), _lib.ptr(params["pps"]), _lib.ptr(params["log_focals"]),
+                                     _lib.ptr(params["quats"]), _lib.ptr(params["trans"]), _lib.ptr(params["log_sizes"]),
+                                     _lib.ptr(adam_m), _lib.ptr(adam_v), mode, train_mask, ctypes.c_float(gamma),
+                                     ctypes.c_float(lossd_gamma), ctypes.c_float(dust3r_w),
+                                     lr.ctypes.data_as(ctypes.c_void_p), niter, ctypes.c_double(0.9),
+                                     ctypes.c_double(0.9), ctypes.c_double(1e-8), _lib.ptr(loss_hist), _lib.ptr(cam),
+                                     _lib.ptr(pts3d), _lib.ptr(depth), _lib.ptr(grad), _lib.ptr(ws), ws.numel(),
+                                     _lib.stream_ptr())
+    _lib.check(rc, "st3r_align_optimize")
+    K = torch.zeros(N, 3, 3, device=dev)
+    K[:, 0, 0] = K[:, 1, 1] = cam[:, 12]
+    K[:, 0, 2], K[:, 1, 2], K[:, 2, 2] = cam[:, 13], cam[:, 14], 1.0
+    cam2w = torch.zeros(N, 4, 4, device=dev)
+    cam2w[:, :3, :3] = cam[:, :9].reshape(N, 3, 3)
+    cam2w[:, :3, 3] = cam[:, 9:12]
+    cam2w[:, 3, 3] = 1.0
+    aoff = meta["aoff"]
+    coff = np.cumsum([0] + meta["n_core"])
+    res = dict(intrinsics=K, cam2w=cam2w,
+               depthmaps=[depth[coff[i]:coff[i + 1]] for i in range(N)],
+               pts3d=[pts3d[aoff[i]:aoff[i + 1]] for i in range(N)])
+    return res, loss_hist[:niter], grad
+
+
+def sparse_scene_optimizer_slam(imgs, subsample, imsizes, pps, base_focals, core_depth, anchors, corres, corres2d,
+                                preds_21, canonical_paths, mst, cache_path=None,
+                                lr1=0.2, niter1=500, loss1=gamma_loss(1.1),
+                                lr2=0.02, niter2=500, loss2=gamma_loss(0.4),
+                                lossd=gamma_loss(1.1),
+                                opt_pp=True, opt_depth=True,
+                                schedule=cosine_schedule, depth_mode="add", exp_depth=False,
+                                lora_depth=False, shared_intrinsics=False,
+                                init={}, device="cuda", dtype=torch.float32,
+                                matching_conf_thr=5., loss_dust3r_w=0.01,
+                                verbose=True, dbg=(), prev_params=None):
+    """starster/reconstruct.py:116-457 on the B200: same arguments, returns (imgs, res_coarse, res_fine, params_ret).
+    Options Starst3r never enables (opt_depth=True, lora_depth, exp_depth, depth_mode='mul', shared_intrinsics,
+    per-image `init`) are outside the fused kernel and raise NotImplementedError."""
+    if opt_depth or lora_depth or exp_depth or depth_mode != "add" or shared_intrinsics or any(init.values()):
+        raise NotImplementedError("sparse_scene_optimizer_slam on B200 implements the configuration Starst3r uses "
+                                  "(reconstruct.py:56-70: opt_depth=False, depth_mode='add', no lora/exp depth, "
+                                  "separate intrinsics, no per-image init)")
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("sparse_scene_optimizer_slam: the fused optimiser only runs on CUDA (no CPU fallback)")
+    assert len(mst[1]) == len(imgs) - 1
+    N = len(imgs)
+    t, meta = flatten_problem(imgs, imsizes, pps, base_focals, core_depth, anchors, corres, corres2d, preds_21, mst,
+                              matching_conf_thr, dev)
+    pps_n = (torch.as_tensor(pps).detach().float().cpu() / meta["imsizes"])
+    params = dict(pps=pps_n.to(dev).contiguous(), log_focals=meta["base_focals"].log().to(dev).contiguous(),
+                  quats=torch.tensor([[0.0, 0, 0, 1]]).repeat(N, 1).to(dev).contiguous(),
+                  trans=torch.zeros(N, 3, device=dev), log_sizes=torch.zeros(N, device=dev))
+    if verbose:
+        print("init focals =", meta["base_focals"].numpy())
+    if prev_params is not None:       # reconstruct.py:408-415 - warm start of the first len(prev) images
+        for k in ("pps", "log_focals", "quats", "trans", "log_sizes"):
+            prev = prev_params[k]
+            n = min(len(prev), N)
+            if n:
+                params[k][:n] = torch.stack([torch.as_tensor(x).detach().reshape(-1) for x in prev[:n]]).to(dev).reshape(
+                    params[k][:n].shape)
+    res_coarse, hist1, _ = _optimize_phase(t, meta, params, 0, 4 | 8 | 16, _gamma_of(loss1), lr1, niter1, schedule,
+                                           loss_dust3r_w, _gamma_of(lossd))
+    if verbose and niter1:
+        print(f">> final loss = {float(hist1[-1])}")
+    res_fine = None
+    if niter2:
+        mask = 4 | 8 | 16 | 2 | (1 if opt_pp else 0)
+        res_fine, hist2, _ = _optimize_phase(t, meta, params, 1, mask, _gamma_of(loss2), lr2, niter2, schedule,
+                                             loss_dust3r_w, _gamma_of(lossd))
+        if verbose:
+            print(f">> final loss = {float(hist2[-1])}")
+    if verbose:
+        f = params["log_focals"].exp().clip(min=torch.as_tensor(0.25 * meta["imsizes"].norm(dim=1)).to(dev),
+                                            max=torch.as_tensor(10 * meta["imsizes"].norm(dim=1)).to(dev))
+        print("Final focals =", f.cpu().numpy())
+    P = torch.nn.Parameter
+    coff = np.cumsum([0] + meta["n_core"])
+    params_ret = {
+        "pps": [P(params["pps"][i].clone()) for i in range(N)],
+        "log_focals": [P(params["log_focals"][i:i + 1].clone()) for i in range(N)],
+        "quats": [P(params["quats"][i].clone()) for i in range(N)],
+        "trans": [P(params["trans"][i].clone()) for i in range(N)],
+        "log_sizes": [P(params["log_sizes"][i:i + 1].clone()) for i in range(N)],
+        "core_depth": [P(t["core"][coff[i]:coff[i + 1]].clone(), requires_grad=False) for i in range(N)],
+    }
+    return imgs, res_coarse, res_fine, params_ret
+
+
+# =================================================================================================================
+# Pipeline around the optimiser: pair loop + matching, canonical views, MST, condense, SparseGA result object.
+# Restated from mast3r/cloud_opt/sparse_ga.py; per-pair tensors are memoised in HBM instead of torch.save files.
+# =================================================================================================================
+_MEMO = {}   # cache_path -> {"fwd": {(a, b): (X11, C11, X21, C21)}, "corres": {(a, b): (score, (xy1, xy2, conf))},
+             #                "canon": {img: ((canon, canon2, cconf), focal)}}
+
+
+def _memo(cache_path):
+    return _MEMO.setdefault(cache_path, {"fwd": {}, "corres": {}, "canon": {}})
+
+
+def convert_dust3r_pairs_naming(imgs, pairs_in):
+    """sparse_ga.py:111-115."""
+    for pair in pairs_in:
+        for k in range(2):
+            pair[k]["instance"] = imgs[pair[k]["idx"]]
+    return pairs_in
+
+
+def symmetric_inference(model, img1, img2, device):
+    """sparse_ga.py:571-592: encoder once, decoder in both directions.  `model` is the (out-of-scope) MASt3R network;
+    any object offering `symmetric_inference(img1, img2)` (e.g. synth.SyntheticMast3r) is used directly."""
+    if hasattr(model, "symmetric_inference"):
+        return model.symmetric_inference(img1, img2)
+    shape1 = torch.from_numpy(img1["true_shape"]).to(device, non_blocking=True)
+    shape2 = torch.from_numpy(img2["true_shape"]).to(device, non_blocking=True)
+    im1 = img1["img"].to(device, non_blocking=True)
+    im2 = img2["img"].to(device, non_blocking=True)
+    feat1, feat2, pos1, pos2 = model._encode_image_pairs(im1, im2, shape1, shape2)
+
+    def decoder(fa, fb, pa, pb, sa, sb):
+        dec1, dec2 = model._decoder(fa, pa, fb, pb)
+        with torch.autocast("cuda", enabled=False):
+            return (model._downstream_head(1, [t.float() for t in dec1], sa),
+                    model._downstream_head(2, [t.float() for t in dec2], sb))
+    res11, res21 = decoder(feat1, feat2, pos1, pos2, shape1, shape2)
+    res22, res12 = decoder(feat2, feat1, pos2, pos1, shape2, shape1)
+    return res11, res21, res22, res12
+
+
+@torch.no_grad()
+def forward_mast3r(pairs, model, cache_path, desc_conf="desc_conf", device="cuda", subsample=8, **matching_kw):
+    """sparse_ga.py:524-568.  Returns ({(name1, name2): ((key1, key2), key_corres)}, cache_path) where the keys index
+    the in-HBM memo (the reference returns file paths)."""
+    memo = _memo(cache_path)
+    res_paths = {}
+    for img1, img2 in pairs:
+        a, b = img1["instance"], img2["instance"]
+        if (b, a) in memo["corres"] and (a, b) not in memo["corres"]:
+            score, (xy1, xy2, confs) = memo["corres"][b, a]
+            memo["corres"][a, b] = (score, (xy2, xy1, confs))                        # :538-540
+        if not ((a, b) in memo["fwd"] and (b, a) in memo["fwd"] and (a, b) in memo["corres"]):
+            if model is None:
+                continue
+            res = symmetric_inference(model, img1, img2, device)
+            X11, X21, X22, X12 = [r["pts3d"][0].to(device).float().contiguous() for r in res]
+            C11, C21, C22, C12 = [r["conf"][0].to(device).float().contiguous() for r in res]
+            descs = [r["desc"][0].to(device) for r in res]
+            qonfs = [r[desc_conf][0].to(device) for r in res]
+            memo["fwd"][a, b] = (X11, C11, X21, C21)
+            memo["fwd"][b, a] = (X22, C22, X12, C12)
+            corres = match.extract_correspondences(descs, qonfs, device=device, subsample=subsample)
+            conf_score = (C11.mean() * C12.mean() * C21.mean() * C22.mean()).sqrt().sqrt()
+            memo["corres"][a, b] = ((float(conf_score), float(corres[2].sum()), len(corres[2])), corres)
+        res_paths[a, b] = ((a, b), (b, a)), (a, b)
+    return res_paths, cache_path
+
+
+def canonical_view(ptmaps11, confs11, subsample, mode="avg-angle"):
+    """sparse_ga.py:817-855 on the device (st3r_canonical_view)."""
+    if mode != "avg-angle":
+        raise NotImplementedError("only mode='avg-angle' is used by Starst3r (reconstruct.py:99)")
+    assert len(ptmaps11) == len(confs11) > 0, "not a single view1 for this image"
+    lib = _lib.load()
+    P, H, W, _ = ptmaps11.shape
+    dev = ptmaps11.device
+    canon = torch.empty(H, W, 3, device=dev)
+    canon2 = torch.empty(H, W, device=dev)
+    cconf = torch.empty(H, W, device=dev)
+    pt = ptmaps11.float().contiguous()
+    cf = confs11.float().contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(lib.st3r_canonical_view(_lib.ptr(pt), _lib.ptr(cf), P, H, W, subsample, _lib.ptr(canon),
+                                           _lib.ptr(canon2), _lib.ptr(cconf), _lib.stream_ptr()), "st3r_canonical_view")
+    return canon, canon2, cconf
+
+
+def estimate_focal_knowing_depth(pts3d, pp=None, focal_mode="weiszfeld", min_focal=0., max_focal=np.inf):
+    """dust3r/post_process.py:12-60, 'weiszfeld' with the principal point at the image centre (sparse_ga.py:696-698)."""
+    if focal_mode != "weiszfeld":
+        raise NotImplementedError("only focal_mode='weiszfeld' is on the Starst3r path")
+    lib = _lib.load()
+    B, H, W, _ = pts3d.shape
+    out = torch.empty(B, device=pts3d.device)
+    x = pts3d.float().contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.st3r_focal_weiszfeld(_lib.ptr(x), B, H, W, ctypes.c_float(min_focal),
+                                            ctypes.c_float(min(max_focal, 3.0e38)), _lib.ptr(out), _lib.stream_ptr()),
+                   "st3r_focal_weiszfeld")
+    return out
+
+
+def anchor_depth_offsets(canon_depth, pixels, subsample=8):
+    """sparse_ga.py:858-886: block-quantised anchor index and depth ratio to the block's core pixel."""
+    H1, W1 = canon_depth.shape
+    W2 = len(range(subsample // 2, W1, subsample))
+    core_idxs, core_offs = {}, {}
+    for img2, (xy1, _confs) in pixels.items():
+        px, py = xy1.long().T
+        cy = (py // subsample) * subsample + subsample // 2
+        cx = (px // subsample) * subsample + subsample // 2
+        core_idxs[img2] = (py // subsample) * W2 + (px // subsample)
+        core_offs[img2] = (canon_depth[py, px] / canon_depth[cy, cx]).detach()
+    return core_idxs, core_offs
+
+
+@torch.no_grad()
+def prepare_canonical_data(imgs, tmp_pairs, subsample, order_imgs=False, min_conf_thr=0, cache_path=None,
+                           device="cuda", **kw):
+    """sparse_ga.py:633-714."""
+    memo = _memo(cache_path)
+    canonical_views, canonical_paths, preds_21 = {}, [], {}
+    pairwise_scores = torch.zeros((len(imgs), len(imgs)), device=device)
+    for img in imgs:
+        canonical_paths.append((cache_path, img))
+        cached = memo["canon"].get(img)
+        pts, cfs, pixels = [], [], {}
+        for (img1, img2), ((key1, key2), key_corres) in tmp_pairs.items():
+            score = None
+            if img == img1:
+                X, C, X2, C2 = memo["fwd"][key1]
+                score, (xy1, xy2, confs) = memo["corres"][key_corres]
+                pixels[img2] = xy1, confs
+                preds_21.setdefault(img, {})[img2] = (X2[::subsample, ::subsample].reshape(-1, 3),
+                                                      C2[::subsample, ::subsample].ravel())
+            if img == img2:
+                X, C, X2, C2 = memo["fwd"][key2]
+                score, (xy1, xy2, confs) = memo["corres"][key_corres]
+                pixels[img1] = xy2, confs
+                preds_21.setdefault(img, {})[img1] = (X2[::subsample, ::subsample].reshape(-1, 3),
+                                                      C2[::subsample, ::subsample].ravel())
+            if score is not None:
+                i, j = imgs.index(img1), imgs.index(img2)
+                pairwise_scores[i, j] = pairwise_scores[j, i] = score[2]
+                if cached is None:
+                    pts.append(X)
+                    cfs.append(C)
+        if cached is None:
+            canon, canon2, cconf = canonical_view(torch.stack(pts), torch.stack(cfs), subsample, **kw)
+            focal = estimate_focal_knowing_depth(canon[None], None, "weiszfeld", min_focal=0.5, max_focal=3.5)
+            memo["canon"][img] = ((canon, canon2, cconf), focal)      # stays as computed on later add_images calls,
+        (canon, canon2, cconf), focal = memo["canon"][img]            # like the reference's file cache (quirk C-6)
+        H, W = canon.shape[:2]
+        pp = torch.tensor([W / 2, H / 2], device=device)
+        core_depth = canon[subsample // 2::subsample, subsample // 2::subsample, 2]
+        idxs, offsets = anchor_depth_offsets(canon2, pixels, subsample=subsample)
+        canonical_views[img] = (pp, (H, W), focal.view(1), core_depth, pixels, idxs, offsets)
+    return tmp_pairs, pairwise_scores, canonical_views, canonical_paths, preds_21
+
+
+def condense_data(imgs, tmp_paths, canonical_views, preds_21, dtype=torch.float32):
+    """sparse_ga.py:729-814: per-image anchors (pixel, core index, depth offset) + per-pair slices into them."""
+    set_imgs = set(imgs)
+    pps, shapes, focals, core_depth, img_anchors, tmp_pixels = [], [], [], [], {}, {}
+    for idx1, img1 in enumerate(imgs):
+        pp, shape, focal, anchors, pixels_confs, idxs, offsets = canonical_views[img1]
+        pps.append(pp); shapes.append(shape); focals.append(focal); core_depth.append(anchors)
+        uv, ii, oo, cur = [], [], [], 0
+        for img2, (pixels, match_confs) in pixels_confs.items():
+            if img2 not in set_imgs:
+                continue
+            assert len(pixels) == len(idxs[img2]) == len(offsets[img2])
+            uv.append(torch.cat((pixels, torch.ones_like(pixels[:, :1])), dim=-1))
+            ii.append(idxs[img2]); oo.append(offsets[img2])
+            tmp_pixels[img1, img2] = pixels.to(dtype), match_confs.to(dtype), slice(cur, cur + len(pixels))
+            cur += len(pixels)
+        img_anchors[idx1] = (torch.cat(uv), torch.cat(ii), torch.cat(oo))
+    all_confs, imgs_slices = [], []
+    corres2d = {i: [] for i in range(len(imgs))}
+    for img1, img2 in tmp_paths:
+        if (img1, img2) not in tmp_pixels or (img2, img1) not in tmp_pixels:
+            continue
+        pix1, confs1, slice1 = tmp_pixels[img1, img2]
+        pix2, confs2, slice2 = tmp_pixels[img2, img1]
+        i1, i2 = imgs.index(img1), imgs.index(img2)
+        confs = (confs1 * confs2).sqrt()
+        all_confs.append(confs)
+        imgs_slices.append(PairOfSlices(i1, slice1, pix1, canonical_views[img1][5][img2], i2, slice2, pix2,
+                                        canonical_views[img2][5][img1], confs, float(confs.sum())))
+        corres2d[i1].append((pix1, confs, i2, slice2))
+        corres2d[i2].append((pix2, confs, i1, slice1))
+    all_confs = torch.cat(all_confs)
+    corres = (all_confs, float(all_confs.sum()), imgs_slices)
+
+    def aggreg(i, ms):
+        pix, confs, j, sl = zip(*ms)
+        c = torch.cat(confs).to(dtype)
+        return i, torch.cat(pix).to(dtype), c, float(c.sum()), list(zip(j, sl))
+    corres2d = [aggreg(i, m) for i, m in corres2d.items()]
+    imsizes = torch.tensor([(W, H) for H, W in shapes], device=pps[0].device)
+    sub = {}
+    for imk in preds_21:
+        sub[imk] = {}
+        for im2k, (pred, conf) in preds_21[imk].items():
+            ia = img_anchors[imgs.index(im2k)][1]
+            sub[imk][im2k] = (pred[ia], conf[ia])
+    return imsizes, torch.stack(pps), torch.cat(focals), core_depth, img_anchors, corres, corres2d, sub
+
+
+def compute_min_spanning_tree(pws):
+    """sparse_ga.py:984-1009 (host, scipy): MST on -score, rooted at the node farthest from any leaf, BFS edge order."""
+    from scipy import sparse as sp
+    n = pws.shape[0]
+    g = sp.dok_array((n, n))
+    for i, j in pws.nonzero().cpu().tolist():
+        g[i, j] = -float(pws[i, j])
+    msp = sp.csgraph.minimum_spanning_tree(g)
+
+    def bfs_ranks(start):
+        order, _ = sp.csgraph.breadth_first_order(msp, start, directed=False)
+        ranks = np.arange(len(order))
+        ranks[order] = ranks.copy()
+        return ranks
+    r1 = bfs_ranks(0)
+    r2 = bfs_ranks(r1.argmax())
+    r1 = bfs_ranks(r2.argmax())
+    root = int(np.minimum(r1, r2).argmax())
+    order, pred = sp.csgraph.breadth_first_order(msp, root, directed=False)
+    return root, [(int(pred[i]), int(i)) for i in order[1:]]
+
+
+class SparseGA:
+    """Result object with the surface of sparse_ga.py:33-108."""
+
+    def __init__(self, img_paths, pairs_in, res_fine, anchors, canonical_paths=None, subsample=8):
+        def fetch(name):
+            for im1, im2 in pairs_in:
+                for im in (im1, im2):
+                    if im["instance"] == name:
+                        return (im["img"][0].permute(1, 2, 0).cpu().numpy() * .5 + .5).clip(min=0., max=1.)
+        self.canonical_paths, self.img_paths = canonical_paths, img_paths
+        self.imgs = [fetch(n) for n in img_paths]
+        self.intrinsics, self.cam2w = res_fine["intrinsics"], res_fine["cam2w"]
+        self.depthmaps, self.pts3d = res_fine["depthmaps"], res_fine["pts3d"]
+        self.working_device = self.cam2w.device
+        self.pts3d_colors = []
+        for i, im in enumerate(self.imgs):
+            x, y = anchors[i][0][..., :2].detach().cpu().long().numpy().T
+            self.pts3d_colors.append(im[y, x])
+            assert self.pts3d_colors[-1].shape == tuple(self.pts3d[i].shape)
+        self.n_imgs = len(self.imgs)
+        self.subsample = subsample
+
+    def get_focals(self):
+        return self.intrinsics[:, 0, 0].clone()
+
+    def get_principal_points(self):
+        return self.intrinsics[:, :2, 2].clone()
+
+    def get_im_poses(self):
+        return self.cam2w
+
+    def get_sparse_pts3d(self):
+        return self.pts3d
+
+    def get_pts3d_colors(self):
+        return self.pts3d_colors
+
+    def get_depthmaps(self):
+        return self.depthmaps
+
+    def get_masks(self):
+        return [slice(None, None) for _ in range(len(self.imgs))]
+
+    def get_dense_pts3d(self, clean_depth=True, subsample=8):
+        """sparse_ga.py:70-93 + clean_pointcloud (dust3r/cloud_opt/base_opt.py:369-405) on the device."""
+        assert self.canonical_paths, "cache_path is required for dense 3d points"
+        lib = _lib.load()
+        dev = self.cam2w.device
+        pts3d, depths, confs = [], [], []
+        cam_h = self.cam2w.detach().float().cpu().contiguous()
+        K_h = self.intrinsics.detach().float().cpu().contiguous()
+        for i, (cache_path, img) in enumerate(self.canonical_paths):
+            (canon, canon2, conf), focal = _memo(cache_path)["canon"][img]
+            H, W = conf.shape
+            p = torch.empty(H * W, 3, device=dev)
+            d = torch.empty(H * W, device=dev)
+            core = self.depthmaps[i].reshape(-1).float().contiguous()
+            c2 = canon2.contiguous()
+            with torch.cuda.device(dev):
+                _lib.check(lib.st3r_dense_points(_lib.ptr(c2), _lib.ptr(core), cam_h[i].numpy().ctypes.data_as(ctypes.c_void_p),
+                                                 K_h[i].numpy().ctypes.data_as(ctypes.c_void_p), ctypes.c_float(float(focal)),
+                                                 H, W, subsample, _lib.ptr(p), _lib.ptr(d), _lib.stream_ptr()),
+                           "st3r_dense_points")
+            pts3d.append(p); depths.append(d); confs.append(conf.clone())
+        if clean_depth:
+            confs = clean_pointcloud(confs, self.intrinsics, torch.linalg.inv(self.cam2w), depths, pts3d)
+        return pts3d, depths, confs
+
+
+def clean_pointcloud(im_confs, K, cams, depthmaps, all_pts3d, tol=0.001, bad_conf=0, dbg=()):
+    """dust3r/cloud_opt/base_opt.py:369-405 (all views must share one size, which Starst3r guarantees per scene)."""
+    assert len(im_confs) == len(cams) == len(K) == len(depthmaps) == len(all_pts3d)
+    assert 0 <= tol < 1
+    lib = _lib.load()
+    N = len(im_confs)
+    H, W = im_confs[0].shape
+    if any(c.shape != (H, W) for c in im_confs):
+        raise NotImplementedError("clean_pointcloud on B200 expects equally sized views")
+    dev = im_confs[0].device
+    conf = torch.stack([c.reshape(-1) for c in im_confs]).float().contiguous()
+    depth = torch.stack([d.reshape(-1) for d in depthmaps]).float().contiguous()
+    pts = torch.stack([p.reshape(-1, 3) for p in all_pts3d]).float().contiguous()
+    cm = torch.cat([cams[:, :3, :3].reshape(N, 9), cams[:, :3, 3], K.reshape(N, 9)], dim=1).float().contiguous()
+    assert cm.shape[1] == lib.st3r_clean_cam_floats()
+    with torch.cuda.device(dev):
+        _lib.check(lib.st3r_clean_pointcloud(_lib.ptr(pts), _lib.ptr(conf), _lib.ptr(depth), _lib.ptr(cm), N, H, W,
+                                             ctypes.c_float(tol), ctypes.c_float(bad_conf), _lib.stream_ptr()),
+                   "st3r_clean_pointcloud")
+    return [conf[i].reshape(H, W) for i in range(N)]
+
+
+def run_sparse_ga(imgs, pairs_in, cache_path, model, subsample=8, desc_conf="desc_conf", device="cuda",
+                  dtype=torch.float32, shared_intrinsics=False, optim_params=None, **kw):
+    """starster/reconstruct.py:75-113."""
+    pairs_in = convert_dust3r_pairs_naming(imgs, pairs_in)
+    pairs, cache_path = forward_mast3r(pairs_in, model, cache_path=cache_path, subsample=subsample,
+                                       desc_conf=desc_conf, device=device)
+    tmp_pairs, pairwise_scores, canonical_views, canonical_paths, preds_21 = prepare_canonical_data(
+        imgs, pairs, subsample, cache_path=cache_path, mode="avg-angle", device=device)
+    mst = compute_min_spanning_tree(pairwise_scores)
+    imsizes, pps, base_focals, core_depth, anchors, corres, corres2d, preds_21 = condense_data(
+        imgs, tmp_pairs, canonical_views, preds_21, dtype)
+    imgs, res_coarse, res_fine, optim_params = sparse_scene_optimizer_slam(
+        imgs, subsample, imsizes, pps, base_focals, core_depth, anchors, corres, corres2d, preds_21, canonical_paths,
+        mst, shared_intrinsics=shared_intrinsics, cache_path=cache_path, device=device, dtype=dtype,
+        prev_params=optim_params, **kw)
+    return SparseGA(imgs, pairs_in, res_fine or res_coarse, anchors, canonical_paths, subsample), optim_params
+
+
+def prepare_images_for_mast3r(imgs):
+    """starster/image.py:112-139."""
+    return [dict(img=im[None], true_shape=np.int32([im.shape[-2:]]), idx=i, instance=str(i)) for i, im in enumerate(imgs)]
+
+
+def reconstruct_scene(model, imgs, filelist, device, optim_params=None, tmpdir=None):
+    """starster/reconstruct.py:19-72: MASt3R inference (out of scope, any `model`) + matching + global alignment."""
+    import tempfile
+    imgs = prepare_images_for_mast3r(imgs)
+    pairs = make_pairs(imgs, scene_graph="complete", prefilter=None, symmetrize=True)
+    if tmpdir is None:
+        tmpdir = tempfile.mkdtemp()
+    return run_sparse_ga(filelist, pairs, tmpdir, model, lr1=0.07, niter1=500, lr2=0.014, niter2=200, device=device,
+                         opt_depth=False, matching_conf_thr=5, shared_intrinsics=False, optim_params=optim_params)
