@@ -49,7 +49,7 @@ def run_reference(sparse_ga, n_views, W, H, niter1, niter2, seed=0, low_conf=Fal
                         anchors=anchors, corres=corres, corres2d=corres2d, preds_21=preds_21c,
                         mst=(int(mst[0]), [(int(a), int(b)) for a, b in mst[1]])))
     out = {}
-    for tag, (n1, n2) in {"init": (0, 0), "short": (niter1, niter2)}.items():
+    for tag, (n1, n2) in {"init": (0, 0), "short": (niter1, niter2), "full": (300, 200)}.items():
         a = plain(dict(imsizes=imsizes, pps=pps, base_focals=base_focals, core_depth=core_depth))   # fresh copies:
         imsz, pp_, bf_, cd_ = a["imsizes"], a["pps"].clone(), a["base_focals"].clone(), [c.clone() for c in a["core_depth"]]
         _, res_c, res_f = sparse_ga.sparse_scene_optimizer(

@@ -30,7 +30,7 @@ struct Work {
   AlignCam* cam; AlignCamTmp* tmp; AlignCamGrad* cgrad;
   float* gcam;        // [N * 17]
   float* sums;        // [4]: main loss numerator, dust3r numerator, spare, stop flag
-  float* gscal;       // [2]: g (global scaling), arg-min index as float
+  float* gscal;       // [2]: g (global scaling), number of images attaining the minimum size, the minimum size
 };
 
 __global__ void __launch_bounds__(CAM_THREADS)
@@ -39,22 +39,24 @@ align_cam_fwd_kernel(St3rAlignProblem pb, Params p, Work w) {
   if (w.sums[3] != 0.f) return;   // NaN loss seen: the reference breaks out of the loop (reconstruct.py:398-399)
   const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
   __shared__ float s_min[CAM_THREADS];
-  __shared__ int s_arg[CAM_THREADS];
   float best = INFINITY;
-  int arg = 0;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     al_cam_local_fwd(ic[i], p.log_focal[i], p.log_size[i], p.quat + 4 * i, w.tmp[i]);
     float s = w.tmp[i].s;
-    if (s < best) { best = s; arg = i; }
+    best = fminf(best, s);
   }
-  s_min[threadIdx.x] = best; s_arg[threadIdx.x] = arg;
+  s_min[threadIdx.x] = best;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float b = INFINITY; int a = 0;
-    for (int t = 0; t < blockDim.x; ++t)
-      if (s_min[t] < b || (s_min[t] == b && s_arg[t] < a)) { b = s_min[t]; a = s_arg[t]; }
+    float b = INFINITY;
+    for (int t = 0; t < blockDim.x; ++t) b = fminf(b, s_min[t]);
+    // torch's sizes.min() backward splits the gradient evenly between tied minima (all sizes tie at the
+    // first iteration, when every log_size is 0), so remember how many images attain the minimum.
+    int ties = 0;
+    for (int i = 0; i < N; ++i) ties += (w.tmp[i].s == b) ? 1 : 0;
     w.gscal[0] = 1.0f / b;
-    w.gscal[1] = (float)a;
+    w.gscal[1] = (float)ties;
+    w.gscal[2] = b;
     al_chain_fwd(N, pb.root, pb.edges, w.tmp, p.trans);
   }
   __syncthreads();
@@ -269,7 +271,7 @@ align_cam_bwd_kernel(St3rAlignProblem pb, Params p, AdamState ad, Work w, int tr
   __shared__ float s_gg[CAM_THREADS];
   if (w.sums[3] != 0.f) return;
   const float g = w.gscal[0];
-  const int jstar = (int)w.gscal[1];
+  const float ties = w.gscal[1], smin = w.gscal[2];
   float gg = 0.f;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     al_cam_final_bwd(ic[i], p.pp + 2 * i, g, w.tmp[i], w.gcam + i * NG, w.cgrad[i]);
@@ -292,7 +294,7 @@ align_cam_bwd_kernel(St3rAlignProblem pb, Params p, AdamState ad, Work w, int tr
   const bool stop = false;  // the NaN iteration itself still steps, like the reference
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     float g_pp[2], g_lf, g_q[4], g_t[3], g_ls;
-    float extra = (i == jstar) ? -gg_total * g * g : 0.f;
+    float extra = (w.tmp[i].s == smin) ? -gg_total * g * g / ties : 0.f;
     al_cam_local_bwd(w.tmp[i], w.cgrad[i], extra, g_pp, &g_lf, g_q, g_t, &g_ls);
     if (grad_out) {
       float* o = grad_out + 11 * i;
@@ -352,7 +354,7 @@ Work carve(void* ws, int N) {
   w.cgrad = a.take<AlignCamGrad>(N);
   w.gcam = a.take<float>((size_t)N * NG);
   w.sums = a.take<float>(4);
-  w.gscal = a.take<float>(2);
+  w.gscal = a.take<float>(4);
   return w;
 }
 

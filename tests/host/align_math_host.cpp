@@ -24,11 +24,13 @@ extern "C" void host_align_eval(const St3rAlignProblem* prob, const float* pp, c
   std::vector<AlignCam> cam(N);
   std::vector<AlignCamGrad> cg(N);
   std::vector<float> gcam((size_t)N * 17, 0.f);
-  float smin = INFINITY; int jstar = 0;
+  float smin = INFINITY;
   for (int i = 0; i < N; ++i) {
     al_cam_local_fwd(ic[i], log_focal[i], log_size[i], quat + 4 * i, tmp[i]);
-    if (tmp[i].s < smin) { smin = tmp[i].s; jstar = i; }
+    if (tmp[i].s < smin) smin = tmp[i].s;
   }
+  int ties = 0;
+  for (int i = 0; i < N; ++i) ties += tmp[i].s == smin;
   const float g = 1.0f / smin;
   al_chain_fwd(N, pb.root, pb.edges, tmp.data(), trans);
   for (int i = 0; i < N; ++i) al_cam_final_fwd(ic[i], pp + 2 * i, g, tmp[i], cam[i]);
@@ -110,6 +112,6 @@ extern "C" void host_align_eval(const St3rAlignProblem* prob, const float* pp, c
   al_chain_bwd(N, pb.root, pb.edges, tmp.data(), trans, cg.data());
   for (int i = 0; i < N; ++i) {
     float* o = out_grad + 11 * i;
-    al_cam_local_bwd(tmp[i], cg[i], i == jstar ? -gg * g * g : 0.f, o, o + 2, o + 3, o + 7, o + 10);
+    al_cam_local_bwd(tmp[i], cg[i], tmp[i].s == smin ? -gg * g * g / ties : 0.f, o, o + 2, o + 3, o + 7, o + 10);
   }
 }

@@ -57,14 +57,37 @@ def test_optimizer_vs_reference(cuda_device, name):
     assert torch.allclose(r["cam2w"], ref0["cam2w"], atol=1e-5)
     for a, b in zip(r["pts3d"], ref0["pts3d"]):
         assert torch.allclose(a, b, atol=1e-4, rtol=1e-5)
-    # the short schedule the fixture was generated with (30 coarse + 20 fine iterations)
+    # the short schedule the fixture was generated with (30 coarse + 20 fine iterations): the trajectories coincide
     n1, n2 = f["niter"]
     _, res_c, res_f, params = run_slam(f, cuda_device, n1, n2)
-    assert_same_up_to_gauge(cpu(res_c), f["out"]["short"]["coarse"], 2e-3)
-    assert_same_up_to_gauge(cpu(res_f), f["out"]["short"]["fine"], 2e-3)
+    assert_same_up_to_gauge(cpu(res_c), f["out"]["short"]["coarse"], 1e-4)
+    assert_same_up_to_gauge(cpu(res_f), f["out"]["short"]["fine"], 1e-4)
     assert set(params) == {"pps", "log_focals", "quats", "trans", "log_sizes", "core_depth"}
     assert all(isinstance(p, torch.nn.Parameter) for p in params["quats"]) and len(params["quats"]) == 3
     assert abs(params["quats"][0].detach().norm().item() - 1) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["align_match3.pt", "align_dust3r3.pt"])
+def test_optimizer_long_schedule(cuda_device, name):
+    """300 + 200 iterations.  The coarse stage converges to the reference's solution.  The fine stage (gamma = 0.4
+    re-projection loss) is chaotic in the reference itself: perturbing the reference's loss weights by 1e-6 moves its
+    own focals by > 2 px on align_match3 (measured with oracle/align_oracle.py), so there parity is
+    stated on the loss reached, evaluated by the oracle at the returned parameters."""
+    f = fx(name)
+    _, res_c, res_f, params = run_slam(f, cuda_device, 300, 200)
+    assert_same_up_to_gauge(cpu(res_c), f["out"]["full"]["coarse"], 5e-3)
+    pb = ao.Problem(f["inputs"])
+    mine = dict(pps=torch.stack([p.detach().cpu() for p in params["pps"]]),
+                log_focals=torch.cat([p.detach().cpu() for p in params["log_focals"]]),
+                quats=torch.stack([p.detach().cpu() for p in params["quats"]]),
+                trans=torch.stack([p.detach().cpu() for p in params["trans"]]),
+                log_sizes=torch.cat([p.detach().cpu() for p in params["log_sizes"]]))
+    loss_mine = pb.total_loss(mine, 1, 0.4)[0].item()
+    _, _, p_ref, _ = ao.run(f["inputs"], lr1=f["lr"][0], niter1=300, lr2=f["lr"][1], niter2=200)
+    loss_ref = pb.total_loss({k: v.detach() for k, v in p_ref.items()}, 1, 0.4)[0].item()
+    assert abs(loss_mine - loss_ref) < 0.02 * abs(loss_ref), (loss_mine, loss_ref)
+    if name == "align_dust3r3.pt":      # well-conditioned case: the fine stage lands on the same solution too
+        assert_same_up_to_gauge(cpu(res_f), f["out"]["full"]["fine"], 5e-3)
 
 
 @pytest.mark.parametrize("name,mode", [("align_match3.pt", 0), ("align_match3.pt", 1), ("align_dust3r3.pt", 0)])
