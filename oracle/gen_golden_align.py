@@ -30,7 +30,7 @@ def plain(x):
 def run_reference(sparse_ga, n_views, W, H, niter1, niter2, seed=0, low_conf=False, lr1=0.07, lr2=0.014, pts_noise=0.0):
     from dust3r.image_pairs import make_pairs
     from starst3r_b200 import synth
-    model = synth.SyntheticMast3r(n_views, W, H, seed=seed, low_conf=low_conf, pts_noise=pts_noise)
+    model = synth.SyntheticMast3r(n_views, W, H, seed=seed, low_conf=low_conf, pts_noise=pts_noise, arc_deg=90.0)
     sparse_ga.symmetric_inference = lambda model, img1, img2, device: model.symmetric_inference(img1, img2)
     raw = model.images()
     imgs = [dict(img=im[None], true_shape=np.int32([im.shape[-2:]]), idx=i, instance=str(i)) for i, im in enumerate(raw)]

@@ -159,7 +159,7 @@ def test_scene_add_images_end_to_end(cuda_device):
     import starst3r_b200 as st
     from starst3r_b200 import synth
     W, H, n = 96, 64, 4
-    model = synth.SyntheticMast3r(n, W, H, seed=0, device=cuda_device)
+    model = synth.SyntheticMast3r(n, W, H, seed=0, device=cuda_device, arc_deg=100.0)
     scene = st.Scene(device=cuda_device)
     scene.add_images(model, model.images())
     assert scene.c2w.shape == (n, 4, 4) and scene.intrinsics.shape == (n, 3, 3) and len(scene.dense_pts) == n
