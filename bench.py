@@ -95,14 +95,8 @@ def make_workload(dev, seed):
 
 
 def allreduce_grads(fr, world):
-    import torch.distributed as dist
-    flat = torch.cat([fr.grads[k].reshape(-1) for k in ("means", "quats", "scales", "opacities", "sh")])
-    dist.all_reduce(flat)
-    off = 0
-    for k in ("means", "quats", "scales", "opacities", "sh"):
-        n = fr.grads[k].numel()
-        fr.grads[k].copy_(flat[off:off + n].view_as(fr.grads[k]))
-        off += n
+    from starst3r_b200 import dist as sd
+    sd.allreduce_gradients(fr.grads)
 
 
 def run_ours(args):

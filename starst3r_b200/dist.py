@@ -1,0 +1,78 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed; NCCL on the B200 box, gloo in the CPU tests).
+
+The reference is single-device; sharding is new capability:
+  * MATCH: unordered image pairs are independent (sparse_ga.py:529 loop body) -> pair p goes to rank p mod G; the
+    only communication is the final gather of the variable-length correspondence lists.
+  * RASTER training: camera views are sharded, the splat is replicated; per step ONE all-reduce (sum) of the
+    per-Gaussian gradients (23 floats per Gaussian), then every rank applies the same Adam update.
+  * ALIGN: replicas only (O(11 N) parameters, strictly sequential iterations): rank 0 computes, result is broadcast.
+"""
+import torch
+import torch.distributed as dist
+
+GRAD_KEYS = ("means", "quats", "scales", "opacities", "sh")
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_indices(n_items, rank=None, world_size=None):
+    """Round-robin ownership: item i belongs to rank i mod G."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    return list(range(rank, n_items, world_size))
+
+
+def unordered_pairs(n_views):
+    """The N(N-1)/2 pairs inference actually runs on (make_pairs 'complete' before symmetrisation)."""
+    return [(i, j) for i in range(n_views) for j in range(i)]
+
+
+def shard_pairs(n_views, rank=None, world_size=None):
+    pairs = unordered_pairs(n_views)
+    return [pairs[k] for k in shard_indices(len(pairs), rank, world_size)]
+
+
+def allreduce_gradients(grads, group=None):
+    """Sum the per-Gaussian gradient tensors over all ranks with a single collective (flatten -> all_reduce -> views)."""
+    _, w = world()
+    if w == 1:
+        return grads
+    flat = torch.cat([grads[k].reshape(-1) for k in GRAD_KEYS])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for k in GRAD_KEYS:
+        n = grads[k].numel()
+        grads[k].copy_(flat[off:off + n].view_as(grads[k]))
+        off += n
+    return grads
+
+
+def gather_varlen(t, group=None):
+    """All-gather of tensors whose first dimension differs per rank (correspondence lists): lengths first, then one
+    padded all_gather.  Returns the list of per-rank tensors (on every rank)."""
+    _, w = world()
+    if w == 1:
+        return [t]
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(w)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(max(sizes), 1)
+    pad = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    out = [torch.empty_like(pad) for _ in range(w)]
+    dist.all_gather(out, pad, group=group)
+    return [o[:s] for o, s in zip(out, sizes)]
+
+
+def broadcast_tensors(tensors, src=0, group=None):
+    _, w = world()
+    if w > 1:
+        for t in tensors:
+            dist.broadcast(t, src, group=group)
+    return tensors
