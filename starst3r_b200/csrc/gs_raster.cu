@@ -177,11 +177,38 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
         }
         br += col.x * fac; bg += col.y * fac; bb += col.z * fac;
       }
+      // Transposed butterfly: 8 of the 9 sums are reduced with 4+2+1+2 shuffles (instead of 8 x 5) by halving the
+      // number of live values at each exchange; afterwards lane l holds the warp total of value (l >> 2) and the 8
+      // lanes with (l & 3) == 0 issue their shared-memory atomics in parallel.  The 9th value takes the plain tree.
+      {
+        const unsigned full = 0xffffffffu;
+        const int lane = lane_id();
+        float a[4], b2[2], c1;
+        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) g[k] = warp_sum(g[k]);
-      if (lane_id() == 0) {
+        for (int k = 0; k < 4; ++k) {
+          float send = h16 ? g[k] : g[k + 4];
+          float keep = h16 ? g[k + 4] : g[k];
+          a[k] = keep + __shfl_xor_sync(full, send, 16);
+        }
 #pragma unroll
-        for (int k = 0; k < 9; ++k) atomicAdd(&acc[t][k], g[k]);
+        for (int k = 0; k < 2; ++k) {
+          float send = h8 ? a[k] : a[k + 2];
+          float keep = h8 ? a[k + 2] : a[k];
+          b2[k] = keep + __shfl_xor_sync(full, send, 8);
+        }
+        {
+          float send = h4 ? b2[0] : b2[1];
+          float keep = h4 ? b2[1] : b2[0];
+          c1 = keep + __shfl_xor_sync(full, send, 4);
+        }
+        c1 += __shfl_xor_sync(full, c1, 2);
+        c1 += __shfl_xor_sync(full, c1, 1);
+        const float g8 = warp_sum(g[8]);
+        // value index held by this lane: bit 4 of the lane selects +4, bit 3 selects +2, bit 2 selects +1
+        const int vi = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
+        if ((lane & 3) == 0 && c1 != 0.f) atomicAdd(&acc[t][vi], c1);
+        if (lane == 1 && g8 != 0.f) atomicAdd(&acc[t][8], g8);
       }
     }
     __syncthreads();

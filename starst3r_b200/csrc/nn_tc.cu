@@ -165,12 +165,28 @@ __device__ __noinline__ int push_candidates(Cand* list, int cnt, uint32_t mask, 
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 nn_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const float* __restrict__ Qsrc,
              const int32_t* __restrict__ qidx, const int32_t* __restrict__ count_ptr, int Mmax,
-             const float* __restrict__ DB, int N, int tiles_per_chunk, const float* __restrict__ db_norm2_max,
+             const float* __restrict__ DB, int N, int tiles_per_chunk, int dynamic,
+             const float* __restrict__ db_norm2_max,
              unsigned long long* __restrict__ packed, int32_t* __restrict__ ovf_flags) {
   const int M = count_ptr ? min(*count_ptr, Mmax) : Mmax;
-  const int m0 = blockIdx.y * BM;
+  int m_tile = blockIdx.y, chunk = blockIdx.x;
+  if (dynamic) {
+    // The live query count is only known on the device (reciprocal-search tail iterations shrink it from
+    // thousands to a handful): re-derive the (query tile, DB chunk) decomposition from it so that the
+    // whole grid stays busy instead of the few CTAs a host-side split for Mmax would leave.
+    const int mtiles = (M + BM - 1) / BM;
+    if (mtiles == 0) return;
+    const int ntiles_total = (N + BN - 1) / BN;
+    int nchunks = max(1, min(ntiles_total, (int)gridDim.x / mtiles));
+    tiles_per_chunk = (ntiles_total + nchunks - 1) / nchunks;
+    nchunks = (ntiles_total + tiles_per_chunk - 1) / tiles_per_chunk;
+    m_tile = blockIdx.x / nchunks;
+    chunk = blockIdx.x - m_tile * nchunks;
+    if (m_tile >= mtiles) return;
+  }
+  const int m0 = m_tile * BM;
   if (m0 >= M) return;
-  const int n_begin = blockIdx.x * tiles_per_chunk * BN;
+  const int n_begin = chunk * tiles_per_chunk * BN;
   if (n_begin >= N) return;
   const int n_end = min(N, n_begin + tiles_per_chunk * BN);
   const int ntiles = (n_end - n_begin + BN - 1) / BN;
@@ -441,9 +457,15 @@ int nn_tc_launch(const float* Qsrc, const int32_t* qidx, const int32_t* count_pt
   int nchunks = max(1, min(ntiles_total, (waves * slots) / mtiles));
   int tiles_per_chunk = (ntiles_total + nchunks - 1) / nchunks;
   nchunks = (ntiles_total + tiles_per_chunk - 1) / tiles_per_chunk;
-  dim3 grid(nchunks, mtiles);
-  nn_tc_kernel<<<grid, NUM_THREADS, SMEM_DYN, stream>>>(tmap, Qsrc, qidx, count_ptr, Mmax, DB, N, tiles_per_chunk,
-                                                        db_norm_bound, packed, ovf_flags);
+  if (count_ptr && mtiles <= slots) {
+    // device-side decomposition (see the kernel): one wave of `slots` CTAs
+    nn_tc_kernel<<<dim3(slots), NUM_THREADS, SMEM_DYN, stream>>>(tmap, Qsrc, qidx, count_ptr, Mmax, DB, N, 0, 1,
+                                                                 db_norm_bound, packed, ovf_flags);
+  } else {
+    dim3 grid(nchunks, mtiles);
+    nn_tc_kernel<<<grid, NUM_THREADS, SMEM_DYN, stream>>>(tmap, Qsrc, qidx, count_ptr, Mmax, DB, N, tiles_per_chunk, 0,
+                                                          db_norm_bound, packed, ovf_flags);
+  }
   ST3R_CHECK_LAUNCH();
   int wpb = 8;
   nn_tc_overflow_kernel<<<(Mmax + wpb - 1) / wpb, wpb * 32, 0, stream>>>(Qsrc, qidx, count_ptr, Mmax, DB, N, packed,

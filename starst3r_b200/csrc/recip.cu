@@ -23,8 +23,8 @@ struct RecipState {
   uint8_t* notyet;
   int32_t* active[2];  // ping-pong active slot lists
   int32_t* counts;     // counts[h] = active length before half-iteration h
-  int32_t* qidx;       // query row indices of the current half-iteration
-  unsigned long long* packed;
+  int32_t* qidx[2];    // query row indices of the current / next half-iteration (ping-pong)
+  unsigned long long* packed[2];
   int32_t* ovf;        // tcgen05 candidate-overflow flags
 };
 
@@ -43,31 +43,25 @@ __global__ void recip_init(RecipState st, int n, int nx, int S, int W1, const in
   st.xy[1][i] = -1; st.old[1][i] = -1;
   st.notyet[i] = 1;
   st.active[0][i] = i;
+  st.qidx[0][i] = s;          // first half-iteration queries P1[seed]
+  st.packed[0][i] = 0ull;
 }
 
-// qidx[i] = xy_src[active[i]]; clears the packed result slots.
-__global__ void recip_prepare(const int32_t* __restrict__ xy_src, const int32_t* __restrict__ active,
-                              const int32_t* __restrict__ count_ptr, int32_t* __restrict__ qidx,
-                              unsigned long long* __restrict__ packed) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= *count_ptr) return;
-  qidx[i] = xy_src[active[i]];
-  packed[i] = 0ull;
-}
-
-// Scatter NN results, drop converged slots, build the next active list.
+// Scatter NN results, drop converged slots, build the next active list and - because the next half-iteration
+// queries exactly the rows just found (P_dst[xy_dst[slot]]) - its query index list and cleared result slots.
 __global__ void recip_update(int32_t* __restrict__ xy_dst, int32_t* __restrict__ old_dst,
                              uint8_t* __restrict__ notyet, const int32_t* __restrict__ active,
                              const int32_t* __restrict__ count_ptr,
                              const unsigned long long* __restrict__ packed,
-                             int32_t* __restrict__ active_next, int32_t* __restrict__ count_next) {
+                             int32_t* __restrict__ active_next, int32_t* __restrict__ count_next,
+                             int32_t* __restrict__ qidx_next, unsigned long long* __restrict__ packed_next) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool in = i < *count_ptr;
   bool keep = false;
-  int s = 0;
+  int s = 0, j = 0;
   if (in) {
     s = active[i];
-    int j = nn_unpack_idx(packed[i]);
+    j = nn_unpack_idx(packed[i]);
     xy_dst[s] = j;
     keep = old_dst[s] != j;
     old_dst[s] = j;
@@ -79,7 +73,12 @@ __global__ void recip_update(int32_t* __restrict__ xy_dst, int32_t* __restrict__
     int base = 0;
     if (lane_id() == leader) base = atomicAdd(count_next, __popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (keep) active_next[base + __popc(m & ((1u << lane_id()) - 1u))] = s;
+    if (keep) {
+      int pos = base + __popc(m & ((1u << lane_id()) - 1u));
+      active_next[pos] = s;
+      qidx_next[pos] = j;
+      packed_next[pos] = 0ull;
+    }
   }
 }
 
@@ -209,8 +208,10 @@ size_t carve(RecipWs* w, void* ws, size_t ws_bytes, int nseed_max, int key_cap, 
   }
   t.st.notyet = a.take<uint8_t>(nseed_max);
   t.st.counts = a.take<int32_t>(2 * max_iter + 2);
-  t.st.qidx = a.take<int32_t>(nseed_max);
-  t.st.packed = a.take<unsigned long long>(nseed_max);
+  for (int s = 0; s < 2; ++s) {
+    t.st.qidx[s] = a.take<int32_t>(nseed_max);
+    t.st.packed[s] = a.take<unsigned long long>(nseed_max);
+  }
   t.st.ovf = a.take<int32_t>(nseed_max);
   t.keys = a.take<uint64_t>(key_cap);
   t.keys_alt = a.take<uint64_t>(key_cap);
@@ -257,17 +258,18 @@ int run_recip(const RecipWs& w, const float* P1, int HW1, int W1, const float* P
       const int src = half, dst = 1 - half;
       const int32_t* act = st.active[h & 1];
       int32_t* act_next = st.active[(h + 1) & 1];
-      recip_prepare<<<nblk(nseed), TPB, 0, stream>>>(st.xy[src], act, st.counts + h, st.qidx, st.packed);
-      ST3R_CHECK_LAUNCH();
+      int32_t* qidx = st.qidx[h & 1];
+      unsigned long long* packed = st.packed[h & 1];
       int rc;
       if (use_tc)
-        rc = nn_tc_launch(P[src], st.qidx, st.counts + h, nseed, P[dst], HW[dst], d, w.norm_bound + dst,
-                          st.packed, st.ovf, stream);
+        rc = nn_tc_launch(P[src], qidx, st.counts + h, nseed, P[dst], HW[dst], d, w.norm_bound + dst, packed, st.ovf,
+                          stream);
       else
-        rc = nn_simt_launch(P[src], st.qidx, st.counts + h, nseed, P[dst], HW[dst], d, st.packed, stream);
+        rc = nn_simt_launch(P[src], qidx, st.counts + h, nseed, P[dst], HW[dst], d, packed, stream);
       if (rc) return rc;
-      recip_update<<<nblk(nseed), TPB, 0, stream>>>(st.xy[dst], st.old[dst], st.notyet, act,
-                                                    st.counts + h, st.packed, act_next, st.counts + h + 1);
+      recip_update<<<nblk(nseed), TPB, 0, stream>>>(st.xy[dst], st.old[dst], st.notyet, act, st.counts + h, packed,
+                                                    act_next, st.counts + h + 1, st.qidx[(h + 1) & 1],
+                                                    st.packed[(h + 1) & 1]);
       ST3R_CHECK_LAUNCH();
     }
   }
