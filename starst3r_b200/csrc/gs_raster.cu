@@ -31,6 +31,23 @@ __device__ __forceinline__ TileRange tile_range(const int32_t* __restrict__ offs
   return r;
 }
 
+// Conservative set of tile rows (bit i = row i of the 16x16 tile) on which a Gaussian can pass the
+// alpha >= 1/255 test: opac * exp(-sigma) >= 1/255  <=>  d^T Q d <= 2 ln(255 opac), whose bounding box has the
+// vertical half-extent sqrt(2 L cov_yy), cov_yy = a / (a c - b^2).  A small margin keeps the cull strictly
+// conservative w.r.t. fp32 rounding of sigma, so results are unchanged; a warp (two pixel rows) skips every
+// Gaussian whose mask misses its rows without evaluating a single alpha.
+__device__ __forceinline__ uint32_t row_mask(const float4 A, const float4 B, int tile_y0) {
+  const float L = logf(255.0f * A.z);
+  if (!(L > 0.f)) return 0u;
+  const float det = B.x * B.z - B.y * B.y;
+  if (!(det > 0.f)) return 0xffffu;
+  const float hy = sqrtf(2.0f * L * B.x / det) * 1.0005f + 2e-3f;
+  const float lo = ceilf(A.y - hy - 0.5f) - (float)tile_y0, hi = floorf(A.y + hy - 0.5f) - (float)tile_y0;
+  if (hi < 0.f || lo > 15.f) return 0u;
+  const int ilo = max(0, (int)lo), ihi = min(15, (int)hi);
+  return ((2u << ihi) - 1u) & ~((1u << ilo) - 1u);
+}
+
 __global__ void __launch_bounds__(BLOCK)
 raster_fwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
                   const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
@@ -38,12 +55,14 @@ raster_fwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
                   int tile_h, float* __restrict__ render, float* __restrict__ alphas, int32_t* __restrict__ last_ids,
                   unsigned long long* __restrict__ n_blend) {
   __shared__ float4 sA[BLOCK], sB[BLOCK], sC[BLOCK];
+  __shared__ uint32_t sM[BLOCK];
   const int c = blockIdx.y, tile = blockIdx.x;
   const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
   const int tr = threadIdx.x;
   const int i = tyi * TILE + (tr >> 4), j = txi * TILE + (tr & 15);
   const float px = (float)j + 0.5f, py = (float)i + 0.5f;
   const bool inside = i < H && j < W;
+  const uint32_t my_rows = 3u << (2 * (tr >> 5));   // the two tile rows this warp owns
   bool done = !inside;
   const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
   const int nb = (rg.hi - rg.lo + BLOCK - 1) / BLOCK;
@@ -55,13 +74,16 @@ raster_fwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
     const int idx = start + tr;
     if (idx < rg.hi) {
       uint32_t e = flatten[idx];
-      sA[tr] = geomA[e];
-      sB[tr] = geomB[e];
+      const float4 A = geomA[e], B = geomB[e];
+      sA[tr] = A;
+      sB[tr] = B;
       sC[tr] = rgb[e];
+      sM[tr] = row_mask(A, B, tyi * TILE);
     }
     __syncthreads();
     const int bs = min(BLOCK, rg.hi - start);
     for (int t = 0; t < bs && !done; ++t) {
+      if (!(sM[t] & my_rows)) continue;   // warp-uniform cull
       const float4 A = sA[t], B = sB[t];
       const float dx = A.x - px, dy = A.y - py;
       const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
@@ -103,7 +125,7 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
                   const float* __restrict__ v_render, const float* __restrict__ v_alphas,
                   float4* __restrict__ v_geomA, float4* __restrict__ v_geomB, float4* __restrict__ v_rgb) {
   __shared__ float4 sA[BLOCK], sB[BLOCK], sC[BLOCK];
-  __shared__ uint32_t sE[BLOCK];
+  __shared__ uint32_t sE[BLOCK], sM[BLOCK];
   __shared__ float acc[BLOCK][9];  // per-batch gradient accumulators (xy 2, opac 1, conic 3, rgb 3)
   const int c = blockIdx.y, tile = blockIdx.x;
   const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
@@ -111,6 +133,7 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
   const int i = tyi * TILE + (tr >> 4), j = txi * TILE + (tr & 15);
   const float px = (float)j + 0.5f, py = (float)i + 0.5f;
   const bool inside = i < H && j < W;
+  const uint32_t my_rows = 3u << (2 * (tr >> 5));
   const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
   if (rg.hi <= rg.lo) return;
   const size_t p = ((size_t)c * H + min(i, H - 1)) * W + min(j, W - 1);
@@ -134,15 +157,18 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
     const int idx = batch_end - tr;
     if (idx >= rg.lo) {
       uint32_t e = flatten[idx];
+      const float4 A = geomA[e], B = geomB[e];
       sE[tr] = e;
-      sA[tr] = geomA[e];
-      sB[tr] = geomB[e];
+      sA[tr] = A;
+      sB[tr] = B;
       sC[tr] = rgb[e];
+      sM[tr] = row_mask(A, B, tyi * TILE);
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[tr][k] = 0.f;
     __syncthreads();
     for (int t = max(0, batch_end - warp_bin_final); t < bs; ++t) {
+      if (!(sM[t] & my_rows)) continue;   // warp-uniform cull (see row_mask)
       bool valid = inside && (batch_end - t <= bin_final);
       float alpha = 0.f, opac = 0.f, vis = 0.f, dx = 0.f, dy = 0.f;
       float4 B = make_float4(0.f, 0.f, 0.f, 0.f);
