@@ -50,6 +50,10 @@ ST3R_API int st3r_device_sm_count(void);
 /* Number of CUDA kernels this library has launched in this process (all entry points). */
 ST3R_API uint64_t st3r_launch_count(void);
 
+/* Diagnostic: cycle counters of the tcgen05 matcher's epilogue warp in CTA 0, h_out4 (HOST) = {tiles, cycles
+ * waiting for an accumulator, cycles in the arg-max epilogue, cycles of the whole tile loop}; reset != 0 clears. */
+ST3R_API int st3r_debug_nn_tc_cycles(unsigned long long* h_out4, int reset);
+
 /* ------------------------------------------------------------------ MATCH */
 
 /* Row arg-max of Q·DBᵀ (dot-product nearest neighbour), ties -> lowest index.

@@ -23,7 +23,7 @@ def _ctype(decl: str):
     if base == "const":
         base = decl.split()[1]
     return {"int": ctypes.c_int, "size_t": ctypes.c_size_t, "float": ctypes.c_float, "double": ctypes.c_double,
-            "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint32_t": ctypes.c_uint32, "uint64_t": ctypes.c_uint64,
+            "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint32_t": ctypes.c_uint32, "uint64_t": ctypes.c_uint64, "unsigned": ctypes.c_uint64,
             "cudaStream_t": ctypes.c_void_p, "void": None}[base]
 
 

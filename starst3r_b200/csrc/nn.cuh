@@ -25,7 +25,8 @@ int nn_simt_launch(const float* Qsrc, const int32_t* qidx, const int32_t* count_
 
 // tcgen05 (TF32 tensor-core) candidate search + exact fp32 re-score.  Same contract.
 // `db_norm_bound` = device pointer to max_j ||DB_j||_2^2 (float), see nn_db_norm_launch;
-// `ovf_flags` = int32 scratch [Mmax] (rows whose candidate list overflowed; cleared inside).
+// `ovf_flags` = int32 scratch [Mmax], ALL ZERO on entry and left all zero on exit (rows whose candidate list
+// overflowed are flagged by the main kernel and cleared by the exact redo kernel).
 int nn_tc_launch(const float* Qsrc, const int32_t* qidx, const int32_t* count_ptr, int Mmax,
                  const float* DB, int N, int d, const float* db_norm_bound,
                  unsigned long long* packed, int32_t* ovf_flags, cudaStream_t stream);

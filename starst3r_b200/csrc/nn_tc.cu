@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include "common.cuh"
 #include "nn.cuh"
+#include "../../include/starst3r_b200.h"
 
 namespace {
 
@@ -104,9 +105,13 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
+#ifdef NN_TC_FMNMX3
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
+#else
+  return fmaxf(fmaxf(a, b), c);
+#endif
 }
 
 // K-major, 128-byte swizzle, dense 8-row groups (SBO = 1024 B), sm_100 descriptor version 1.
@@ -134,6 +139,10 @@ __device__ __forceinline__ float exact_score(const float* __restrict__ q, const 
 }
 
 struct Cand { int j; float s; };
+
+// Diagnostic cycle counters (epilogue warp of CTA 0): [0] tiles, [1] cycles waiting for the accumulator,
+// [2] cycles in the arg-max epilogue proper, [3] total cycles of the tile loop.  Read by st3r_debug_nn_tc_cycles().
+__device__ unsigned long long g_nn_tc_cycles[4];
 
 constexpr int CAND_OVERFLOW = 0x100;
 
@@ -285,21 +294,31 @@ nn_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const float* __restric
     }
     float run_max = row_ok ? -INFINITY : INFINITY;  // padded rows never trigger
 
+    const bool dbg = (blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0);
+    unsigned long long c_wait = 0, c_epi = 0;
+    const long long c_start = clock64();
     for (int t = 0; t < ntiles; ++t) {
       int a = t & 1;
       uint32_t aph = (uint32_t)(t >> 1) & 1u;
+      const long long c0 = clock64();
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
+      const long long c1 = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * BN);
       const int col_base = n_begin + t * BN;
       const bool ragged = col_base + BN > n_end;
-      float v[2][32];
-      tc_ld32(taddr, v[0]);
+      // Pull the whole 128-column accumulator row into registers with four back-to-back tcgen05.ld (their
+      // latencies overlap; waiting per 32-column chunk serialised ~200 cycles four times per tile), then hand
+      // the TMEM stage back to the MMA warp BEFORE the arg-max arithmetic so tile t+2 can start immediately.
+      float v[BN];
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) tc_ld32(taddr + c * 32, v + c * 32);
       tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(tempty_bar(a));
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
-        if (c + 1 < BN / 32) tc_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
-        float* x = v[c & 1];
+        float* x = v + c * 32;
         if (ragged) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
@@ -320,10 +339,15 @@ nn_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const float* __restric
           for (int i = 0; i < 32; ++i) mask |= (x[i] >= thr ? 1u : 0u) << i;
           cnt = push_candidates(list, cnt, mask, col_base + c * 32, cmax, thr);
         }
-        if (c + 1 < BN / 32) tc_wait_ld();
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(a));
+      c_wait += (unsigned long long)(c1 - c0);
+      c_epi += (unsigned long long)(clock64() - c1);
+    }
+    if (dbg) {
+      atomicAdd(&g_nn_tc_cycles[0], (unsigned long long)ntiles);
+      atomicAdd(&g_nn_tc_cycles[1], c_wait);
+      atomicAdd(&g_nn_tc_cycles[2], c_epi);
+      atomicAdd(&g_nn_tc_cycles[3], (unsigned long long)(clock64() - c_start));
     }
 
     if (row_ok) {
@@ -356,7 +380,7 @@ nn_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const float* __restric
 __global__ void nn_tc_overflow_kernel(const float* __restrict__ Qsrc, const int32_t* __restrict__ qidx,
                                       const int32_t* __restrict__ count_ptr, int Mmax,
                                       const float* __restrict__ DB, int N,
-                                      unsigned long long* __restrict__ packed, const int32_t* __restrict__ ovf_flags) {
+                                      unsigned long long* __restrict__ packed, int32_t* __restrict__ ovf_flags) {
   const int M = count_ptr ? min(*count_ptr, Mmax) : Mmax;
   int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= M || !ovf_flags[r]) return;
@@ -372,7 +396,10 @@ __global__ void nn_tc_overflow_kernel(const float* __restrict__ Qsrc, const int3
     int jo = __shfl_xor_sync(0xffffffffu, bj, off);
     if (so > bs || (so == bs && jo < bj)) { bs = so; bj = jo; }
   }
-  if (lane_id() == 0 && bj != 0x7fffffff) atomicMax(packed + r, nn_pack(bs, bj));
+  if (lane_id() == 0) {
+    if (bj != 0x7fffffff) atomicMax(packed + r, nn_pack(bs, bj));
+    ovf_flags[r] = 0;   // consumed: the flag array stays all-zero between calls, so callers clear it only once
+  }
 }
 
 __global__ void db_norm_kernel(const float* __restrict__ DB, int N, int d, uint32_t* __restrict__ out_bits) {
@@ -406,6 +433,15 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace
 
 bool nn_tc_supported(int d) { return d == DK; }
+
+extern "C" int st3r_debug_nn_tc_cycles(unsigned long long* h_out4, int reset) {
+  if (h_out4) ST3R_CHECK_CUDA(cudaMemcpyFromSymbol(h_out4, g_nn_tc_cycles, sizeof(g_nn_tc_cycles)));
+  if (reset) {
+    unsigned long long z[4] = {0, 0, 0, 0};
+    ST3R_CHECK_CUDA(cudaMemcpyToSymbol(g_nn_tc_cycles, z, sizeof(z)));
+  }
+  return ST3R_OK;
+}
 
 int nn_db_norm_launch(const float* DB, int N, int d, float* out_bound, cudaStream_t stream) {
   ST3R_CHECK_CUDA(cudaMemsetAsync(out_bound, 0, sizeof(float), stream));
@@ -447,7 +483,6 @@ int nn_tc_launch(const float* Qsrc, const int32_t* qidx, const int32_t* count_pt
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
     attr_set = true;
   }
-  ST3R_CHECK_CUDA(cudaMemsetAsync(ovf_flags, 0, (size_t)Mmax * sizeof(int32_t), stream));
   const int mtiles = (Mmax + BM - 1) / BM;
   const int ntiles_total = (N + BN - 1) / BN;
   // Chunk the DB so that the grid is (close to) a whole number of waves of 2 CTAs per SM: long chunks keep

@@ -244,6 +244,7 @@ int run_recip(const RecipWs& w, const float* P1, int HW1, int W1, const float* P
   ST3R_CHECK_LAUNCH();
   bool use_tc = (impl == ST3R_NN_TCGEN05) || (impl == ST3R_NN_AUTO && nn_tc_supported(d));
   if (use_tc) {
+    ST3R_CHECK_CUDA(cudaMemsetAsync(st.ovf, 0, (size_t)nseed * sizeof(int32_t), stream));
     int rc = nn_db_norm_launch(P1, HW1, d, w.norm_bound + 0, stream);
     if (rc) return rc;
     rc = nn_db_norm_launch(P2, HW2, d, w.norm_bound + 1, stream);
@@ -324,6 +325,7 @@ int st3r_nn_argmax(const float* Q, int M, const float* DB, int N, int d, int32_t
   bool use_tc = (impl == ST3R_NN_TCGEN05) || (impl == ST3R_NN_AUTO && nn_tc_supported(d) && M >= 64);
   if (impl == ST3R_NN_TCGEN05) ST3R_CHECK_ARG(nn_tc_supported(d), "st3r_nn_argmax: tcgen05 path needs d=24");
   if (use_tc && N > 0) {
+    ST3R_CHECK_CUDA(cudaMemsetAsync(ovf, 0, (size_t)M * sizeof(int32_t), stream));
     rc = nn_db_norm_launch(DB, N, d, bound, stream);
     if (rc) return rc;
     rc = nn_tc_launch(Q, nullptr, nullptr, M, DB, N, d, bound, packed, ovf, stream);
