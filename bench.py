@@ -274,7 +274,7 @@ def run_ours(args):
             "blends_per_sec": n_blend * world / (shares.get("st3r_gs_raster_fwd", float("nan")) * 1e-3),
             "blends_per_frame": n_blend, "intersections": n_isect, "visible": n_vis, "loss": float(loss.item()),
             "match": match_res}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -324,7 +324,7 @@ def run_reference(args):
                                    "configs[1]; each step = bounded sample of 1 view"},
             "cpu_baseline": best,
             "e2e": {"value": best["value"], "unit": "Gaussians/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
 
 
 def main():
@@ -336,11 +336,25 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # Exactly ONE line goes to stdout (the JSON): libraries that chat on fd 1 (NCCL prints its version there) are
+    # diverted to stderr until the result is ready.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    _emit.fd = saved
     if args.impl == "reference":
         return run_reference(args)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback")
     run_ours(args)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_emit.fd, (json.dumps(line) + "\n").encode())
+
+
+_emit.fd = 1
 
 
 if __name__ == "__main__":
