@@ -32,3 +32,13 @@ int nn_tc_launch(const float* Qsrc, const int32_t* qidx, const int32_t* count_pt
                  unsigned long long* packed, int32_t* ovf_flags, cudaStream_t stream);
 int nn_db_norm_launch(const float* DB, int N, int d, float* out_bound, cudaStream_t stream);
 bool nn_tc_supported(int d);
+
+// Batched form: up to NN_MAX_BATCH independent NN problems in ONE launch (the four seeded searches of an image
+// pair advance in lock-step, so batching them divides the length of the launch chain by four).
+constexpr int NN_MAX_BATCH = 4;
+struct NnBatchItem {
+  const float* Qsrc; const int32_t* qidx; const int32_t* count_ptr; int Mmax;
+  const float* DB; int N; const float* db_norm_bound;
+  unsigned long long* packed; int32_t* ovf_flags;
+};
+int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stream);

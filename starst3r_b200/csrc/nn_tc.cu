@@ -171,12 +171,28 @@ __device__ __noinline__ int push_candidates(Cand* list, int cnt, uint32_t mask, 
   return cnt;
 }
 
+struct NnTcParams {
+  CUtensorMap tmap[NN_MAX_BATCH];
+  NnBatchItem it[NN_MAX_BATCH];
+  int tiles_per_chunk;
+  int dynamic;
+};
+
 __global__ void __launch_bounds__(NUM_THREADS, 2)
-nn_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const float* __restrict__ Qsrc,
-             const int32_t* __restrict__ qidx, const int32_t* __restrict__ count_ptr, int Mmax,
-             const float* __restrict__ DB, int N, int tiles_per_chunk, int dynamic,
-             const float* __restrict__ db_norm2_max,
-             unsigned long long* __restrict__ packed, int32_t* __restrict__ ovf_flags) {
+nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
+  const NnBatchItem& it = prm.it[blockIdx.z];
+  const CUtensorMap* tmap_db = &prm.tmap[blockIdx.z];
+  const float* __restrict__ Qsrc = it.Qsrc;
+  const int32_t* __restrict__ qidx = it.qidx;
+  const int32_t* __restrict__ count_ptr = it.count_ptr;
+  const int Mmax = it.Mmax;
+  const float* __restrict__ DB = it.DB;
+  const int N = it.N;
+  const float* __restrict__ db_norm2_max = it.db_norm_bound;
+  unsigned long long* __restrict__ packed = it.packed;
+  int32_t* __restrict__ ovf_flags = it.ovf_flags;
+  int tiles_per_chunk = prm.tiles_per_chunk;
+  const int dynamic = prm.dynamic;
   const int M = count_ptr ? min(*count_ptr, Mmax) : Mmax;
   int m_tile = blockIdx.y, chunk = blockIdx.x;
   if (dynamic) {
@@ -250,7 +266,7 @@ nn_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const float* __restric
         uint32_t ph = (uint32_t)(t / STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
         mbar_arrive_expect_tx(full_bar(s), BN * ROWB);
-        tma_load_2d(sB + s * BN * ROWB, &tmap_db, 0, n_begin + t * BN, full_bar(s));
+        tma_load_2d(sB + s * BN * ROWB, tmap_db, 0, n_begin + t * BN, full_bar(s));
       }
     }
   } else if (warp == 1) {
@@ -294,7 +310,7 @@ nn_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const float* __restric
     }
     float run_max = row_ok ? -INFINITY : INFINITY;  // padded rows never trigger
 
-    const bool dbg = (blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0);
+    const bool dbg = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0);
     unsigned long long c_wait = 0, c_epi = 0;
     const long long c_start = clock64();
     for (int t = 0; t < ntiles; ++t) {
@@ -377,11 +393,17 @@ nn_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const float* __restric
 }
 
 // Exact redo of rows whose candidate list overflowed: one warp per row.
-__global__ void nn_tc_overflow_kernel(const float* __restrict__ Qsrc, const int32_t* __restrict__ qidx,
-                                      const int32_t* __restrict__ count_ptr, int Mmax,
-                                      const float* __restrict__ DB, int N,
-                                      unsigned long long* __restrict__ packed, int32_t* __restrict__ ovf_flags) {
-  const int M = count_ptr ? min(*count_ptr, Mmax) : Mmax;
+struct NnOvfParams { NnBatchItem it[NN_MAX_BATCH]; };
+
+__global__ void nn_tc_overflow_kernel(const NnOvfParams prm) {
+  const NnBatchItem& it = prm.it[blockIdx.y];
+  const float* __restrict__ Qsrc = it.Qsrc;
+  const int32_t* __restrict__ qidx = it.qidx;
+  const float* __restrict__ DB = it.DB;
+  const int N = it.N;
+  unsigned long long* __restrict__ packed = it.packed;
+  int32_t* __restrict__ ovf_flags = it.ovf_flags;
+  const int M = it.count_ptr ? min(*it.count_ptr, it.Mmax) : it.Mmax;
   int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= M || !ovf_flags[r]) return;
   const float* q = Qsrc + (qidx ? (size_t)qidx[r] : (size_t)r) * DK;
@@ -452,13 +474,7 @@ int nn_db_norm_launch(const float* DB, int N, int d, float* out_bound, cudaStrea
   return ST3R_OK;
 }
 
-int nn_tc_launch(const float* Qsrc, const int32_t* qidx, const int32_t* count_ptr, int Mmax, const float* DB,
-                 int N, int d, const float* db_norm_bound, unsigned long long* packed, int32_t* ovf_flags,
-                 cudaStream_t stream) {
-  if (Mmax <= 0 || N <= 0) return ST3R_OK;
-  ST3R_CHECK_ARG(d == DK, "nn_tc: only d == 24 is supported (got %d)", d);
-  ST3R_CHECK_ARG(((uintptr_t)DB % 16) == 0 && ((uintptr_t)Qsrc % 16) == 0, "nn_tc: operands must be 16-byte aligned");
-  ST3R_CHECK_ARG(ovf_flags && db_norm_bound, "nn_tc: missing scratch");
+static int encode_db_tmap(CUtensorMap* tmap, const float* DB, int N) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) {
     st3r_set_error("nn_tc: cuTensorMapEncodeTiled is unavailable in this driver");
@@ -466,45 +482,85 @@ int nn_tc_launch(const float* Qsrc, const int32_t* qidx, const int32_t* count_pt
   }
   // DB viewed as a [N, 24] fp32 tensor; the box is [128 rows, 32 floats]: the 8 out-of-bounds
   // floats per row are zero-filled by TMA, which pads K to the 128-byte swizzle span for free.
-  CUtensorMap tmap;
   cuuint64_t gdim[2] = {(cuuint64_t)DK, (cuuint64_t)N};
   cuuint64_t gstride[1] = {(cuuint64_t)DK * sizeof(float)};
   cuuint32_t box[2] = {32, (cuuint32_t)BN};
   cuuint32_t estr[2] = {1, 1};
-  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(DB), gdim, gstride, box, estr,
+  CUresult cr = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(DB), gdim, gstride, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) {
     st3r_set_error("nn_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
     return ST3R_ERR_CUDA;
   }
+  return ST3R_OK;
+}
+
+int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stream) {
+  ST3R_CHECK_ARG(n >= 1 && n <= NN_MAX_BATCH, "nn_tc: batch size must be 1..%d", NN_MAX_BATCH);
+  ST3R_CHECK_ARG(d == DK, "nn_tc: only d == 24 is supported (got %d)", d);
+  NnTcParams prm;
+  NnOvfParams ovf;
+  int m = 0, max_M = 0;
+  bool all_counts = true;
+  for (int i = 0; i < n; ++i) {
+    const NnBatchItem& it = items[i];
+    if (it.Mmax <= 0 || it.N <= 0) continue;
+    ST3R_CHECK_ARG(((uintptr_t)it.DB % 16) == 0 && ((uintptr_t)it.Qsrc % 16) == 0, "nn_tc: operands must be 16-byte aligned");
+    ST3R_CHECK_ARG(it.ovf_flags && it.db_norm_bound && it.packed, "nn_tc: missing scratch");
+    int rc = encode_db_tmap(&prm.tmap[m], it.DB, it.N);
+    if (rc) return rc;
+    prm.it[m] = it;
+    ovf.it[m] = it;
+    max_M = max(max_M, it.Mmax);
+    all_counts = all_counts && it.count_ptr != nullptr;
+    ++m;
+  }
+  if (m == 0) return ST3R_OK;
+  for (int i = m; i < NN_MAX_BATCH; ++i) { prm.tmap[i] = prm.tmap[0]; prm.it[i] = prm.it[0]; ovf.it[i] = ovf.it[0]; }
   static bool attr_set = false;
   if (!attr_set) {
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
     attr_set = true;
   }
-  const int mtiles = (Mmax + BM - 1) / BM;
-  const int ntiles_total = (N + BN - 1) / BN;
-  // Chunk the DB so that the grid is (close to) a whole number of waves of 2 CTAs per SM: long chunks keep
-  // the per-row candidate restarts rare, and a partial last wave would idle most of the chip.
   const int slots = 2 * st3r_num_sms();
-  int waves = max(1, (mtiles * ((ntiles_total + MAX_TILES_PER_CHUNK - 1) / MAX_TILES_PER_CHUNK) + slots - 1) / slots);
-  int nchunks = max(1, min(ntiles_total, (waves * slots) / mtiles));
-  int tiles_per_chunk = (ntiles_total + nchunks - 1) / nchunks;
-  nchunks = (ntiles_total + tiles_per_chunk - 1) / tiles_per_chunk;
-  if (count_ptr && mtiles <= slots) {
-    // device-side decomposition (see the kernel): one wave of `slots` CTAs
-    nn_tc_kernel<<<dim3(slots), NUM_THREADS, SMEM_DYN, stream>>>(tmap, Qsrc, qidx, count_ptr, Mmax, DB, N, 0, 1,
-                                                                 db_norm_bound, packed, ovf_flags);
+  const int mtiles = (max_M + BM - 1) / BM;
+  if (all_counts && mtiles <= slots) {
+    // device-side decomposition (see the kernel): one wave of `slots` CTAs per problem
+    prm.tiles_per_chunk = 0;
+    prm.dynamic = 1;
+    nn_tc_kernel<<<dim3(slots, 1, m), NUM_THREADS, SMEM_DYN, stream>>>(prm);
+    ST3R_CHECK_LAUNCH();
   } else {
-    dim3 grid(nchunks, mtiles);
-    nn_tc_kernel<<<grid, NUM_THREADS, SMEM_DYN, stream>>>(tmap, Qsrc, qidx, count_ptr, Mmax, DB, N, tiles_per_chunk, 0,
-                                                          db_norm_bound, packed, ovf_flags);
+    // host-side decomposition, one problem per launch.  Chunk the DB so that the grid is (close to) a whole number
+    // of waves of 2 CTAs per SM: long chunks keep the per-row candidate restarts rare, and a partial last wave
+    // would idle most of the chip.
+    for (int i = 0; i < m; ++i) {
+      NnTcParams one = prm;
+      one.tmap[0] = prm.tmap[i];
+      one.it[0] = prm.it[i];
+      const int mt = (prm.it[i].Mmax + BM - 1) / BM;
+      const int ntiles_total = (prm.it[i].N + BN - 1) / BN;
+      int waves = max(1, (mt * ((ntiles_total + MAX_TILES_PER_CHUNK - 1) / MAX_TILES_PER_CHUNK) + slots - 1) / slots);
+      int nchunks = max(1, min(ntiles_total, (waves * slots) / mt));
+      int tiles_per_chunk = (ntiles_total + nchunks - 1) / nchunks;
+      nchunks = (ntiles_total + tiles_per_chunk - 1) / tiles_per_chunk;
+      one.tiles_per_chunk = tiles_per_chunk;
+      one.dynamic = 0;
+      nn_tc_kernel<<<dim3(nchunks, mt, 1), NUM_THREADS, SMEM_DYN, stream>>>(one);
+      ST3R_CHECK_LAUNCH();
+    }
   }
-  ST3R_CHECK_LAUNCH();
-  int wpb = 8;
-  nn_tc_overflow_kernel<<<(Mmax + wpb - 1) / wpb, wpb * 32, 0, stream>>>(Qsrc, qidx, count_ptr, Mmax, DB, N, packed,
-                                                                         ovf_flags);
+  const int wpb = 8;
+  nn_tc_overflow_kernel<<<dim3((max_M + wpb - 1) / wpb, m), wpb * 32, 0, stream>>>(ovf);
   ST3R_CHECK_LAUNCH();
   return ST3R_OK;
+}
+
+int nn_tc_launch(const float* Qsrc, const int32_t* qidx, const int32_t* count_ptr, int Mmax, const float* DB,
+                 int N, int d, const float* db_norm_bound, unsigned long long* packed, int32_t* ovf_flags,
+                 cudaStream_t stream) {
+  if (Mmax <= 0 || N <= 0) return ST3R_OK;
+  NnBatchItem it{Qsrc, qidx, count_ptr, Mmax, DB, N, db_norm_bound, packed, ovf_flags};
+  return nn_tc_launch_batch(&it, 1, d, stream);
 }

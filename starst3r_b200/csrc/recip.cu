@@ -28,16 +28,28 @@ struct RecipState {
   int32_t* ovf;        // tcgen05 candidate-overflow flags
 };
 
-__global__ void recip_init(RecipState st, int n, int nx, int S, int W1, const int32_t* seeds, int ncounts) {
+constexpr int RB = NN_MAX_BATCH;
+// Up to four seeded searches advanced in lock-step (blockIdx.y selects the search).
+struct RecipBatch {
+  RecipState st[RB];
+  int nseed[RB], nx[RB], W1[RB], swap[RB], set[RB];
+  const int32_t* seeds[RB];
+  int S, n;
+};
+
+__global__ void recip_init(RecipBatch b, int ncounts) {
+  const RecipState& st = b.st[blockIdx.y];
+  const int n = b.nseed[blockIdx.y];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < ncounts) st.counts[i] = (i == 0) ? n : 0;
   if (i >= n) return;
   int32_t s;
-  if (seeds) {
-    s = seeds[i];
+  if (b.seeds[blockIdx.y]) {
+    s = b.seeds[blockIdx.y][i];
   } else {
+    const int nx = b.nx[blockIdx.y], S = b.S;
     int y = S / 2 + (i / nx) * S, x = S / 2 + (i % nx) * S;
-    s = x + W1 * y;
+    s = x + b.W1[blockIdx.y] * y;
   }
   st.xy[0][i] = s; st.old[0][i] = s;
   st.xy[1][i] = -1; st.old[1][i] = -1;
@@ -45,18 +57,20 @@ __global__ void recip_init(RecipState st, int n, int nx, int S, int W1, const in
   st.active[0][i] = i;
   st.qidx[0][i] = s;          // first half-iteration queries P1[seed]
   st.packed[0][i] = 0ull;
+  st.ovf[i] = 0;
 }
 
 // Scatter NN results, drop converged slots, build the next active list and - because the next half-iteration
 // queries exactly the rows just found (P_dst[xy_dst[slot]]) - its query index list and cleared result slots.
-__global__ void recip_update(int32_t* __restrict__ xy_dst, int32_t* __restrict__ old_dst,
-                             uint8_t* __restrict__ notyet, const int32_t* __restrict__ active,
-                             const int32_t* __restrict__ count_ptr,
-                             const unsigned long long* __restrict__ packed,
-                             int32_t* __restrict__ active_next, int32_t* __restrict__ count_next,
-                             int32_t* __restrict__ qidx_next, unsigned long long* __restrict__ packed_next) {
+__global__ void recip_update(RecipBatch b, int h, int dst) {
+  const RecipState& st = b.st[blockIdx.y];
+  int32_t* __restrict__ xy_dst = st.xy[dst];
+  int32_t* __restrict__ old_dst = st.old[dst];
+  const int32_t* __restrict__ active = st.active[h & 1];
+  int32_t* __restrict__ active_next = st.active[(h + 1) & 1];
+  const unsigned long long* __restrict__ packed = st.packed[h & 1];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool in = i < *count_ptr;
+  bool in = i < st.counts[h];
   bool keep = false;
   int s = 0, j = 0;
   if (in) {
@@ -65,29 +79,29 @@ __global__ void recip_update(int32_t* __restrict__ xy_dst, int32_t* __restrict__
     xy_dst[s] = j;
     keep = old_dst[s] != j;
     old_dst[s] = j;
-    if (!keep) notyet[s] = 0;
+    if (!keep) st.notyet[s] = 0;
   }
   unsigned m = __ballot_sync(0xffffffffu, keep);
   if (m) {
     int leader = __ffs(m) - 1;
     int base = 0;
-    if (lane_id() == leader) base = atomicAdd(count_next, __popc(m));
+    if (lane_id() == leader) base = atomicAdd(st.counts + h + 1, __popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (keep) {
       int pos = base + __popc(m & ((1u << lane_id()) - 1u));
       active_next[pos] = s;
-      qidx_next[pos] = j;
-      packed_next[pos] = 0ull;
+      st.qidx[(h + 1) & 1][pos] = j;
+      st.packed[(h + 1) & 1][pos] = 0ull;
     }
   }
 }
 
 // Append converged (idx_a, idx_b) pairs as sort keys:  key = idx1<<33 | idx2<<1 | set.
-__global__ void recip_collect(const int32_t* __restrict__ xy1, const int32_t* __restrict__ xy2,
-                              const uint8_t* __restrict__ notyet, int n, int swap, int set,
-                              uint64_t* __restrict__ keys, int32_t* __restrict__ nkeys, int cap) {
+__global__ void recip_collect(RecipBatch b, uint64_t* __restrict__ keys, int32_t* __restrict__ nkeys, int cap) {
+  const RecipState& st = b.st[blockIdx.y];
+  const int n = b.nseed[blockIdx.y];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool conv = i < n && notyet[i] == 0;
+  bool conv = i < n && st.notyet[i] == 0;
   unsigned m = __ballot_sync(0xffffffffu, conv);
   if (!m) return;
   int leader = __ffs(m) - 1;
@@ -96,9 +110,9 @@ __global__ void recip_collect(const int32_t* __restrict__ xy1, const int32_t* __
   base = __shfl_sync(0xffffffffu, base, leader);
   if (conv) {
     int pos = base + __popc(m & ((1u << lane_id()) - 1u));
-    uint32_t a = (uint32_t)xy1[i], b = (uint32_t)xy2[i];
-    if (swap) { uint32_t t = a; a = b; b = t; }
-    if (pos < cap) keys[pos] = ((uint64_t)a << 33) | ((uint64_t)b << 1) | (uint64_t)set;
+    uint32_t a = (uint32_t)st.xy[0][i], c = (uint32_t)st.xy[1][i];
+    if (b.swap[blockIdx.y]) { uint32_t t = a; a = c; c = t; }
+    if (pos < cap) keys[pos] = ((uint64_t)a << 33) | ((uint64_t)c << 1) | (uint64_t)b.set[blockIdx.y];
   }
 }
 
@@ -190,7 +204,7 @@ int bits_for(long long n) {  // number of bits needed to represent values < n
 }
 
 struct RecipWs {
-  RecipState st;
+  RecipState st[RB];
   uint64_t* keys; uint64_t* keys_alt;
   uint32_t* vals; uint32_t* vals_alt;
   int32_t* nkeys;
@@ -198,27 +212,28 @@ struct RecipWs {
   void* sort_ws; size_t sort_ws_bytes;
 };
 
-size_t carve(RecipWs* w, void* ws, size_t ws_bytes, int nseed_max, int key_cap, int max_iter, bool dry) {
+size_t carve(RecipWs* w, void* ws, size_t ws_bytes, int nseed_max, int key_cap, int max_iter, bool dry, int nprob = 1) {
   WsAlloc a(dry ? (void*)0 : ws, dry ? (size_t)-1 : ws_bytes);
   RecipWs t;
-  for (int s = 0; s < 2; ++s) {
-    t.st.xy[s] = a.take<int32_t>(nseed_max);
-    t.st.old[s] = a.take<int32_t>(nseed_max);
-    t.st.active[s] = a.take<int32_t>(nseed_max);
+  for (int p = 0; p < RB; ++p) {
+    if (p >= nprob) { t.st[p] = t.st[0]; continue; }
+    for (int s = 0; s < 2; ++s) {
+      t.st[p].xy[s] = a.take<int32_t>(nseed_max);
+      t.st[p].old[s] = a.take<int32_t>(nseed_max);
+      t.st[p].active[s] = a.take<int32_t>(nseed_max);
+      t.st[p].qidx[s] = a.take<int32_t>(nseed_max);
+      t.st[p].packed[s] = a.take<unsigned long long>(nseed_max);
+    }
+    t.st[p].notyet = a.take<uint8_t>(nseed_max);
+    t.st[p].counts = a.take<int32_t>(2 * max_iter + 2);
+    t.st[p].ovf = a.take<int32_t>(nseed_max);
   }
-  t.st.notyet = a.take<uint8_t>(nseed_max);
-  t.st.counts = a.take<int32_t>(2 * max_iter + 2);
-  for (int s = 0; s < 2; ++s) {
-    t.st.qidx[s] = a.take<int32_t>(nseed_max);
-    t.st.packed[s] = a.take<unsigned long long>(nseed_max);
-  }
-  t.st.ovf = a.take<int32_t>(nseed_max);
   t.keys = a.take<uint64_t>(key_cap);
   t.keys_alt = a.take<uint64_t>(key_cap);
   t.vals = a.take<uint32_t>(key_cap);
   t.vals_alt = a.take<uint32_t>(key_cap);
   t.nkeys = a.take<int32_t>(4);
-  t.norm_bound = a.take<float>(4);
+  t.norm_bound = a.take<float>(8);
   t.sort_ws_bytes = radix_sort_ws_bytes(key_cap);
   t.sort_ws = a.take<char>(t.sort_ws_bytes);
   if (w) *w = t;
@@ -233,49 +248,59 @@ int seed_count(int H, int W, int S, int* nx_out) {
   return ny * nx;
 }
 
-// One seeded reciprocal search P1 -> P2 -> P1 ...; appends converged pairs to w.keys.
-int run_recip(const RecipWs& w, const float* P1, int HW1, int W1, const float* P2, int HW2, int d,
-              int nseed, int nx, int S, const int32_t* seeds, int max_iter, int swap, int set,
-              int key_cap, int impl, cudaStream_t stream) {
-  if (nseed <= 0) return ST3R_OK;
-  const RecipState& st = w.st;
-  int ncounts = 2 * max_iter + 2;
-  recip_init<<<nblk(max(nseed, ncounts)), TPB, 0, stream>>>(st, nseed, nx, S, W1, seeds, ncounts);
-  ST3R_CHECK_LAUNCH();
-  bool use_tc = (impl == ST3R_NN_TCGEN05) || (impl == ST3R_NN_AUTO && nn_tc_supported(d));
-  if (use_tc) {
-    ST3R_CHECK_CUDA(cudaMemsetAsync(st.ovf, 0, (size_t)nseed * sizeof(int32_t), stream));
-    int rc = nn_db_norm_launch(P1, HW1, d, w.norm_bound + 0, stream);
-    if (rc) return rc;
-    rc = nn_db_norm_launch(P2, HW2, d, w.norm_bound + 1, stream);
-    if (rc) return rc;
+struct RecipProblem {
+  const float* P1; int HW1, W1;      // seeds live in map 1
+  const float* P2; int HW2;
+  int nseed, nx; const int32_t* seeds;
+  int swap, set;
+  const float* norm1; const float* norm2;   // device max ||row||^2 of P1 / P2 (tcgen05 path)
+};
+
+// n seeded reciprocal searches P1 -> P2 -> P1 ... advanced in lock-step; converged pairs are appended to w.keys.
+int run_recip_batch(const RecipWs& w, const RecipProblem* pr, int n, int d, int S, int max_iter, int key_cap, int impl,
+                    cudaStream_t stream) {
+  RecipBatch b;
+  b.S = S; b.n = n;
+  int max_seed = 0;
+  for (int p = 0; p < RB; ++p) {
+    const RecipProblem& q = pr[p < n ? p : 0];
+    b.st[p] = w.st[p < n ? p : 0];
+    b.nseed[p] = p < n ? q.nseed : 0;
+    b.nx[p] = q.nx > 0 ? q.nx : 1; b.W1[p] = q.W1; b.swap[p] = q.swap; b.set[p] = q.set; b.seeds[p] = q.seeds;
+    if (p < n) max_seed = max(max_seed, q.nseed);
   }
-  const float* P[2] = {P1, P2};
-  const int HW[2] = {HW1, HW2};
+  if (max_seed <= 0) return ST3R_OK;
+  const int ncounts = 2 * max_iter + 2;
+  recip_init<<<dim3(nblk(max(max_seed, ncounts)), n), TPB, 0, stream>>>(b, ncounts);
+  ST3R_CHECK_LAUNCH();
+  const bool use_tc = (impl == ST3R_NN_TCGEN05) || (impl == ST3R_NN_AUTO && nn_tc_supported(d));
   int h = 0;
   for (int it = 0; it < max_iter; ++it) {
     for (int half = 0; half < 2; ++half, ++h) {
       // half 0: query rows P1[xy1[active]] against DB P2 -> xy2;  half 1: the converse.
-      const int src = half, dst = 1 - half;
-      const int32_t* act = st.active[h & 1];
-      int32_t* act_next = st.active[(h + 1) & 1];
-      int32_t* qidx = st.qidx[h & 1];
-      unsigned long long* packed = st.packed[h & 1];
-      int rc;
-      if (use_tc)
-        rc = nn_tc_launch(P[src], qidx, st.counts + h, nseed, P[dst], HW[dst], d, w.norm_bound + dst, packed, st.ovf,
-                          stream);
-      else
-        rc = nn_simt_launch(P[src], qidx, st.counts + h, nseed, P[dst], HW[dst], d, packed, stream);
+      const int dst = 1 - half;
+      NnBatchItem items[RB];
+      for (int p = 0; p < n; ++p) {
+        const RecipProblem& q = pr[p];
+        const RecipState& st = w.st[p];
+        items[p] = NnBatchItem{half == 0 ? q.P1 : q.P2, st.qidx[h & 1], st.counts + h, q.nseed,
+                               half == 0 ? q.P2 : q.P1, half == 0 ? q.HW2 : q.HW1, half == 0 ? q.norm2 : q.norm1,
+                               st.packed[h & 1], st.ovf};
+      }
+      int rc = ST3R_OK;
+      if (use_tc) {
+        rc = nn_tc_launch_batch(items, n, d, stream);
+      } else {
+        for (int p = 0; p < n && rc == ST3R_OK; ++p)
+          rc = nn_simt_launch(items[p].Qsrc, items[p].qidx, items[p].count_ptr, items[p].Mmax, items[p].DB, items[p].N, d,
+                              items[p].packed, stream);
+      }
       if (rc) return rc;
-      recip_update<<<nblk(nseed), TPB, 0, stream>>>(st.xy[dst], st.old[dst], st.notyet, act, st.counts + h, packed,
-                                                    act_next, st.counts + h + 1, st.qidx[(h + 1) & 1],
-                                                    st.packed[(h + 1) & 1]);
+      recip_update<<<dim3(nblk(max_seed), n), TPB, 0, stream>>>(b, h, dst);
       ST3R_CHECK_LAUNCH();
     }
   }
-  recip_collect<<<nblk(nseed), TPB, 0, stream>>>(st.xy[0], st.xy[1], st.notyet, nseed, swap, set,
-                                                 w.keys, w.nkeys, key_cap);
+  recip_collect<<<dim3(nblk(max_seed), n), TPB, 0, stream>>>(b, w.keys, w.nkeys, key_cap);
   ST3R_CHECK_LAUNCH();
   return ST3R_OK;
 }
@@ -358,8 +383,15 @@ int st3r_recip_nn(const float* P1, int H1, int W1, const float* P2, int H2, int 
   ST3R_CHECK_ARG(ws && ws_bytes >= need, "st3r_recip_nn: workspace too small (%zu < %zu)", ws_bytes, need);
   ST3R_CHECK_CUDA(cudaMemsetAsync(w.nkeys, 0, 4 * sizeof(int32_t), stream));
   if (nseed == 0) { ST3R_CHECK_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int32_t), stream)); return ST3R_OK; }
-  int rc = run_recip(w, P1, H1 * W1, W1, P2, H2 * W2, d, nseed, nx, subsample, seeds, max_iter, 0, 0,
-                     nseed, impl, stream);
+  const bool use_tc = (impl == ST3R_NN_TCGEN05) || (impl == ST3R_NN_AUTO && nn_tc_supported(d));
+  if (use_tc) {
+    int rc = nn_db_norm_launch(P1, H1 * W1, d, w.norm_bound + 0, stream);
+    if (rc) return rc;
+    rc = nn_db_norm_launch(P2, H2 * W2, d, w.norm_bound + 1, stream);
+    if (rc) return rc;
+  }
+  RecipProblem pr{P1, H1 * W1, W1, P2, H2 * W2, nseed, nx, seeds, 0, 0, w.norm_bound + 0, w.norm_bound + 1};
+  int rc = run_recip_batch(w, &pr, 1, d, subsample, max_iter, nseed, impl, stream);
   if (rc) return rc;
   UniqueOut out = {};
   out.idx1 = out_idx1; out.idx2 = out_idx2; out.n_out = n_out; out.W1 = W1; out.W2 = W2;
@@ -391,7 +423,7 @@ int st3r_extract_corres_cap(int H1, int W1, int H2, int W2, int subsample) {
 
 size_t st3r_extract_corres_ws_bytes(int H1, int W1, int H2, int W2, int subsample, int max_iter) {
   int n1 = seed_count(H1, W1, subsample, nullptr), n2 = seed_count(H2, W2, subsample, nullptr);
-  return carve(nullptr, nullptr, 0, max(max(n1, n2), 1), max(2 * (n1 + n2), 1), max_iter, true);
+  return carve(nullptr, nullptr, 0, max(max(n1, n2), 1), max(2 * (n1 + n2), 1), max_iter, true, 4);
 }
 
 int st3r_extract_corres(const float* feat11, const float* feat21, const float* feat22, const float* feat12,
@@ -409,18 +441,25 @@ int st3r_extract_corres(const float* feat11, const float* feat21, const float* f
   int n1 = seed_count(H1, W1, subsample, &nx1), n2 = seed_count(H2, W2, subsample, &nx2);
   int cap = 2 * (n1 + n2);
   RecipWs w;
-  size_t need = carve(&w, ws, ws_bytes, max(max(n1, n2), 1), max(cap, 1), max_iter, false);
+  size_t need = carve(&w, ws, ws_bytes, max(max(n1, n2), 1), max(cap, 1), max_iter, false, 4);
   ST3R_CHECK_ARG(ws && ws_bytes >= need, "st3r_extract_corres: workspace too small (%zu < %zu)", ws_bytes, need);
   ST3R_CHECK_CUDA(cudaMemsetAsync(w.nkeys, 0, 4 * sizeof(int32_t), stream));
-  // sparse_ga.py:612-620 - two descriptor sets, each matched in both directions.
-  const float* A[2] = {feat11, feat12};
-  const float* B[2] = {feat21, feat22};
-  for (int set = 0; set < 2; ++set) {
-    int rc = run_recip(w, A[set], H1 * W1, W1, B[set], H2 * W2, d, n1, nx1, subsample, nullptr, max_iter, 0,
-                       set, cap, impl, stream);
-    if (rc) return rc;
-    rc = run_recip(w, B[set], H2 * W2, W2, A[set], H1 * W1, d, n2, nx2, subsample, nullptr, max_iter, 1,
-                   set, cap, impl, stream);
+  // sparse_ga.py:612-620 - two descriptor sets, each matched in both directions: four searches in lock-step.
+  const bool use_tc = (impl == ST3R_NN_TCGEN05) || (impl == ST3R_NN_AUTO && nn_tc_supported(d));
+  const float* maps[4] = {feat11, feat21, feat12, feat22};
+  if (use_tc) {
+    for (int k = 0; k < 4; ++k) {
+      int rc = nn_db_norm_launch(maps[k], (k & 1) ? H2 * W2 : H1 * W1, d, w.norm_bound + k, stream);
+      if (rc) return rc;
+    }
+  }
+  RecipProblem pr[4] = {
+      {feat11, H1 * W1, W1, feat21, H2 * W2, n1, nx1, nullptr, 0, 0, w.norm_bound + 0, w.norm_bound + 1},
+      {feat21, H2 * W2, W2, feat11, H1 * W1, n2, nx2, nullptr, 1, 0, w.norm_bound + 1, w.norm_bound + 0},
+      {feat12, H1 * W1, W1, feat22, H2 * W2, n1, nx1, nullptr, 0, 1, w.norm_bound + 2, w.norm_bound + 3},
+      {feat22, H2 * W2, W2, feat12, H1 * W1, n2, nx2, nullptr, 1, 1, w.norm_bound + 3, w.norm_bound + 2}};
+  {
+    int rc = run_recip_batch(w, pr, 4, d, subsample, max_iter, cap, impl, stream);
     if (rc) return rc;
   }
   UniqueOut out = {};
