@@ -181,6 +181,41 @@ ST3R_API int st3r_adam_step(int n_seg, float* const* h_params, const float* cons
                    const int* h_ld_grad, double lr, double beta1, double beta2, double eps, int step,
                    cudaStream_t stream);
 
+/* ------------------------------------------------------------------ MCMC strategy
+ * gsplat.MCMCStrategy as driven by starster/gs.py:43-45 (construction), :146-147 (step_pre_backward, a no-op for
+ * MCMC) and :163-164 (step_post_backward(..., lr=1e-3)); gsplat 1.4 strategy/mcmc.py + strategy/ops.py semantics
+ * (SURVEY.md Appendix A.8).  Random draws (torch.randn_like, torch.multinomial) stay with the caller so the RNG
+ * stream is the reference's; these entry points are deterministic given the draws. */
+
+/* inject_noise_to_position: means += Sigma * (noise * op_sigmoid(1 - sigmoid(opacity)) * scaler), Sigma from
+ * normalised wxyz quats and exp(scales); op_sigmoid(x) = 1 / (1 + exp(-100 (x - 0.995))).  noise [N,3] ~ N(0,1). */
+ST3R_API int st3r_mcmc_inject_noise(float* means, const float* quats, const float* scales, const float* opacities,
+                           const float* noise, int N, float scaler, cudaStream_t stream);
+/* compute_relocation(opacities, scales, ratios, binoms): ACTIVATED opacities [N] / scales [N,3], ratios [N] int32
+ * (clamped to [1, n_max]), binoms [n_max, n_max] (binoms[n,k] = C(n,k)) -> new_opacities [N], new_scales [N,3]. */
+ST3R_API int st3r_mcmc_compute_relocation(const float* opacities, const float* scales, const int32_t* ratios,
+                                 const float* binoms, int n_max, int N, float* new_opacities, float* new_scales,
+                                 cudaStream_t stream);
+/* Dead / alive split of MCMCStrategy._relocate_gs: probs[i] = sigmoid(opacities_raw[i]); dead <=> probs <= min_opacity.
+ * dead_idx / alive_idx (capacity N, ascending = torch.nonzero order), alive_probs[k] = probs[alive_idx[k]],
+ * *n_dead (device). */
+ST3R_API size_t st3r_mcmc_partition_ws_bytes(int N);
+ST3R_API int st3r_mcmc_partition(const float* opacities_raw, int N, float min_opacity, int32_t* dead_idx, int32_t* alive_idx,
+                        float* probs, float* alive_probs, int32_t* n_dead, void* ws, size_t ws_bytes,
+                        cudaStream_t stream);
+/* relocate() / sample_add() of gsplat strategy/ops.py on RAW parameters (opacities = logit, scales = log).
+ * sampled [n] int64 = torch.multinomial draws; source s_i = alive_idx ? alive_idx[sampled[i]] : sampled[i];
+ * destination d_i = dst ? dst[i] : dst_base + i (dead rows for relocate; appended rows N.. for sample_add, the
+ * tensors must already have room).  ratio = bincount(sources)[s_i] + 1; the sources AND destinations receive
+ * logit(clamp(new_opacity, min_opacity, 1 - eps)) / log(new_scale); every other parameter tensor (h_row_ptrs[k],
+ * h_row_cols[k] floats per row: means, quats, sh0, shN) copies row s_i -> d_i; every moment tensor
+ * (h_moment_ptrs: exp_avg / exp_avg_sq of all parameters; pass 0 for sample_add) gets row s_i zeroed.
+ * counts [N] int32 is scratch.  h_* are HOST arrays (at most 16 entries each). */
+ST3R_API int st3r_mcmc_relocate(float* opacities_raw, float* scales_raw, int n_rows, float* const* h_row_ptrs,
+                       const int* h_row_cols, int n_moments, float* const* h_moment_ptrs, const int* h_moment_cols,
+                       const int64_t* sampled, const int32_t* alive_idx, const int32_t* dst, int dst_base, int n, int N,
+                       const float* binoms, int n_max, float min_opacity, int32_t* counts, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ ALIGN
  * Fused sparse-global-alignment optimiser: optimize_loop of starster/reconstruct.py:371-406 with
  * make_K_cam_depth (:209-261), loss_3d / loss_2d / loss_dust3r (:311-369), make_pts3d / reproj2d

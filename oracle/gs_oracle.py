@@ -317,3 +317,106 @@ def train_step(params, states, imgs, viewmats, Ks, width, height, step, lr=1e-3,
             denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
             p.addcdiv_(m, denom, value=-(lr / bc1))
     return float(loss), grads, render.detach(), info
+
+
+# ----------------------------------------------------------------------------- MCMC strategy
+# gsplat.MCMCStrategy (reference call sites starster/gs.py:43-45, :146-147, :163-164).  PARITY UNPINNED like the
+# rest of this file: restated from the published gsplat 1.4 strategy/mcmc.py + strategy/ops.py (SURVEY.md
+# Appendix A.8) and pinned only by closed-form known-answer tests (tests/test_gs_math_host.py).  The random draws
+# (torch.multinomial indices, torch.randn noise) are explicit arguments so the CUDA path can be compared on the
+# same draws.
+MCMC_N_MAX = 51
+
+
+def mcmc_binoms(n_max=MCMC_N_MAX):
+    """MCMCStrategy.initialize_state: binoms[n, k] = C(n, k)."""
+    b = torch.zeros((n_max, n_max), dtype=torch.float32)
+    for n in range(n_max):
+        for k in range(n + 1):
+            b[n, k] = math.comb(n, k)
+    return b
+
+
+def mcmc_compute_relocation(opacities, scales, ratios, binoms):
+    """gsplat compute_relocation (activated opacities [N], scales [N,3], ratios [N] int): Eq. 9 of the 3DGS-MCMC
+    paper, evaluated with the same loop order as the gsplat kernel, in fp32."""
+    n_max = binoms.shape[0]
+    N = opacities.shape[0]
+    ratios = ratios.clamp(1, n_max).to(torch.int64)
+    new_op = torch.empty(N, dtype=torch.float32)
+    new_sc = torch.empty(N, 3, dtype=torch.float32)
+    f32 = np.float32
+    for idx in range(N):
+        n = int(ratios[idx])
+        o = f32(opacities[idx].item())
+        no = f32(1.0) - f32(np.power(f32(1.0) - o, f32(1.0) / f32(n), dtype=np.float32))
+        denom = f32(0.0)
+        for i in range(1, n + 1):
+            p = no
+            for k in range(i):
+                term = f32((-1.0 if k & 1 else 1.0)) / f32(np.sqrt(f32(k + 1))) * p
+                denom = f32(denom + f32(binoms[i - 1, k].item()) * term)
+                p = f32(p * no)
+        new_op[idx] = float(no)
+        new_sc[idx] = (o / denom) * scales[idx]
+    return new_op, new_sc
+
+
+def _mcmc_new_values(params, sources, binoms, min_opacity):
+    opac = torch.sigmoid(params["opacities"])
+    eps = torch.finfo(torch.float32).eps
+    ratios = torch.bincount(sources, minlength=opac.shape[0])[sources] + 1
+    new_op, new_sc = mcmc_compute_relocation(opac[sources], torch.exp(params["scales"])[sources], ratios, binoms)
+    new_op = torch.clamp(new_op, max=1.0 - eps, min=min_opacity)
+    return torch.logit(new_op), torch.log(new_sc)
+
+
+def mcmc_relocate(params, moments, sampled, binoms, min_opacity=0.005):
+    """gsplat ops.relocate.  params: dict name -> tensor [N, ...] (raw opacities / scales), modified in place;
+    moments: dict name -> (exp_avg, exp_avg_sq); sampled: the torch.multinomial draw (indices into the ALIVE
+    list, length = number of dead Gaussians)."""
+    opac = torch.sigmoid(params["opacities"])
+    dead_mask = opac <= min_opacity
+    dead = dead_mask.nonzero(as_tuple=True)[0]
+    alive = (~dead_mask).nonzero(as_tuple=True)[0]
+    assert len(sampled) == len(dead)
+    src = alive[sampled]
+    raw_o, raw_s = _mcmc_new_values(params, src, binoms, min_opacity)
+    for name, p in params.items():
+        if name == "opacities":
+            p[src] = raw_o
+        elif name == "scales":
+            p[src] = raw_s
+        p[dead] = p[src]
+    for name, (m, v) in moments.items():
+        m[src] = 0
+        v[src] = 0
+    return dead, src
+
+
+def mcmc_sample_add(params, moments, sampled, binoms, min_opacity=0.005):
+    """gsplat ops.sample_add: returns the grown (params, moments) dicts."""
+    raw_o, raw_s = _mcmc_new_values(params, sampled, binoms, min_opacity)
+    out_p, out_m = {}, {}
+    for name, p in params.items():
+        p = p.clone()
+        if name == "opacities":
+            p[sampled] = raw_o
+        elif name == "scales":
+            p[sampled] = raw_s
+        out_p[name] = torch.cat([p, p[sampled]])
+    for name, (m, v) in moments.items():
+        z = torch.zeros((len(sampled), *m.shape[1:]), dtype=m.dtype)
+        out_m[name] = (torch.cat([m, z]), torch.cat([v, z]))
+    return out_p, out_m
+
+
+def mcmc_inject_noise(params, noise, scaler):
+    """gsplat ops.inject_noise_to_position with an explicit N(0,1) draw `noise` [N,3]; returns the new means."""
+    opac = torch.sigmoid(params["opacities"].flatten())
+    c6 = quat_scale_to_covar(params["quats"], torch.exp(params["scales"]))
+    covars = torch.stack([c6[:, 0], c6[:, 1], c6[:, 2], c6[:, 1], c6[:, 3], c6[:, 4], c6[:, 2], c6[:, 4], c6[:, 5]],
+                         dim=-1).reshape(-1, 3, 3)
+    gate = 1.0 / (1.0 + torch.exp(-100.0 * ((1.0 - opac) - 0.995)))
+    n = noise * gate.unsqueeze(-1) * scaler
+    return params["means"] + torch.einsum("bij,bj->bi", covars, n)

@@ -8,7 +8,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstarst3r_b200.so")
+# ST3R_B200_LIB overrides the path (development builds with instrumentation); there is still no fallback.
+LIB_PATH = os.environ.get("ST3R_B200_LIB") or os.path.join(_HERE, "libstarst3r_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "starst3r_b200.h")
 
 _lib = None

@@ -277,44 +277,189 @@ def adam_step(segments, lr, betas, eps, step):
     _lib.check(rc, "st3r_adam_step")
 
 
-class MCMCStrategyStub:
-    """Placeholder for gsplat.MCMCStrategy (gs.py:43-45).  With gsplat's defaults relocation / densification only
-    fires for 500 < step < 25000 with step % 100 == 0 and `step` restarts at 0 on every run_3dgs_optim call
-    (gs.py:143), so the documented usage (<= 500 iterations per call) only ever applies the per-step position
-    noise, which is applied faithfully.  Relocation itself is on the §8f list."""
-    cap_max, noise_lr, refine_start_iter, refine_stop_iter, refine_every, min_opacity = 1_000_000, 5e5, 500, 25_000, 100, 0.005
+class MCMCStrategy:
+    """gsplat.MCMCStrategy as Starst3r drives it (gs.py:43-45 construction with defaults, :146-147
+    step_pre_backward, :163-164 step_post_backward(..., lr=1e-3)); gsplat 1.4 strategy/mcmc.py + strategy/ops.py
+    semantics.  The numeric work runs in csrc/gs_mcmc.cu; the random draws come from
+    torch.multinomial / torch.randn_like exactly where gsplat takes them, so the RNG stream is the reference's.
+    Like gsplat it assumes logit opacities and log scales (the reference renders them raw: quirk C-1, preserved)."""
+
+    N_MAX = 51
+
+    def __init__(self, cap_max=1_000_000, noise_lr=5e5, refine_start_iter=500, refine_stop_iter=25_000,
+                 refine_every=100, min_opacity=0.005, verbose=False):
+        self.cap_max, self.noise_lr = cap_max, noise_lr
+        self.refine_start_iter, self.refine_stop_iter, self.refine_every = refine_start_iter, refine_stop_iter, refine_every
+        self.min_opacity, self.verbose = min_opacity, verbose
 
     def check_sanity(self, params, optimizers):
+        assert set(params.keys()) == set(optimizers.keys()), "params and optimizers must have the same keys"
         for k in ("means", "scales", "quats", "opacities"):
-            assert k in params and k in optimizers, f"{k} is required"
+            assert k in params, f"{k} is required in params but missing."
 
     def initialize_state(self):
-        return {"binoms": None}
+        binoms = torch.zeros((self.N_MAX, self.N_MAX))
+        for n in range(self.N_MAX):
+            for k in range(n + 1):
+                binoms[n, k] = math.comb(n, k)
+        return {"binoms": binoms}
 
     def step_pre_backward(self, params, optimizers, state, step, info):
         pass
 
     def step_post_backward(self, params, optimizers, state, step, info, lr):
+        dev = params["means"].device
+        if dev.type != "cuda":
+            raise RuntimeError("starst3r_b200.gs.MCMCStrategy needs the splats on a CUDA device (no CPU fallback)")
+        binoms = state["binoms"] = state["binoms"].to(dev).contiguous()
         if self.refine_start_iter < step < self.refine_stop_iter and step % self.refine_every == 0:
-            raise NotImplementedError("MCMC relocation / densification (gsplat.MCMCStrategy refine step) is not part of "
-                                      "the round-1 B200 hot path; run <= 500 iterations per call or enable_pruning=False")
-        with torch.no_grad():
-            opac = torch.sigmoid(params["opacities"].data)
-            sc = torch.exp(params["scales"].data)
-            R = _quat_to_rotmat(params["quats"].data)
-            M = R * sc[:, None, :]
-            cov = M @ M.transpose(1, 2)
-            w = 1.0 / (1.0 + torch.exp(-100.0 * ((1 - opac) - 0.995)))
-            noise = torch.randn_like(params["means"].data) * w[:, None] * lr * self.noise_lr
-            params["means"].data.add_(torch.einsum("nij,nj->ni", cov, noise))
+            n_relocated = self._relocate_gs(params, optimizers, binoms)
+            n_new = self._add_new_gs(params, optimizers, binoms)
+            if self.verbose:
+                print(f"Step {step}: Relocated {n_relocated} GSs. Added {n_new} GSs. Now having {len(params['means'])} GSs.")
+        inject_noise_to_position(params, lr * self.noise_lr)
+
+    # ---- gsplat strategy/ops.py: relocate / sample_add
+    def _relocate_gs(self, params, optimizers, binoms, sampled=None):
+        lib = _lib.load()
+        opac = params["opacities"].data
+        dev, N = opac.device, opac.shape[0]
+        dead = torch.empty(N, dtype=torch.int32, device=dev)
+        alive = torch.empty(N, dtype=torch.int32, device=dev)
+        probs = torch.empty(N, dtype=torch.float32, device=dev)
+        alive_probs = torch.empty(N, dtype=torch.float32, device=dev)
+        n_dead_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = _ws(lib.st3r_mcmc_partition_ws_bytes(N), dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.st3r_mcmc_partition(_lib.ptr(opac), N, _f(self.min_opacity), _lib.ptr(dead), _lib.ptr(alive),
+                                               _lib.ptr(probs), _lib.ptr(alive_probs), _lib.ptr(n_dead_dev), _lib.ptr(ws),
+                                               ws.numel(), _lib.stream_ptr()), "st3r_mcmc_partition")
+        n_dead = int(n_dead_dev.item())      # gsplat reads dead_mask.sum().item() at the same place
+        if n_dead == 0:
+            return 0
+        if n_dead == N:
+            raise RuntimeError("MCMCStrategy: every Gaussian is dead (sigmoid(opacity) <= min_opacity); nothing to sample")
+        if sampled is None:
+            sampled = _multinomial_sample(alive_probs[:N - n_dead], n_dead)
+        _relocate_rows(params, optimizers, sampled, alive, dead, 0, n_dead, N, binoms, self.min_opacity, True)
+        _rewrap(params, optimizers, {k: v.data for k, v in params.items()}, None)
+        return n_dead
+
+    def _add_new_gs(self, params, optimizers, binoms, sampled=None):
+        N = len(params["means"])
+        n_target = min(self.cap_max, int(1.05 * N))
+        n = max(0, n_target - N)
+        if n == 0:
+            return 0
+        if sampled is None:
+            sampled = _multinomial_sample(torch.sigmoid(params["opacities"].data.flatten()), n)
+        grown = {}
+        for k, p in params.items():
+            g = torch.empty((N + n, *p.shape[1:]), dtype=p.dtype, device=p.device)
+            g[:N].copy_(p.data)
+            grown[k] = g
+        tmp = {k: torch.nn.Parameter(v, requires_grad=False) for k, v in grown.items()}
+        _relocate_rows(tmp, None, sampled, None, None, N, n, N, binoms, self.min_opacity, False)
+        _rewrap(params, optimizers, grown, n)
+        return n
 
 
-def _quat_to_rotmat(q):
-    q = torch.nn.functional.normalize(q, dim=-1)
-    w, x, y, z = q.unbind(-1)
-    return torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
-                        2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
-                        2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], dim=-1).reshape(-1, 3, 3)
+# kept for callers of the round-1 name
+MCMCStrategyStub = MCMCStrategy
+
+
+def _multinomial_sample(weights, n, replacement=True):
+    """gsplat ops._multinomial_sample: torch.multinomial up to 2**24 categories, numpy beyond."""
+    if weights.shape[0] <= 2 ** 24:
+        return torch.multinomial(weights, n, replacement=replacement)
+    import numpy as np
+    w = (weights / weights.sum()).detach().cpu().numpy()
+    idx = np.random.choice(weights.shape[0], size=n, p=w, replace=replacement)
+    return torch.from_numpy(idx).to(weights.device)
+
+
+def _adam_state(opt, p):
+    return opt.state.get(p, None)
+
+
+def _relocate_rows(params, optimizers, sampled, alive, dst, dst_base, n, N, binoms, min_opacity, zero_moments):
+    """One st3r_mcmc_relocate call over every parameter tensor (and, for relocate, every Adam moment tensor)."""
+    lib = _lib.load()
+    dev = params["means"].device
+    sampled = sampled.to(device=dev, dtype=torch.int64).contiguous()
+    assert sampled.numel() == n
+    rows = [(k, p.data) for k, p in params.items() if k not in ("opacities", "scales")]
+    moments = []
+    if zero_moments and optimizers is not None:
+        for k, p in params.items():
+            st = _adam_state(optimizers[k], p)
+            if st:
+                moments += [st["exp_avg"], st["exp_avg_sq"]]
+    for _, t in rows:
+        assert t.is_contiguous() and t.dtype == torch.float32
+    counts = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+
+    def table(tensors):
+        k = len(tensors)
+        return (ctypes.c_void_p * max(k, 1))(*[t.data_ptr() for t in tensors]), \
+               (ctypes.c_int * max(k, 1))(*[t[0].numel() for t in tensors])
+
+    rp, rc = table([t for _, t in rows])
+    mp, mc = table(moments)
+    with torch.cuda.device(dev):
+        _lib.check(lib.st3r_mcmc_relocate(_lib.ptr(params["opacities"].data), _lib.ptr(params["scales"].data),
+                                          len(rows), rp, rc, len(moments), mp, mc, _lib.ptr(sampled), _lib.ptr(alive),
+                                          _lib.ptr(dst), dst_base, n, N, _lib.ptr(binoms), binoms.shape[0],
+                                          _f(min_opacity), _lib.ptr(counts), _lib.stream_ptr()), "st3r_mcmc_relocate")
+
+
+def _rewrap(params, optimizers, new_data, n_added):
+    """gsplat ops._update_param_with_optimizer: every entry of `params` becomes a fresh nn.Parameter and the
+    optimiser state moves to it (moments grown by `n_added` zero rows for sample_add)."""
+    for k in list(params.keys()):
+        old = params[k]
+        new = torch.nn.Parameter(new_data[k], requires_grad=old.requires_grad)
+        opt = optimizers[k]
+        st = opt.state.pop(old, None)
+        if st is not None:
+            if n_added:
+                for key in ("exp_avg", "exp_avg_sq"):
+                    z = torch.zeros((n_added, *st[key].shape[1:]), dtype=st[key].dtype, device=st[key].device)
+                    st[key] = torch.cat([st[key], z])
+            opt.state[new] = st
+        for g in opt.param_groups:
+            g["params"] = [new if q is old else q for q in g["params"]]
+        params[k] = new
+
+
+def inject_noise_to_position(params, scaler, noise=None):
+    """gsplat ops.inject_noise_to_position (fused in st3r_mcmc_inject_noise); `noise` defaults to
+    torch.randn_like(means), the draw gsplat makes."""
+    lib = _lib.load()
+    means = params["means"].data
+    if noise is None:
+        noise = torch.randn_like(means)
+    with torch.cuda.device(means.device):
+        _lib.check(lib.st3r_mcmc_inject_noise(_lib.ptr(means), _lib.ptr(params["quats"].data.contiguous()),
+                                              _lib.ptr(params["scales"].data.contiguous()),
+                                              _lib.ptr(params["opacities"].data.contiguous()), _lib.ptr(noise.contiguous()),
+                                              means.shape[0], _f(scaler), _lib.stream_ptr()), "st3r_mcmc_inject_noise")
+
+
+def compute_relocation(opacities, scales, ratios, binoms):
+    """gsplat.relocation.compute_relocation (activated opacities [N], scales [N,3], ratios [N] int)."""
+    lib = _lib.load()
+    _lib.require_cuda(opacities, scales, ratios, binoms)
+    N = opacities.shape[0]
+    new_o = torch.empty_like(opacities, dtype=torch.float32)
+    new_s = torch.empty_like(scales, dtype=torch.float32)
+    with torch.cuda.device(opacities.device):
+        _lib.check(lib.st3r_mcmc_compute_relocation(_lib.ptr(opacities.float().contiguous()), _lib.ptr(scales.float().contiguous()),
+                                                    _lib.ptr(ratios.to(torch.int32).contiguous()),
+                                                    _lib.ptr(binoms.float().contiguous()), binoms.shape[0], N,
+                                                    _lib.ptr(new_o), _lib.ptr(new_s), _lib.stream_ptr()),
+                   "st3r_mcmc_compute_relocation")
+    return new_o, new_s
 
 
 # ------------------------------------------------------------------------------------------- reference API
@@ -338,7 +483,7 @@ def init_3dgs(scene, init_scale=3e-3, lr=1e-3):
     scene.gaussians = {k: torch.nn.Parameter(v.to(scene.device).contiguous()) for k, v in g.items()}
     scene.optimizers = {k: FusedAdam([v], lr=lr) for k, v in scene.gaussians.items()}
     scene.ssim = None          # the SSIM term lives inside the fused loss kernel (st3r_gs_loss_fwd / _bwd)
-    scene.strategy = MCMCStrategyStub()
+    scene.strategy = MCMCStrategy()
     scene.strategy.check_sanity(scene.gaussians, scene.optimizers)
     scene.strategy_state = scene.strategy.initialize_state()
     scene._gs_truth = None
@@ -415,17 +560,25 @@ def run_3dgs_optim(scene, iters, enable_pruning=False, loss_ssim_fac=0.2, loss_o
     truth = _truth_images(scene, dev)
     cams = make_cams(scene.w2c.to(dev), scene.intrinsics.to(dev))
     names = ("means", "scales", "quats", "opacities", "shN")
-    params = {k: gz[k].data for k in names}
-    states = {}
-    for k in names:
-        opt = scene.optimizers[k]
-        st = opt._st(gz[k]) if isinstance(opt, FusedAdam) else opt.state.setdefault(gz[k], dict(
-            step=torch.zeros(()), exp_avg=torch.zeros_like(gz[k].data), exp_avg_sq=torch.zeros_like(gz[k].data)))
-        states[k] = (st["exp_avg"], st["exp_avg_sq"])
+
+    def bind():
+        """Raw views of the splat tensors and their Adam moments (re-bound after the strategy replaced them)."""
+        params = {k: gz[k].data for k in names}
+        states = {}
+        for k in names:
+            opt = scene.optimizers[k]
+            st = opt._st(gz[k]) if isinstance(opt, FusedAdam) else opt.state.setdefault(gz[k], dict(
+                step=torch.zeros(()), exp_avg=torch.zeros_like(gz[k].data), exp_avg_sq=torch.zeros_like(gz[k].data)))
+            states[k] = (st["exp_avg"], st["exp_avg_sq"])
+        return params, states
+
+    params, states = bind()
     group = scene.optimizers["means"].param_groups[0]
     losses_dev = []
     pbar = trange(iters, disable=not verbose)
     for step in pbar:
+        if enable_pruning:
+            scene.strategy.step_pre_backward(scene.gaussians, scene.optimizers, scene.strategy_state, step, None)
         opt_step = int(scene.optimizers["means"]._st(gz["means"])["step"].item()) + 1
         loss, fr = train_step(params, states, truth, cams, width, height, opt_step, lr=group["lr"],
                               betas=group["betas"], eps=group["eps"], loss_ssim_fac=loss_ssim_fac,
@@ -437,6 +590,8 @@ def run_3dgs_optim(scene, iters, enable_pruning=False, loss_ssim_fac=0.2, loss_o
             pbar.set_description(f"Gsplat optimization: loss={loss.item()}")
         if enable_pruning:
             scene.strategy.step_post_backward(scene.gaussians, scene.optimizers, scene.strategy_state, step, None, 1e-3)
+            if gz["means"].data.data_ptr() != params["means"].data_ptr() or gz["means"].shape[0] != params["means"].shape[0]:
+                params, states = bind()
     if not losses_dev:
         return []
     return torch.stack(losses_dev).cpu().tolist()
