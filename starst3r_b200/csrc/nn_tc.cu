@@ -29,15 +29,26 @@ constexpr int ROWB = 128;          // smem bytes per operand row (32 floats, 24 
 constexpr int STAGES = 4;          // smem ring depth for DB tiles
 constexpr int ACC_STAGES = 2;      // TMEM accumulator stages
 constexpr int CAND_CAP = 12;       // candidates kept per row
-constexpr int NUM_THREADS = 192;   // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-5: epilogue
+#ifndef NN_TC_EPI_SPLIT
+#define NN_TC_EPI_SPLIT 1
+#endif
+// Epilogue warps per TMEM lane quarter: each scans BN / EPI_SPLIT accumulator columns of its 32 rows.  (Measured:
+// 2 per quarter is no faster than 1; neither is one CTA per SM with 4 accumulator stages, nor the query tile in
+// tensor memory: the TMA + MMA pipeline alone, epilogue compiled out, already takes 2/3 of the kernel time.)
+constexpr int EPI_SPLIT = NN_TC_EPI_SPLIT;
+constexpr int EPI_COLS = BN / EPI_SPLIT;        // columns per epilogue thread and tile
+constexpr int EPI_CHUNKS = EPI_COLS / 32;
+constexpr int EPI_THREADS = 128 * EPI_SPLIT;
+constexpr int NUM_THREADS = 64 + EPI_THREADS;   // warp0: TMA, warp1: MMA + TMEM alloc, then the epilogue warps
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 256
 constexpr int MAX_TILES_PER_CHUNK = 512;
+constexpr int MAX_PROBE = 8;         // max-only probe tiles per CTA (see the kernel)
 constexpr float DELTA_COEF = 4.2e-3f;  // > 2 * 2^-9 (+ fp32 accumulation slack)
 
 constexpr int SMEM_A = 0;
 constexpr int SMEM_B = SMEM_A + BM * ROWB;
 constexpr int SMEM_CAND = SMEM_B + STAGES * BN * ROWB;
-constexpr int SMEM_BAR = SMEM_CAND + BM * CAND_CAP * 8;
+constexpr int SMEM_BAR = SMEM_CAND + EPI_SPLIT * BM * CAND_CAP * 8;
 constexpr int SMEM_TOTAL = SMEM_BAR + 256;
 constexpr int SMEM_DYN = SMEM_TOTAL + 1024;  // slack for 1024-byte alignment
 
@@ -112,6 +123,15 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 #else
   return fmaxf(fmaxf(a, b), c);
 #endif
+}
+
+// Maximum of 32 consecutive accumulator columns: 15 three-input max instructions + 1.
+__device__ __forceinline__ float chunk_max(const float* x) {
+  float m01 = fmax3(x[0], x[1], x[2]), m02 = fmax3(x[3], x[4], x[5]), m03 = fmax3(x[6], x[7], x[8]);
+  float m04 = fmax3(x[9], x[10], x[11]), m05 = fmax3(x[12], x[13], x[14]), m06 = fmax3(x[15], x[16], x[17]);
+  float m07 = fmax3(x[18], x[19], x[20]), m08 = fmax3(x[21], x[22], x[23]), m09 = fmax3(x[24], x[25], x[26]);
+  float m10 = fmax3(x[27], x[28], x[29]), m11 = fmaxf(x[30], x[31]);
+  return fmax3(fmax3(m01, m02, m03), fmax3(m04, m05, m06), fmax3(fmax3(m07, m08, m09), m10, m11));
 }
 
 // K-major, 128-byte swizzle, dense 8-row groups (SBO = 1024 B), sm_100 descriptor version 1.
@@ -215,6 +235,17 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
   if (n_begin >= N) return;
   const int n_end = min(N, n_begin + tiles_per_chunk * BN);
   const int ntiles = (n_end - n_begin + BN - 1) / BN;
+  // Probe tiles.  A streaming arg-max restarts its candidate bookkeeping at every new running maximum: ~ln(columns)
+  // times per row, i.e. for a 32-row warp in a quarter of all 32-column chunks.  Each CTA therefore first runs a
+  // few FULL tiles spread evenly over the WHOLE DB in max-only mode: their maximum is a valid lower bound of the
+  // row's final approximate maximum, which makes later "near the running maximum" hits rare (a few per row) and
+  // identical in all CTAs that share the query rows.  Probe columns are seen again by the CTA that owns them.
+  const int ntiles_all = (N + BN - 1) / BN;
+  const int n_probe = ntiles_all >= 2 ? min(MAX_PROBE, ntiles / 8) : 0;
+  const int nseq = n_probe + ntiles;
+  auto seq_col = [&](int t) {
+    return t < n_probe ? (int)(((long long)t * (ntiles_all - 1)) / n_probe) * BN : n_begin + (t - n_probe) * BN;
+  };
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -232,7 +263,7 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_THREADS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -261,18 +292,18 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int t = 0; t < ntiles; ++t) {
+      for (int t = 0; t < nseq; ++t) {
         int s = t % STAGES;
         uint32_t ph = (uint32_t)(t / STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
         mbar_arrive_expect_tx(full_bar(s), BN * ROWB);
-        tma_load_2d(sB + s * BN * ROWB, tmap_db, 0, n_begin + t * BN, full_bar(s));
+        tma_load_2d(sB + s * BN * ROWB, tmap_db, 0, seq_col(t), full_bar(s));
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      for (int t = 0; t < ntiles; ++t) {
+      for (int t = 0; t < nseq; ++t) {
         int s = t % STAGES;
         uint32_t ph = (uint32_t)(t / STAGES) & 1u;
         int a = t & 1;
@@ -297,7 +328,8 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
     const int row = quarter * 32 + lane;     // accumulator row == TMEM lane
     const int gm = m0 + row;
     const bool row_ok = gm < M;
-    Cand* list = cand_all + row * CAND_CAP;
+    const int part = (warp - 2) >> 2;        // which EPI_COLS-wide slice of every tile this warp scans
+    Cand* list = cand_all + (part * BM + row) * CAND_CAP;
     int cnt = 0;  // bit 8 set => the list overflowed (row redone exactly afterwards)
     const float* qrow = Qsrc;
     float delta = 0.f;
@@ -310,61 +342,89 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
     }
     float run_max = row_ok ? -INFINITY : INFINITY;  // padded rows never trigger
 
+#ifdef NN_TC_DEBUG_CYCLES
     const bool dbg = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0);
     unsigned long long c_wait = 0, c_epi = 0;
     const long long c_start = clock64();
-    for (int t = 0; t < ntiles; ++t) {
+#endif
+    for (int t = 0; t < nseq; ++t) {
       int a = t & 1;
       uint32_t aph = (uint32_t)(t >> 1) & 1u;
+#ifdef NN_TC_DEBUG_CYCLES
       const long long c0 = clock64();
+#endif
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
+#ifdef NN_TC_DEBUG_CYCLES
       const long long c1 = clock64();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * BN);
-      const int col_base = n_begin + t * BN;
-      const bool ragged = col_base + BN > n_end;
-      // Pull the whole 128-column accumulator row into registers with four back-to-back tcgen05.ld (their
-      // latencies overlap; waiting per 32-column chunk serialised ~200 cycles four times per tile), then hand
-      // the TMEM stage back to the MMA warp BEFORE the arg-max arithmetic so tile t+2 can start immediately.
-      float v[BN];
+#endif
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * BN + part * EPI_COLS);
+      // Pull this thread's accumulator columns into registers with back-to-back tcgen05.ld (their latencies
+      // overlap), then hand the TMEM stage back to the MMA warp BEFORE the arg-max arithmetic so tile t+2 can
+      // start immediately.
+      float v[EPI_COLS];
+#ifdef NN_TC_EXP_NOLD   // timing experiment only (wrong results): no TMEM read
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) tc_ld32(taddr + c * 32, v + c * 32);
+      for (int c = 0; c < EPI_COLS; ++c) v[c] = __int_as_float(taddr + c + t);
+#else
+#pragma unroll
+      for (int c = 0; c < EPI_CHUNKS; ++c) tc_ld32(taddr + c * 32, v + c * 32);
       tc_wait_ld();
+#endif
       tc_fence_before();
       mbar_arrive(tempty_bar(a));
+#ifdef NN_TC_EXP_NOALU  // timing experiment only (wrong results): no arg-max arithmetic
+      if (v[t & (EPI_COLS - 1)] == 123.456f) run_max = v[5];
+      continue;
+#endif
+      // Hot path: three-input max instructions and ONE test per tile, straight-line.
+      float cm[EPI_CHUNKS];
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        float* x = v + c * 32;
-        if (ragged) {
+      for (int c = 0; c < EPI_CHUNKS; ++c) cm[c] = chunk_max(v + c * 32);
+      float tmax = cm[0];
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col_base + c * 32 + i >= n_end) x[i] = -INFINITY;
-        }
-        float m01 = fmax3(x[0], x[1], x[2]), m02 = fmax3(x[3], x[4], x[5]), m03 = fmax3(x[6], x[7], x[8]);
-        float m04 = fmax3(x[9], x[10], x[11]), m05 = fmax3(x[12], x[13], x[14]), m06 = fmax3(x[15], x[16], x[17]);
-        float m07 = fmax3(x[18], x[19], x[20]), m08 = fmax3(x[21], x[22], x[23]), m09 = fmax3(x[24], x[25], x[26]);
-        float m10 = fmax3(x[27], x[28], x[29]), m11 = fmaxf(x[30], x[31]);
-        float cmax = fmax3(fmax3(m01, m02, m03), fmax3(m04, m05, m06), fmax3(fmax3(m07, m08, m09), m10, m11));
-        if (cmax >= run_max - delta) {
-          // Rare path (a few times per row): kept out of line and loop-based so that the hot
-          // epilogue stays small enough for the instruction cache.
-          run_max = fmaxf(run_max, cmax);
-          const float thr = run_max - delta;
-          uint32_t mask = 0;
+      for (int c = 1; c < EPI_CHUNKS; ++c) tmax = fmaxf(tmax, cm[c]);
+      if (t < n_probe) {
+        run_max = fmaxf(run_max, tmax);          // probe tiles are always full tiles
+      } else {
+        const int col_base = n_begin + (t - n_probe) * BN + part * EPI_COLS;
+        const bool ragged = col_base + EPI_COLS > n_end;
+        if (__builtin_expect(ragged || tmax >= run_max - delta, 0)) {
+          // Cold path (a few times per row, or the single ragged tile of the DB).
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mask |= (x[i] >= thr ? 1u : 0u) << i;
-          cnt = push_candidates(list, cnt, mask, col_base + c * 32, cmax, thr);
+          for (int c = 0; c < EPI_CHUNKS; ++c) {
+            float* x = v + c * 32;
+            float cmax = cm[c];
+            if (ragged) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col_base + c * 32 + i >= n_end) x[i] = -INFINITY;
+              cmax = chunk_max(x);
+            }
+            if (cmax >= run_max - delta) {
+              run_max = fmaxf(run_max, cmax);
+              const float thr = run_max - delta;
+              uint32_t mask = 0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mask |= (x[i] >= thr ? 1u : 0u) << i;
+              cnt = push_candidates(list, cnt, mask, col_base + c * 32, cmax, thr);
+            }
+          }
         }
       }
+#ifdef NN_TC_DEBUG_CYCLES
       c_wait += (unsigned long long)(c1 - c0);
       c_epi += (unsigned long long)(clock64() - c1);
+#endif
     }
+#ifdef NN_TC_DEBUG_CYCLES
     if (dbg) {
-      atomicAdd(&g_nn_tc_cycles[0], (unsigned long long)ntiles);
+      atomicAdd(&g_nn_tc_cycles[0], (unsigned long long)nseq);
       atomicAdd(&g_nn_tc_cycles[1], c_wait);
       atomicAdd(&g_nn_tc_cycles[2], c_epi);
       atomicAdd(&g_nn_tc_cycles[3], (unsigned long long)(clock64() - c_start));
     }
+#endif
 
     if (row_ok) {
       if (cnt & CAND_OVERFLOW) {
