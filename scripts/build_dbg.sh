@@ -2,7 +2,7 @@
 # Instrumented variants of the library (development aid for the tcgen05 matcher):
 #   libstarst3r_b200_dbg.so        cycle counters in the epilogue (st3r_debug_nn_tc_cycles)
 #   libstarst3r_b200_nold.so       + no TMEM read, no arg-max arithmetic (timing only: the TMA + MMA pipeline alone)
-#   libstarst3r_b200_g{G}s{S}.so   G epilogue groups x S column splits (A/B against the default)
+#   libstarst3r_b200_split2.so     two epilogue warps per TMEM lane quarter (A/B against the default of one)
 # Select one with ST3R_B200_LIB=<path>.
 set -e
 cd "$(dirname "$0")/.."
@@ -10,13 +10,11 @@ python -m starst3r_b200.build > /dev/null
 B=starst3r_b200/build
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr"
 OBJS=$(ls $B/*.o | grep -v nn_tc.o | grep -v _var_)
-for v in dbg nold g2s2 g1s1 g1s2; do
+for v in dbg nold split2; do
   D=""
   [ $v = dbg ] && D="-DNN_TC_DEBUG_CYCLES"
   [ $v = nold ] && D="-DNN_TC_DEBUG_CYCLES -DNN_TC_EXP_NOLD -DNN_TC_EXP_NOALU"
-  [ $v = g2s2 ] && D="-DNN_TC_EPI_SPLIT=2"
-  [ $v = g1s1 ] && D="-DNN_TC_EPI_GROUPS=1"
-  [ $v = g1s2 ] && D="-DNN_TC_EPI_GROUPS=1 -DNN_TC_EPI_SPLIT=2"
+  [ $v = split2 ] && D="-DNN_TC_EPI_SPLIT=2"
   nvcc $FLAGS $D -c starst3r_b200/csrc/nn_tc.cu -o $B/nn_tc_var_$v.o
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o starst3r_b200/libstarst3r_b200_$v.so $OBJS $B/nn_tc_var_$v.o -cudart static -lpthread -ldl -lrt
 done
