@@ -118,11 +118,12 @@ def run_ours(args):
             dist.broadcast(v, 0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
-    def step_fn(i, prof=False):
-        if world == 1:
-            return gs.train_step(params, states, truth, cams, W, H, i + 1, count_blends=prof)
-        return gs.train_step(params, states, truth, cams, W, H, i + 1, count_blends=prof,
-                             grad_hook=lambda fr: allreduce_grads(fr, world))
+    plan = gs.TrainPlan(N_GAUSS, N_VIEWS, W, H, dev)     # persistent buffers: no allocation / host sync per step
+    hook = (lambda fr: allreduce_grads(fr, world)) if world > 1 else None
+
+    def step_fn(i, prof=False, images=None):
+        return gs.train_step(params, states, truth if images is None else images, cams, W, H, i + 1,
+                             count_blends=prof, grad_hook=hook, plan=plan)
 
     def barrier():
         if world > 1:
@@ -139,20 +140,25 @@ def run_ours(args):
     # ---- device-resident timing: K steps, L2 flushed between steps (flush not timed) -----------------
     launches0 = lib.st3r_launch_count()
     evs = []
-    gs.PROF = {}
     barrier()
     for i in range(args.steps):
         flush.fill_(i & 0xff)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        loss, fr = step_fn(args.warmup + i, prof=True)
+        loss, fr = step_fn(args.warmup + i)
         e1.record()
         evs.append((e0, e1))
     barrier()
     launches = lib.st3r_launch_count() - launches0
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    # per-entry-point CUDA events (and the blend counter) in a separate, untimed pass: they cost host time
+    gs.PROF = {}
+    for i in range(3):
+        flush.fill_(i)
+        loss, fr = step_fn(args.warmup + args.steps + i, prof=True)
     prof = gs.prof_summary()
     gs.PROF = None
-    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    n_done = args.warmup + args.steps + 3
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -182,21 +188,43 @@ def run_ours(args):
                 "step_breakdown_ms": {k: round(v, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])}}
 
     # ---- end-to-end: truth images come from pinned host memory every step, the loss is read back -----
+    # The upload of step i+1's images runs on a copy stream under step i's kernels (two device buffers); every
+    # step's images are copied inside the timed region and every step's loss is read back (one step late, so the
+    # read does not drain the queue).
     truth_host = truth.cpu().pin_memory()
-    truth_dev = torch.empty_like(truth)
+    truth_dev = [torch.empty_like(truth), torch.empty_like(truth)]
+    loss_host = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream()
+    ready = [torch.cuda.Event(), torch.cuda.Event()]     # upload of buffer b finished
+    freed = [torch.cuda.Event(), torch.cuda.Event()]     # step that read buffer b finished
+
+    def upload(b):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[b])
+            truth_dev[b].copy_(truth_host, non_blocking=True)
+            ready[b].record(copy_stream)
+
     barrier()
+    for b in (0, 1):
+        freed[b].record(main_stream)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    copy_stream.wait_event(e0)
+    upload(0)
+    losses = []
     for i in range(args.steps):
-        truth_dev.copy_(truth_host, non_blocking=True)
-        if world == 1:
-            loss, _ = gs.train_step(params, states, truth_dev, cams, W, H, args.warmup + args.steps + i + 1)
-        else:
-            loss, _ = gs.train_step(params, states, truth_dev, cams, W, H, args.warmup + args.steps + i + 1,
-                                    grad_hook=lambda fr: allreduce_grads(fr, world))
-        loss.item()
+        b = i & 1
+        if i + 1 < args.steps:
+            upload(1 - b)
+        main_stream.wait_event(ready[b])
+        loss, _ = step_fn(n_done + i, images=truth_dev[b])
+        freed[b].record(main_stream)
+        loss_host[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+        losses.append(loss)
     e1.record()
     barrier()
+    assert all(math.isfinite(x) for x in loss_host.tolist())
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

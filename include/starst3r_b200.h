@@ -172,6 +172,12 @@ ST3R_API int st3r_gs_loss_fwd(const float* render, const float* truth, int C, in
 ST3R_API int st3r_gs_loss_bwd(const float* render, const float* truth, const float* dmaps, int C, int height, int width,
                      float ssim_fac, float* v_render, cudaStream_t stream);
 
+/* Scalar loss of one training iteration from the accumulators of st3r_gs_loss_fwd / st3r_gs_project_bwd:
+ * sum over views of (1-f) * L1 + f * (1 - SSIM) (gs.py:126-131,149-152) + reg_opac * reg_sums[0] + reg_scale *
+ * reg_sums[1] (gs.py:132-136; reg_sums may be NULL).  loss_out is one device float. */
+ST3R_API int st3r_gs_loss_finalize(const float* sums, const float* reg_sums, int C, int height, int width, float ssim_fac,
+                          float reg_opac, float reg_scale, float* loss_out, cudaStream_t stream);
+
 /* torch.optim.Adam step over up to 8 tensors in one launch.  Arrays are HOST arrays of device pointers /
  * sizes; tensor i is rows[i] x cols[i] with leading dimensions ld_param[i] (param and both moments) and
  * ld_grad[i].  step is 1-based; the hyper-parameters are doubles (torch keeps them as Python floats and rounds

@@ -8,8 +8,9 @@ dev = torch.device("cuda:0")
 what = sys.argv[1] if len(sys.argv) > 1 else "both"
 if what in ("both", "step"):
     params, states, truth, cams = bench.make_workload(dev, 0)
+    plan = gs.TrainPlan(bench.N_GAUSS, bench.N_VIEWS, bench.W, bench.H, dev)
     for i in range(3):
-        loss, fr = gs.train_step(params, states, truth, cams, bench.W, bench.H, i + 1)
+        loss, fr = gs.train_step(params, states, truth, cams, bench.W, bench.H, i + 1, plan=plan)
     torch.cuda.synchronize()
 if what in ("both", "match"):
     A, B = synth.descriptor_pair(512, 512, seed=0, device=dev)

@@ -163,6 +163,20 @@ ssim_l1_bwd_kernel(const float* __restrict__ render, const float* __restrict__ t
   }
 }
 
+// loss = sum_views [(1-f) * L1_v + f * (1 - SSIM_v)] + reg_o * sum sigmoid(opacity) + reg_s * sum exp(scale)
+// (gs.py:126-136 summed over the views, gs.py:149-152), evaluated in the order the PyTorch expression uses.
+__global__ void loss_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ reg, int C, float inv_l1,
+                                     float inv_ssim, float f, float reg_o, float reg_s, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float acc = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float l1 = sums[2 * c + 1] * inv_l1, ssim = sums[2 * c] * inv_ssim;
+    acc += l1 * (1.0f - f) + (1.0f - ssim) * f;
+  }
+  if (reg) acc = acc + reg[0] * reg_o + reg[1] * reg_s;
+  *out = acc;
+}
+
 bool g_win_set = false;
 
 int set_window() {
@@ -209,6 +223,17 @@ int st3r_gs_loss_bwd(const float* render, const float* truth, const float* dmaps
   float coef_l1 = (1.0f - ssim_fac) / (3.0f * (float)height * (float)width);
   dim3 grid((width + LT - 1) / LT, (height + LT - 1) / LT, C);
   ssim_l1_bwd_kernel<<<grid, LT * LT, 0, stream>>>(render, truth, dmaps, height, width, coef_l1, v_render);
+  ST3R_CHECK_LAUNCH();
+  return ST3R_OK;
+}
+
+int st3r_gs_loss_finalize(const float* sums, const float* reg_sums, int C, int height, int width, float ssim_fac,
+                          float reg_opac, float reg_scale, float* loss_out, cudaStream_t stream) {
+  ST3R_CHECK_ARG(C >= 0 && height > 10 && width > 10, "st3r_gs_loss_finalize: bad sizes");
+  ST3R_CHECK_ARG(sums && loss_out, "st3r_gs_loss_finalize: null pointer");
+  loss_finalize_kernel<<<1, 32, 0, stream>>>(sums, reg_sums, C, 1.0f / (3.0f * (float)height * (float)width),
+                                             1.0f / (3.0f * (float)(height - 10) * (float)(width - 10)), ssim_fac,
+                                             reg_opac, reg_scale, loss_out);
   ST3R_CHECK_LAUNCH();
   return ST3R_OK;
 }

@@ -71,10 +71,103 @@ def make_cams(viewmats, Ks):
 
 class _Frame:
     """Device state of one forward pass (kept for the backward)."""
-    pass
+    _n_isect = None
+
+    @property
+    def n_isect(self):
+        """Number of (Gaussian, tile) intersections of this frame (host int; read from the device on first use)."""
+        if self._n_isect is None:
+            self._n_isect = int(self.n_isect_dev.item())
+        return self._n_isect
 
 
-def _forward(means, quats, scales, opacities, shN, cams, width, height, count_blends=False):
+class TrainPlan:
+    """Persistent device buffers for repeated frames of one shape: no allocation and NO host synchronisation per
+    frame.  gsplat (and the un-planned path below) reads the intersection count back every frame to size the sort
+    buffers exactly; here they have a capacity (HEADROOM x the last known count), the kernels clamp to it on the
+    device, and the count is copied to pinned memory asynchronously and checked one frame later: an overflow raises
+    (loudly, never truncates silently) and a count above 80 % of the capacity grows the buffers."""
+    HEADROOM = 1.5
+
+    def __init__(self, N, C, width, height, device):
+        lib = _lib.load()
+        self.N, self.C, self.W, self.H, self.dev = N, C, int(width), int(height), device
+        self.tile_w, self.tile_h = (self.W + TILE - 1) // TILE, (self.H + TILE - 1) // TILE
+        E = max(C * N, 1)
+        i32, f32 = torch.int32, torch.float32
+        self.radii = torch.empty(E, dtype=i32, device=device)
+        self.geomA = torch.empty((E, 4), dtype=f32, device=device)
+        self.geomB = torch.empty((E, 4), dtype=f32, device=device)
+        self.rgb = torch.empty((E, 4), dtype=f32, device=device)
+        self.tiles = torch.empty(E, dtype=i32, device=device)
+        self.cum = torch.empty(E, dtype=i32, device=device)
+        self.n_raw = torch.zeros(1, dtype=i32, device=device)        # true count of the current frame
+        self.n_clamped = torch.zeros(1, dtype=i32, device=device)    # min(count, capacity): what the kernels use
+        self.scan_ws = _ws(lib.st3r_scan_ws_bytes(C * N), device)
+        self.offsets = torch.empty(max(C * self.tile_w * self.tile_h, 1), dtype=i32, device=device)
+        self.render = torch.empty((C, self.H, self.W, 3), dtype=f32, device=device)
+        self.alphas = torch.empty((C, self.H, self.W), dtype=f32, device=device)
+        self.last_ids = torch.empty((C, self.H, self.W), dtype=i32, device=device)
+        self.n_blend = torch.zeros(1, dtype=torch.int64, device=device)
+        # backward / loss
+        self.v_geom = torch.empty((3, E, 4), dtype=f32, device=device)
+        self.grads = dict(means=torch.empty((N, 3), dtype=f32, device=device), quats=torch.empty((N, 4), dtype=f32, device=device),
+                          scales=torch.empty((N, 3), dtype=f32, device=device), opacities=torch.empty((N,), dtype=f32, device=device),
+                          sh=torch.empty((N, 4, 3), dtype=f32, device=device))
+        self.dmaps = torch.empty((C, self.H, self.W, 3, 3), dtype=f32, device=device)
+        self.acc = torch.zeros((2 * C + 2,), dtype=f32, device=device)    # [C,2] SSIM / L1 sums | 2 regulariser sums
+        self.v_render = torch.empty((C, self.H, self.W, 3), dtype=f32, device=device)
+        self.cap = 0
+        self.keys = self.vals = self.keys_alt = self.vals_alt = self.sort_ws = None
+        self._host = torch.zeros(64, dtype=i32).pin_memory()           # ring of asynchronously copied counts
+        self._pending = []                                              # (event, slot, capacity at launch)
+        self._slot = 0
+        self.last_n_isect = None
+
+    def matches(self, N, C, width, height, device):
+        return (self.N, self.C, self.W, self.H) == (N, C, int(width), int(height)) and self.dev == device
+
+    def _alloc_isect(self, cap):
+        lib = _lib.load()
+        self.cap = int(cap)
+        self.keys = torch.empty(self.cap, dtype=torch.int64, device=self.dev)
+        self.vals = torch.empty(self.cap, dtype=torch.int32, device=self.dev)
+        self.keys_alt = torch.empty(self.cap, dtype=torch.int64, device=self.dev)
+        self.vals_alt = torch.empty(self.cap, dtype=torch.int32, device=self.dev)
+        self.sort_ws = _ws(lib.st3r_radix_sort_ws_bytes(self.cap), self.dev)
+
+    def poll(self, wait_all=False):
+        """Checks the counts of earlier frames (waits for all but the newest, so the host stays at most one frame
+        ahead of the device).  Raises on overflow; grows the capacity for the NEXT frame when it runs tight."""
+        keep = 0 if wait_all else 1
+        while len(self._pending) > keep:
+            ev, slot, cap = self._pending.pop(0)
+            ev.synchronize()
+            n = int(self._host[slot])
+            self.last_n_isect = n
+            if n > 0.8 * self.cap:
+                torch.cuda.current_stream().synchronize()
+                self._alloc_isect(max(int(self.HEADROOM * n), 1024))
+            if n > cap:
+                raise RuntimeError(f"starst3r_b200.gs.TrainPlan: {n} tile intersections exceed the buffer capacity {cap}; "
+                                   "that frame was rendered truncated - re-run it (the capacity has been raised)")
+
+    def after_scan(self):
+        """Called right after the scan of a frame: capacity bookkeeping without stalling the device."""
+        if self.cap == 0:                       # first frame of this plan: size from the true count (one sync)
+            n = int(self.n_raw.item())
+            self.last_n_isect = n
+            self._alloc_isect(max(int(self.HEADROOM * n), 1024))
+        else:
+            slot = self._slot = (self._slot + 1) % self._host.numel()
+            self._host[slot:slot + 1].copy_(self.n_raw, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pending.append((ev, slot, self.cap))
+        torch.clamp(self.n_raw, max=self.cap, out=self.n_clamped)
+
+
+def _forward(means, quats, scales, opacities, shN, cams, width, height, count_blends=False, plan=None):
     lib = _lib.load()
     _lib.require_cuda(means, quats, scales, opacities, shN, cams)
     dev = means.device
@@ -85,13 +178,19 @@ def _forward(means, quats, scales, opacities, shN, cams, width, height, count_bl
     fr.N, fr.C, fr.W, fr.H, fr.sh_coeffs, fr.cams = N, C, int(width), int(height), sh_coeffs, cams
     fr.tile_w, fr.tile_h = (fr.W + TILE - 1) // TILE, (fr.H + TILE - 1) // TILE
     E = max(C * N, 1)
-    fr.radii = torch.empty(E, dtype=torch.int32, device=dev)
-    fr.geomA = torch.empty((E, 4), dtype=torch.float32, device=dev)
-    fr.geomB = torch.empty((E, 4), dtype=torch.float32, device=dev)
-    fr.rgb = torch.empty((E, 4), dtype=torch.float32, device=dev)
-    fr.tiles = torch.empty(E, dtype=torch.int32, device=dev)
-    fr.cum = torch.empty(E, dtype=torch.int32, device=dev)
-    fr.n_isect_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    if plan is not None:
+        assert plan.matches(N, C, width, height, dev), "TrainPlan was built for another problem shape"
+        plan.poll()
+        fr.radii, fr.geomA, fr.geomB, fr.rgb, fr.tiles, fr.cum = plan.radii, plan.geomA, plan.geomB, plan.rgb, plan.tiles, plan.cum
+        fr.n_isect_dev = plan.n_raw
+    else:
+        fr.radii = torch.empty(E, dtype=torch.int32, device=dev)
+        fr.geomA = torch.empty((E, 4), dtype=torch.float32, device=dev)
+        fr.geomB = torch.empty((E, 4), dtype=torch.float32, device=dev)
+        fr.rgb = torch.empty((E, 4), dtype=torch.float32, device=dev)
+        fr.tiles = torch.empty(E, dtype=torch.int32, device=dev)
+        fr.cum = torch.empty(E, dtype=torch.int32, device=dev)
+        fr.n_isect_dev = torch.zeros(1, dtype=torch.int32, device=dev)
     st = _lib.stream_ptr()
     with torch.cuda.device(dev):
         with _Prof("st3r_gs_project"):
@@ -99,37 +198,49 @@ def _forward(means, quats, scales, opacities, shN, cams, width, height, count_bl
                                            _lib.ptr(shN), sh_coeffs, _lib.ptr(cams), N, C, fr.W, fr.H, TILE, _f(EPS2D),
                                            _f(NEAR), _f(FAR), _f(RADIUS_CLIP), _lib.ptr(fr.radii), _lib.ptr(fr.geomA),
                                            _lib.ptr(fr.geomB), _lib.ptr(fr.rgb), _lib.ptr(fr.tiles), st), "st3r_gs_project")
-        ws = _ws(lib.st3r_scan_ws_bytes(C * N), dev)
+        ws = plan.scan_ws if plan is not None else _ws(lib.st3r_scan_ws_bytes(C * N), dev)
         with _Prof("st3r_exclusive_scan_i32"):
             _lib.check(lib.st3r_exclusive_scan_i32(_lib.ptr(fr.tiles), _lib.ptr(fr.cum), C * N, _lib.ptr(fr.n_isect_dev),
                                                    _lib.ptr(ws), ws.numel(), st), "st3r_exclusive_scan_i32")
-        # One host read per frame sizes the intersection buffers exactly (gsplat does the same).
-        n_isect = int(fr.n_isect_dev.item())
-        fr.n_isect = n_isect
-        cap = max(n_isect, 1)
-        fr.keys = torch.empty(cap, dtype=torch.int64, device=dev)
-        fr.vals = torch.empty(cap, dtype=torch.int32, device=dev)
-        keys_alt = torch.empty(cap, dtype=torch.int64, device=dev)
-        vals_alt = torch.empty(cap, dtype=torch.int32, device=dev)
+        if plan is not None:
+            # capacity-sized intersection buffers, count clamped on the device, checked one frame later
+            plan.after_scan()
+            cap, n_dev = plan.cap, plan.n_clamped
+            fr.keys, fr.vals, keys_alt, vals_alt, ws = plan.keys, plan.vals, plan.keys_alt, plan.vals_alt, plan.sort_ws
+            fr.n_isect_dev = n_dev
+        else:
+            # One host read per frame sizes the intersection buffers exactly (gsplat does the same).
+            n_isect = int(fr.n_isect_dev.item())
+            fr._n_isect = n_isect
+            cap, n_dev = max(n_isect, 1), fr.n_isect_dev
+            fr.keys = torch.empty(cap, dtype=torch.int64, device=dev)
+            fr.vals = torch.empty(cap, dtype=torch.int32, device=dev)
+            keys_alt = torch.empty(cap, dtype=torch.int64, device=dev)
+            vals_alt = torch.empty(cap, dtype=torch.int32, device=dev)
+            ws = _ws(lib.st3r_radix_sort_ws_bytes(cap), dev)
+        n_cap = cap if plan is not None else fr._n_isect
         with _Prof("st3r_gs_isect"):
             _lib.check(lib.st3r_gs_isect(_lib.ptr(fr.radii), _lib.ptr(fr.geomA), _lib.ptr(fr.cum), N, C, fr.W, fr.H, TILE,
-                                         _lib.ptr(fr.keys), _lib.ptr(fr.vals), n_isect, st), "st3r_gs_isect")
-        ws = _ws(lib.st3r_radix_sort_ws_bytes(n_isect), dev)
+                                         _lib.ptr(fr.keys), _lib.ptr(fr.vals), n_cap, st), "st3r_gs_isect")
         bits = lib.st3r_gs_sort_bits(C, fr.W, fr.H, TILE)
         with _Prof("st3r_radix_sort_pairs"):
             _lib.check(lib.st3r_radix_sort_pairs(_lib.ptr(fr.keys), _lib.ptr(fr.vals), _lib.ptr(keys_alt),
-                                                 _lib.ptr(vals_alt), _lib.ptr(fr.n_isect_dev), n_isect, 0, bits,
+                                                 _lib.ptr(vals_alt), _lib.ptr(n_dev), n_cap, 0, bits,
                                                  _lib.ptr(ws), ws.numel(), st), "st3r_radix_sort_pairs")
-        fr.offsets = torch.empty(max(C * fr.tile_w * fr.tile_h, 1), dtype=torch.int32, device=dev)
+        if plan is not None:
+            fr.offsets, fr.render, fr.alphas, fr.last_ids = plan.offsets, plan.render, plan.alphas, plan.last_ids
+            fr.n_blend = plan.n_blend.zero_() if count_blends else None
+        else:
+            fr.offsets = torch.empty(max(C * fr.tile_w * fr.tile_h, 1), dtype=torch.int32, device=dev)
+            fr.render = torch.empty((C, fr.H, fr.W, 3), dtype=torch.float32, device=dev)
+            fr.alphas = torch.empty((C, fr.H, fr.W), dtype=torch.float32, device=dev)
+            fr.last_ids = torch.empty((C, fr.H, fr.W), dtype=torch.int32, device=dev)
+            fr.n_blend = torch.zeros(1, dtype=torch.int64, device=dev) if count_blends else None
         with _Prof("st3r_gs_offsets"):
-            _lib.check(lib.st3r_gs_offsets(_lib.ptr(fr.keys), _lib.ptr(fr.n_isect_dev), n_isect, C, fr.W, fr.H, TILE,
+            _lib.check(lib.st3r_gs_offsets(_lib.ptr(fr.keys), _lib.ptr(n_dev), n_cap, C, fr.W, fr.H, TILE,
                                            _lib.ptr(fr.offsets), st), "st3r_gs_offsets")
-        fr.render = torch.empty((C, fr.H, fr.W, 3), dtype=torch.float32, device=dev)
-        fr.alphas = torch.empty((C, fr.H, fr.W), dtype=torch.float32, device=dev)
-        fr.last_ids = torch.empty((C, fr.H, fr.W), dtype=torch.int32, device=dev)
-        fr.n_blend = torch.zeros(1, dtype=torch.int64, device=dev) if count_blends else None
         with _Prof("st3r_gs_raster_fwd"):
-            _lib.check(lib.st3r_gs_raster_fwd(_lib.ptr(fr.offsets), _lib.ptr(fr.n_isect_dev), _lib.ptr(fr.vals),
+            _lib.check(lib.st3r_gs_raster_fwd(_lib.ptr(fr.offsets), _lib.ptr(n_dev), _lib.ptr(fr.vals),
                                               _lib.ptr(fr.geomA), _lib.ptr(fr.geomB), _lib.ptr(fr.rgb), C, fr.W, fr.H, TILE,
                                               _lib.ptr(fr.render), _lib.ptr(fr.alphas), _lib.ptr(fr.last_ids),
                                               _lib.ptr(fr.n_blend), st), "st3r_gs_raster_fwd")
@@ -137,18 +248,23 @@ def _forward(means, quats, scales, opacities, shN, cams, width, height, count_bl
 
 
 def _backward(fr, means, quats, scales, opacities, shN, v_render, v_alphas, reg_opac=0.0, reg_scale=0.0,
-              reg_sums=None):
+              reg_sums=None, plan=None):
     """Blend backward + projection/SH backward.  Returns (v_means, v_quats, v_scales, v_opacities, v_sh [N,4,3])."""
     lib = _lib.load()
     dev = means.device
     N, C = fr.N, fr.C
     E = max(C * N, 1)
-    v_geom = torch.zeros((3, E, 4), dtype=torch.float32, device=dev)
-    v_means = torch.empty((N, 3), dtype=torch.float32, device=dev)
-    v_quats = torch.empty((N, 4), dtype=torch.float32, device=dev)
-    v_scales = torch.empty((N, 3), dtype=torch.float32, device=dev)
-    v_opac = torch.empty((N,), dtype=torch.float32, device=dev)
-    v_sh = torch.empty((N, 4, 3), dtype=torch.float32, device=dev)
+    if plan is not None:
+        v_geom = plan.v_geom.zero_()
+        g = plan.grads
+        v_means, v_quats, v_scales, v_opac, v_sh = g["means"], g["quats"], g["scales"], g["opacities"], g["sh"]
+    else:
+        v_geom = torch.zeros((3, E, 4), dtype=torch.float32, device=dev)
+        v_means = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        v_quats = torch.empty((N, 4), dtype=torch.float32, device=dev)
+        v_scales = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        v_opac = torch.empty((N,), dtype=torch.float32, device=dev)
+        v_sh = torch.empty((N, 4, 3), dtype=torch.float32, device=dev)
     st = _lib.stream_ptr()
     with torch.cuda.device(dev):
         with _Prof("st3r_gs_raster_bwd"):
@@ -512,19 +628,25 @@ def _truth_images(scene, device):
 
 
 def train_step(params, states, truth, cams, width, height, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
-               loss_ssim_fac=0.2, loss_opacity_fac=0.01, loss_scale_fac=0.01, count_blends=False, grad_hook=None):
+               loss_ssim_fac=0.2, loss_opacity_fac=0.01, loss_scale_fac=0.01, count_blends=False, grad_hook=None,
+               plan=None, loss_out=None):
     """One fused iteration of gs.py:143-161 (without the strategy hooks): render all C views, loss, backward, Adam.
     params: dict of contiguous fp32 device tensors (means, scales, quats, opacities, shN), updated in place;
-    states: dict name -> (exp_avg, exp_avg_sq).  Returns (loss tensor [] on device, frame)."""
+    states: dict name -> (exp_avg, exp_avg_sq).  With a TrainPlan the iteration allocates nothing and never
+    synchronises with the host.  Returns (loss tensor [] on device, frame)."""
     lib = _lib.load()
     means, quats, scales, opac, shN = (params[k] for k in ("means", "quats", "scales", "opacities", "shN"))
     dev = means.device
-    fr = _forward(means, quats, scales, opac, shN, cams, width, height, count_blends)
+    fr = _forward(means, quats, scales, opac, shN, cams, width, height, count_blends, plan)
     C, N, H, W = fr.C, fr.N, fr.H, fr.W
-    dmaps = torch.empty((C, H, W, 3, 3), dtype=torch.float32, device=dev)
-    sums = torch.zeros((C, 2), dtype=torch.float32, device=dev)
-    reg = torch.zeros(2, dtype=torch.float32, device=dev)
-    v_render = torch.empty_like(fr.render)
+    if plan is not None:
+        acc = plan.acc.zero_()
+        dmaps, v_render = plan.dmaps, plan.v_render
+    else:
+        acc = torch.zeros((2 * C + 2,), dtype=torch.float32, device=dev)
+        dmaps = torch.empty((C, H, W, 3, 3), dtype=torch.float32, device=dev)
+        v_render = torch.empty_like(fr.render)
+    sums, reg = acc[:2 * C], acc[2 * C:]
     st = _lib.stream_ptr()
     with torch.cuda.device(dev):
         with _Prof("st3r_gs_loss_fwd"):
@@ -535,7 +657,7 @@ def train_step(params, states, truth, cams, width, height, step, lr=1e-3, betas=
                                             _f(loss_ssim_fac), _lib.ptr(v_render), st), "st3r_gs_loss_bwd")
     reg_o = C * loss_opacity_fac / max(N, 1)
     reg_s = C * loss_scale_fac / max(3 * N, 1)
-    vm, vq, vs, vo, vsh = _backward(fr, means, quats, scales, opac, shN, v_render, None, reg_o, reg_s, reg)
+    vm, vq, vs, vo, vsh = _backward(fr, means, quats, scales, opac, shN, v_render, None, reg_o, reg_s, reg, plan)
     fr.grads = dict(means=vm, quats=vq, scales=vs, opacities=vo, sh=vsh)
     if grad_hook is not None:      # multi-GPU: all-reduce of the per-Gaussian gradients (views are sharded)
         grad_hook(fr)
@@ -543,9 +665,10 @@ def train_step(params, states, truth, cams, width, height, step, lr=1e-3, betas=
             (quats, vq, *states["quats"], N, 4, 4, 4), (opac, vo, *states["opacities"], N, 1, 1, 1),
             (shN, vsh, *states["shN"], N, 12, shN.shape[1] * 3, 12)]
     adam_step(segs, lr, betas, eps, step)
-    l1 = sums[:, 1] / (3.0 * H * W)
-    ssim = sums[:, 0] / (3.0 * (H - 10) * (W - 10))
-    loss = (l1 * (1 - loss_ssim_fac) + (1 - ssim) * loss_ssim_fac).sum() + reg[0] * reg_o + reg[1] * reg_s
+    loss = loss_out if loss_out is not None else torch.empty((), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.st3r_gs_loss_finalize(_lib.ptr(sums), _lib.ptr(reg), C, H, W, _f(loss_ssim_fac), _f(reg_o), _f(reg_s),
+                                             _lib.ptr(loss), st), "st3r_gs_loss_finalize")
     return loss, fr
 
 
@@ -574,7 +697,15 @@ def run_3dgs_optim(scene, iters, enable_pruning=False, loss_ssim_fac=0.2, loss_o
 
     params, states = bind()
     group = scene.optimizers["means"].param_groups[0]
-    losses_dev = []
+    losses_dev = torch.zeros(max(iters, 1), dtype=torch.float32, device=dev)
+    n_views = cams.shape[0]
+
+    def get_plan():
+        plan = getattr(scene, "_gs_plan", None)
+        if plan is None or not plan.matches(params["means"].shape[0], n_views, width, height, dev):
+            plan = scene._gs_plan = TrainPlan(params["means"].shape[0], n_views, width, height, dev)
+        return plan
+
     pbar = trange(iters, disable=not verbose)
     for step in pbar:
         if enable_pruning:
@@ -582,16 +713,17 @@ def run_3dgs_optim(scene, iters, enable_pruning=False, loss_ssim_fac=0.2, loss_o
         opt_step = int(scene.optimizers["means"]._st(gz["means"])["step"].item()) + 1
         loss, fr = train_step(params, states, truth, cams, width, height, opt_step, lr=group["lr"],
                               betas=group["betas"], eps=group["eps"], loss_ssim_fac=loss_ssim_fac,
-                              loss_opacity_fac=loss_opacity_fac, loss_scale_fac=loss_scale_fac)
+                              loss_opacity_fac=loss_opacity_fac, loss_scale_fac=loss_scale_fac, plan=get_plan(),
+                              loss_out=losses_dev[step])
         for k in names:
             scene.optimizers[k]._st(gz[k])["step"] += 1
-        losses_dev.append(loss)
         if verbose:
             pbar.set_description(f"Gsplat optimization: loss={loss.item()}")
         if enable_pruning:
             scene.strategy.step_post_backward(scene.gaussians, scene.optimizers, scene.strategy_state, step, None, 1e-3)
             if gz["means"].data.data_ptr() != params["means"].data_ptr() or gz["means"].shape[0] != params["means"].shape[0]:
                 params, states = bind()
-    if not losses_dev:
+    if iters <= 0:
         return []
-    return torch.stack(losses_dev).cpu().tolist()
+    get_plan().poll(wait_all=True)
+    return losses_dev[:iters].cpu().tolist()

@@ -223,6 +223,49 @@ def test_train_steps_vs_oracle(cuda_device):
         assert frac_close > 0.97, (k, frac_close)
 
 
+def test_train_plan_matches_unplanned(cuda_device):
+    """TrainPlan (persistent buffers, capacity-sized intersection lists, no host sync) runs the same kernels on the
+    same data as the exact-size path: identical bin indices and render, parameters equal up to the order of the
+    fp32 gradient atomics; it re-sizes itself when the intersection count grows, and fails loudly on overflow."""
+    import starst3r_b200 as st
+    from starst3r_b200 import gs
+    sp, viewmats, Ks, W, H = small_scene(n=800, C=3, seed=5)
+    truth = torch.rand(3, H, W, 3, generator=torch.Generator().manual_seed(1)).to(cuda_device)
+    cams = gs.make_cams(viewmats.to(cuda_device), Ks.to(cuda_device))
+
+    def fresh():
+        p = {k: v.clone().to(cuda_device).contiguous() for k, v in sp.items()}
+        return p, {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in p.items()}
+    pa, sa = fresh()
+    pb, sb = fresh()
+    plan = gs.TrainPlan(800, 3, W, H, cuda_device)
+    for i in range(6):
+        la, fa = gs.train_step(pa, sa, truth, cams, W, H, i + 1)
+        lb, fb = gs.train_step(pb, sb, truth, cams, W, H, i + 1, plan=plan)
+        n = fa.n_isect
+        assert fb.n_isect == n and plan.cap >= n
+        if i == 0:      # same inputs: the integer pipeline and the render are bit-identical
+            assert torch.equal(fa.keys[:n], fb.keys[:n]) and torch.equal(fa.vals[:n], fb.vals[:n])
+            assert torch.equal(fa.offsets, fb.offsets) and torch.equal(fa.render, fb.render)
+        assert abs(la.item() - lb.item()) <= 1e-5 * abs(la.item())
+    for k in pa:
+        assert torch.allclose(pa[k], pb[k], rtol=1e-4, atol=1e-5), k
+    plan.poll(wait_all=True)
+    # growth: inflate the Gaussians so the intersection count jumps past 80 % of the capacity
+    cap0 = plan.cap
+    pb["scales"] *= 1.6
+    for i in range(3):
+        try:
+            gs.train_step(pb, sb, truth, cams, W, H, 7 + i, plan=plan)
+            plan.poll(wait_all=True)
+        except RuntimeError as e:     # a jump beyond the headroom is reported, never silently truncated
+            assert "exceed the buffer capacity" in str(e)
+    assert plan.cap > cap0
+    lb, fb = gs.train_step(pb, sb, truth, cams, W, H, 10, plan=plan)
+    plan.poll(wait_all=True)
+    assert fb.n_isect <= plan.cap and plan.last_n_isect == fb.n_isect
+
+
 def test_scene_api_run_3dgs_optim(cuda_device):
     """Scene.init_3dgs / run_3dgs_optim / render_3dgs_original with the reference's call pattern (main.py:77-88):
     the loss decreases and the API objects have the reference's shape."""
