@@ -48,6 +48,21 @@ __device__ __forceinline__ uint32_t row_mask(const float4 A, const float4 B, int
   return ((2u << ihi) - 1u) & ~((1u << ilo) - 1u);
 }
 
+// Per-warp visit lists.  Every warp owns two tile rows; testing each staged Gaussian's row mask in every warp cost
+// ~18 instructions per (warp, Gaussian) although 70 % of the tests fail (ncu source view, r01b: 29 % of all
+// instructions of the backward kernel).  Instead the mask of the Gaussian held by thread `tr` is transposed once per
+// batch with eight ballots per warp into list[row pair][word] (bit = Gaussian of the batch), and each warp walks
+// only the set bits of its own 256-bit list.
+__device__ __forceinline__ void publish_visit_lists(uint32_t m, uint32_t (*list)[8]) {
+  uint32_t mine = 0;
+#pragma unroll
+  for (int rp = 0; rp < 8; ++rp) {
+    const uint32_t b = __ballot_sync(0xffffffffu, (m >> (2 * rp)) & 3u);
+    if (lane_id() == rp) mine = b;
+  }
+  if (lane_id() < 8) list[lane_id()][threadIdx.x >> 5] = mine;
+}
+
 __global__ void __launch_bounds__(BLOCK)
 raster_fwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
                   const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
@@ -55,14 +70,14 @@ raster_fwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
                   int tile_h, float* __restrict__ render, float* __restrict__ alphas, int32_t* __restrict__ last_ids,
                   unsigned long long* __restrict__ n_blend) {
   __shared__ float4 sA[BLOCK], sB[BLOCK], sC[BLOCK];
-  __shared__ uint32_t sM[BLOCK];
+  __shared__ uint32_t sL[8][8];
   const int c = blockIdx.y, tile = blockIdx.x;
   const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
   const int tr = threadIdx.x;
   const int i = tyi * TILE + (tr >> 4), j = txi * TILE + (tr & 15);
   const float px = (float)j + 0.5f, py = (float)i + 0.5f;
   const bool inside = i < H && j < W;
-  const uint32_t my_rows = 3u << (2 * (tr >> 5));   // the two tile rows this warp owns
+  const int wrp = tr >> 5;                          // this warp owns tile rows 2 wrp, 2 wrp + 1
   bool done = !inside;
   const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
   const int nb = (rg.hi - rg.lo + BLOCK - 1) / BLOCK;
@@ -72,31 +87,38 @@ raster_fwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
     if (__syncthreads_count(done) == BLOCK) break;
     const int start = rg.lo + b * BLOCK;
     const int idx = start + tr;
+    uint32_t m = 0;
     if (idx < rg.hi) {
       uint32_t e = flatten[idx];
       const float4 A = geomA[e], B = geomB[e];
       sA[tr] = A;
       sB[tr] = B;
       sC[tr] = rgb[e];
-      sM[tr] = row_mask(A, B, tyi * TILE);
+      m = row_mask(A, B, tyi * TILE);
     }
+    publish_visit_lists(m, sL);
     __syncthreads();
-    const int bs = min(BLOCK, rg.hi - start);
-    for (int t = 0; t < bs && !done; ++t) {
-      if (!(sM[t] & my_rows)) continue;   // warp-uniform cull
-      const float4 A = sA[t], B = sB[t];
-      const float dx = A.x - px, dy = A.y - py;
-      const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
-      const float alpha = fminf(ALPHA_MAX, A.z * __expf(-sigma));
-      if (sigma < 0.f || alpha < ALPHA_MIN) continue;
-      const float nT = T * (1.0f - alpha);
-      if (nT <= T_MIN) { done = true; break; }
-      const float w = alpha * T;
-      const float4 col = sC[t];
-      pr += col.x * w; pg += col.y * w; pb += col.z * w;
-      cur = start + t;
-      T = nT;
-      ++blends;
+    for (int wi = 0; wi < 8; ++wi) {
+      uint32_t bits = sL[wrp][wi];        // warp-uniform: the Gaussians of this batch that can touch my two rows
+      if (bits && __all_sync(0xffffffffu, done)) break;
+      while (bits) {
+        const int t = wi * 32 + __ffs(bits) - 1;
+        bits &= bits - 1;
+        if (done) continue;
+        const float4 A = sA[t], B = sB[t];
+        const float dx = A.x - px, dy = A.y - py;
+        const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
+        const float alpha = fminf(ALPHA_MAX, A.z * __expf(-sigma));
+        if (sigma < 0.f || alpha < ALPHA_MIN) continue;
+        const float nT = T * (1.0f - alpha);
+        if (nT <= T_MIN) { done = true; continue; }
+        const float w = alpha * T;
+        const float4 col = sC[t];
+        pr += col.x * w; pg += col.y * w; pb += col.z * w;
+        cur = start + t;
+        T = nT;
+        ++blends;
+      }
     }
   }
   if (inside) {
@@ -125,7 +147,8 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
                   const float* __restrict__ v_render, const float* __restrict__ v_alphas,
                   float4* __restrict__ v_geomA, float4* __restrict__ v_geomB, float4* __restrict__ v_rgb) {
   __shared__ float4 sA[BLOCK], sB[BLOCK], sC[BLOCK];
-  __shared__ uint32_t sE[BLOCK], sM[BLOCK];
+  __shared__ uint32_t sE[BLOCK];
+  __shared__ uint32_t sL[8][8];
   __shared__ float acc[BLOCK][9];  // per-batch gradient accumulators (xy 2, opac 1, conic 3, rgb 3)
   const int c = blockIdx.y, tile = blockIdx.x;
   const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
@@ -133,7 +156,7 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
   const int i = tyi * TILE + (tr >> 4), j = txi * TILE + (tr & 15);
   const float px = (float)j + 0.5f, py = (float)i + 0.5f;
   const bool inside = i < H && j < W;
-  const uint32_t my_rows = 3u << (2 * (tr >> 5));
+  const int wrp = tr >> 5;
   const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
   if (rg.hi <= rg.lo) return;
   const size_t p = ((size_t)c * H + min(i, H - 1)) * W + min(j, W - 1);
@@ -155,6 +178,7 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
     const int batch_end = rg.hi - 1 - BLOCK * b;
     const int bs = min(BLOCK, batch_end + 1 - rg.lo);
     const int idx = batch_end - tr;
+    uint32_t m = 0;
     if (idx >= rg.lo) {
       uint32_t e = flatten[idx];
       const float4 A = geomA[e], B = geomB[e];
@@ -162,13 +186,21 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
       sA[tr] = A;
       sB[tr] = B;
       sC[tr] = rgb[e];
-      sM[tr] = row_mask(A, B, tyi * TILE);
+      m = row_mask(A, B, tyi * TILE);
     }
+    publish_visit_lists(m, sL);
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[tr][k] = 0.f;
     __syncthreads();
-    for (int t = max(0, batch_end - warp_bin_final); t < bs; ++t) {
-      if (!(sM[t] & my_rows)) continue;   // warp-uniform cull (see row_mask)
+    // Batch slot t holds sorted position batch_end - t: ascending t walks back to front.  Slots before t0 lie behind
+    // the last Gaussian any pixel of this warp blended in the forward pass.
+    const int t0 = max(0, batch_end - warp_bin_final);
+    for (int wi = t0 >> 5; wi < 8; ++wi) {
+     uint32_t bits = sL[wrp][wi];
+     if (wi == (t0 >> 5)) bits &= 0xffffffffu << (t0 & 31);
+     while (bits) {
+      const int t = wi * 32 + __ffs(bits) - 1;
+      bits &= bits - 1;
       bool valid = inside && (batch_end - t <= bin_final);
       float alpha = 0.f, opac = 0.f, vis = 0.f, dx = 0.f, dy = 0.f;
       float4 B = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -236,6 +268,7 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
         if ((lane & 3) == 0 && c1 != 0.f) atomicAdd(&acc[t][vi], c1);
         if (lane == 1 && g8 != 0.f) atomicAdd(&acc[t][8], g8);
       }
+     }
     }
     __syncthreads();
     if (tr < bs) {
