@@ -141,6 +141,15 @@ ST3R_API int st3r_radix_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t* key
 ST3R_API int st3r_gs_offsets(const uint64_t* keys, const int32_t* n_isect, int n_cap, int C, int width, int height,
                     int tile_size, int32_t* offsets, cudaStream_t stream);
 
+/* isect_tiles + SortPairs + isect_offset_encode in one call (same outputs, bit for bit, as the three entry points
+ * above): counting sort on (camera, tile), shared-memory sort on (depth, entry) inside each tile.  offsets
+ * [C, tile_h, tile_w] int32; *n_isect_out (device) = true number of intersections; keys / vals capacity n_cap (pairs
+ * beyond it are dropped and offsets is clamped to it; n_cap = 0 only counts). */
+ST3R_API size_t st3r_gs_bin_ws_bytes(int C, int width, int height, int tile_size, int n_cap);
+ST3R_API int st3r_gs_bin_tiles(const int32_t* radii, const float* geomA, int N, int C, int width, int height, int tile_size,
+                      int32_t* offsets, int32_t* n_isect_out, uint64_t* keys, uint32_t* vals, int n_cap, void* ws,
+                      size_t ws_bytes, cudaStream_t stream);
+
 /* rasterize_to_pixels forward: render [C,H,W,3], alphas [C,H,W], last_ids [C,H,W] int32;
  * n_blend (optional, uint64, accumulated) counts blended (pixel, Gaussian) pairs. */
 ST3R_API int st3r_gs_raster_fwd(const int32_t* offsets, const int32_t* n_isect, const uint32_t* flatten_ids,

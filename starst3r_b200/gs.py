@@ -17,6 +17,9 @@ from . import _lib
 __all__ = ("init_3dgs", "render_3dgs", "render_3dgs_original", "run_3dgs_optim", "rasterization", "FusedAdam")
 
 TILE = 16
+# "fused": st3r_gs_bin_tiles (counting sort by tile + in-tile shared-memory sort); "radix": the generic
+# st3r_gs_isect -> st3r_radix_sort_pairs -> st3r_gs_offsets chain.  Both produce identical arrays.
+BINNING = "fused"
 EPS2D, NEAR, FAR, RADIUS_CLIP = 0.3, 0.01, 1e10, 0.0
 
 
@@ -135,6 +138,8 @@ class TrainPlan:
         self.keys_alt = torch.empty(self.cap, dtype=torch.int64, device=self.dev)
         self.vals_alt = torch.empty(self.cap, dtype=torch.int32, device=self.dev)
         self.sort_ws = _ws(lib.st3r_radix_sort_ws_bytes(self.cap), self.dev)
+        self.bin_ws = _ws(lib.st3r_gs_bin_ws_bytes(self.C, self.W, self.H, TILE, self.cap), self.dev)
+        self.n_total = torch.zeros(1, dtype=torch.int32, device=self.dev)
 
     def poll(self, wait_all=False):
         """Checks the counts of earlier frames (waits for all but the newest, so the host stays at most one frame
@@ -205,40 +210,48 @@ def _forward(means, quats, scales, opacities, shN, cams, width, height, count_bl
         if plan is not None:
             # capacity-sized intersection buffers, count clamped on the device, checked one frame later
             plan.after_scan()
-            cap, n_dev = plan.cap, plan.n_clamped
+            n_cap, n_dev = plan.cap, plan.n_clamped
             fr.keys, fr.vals, keys_alt, vals_alt, ws = plan.keys, plan.vals, plan.keys_alt, plan.vals_alt, plan.sort_ws
+            bin_ws, n_total = plan.bin_ws, plan.n_total
             fr.n_isect_dev = n_dev
+            fr.offsets, fr.render, fr.alphas, fr.last_ids = plan.offsets, plan.render, plan.alphas, plan.last_ids
+            fr.n_blend = plan.n_blend.zero_() if count_blends else None
         else:
             # One host read per frame sizes the intersection buffers exactly (gsplat does the same).
             n_isect = int(fr.n_isect_dev.item())
             fr._n_isect = n_isect
-            cap, n_dev = max(n_isect, 1), fr.n_isect_dev
-            fr.keys = torch.empty(cap, dtype=torch.int64, device=dev)
-            fr.vals = torch.empty(cap, dtype=torch.int32, device=dev)
-            keys_alt = torch.empty(cap, dtype=torch.int64, device=dev)
-            vals_alt = torch.empty(cap, dtype=torch.int32, device=dev)
-            ws = _ws(lib.st3r_radix_sort_ws_bytes(cap), dev)
-        n_cap = cap if plan is not None else fr._n_isect
-        with _Prof("st3r_gs_isect"):
-            _lib.check(lib.st3r_gs_isect(_lib.ptr(fr.radii), _lib.ptr(fr.geomA), _lib.ptr(fr.cum), N, C, fr.W, fr.H, TILE,
-                                         _lib.ptr(fr.keys), _lib.ptr(fr.vals), n_cap, st), "st3r_gs_isect")
-        bits = lib.st3r_gs_sort_bits(C, fr.W, fr.H, TILE)
-        with _Prof("st3r_radix_sort_pairs"):
-            _lib.check(lib.st3r_radix_sort_pairs(_lib.ptr(fr.keys), _lib.ptr(fr.vals), _lib.ptr(keys_alt),
-                                                 _lib.ptr(vals_alt), _lib.ptr(n_dev), n_cap, 0, bits,
-                                                 _lib.ptr(ws), ws.numel(), st), "st3r_radix_sort_pairs")
-        if plan is not None:
-            fr.offsets, fr.render, fr.alphas, fr.last_ids = plan.offsets, plan.render, plan.alphas, plan.last_ids
-            fr.n_blend = plan.n_blend.zero_() if count_blends else None
-        else:
+            n_cap, n_dev = n_isect, fr.n_isect_dev
+            fr.keys = torch.empty(max(n_cap, 1), dtype=torch.int64, device=dev)
+            fr.vals = torch.empty(max(n_cap, 1), dtype=torch.int32, device=dev)
             fr.offsets = torch.empty(max(C * fr.tile_w * fr.tile_h, 1), dtype=torch.int32, device=dev)
             fr.render = torch.empty((C, fr.H, fr.W, 3), dtype=torch.float32, device=dev)
             fr.alphas = torch.empty((C, fr.H, fr.W), dtype=torch.float32, device=dev)
             fr.last_ids = torch.empty((C, fr.H, fr.W), dtype=torch.int32, device=dev)
             fr.n_blend = torch.zeros(1, dtype=torch.int64, device=dev) if count_blends else None
-        with _Prof("st3r_gs_offsets"):
-            _lib.check(lib.st3r_gs_offsets(_lib.ptr(fr.keys), _lib.ptr(n_dev), n_cap, C, fr.W, fr.H, TILE,
-                                           _lib.ptr(fr.offsets), st), "st3r_gs_offsets")
+            if BINNING == "fused":
+                bin_ws = _ws(lib.st3r_gs_bin_ws_bytes(C, fr.W, fr.H, TILE, n_cap), dev)
+                n_total = torch.zeros(1, dtype=torch.int32, device=dev)
+            else:
+                keys_alt = torch.empty(max(n_cap, 1), dtype=torch.int64, device=dev)
+                vals_alt = torch.empty(max(n_cap, 1), dtype=torch.int32, device=dev)
+                ws = _ws(lib.st3r_radix_sort_ws_bytes(max(n_cap, 1)), dev)
+        if BINNING == "fused":
+            with _Prof("st3r_gs_bin_tiles"):
+                _lib.check(lib.st3r_gs_bin_tiles(_lib.ptr(fr.radii), _lib.ptr(fr.geomA), N, C, fr.W, fr.H, TILE,
+                                                 _lib.ptr(fr.offsets), _lib.ptr(n_total), _lib.ptr(fr.keys), _lib.ptr(fr.vals),
+                                                 n_cap, _lib.ptr(bin_ws), bin_ws.numel(), st), "st3r_gs_bin_tiles")
+        else:
+            with _Prof("st3r_gs_isect"):
+                _lib.check(lib.st3r_gs_isect(_lib.ptr(fr.radii), _lib.ptr(fr.geomA), _lib.ptr(fr.cum), N, C, fr.W, fr.H, TILE,
+                                             _lib.ptr(fr.keys), _lib.ptr(fr.vals), n_cap, st), "st3r_gs_isect")
+            bits = lib.st3r_gs_sort_bits(C, fr.W, fr.H, TILE)
+            with _Prof("st3r_radix_sort_pairs"):
+                _lib.check(lib.st3r_radix_sort_pairs(_lib.ptr(fr.keys), _lib.ptr(fr.vals), _lib.ptr(keys_alt),
+                                                     _lib.ptr(vals_alt), _lib.ptr(n_dev), n_cap, 0, bits,
+                                                     _lib.ptr(ws), ws.numel(), st), "st3r_radix_sort_pairs")
+            with _Prof("st3r_gs_offsets"):
+                _lib.check(lib.st3r_gs_offsets(_lib.ptr(fr.keys), _lib.ptr(n_dev), n_cap, C, fr.W, fr.H, TILE,
+                                               _lib.ptr(fr.offsets), st), "st3r_gs_offsets")
         with _Prof("st3r_gs_raster_fwd"):
             _lib.check(lib.st3r_gs_raster_fwd(_lib.ptr(fr.offsets), _lib.ptr(n_dev), _lib.ptr(fr.vals),
                                               _lib.ptr(fr.geomA), _lib.ptr(fr.geomB), _lib.ptr(fr.rgb), C, fr.W, fr.H, TILE,

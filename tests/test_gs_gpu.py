@@ -223,6 +223,35 @@ def test_train_steps_vs_oracle(cuda_device):
         assert frac_close > 0.97, (k, frac_close)
 
 
+@pytest.mark.parametrize("n,scale_mult,C,W,H", [(500, 8.0, 3, 80, 48), (3000, 60.0, 2, 64, 64), (20000, 40.0, 1, 40, 40),
+                                                 (50, 1.0, 2, 33, 17)])
+def test_fused_binning_equals_radix_chain(cuda_device, n, scale_mult, C, W, H):
+    """st3r_gs_bin_tiles (counting sort by tile + in-tile sort) == st3r_gs_isect + st3r_radix_sort_pairs +
+    st3r_gs_offsets, bit for bit (isect_ids, flatten_ids, isect_offsets), including tiles whose list is longer than
+    the shared-memory sort (4096 pairs; the 20000-Gaussian case has ~20000 per tile)."""
+    from starst3r_b200 import gs
+    sp, viewmats, Ks, W, H = small_scene(n=n, C=C, W=W, H=H, seed=n, scale_mult=scale_mult)
+    d = to(cuda_device, sp)
+    out = {}
+    for mode in ("radix", "fused"):
+        gs.BINNING = mode
+        try:
+            with torch.no_grad():
+                r, a, info = gs.rasterization(d["means"], d["quats"], d["scales"], d["opacities"], d["shN"],
+                                              viewmats.to(cuda_device), Ks.to(cuda_device), W, H)
+        finally:
+            gs.BINNING = "fused"
+        out[mode] = (r, a, info)
+    ia, ib = out["radix"][2], out["fused"][2]
+    assert ia["isect_ids"].numel() == ib["isect_ids"].numel() and ia["isect_ids"].numel() > 0
+    if n == 20000:
+        per_tile = torch.diff(ia["isect_offsets"].flatten())
+        assert per_tile.max().item() > 4096          # exercises the global-memory sort path
+    for k in ("isect_ids", "flatten_ids", "isect_offsets"):
+        assert torch.equal(ia[k], ib[k]), k
+    assert torch.equal(out["radix"][0], out["fused"][0]) and torch.equal(out["radix"][1], out["fused"][1])
+
+
 def test_train_plan_matches_unplanned(cuda_device):
     """TrainPlan (persistent buffers, capacity-sized intersection lists, no host sync) runs the same kernels on the
     same data as the exact-size path: identical bin indices and render, parameters equal up to the order of the
