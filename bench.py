@@ -119,7 +119,18 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     plan = gs.TrainPlan(N_GAUSS, N_VIEWS, W, H, dev)     # persistent buffers: no allocation / host sync per step
-    hook = (lambda fr: allreduce_grads(fr, world)) if world > 1 else None
+    hook, exchange = None, "none"
+    if world > 1:
+        # gradient exchange: peer loads inside the fused Adam kernel (symmetric memory over NVLink); NCCL all-reduce
+        # only if symmetric memory cannot be set up on this box
+        try:
+            from starst3r_b200 import dist as sd
+            plan.peer = sd.PeerGradExchange(N_GAUSS, dev)
+            exchange = "fused P2P gradient sum + Adam (st3r_adam_step_peers, NVLink peer loads)"
+        except Exception as e:      # noqa: BLE001
+            print(f"bench: symmetric memory unavailable ({e!r}); using NCCL all-reduce", file=sys.stderr)
+            hook = lambda fr: allreduce_grads(fr, world)
+            exchange = "NCCL all-reduce of the gradients + Adam"
 
     def step_fn(i, prof=False, images=None):
         return gs.train_step(params, states, truth if images is None else images, cams, W, H, i + 1,
@@ -296,7 +307,7 @@ def run_ours(args):
             "config": {"workload": "8-view 512x512 synthetic scene, 200k Gaussians, 3DGS train step "
                                    "(render fwd + L1/SSIM loss + bwd + Adam), BASELINE.json configs[1]",
                        "views_per_gpu": N_VIEWS, "gaussians": N_GAUSS, "image": [H, W],
-                       "parallelism": f"views sharded dp{world}, gradient all-reduce" if world > 1 else "single GPU",
+                       "parallelism": f"views sharded dp{world}, {exchange}" if world > 1 else "single GPU",
                        "l2": "256 MiB flush between timed steps"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,

@@ -196,6 +196,16 @@ ST3R_API int st3r_adam_step(int n_seg, float* const* h_params, const float* cons
                    const int* h_ld_grad, double lr, double beta1, double beta2, double eps, int step,
                    cudaStream_t stream);
 
+/* Multi-GPU form of st3r_adam_step: gradient all-reduce fused with the Adam update over peer memory.  Every rank
+ * keeps its per-Gaussian gradients in a symmetric buffer mapped by all ranks (NVLink P2P); h_peer_grad_bases[r] is
+ * rank r's buffer as seen from THIS device, h_grad_offsets[i] the float offset of tensor i inside it (same on all
+ * ranks; row stride h_ld_grad[i]).  Each element is summed over the ranks in rank order (identical on every replica)
+ * and applied at once.  The caller orders the kernel after every rank's gradient writes (cross-device barrier). */
+ST3R_API int st3r_adam_step_peers(int n_seg, float* const* h_params, const long long* h_grad_offsets, float* const* h_exp_avg,
+                         float* const* h_exp_avg_sq, const int* h_rows, const int* h_cols, const int* h_ld_param,
+                         const int* h_ld_grad, int world, const float* const* h_peer_grad_bases, double lr,
+                         double beta1, double beta2, double eps, int step, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ MCMC strategy
  * gsplat.MCMCStrategy as driven by starster/gs.py:43-45 (construction), :146-147 (step_pre_backward, a no-op for
  * MCMC) and :163-164 (step_post_backward(..., lr=1e-3)); gsplat 1.4 strategy/mcmc.py + strategy/ops.py semantics

@@ -34,7 +34,77 @@ adam_kernel(AdamSegs segs, float lr_over_bc1, float inv_sqrt_bc2, float one_minu
     sg.v[ip] = v;
   }
 }
+// Fused gradient all-reduce + Adam over peer memory (multi-GPU training, SURVEY.md §8e: views are sharded, the splat is
+// replicated, the only exchange is the sum of the per-Gaussian gradients).  Every rank's gradients live at the same
+// offsets of a symmetric buffer that all ranks map (NVLink P2P through NVSwitch); this kernel reads element i of every
+// peer, adds them in rank order (so all replicas compute bit-identical sums and stay in lock-step) and applies the
+// Adam update in the same pass: the reduced gradient never exists in HBM and there is no separate collective.
+constexpr int MAX_PEERS = 8;
+struct PeerGrads { const float* base[MAX_PEERS]; int world; };
+struct PeerOffsets { long long off[8]; };
+
+__global__ void __launch_bounds__(256)
+adam_peer_kernel(AdamSegs segs, PeerGrads peers, PeerOffsets goff, float lr_over_bc1, float inv_sqrt_bc2,
+                 float one_minus_b1, float b2, float one_minus_b2, float eps) {
+  const AdamSeg sg = segs.s[blockIdx.y];
+  const long long base = goff.off[blockIdx.y];
+  const long long total = (long long)sg.rows * sg.cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / sg.cols), c = (int)(i - (long long)r * sg.cols);
+    const size_t ip = (size_t)r * sg.ld_p + c;
+    const long long ig = base + (long long)r * sg.ld_g + c;
+    float g = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAX_PEERS; ++k)
+      if (k < peers.world) g += __ldcv(peers.base[k] + ig);     // volatile-cached: never a stale L1 line of peer memory
+    float m = sg.m[ip], v = sg.v[ip];
+    m = m + (g - m) * one_minus_b1;
+    v = v * b2 + one_minus_b2 * g * g;
+    const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
+    sg.p[ip] = sg.p[ip] - lr_over_bc1 * (m / denom);
+    sg.m[ip] = m;
+    sg.v[ip] = v;
+  }
+}
 }  // namespace
+
+extern "C" int st3r_adam_step_peers(int n_seg, float* const* params, const long long* grad_offsets, float* const* exp_avg,
+                                    float* const* exp_avg_sq, const int* rows, const int* cols, const int* ld_param,
+                                    const int* ld_grad, int world, const float* const* peer_grad_bases, double lr,
+                                    double beta1, double beta2, double eps, int step, cudaStream_t stream) {
+  ST3R_CHECK_ARG(n_seg >= 0 && n_seg <= 8 && step >= 1, "st3r_adam_step_peers: bad args (n_seg <= 8, step >= 1)");
+  ST3R_CHECK_ARG(world >= 1 && world <= MAX_PEERS, "st3r_adam_step_peers: world size must be 1..%d", MAX_PEERS);
+  if (n_seg == 0) return ST3R_OK;
+  ST3R_CHECK_ARG(params && grad_offsets && exp_avg && exp_avg_sq && rows && cols && ld_param && ld_grad && peer_grad_bases,
+                 "st3r_adam_step_peers: null");
+  AdamSegs segs;
+  PeerGrads peers;
+  PeerOffsets goff;
+  segs.n = n_seg;
+  peers.world = world;
+  for (int k = 0; k < MAX_PEERS; ++k) peers.base[k] = peer_grad_bases[k < world ? k : 0];
+  for (int k = 0; k < world; ++k) ST3R_CHECK_ARG(peer_grad_bases[k], "st3r_adam_step_peers: null peer buffer %d", k);
+  long long max_total = 0;
+  for (int i = 0; i < 8; ++i) goff.off[i] = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    ST3R_CHECK_ARG(params[i] && exp_avg[i] && exp_avg_sq[i] && rows[i] >= 0 && cols[i] > 0 && grad_offsets[i] >= 0,
+                   "st3r_adam_step_peers: bad segment %d", i);
+    segs.s[i] = AdamSeg{params[i], nullptr, exp_avg[i], exp_avg_sq[i], rows[i], cols[i], ld_param[i], ld_grad[i]};
+    goff.off[i] = grad_offsets[i];
+    long long t = (long long)rows[i] * cols[i];
+    if (t > max_total) max_total = t;
+  }
+  if (max_total == 0) return ST3R_OK;
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  int blocks = (int)((max_total + 255) / 256);
+  int cap = st3r_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  adam_peer_kernel<<<dim3(blocks, n_seg), 256, 0, stream>>>(segs, peers, goff, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)),
+                                                           (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+                                                           (float)eps);
+  ST3R_CHECK_LAUNCH();
+  return ST3R_OK;
+}
 
 extern "C" int st3r_adam_step(int n_seg, float* const* params, const float* const* grads, float* const* exp_avg,
                               float* const* exp_avg_sq, const int* rows, const int* cols, const int* ld_param,

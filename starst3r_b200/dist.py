@@ -76,3 +76,48 @@ def broadcast_tensors(tensors, src=0, group=None):
         for t in tensors:
             dist.broadcast(t, src, group=group)
     return tensors
+
+
+class PeerGradExchange:
+    """Gradient exchange of sharded-view training without a collective call: every rank's per-Gaussian gradients live
+    in a symmetric-memory buffer that all ranks of the node map over NVLink (torch symmetric memory does the
+    allocation, the handle exchange and the cross-device barrier: plumbing); the sum over ranks happens inside the
+    fused Adam kernel (csrc/gs_adam.cu: st3r_adam_step_peers), which reads every peer's buffer directly.
+    Two gradient buffers alternate between iterations, so ONE barrier per step orders both "all gradients of step k
+    are written" and "nobody still reads the buffer step k+1 will overwrite"."""
+    FLOATS = 23            # means 3 | quats 4 | scales 3 | opacity 1 | SH (4 coefficients x 3)
+
+    def __init__(self, n_gauss, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.N = int(n_gauss)
+        self.group = group if group is not None else dist.group.WORLD
+        self.stride = (self.FLOATS * self.N + 63) // 64 * 64          # floats per parity, 256-byte aligned
+        self.buf = symm_mem.empty(2 * self.stride, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.rank, self.world = self.hdl.rank, self.hdl.world_size
+        self.step = 0
+        N = self.N
+        self.offsets = dict(means=0, quats=3 * N, scales=7 * N, opacities=10 * N, sh=11 * N)
+        self.sets = []
+        for parity in (0, 1):
+            b = self.buf[parity * self.stride:(parity + 1) * self.stride]
+            self.sets.append(dict(means=b[0:3 * N].view(N, 3), quats=b[3 * N:7 * N].view(N, 4),
+                                  scales=b[7 * N:10 * N].view(N, 3), opacities=b[10 * N:11 * N],
+                                  sh=b[11 * N:23 * N].view(N, 4, 3)))
+        self.hdl.barrier(channel=0)
+
+    def grads(self):
+        """Gradient tensors the backward pass of the CURRENT step must write into."""
+        return self.sets[self.step & 1]
+
+    def peer_bases(self):
+        """Device addresses of every rank's buffer of the current parity, as seen from this device."""
+        off = (self.step & 1) * self.stride * 4
+        return [int(p) + off for p in self.hdl.buffer_ptrs]
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
+
+    def advance(self):
+        self.step += 1

@@ -120,6 +120,7 @@ class TrainPlan:
         self.dmaps = torch.empty((C, self.H, self.W, 3, 3), dtype=f32, device=device)
         self.acc = torch.zeros((2 * C + 2,), dtype=f32, device=device)    # [C,2] SSIM / L1 sums | 2 regulariser sums
         self.v_render = torch.empty((C, self.H, self.W, 3), dtype=f32, device=device)
+        self.peer = None       # dist.PeerGradExchange when the views are sharded over GPUs (gradients live there)
         self.cap = 0
         self.keys = self.vals = self.keys_alt = self.vals_alt = self.sort_ws = None
         self._host = torch.zeros(64, dtype=i32).pin_memory()           # ring of asynchronously copied counts
@@ -269,7 +270,7 @@ def _backward(fr, means, quats, scales, opacities, shN, v_render, v_alphas, reg_
     E = max(C * N, 1)
     if plan is not None:
         v_geom = plan.v_geom.zero_()
-        g = plan.grads
+        g = plan.peer.grads() if plan.peer is not None else plan.grads
         v_means, v_quats, v_scales, v_opac, v_sh = g["means"], g["quats"], g["scales"], g["opacities"], g["sh"]
     else:
         v_geom = torch.zeros((3, E, 4), dtype=torch.float32, device=dev)
@@ -404,6 +405,26 @@ def adam_step(segments, lr, betas, eps, step):
                                 ctypes.c_double(betas[1]), ctypes.c_double(eps),
                                 int(step), _lib.stream_ptr())
     _lib.check(rc, "st3r_adam_step")
+
+
+def adam_step_peers(segments, grad_offsets, peer_bases, lr, betas, eps, step):
+    """Fused (sum of the gradients over all ranks' symmetric buffers) + Adam; see st3r_adam_step_peers."""
+    lib = _lib.load()
+    n, w = len(segments), len(peer_bases)
+    PP, II, LL = ctypes.c_void_p * n, ctypes.c_int * n, ctypes.c_longlong * n
+    p = PP(*[s[0].data_ptr() for s in segments])
+    m = PP(*[s[2].data_ptr() for s in segments])
+    v = PP(*[s[3].data_ptr() for s in segments])
+    rows, cols = II(*[int(s[4]) for s in segments]), II(*[int(s[5]) for s in segments])
+    ldp, ldg = II(*[int(s[6]) for s in segments]), II(*[int(s[7]) for s in segments])
+    offs = LL(*[int(o) for o in grad_offsets])
+    bases = (ctypes.c_void_p * w)(*[int(b) for b in peer_bases])
+    dev = segments[0][0].device
+    with torch.cuda.device(dev), _Prof("st3r_adam_step_peers"):
+        rc = lib.st3r_adam_step_peers(n, p, offs, m, v, rows, cols, ldp, ldg, w, bases, ctypes.c_double(lr),
+                                      ctypes.c_double(betas[0]), ctypes.c_double(betas[1]), ctypes.c_double(eps),
+                                      int(step), _lib.stream_ptr())
+    _lib.check(rc, "st3r_adam_step_peers")
 
 
 class MCMCStrategy:
@@ -677,7 +698,15 @@ def train_step(params, states, truth, cams, width, height, step, lr=1e-3, betas=
     segs = [(means, vm, *states["means"], N, 3, 3, 3), (scales, vs, *states["scales"], N, 3, 3, 3),
             (quats, vq, *states["quats"], N, 4, 4, 4), (opac, vo, *states["opacities"], N, 1, 1, 1),
             (shN, vsh, *states["shN"], N, 12, shN.shape[1] * 3, 12)]
-    adam_step(segs, lr, betas, eps, step)
+    peer = plan.peer if plan is not None else None
+    if peer is not None:
+        # sharded views: one cross-device barrier, then the gradient sum over the ranks happens inside the Adam kernel
+        peer.barrier()
+        adam_step_peers(segs, [peer.offsets[k] for k in ("means", "scales", "quats", "opacities", "sh")], peer.peer_bases(),
+                        lr, betas, eps, step)
+        peer.advance()
+    else:
+        adam_step(segs, lr, betas, eps, step)
     loss = loss_out if loss_out is not None else torch.empty((), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.st3r_gs_loss_finalize(_lib.ptr(sums), _lib.ptr(reg), C, H, W, _f(loss_ssim_fac), _f(reg_o), _f(reg_s),
