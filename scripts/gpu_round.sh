@@ -20,7 +20,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/${TAG}_launches_match_pair.csv \
     python scripts/prof_step.py match > $OUT/ncu_match.log 2>&1
 echo "== ncu full captures"
-for k in raster_bwd_kernel raster_fwd_kernel; do
+for k in raster_bwd_kernel raster_fwd_kernel tile_sort_kernel ssim_l1_fwd_kernel; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip 2 -c 1 -f -o $OUT/${TAG}_prof_$k \
       python scripts/prof_step.py step > $OUT/ncu_$k.log 2>&1
 done

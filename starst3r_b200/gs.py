@@ -14,7 +14,8 @@ from tqdm import trange
 
 from . import _lib
 
-__all__ = ("init_3dgs", "render_3dgs", "render_3dgs_original", "run_3dgs_optim", "rasterization", "FusedAdam")
+__all__ = ("init_3dgs", "render_3dgs", "render_3dgs_original", "render_3dgs_path", "run_3dgs_optim", "rasterization",
+           "FusedAdam", "MCMCStrategy", "TrainPlan")
 
 TILE = 16
 # "fused": st3r_gs_bin_tiles (counting sort by tile + in-tile shared-memory sort); "radix": the generic
@@ -649,6 +650,24 @@ def render_3dgs(scene, w2c, intrinsics, width, height):
 def render_3dgs_original(scene, width, height):
     """gs.py:90-95."""
     return scene.render_3dgs(scene.w2c, scene.intrinsics, width, height)
+
+
+def render_3dgs_path(scene, c2w_start, c2w_end, steps, intrinsics, width, height, chunk=32):
+    """Novel-view fly-through (what the reference's demo renders frame by frame with
+    utils.interp_se3_path + render_3dgs): the interpolated cameras are rendered `chunk` at a time as ONE batched
+    rasterization call each (the kernels are batched over cameras).  Returns [steps, H, W, 3] on the device."""
+    from .utils import interp_se3_path
+    dev = scene.gaussians["means"].device
+    path = interp_se3_path(c2w_start.detach().cpu().float(), c2w_end.detach().cpu().float(), steps)
+    w2c = torch.linalg.inv(path).to(dev)
+    K = intrinsics.to(dev).float()
+    K = K.expand(steps, 3, 3) if K.dim() == 2 else K
+    frames = []
+    with torch.no_grad():
+        for i in range(0, steps, chunk):
+            img, _, _ = render_3dgs(scene, w2c[i:i + chunk], K[i:i + chunk], width, height)
+            frames.append(img)
+    return torch.cat(frames)
 
 
 def _truth_images(scene, device):

@@ -304,6 +304,52 @@ def _memo(cache_path):
     return _MEMO.setdefault(cache_path, {"fwd": {}, "corres": {}, "canon": {}})
 
 
+# ---- optional disk mirror in the reference's own file formats -----------------------------------
+# Default: everything streams from HBM.  With PERSIST_CACHE = True (and a cache_path) every memo entry is also
+# written / looked up on disk exactly where and how the reference stores it, so a cache directory produced by
+# either implementation can be consumed by the other:
+#   forward/<md5 a>/<md5 b>.pth                     = (X11 [H,W,3], C11 [H,W], X21 [H,W,3], C21 [H,W])   sparse_ga.py:552
+#   corres_conf=<desc_conf>_subsample=<S>/<a>-<b>.pth = ((conf_score, sum conf, n), (xy1, xy2, conf))    sparse_ga.py:561
+#   canon_views/<md5 img>_subsample=<S>_kw=<kw>.pth  = ((canon, canon2, cconf), focal)                   sparse_ga.py:706
+PERSIST_CACHE = False
+
+
+def _md5(name):
+    import hashlib
+    return hashlib.md5(name.encode("utf-8")).hexdigest()
+
+
+def _cache_file(cache_path, kind, a, b=None, desc_conf="desc_conf", subsample=8, kw=None):
+    import os
+    if kind == "fwd":
+        return os.path.join(cache_path, "forward", _md5(a), _md5(b) + ".pth")
+    if kind == "corres":
+        return os.path.join(cache_path, f"corres_conf={desc_conf}_{subsample=}", f"{_md5(a)}-{_md5(b)}.pth")
+    return os.path.join(cache_path, "canon_views", _md5(a) + f"_{subsample=}_{kw=}.pth")
+
+
+def _disk_get(path, device):
+    import os
+    if not (PERSIST_CACHE and path and os.path.isfile(path)):
+        return None
+    return torch.load(path, map_location=device)
+
+
+def _disk_put(path, obj):
+    import os
+    if not (PERSIST_CACHE and path):
+        return
+
+    def cpu(x):
+        if isinstance(x, torch.Tensor):
+            return x.detach().cpu()
+        if isinstance(x, (tuple, list)):
+            return type(x)(cpu(v) for v in x)
+        return x
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    torch.save(cpu(obj), path)
+
+
 def convert_dust3r_pairs_naming(imgs, pairs_in):
     """sparse_ga.py:111-115."""
     for pair in pairs_in:
@@ -339,11 +385,20 @@ def forward_mast3r(pairs, model, cache_path, desc_conf="desc_conf", device="cuda
     the in-HBM memo (the reference returns file paths)."""
     memo = _memo(cache_path)
     res_paths = {}
+    fkw = dict(desc_conf=desc_conf, subsample=subsample)
     for img1, img2 in pairs:
         a, b = img1["instance"], img2["instance"]
+        if PERSIST_CACHE and cache_path:        # adopt entries another run (or the reference) left on disk
+            for key, kind in (((a, b), "fwd"), ((b, a), "fwd"), ((a, b), "corres"), ((b, a), "corres")):
+                store = memo["fwd" if kind == "fwd" else "corres"]
+                if key not in store:
+                    got = _disk_get(_cache_file(cache_path, kind, *key, **fkw), device)
+                    if got is not None:
+                        store[key] = tuple(got) if kind == "fwd" else (tuple(got[0]), tuple(got[1]))
         if (b, a) in memo["corres"] and (a, b) not in memo["corres"]:
             score, (xy1, xy2, confs) = memo["corres"][b, a]
             memo["corres"][a, b] = (score, (xy2, xy1, confs))                        # :538-540
+            _disk_put(cache_path and _cache_file(cache_path, "corres", a, b, **fkw), memo["corres"][a, b])
         if not ((a, b) in memo["fwd"] and (b, a) in memo["fwd"] and (a, b) in memo["corres"]):
             if model is None:
                 continue
@@ -357,6 +412,10 @@ def forward_mast3r(pairs, model, cache_path, desc_conf="desc_conf", device="cuda
             corres = match.extract_correspondences(descs, qonfs, device=device, subsample=subsample)
             conf_score = (C11.mean() * C12.mean() * C21.mean() * C22.mean()).sqrt().sqrt()
             memo["corres"][a, b] = ((float(conf_score), float(corres[2].sum()), len(corres[2])), corres)
+            if PERSIST_CACHE and cache_path:
+                _disk_put(_cache_file(cache_path, "fwd", a, b), memo["fwd"][a, b])
+                _disk_put(_cache_file(cache_path, "fwd", b, a), memo["fwd"][b, a])
+                _disk_put(_cache_file(cache_path, "corres", a, b, **fkw), memo["corres"][a, b])
         res_paths[a, b] = ((a, b), (b, a)), (a, b)
     return res_paths, cache_path
 
@@ -419,6 +478,10 @@ def prepare_canonical_data(imgs, tmp_pairs, subsample, order_imgs=False, min_con
     for img in imgs:
         canonical_paths.append((cache_path, img))
         cached = memo["canon"].get(img)
+        if cached is None and PERSIST_CACHE and cache_path:
+            got = _disk_get(_cache_file(cache_path, "canon", img, subsample=subsample, kw=kw), device)
+            if got is not None:
+                cached = memo["canon"][img] = (tuple(got[0]), got[1])
         pts, cfs, pixels = [], [], {}
         for (img1, img2), ((key1, key2), key_corres) in tmp_pairs.items():
             score = None
@@ -444,6 +507,7 @@ def prepare_canonical_data(imgs, tmp_pairs, subsample, order_imgs=False, min_con
             canon, canon2, cconf = canonical_view(torch.stack(pts), torch.stack(cfs), subsample, **kw)
             focal = estimate_focal_knowing_depth(canon[None], None, "weiszfeld", min_focal=0.5, max_focal=3.5)
             memo["canon"][img] = ((canon, canon2, cconf), focal)      # stays as computed on later add_images calls,
+            _disk_put(cache_path and _cache_file(cache_path, "canon", img, subsample=subsample, kw=kw), memo["canon"][img])
         (canon, canon2, cconf), focal = memo["canon"][img]            # like the reference's file cache (quirk C-6)
         H, W = canon.shape[:2]
         pp = torch.tensor([W / 2, H / 2], device=device)

@@ -180,3 +180,41 @@ def test_scene_add_images_end_to_end(cuda_device):
     scene.init_3dgs()
     losses = scene.run_3dgs_optim(10)
     assert len(losses) == 10 and losses[-1] < losses[0]
+
+
+def test_disk_cache_in_reference_file_formats(cuda_device, tmp_path):
+    """with reconstruct.PERSIST_CACHE the pair / correspondence / canonical-view cache is mirrored on disk
+    in the reference's own layout (sparse_ga.py:530-536,552-561,643,706): same paths, same tuple structure, CPU
+    tensors.  A second run that only has the files (memo dropped, no model) reproduces the first one."""
+    import hashlib
+    from starst3r_b200 import reconstruct as rc
+    from starst3r_b200 import synth
+    W, H, n = 64, 48, 3
+    model = synth.SyntheticMast3r(n, W, H, seed=1, device=cuda_device, arc_deg=90.0)
+    imgs = rc.prepare_images_for_mast3r(model.images())
+    names = [str(i) for i in range(n)]
+    pairs = rc.convert_dust3r_pairs_naming(names, rc.make_pairs(imgs, "complete", None, True))
+    cache = str(tmp_path)
+    md5 = lambda s: hashlib.md5(s.encode()).hexdigest()     # noqa: E731
+    rc.PERSIST_CACHE = True
+    try:
+        res1, _ = rc.forward_mast3r(pairs, model, cache, device=cuda_device)
+        out1 = rc.prepare_canonical_data(names, res1, 8, cache_path=cache, mode="avg-angle", device=cuda_device)
+        f = torch.load(f"{cache}/forward/{md5('0')}/{md5('1')}.pth")
+        assert len(f) == 4 and f[0].shape == (H, W, 3) and f[1].shape == (H, W) and not f[0].is_cuda
+        score, (xy1, xy2, conf) = torch.load(f"{cache}/corres_conf=desc_conf_subsample=8/{md5('0')}-{md5('1')}.pth")
+        assert len(score) == 3 and score[2] == len(conf) and xy1.dtype == torch.int64 and xy1.shape == (len(conf), 2)
+        (canon, canon2, cconf), focal = torch.load(f"{cache}/canon_views/{md5('0')}_subsample=8_kw={{'mode': 'avg-angle'}}.pth")
+        assert canon.shape == (H, W, 3) and canon2.shape == (H, W) and cconf.shape == (H, W) and focal.numel() == 1
+        # second run: files only
+        rc._MEMO.clear()
+        res2, _ = rc.forward_mast3r(pairs, None, cache, device=cuda_device)
+        assert set(res2) == set(res1)
+        out2 = rc.prepare_canonical_data(names, res2, 8, cache_path=cache, mode="avg-angle", device=cuda_device)
+        assert torch.equal(out1[1], out2[1])                                     # pairwise scores
+        for img in names:
+            a, b = out1[2][img], out2[2][img]
+            assert torch.equal(a[2].cpu(), b[2].cpu()) and torch.equal(a[3].cpu(), b[3].cpu())   # focal, core depth
+    finally:
+        rc.PERSIST_CACHE = False
+        rc._MEMO.clear()

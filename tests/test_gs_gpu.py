@@ -327,3 +327,7 @@ def test_scene_api_run_3dgs_optim(cuda_device):
     assert scene.gaussians["sh0"].grad is None
     r, a, info = scene.render_3dgs_original(W, H)
     assert r.shape == (C, H, W, 3) and a.shape == (C, H, W, 1) and "isect_offsets" in info
+    # fly-through between two training cameras: end points reproduce the per-camera renders
+    path = st.gs.render_3dgs_path(scene, scene.c2w[0], scene.c2w[1], 5, scene.intrinsics[0], W, H, chunk=2)
+    assert path.shape == (5, H, W, 3) and torch.isfinite(path).all()
+    assert torch.allclose(path[0], r[0], atol=2e-3) and torch.allclose(path[-1], r[1], atol=2e-3)
