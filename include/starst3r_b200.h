@@ -174,7 +174,7 @@ ST3R_API int st3r_gs_project_bwd(const float* means, const float* quats, const f
                         cudaStream_t stream);
 
 /* (1-f) * L1 + f * (1 - SSIM) per view (gs.py:126-131; SSIM = torchmetrics, data_range 1).
- * render/truth [C,H,W,3]; dmaps [C,H,W,3,3] scratch; sums [C,2] (zeroed by caller) receives
+ * render/truth [C,H,W,3]; dmaps: 9*C*H*W floats of scratch (layout private to the pair of calls); sums [C,2] (zeroed by caller) receives
  * (sum of interior SSIM, sum |truth - render|).  bwd writes v_render = dLoss/d(render). */
 ST3R_API int st3r_gs_loss_fwd(const float* render, const float* truth, int C, int height, int width, float ssim_fac,
                      float* dmaps, float* sums, cudaStream_t stream);
