@@ -275,12 +275,33 @@ def run_ours(args):
     # e2e: descriptors + confidences from pinned host memory, correspondences read back
     hfe = [f.cpu().pin_memory() for f in feats]
     hq = [x.cpu().pin_memory() for x in q]
+    # two device staging sets: pair p+1 is uploaded on the copy stream while pair p is matched; every pair's inputs are
+    # copied and every pair's correspondences are read back inside the timed region
+    stage = [([torch.empty_like(f) for f in feats], [torch.empty_like(x) for x in q]) for _ in range(2)]
+    up_done = [torch.cuda.Event(), torch.cuda.Event()]
+    use_done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def upload_pair(b):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(use_done[b])
+            for dst, src in zip(stage[b][0] + stage[b][1], hfe + hq):
+                dst.copy_(src, non_blocking=True)
+            up_done[b].record(copy_stream)
+
     m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    for b in (0, 1):
+        use_done[b].record(main_stream)
     m0.record()
-    for _ in range(n_pairs):
-        xy1, xy2, conf = match.extract_correspondences([f.to(dev, non_blocking=True) for f in hfe],
-                                                       [x.to(dev, non_blocking=True) for x in hq], 8, device=dev)
+    copy_stream.wait_event(m0)
+    upload_pair(0)
+    for p_i in range(n_pairs):
+        b = p_i & 1
+        if p_i + 1 < n_pairs:
+            upload_pair(1 - b)
+        main_stream.wait_event(up_done[b])
+        xy1, xy2, conf = match.extract_correspondences(stage[b][0], stage[b][1], 8, device=dev)
+        use_done[b].record(main_stream)
         xy1.cpu(), xy2.cpu(), conf.cpu()
     m1.record()
     barrier()
