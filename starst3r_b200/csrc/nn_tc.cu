@@ -8,13 +8,17 @@
 //
 // Exactness.  The reference scores in true fp32 (sequential FMA chain).  TF32 drops 13
 // mantissa bits of each operand, so |approx - exact| <= eps = 2^-9 * |q| * max_j |db_j|.
-// The epilogue therefore keeps, per query row, every column whose approximate score is
-// within 2*eps of the running approximate maximum (a handful), and re-scores those
-// candidates with the exact fp32 FMA chain at the end.  The true arg-max (and all its
-// exact ties) is always among the candidates, so the result is bit-identical to the SIMT
-// kernel / the reference, ties -> lowest index.  Rows whose candidate list overflows
-// (degenerate inputs, e.g. constant descriptor maps) are re-done by an exact warp-per-row
-// kernel.
+// The epilogue keeps a running approximate row maximum and appends every column within
+// delta = 2 eps of it to a small per-row candidate list in shared memory (entries that fall out
+// of the band as the maximum rises are compacted away).  At the end of a CTA's DB range the
+// survivors (typically 1-3) are re-scored with the exact fp32 FMA chain; the true arg-max and all
+// its exact ties are always among them, so the result is bit-identical to the SIMT kernel / the
+// reference (ties -> lowest index).  When a list fills up - smooth descriptor fields such as real
+// MASt3R maps or the synthetic scene put ~100 columns per row inside the band - it is resolved on
+// the spot: its entries are re-scored exactly, the exact best (score, lowest index) is kept in a
+// register and raises the running bound (a column can only win if its approximate score is
+// >= best_exact - eps), and the list starts empty again.  (A first version flagged such rows for
+// an exact warp-per-row kernel: 100 ms per pair on the synthetic scene instead of 2.5 ms.)
 #include <cuda.h>
 #include "common.cuh"
 #include "nn.cuh"
@@ -28,7 +32,6 @@ constexpr int DK = 24;             // descriptor dim
 constexpr int ROWB = 128;          // smem bytes per operand row (32 floats, 24 real + 8 zero)
 constexpr int STAGES = 4;          // smem ring depth for DB tiles
 constexpr int ACC_STAGES = 2;      // TMEM accumulator stages
-constexpr int CAND_CAP = 12;       // candidates kept per row
 #ifndef NN_TC_EPI_SPLIT
 #define NN_TC_EPI_SPLIT 1
 #endif
@@ -47,8 +50,11 @@ constexpr float DELTA_COEF = 4.2e-3f;  // > 2 * 2^-9 (+ fp32 accumulation slack)
 
 constexpr int SMEM_A = 0;
 constexpr int SMEM_B = SMEM_A + BM * ROWB;
+constexpr int CAND_CAP = 12;       // candidates kept per (row, epilogue thread) between resolutions
 constexpr int SMEM_CAND = SMEM_B + STAGES * BN * ROWB;
-constexpr int SMEM_BAR = SMEM_CAND + EPI_SPLIT * BM * CAND_CAP * 8;
+constexpr int SMEM_CTX = SMEM_CAND + EPI_SPLIT * BM * CAND_CAP * 8;    // EpiCtx per (row, epilogue thread)
+constexpr int SMEM_DBP = SMEM_CTX + EPI_SPLIT * BM * 24;               // DB base pointer of this CTA's problem
+constexpr int SMEM_BAR = SMEM_DBP + 16;
 constexpr int SMEM_TOTAL = SMEM_BAR + 256;
 constexpr int SMEM_DYN = SMEM_TOTAL + 1024;  // slack for 1024-byte alignment
 
@@ -158,37 +164,76 @@ __device__ __forceinline__ float exact_score(const float* __restrict__ q, const 
   return s;
 }
 
-struct Cand { int j; float s; };
-
 // Diagnostic cycle counters (epilogue warp of CTA 0): [0] tiles, [1] cycles waiting for the accumulator,
 // [2] cycles in the arg-max epilogue proper, [3] total cycles of the tile loop.  Read by st3r_debug_nn_tc_cycles().
 __device__ unsigned long long g_nn_tc_cycles[4];
 
-constexpr int CAND_OVERFLOW = 0x100;
+struct Cand { int j; float s; };
 
-// Appends the columns flagged in `mask` (column = col0 + bit) to a row's candidate list.  The stored
-// score is an upper bound of the column's approximate score (the chunk maximum), which keeps the
-// later `score >= final_max - delta` filter conservative.  When the list is full it is first
-// compacted against the current threshold; if it is still full the row is flagged as overflowed.
-__device__ __noinline__ int push_candidates(Cand* list, int cnt, uint32_t mask, int col0, float score_ub, float thr) {
-  if (cnt & CAND_OVERFLOW) return cnt;
+// Per epilogue thread state that only the cold path touches lives in shared memory, so it costs the hot loop no
+// registers and the out-of-line cold function needs few arguments.
+struct EpiCtx {
+  const float* q;              // this row's query descriptor (global)
+  unsigned long long best;     // exact best so far, packed (score, ~index): 64-bit max == best score, lowest index
+  float delta;
+  int pad;
+};
+static_assert(sizeof(EpiCtx) == 24, "EpiCtx layout");
+
+extern __shared__ uint8_t smem_raw[];
+__device__ __forceinline__ uint8_t* smem_base() {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+}
+
+// Exact fp32 re-score of the list entries still inside the band, merged into the row's exact best.
+__device__ __forceinline__ float resolve_list(const Cand* list, int cnt, float thr, EpiCtx* ctx, const float* __restrict__ DB) {
+  unsigned long long best = ctx->best;
+  const float* q = ctx->q;
+  for (int i = 0; i < cnt; ++i) {
+    const Cand c = list[i];
+    if (c.s < thr) continue;
+    const unsigned long long k = nn_pack(exact_score(q, DB + (size_t)c.j * DK), c.j);
+    best = k > best ? k : best;
+  }
+  ctx->best = best;
+  return best ? nn_unpack_score(best) : -INFINITY;
+}
+
+// Cold path of the epilogue for one 32-column chunk (out of line, loop-based: the hot loop must stay small enough
+// for the instruction cache and keep its registers).  Appends the columns flagged in `mask` (column = col0 + bit)
+// to the row's candidate list; the stored score is an upper bound of the column's approximate score (the chunk
+// maximum), which keeps the later `score >= thr` filter conservative.  A full list is first compacted against the
+// current threshold; if it is still full of live candidates it is resolved exactly on the spot and restarted empty,
+// and the exact best raises the running bound (a later column can only win if its approximate score is
+// >= best - eps, and eps <= delta / 2).  Returns (bits of the new running maximum << 32) | new count.
+__device__ __noinline__ unsigned long long absorb_candidates(int slot, int cnt, uint32_t mask, int col0, float cmax,
+                                                             float run_max) {
+  uint8_t* smem = smem_base();
+  Cand* list = reinterpret_cast<Cand*>(smem + SMEM_CAND) + slot * CAND_CAP;
+  EpiCtx* ctx = reinterpret_cast<EpiCtx*>(smem + SMEM_CTX) + slot;
+  const float delta = ctx->delta;
   while (mask) {
-    int i = __ffs(mask) - 1;
-    mask &= mask - 1;
     if (cnt == CAND_CAP) {
+      const float thr = run_max - delta;
       int w = 0;
       for (int k = 0; k < CAND_CAP; ++k) {
         Cand c = list[k];
         if (c.s >= thr) list[w++] = c;
       }
       cnt = w;
-      if (cnt == CAND_CAP) return cnt | CAND_OVERFLOW;
+      if (cnt == CAND_CAP) {
+        const float bs = resolve_list(list, cnt, thr, ctx, *reinterpret_cast<const float* const*>(smem + SMEM_DBP));
+        cnt = 0;
+        run_max = fmaxf(run_max, bs + 0.5f * delta);
+      }
     }
+    const int i = __ffs(mask) - 1;
+    mask &= mask - 1;
     list[cnt].j = col0 + i;
-    list[cnt].s = score_ub;
+    list[cnt].s = cmax;
     ++cnt;
   }
-  return cnt;
+  return ((unsigned long long)__float_as_uint(run_max) << 32) | (unsigned long long)(uint32_t)cnt;
 }
 
 struct NnTcParams {
@@ -210,7 +255,6 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
   const int N = it.N;
   const float* __restrict__ db_norm2_max = it.db_norm_bound;
   unsigned long long* __restrict__ packed = it.packed;
-  int32_t* __restrict__ ovf_flags = it.ovf_flags;
   int tiles_per_chunk = prm.tiles_per_chunk;
   const int dynamic = prm.dynamic;
   const int M = count_ptr ? min(*count_ptr, Mmax) : Mmax;
@@ -247,11 +291,9 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
     return t < n_probe ? (int)(((long long)t * (ntiles_all - 1)) / n_probe) * BN : n_begin + (t - n_probe) * BN;
   };
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_base();
   const uint32_t sA = smem_u32(smem + SMEM_A);
   const uint32_t sB = smem_u32(smem + SMEM_B);
-  Cand* cand_all = reinterpret_cast<Cand*>(smem + SMEM_CAND);
   const uint32_t bar0 = smem_u32(smem + SMEM_BAR);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
@@ -329,8 +371,8 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
     const int gm = m0 + row;
     const bool row_ok = gm < M;
     const int part = (warp - 2) >> 2;        // which EPI_COLS-wide slice of every tile this warp scans
-    Cand* list = cand_all + (part * BM + row) * CAND_CAP;
-    int cnt = 0;  // bit 8 set => the list overflowed (row redone exactly afterwards)
+    const int slot = part * BM + row;       // candidate list / EpiCtx of this thread
+    int cnt = 0;
     const float* qrow = Qsrc;
     float delta = 0.f;
     if (row_ok) {
@@ -341,6 +383,12 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
       delta = DELTA_COEF * sqrtf(n2) * sqrtf(*db_norm2_max) + 1e-30f;
     }
     float run_max = row_ok ? -INFINITY : INFINITY;  // padded rows never trigger
+    {
+      EpiCtx* ctx = reinterpret_cast<EpiCtx*>(smem + SMEM_CTX) + slot;
+      ctx->q = qrow; ctx->best = 0ull; ctx->delta = delta;
+      if (threadIdx.x == 64) *reinterpret_cast<const float**>(smem + SMEM_DBP) = DB;   // first epilogue thread
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");                      // DB pointer visible to all
+    }
 
 #ifdef NN_TC_DEBUG_CYCLES
     const bool dbg = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0);
@@ -407,7 +455,9 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
               uint32_t mask = 0;
 #pragma unroll
               for (int i = 0; i < 32; ++i) mask |= (x[i] >= thr ? 1u : 0u) << i;
-              cnt = push_candidates(list, cnt, mask, col_base + c * 32, cmax, thr);
+              const unsigned long long r = absorb_candidates(slot, cnt, mask, col_base + c * 32, cmax, run_max);
+              cnt = (int)(uint32_t)r;
+              run_max = __uint_as_float((uint32_t)(r >> 32));
             }
           }
         }
@@ -427,20 +477,9 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
 #endif
 
     if (row_ok) {
-      if (cnt & CAND_OVERFLOW) {
-        ovf_flags[gm] = 1;
-      } else {
-        const float thr = run_max - delta;
-        float bs = -INFINITY;
-        int bj = 0x7fffffff;
-        for (int i = 0; i < cnt; ++i) {
-          Cand c = list[i];
-          if (c.s < thr) continue;
-          float s = exact_score(qrow, DB + (size_t)c.j * DK);
-          if (s > bs || (s == bs && c.j < bj)) { bs = s; bj = c.j; }
-        }
-        if (bj != 0x7fffffff) atomicMax(packed + gm, nn_pack(bs, bj));
-      }
+      EpiCtx* ctx = reinterpret_cast<EpiCtx*>(smem + SMEM_CTX) + slot;
+      resolve_list(reinterpret_cast<Cand*>(smem + SMEM_CAND) + slot * CAND_CAP, cnt, run_max - delta, ctx, DB);
+      if (ctx->best != 0ull) atomicMax(packed + gm, ctx->best);
     }
   }
 
@@ -449,38 +488,6 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
-  }
-}
-
-// Exact redo of rows whose candidate list overflowed: one warp per row.
-struct NnOvfParams { NnBatchItem it[NN_MAX_BATCH]; };
-
-__global__ void nn_tc_overflow_kernel(const NnOvfParams prm) {
-  const NnBatchItem& it = prm.it[blockIdx.y];
-  const float* __restrict__ Qsrc = it.Qsrc;
-  const int32_t* __restrict__ qidx = it.qidx;
-  const float* __restrict__ DB = it.DB;
-  const int N = it.N;
-  unsigned long long* __restrict__ packed = it.packed;
-  int32_t* __restrict__ ovf_flags = it.ovf_flags;
-  const int M = it.count_ptr ? min(*it.count_ptr, it.Mmax) : it.Mmax;
-  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (r >= M || !ovf_flags[r]) return;
-  const float* q = Qsrc + (qidx ? (size_t)qidx[r] : (size_t)r) * DK;
-  float bs = -INFINITY;
-  int bj = 0x7fffffff;
-  for (int j = lane_id(); j < N; j += 32) {
-    float s = exact_score(q, DB + (size_t)j * DK);
-    if (s > bs) { bs = s; bj = j; }
-  }
-  for (int off = 1; off < 32; off <<= 1) {
-    float so = __shfl_xor_sync(0xffffffffu, bs, off);
-    int jo = __shfl_xor_sync(0xffffffffu, bj, off);
-    if (so > bs || (so == bs && jo < bj)) { bs = so; bj = jo; }
-  }
-  if (lane_id() == 0) {
-    if (bj != 0x7fffffff) atomicMax(packed + r, nn_pack(bs, bj));
-    ovf_flags[r] = 0;   // consumed: the flag array stays all-zero between calls, so callers clear it only once
   }
 }
 
@@ -560,24 +567,22 @@ int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stre
   ST3R_CHECK_ARG(n >= 1 && n <= NN_MAX_BATCH, "nn_tc: batch size must be 1..%d", NN_MAX_BATCH);
   ST3R_CHECK_ARG(d == DK, "nn_tc: only d == 24 is supported (got %d)", d);
   NnTcParams prm;
-  NnOvfParams ovf;
   int m = 0, max_M = 0;
   bool all_counts = true;
   for (int i = 0; i < n; ++i) {
     const NnBatchItem& it = items[i];
     if (it.Mmax <= 0 || it.N <= 0) continue;
     ST3R_CHECK_ARG(((uintptr_t)it.DB % 16) == 0 && ((uintptr_t)it.Qsrc % 16) == 0, "nn_tc: operands must be 16-byte aligned");
-    ST3R_CHECK_ARG(it.ovf_flags && it.db_norm_bound && it.packed, "nn_tc: missing scratch");
+    ST3R_CHECK_ARG(it.db_norm_bound && it.packed, "nn_tc: missing scratch");
     int rc = encode_db_tmap(&prm.tmap[m], it.DB, it.N);
     if (rc) return rc;
     prm.it[m] = it;
-    ovf.it[m] = it;
     max_M = max(max_M, it.Mmax);
     all_counts = all_counts && it.count_ptr != nullptr;
     ++m;
   }
   if (m == 0) return ST3R_OK;
-  for (int i = m; i < NN_MAX_BATCH; ++i) { prm.tmap[i] = prm.tmap[0]; prm.it[i] = prm.it[0]; ovf.it[i] = ovf.it[0]; }
+  for (int i = m; i < NN_MAX_BATCH; ++i) { prm.tmap[i] = prm.tmap[0]; prm.it[i] = prm.it[0]; }
   static bool attr_set = false;
   if (!attr_set) {
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
@@ -611,9 +616,6 @@ int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stre
       ST3R_CHECK_LAUNCH();
     }
   }
-  const int wpb = 8;
-  nn_tc_overflow_kernel<<<dim3((max_M + wpb - 1) / wpb, m), wpb * 32, 0, stream>>>(ovf);
-  ST3R_CHECK_LAUNCH();
   return ST3R_OK;
 }
 
