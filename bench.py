@@ -78,10 +78,10 @@ class ClockSampler:
                 "samples": len(sm), "window": "warm-up + timed steps + e2e + match legs (GPU busy throughout)"}
 
 
-def make_workload(dev, seed):
+def make_workload(dev, seed, scale_mode="init"):
     from starst3r_b200 import gs, synth
     viewmats, Ks = synth.look_at_cameras(N_VIEWS, W, H, device=dev)
-    target = synth.random_splats(N_GAUSS, seed=seed, scale_mode="init", device=dev)
+    target = synth.random_splats(N_GAUSS, seed=seed, scale_mode=scale_mode, device=dev)
     with torch.no_grad():
         truth, _, _ = gs.rasterization(target["means"], target["quats"], target["scales"], target["opacities"],
                                        target["shN"], viewmats, Ks, W, H)
@@ -207,6 +207,27 @@ def run_ours(args):
                 "ncu_issue_active_pct": ncu.get("issue_active_pct"), "ncu_sm_throughput_pct": ncu.get("sm_throughput_pct"),
                 "kernel_ms": round(top_ms, 4), "alg_bytes": alg_bytes.get(top, 0),
                 "step_breakdown_ms": {k: round(v, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])}}
+
+    # ---- second sweep of SURVEY 8d: log-normal scales exp(N(-4, 0.5)) (6x larger splats, ~20x the blends) -----------
+    sweep = None
+    if world == 1:
+        p2, s2, t2, c2 = make_workload(dev, seed=rank, scale_mode="rand")
+        plan2 = gs.TrainPlan(N_GAUSS, N_VIEWS, W, H, dev)
+        for i in range(4):
+            gs.train_step(p2, s2, t2, c2, W, H, i + 1, plan=plan2)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(5):
+            _, fr2 = gs.train_step(p2, s2, t2, c2, W, H, 5 + i, plan=plan2, count_blends=(i == 4))
+        e1.record()
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1) / 5
+        sweep = {"workload": "same step, scales = exp(N(-4, 0.5)) instead of the 3e-3 initialisation", "ms_per_step": ms2,
+                 "gaussians_per_sec": N_GAUSS * N_VIEWS / (ms2 * 1e-3), "intersections": fr2.n_isect,
+                 "blends_per_frame": int(fr2.n_blend.item())}
+        del p2, s2, t2, c2, plan2, fr2
+        torch.cuda.empty_cache()
 
     # ---- end-to-end: truth images come from pinned host memory every step, the loss is read back -----
     # The upload of step i+1's images runs on a copy stream under step i's kernels (two device buffers); every
@@ -345,7 +366,7 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu,
             "blends_per_sec": n_blend * world / (shares.get("st3r_gs_raster_fwd", float("nan")) * 1e-3),
             "blends_per_frame": n_blend, "intersections": n_isect, "visible": n_vis, "loss": float(loss.item()),
-            "match": match_res, "reconstruct": recon}
+            "sweep_lognormal_scales": sweep, "match": match_res, "reconstruct": recon}
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -67,7 +67,7 @@ def make_cams(viewmats, Ks):
     C = viewmats.shape[0]
     V = viewmats.detach().float()
     K = Ks.detach().float()
-    pos = torch.linalg.inv(V)[:, :3, 3]
+    pos = torch.linalg.inv(V.cpu())[:, :3, 3].to(V.device)     # C tiny inverses: host (no cuSOLVER initialisation)
     cams = torch.cat([V[:, :3, :3].reshape(C, 9), V[:, :3, 3], K[:, 0, 0:1], K[:, 1, 1:2], K[:, 0, 2:3], K[:, 1, 2:3],
                       pos], dim=1)
     return cams.contiguous()

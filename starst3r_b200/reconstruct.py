@@ -653,7 +653,9 @@ class SparseGA:
                            "st3r_dense_points")
             pts3d.append(p); depths.append(d); confs.append(conf.clone())
         if clean_depth:
-            confs = clean_pointcloud(confs, self.intrinsics, torch.linalg.inv(self.cam2w), depths, pts3d)
+            # N tiny 4x4 inverses: on the host (the first cuSOLVER call on a device costs ~0.3 s of initialisation)
+            w2c = torch.linalg.inv(self.cam2w.detach().float().cpu()).to(dev)
+            confs = clean_pointcloud(confs, self.intrinsics, w2c, depths, pts3d)
         return pts3d, depths, confs
 
 
