@@ -24,12 +24,10 @@ int nn_simt_launch(const float* Qsrc, const int32_t* qidx, const int32_t* count_
                    const float* DB, int N, int d, unsigned long long* packed, cudaStream_t stream);
 
 // tcgen05 (TF32 tensor-core) candidate search + exact fp32 re-score.  Same contract.
-// `db_norm_bound` = device pointer to max_j ||DB_j||_2^2 (float), see nn_db_norm_launch;
-// `ovf_flags` = int32 scratch [Mmax], ALL ZERO on entry and left all zero on exit (rows whose candidate list
-// overflowed are flagged by the main kernel and cleared by the exact redo kernel).
+// `db_norm_bound` = device pointer to max_j ||DB_j||_2^2 (float), see nn_db_norm_launch.
 int nn_tc_launch(const float* Qsrc, const int32_t* qidx, const int32_t* count_ptr, int Mmax,
                  const float* DB, int N, int d, const float* db_norm_bound,
-                 unsigned long long* packed, int32_t* ovf_flags, cudaStream_t stream);
+                 unsigned long long* packed, cudaStream_t stream);
 int nn_db_norm_launch(const float* DB, int N, int d, float* out_bound, cudaStream_t stream);
 bool nn_tc_supported(int d);
 
@@ -39,6 +37,6 @@ constexpr int NN_MAX_BATCH = 4;
 struct NnBatchItem {
   const float* Qsrc; const int32_t* qidx; const int32_t* count_ptr; int Mmax;
   const float* DB; int N; const float* db_norm_bound;
-  unsigned long long* packed; int32_t* ovf_flags;
+  unsigned long long* packed;
 };
 int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stream);

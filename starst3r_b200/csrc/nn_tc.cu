@@ -620,9 +620,8 @@ int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stre
 }
 
 int nn_tc_launch(const float* Qsrc, const int32_t* qidx, const int32_t* count_ptr, int Mmax, const float* DB,
-                 int N, int d, const float* db_norm_bound, unsigned long long* packed, int32_t* ovf_flags,
-                 cudaStream_t stream) {
+                 int N, int d, const float* db_norm_bound, unsigned long long* packed, cudaStream_t stream) {
   if (Mmax <= 0 || N <= 0) return ST3R_OK;
-  NnBatchItem it{Qsrc, qidx, count_ptr, Mmax, DB, N, db_norm_bound, packed, ovf_flags};
+  NnBatchItem it{Qsrc, qidx, count_ptr, Mmax, DB, N, db_norm_bound, packed};
   return nn_tc_launch_batch(&it, 1, d, stream);
 }

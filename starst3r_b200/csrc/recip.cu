@@ -25,7 +25,6 @@ struct RecipState {
   int32_t* counts;     // counts[h] = active length before half-iteration h
   int32_t* qidx[2];    // query row indices of the current / next half-iteration (ping-pong)
   unsigned long long* packed[2];
-  int32_t* ovf;        // tcgen05 candidate-overflow flags
 };
 
 constexpr int RB = NN_MAX_BATCH;
@@ -57,7 +56,6 @@ __global__ void recip_init(RecipBatch b, int ncounts) {
   st.active[0][i] = i;
   st.qidx[0][i] = s;          // first half-iteration queries P1[seed]
   st.packed[0][i] = 0ull;
-  st.ovf[i] = 0;
 }
 
 // Scatter NN results, drop converged slots, build the next active list and - because the next half-iteration
@@ -226,7 +224,6 @@ size_t carve(RecipWs* w, void* ws, size_t ws_bytes, int nseed_max, int key_cap, 
     }
     t.st[p].notyet = a.take<uint8_t>(nseed_max);
     t.st[p].counts = a.take<int32_t>(2 * max_iter + 2);
-    t.st[p].ovf = a.take<int32_t>(nseed_max);
   }
   t.keys = a.take<uint64_t>(key_cap);
   t.keys_alt = a.take<uint64_t>(key_cap);
@@ -285,7 +282,7 @@ int run_recip_batch(const RecipWs& w, const RecipProblem* pr, int n, int d, int 
         const RecipState& st = w.st[p];
         items[p] = NnBatchItem{half == 0 ? q.P1 : q.P2, st.qidx[h & 1], st.counts + h, q.nseed,
                                half == 0 ? q.P2 : q.P1, half == 0 ? q.HW2 : q.HW1, half == 0 ? q.norm2 : q.norm1,
-                               st.packed[h & 1], st.ovf};
+                               st.packed[h & 1]};
       }
       int rc = ST3R_OK;
       if (use_tc) {
@@ -344,16 +341,14 @@ int st3r_nn_argmax(const float* Q, int M, const float* DB, int N, int d, int32_t
   WsAlloc a(ws, ws_bytes);
   unsigned long long* packed = a.take<unsigned long long>(M);
   float* bound = a.take<float>(4);
-  int32_t* ovf = a.take<int32_t>(M);
   ST3R_CHECK_CUDA(cudaMemsetAsync(packed, 0, (size_t)M * sizeof(unsigned long long), stream));
   int rc;
   bool use_tc = (impl == ST3R_NN_TCGEN05) || (impl == ST3R_NN_AUTO && nn_tc_supported(d) && M >= 64);
   if (impl == ST3R_NN_TCGEN05) ST3R_CHECK_ARG(nn_tc_supported(d), "st3r_nn_argmax: tcgen05 path needs d=24");
   if (use_tc && N > 0) {
-    ST3R_CHECK_CUDA(cudaMemsetAsync(ovf, 0, (size_t)M * sizeof(int32_t), stream));
     rc = nn_db_norm_launch(DB, N, d, bound, stream);
     if (rc) return rc;
-    rc = nn_tc_launch(Q, nullptr, nullptr, M, DB, N, d, bound, packed, ovf, stream);
+    rc = nn_tc_launch(Q, nullptr, nullptr, M, DB, N, d, bound, packed, stream);
   } else {
     rc = nn_simt_launch(Q, nullptr, nullptr, M, DB, N, d, packed, stream);
   }
