@@ -26,24 +26,27 @@
 
 namespace {
 
-constexpr int BM = 128;            // query rows per CTA (UMMA M)
+// One CTA per SM scores MH = 2 query tiles of 128 rows against ONE stream of DB tiles: every DB tile that TMA brings
+// in from L2 feeds two UMMA groups.  With one 128-row tile per CTA (two CTAs per SM, each with its own stream) the
+// TMA stream alone - MMAs, TMEM reads and arithmetic compiled out - ran at 640 cycles per tile per CTA: 12 KB per
+// 320 cycles per SM is 38 B/clk/SM, the L2 -> SM bandwidth of the chip (~42 B/clk/SM), i.e. the kernel was L2-bound at
+// 64 FLOP per L2 byte.  Sharing the stream halves the L2 traffic per FLOP.
+constexpr int UM = 128;            // rows of one UMMA (M)
+constexpr int MH = 2;              // query tiles per CTA
+constexpr int BM = UM * MH;        // query rows per CTA
 constexpr int BN = 128;            // DB rows per MMA tile (UMMA N)
 constexpr int DK = 24;             // descriptor dim
 constexpr int ROWB = 128;          // smem bytes per operand row (32 floats, 24 real + 8 zero)
-constexpr int STAGES = 4;          // smem ring depth for DB tiles
-constexpr int ACC_STAGES = 2;      // TMEM accumulator stages
-#ifndef NN_TC_EPI_SPLIT
-#define NN_TC_EPI_SPLIT 1
-#endif
-// Epilogue warps per TMEM lane quarter: each scans BN / EPI_SPLIT accumulator columns of its 32 rows.  (Measured:
-// 2 per quarter is no faster than 1; neither is one CTA per SM with 4 accumulator stages, nor the query tile in
-// tensor memory: the TMA + MMA pipeline alone, epilogue compiled out, already takes 2/3 of the kernel time.)
-constexpr int EPI_SPLIT = NN_TC_EPI_SPLIT;
-constexpr int EPI_COLS = BN / EPI_SPLIT;        // columns per epilogue thread and tile
+constexpr int STAGES = 6;          // smem ring depth for DB tiles
+constexpr int ACC_STAGES = 2;      // TMEM accumulator stages per query tile
+// Warps 0..7: epilogue (warp % 4 = TMEM lane quarter, warp / 4 = query tile); warp 8: TMA producer; warp 9: MMA issuer.
+constexpr int EPI_COLS = BN;
 constexpr int EPI_CHUNKS = EPI_COLS / 32;
-constexpr int EPI_THREADS = 128 * EPI_SPLIT;
-constexpr int NUM_THREADS = 64 + EPI_THREADS;   // warp0: TMA, warp1: MMA + TMEM alloc, then the epilogue warps
-constexpr int TMEM_COLS = ACC_STAGES * BN;  // 256
+constexpr int EPI_THREADS = BM;                 // one thread per query row
+constexpr int EPI_WARPS = EPI_THREADS / 32;
+constexpr int WARP_TMA = EPI_WARPS, WARP_MMA = EPI_WARPS + 1;
+constexpr int NUM_THREADS = EPI_THREADS + 64;
+constexpr int TMEM_COLS = MH * ACC_STAGES * BN;  // 512: the whole tensor memory of the SM
 constexpr int MAX_TILES_PER_CHUNK = 512;
 constexpr int MAX_PROBE = 8;         // max-only probe tiles per CTA (see the kernel)
 constexpr float DELTA_COEF = 4.2e-3f;  // > 2 * 2^-9 (+ fp32 accumulation slack)
@@ -52,8 +55,8 @@ constexpr int SMEM_A = 0;
 constexpr int SMEM_B = SMEM_A + BM * ROWB;
 constexpr int CAND_CAP = 12;       // candidates kept per (row, epilogue thread) between resolutions
 constexpr int SMEM_CAND = SMEM_B + STAGES * BN * ROWB;
-constexpr int SMEM_CTX = SMEM_CAND + EPI_SPLIT * BM * CAND_CAP * 8;    // EpiCtx per (row, epilogue thread)
-constexpr int SMEM_DBP = SMEM_CTX + EPI_SPLIT * BM * 24;               // DB base pointer of this CTA's problem
+constexpr int SMEM_CTX = SMEM_CAND + BM * CAND_CAP * 8;    // EpiCtx per query row
+constexpr int SMEM_DBP = SMEM_CTX + BM * 24;               // DB base pointer of this CTA's problem
 constexpr int SMEM_BAR = SMEM_DBP + 16;
 constexpr int SMEM_TOTAL = SMEM_BAR + 256;
 constexpr int SMEM_DYN = SMEM_TOTAL + 1024;  // slack for 1024-byte alignment
@@ -151,7 +154,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128.
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
 
 __device__ __forceinline__ float exact_score(const float* __restrict__ q, const float* __restrict__ b) {
   float s = 0.f;
@@ -243,7 +246,7 @@ struct NnTcParams {
   int dynamic;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
   const NnBatchItem& it = prm.it[blockIdx.z];
   const CUtensorMap* tmap_db = &prm.tmap[blockIdx.z];
@@ -305,10 +308,10 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_THREADS); }
+    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
                  "n"(TMEM_COLS)
                  : "memory");
@@ -331,7 +334,7 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 0) {
+  if (warp == WARP_TMA) {
     // ===== TMA producer =====
     if (lane == 0) {
       for (int t = 0; t < nseq; ++t) {
@@ -342,7 +345,7 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
         tma_load_2d(sB + s * BN * ROWB, tmap_db, 0, seq_col(t), full_bar(s));
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == WARP_MMA) {
     // ===== MMA issuer =====
     if (lane == 0) {
       for (int t = 0; t < nseq; ++t) {
@@ -353,12 +356,15 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
         mbar_wait(tempty_bar(a), aph ^ 1u);
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
 #pragma unroll
-        for (int kk = 0; kk < DK / 8; ++kk) {
-          uint64_t da = make_smem_desc(sA + kk * 32);
-          uint64_t db = make_smem_desc(sB + s * BN * ROWB + kk * 32);
-          tc_mma_tf32(d_tmem, da, db, IDESC, kk > 0 ? 1u : 0u);
+        for (int h = 0; h < MH; ++h) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)((h * ACC_STAGES + a) * BN);
+#pragma unroll
+          for (int kk = 0; kk < DK / 8; ++kk) {
+            uint64_t da = make_smem_desc(sA + h * UM * ROWB + kk * 32);
+            uint64_t db = make_smem_desc(sB + s * BN * ROWB + kk * 32);
+            tc_mma_tf32(d_tmem, da, db, IDESC, kk > 0 ? 1u : 0u);
+          }
         }
         tc_commit(empty_bar(s));   // smem stage free once these MMAs retire
         tc_commit(tfull_bar(a));   // accumulator ready for the epilogue
@@ -367,11 +373,11 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
   } else {
     // ===== epilogue: fused arg-max over TMEM accumulators =====
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;     // accumulator row == TMEM lane
+    const int half = warp >> 2;              // which of the CTA's query tiles
+    const int row = half * UM + quarter * 32 + lane;   // query row inside the CTA; its accumulator is TMEM lane row % 128
     const int gm = m0 + row;
     const bool row_ok = gm < M;
-    const int part = (warp - 2) >> 2;        // which EPI_COLS-wide slice of every tile this warp scans
-    const int slot = part * BM + row;       // candidate list / EpiCtx of this thread
+    const int slot = row;                    // candidate list / EpiCtx of this thread
     int cnt = 0;
     const float* qrow = Qsrc;
     float delta = 0.f;
@@ -386,12 +392,12 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
     {
       EpiCtx* ctx = reinterpret_cast<EpiCtx*>(smem + SMEM_CTX) + slot;
       ctx->q = qrow; ctx->best = 0ull; ctx->delta = delta;
-      if (threadIdx.x == 64) *reinterpret_cast<const float**>(smem + SMEM_DBP) = DB;   // first epilogue thread
+      if (threadIdx.x == 0) *reinterpret_cast<const float**>(smem + SMEM_DBP) = DB;
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");                      // DB pointer visible to all
     }
 
 #ifdef NN_TC_DEBUG_CYCLES
-    const bool dbg = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0);
+    const bool dbg = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 0 && lane == 0);
     unsigned long long c_wait = 0, c_epi = 0;
     const long long c_start = clock64();
 #endif
@@ -406,7 +412,7 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
 #ifdef NN_TC_DEBUG_CYCLES
       const long long c1 = clock64();
 #endif
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * BN + part * EPI_COLS);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((half * ACC_STAGES + a) * BN);
       // Pull this thread's accumulator columns into registers with back-to-back tcgen05.ld (their latencies
       // overlap), then hand the TMEM stage back to the MMA warp BEFORE the arg-max arithmetic so tile t+2 can
       // start immediately.
@@ -420,7 +426,8 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
       tc_wait_ld();
 #endif
       tc_fence_before();
-      mbar_arrive(tempty_bar(a));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(a));      // one arrival per warp
 #ifdef NN_TC_EXP_NOALU  // timing experiment only (wrong results): no arg-max arithmetic
       if (v[t & (EPI_COLS - 1)] == 123.456f) run_max = v[5];
       continue;
@@ -435,7 +442,7 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
       if (t < n_probe) {
         run_max = fmaxf(run_max, tmax);          // probe tiles are always full tiles
       } else {
-        const int col_base = n_begin + (t - n_probe) * BN + part * EPI_COLS;
+        const int col_base = n_begin + (t - n_probe) * BN;
         const bool ragged = col_base + EPI_COLS > n_end;
         if (__builtin_expect(ragged || tmax >= run_max - delta, 0)) {
           // Cold path (a few times per row, or the single ragged tile of the DB).
@@ -485,7 +492,7 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
@@ -588,7 +595,7 @@ int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stre
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
     attr_set = true;
   }
-  const int slots = 2 * st3r_num_sms();
+  const int slots = st3r_num_sms();      // one CTA per SM (it owns the whole tensor memory)
   const int mtiles = (max_M + BM - 1) / BM;
   if (all_counts && mtiles <= slots) {
     // device-side decomposition (see the kernel): one wave of `slots` CTAs per problem
@@ -598,7 +605,7 @@ int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stre
     ST3R_CHECK_LAUNCH();
   } else {
     // host-side decomposition, one problem per launch.  Chunk the DB so that the grid is (close to) a whole number
-    // of waves of 2 CTAs per SM: long chunks keep the per-row candidate restarts rare, and a partial last wave
+    // of waves of one CTA per SM: long chunks keep the per-row candidate restarts rare, and a partial last wave
     // would idle most of the chip.
     for (int i = 0; i < m; ++i) {
       NnTcParams one = prm;
