@@ -96,8 +96,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+#ifdef NN_TC_EXP_NOFENCE   // timing experiment only
+__device__ __forceinline__ void tc_fence_before() {}
+__device__ __forceinline__ void tc_fence_after() {}
+#else
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+#endif
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -356,6 +361,11 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
         mbar_wait(tempty_bar(a), aph ^ 1u);
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
+#ifdef NN_TC_EXP_NOMMA   // timing experiment only (wrong results): TMA stream + barrier hand-offs, no tensor work
+        mbar_arrive(empty_bar(s));
+        mbar_arrive(tfull_bar(a));
+        continue;
+#endif
 #pragma unroll
         for (int h = 0; h < MH; ++h) {
           const uint32_t d_tmem = tmem_base + (uint32_t)((h * ACC_STAGES + a) * BN);
