@@ -25,6 +25,8 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 N_GAUSS, N_VIEWS, W, H = 200_000, 8, 512, 512
+WORKLOAD = ("8-view 512x512 synthetic scene, 200k Gaussians, 3DGS train step (render fwd + L1/SSIM loss + bwd + Adam), "
+            "BASELINE.json configs[1]")
 MATCH_HW = 512
 
 
@@ -357,9 +359,7 @@ def run_ours(args):
     line = {"metric": "gaussians_per_sec_rasterized", "value": value, "unit": "Gaussians/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "8-view 512x512 synthetic scene, 200k Gaussians, 3DGS train step "
-                                   "(render fwd + L1/SSIM loss + bwd + Adam), BASELINE.json configs[1]",
-                       "views_per_gpu": N_VIEWS, "gaussians": N_GAUSS, "image": [H, W],
+            "config": {"workload": WORKLOAD, "views_per_gpu": N_VIEWS, "gaussians": N_GAUSS, "image": [H, W],
                        "parallelism": f"views sharded dp{world}, {exchange}" if world > 1 else "single GPU",
                        "l2": "256 MiB flush between timed steps"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
@@ -475,8 +475,8 @@ def run_reference(args):
             "unit": "Gaussians/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": len(vals), "warmup": 0,
             "ms_per_step": best["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "8-view 512x512 synthetic scene, 200k Gaussians, 3DGS train step, BASELINE.json "
-                                   "configs[1]; each step = bounded sample of 1 view"},
+            "config": {"workload": WORKLOAD, "views_per_gpu": N_VIEWS, "gaussians": N_GAUSS, "image": [H, W],
+                       "parallelism": "host cores (PyTorch CPU)", "sample": "each step = bounded sample of 1 of the 8 views"},
             "cpu_baseline": best,
             "e2e": {"value": best["value"], "unit": "Gaussians/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(line)
