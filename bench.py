@@ -349,7 +349,12 @@ def run_ours(args):
                               "alg_flops_per_pair": flops, "query_rows_per_pair": rows}}
 
     # ---- MATCH + ALIGN end to end (rank 0, N = 1 only): reconstruct_scene on BASELINE.json configs[1] ------------
-    recon = reconstruct_leg(dev) if world == 1 and rank == 0 and not args.no_align else None
+    recon = None
+    if world == 1 and rank == 0 and not args.no_align:
+        try:
+            recon = reconstruct_leg(dev)
+        except Exception as e:      # noqa: BLE001 - an auxiliary leg must not take the headline line down with it
+            recon = {"error": repr(e)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -10,14 +10,13 @@ python -m starst3r_b200.build > /dev/null
 B=starst3r_b200/build
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr"
 OBJS=$(ls $B/*.o | grep -v nn_tc.o | grep -v _var_)
-for v in dbg nold nold_nomma nold_nomma_nofence nold_nofence; do
+for v in dbg nold bn128 bn32; do
   D=""
   N="-DNN_TC_DEBUG_CYCLES -DNN_TC_EXP_NOLD -DNN_TC_EXP_NOALU"
   [ $v = dbg ] && D="-DNN_TC_DEBUG_CYCLES"
   [ $v = nold ] && D="$N"
-  [ $v = nold_nomma ] && D="$N -DNN_TC_EXP_NOMMA"
-  [ $v = nold_nomma_nofence ] && D="$N -DNN_TC_EXP_NOMMA -DNN_TC_EXP_NOFENCE"
-  [ $v = nold_nofence ] && D="$N -DNN_TC_EXP_NOFENCE"
+  [ $v = bn128 ] && D="-DNN_TC_BN=128"
+  [ $v = bn32 ] && D="-DNN_TC_BN=32"
   nvcc $FLAGS $D -c starst3r_b200/csrc/nn_tc.cu -o $B/nn_tc_var_$v.o
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o starst3r_b200/libstarst3r_b200_$v.so $OBJS $B/nn_tc_var_$v.o -cudart static -lpthread -ldl -lrt
 done

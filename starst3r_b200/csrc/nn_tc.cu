@@ -34,11 +34,17 @@ namespace {
 constexpr int UM = 128;            // rows of one UMMA (M)
 constexpr int MH = 2;              // query tiles per CTA
 constexpr int BM = UM * MH;        // query rows per CTA
-constexpr int BN = 128;            // DB rows per MMA tile (UMMA N)
+#ifndef NN_TC_BN
+#define NN_TC_BN 128
+#endif
+constexpr int BN = NN_TC_BN;       // DB rows per MMA tile (UMMA N)
 constexpr int DK = 24;             // descriptor dim
 constexpr int ROWB = 128;          // smem bytes per operand row (32 floats, 24 real + 8 zero)
-constexpr int STAGES = 6;          // smem ring depth for DB tiles
-constexpr int ACC_STAGES = 2;      // TMEM accumulator stages per query tile
+constexpr int STAGES = 768 / BN;    // smem ring depth for DB tiles (96 KB)
+// All 512 TMEM columns hold accumulators: the kernel's throughput is (columns in flight) / (round trip MMA issue ->
+// commit -> epilogue read -> release), and narrower tiles shorten the round trip (its UMMA and TMEM-read parts scale
+// with the tile width, its barrier hops do not).
+constexpr int ACC_STAGES = 256 / BN;  // TMEM accumulator stages per query tile
 // Warps 0..7: epilogue (warp % 4 = TMEM lane quarter, warp / 4 = query tile); warp 8: TMA producer; warp 9: MMA issuer.
 constexpr int EPI_COLS = BN;
 constexpr int EPI_CHUNKS = EPI_COLS / 32;
@@ -47,8 +53,8 @@ constexpr int EPI_WARPS = EPI_THREADS / 32;
 constexpr int WARP_TMA = EPI_WARPS, WARP_MMA = EPI_WARPS + 1;
 constexpr int NUM_THREADS = EPI_THREADS + 64;
 constexpr int TMEM_COLS = MH * ACC_STAGES * BN;  // 512: the whole tensor memory of the SM
-constexpr int MAX_TILES_PER_CHUNK = 512;
-constexpr int MAX_PROBE = 8;         // max-only probe tiles per CTA (see the kernel)
+constexpr int MAX_TILES_PER_CHUNK = 65536 / BN;
+constexpr int MAX_PROBE = 1024 / BN;  // max-only probe tiles per CTA (see the kernel)
 constexpr float DELTA_COEF = 4.2e-3f;  // > 2 * 2^-9 (+ fp32 accumulation slack)
 
 constexpr int SMEM_A = 0;
@@ -58,7 +64,7 @@ constexpr int SMEM_CAND = SMEM_B + STAGES * BN * ROWB;
 constexpr int SMEM_CTX = SMEM_CAND + BM * CAND_CAP * 8;    // EpiCtx per query row
 constexpr int SMEM_DBP = SMEM_CTX + BM * 24;               // DB base pointer of this CTA's problem
 constexpr int SMEM_BAR = SMEM_DBP + 16;
-constexpr int SMEM_TOTAL = SMEM_BAR + 256;
+constexpr int SMEM_TOTAL = SMEM_BAR + 512;   // up to 48 mbarriers + the TMEM base address
 constexpr int SMEM_DYN = SMEM_TOTAL + 1024;  // slack for 1024-byte alignment
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -356,8 +362,8 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
       for (int t = 0; t < nseq; ++t) {
         int s = t % STAGES;
         uint32_t ph = (uint32_t)(t / STAGES) & 1u;
-        int a = t & 1;
-        uint32_t aph = (uint32_t)(t >> 1) & 1u;
+        int a = t % ACC_STAGES;
+        uint32_t aph = (uint32_t)(t / ACC_STAGES) & 1u;
         mbar_wait(tempty_bar(a), aph ^ 1u);
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
@@ -412,8 +418,8 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
     const long long c_start = clock64();
 #endif
     for (int t = 0; t < nseq; ++t) {
-      int a = t & 1;
-      uint32_t aph = (uint32_t)(t >> 1) & 1u;
+      int a = t % ACC_STAGES;
+      uint32_t aph = (uint32_t)(t / ACC_STAGES) & 1u;
 #ifdef NN_TC_DEBUG_CYCLES
       const long long c0 = clock64();
 #endif
