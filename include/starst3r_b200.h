@@ -54,6 +54,14 @@ ST3R_API uint64_t st3r_launch_count(void);
  * waiting for an accumulator, cycles in the arg-max epilogue, cycles of the whole tile loop}; reset != 0 clears. */
 ST3R_API int st3r_debug_nn_tc_cycles(unsigned long long* h_out4, int reset);
 
+/* The tcgen05 matcher has two variants of its rare path (exact re-scoring of near-tie columns): per-thread (best when
+ * 1-3 columns per query row tie within the TF32 error band: random-like descriptors) and warp-cooperative (best for
+ * smooth descriptor fields, where ~100 do).  Results are identical.  st3r_nn_tc_stats copies {query rows scanned, exact
+ * list resolutions} accumulated by all launches so far to h_out2 (HOST; synchronises), optionally resetting them;
+ * st3r_nn_tc_set_cooperative selects the variant for subsequent launches of this process. */
+ST3R_API int st3r_nn_tc_stats(unsigned long long* h_out2, int reset);
+ST3R_API int st3r_nn_tc_set_cooperative(int on);
+
 /* ------------------------------------------------------------------ MATCH */
 
 /* Row arg-max of Q·DBᵀ (dot-product nearest neighbour), ties -> lowest index.

@@ -190,7 +190,7 @@ struct EpiCtx {
   const float* q;              // this row's query descriptor (global)
   unsigned long long best;     // exact best so far, packed (score, ~index): 64-bit max == best score, lowest index
   float delta;
-  int pad;
+  int resolves;                // exact list resolutions of this row in this CTA (statistics)
 };
 static_assert(sizeof(EpiCtx) == 24, "EpiCtx layout");
 
@@ -237,6 +237,7 @@ __device__ __noinline__ unsigned long long absorb_candidates(int slot, int cnt, 
       cnt = w;
       if (cnt == CAND_CAP) {
         const float bs = resolve_list(list, cnt, thr, ctx, *reinterpret_cast<const float* const*>(smem + SMEM_DBP));
+        ++ctx->resolves;
         cnt = 0;
         run_max = fmaxf(run_max, bs + 0.5f * delta);
       }
@@ -250,6 +251,76 @@ __device__ __noinline__ unsigned long long absorb_candidates(int slot, int cnt, 
   return ((unsigned long long)__float_as_uint(run_max) << 32) | (unsigned long long)(uint32_t)cnt;
 }
 
+// ---- cooperative variant of the cold path (kernel template parameter kCoop) -----------------------------------
+// Smooth descriptor fields (real MASt3R maps, the synthetic scene) keep ~100 columns per row inside the band, so
+// lists fill up ~8 times per row; resolving a list in the thread that owns it means twelve dependent L2 round trips
+// while the other 31 lanes of its warp wait.  Here the whole warp enters the cold path together, lanes append without
+// resolving, and full lists are resolved by the warp: the 12 entries of one row are re-scored by 12 lanes in parallel.
+// It costs the random-descriptor case ~14 % (warp-wide votes on every cold tile), so the host picks the variant from
+// the resolution statistics of earlier calls (st3r_nn_tc_stats / st3r_nn_tc_set_cooperative).
+__device__ __noinline__ unsigned long long absorb_no_resolve(int slot, int cnt, uint32_t mask, int col0, float cmax, float thr) {
+  Cand* list = reinterpret_cast<Cand*>(smem_base() + SMEM_CAND) + slot * CAND_CAP;
+  while (mask) {
+    if (cnt == CAND_CAP) {
+      int w = 0;
+      for (int k = 0; k < CAND_CAP; ++k) {
+        Cand c = list[k];
+        if (c.s >= thr) list[w++] = c;
+      }
+      cnt = w;
+      if (cnt == CAND_CAP) break;           // full of live candidates: the warp resolves it
+    }
+    const int i = __ffs(mask) - 1;
+    mask &= mask - 1;
+    list[cnt].j = col0 + i;
+    list[cnt].s = cmax;
+    ++cnt;
+  }
+  return ((unsigned long long)mask << 32) | (unsigned long long)(uint32_t)cnt;
+}
+
+// Called by ALL lanes of an epilogue warp; `need` marks the lanes whose list is full of live candidates.  Returns the
+// (possibly raised) running maximum of the calling lane; the resolved lists restart empty (caller resets its count).
+__device__ __noinline__ float resolve_full_lists(int slot, bool need, float run_max) {
+  uint8_t* smem = smem_base();
+  const Cand* lists = reinterpret_cast<const Cand*>(smem + SMEM_CAND);
+  EpiCtx* ctxs = reinterpret_cast<EpiCtx*>(smem + SMEM_CTX);
+  const float* DB = *reinterpret_cast<const float* const*>(smem + SMEM_DBP);
+  const float delta = ctxs[slot].delta;
+  const int lane = lane_id();
+  uint32_t victims = __ballot_sync(0xffffffffu, need);
+  __syncwarp();                                // list writes are visible to the helping lanes
+  while (victims) {
+    const int v = __ffs(victims) - 1;
+    victims &= victims - 1;
+    const int vslot = __shfl_sync(0xffffffffu, slot, v);
+    const float vthr = __shfl_sync(0xffffffffu, run_max - delta, v);
+    unsigned long long k = 0ull;
+    if (lane < CAND_CAP) {
+      const Cand c = lists[vslot * CAND_CAP + lane];
+      if (c.s >= vthr) k = nn_pack(exact_score(ctxs[vslot].q, DB + (size_t)c.j * DK), c.j);
+    }
+#pragma unroll
+    for (int off = 8; off; off >>= 1) {         // entries live in lanes 0..11: a 16-lane tree covers them
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, off);
+      k = o > k ? o : k;
+    }
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (lane == v) {
+      unsigned long long best = ctxs[slot].best;
+      best = k > best ? k : best;
+      ctxs[slot].best = best;
+      ++ctxs[slot].resolves;
+      if (best) run_max = fmaxf(run_max, nn_unpack_score(best) + 0.5f * delta);
+    }
+  }
+  __syncwarp();
+  return run_max;
+}
+
+// Statistics for the host's choice of variant: [0] query rows scanned, [1] exact list resolutions.
+__device__ unsigned long long g_nn_tc_stats[2];
+
 struct NnTcParams {
   CUtensorMap tmap[NN_MAX_BATCH];
   NnBatchItem it[NN_MAX_BATCH];
@@ -257,6 +328,7 @@ struct NnTcParams {
   int dynamic;
 };
 
+template <bool kCoop>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
   const NnBatchItem& it = prm.it[blockIdx.z];
@@ -407,7 +479,7 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
     float run_max = row_ok ? -INFINITY : INFINITY;  // padded rows never trigger
     {
       EpiCtx* ctx = reinterpret_cast<EpiCtx*>(smem + SMEM_CTX) + slot;
-      ctx->q = qrow; ctx->best = 0ull; ctx->delta = delta;
+      ctx->q = qrow; ctx->best = 0ull; ctx->delta = delta; ctx->resolves = 0;
       if (threadIdx.x == 0) *reinterpret_cast<const float**>(smem + SMEM_DBP) = DB;
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");                      // DB pointer visible to all
     }
@@ -460,7 +532,40 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
       } else {
         const int col_base = n_begin + (t - n_probe) * BN;
         const bool ragged = col_base + EPI_COLS > n_end;
-        if (__builtin_expect(ragged || tmax >= run_max - delta, 0)) {
+        if (kCoop) {
+          if (__builtin_expect(__any_sync(0xffffffffu, ragged || tmax >= run_max - delta), 0)) {
+            // Cold path, taken by the whole warp together (see resolve_full_lists).
+#pragma unroll
+            for (int c = 0; c < EPI_CHUNKS; ++c) {
+              float* x = v + c * 32;
+              float cmax = cm[c];
+              if (ragged) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (col_base + c * 32 + i >= n_end) x[i] = -INFINITY;
+                cmax = chunk_max(x);
+              }
+              uint32_t rem = 0;                    // flagged columns still to be listed
+              if (cmax >= run_max - delta) {
+                run_max = fmaxf(run_max, cmax);
+                const float thr = run_max - delta;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) rem |= (x[i] >= thr ? 1u : 0u) << i;
+                const unsigned long long r = absorb_no_resolve(slot, cnt, rem, col_base + c * 32, cmax, thr);
+                cnt = (int)(uint32_t)r;
+                rem = (uint32_t)(r >> 32);
+              }
+              while (__any_sync(0xffffffffu, rem != 0)) {      // some lane's list is full of live candidates
+                run_max = resolve_full_lists(slot, rem != 0, run_max);
+                if (rem) {
+                  const unsigned long long r = absorb_no_resolve(slot, 0, rem, col_base + c * 32, cmax, run_max - delta);
+                  cnt = (int)(uint32_t)r;
+                  rem = (uint32_t)(r >> 32);
+                }
+              }
+            }
+          }
+        } else if (__builtin_expect(ragged || tmax >= run_max - delta, 0)) {
           // Cold path (a few times per row, or the single ragged tile of the DB).
 #pragma unroll
           for (int c = 0; c < EPI_CHUNKS; ++c) {
@@ -504,6 +609,18 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
       resolve_list(reinterpret_cast<Cand*>(smem + SMEM_CAND) + slot * CAND_CAP, cnt, run_max - delta, ctx, DB);
       if (ctx->best != 0ull) atomicMax(packed + gm, ctx->best);
     }
+    {   // statistics: one pair of atomics per warp
+      EpiCtx* ctx = reinterpret_cast<EpiCtx*>(smem + SMEM_CTX) + slot;
+      int nres = row_ok ? ctx->resolves : 0, nrow = (row_ok && n_begin == 0) ? 1 : 0;   // each query row counted once
+      for (int off = 16; off; off >>= 1) {
+        nres += __shfl_xor_sync(0xffffffffu, nres, off);
+        nrow += __shfl_xor_sync(0xffffffffu, nrow, off);
+      }
+      if (lane == 0) {
+        if (nrow) atomicAdd(&g_nn_tc_stats[0], (unsigned long long)nrow);
+        if (nres) atomicAdd(&g_nn_tc_stats[1], (unsigned long long)nres);
+      }
+    }
   }
 
   tc_fence_before();
@@ -545,6 +662,22 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace
 
 bool nn_tc_supported(int d) { return d == DK; }
+
+static int g_nn_tc_coop = 0;
+
+extern "C" int st3r_nn_tc_set_cooperative(int on) {
+  g_nn_tc_coop = on ? 1 : 0;
+  return ST3R_OK;
+}
+
+extern "C" int st3r_nn_tc_stats(unsigned long long* h_out2, int reset) {
+  if (h_out2) ST3R_CHECK_CUDA(cudaMemcpyFromSymbol(h_out2, g_nn_tc_stats, sizeof(g_nn_tc_stats)));
+  if (reset) {
+    unsigned long long z[2] = {0, 0};
+    ST3R_CHECK_CUDA(cudaMemcpyToSymbol(g_nn_tc_stats, z, sizeof(z)));
+  }
+  return ST3R_OK;
+}
 
 extern "C" int st3r_debug_nn_tc_cycles(unsigned long long* h_out4, int reset) {
   if (h_out4) ST3R_CHECK_CUDA(cudaMemcpyFromSymbol(h_out4, g_nn_tc_cycles, sizeof(g_nn_tc_cycles)));
@@ -608,7 +741,8 @@ int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stre
   for (int i = m; i < NN_MAX_BATCH; ++i) { prm.tmap[i] = prm.tmap[0]; prm.it[i] = prm.it[0]; }
   static bool attr_set = false;
   if (!attr_set) {
-    ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
+    ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
+    ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
     attr_set = true;
   }
   const int slots = st3r_num_sms();      // one CTA per SM (it owns the whole tensor memory)
@@ -617,7 +751,8 @@ int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stre
     // device-side decomposition (see the kernel): one wave of `slots` CTAs per problem
     prm.tiles_per_chunk = 0;
     prm.dynamic = 1;
-    nn_tc_kernel<<<dim3(slots, 1, m), NUM_THREADS, SMEM_DYN, stream>>>(prm);
+    if (g_nn_tc_coop) nn_tc_kernel<true><<<dim3(slots, 1, m), NUM_THREADS, SMEM_DYN, stream>>>(prm);
+    else nn_tc_kernel<false><<<dim3(slots, 1, m), NUM_THREADS, SMEM_DYN, stream>>>(prm);
     ST3R_CHECK_LAUNCH();
   } else {
     // host-side decomposition, one problem per launch.  Chunk the DB so that the grid is (close to) a whole number
@@ -635,7 +770,8 @@ int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stre
       nchunks = (ntiles_total + tiles_per_chunk - 1) / tiles_per_chunk;
       one.tiles_per_chunk = tiles_per_chunk;
       one.dynamic = 0;
-      nn_tc_kernel<<<dim3(nchunks, mt, 1), NUM_THREADS, SMEM_DYN, stream>>>(one);
+      if (g_nn_tc_coop) nn_tc_kernel<true><<<dim3(nchunks, mt, 1), NUM_THREADS, SMEM_DYN, stream>>>(one);
+      else nn_tc_kernel<false><<<dim3(nchunks, mt, 1), NUM_THREADS, SMEM_DYN, stream>>>(one);
       ST3R_CHECK_LAUNCH();
     }
   }

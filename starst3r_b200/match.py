@@ -286,7 +286,7 @@ class _ExtractPlan:
         self.conf = torch.empty(cap, dtype=torch.float32, device=dev)
         self.n_out = torch.zeros(1, dtype=torch.int32, device=dev)
         self.ws = _ws(lib.st3r_extract_corres_ws_bytes(H1, W1, H2, W2, subsample, max_iter), dev)
-        self.graph = None
+        self.graphs = {}            # matcher variant (cooperative rare path or not) -> captured graph
         self.lib, self.dev = lib, dev
 
     def _launch(self):
@@ -304,19 +304,48 @@ class _ExtractPlan:
             for dst, src in zip(self.feats + self.qonfs, list(feats) + list(qonfs)):
                 if dst.data_ptr() != src.data_ptr():
                     dst.copy_(src, non_blocking=True)
-            if self.graph is None:
+            coop = _apply_variant(self.lib)
+            if coop not in self.graphs:
                 self._launch()                      # eager warm-up (sets kernel attributes, loads modules)
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._launch()
-                self.graph = g
-            self.graph.replay()
+                self.graphs[coop] = g
+            self.graphs[coop].replay()
         return self.xy1, self.xy2, self.conf, self.n_out
 
 
 _PLANS = {}
 USE_CUDA_GRAPHS = True
+
+# Variant of the tcgen05 matcher's rare path (st3r_nn_tc_set_cooperative): "auto" follows the statistics the kernels
+# collect (exact list resolutions per scanned row): random-like descriptors resolve ~never and run the per-thread
+# variant; smooth descriptor fields (real MASt3R maps) resolve ~once per row and DB range and run the warp-cooperative
+# one (2x faster there, ~14 % slower on random data).  True / False pin it.  Results are identical either way.
+NN_COOPERATIVE = "auto"
+_variant = {"on": False}
+
+
+def _apply_variant(lib):
+    on = _variant["on"] if NN_COOPERATIVE == "auto" else bool(NN_COOPERATIVE)
+    lib.st3r_nn_tc_set_cooperative(int(on))
+    return on
+
+
+def _adapt_variant(lib):
+    """Called where the host has just synchronised anyway (the correspondence count was read back)."""
+    if NN_COOPERATIVE != "auto":
+        return
+    st = (ctypes.c_ulonglong * 2)()
+    _lib.check(lib.st3r_nn_tc_stats(st, 1), "st3r_nn_tc_stats")
+    rows, resolves = int(st[0]), int(st[1])
+    if rows >= 256:
+        ratio = resolves / rows          # exact list resolutions per query row
+        if ratio > 0.5:
+            _variant["on"] = True
+        elif ratio < 0.1:
+            _variant["on"] = False
 
 
 def extract_correspondences_device(feats, qonfs, subsample=8, impl="auto", max_iter=10):
@@ -340,6 +369,7 @@ def extract_correspondences_device(feats, qonfs, subsample=8, impl="auto", max_i
         for dst, src in zip(plan.feats + plan.qonfs, list(feats) + list(qonfs)):
             dst.copy_(src, non_blocking=True)
         with torch.cuda.device(dev):
+            _apply_variant(lib)
             plan._launch()
         return plan.xy1, plan.xy2, plan.conf, plan.n_out
     return plan.run([x.float() for x in feats], [x.float() for x in qonfs])
@@ -355,4 +385,5 @@ def extract_correspondences(feats, qonfs, subsample=8, device=None, ptmap_key="p
     qonfs = [_f32(q, device) for q in qonfs]
     xy1, xy2, conf, n_out = extract_correspondences_device(feats, qonfs, subsample, impl)
     n = int(n_out.item())
+    _adapt_variant(_lib.load())
     return xy1[:n].clone(), xy2[:n].clone(), conf[:n].clone()      # the plan's buffers are reused by the next pair

@@ -170,3 +170,50 @@ def test_full_size_properties(cuda_device, impl):
     s1, s2 = match.fast_reciprocal_NNs(A, A, 8, ret_xy=False, device=cuda_device, dist="dot", impl=impl)
     y, x = np.mgrid[4:512:8, 4:512:8].reshape(2, -1)
     assert np.array_equal(s1, np.sort(x + 512 * y)) and np.array_equal(s1, s2)
+
+
+def test_cooperative_variant_identical_and_auto_selected(cuda_device):
+    """The warp-cooperative rare path (st3r_nn_tc_set_cooperative) returns bit-identical correspondences on random
+    AND on smooth descriptor fields (many near-tie columns per row), and "auto" follows the kernels' statistics
+    (exact list resolutions per query row: > 0.5 switches it on, < 0.1 off)."""
+    import ctypes
+    from starst3r_b200 import _lib, match, synth
+    lib = _lib.load()
+    H = W = 256
+    g = torch.Generator().manual_seed(0)
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    X = torch.stack([xx / W, yy / H, (xx + yy) / (W + H)], -1)
+    freq = torch.randn(24, 3, generator=g) * 2.5
+    smooth = lambda salt: torch.nn.functional.normalize(                                       # noqa: E731
+        torch.cos(X @ freq.T + salt) + 0.003 * torch.randn(H, W, 24, generator=g), dim=-1).to(cuda_device)
+    A, B = synth.descriptor_pair(H, W, seed=3, device=cuda_device)
+    cases = {"random": [A, B, B, A], "smooth": [smooth(0.0), smooth(0.01), smooth(0.02), smooth(0.03)]}
+    q = [torch.ones(H, W, device=cuda_device) for _ in range(4)]
+    out, ratio = {}, {}
+
+    def stats():
+        st = (ctypes.c_ulonglong * 2)()
+        _lib.check(lib.st3r_nn_tc_stats(st, 1), "stats")
+        return int(st[1]) / max(int(st[0]), 1)
+    try:
+        for mode in (False, True):
+            match.NN_COOPERATIVE = mode
+            for name, feats in cases.items():
+                stats()
+                out[name, mode] = [t.cpu() for t in match.extract_correspondences(feats, q, 8, device=cuda_device)]
+                ratio[name, mode] = stats()
+        for name in cases:
+            for a, b in zip(out[name, False], out[name, True]):
+                assert torch.equal(a, b), name
+            assert out[name, False][0].shape[0] > 50
+        assert ratio["random", False] < 0.1 < 0.5 < ratio["smooth", False], ratio      # the regimes the switch separates
+        match.NN_COOPERATIVE = "auto"
+        match._variant["on"] = False
+        stats()
+        match.extract_correspondences(cases["smooth"], q, 8, device=cuda_device)
+        assert match._variant["on"] is True
+        match.extract_correspondences(cases["random"], q, 8, device=cuda_device)
+        assert match._variant["on"] is False
+    finally:
+        match.NN_COOPERATIVE = "auto"
+        match._variant["on"] = False
