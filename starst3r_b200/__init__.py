@@ -3,6 +3,7 @@
 __version__ = "0.1.0"
 
 from . import gs, match  # noqa: F401
+from .image import load_image, load_images, prepare_images_for_mast3r, process_image  # noqa: F401
 from .scene import Scene  # noqa: F401
 from .utils import interp_se3, interp_se3_path  # noqa: F401
 

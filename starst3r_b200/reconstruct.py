@@ -699,9 +699,7 @@ def run_sparse_ga(imgs, pairs_in, cache_path, model, subsample=8, desc_conf="des
     return SparseGA(imgs, pairs_in, res_fine or res_coarse, anchors, canonical_paths, subsample), optim_params
 
 
-def prepare_images_for_mast3r(imgs):
-    """starster/image.py:112-139."""
-    return [dict(img=im[None], true_shape=np.int32([im.shape[-2:]]), idx=i, instance=str(i)) for i, im in enumerate(imgs)]
+from .image import prepare_images_for_mast3r  # noqa: E402  (starster/image.py:112-139)
 
 
 def reconstruct_scene(model, imgs, filelist, device, optim_params=None, tmpdir=None):
