@@ -205,16 +205,22 @@ def _forward(means, quats, scales, opacities, shN, cams, width, height, count_bl
                                            _lib.ptr(shN), sh_coeffs, _lib.ptr(cams), N, C, fr.W, fr.H, TILE, _f(EPS2D),
                                            _f(NEAR), _f(FAR), _f(RADIUS_CLIP), _lib.ptr(fr.radii), _lib.ptr(fr.geomA),
                                            _lib.ptr(fr.geomB), _lib.ptr(fr.rgb), _lib.ptr(fr.tiles), st), "st3r_gs_project")
-        ws = plan.scan_ws if plan is not None else _ws(lib.st3r_scan_ws_bytes(C * N), dev)
-        with _Prof("st3r_exclusive_scan_i32"):
-            _lib.check(lib.st3r_exclusive_scan_i32(_lib.ptr(fr.tiles), _lib.ptr(fr.cum), C * N, _lib.ptr(fr.n_isect_dev),
-                                                   _lib.ptr(ws), ws.numel(), st), "st3r_exclusive_scan_i32")
+        # The per-entry scan (torch.cumsum of tiles_per_gauss in gsplat) gives the emission offsets of the generic chain
+        # and the intersection total.  The fused binning does not need the offsets and reports the total itself, so a
+        # sized plan skips the scan altogether.
+        late_count = plan is not None and plan.cap > 0 and BINNING == "fused"
+        if not late_count:
+            ws = plan.scan_ws if plan is not None else _ws(lib.st3r_scan_ws_bytes(C * N), dev)
+            with _Prof("st3r_exclusive_scan_i32"):
+                _lib.check(lib.st3r_exclusive_scan_i32(_lib.ptr(fr.tiles), _lib.ptr(fr.cum), C * N, _lib.ptr(fr.n_isect_dev),
+                                                       _lib.ptr(ws), ws.numel(), st), "st3r_exclusive_scan_i32")
         if plan is not None:
             # capacity-sized intersection buffers, count clamped on the device, checked one frame later
-            plan.after_scan()
+            if not late_count:
+                plan.after_scan()
             n_cap, n_dev = plan.cap, plan.n_clamped
             fr.keys, fr.vals, keys_alt, vals_alt, ws = plan.keys, plan.vals, plan.keys_alt, plan.vals_alt, plan.sort_ws
-            bin_ws, n_total = plan.bin_ws, plan.n_total
+            bin_ws, n_total = plan.bin_ws, (plan.n_raw if late_count else plan.n_total)
             fr.n_isect_dev = n_dev
             fr.offsets, fr.render, fr.alphas, fr.last_ids = plan.offsets, plan.render, plan.alphas, plan.last_ids
             fr.n_blend = plan.n_blend.zero_() if count_blends else None
@@ -242,6 +248,8 @@ def _forward(means, quats, scales, opacities, shN, cams, width, height, count_bl
                 _lib.check(lib.st3r_gs_bin_tiles(_lib.ptr(fr.radii), _lib.ptr(fr.geomA), N, C, fr.W, fr.H, TILE,
                                                  _lib.ptr(fr.offsets), _lib.ptr(n_total), _lib.ptr(fr.keys), _lib.ptr(fr.vals),
                                                  n_cap, _lib.ptr(bin_ws), bin_ws.numel(), st), "st3r_gs_bin_tiles")
+            if late_count:
+                plan.after_scan()           # the total just written by the binning: async copy + device-side clamp
         else:
             with _Prof("st3r_gs_isect"):
                 _lib.check(lib.st3r_gs_isect(_lib.ptr(fr.radii), _lib.ptr(fr.geomA), _lib.ptr(fr.cum), N, C, fr.W, fr.H, TILE,
