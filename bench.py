@@ -128,7 +128,9 @@ def run_ours(args):
         try:
             from starst3r_b200 import dist as sd
             plan.peer = sd.PeerGradExchange(N_GAUSS, dev)
-            exchange = "fused P2P gradient sum + Adam (st3r_adam_step_peers, NVLink peer loads)"
+            exchange = ("P2P reduce-scatter + all-gather of the gradient sum over NVLink peer memory (st3r_grad_reduce_scatter) "
+                        "+ Adam" if plan.peer.scatter else
+                        "fused P2P gradient sum + Adam (st3r_adam_step_peers, NVLink peer loads)")
         except Exception as e:      # noqa: BLE001
             print(f"bench: symmetric memory unavailable ({e!r}); using NCCL all-reduce", file=sys.stderr)
             hook = lambda fr: allreduce_grads(fr, world)

@@ -214,6 +214,13 @@ ST3R_API int st3r_adam_step_peers(int n_seg, float* const* h_params, const long 
                          const int* h_ld_grad, int world, const float* const* h_peer_grad_bases, double lr,
                          double beta1, double beta2, double eps, int step, cudaStream_t stream);
 
+/* The same exchange as reduce-scatter + all-gather for larger nodes: this rank sums its 1/world slice of every rank's
+ * gradient buffer (rank order: bit-identical to st3r_adam_step_peers) and stores it into every rank's `reduced` buffer
+ * (both symmetric, n_floats a multiple of 4, 16-byte aligned); after a cross-device barrier st3r_adam_step runs on the
+ * local reduced buffer.  Remote traffic per GPU: 2 (G-1)/G L instead of (G-1) L. */
+ST3R_API int st3r_grad_reduce_scatter(int world, int rank, const float* const* h_peer_grad_bases,
+                             float* const* h_peer_reduced_bases, int64_t n_floats, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ MCMC strategy
  * gsplat.MCMCStrategy as driven by starster/gs.py:43-45 (construction), :146-147 (step_pre_backward, a no-op for
  * MCMC) and :163-164 (step_post_backward(..., lr=1e-3)); gsplat 1.4 strategy/mcmc.py + strategy/ops.py semantics

@@ -66,7 +66,52 @@ adam_peer_kernel(AdamSegs segs, PeerGrads peers, PeerOffsets goff, float lr_over
     sg.v[ip] = v;
   }
 }
+// Reduce-scatter + all-gather form of the same exchange for larger node sizes: rank r sums elements [r L/G, (r+1) L/G)
+// of every peer's gradient buffer (rank order, so the sums are bit-identical to adam_peer_kernel's) and stores the
+// result into EVERY peer's `reduced` buffer.  Remote traffic per GPU: (G-1)/G L loads + (G-1)/G L stores instead of
+// (G-1) L loads; the Adam kernel then runs on local memory.
+__global__ void __launch_bounds__(256)
+grad_reduce_scatter_kernel(PeerGrads grads, PeerGrads reduced_rw, long long begin4, long long end4) {
+  for (long long i = begin4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < end4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < MAX_PEERS; ++k)
+      if (k < grads.world) {
+        const float4 v = __ldcv(reinterpret_cast<const float4*>(grads.base[k]) + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+#pragma unroll
+    for (int k = 0; k < MAX_PEERS; ++k)
+      if (k < grads.world) reinterpret_cast<float4*>(const_cast<float*>(reduced_rw.base[k]))[i] = acc;
+  }
+}
 }  // namespace
+
+extern "C" int st3r_grad_reduce_scatter(int world, int rank, const float* const* peer_grad_bases,
+                                        float* const* peer_reduced_bases, int64_t n_floats, cudaStream_t stream) {
+  ST3R_CHECK_ARG(world >= 1 && world <= MAX_PEERS && rank >= 0 && rank < world, "st3r_grad_reduce_scatter: bad world / rank");
+  ST3R_CHECK_ARG(n_floats >= 0 && n_floats % 4 == 0, "st3r_grad_reduce_scatter: length must be a multiple of 4 floats");
+  if (n_floats == 0) return ST3R_OK;
+  ST3R_CHECK_ARG(peer_grad_bases && peer_reduced_bases, "st3r_grad_reduce_scatter: null");
+  PeerGrads g, r;
+  g.world = r.world = world;
+  for (int k = 0; k < MAX_PEERS; ++k) {
+    g.base[k] = peer_grad_bases[k < world ? k : 0];
+    r.base[k] = peer_reduced_bases[k < world ? k : 0];
+    ST3R_CHECK_ARG(g.base[k] && r.base[k] && ((uintptr_t)g.base[k] % 16) == 0 && ((uintptr_t)r.base[k] % 16) == 0,
+                   "st3r_grad_reduce_scatter: peer buffers must be non-null and 16-byte aligned");
+  }
+  const long long n4 = n_floats / 4, chunk = (n4 + world - 1) / world;
+  const long long begin4 = chunk * rank, end4 = begin4 + chunk < n4 ? begin4 + chunk : n4;
+  if (begin4 >= end4) return ST3R_OK;
+  long long blocks = (end4 - begin4 + 255) / 256;
+  const long long cap = (long long)st3r_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  grad_reduce_scatter_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, r, begin4, end4);
+  ST3R_CHECK_LAUNCH();
+  return ST3R_OK;
+}
 
 extern "C" int st3r_adam_step_peers(int n_seg, float* const* params, const long long* grad_offsets, float* const* exp_avg,
                                     float* const* exp_avg_sq, const int* rows, const int* cols, const int* ld_param,

@@ -86,6 +86,10 @@ class PeerGradExchange:
     Two gradient buffers alternate between iterations, so ONE barrier per step orders both "all gradients of step k
     are written" and "nobody still reads the buffer step k+1 will overwrite"."""
     FLOATS = 23            # means 3 | quats 4 | scales 3 | opacity 1 | SH (4 coefficients x 3)
+    # From this many ranks on the exchange runs as reduce-scatter + all-gather (st3r_grad_reduce_scatter: every rank sums
+    # 1/G of the elements and stores them to all peers, 2 (G-1)/G L remote bytes) instead of every rank loading all
+    # peers' gradients inside the Adam kernel ((G-1) L).  Same sums, bit for bit.
+    SCATTER_FROM = 4
 
     def __init__(self, n_gauss, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
@@ -105,7 +109,27 @@ class PeerGradExchange:
             self.sets.append(dict(means=b[0:3 * N].view(N, 3), quats=b[3 * N:7 * N].view(N, 4),
                                   scales=b[7 * N:10 * N].view(N, 3), opacities=b[10 * N:11 * N],
                                   sh=b[11 * N:23 * N].view(N, 4, 3)))
+        self.scatter = self.world >= self.SCATTER_FROM
+        self.red = symm_mem.empty(self.stride, dtype=torch.float32, device=device)       # reduced gradients (all-gathered)
+        self.red.zero_()
+        self.red_hdl = symm_mem.rendezvous(self.red, self.group)
+        r = self.red
+        self.reduced = dict(means=r[0:3 * N].view(N, 3), quats=r[3 * N:7 * N].view(N, 4), scales=r[7 * N:10 * N].view(N, 3),
+                            opacities=r[10 * N:11 * N], sh=r[11 * N:23 * N].view(N, 4, 3))
         self.hdl.barrier(channel=0)
+
+    def reduce_scatter(self):
+        """Sum this rank's slice over all ranks and store it to every rank's `reduced` buffer (call between two
+        barriers: gradients complete before, reduced complete after)."""
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        w = self.world
+        g = (ctypes.c_void_p * w)(*self.peer_bases())
+        r = (ctypes.c_void_p * w)(*[int(p) for p in self.red_hdl.buffer_ptrs])
+        with torch.cuda.device(self.buf.device):
+            _lib.check(lib.st3r_grad_reduce_scatter(w, self.rank, g, r, ctypes.c_int64(self.stride), _lib.stream_ptr()),
+                       "st3r_grad_reduce_scatter")
 
     def grads(self):
         """Gradient tensors the backward pass of the CURRENT step must write into."""

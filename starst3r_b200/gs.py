@@ -729,8 +729,17 @@ def train_step(params, states, truth, cams, width, height, step, lr=1e-3, betas=
     if peer is not None:
         # sharded views: one cross-device barrier, then the gradient sum over the ranks happens inside the Adam kernel
         peer.barrier()
-        adam_step_peers(segs, [peer.offsets[k] for k in ("means", "scales", "quats", "opacities", "sh")], peer.peer_bases(),
-                        lr, betas, eps, step)
+        if peer.scatter:           # larger nodes: reduce-scatter + all-gather over peer memory, then a local Adam
+            peer.reduce_scatter()
+            peer.barrier()
+            rd = peer.reduced
+            segs = [(means, rd["means"], *states["means"], N, 3, 3, 3), (scales, rd["scales"], *states["scales"], N, 3, 3, 3),
+                    (quats, rd["quats"], *states["quats"], N, 4, 4, 4), (opac, rd["opacities"], *states["opacities"], N, 1, 1, 1),
+                    (shN, rd["sh"], *states["shN"], N, 12, shN.shape[1] * 3, 12)]
+            adam_step(segs, lr, betas, eps, step)
+        else:
+            adam_step_peers(segs, [peer.offsets[k] for k in ("means", "scales", "quats", "opacities", "sh")],
+                            peer.peer_bases(), lr, betas, eps, step)
         peer.advance()
     else:
         adam_step(segs, lr, betas, eps, step)

@@ -52,8 +52,16 @@ def _worker(rank, world, port, out_dir):
     plan_b.peer = sd.PeerGradExchange(N, dev)
     for i in range(steps):
         gs.train_step(pb, sb, tr, cams, W, H, i + 1, plan=plan_b)
+    # B': the reduce-scatter + all-gather form of the same exchange (default from 4 ranks on; forced here)
+    pd, sd_ = fresh()
+    plan_d = gs.TrainPlan(N, len(mine), W, H, dev)
+    plan_d.peer = sd.PeerGradExchange(N, dev)
+    plan_d.peer.scatter = True
+    for i in range(steps):
+        gs.train_step(pd, sd_, tr, cams, W, H, i + 1, plan=plan_d)
     torch.cuda.synchronize()
-    res = {"a": {k: v.cpu() for k, v in pa.items()}, "b": {k: v.cpu() for k, v in pb.items()}}
+    res = {"a": {k: v.cpu() for k, v in pa.items()}, "b": {k: v.cpu() for k, v in pb.items()},
+           "d": {k: v.cpu() for k, v in pd.items()}}
     if rank == 0:   # single-GPU training over ALL views: the oracle of the sharded path
         pc, sc = fresh()
         for i in range(steps):
@@ -73,6 +81,10 @@ def test_peer_exchange_matches_allreduce_and_single_gpu(tmp_path):
     r = [torch.load(os.path.join(tmp_path, f"rank{k}.pt")) for k in range(world)]
     for k in r[0]["a"]:
         assert torch.equal(r[0]["b"][k], r[1]["b"][k]), f"replicas diverged: {k}"
+        assert torch.equal(r[0]["d"][k], r[1]["d"][k]), f"replicas diverged (reduce-scatter form): {k}"
+        # (the two forms sum in the same order, but two training runs are not bit-reproducible: the blend backward
+        # accumulates with fp32 atomics)
+        assert torch.allclose(r[0]["d"][k], r[0]["b"][k], rtol=1e-5, atol=1e-6), k
         assert torch.allclose(r[0]["a"][k], r[0]["b"][k], rtol=1e-5, atol=1e-6), k
         # Adam turns a gradient into a step of ~lr whatever its size: compare to the single-GPU run at 1e-4 absolute
         # (5 steps x lr 1e-3, gradients equal up to fp32 summation order)
