@@ -268,8 +268,8 @@ def recip_query_rows(pts1, pts2, subsample=8, max_iter=10, impl="auto"):
 
 
 class _ExtractPlan:
-    """Persistent buffers + a captured CUDA graph of one st3r_extract_corres launch chain (~400 small launches:
-    4 searches x 20 half-iterations x {NN, overflow redo, update} + sort + unique).  The chain is launch-latency
+    """Persistent buffers + a captured CUDA graph of one st3r_extract_corres launch chain (~60 small launches: the four
+    searches advance in lock-step, 20 half-iterations x {batched NN, update}, + sort + unique).  The chain is launch-latency
     bound (measured: ~50 % of the pair time is gaps between tiny tail kernels), and its shape only depends on the
     map sizes, so it is captured once per (H1, W1, H2, W2, d, subsample, impl) and replayed; inputs are copied into
     the plan's staging buffers (8 device-to-device copies, ~100 MB at 512x512, ~35 us)."""
