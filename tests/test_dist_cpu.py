@@ -82,3 +82,51 @@ def test_single_process_passthrough():
     assert sd.shard_indices(5) == [0, 1, 2, 3, 4]
     g = {k: torch.ones(2) for k in sd.GRAD_KEYS}
     assert sd.allreduce_gradients(g) is g
+
+
+def _shard_worker(rank, world, port, q):
+    """Sharded-view training on the CPU oracle: the sum over ranks of the per-shard gradients (each rank renders only
+    its views; the regularisers scale with the number of views it holds) equals the gradient of the full problem,
+    which is what the GPU exchange (dist.PeerGradExchange / allreduce_gradients) relies on."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import gs_oracle as go
+        from starst3r_b200 import synth
+        torch.set_num_threads(1)
+        W, H, C, N = 32, 24, 4, 60
+        sp = synth.random_splats(N, seed=2, scale_mode="rand")
+        sp["scales"] = sp["scales"] * 10
+        viewmats, Ks = synth.look_at_cameras(C, W, H)
+        truth = torch.rand(C, H, W, 3, generator=torch.Generator().manual_seed(0))
+        mine = sd.shard_indices(C)
+
+        def grads_of(idx):
+            p = {k: v.clone() for k, v in sp.items()}
+            st = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in p.items()}
+            _, g, _, _ = go.train_step(p, st, truth[idx], viewmats[idx], Ks[idx], W, H, 1)
+            return {"means": g["means"], "quats": g["quats"], "scales": g["scales"], "opacities": g["opacities"],
+                    "sh": g["shN"][:, :4].contiguous()}
+        local = grads_of(mine)
+        sd.allreduce_gradients(local)
+        if rank == 0:
+            full = grads_of(list(range(C)))
+            for k in full:
+                scale = float(full[k].abs().max()) + 1e-12
+                assert float((full[k] - local[k]).abs().max()) <= 1e-4 * scale, k
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_views_gradient_sum_equals_full_gradient():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=300) for _ in procs]
+    [p.join(timeout=60) for p in procs]
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
