@@ -291,6 +291,12 @@ typedef struct {
 ST3R_API size_t st3r_align_ws_bytes(int n_img);
 ST3R_API int st3r_align_cam_floats(void);          /* floats per camera record in cam_out: R(9) t(3) f cx cy A B bf pad(2) */
 ST3R_API int st3r_align_img_const_bytes(void);
+/* Implementation variants for subsequent ALIGN calls of this process (bit mask, 0 = default).  Bit 0: the
+ * per-correspondence loss kernels of st3r_align_optimize keep the gradients of the current image pair in registers
+ * along a contiguous entry range and spread the CTA sums over replicated tables (default: every row of 32 entries
+ * is reduced across the warp).  Bit 1: st3r_focal_weiszfeld runs one 8-CTA thread-block cluster per image (default:
+ * one CTA).  Same arithmetic per element; only the floating-point summation order differs. */
+ST3R_API int st3r_align_set_variant(int variant);
 /* Runs `niter` iterations (mode 0: loss_3d, mode 1: loss_2d; both + dust3r_w * loss_dust3r) on the raw parameters
  * pp [N,2] (normalised principal points), log_focal [N], quat [N,4] (XYZW), trans [N,3], log_size [N]; Adam moments
  * adam_m / adam_v are [N,11] in that parameter order (zero them to start a phase).  train_mask bits: 1 pp, 2

@@ -21,6 +21,11 @@ namespace {
 constexpr int CAM_THREADS = 256;
 constexpr int LOSS_THREADS = 256;
 constexpr int NG = ALIGN_CAM_GRADS;
+// Variant 1 of the loss kernels ("segmented", st3r_align_set_variant): replicas of the per-image gradient table in
+// HBM (CTA b adds into replica b % ALIGN_REPL) and the ranges one warp walks.
+constexpr int ALIGN_REPL = 8;
+constexpr int SEG_MIN_PER_WARP = 128;   // entries per warp (4 rows of 32) before the grid stops growing
+constexpr int SEG_MAX_CTAS = 592;       // 4 per SM on a 148-SM part
 static_assert(sizeof(AlignImgConst) == sizeof(St3rAlignImgConst), "public / internal image record mismatch");
 
 struct Params { float* pp; float* log_focal; float* quat; float* trans; float* log_size; };
@@ -28,7 +33,7 @@ struct AdamState { float* m; float* v; };   // laid out like the flat parameter 
 
 struct Work {
   AlignCam* cam; AlignCamTmp* tmp; AlignCamGrad* cgrad;
-  float* gcam;        // [N * 17]
+  float* gcam;        // [ALIGN_REPL][N * 17] (variant 0 uses the first replica only)
   float* sums;        // [4]: main loss numerator, dust3r numerator, spare, stop flag
   float* gscal;       // [2]: g (global scaling), number of images attaining the minimum size, the minimum size
 };
@@ -251,6 +256,154 @@ align_lossd_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, float
   flush_table(table, N, w.gcam, loss, w.sums + 1);
 }
 
+
+// ---- variant 1: segmented accumulation -------------------------------------------------------------------------
+// The kernels above reduce 2 x 17 gradient values across the warp for EVERY row of 32 entries (170 shuffles + 34
+// shared-memory atomics) and every CTA of a ~1100-CTA grid then adds its table to the same N x 17 words of HBM
+// (profiles/r01u_launches_reconstruct.csv: 92 / 109 us per launch for ~0.6 M entries, where the entry lists are a
+// ~30 MB stream).  Entries of one image pair are contiguous (flatten_problem emits them slice by slice), so here a
+// warp walks a contiguous range and keeps the two images' gradients in REGISTERS while the pair does not change -
+// the vjp helpers accumulate straight into them - and reduces across lanes only when the pair changes or its range
+// ends.  The grid is ~4x smaller and CTA b adds its table into replica b % ALIGN_REPL, which align_cam_bwd folds.
+template <int KIND> struct SegEntry { Anchor a1, a2; int i1, i2; };
+
+template <int KIND>
+__device__ __forceinline__ void seg_load(const St3rAlignProblem& pb, const AlignImgConst* ic, int m, SegEntry<KIND>& e) {
+  if (KIND == 0) {
+    e.a1 = load_anchor(pb, ic, pb.e3_a1[m]); e.a2 = load_anchor(pb, ic, pb.e3_a2[m]);
+    e.i1 = e.a1.img; e.i2 = e.a2.img;
+  } else if (KIND == 1) {
+    e.i1 = pb.e2_img1[m];
+    e.a2 = load_anchor(pb, ic, pb.e2_a2[m]);
+    e.i2 = e.a2.img;
+  } else {
+    e.a1 = load_anchor(pb, ic, pb.ed_a1[m]);
+    e.i1 = e.a1.img;
+    e.i2 = pb.ed_img2[m];
+  }
+}
+
+// Loss of entry m; ADDS its gradients w.r.t. the two camera records into g1 / g2.  Same arithmetic as the bodies of
+// align_loss3d / align_loss2d / align_lossd above.
+template <int KIND>
+__device__ __forceinline__ float seg_eval(const St3rAlignProblem& pb, const Work& w, int m, const SegEntry<KIND>& e,
+                                          float gamma, float offset, float off_pow, float scale, float* g1, float* g2) {
+  const AlignCam c1 = w.cam[e.i1], c2 = w.cam[e.i2];
+  float dl;
+  if (KIND == 0) {
+    float P1[3], P2[3], pc1[3], pc2[3], z1, z2, D1, D2, o1, o2;
+    al_anchor_point(c1, e.a1.u, e.a1.v, e.a1.core, e.a1.off, P1, pc1, &z1, &D1, &o1);
+    al_anchor_point(c2, e.a2.u, e.a2.v, e.a2.core, e.a2.off, P2, pc2, &z2, &D2, &o2);
+    const float d[3] = {P1[0] - P2[0], P1[1] - P2[1], P1[2] - P2[2]};
+    const float dist = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    const float l = al_gamma_loss(dist, gamma, offset, off_pow, &dl);
+    const float cw = pb.e3_conf[m] * scale;
+    const float k = dist > 0.f ? cw * dl / dist : 0.f;
+    const float GP1[3] = {k * d[0], k * d[1], k * d[2]}, GP2[3] = {-k * d[0], -k * d[1], -k * d[2]};
+    al_anchor_point_vjp(c1, e.a1.u, e.a1.v, e.a1.core, e.a1.off, pc1, z1, D1, o1, GP1, g1);
+    al_anchor_point_vjp(c2, e.a2.u, e.a2.v, e.a2.core, e.a2.off, pc2, z2, D2, o2, GP2, g2);
+    return cw * l;
+  } else if (KIND == 1) {
+    float P2[3], pc2[3], z2, D2, o2;
+    al_anchor_point(c2, e.a2.u, e.a2.v, e.a2.core, e.a2.off, P2, pc2, &z2, &D2, &o2);
+    float uv[2];
+    AlignReproj q;
+    al_reproj(c1, P2, uv, q);
+    const float d[2] = {pb.e2_pix[2 * m] - uv[0], pb.e2_pix[2 * m + 1] - uv[1]};
+    const float dist = sqrtf(d[0] * d[0] + d[1] * d[1]);
+    const float l = al_gamma_loss(dist, gamma, offset, off_pow, &dl);
+    const float cw = pb.e2_conf[m] * scale;
+    const float k = dist > 0.f ? cw * dl / dist : 0.f;
+    const float Guv[2] = {-k * d[0], -k * d[1]};
+    float GP[3];
+    al_reproj_vjp(c1, P2, q, Guv, g1, GP);
+    al_anchor_point_vjp(c2, e.a2.u, e.a2.v, e.a2.core, e.a2.off, pc2, z2, D2, o2, GP, g2);
+    return cw * l;
+  } else {
+    float P1[3], pc1[3], z1, D1, o1;
+    al_anchor_point(c1, e.a1.u, e.a1.v, e.a1.core, e.a1.off, P1, pc1, &z1, &D1, &o1);
+    const float tg[3] = {pb.ed_tgt[3 * m], pb.ed_tgt[3 * m + 1], pb.ed_tgt[3 * m + 2]};
+    float T[3];
+    al_mat3_vec(c2.R, tg, T);
+    T[0] += c2.t[0]; T[1] += c2.t[1]; T[2] += c2.t[2];
+    const float d[3] = {P1[0] - T[0], P1[1] - T[1], P1[2] - T[2]};
+    const float dist = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    const float l = al_gamma_loss(dist, gamma, offset, off_pow, &dl);
+    const float cw = pb.ed_conf[m] * scale;
+    const float k = dist > 0.f ? cw * dl / dist : 0.f;
+    const float GP1[3] = {k * d[0], k * d[1], k * d[2]};
+    al_anchor_point_vjp(c1, e.a1.u, e.a1.v, e.a1.core, e.a1.off, pc1, z1, D1, o1, GP1, g1);
+    for (int a = 0; a < 3; ++a) {
+      for (int b = 0; b < 3; ++b) g2[3 * a + b] += -GP1[a] * tg[b];
+      g2[9 + a] += -GP1[a];
+    }
+    return cw * l;
+  }
+}
+
+// Warp-wide sum of a lane-private gradient record into the CTA table; the record restarts at zero.
+__device__ __forceinline__ void seg_flush(float* table, int img, float* acc) {
+  if (img < 0) return;   // warp-uniform
+#pragma unroll
+  for (int k = 0; k < NG; ++k) {
+    float v = acc[k];
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane_id() == 0 && v != 0.f) atomicAdd(table + img * NG + k, v);
+    acc[k] = 0.f;
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(LOSS_THREADS)
+align_loss_seg_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, float off_pow, float scale, int per_warp,
+                      float* loss_out) {
+  extern __shared__ float table[];
+  if (w.sums[3] != 0.f) return;
+  const int N = pb.n_img;
+  const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
+  for (int e = threadIdx.x; e < N * NG; e += blockDim.x) table[e] = 0.f;
+  __syncthreads();
+  const int n = KIND == 0 ? pb.n3 : (KIND == 1 ? pb.n2 : pb.nd);
+  const int lane = lane_id();
+  const long long wbeg = ((long long)blockIdx.x * (LOSS_THREADS / 32) + (threadIdx.x >> 5)) * per_warp;
+  const int begin = (int)(wbeg < n ? wbeg : n), end = (int)(wbeg + per_warp < n ? wbeg + per_warp : n);
+  float acc1[NG], acc2[NG];
+#pragma unroll
+  for (int k = 0; k < NG; ++k) acc1[k] = acc2[k] = 0.f;
+  int cur1 = -1, cur2 = -1;      // image pair whose gradients acc1 / acc2 hold (warp-uniform)
+  float loss = 0.f;
+  for (int base = begin; base < end; base += 32) {
+    const int m = base + lane;
+    const bool active = m < end;
+    SegEntry<KIND> e;
+    e.i1 = e.i2 = -1;
+    if (active) seg_load<KIND>(pb, ic, m, e);
+    const int key = active ? ((e.i1 << 16) | e.i2) : -1;        // n_img < 2^15 (the shared table caps it far lower)
+    const int first = __shfl_sync(0xffffffffu, key, 0);         // lane 0 is active in every row
+    const bool uniform = __all_sync(0xffffffffu, !active || key == first);
+    if (uniform) {
+      const int f1 = first >> 16, f2 = first & 0xffff;
+      if (f1 != cur1 || f2 != cur2) {
+        seg_flush(table, cur1, acc1);
+        seg_flush(table, cur2, acc2);
+        cur1 = f1; cur2 = f2;
+      }
+      if (active) loss += seg_eval<KIND>(pb, w, m, e, gamma, offset, off_pow, scale, acc1, acc2);
+    } else {
+      // a row that straddles two image pairs: per-row reduction like variant 0
+      float g1[NG], g2[NG];
+#pragma unroll
+      for (int k = 0; k < NG; ++k) g1[k] = g2[k] = 0.f;
+      if (active) loss += seg_eval<KIND>(pb, w, m, e, gamma, offset, off_pow, scale, g1, g2);
+      accum_image(table, e.i1, active, g1);
+      accum_image(table, e.i2, active, g2);
+    }
+  }
+  seg_flush(table, cur1, acc1);
+  seg_flush(table, cur2, acc2);
+  flush_table(table, N, w.gcam + (size_t)(blockIdx.x % ALIGN_REPL) * N * NG, loss, loss_out);
+}
+
 __device__ __forceinline__ void adam_update(float* p, float g, float* m, float* v, float lr_over_bc1, float inv_sqrt_bc2,
                                             float omb1, float b2, float omb2, float eps) {
   float mm = *m + (g - *m) * omb1;
@@ -265,7 +418,7 @@ __device__ __forceinline__ void adam_update(float* p, float g, float* m, float* 
 __global__ void __launch_bounds__(CAM_THREADS)
 align_cam_bwd_kernel(St3rAlignProblem pb, Params p, AdamState ad, Work w, int train_mask, float lr_over_bc1,
                      float inv_sqrt_bc2, float omb1, float b2, float omb2, float eps, float dust3r_w,
-                     float* loss_hist, int iter, float* grad_out /* optional [11 N], for tests */) {
+                     float* loss_hist, int iter, float* grad_out /* optional [11 N], for tests */, int reps) {
   const int N = pb.n_img;
   const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
   __shared__ float s_gg[CAM_THREADS];
@@ -274,7 +427,17 @@ align_cam_bwd_kernel(St3rAlignProblem pb, Params p, AdamState ad, Work w, int tr
   const float ties = w.gscal[1], smin = w.gscal[2];
   float gg = 0.f;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    al_cam_final_bwd(ic[i], p.pp + 2 * i, g, w.tmp[i], w.gcam + i * NG, w.cgrad[i]);
+    const float* gsrc = w.gcam + i * NG;
+    float folded[NG];
+    if (reps > 1) {     // variant 1: the loss CTAs spread their sums over `reps` replicas of the table
+#pragma unroll
+      for (int k = 0; k < NG; ++k) folded[k] = gsrc[k];
+      for (int r = 1; r < reps; ++r)
+#pragma unroll
+        for (int k = 0; k < NG; ++k) folded[k] += gsrc[(size_t)r * N * NG + k];
+      gsrc = folded;
+    }
+    al_cam_final_bwd(ic[i], p.pp + 2 * i, g, w.tmp[i], gsrc, w.cgrad[i]);
     gg += w.cgrad[i].g_g;
   }
   s_gg[threadIdx.x] = gg;
@@ -323,7 +486,8 @@ align_cam_bwd_kernel(St3rAlignProblem pb, Params p, AdamState ad, Work w, int tr
       float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
       q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
     }
-    for (int k = 0; k < NG; ++k) w.gcam[i * NG + k] = 0.f;
+    for (int r = 0; r < reps; ++r)
+      for (int k = 0; k < NG; ++k) w.gcam[(size_t)r * N * NG + i * NG + k] = 0.f;
   }
 }
 
@@ -352,7 +516,7 @@ Work carve(void* ws, int N) {
   w.cam = a.take<AlignCam>(N);
   w.tmp = a.take<AlignCamTmp>(N);
   w.cgrad = a.take<AlignCamGrad>(N);
-  w.gcam = a.take<float>((size_t)N * NG);
+  w.gcam = a.take<float>((size_t)N * NG * ALIGN_REPL);
   w.sums = a.take<float>(4);
   w.gscal = a.take<float>(4);
   return w;
@@ -360,12 +524,23 @@ Work carve(void* ws, int N) {
 
 }  // namespace
 
+// bit 0: segmented accumulation in the loss kernels (align_loss_seg_kernel); bit 1: one thread-block cluster per image
+// in st3r_focal_weiszfeld (align_dense.cu).  0 = the variants every committed profile was measured with.
+static int g_align_variant = 0;
+int align_variant() { return g_align_variant; }
+
 extern "C" {
+
+int st3r_align_set_variant(int variant) {
+  ST3R_CHECK_ARG(variant >= 0 && variant <= 3, "st3r_align_set_variant: unknown variant %d", variant);
+  g_align_variant = variant;
+  return ST3R_OK;
+}
 
 size_t st3r_align_ws_bytes(int n_img) {
   size_t n = (size_t)(n_img > 0 ? n_img : 1);
   return st3r_align_up(n * sizeof(AlignCam), 256) + st3r_align_up(n * sizeof(AlignCamTmp), 256) +
-         st3r_align_up(n * sizeof(AlignCamGrad), 256) + st3r_align_up(n * NG * sizeof(float), 256) + 4096;
+         st3r_align_up(n * sizeof(AlignCamGrad), 256) + st3r_align_up(n * NG * ALIGN_REPL * sizeof(float), 256) + 4096;
 }
 int st3r_align_cam_floats(void) { return (int)(sizeof(AlignCam) / sizeof(float)); }
 int st3r_align_img_const_bytes(void) { return (int)sizeof(AlignImgConst); }
@@ -388,12 +563,17 @@ int st3r_align_optimize(const St3rAlignProblem* prob, float* pp, float* log_foca
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(align_loss3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(align_loss2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(align_lossd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    ST3R_CHECK_CUDA(cudaFuncSetAttribute(align_loss_seg_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    ST3R_CHECK_CUDA(cudaFuncSetAttribute(align_loss_seg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    ST3R_CHECK_CUDA(cudaFuncSetAttribute(align_loss_seg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
   Work w = carve(ws, N);
   Params p{pp, log_focal, quat, trans, log_size};
   AdamState ad{adam_m, adam_v};
-  ST3R_CHECK_CUDA(cudaMemsetAsync(w.gcam, 0, (size_t)N * NG * sizeof(float), stream));
+  const int variant = g_align_variant & 1;
+  const int reps = variant == 1 ? ALIGN_REPL : 1;
+  ST3R_CHECK_CUDA(cudaMemsetAsync(w.gcam, 0, (size_t)N * NG * ALIGN_REPL * sizeof(float), stream));
   ST3R_CHECK_CUDA(cudaMemsetAsync(w.sums, 0, 4 * sizeof(float), stream));
 
   auto gamma_consts = [](float gm, float* off, float* offpow) {
@@ -410,6 +590,16 @@ int st3r_align_optimize(const St3rAlignProblem* prob, float* pp, float* log_foca
   const float scale_main = (n_main > 0 && norm_main != 0.f) ? 1.0f / norm_main : 0.f;
   const float scale_d = (pb.nd > 0 && pb.normd != 0.f) ? 1.0f / pb.normd : 0.f;
   auto blocks_for = [](int n) { int b = (n + LOSS_THREADS * 2 - 1) / (LOSS_THREADS * 2); return b < 1 ? 1 : (b > 1184 ? 1184 : b); };
+  // variant 1: every warp walks `per_warp` consecutive entries (a multiple of 32), at most SEG_MAX_CTAS CTAs
+  constexpr int WARPS = LOSS_THREADS / 32;
+  auto seg_blocks = [](int n) {
+    int b = (n + WARPS * SEG_MIN_PER_WARP - 1) / (WARPS * SEG_MIN_PER_WARP);
+    return b < 1 ? 1 : (b > SEG_MAX_CTAS ? SEG_MAX_CTAS : b);
+  };
+  auto seg_per_warp = [](int n, int blocks) {
+    const long long warps = (long long)blocks * WARPS;
+    return (int)(((n + warps - 1) / warps + 31) / 32 * 32);
+  };
 
   const int iters = niter > 0 ? niter : 1;
   for (int it = 0; it < iters; ++it) {
@@ -417,16 +607,29 @@ int st3r_align_optimize(const St3rAlignProblem* prob, float* pp, float* log_foca
     ST3R_CHECK_LAUNCH();
     if (niter == 0) break;
     if (n_main > 0) {
-      if (mode == 0)
+      if (variant == 1) {
+        const int gb = seg_blocks(n_main), pw = seg_per_warp(n_main, gb);
+        if (mode == 0)
+          align_loss_seg_kernel<0><<<gb, LOSS_THREADS, table_bytes, stream>>>(pb, w, gamma, off_m, offp_m, scale_main, pw, w.sums + 0);
+        else
+          align_loss_seg_kernel<1><<<gb, LOSS_THREADS, table_bytes, stream>>>(pb, w, gamma, off_m, offp_m, scale_main, pw, w.sums + 0);
+      } else if (mode == 0) {
         align_loss3d_kernel<<<blocks_for(n_main), LOSS_THREADS, table_bytes, stream>>>(pb, w, gamma, off_m, offp_m, scale_main);
-      else
+      } else {
         align_loss2d_kernel<<<blocks_for(n_main), LOSS_THREADS, table_bytes, stream>>>(pb, w, gamma, off_m, offp_m, scale_main);
+      }
       ST3R_CHECK_LAUNCH();
     }
     if (pb.nd > 0 && dust3r_w != 0.f) {
       // the dust3r term enters the total loss with weight dust3r_w (reconstruct.py:389)
-      align_lossd_kernel<<<blocks_for(pb.nd), LOSS_THREADS, table_bytes, stream>>>(pb, w, gamma_dust3r, off_d, offp_d,
-                                                                                   scale_d * dust3r_w);
+      if (variant == 1) {
+        const int gb = seg_blocks(pb.nd), pw = seg_per_warp(pb.nd, gb);
+        align_loss_seg_kernel<2><<<gb, LOSS_THREADS, table_bytes, stream>>>(pb, w, gamma_dust3r, off_d, offp_d,
+                                                                           scale_d * dust3r_w, pw, w.sums + 1);
+      } else {
+        align_lossd_kernel<<<blocks_for(pb.nd), LOSS_THREADS, table_bytes, stream>>>(pb, w, gamma_dust3r, off_d, offp_d,
+                                                                                     scale_d * dust3r_w);
+      }
       ST3R_CHECK_LAUNCH();
     }
     const int step = it + 1;
@@ -434,7 +637,7 @@ int st3r_align_optimize(const St3rAlignProblem* prob, float* pp, float* log_foca
     align_cam_bwd_kernel<<<1, CAM_THREADS, 0, stream>>>(pb, p, ad, w, train_mask, (float)((double)h_lr[it] / bc1),
                                                         (float)(1.0 / sqrt(bc2)), (float)(1.0 - beta1), (float)beta2,
                                                         (float)(1.0 - beta2), (float)eps, 1.0f, loss_hist, it,
-                                                        (it == iters - 1) ? grad_out : nullptr);
+                                                        (it == iters - 1) ? grad_out : nullptr, reps);
     ST3R_CHECK_LAUNCH();
   }
   if (cam_out) ST3R_CHECK_CUDA(cudaMemcpyAsync(cam_out, w.cam, (size_t)N * sizeof(AlignCam), cudaMemcpyDeviceToDevice, stream));

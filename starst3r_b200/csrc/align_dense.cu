@@ -7,8 +7,13 @@
 //   clean_pointcloud(dust3r/cloud_opt/base_opt.py:369-405): lower the confidence of points that lie in front of a
 //                   more confident view's depth map; images are processed in order because image i reads the
 //                   already cleaned confidences of images j < i.
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "../../include/starst3r_b200.h"
+
+namespace cg = cooperative_groups;
+
+int align_variant();   // align.cu (st3r_align_set_variant)
 
 namespace {
 
@@ -94,6 +99,76 @@ focal_weiszfeld_kernel(const float* __restrict__ canon, int H, int W, float min_
   }
 }
 
+// Variant with a thread-block cluster per image (st3r_align_set_variant bit 1).  The single-CTA kernel above streams
+// the point map eleven times through one SM (1.5 ms per 512 x 512 image, profiles/r01u_launches_reconstruct.csv);
+// here WZ_CLUSTER CTAs split the pixels, publish their partial sums in their own shared memory, and after a cluster
+// barrier every CTA adds the partials of all ranks in rank order over distributed shared memory, so all of them
+// continue with the same focal.  Two slots alternate between iterations: one cluster barrier per iteration.
+constexpr int WZ_CLUSTER = 8;
+
+__global__ void __cluster_dims__(WZ_CLUSTER, 1, 1) __launch_bounds__(1024)
+focal_weiszfeld_cluster_kernel(const float* __restrict__ canon, int H, int W, float min_focal, float max_focal,
+                               float* __restrict__ out) {
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float red[2][32];
+  __shared__ float part[2][2];
+  __shared__ float s_f;
+  const int img = blockIdx.x / WZ_CLUSTER;
+  const int rank = (int)cluster.block_rank();
+  const float* X = canon + (size_t)img * H * W * 3;
+  const int n = H * W;
+  const float cx = 0.5f * W, cy = 0.5f * H;
+  float focal = 0.f;
+  for (int iter = 0; iter <= 10; ++iter) {
+    float a = 0.f, b = 0.f;
+    for (int i = rank * blockDim.x + threadIdx.x; i < n; i += WZ_CLUSTER * blockDim.x) {
+      const float u = (float)(i % W) - cx, v = (float)(i / W) - cy;
+      float qx = X[3 * i] / X[3 * i + 2], qy = X[3 * i + 1] / X[3 * i + 2];
+      if (isinf(qx)) qx = 0.f;
+      if (isinf(qy)) qy = 0.f;
+      if (isnan(qx)) qx = 0.f;
+      if (isnan(qy)) qy = 0.f;
+      const float dxp = qx * u + qy * v, dxx = qx * qx + qy * qy;
+      float w = 1.f;
+      if (iter > 0) {
+        const float ex = u - focal * qx, ey = v - focal * qy;
+        w = 1.0f / fmaxf(sqrtf(ex * ex + ey * ey), 1e-8f);
+      }
+      a += w * dxp;
+      b += w * dxx;
+    }
+    for (int off = 16; off; off >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, off);
+      b += __shfl_xor_sync(0xffffffffu, b, off);
+    }
+    if (lane_id() == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float sa = 0.f, sb = 0.f;
+      for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { sa += red[0][k]; sb += red[1][k]; }
+      part[iter & 1][0] = sa;
+      part[iter & 1][1] = sb;
+    }
+    cluster.sync();                       // every rank's partial of this iteration is published
+    if (threadIdx.x == 0) {
+      float sa = 0.f, sb = 0.f;
+      for (int r = 0; r < WZ_CLUSTER; ++r) {
+        const float* rp = cluster.map_shared_rank(&part[iter & 1][0], r);
+        sa += rp[0];
+        sb += rp[1];
+      }
+      s_f = sa / sb;
+    }
+    __syncthreads();
+    focal = s_f;
+  }
+  cluster.sync();                         // nobody exits while a peer may still read its shared memory
+  if (rank == 0 && threadIdx.x == 0) {
+    const float fb = (float)max(H, W) / (2.0f * tanf(0.5235987755982988f));
+    out[img] = fminf(fmaxf(focal, min_focal * fb), max_focal * fb);
+  }
+}
+
 struct DenseCam { float R[9]; float t[3]; float f, cx, cy, bf; };
 
 // Every pixel as an anchor of its 8x8 block: pts3d [HW,3] (world) and depth [HW] (camera z).
@@ -162,7 +237,10 @@ int st3r_focal_weiszfeld(const float* canon, int n_img, int H, int W, float min_
   ST3R_CHECK_ARG(n_img >= 0 && H > 0 && W > 0, "st3r_focal_weiszfeld: bad sizes");
   if (n_img == 0) return ST3R_OK;
   ST3R_CHECK_ARG(canon && focal_out, "st3r_focal_weiszfeld: null pointer");
-  focal_weiszfeld_kernel<<<n_img, 1024, 0, stream>>>(canon, H, W, min_focal, max_focal, focal_out);
+  if (align_variant() & 2)
+    focal_weiszfeld_cluster_kernel<<<n_img * WZ_CLUSTER, 1024, 0, stream>>>(canon, H, W, min_focal, max_focal, focal_out);
+  else
+    focal_weiszfeld_kernel<<<n_img, 1024, 0, stream>>>(canon, H, W, min_focal, max_focal, focal_out);
   ST3R_CHECK_LAUNCH();
   return ST3R_OK;
 }

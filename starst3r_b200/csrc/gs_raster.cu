@@ -265,8 +265,11 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
         const float g8 = warp_sum(g[8]);
         // value index held by this lane: bit 4 of the lane selects +4, bit 3 selects +2, bit 2 selects +1
         const int vi = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
-        if ((lane & 3) == 0 && c1 != 0.f) atomicAdd(&acc[t][vi], c1);
-        if (lane == 1 && g8 != 0.f) atomicAdd(&acc[t][8], g8);
+        // One shared-memory update for all nine sums: lanes 0, 4, ..., 28 carry values 0..7 and lane 1 the ninth
+        // (fp32 shared atomics are compare-and-swap loops, ATOMS.CAST.SPIN; nine distinct words, one pass).
+        const bool ninth = lane == 1;
+        const float sum = ninth ? g8 : c1;
+        if (((lane & 3) == 0 || ninth) && sum != 0.f) atomicAdd(&acc[t][ninth ? 8 : vi], sum);
       }
      }
     }

@@ -7,6 +7,7 @@ cleaning via st3r_canonical_view, st3r_dense_points, st3r_clean_pointcloud (alig
 HBM (no torch.save round trip); `tmpdir` / `cache_dir` are accepted for signature parity.
 """
 import ctypes
+import os
 import math
 from collections import namedtuple
 
@@ -183,10 +184,17 @@ def problem_struct(t, meta):
     return p
 
 
+# Variants of the ALIGN kernels (bit mask of st3r_align_set_variant): bit 0 = segmented register accumulation +
+# replicated gradient tables in the loss kernels, bit 1 = one thread-block cluster per image in the Weiszfeld focal
+# kernel.  0 = the variants all committed measurements were taken with.  ST3R_ALIGN_VARIANT sets the initial value.
+ALIGN_VARIANT = int(os.environ.get("ST3R_ALIGN_VARIANT", "0"))
+
+
 def _optimize_phase(t, meta, params, mode, train_mask, gamma, lr_base, niter, schedule, dust3r_w, lossd_gamma,
                     want_grad=False):
     """One optimize_loop call (reconstruct.py:371-406) on the device."""
     lib = _lib.load()
+    _lib.check(lib.st3r_align_set_variant(int(ALIGN_VARIANT)), "st3r_align_set_variant")
     dev = params["pps"].device
     N = meta["N"]
     prob = problem_struct(t, meta)
@@ -447,6 +455,7 @@ def estimate_focal_knowing_depth(pts3d, pp=None, focal_mode="weiszfeld", min_foc
     B, H, W, _ = pts3d.shape
     out = torch.empty(B, device=pts3d.device)
     x = pts3d.float().contiguous()
+    _lib.check(lib.st3r_align_set_variant(int(ALIGN_VARIANT)), "st3r_align_set_variant")
     with torch.cuda.device(x.device):
         _lib.check(lib.st3r_focal_weiszfeld(_lib.ptr(x), B, H, W, ctypes.c_float(min_focal),
                                             ctypes.c_float(min(max_focal, 3.0e38)), _lib.ptr(out), _lib.stream_ptr()),
