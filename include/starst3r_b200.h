@@ -61,6 +61,13 @@ ST3R_API int st3r_debug_nn_tc_cycles(unsigned long long* h_out4, int reset);
  * st3r_nn_tc_set_cooperative selects the variant for subsequent launches of this process. */
 ST3R_API int st3r_nn_tc_stats(unsigned long long* h_out2, int reset);
 ST3R_API int st3r_nn_tc_set_cooperative(int on);
+/* Split-precision variant of the tcgen05 matcher (off by default): every operand is split into its tf32 head and the
+ * tf32 head of the remainder and the kernel accumulates hi.hi + hi.lo + lo.hi (3 x the tensor work), which narrows
+ * the band of columns that need an exact fp32 re-score ~40x - for smooth descriptor fields, where ~100 columns per
+ * row sit inside the plain TF32 band.  Results are identical (the exact re-score decides either way).  While it is
+ * on, st3r_nn_argmax_ws_bytes and st3r_extract_corres_ws_bytes include two [rows, 24] float arrays per descriptor
+ * map; st3r_recip_nn always runs the plain variant. */
+ST3R_API int st3r_nn_tc_set_split(int on);
 
 /* ------------------------------------------------------------------ MATCH */
 

@@ -27,7 +27,8 @@ int nn_simt_launch(const float* Qsrc, const int32_t* qidx, const int32_t* count_
 // `db_norm_bound` = device pointer to max_j ||DB_j||_2^2 (float), see nn_db_norm_launch.
 int nn_tc_launch(const float* Qsrc, const int32_t* qidx, const int32_t* count_ptr, int Mmax,
                  const float* DB, int N, int d, const float* db_norm_bound,
-                 unsigned long long* packed, cudaStream_t stream);
+                 unsigned long long* packed, cudaStream_t stream, const float* DB_hi = nullptr,
+                 const float* DB_lo = nullptr);
 int nn_db_norm_launch(const float* DB, int N, int d, float* out_bound, cudaStream_t stream);
 bool nn_tc_supported(int d);
 
@@ -38,5 +39,10 @@ struct NnBatchItem {
   const float* Qsrc; const int32_t* qidx; const int32_t* count_ptr; int Mmax;
   const float* DB; int N; const float* db_norm_bound;
   unsigned long long* packed;
+  // Optional tf32 head / tail of DB (nn_tc_split_launch): with both present and st3r_nn_tc_set_split(1) the
+  // split-precision variant of the tcgen05 kernel runs (3 x TF32 products, ~40x narrower candidate band).
+  const float* DB_hi = nullptr; const float* DB_lo = nullptr;
 };
+int nn_tc_split_launch(const float* DB, int N, int d, float* hi, float* lo, cudaStream_t stream);
+bool nn_tc_split_enabled();
 int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stream);

@@ -40,7 +40,6 @@ constexpr int BM = UM * MH;        // query rows per CTA
 constexpr int BN = NN_TC_BN;       // DB rows per MMA tile (UMMA N)
 constexpr int DK = 24;             // descriptor dim
 constexpr int ROWB = 128;          // smem bytes per operand row (32 floats, 24 real + 8 zero)
-constexpr int STAGES = 768 / BN;    // smem ring depth for DB tiles (96 KB)
 // All 512 TMEM columns hold accumulators: the kernel's throughput is (columns in flight) / (round trip MMA issue ->
 // commit -> epilogue read -> release), and narrower tiles shorten the round trip (its UMMA and TMEM-read parts scale
 // with the tile width, its barrier hops do not).
@@ -57,15 +56,33 @@ constexpr int MAX_TILES_PER_CHUNK = 65536 / BN;
 constexpr int MAX_PROBE = 1024 / BN;  // max-only probe tiles per CTA (see the kernel)
 constexpr float DELTA_COEF = 4.2e-3f;  // > 2 * 2^-9 (+ fp32 accumulation slack)
 
-constexpr int SMEM_A = 0;
-constexpr int SMEM_B = SMEM_A + BM * ROWB;
 constexpr int CAND_CAP = 12;       // candidates kept per (row, epilogue thread) between resolutions
-constexpr int SMEM_CAND = SMEM_B + STAGES * BN * ROWB;
-constexpr int SMEM_CTX = SMEM_CAND + BM * CAND_CAP * 8;    // EpiCtx per query row
-constexpr int SMEM_DBP = SMEM_CTX + BM * 24;               // DB base pointer of this CTA's problem
-constexpr int SMEM_BAR = SMEM_DBP + 16;
-constexpr int SMEM_TOTAL = SMEM_BAR + 512;   // up to 48 mbarriers + the TMEM base address
-constexpr int SMEM_DYN = SMEM_TOTAL + 1024;  // slack for 1024-byte alignment
+// Split-precision variant (kernel template parameter kSplit, st3r_nn_tc_set_split).  kind::tf32 keeps 10 mantissa
+// bits per operand, so smooth descriptor fields (real MASt3R maps) leave ~100 columns per row inside the error band
+// and the exact re-scores dominate (7.9 ms instead of 2.5 ms per 512 x 512 pair).  With x = hi + lo + r, hi and lo
+// both exactly representable in tf32 (|lo| <= 2^-10 |x|, |r| <= 2^-20 |x|), the three products
+// hi_q.hi_d + hi_q.lo_d + lo_q.hi_d reproduce the fp32 dot product to ~2^-18 |q| |d| plus the accumulation error of
+// the tensor core: the band narrows ~40x for 3x the tensor work (which the hand-off bound pipeline largely hides).
+// hi / lo of the DB are produced once per map by nn_tc_split_launch (so the tensor core never has to convert a value
+// that is not already tf32: no dependence on its truncate-or-round behaviour); hi / lo of the query tile are
+// produced while it is gathered into shared memory.  Shared memory: the query tile and every DB stage double.
+template <bool kSplit>
+struct Lay {
+  static constexpr int PARTS = kSplit ? 2 : 1;
+  static constexpr int A_BYTES = BM * ROWB * PARTS;
+  static constexpr int STAGE_BYTES = BN * ROWB * PARTS;
+  static constexpr int STAGES = (kSplit ? 512 : 768) / BN;   // smem ring depth for DB tiles (128 KB / 96 KB)
+  static constexpr int SMEM_A = 0;
+  static constexpr int SMEM_B = SMEM_A + A_BYTES;
+  static constexpr int SMEM_CAND = SMEM_B + STAGES * STAGE_BYTES;
+  static constexpr int SMEM_CTX = SMEM_CAND + BM * CAND_CAP * 8;    // EpiCtx per query row
+  static constexpr int SMEM_DBP = SMEM_CTX + BM * 24;               // DB base pointer of this CTA's problem
+  static constexpr int SMEM_BAR = SMEM_DBP + 16;
+  static constexpr int SMEM_TOTAL = SMEM_BAR + 512;   // up to 48 mbarriers + the TMEM base address
+  static constexpr int SMEM_DYN = SMEM_TOTAL + 1024;  // slack for 1024-byte alignment
+  static_assert(SMEM_DYN <= 227 * 1024, "shared memory budget of one CTA");
+};
+constexpr float DELTA_COEF_SPLIT = 1.0e-4f;   // 2 x (3 x 2^-20 products dropped + <= ~2e-5 fp32 accumulation), 2x margin
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -145,6 +162,22 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 #endif
 }
 
+// x -> its tf32 head (returned in x: sign, exponent and the 10 leading mantissa bits, i.e. what kind::tf32 reads) and
+// the tf32 head of the remainder (lo).  x - head is exact in fp32.
+__host__ __device__ __forceinline__ void split_tf32(float& x, float& lo) {
+#ifdef __CUDA_ARCH__
+  const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  lo = __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u);
+#else
+  union { float f; uint32_t u; } a, b;
+  a.f = x; a.u &= 0xffffe000u;
+  const float hi = a.f;
+  b.f = x - hi; b.u &= 0xffffe000u;
+  lo = b.f;
+#endif
+  x = hi;
+}
+
 // Maximum of 32 consecutive accumulator columns: 15 three-input max instructions + 1.
 __device__ __forceinline__ float chunk_max(const float* x) {
   float m01 = fmax3(x[0], x[1], x[2]), m02 = fmax3(x[3], x[4], x[5]), m03 = fmax3(x[6], x[7], x[8]);
@@ -220,8 +253,10 @@ __device__ __forceinline__ float resolve_list(const Cand* list, int cnt, float t
 // current threshold; if it is still full of live candidates it is resolved exactly on the spot and restarted empty,
 // and the exact best raises the running bound (a later column can only win if its approximate score is
 // >= best - eps, and eps <= delta / 2).  Returns (bits of the new running maximum << 32) | new count.
+template <bool kSplit>
 __device__ __noinline__ unsigned long long absorb_candidates(int slot, int cnt, uint32_t mask, int col0, float cmax,
                                                              float run_max) {
+  constexpr int SMEM_CAND = Lay<kSplit>::SMEM_CAND, SMEM_CTX = Lay<kSplit>::SMEM_CTX, SMEM_DBP = Lay<kSplit>::SMEM_DBP;
   uint8_t* smem = smem_base();
   Cand* list = reinterpret_cast<Cand*>(smem + SMEM_CAND) + slot * CAND_CAP;
   EpiCtx* ctx = reinterpret_cast<EpiCtx*>(smem + SMEM_CTX) + slot;
@@ -258,8 +293,9 @@ __device__ __noinline__ unsigned long long absorb_candidates(int slot, int cnt, 
 // resolving, and full lists are resolved by the warp: the 12 entries of one row are re-scored by 12 lanes in parallel.
 // It costs the random-descriptor case ~14 % (warp-wide votes on every cold tile), so the host picks the variant from
 // the resolution statistics of earlier calls (st3r_nn_tc_stats / st3r_nn_tc_set_cooperative).
+template <bool kSplit>
 __device__ __noinline__ unsigned long long absorb_no_resolve(int slot, int cnt, uint32_t mask, int col0, float cmax, float thr) {
-  Cand* list = reinterpret_cast<Cand*>(smem_base() + SMEM_CAND) + slot * CAND_CAP;
+  Cand* list = reinterpret_cast<Cand*>(smem_base() + Lay<kSplit>::SMEM_CAND) + slot * CAND_CAP;
   while (mask) {
     if (cnt == CAND_CAP) {
       int w = 0;
@@ -281,7 +317,9 @@ __device__ __noinline__ unsigned long long absorb_no_resolve(int slot, int cnt, 
 
 // Called by ALL lanes of an epilogue warp; `need` marks the lanes whose list is full of live candidates.  Returns the
 // (possibly raised) running maximum of the calling lane; the resolved lists restart empty (caller resets its count).
+template <bool kSplit>
 __device__ __noinline__ float resolve_full_lists(int slot, bool need, float run_max) {
+  constexpr int SMEM_CAND = Lay<kSplit>::SMEM_CAND, SMEM_CTX = Lay<kSplit>::SMEM_CTX, SMEM_DBP = Lay<kSplit>::SMEM_DBP;
   uint8_t* smem = smem_base();
   const Cand* lists = reinterpret_cast<const Cand*>(smem + SMEM_CAND);
   EpiCtx* ctxs = reinterpret_cast<EpiCtx*>(smem + SMEM_CTX);
@@ -322,17 +360,22 @@ __device__ __noinline__ float resolve_full_lists(int slot, bool need, float run_
 __device__ unsigned long long g_nn_tc_stats[2];
 
 struct NnTcParams {
-  CUtensorMap tmap[NN_MAX_BATCH];
+  CUtensorMap tmap[NN_MAX_BATCH];      // the DB (kSplit: its tf32 head, NnBatchItem::DB_hi)
+  CUtensorMap tmap_lo[NN_MAX_BATCH];   // kSplit only: the tf32 tail (NnBatchItem::DB_lo)
   NnBatchItem it[NN_MAX_BATCH];
   int tiles_per_chunk;
   int dynamic;
 };
 
-template <bool kCoop>
+template <bool kCoop, bool kSplit>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
+  using L = Lay<kSplit>;
+  constexpr int STAGES = L::STAGES, SMEM_A = L::SMEM_A, SMEM_B = L::SMEM_B, SMEM_CAND = L::SMEM_CAND,
+                SMEM_CTX = L::SMEM_CTX, SMEM_DBP = L::SMEM_DBP, SMEM_BAR = L::SMEM_BAR;
   const NnBatchItem& it = prm.it[blockIdx.z];
   const CUtensorMap* tmap_db = &prm.tmap[blockIdx.z];
+  const CUtensorMap* tmap_db_lo = &prm.tmap_lo[blockIdx.z];
   const float* __restrict__ Qsrc = it.Qsrc;
   const int32_t* __restrict__ qidx = it.qidx;
   const int32_t* __restrict__ count_ptr = it.count_ptr;
@@ -409,6 +452,11 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
       size_t row = qidx ? (size_t)qidx[gm] : (size_t)gm;
       v = *reinterpret_cast<const float4*>(Qsrc + row * DK + c * 4);
     }
+    if (kSplit) {     // tf32 head and tail of every element (see Lay): two tiles, same swizzled layout
+      float4 lo;
+      split_tf32(v.x, lo.x); split_tf32(v.y, lo.y); split_tf32(v.z, lo.z); split_tf32(v.w, lo.w);
+      *reinterpret_cast<float4*>(smem + SMEM_A + BM * ROWB + r * ROWB + ((c ^ (r & 7)) << 4)) = lo;
+    }
     *reinterpret_cast<float4*>(smem + SMEM_A + r * ROWB + ((c ^ (r & 7)) << 4)) = v;
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -424,8 +472,9 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
         int s = t % STAGES;
         uint32_t ph = (uint32_t)(t / STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_arrive_expect_tx(full_bar(s), BN * ROWB);
-        tma_load_2d(sB + s * BN * ROWB, tmap_db, 0, seq_col(t), full_bar(s));
+        mbar_arrive_expect_tx(full_bar(s), L::STAGE_BYTES);
+        tma_load_2d(sB + s * L::STAGE_BYTES, tmap_db, 0, seq_col(t), full_bar(s));
+        if (kSplit) tma_load_2d(sB + s * L::STAGE_BYTES + BN * ROWB, tmap_db_lo, 0, seq_col(t), full_bar(s));
       }
     }
   } else if (warp == WARP_MMA) {
@@ -450,8 +499,22 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
 #pragma unroll
           for (int kk = 0; kk < DK / 8; ++kk) {
             uint64_t da = make_smem_desc(sA + h * UM * ROWB + kk * 32);
-            uint64_t db = make_smem_desc(sB + s * BN * ROWB + kk * 32);
+            uint64_t db = make_smem_desc(sB + s * L::STAGE_BYTES + kk * 32);
             tc_mma_tf32(d_tmem, da, db, IDESC, kk > 0 ? 1u : 0u);
+          }
+          if (kSplit) {   // + hi_q . lo_d + lo_q . hi_d into the same accumulator
+#pragma unroll
+            for (int kk = 0; kk < DK / 8; ++kk) {
+              uint64_t da = make_smem_desc(sA + h * UM * ROWB + kk * 32);
+              uint64_t db = make_smem_desc(sB + s * L::STAGE_BYTES + BN * ROWB + kk * 32);
+              tc_mma_tf32(d_tmem, da, db, IDESC, 1u);
+            }
+#pragma unroll
+            for (int kk = 0; kk < DK / 8; ++kk) {
+              uint64_t da = make_smem_desc(sA + BM * ROWB + h * UM * ROWB + kk * 32);
+              uint64_t db = make_smem_desc(sB + s * L::STAGE_BYTES + kk * 32);
+              tc_mma_tf32(d_tmem, da, db, IDESC, 1u);
+            }
           }
         }
         tc_commit(empty_bar(s));   // smem stage free once these MMAs retire
@@ -474,7 +537,7 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
       float n2 = 0.f;
 #pragma unroll
       for (int k = 0; k < DK; ++k) n2 = fmaf(qrow[k], qrow[k], n2);
-      delta = DELTA_COEF * sqrtf(n2) * sqrtf(*db_norm2_max) + 1e-30f;
+      delta = (kSplit ? DELTA_COEF_SPLIT : DELTA_COEF) * sqrtf(n2) * sqrtf(*db_norm2_max) + 1e-30f;
     }
     float run_max = row_ok ? -INFINITY : INFINITY;  // padded rows never trigger
     {
@@ -551,14 +614,14 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
                 const float thr = run_max - delta;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) rem |= (x[i] >= thr ? 1u : 0u) << i;
-                const unsigned long long r = absorb_no_resolve(slot, cnt, rem, col_base + c * 32, cmax, thr);
+                const unsigned long long r = absorb_no_resolve<kSplit>(slot, cnt, rem, col_base + c * 32, cmax, thr);
                 cnt = (int)(uint32_t)r;
                 rem = (uint32_t)(r >> 32);
               }
               while (__any_sync(0xffffffffu, rem != 0)) {      // some lane's list is full of live candidates
-                run_max = resolve_full_lists(slot, rem != 0, run_max);
+                run_max = resolve_full_lists<kSplit>(slot, rem != 0, run_max);
                 if (rem) {
-                  const unsigned long long r = absorb_no_resolve(slot, 0, rem, col_base + c * 32, cmax, run_max - delta);
+                  const unsigned long long r = absorb_no_resolve<kSplit>(slot, 0, rem, col_base + c * 32, cmax, run_max - delta);
                   cnt = (int)(uint32_t)r;
                   rem = (uint32_t)(r >> 32);
                 }
@@ -583,7 +646,7 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
               uint32_t mask = 0;
 #pragma unroll
               for (int i = 0; i < 32; ++i) mask |= (x[i] >= thr ? 1u : 0u) << i;
-              const unsigned long long r = absorb_candidates(slot, cnt, mask, col_base + c * 32, cmax, run_max);
+              const unsigned long long r = absorb_candidates<kSplit>(slot, cnt, mask, col_base + c * 32, cmax, run_max);
               cnt = (int)(uint32_t)r;
               run_max = __uint_as_float((uint32_t)(r >> 32));
             }
@@ -643,6 +706,16 @@ __global__ void db_norm_kernel(const float* __restrict__ DB, int N, int d, uint3
   if (lane_id() == 0) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order like uints
 }
 
+// DB [N, d] -> its tf32 head and tail (same shape), see Lay.  One pass per map and API call, next to db_norm_kernel.
+__global__ void db_split_kernel(const float4* __restrict__ DB, size_t n4, float4* __restrict__ hi, float4* __restrict__ lo) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = DB[i], l;
+    split_tf32(v.x, l.x); split_tf32(v.y, l.y); split_tf32(v.z, l.z); split_tf32(v.w, l.w);
+    hi[i] = v;
+    lo[i] = l;
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -664,6 +737,27 @@ EncodeTiledFn get_encode_fn() {
 bool nn_tc_supported(int d) { return d == DK; }
 
 static int g_nn_tc_coop = 0;
+static int g_nn_tc_split = 0;
+
+bool nn_tc_split_enabled() { return g_nn_tc_split != 0; }
+
+extern "C" int st3r_nn_tc_set_split(int on) {
+  g_nn_tc_split = on ? 1 : 0;
+  return ST3R_OK;
+}
+
+int nn_tc_split_launch(const float* DB, int N, int d, float* hi, float* lo, cudaStream_t stream) {
+  ST3R_CHECK_ARG(d == DK, "nn_tc: the split-precision variant needs d == 24");
+  ST3R_CHECK_ARG(DB && hi && lo && ((uintptr_t)DB % 16) == 0 && ((uintptr_t)hi % 16) == 0 && ((uintptr_t)lo % 16) == 0,
+                 "nn_tc_split: operands must be non-null and 16-byte aligned");
+  if (N <= 0) return ST3R_OK;
+  const size_t n4 = (size_t)N * DK / 4;
+  const int blocks = (int)min((n4 + 255) / 256, (size_t)st3r_num_sms() * 8);
+  db_split_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(DB), n4, reinterpret_cast<float4*>(hi),
+                                              reinterpret_cast<float4*>(lo));
+  ST3R_CHECK_LAUNCH();
+  return ST3R_OK;
+}
 
 extern "C" int st3r_nn_tc_set_cooperative(int on) {
   g_nn_tc_coop = on ? 1 : 0;
@@ -725,12 +819,25 @@ int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stre
   NnTcParams prm;
   int m = 0, max_M = 0;
   bool all_counts = true;
+  // the split-precision variant runs when it is switched on AND the caller prepared the tf32 head / tail of every DB
+  bool split = g_nn_tc_split != 0;
+  for (int i = 0; i < n; ++i)
+    if (items[i].Mmax > 0 && items[i].N > 0 && !(items[i].DB_hi && items[i].DB_lo)) split = false;
   for (int i = 0; i < n; ++i) {
     const NnBatchItem& it = items[i];
     if (it.Mmax <= 0 || it.N <= 0) continue;
     ST3R_CHECK_ARG(((uintptr_t)it.DB % 16) == 0 && ((uintptr_t)it.Qsrc % 16) == 0, "nn_tc: operands must be 16-byte aligned");
     ST3R_CHECK_ARG(it.db_norm_bound && it.packed, "nn_tc: missing scratch");
-    int rc = encode_db_tmap(&prm.tmap[m], it.DB, it.N);
+    int rc;
+    if (split) {
+      ST3R_CHECK_ARG(((uintptr_t)it.DB_hi % 16) == 0 && ((uintptr_t)it.DB_lo % 16) == 0, "nn_tc: split arrays must be 16-byte aligned");
+      rc = encode_db_tmap(&prm.tmap[m], it.DB_hi, it.N);
+      if (rc) return rc;
+      rc = encode_db_tmap(&prm.tmap_lo[m], it.DB_lo, it.N);
+    } else {
+      rc = encode_db_tmap(&prm.tmap[m], it.DB, it.N);
+      prm.tmap_lo[m] = prm.tmap[m];
+    }
     if (rc) return rc;
     prm.it[m] = it;
     max_M = max(max_M, it.Mmax);
@@ -738,21 +845,31 @@ int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stre
     ++m;
   }
   if (m == 0) return ST3R_OK;
-  for (int i = m; i < NN_MAX_BATCH; ++i) { prm.tmap[i] = prm.tmap[0]; prm.it[i] = prm.it[0]; }
+  for (int i = m; i < NN_MAX_BATCH; ++i) { prm.tmap[i] = prm.tmap[0]; prm.tmap_lo[i] = prm.tmap_lo[0]; prm.it[i] = prm.it[0]; }
   static bool attr_set = false;
   if (!attr_set) {
-    ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
-    ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
+    ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<false>::SMEM_DYN));
+    ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<false>::SMEM_DYN));
+    ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<true>::SMEM_DYN));
+    ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<true>::SMEM_DYN));
     attr_set = true;
   }
+  auto launch = [&](dim3 grid, const NnTcParams& q) {
+    if (split) {
+      if (g_nn_tc_coop) nn_tc_kernel<true, true><<<grid, NUM_THREADS, Lay<true>::SMEM_DYN, stream>>>(q);
+      else nn_tc_kernel<false, true><<<grid, NUM_THREADS, Lay<true>::SMEM_DYN, stream>>>(q);
+    } else {
+      if (g_nn_tc_coop) nn_tc_kernel<true, false><<<grid, NUM_THREADS, Lay<false>::SMEM_DYN, stream>>>(q);
+      else nn_tc_kernel<false, false><<<grid, NUM_THREADS, Lay<false>::SMEM_DYN, stream>>>(q);
+    }
+  };
   const int slots = st3r_num_sms();      // one CTA per SM (it owns the whole tensor memory)
   const int mtiles = (max_M + BM - 1) / BM;
   if (all_counts && mtiles <= slots) {
     // device-side decomposition (see the kernel): one wave of `slots` CTAs per problem
     prm.tiles_per_chunk = 0;
     prm.dynamic = 1;
-    if (g_nn_tc_coop) nn_tc_kernel<true><<<dim3(slots, 1, m), NUM_THREADS, SMEM_DYN, stream>>>(prm);
-    else nn_tc_kernel<false><<<dim3(slots, 1, m), NUM_THREADS, SMEM_DYN, stream>>>(prm);
+    launch(dim3(slots, 1, m), prm);
     ST3R_CHECK_LAUNCH();
   } else {
     // host-side decomposition, one problem per launch.  Chunk the DB so that the grid is (close to) a whole number
@@ -761,6 +878,7 @@ int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stre
     for (int i = 0; i < m; ++i) {
       NnTcParams one = prm;
       one.tmap[0] = prm.tmap[i];
+      one.tmap_lo[0] = prm.tmap_lo[i];
       one.it[0] = prm.it[i];
       const int mt = (prm.it[i].Mmax + BM - 1) / BM;
       const int ntiles_total = (prm.it[i].N + BN - 1) / BN;
@@ -770,8 +888,7 @@ int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stre
       nchunks = (ntiles_total + tiles_per_chunk - 1) / tiles_per_chunk;
       one.tiles_per_chunk = tiles_per_chunk;
       one.dynamic = 0;
-      if (g_nn_tc_coop) nn_tc_kernel<true><<<dim3(nchunks, mt, 1), NUM_THREADS, SMEM_DYN, stream>>>(one);
-      else nn_tc_kernel<false><<<dim3(nchunks, mt, 1), NUM_THREADS, SMEM_DYN, stream>>>(one);
+      launch(dim3(nchunks, mt, 1), one);
       ST3R_CHECK_LAUNCH();
     }
   }
@@ -779,8 +896,9 @@ int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stre
 }
 
 int nn_tc_launch(const float* Qsrc, const int32_t* qidx, const int32_t* count_ptr, int Mmax, const float* DB,
-                 int N, int d, const float* db_norm_bound, unsigned long long* packed, cudaStream_t stream) {
+                 int N, int d, const float* db_norm_bound, unsigned long long* packed, cudaStream_t stream,
+                 const float* DB_hi, const float* DB_lo) {
   if (Mmax <= 0 || N <= 0) return ST3R_OK;
-  NnBatchItem it{Qsrc, qidx, count_ptr, Mmax, DB, N, db_norm_bound, packed};
+  NnBatchItem it{Qsrc, qidx, count_ptr, Mmax, DB, N, db_norm_bound, packed, DB_hi, DB_lo};
   return nn_tc_launch_batch(&it, 1, d, stream);
 }

@@ -208,9 +208,13 @@ struct RecipWs {
   int32_t* nkeys;
   float* norm_bound;  // [2]
   void* sort_ws; size_t sort_ws_bytes;
+  float* split_hi[RB]; float* split_lo[RB];   // tf32 head / tail of the maps (split-precision matcher), else null
 };
 
-size_t carve(RecipWs* w, void* ws, size_t ws_bytes, int nseed_max, int key_cap, int max_iter, bool dry, int nprob = 1) {
+// `split_rows` (optional, n_split entries): rows of the descriptor maps whose tf32 head / tail arrays the
+// split-precision matcher needs; they are carved last so that the layout of everything else does not depend on them.
+size_t carve(RecipWs* w, void* ws, size_t ws_bytes, int nseed_max, int key_cap, int max_iter, bool dry, int nprob = 1,
+             const int* split_rows = nullptr, int n_split = 0, int d = 0) {
   WsAlloc a(dry ? (void*)0 : ws, dry ? (size_t)-1 : ws_bytes);
   RecipWs t;
   for (int p = 0; p < RB; ++p) {
@@ -233,6 +237,13 @@ size_t carve(RecipWs* w, void* ws, size_t ws_bytes, int nseed_max, int key_cap, 
   t.norm_bound = a.take<float>(8);
   t.sort_ws_bytes = radix_sort_ws_bytes(key_cap);
   t.sort_ws = a.take<char>(t.sort_ws_bytes);
+  for (int k = 0; k < RB; ++k) {
+    t.split_hi[k] = t.split_lo[k] = nullptr;
+    if (split_rows && k < n_split) {
+      t.split_hi[k] = a.take<float>((size_t)split_rows[k] * d);
+      t.split_lo[k] = a.take<float>((size_t)split_rows[k] * d);
+    }
+  }
   if (w) *w = t;
   return a.off + 256;
 }
@@ -251,6 +262,8 @@ struct RecipProblem {
   int nseed, nx; const int32_t* seeds;
   int swap, set;
   const float* norm1; const float* norm2;   // device max ||row||^2 of P1 / P2 (tcgen05 path)
+  const float* hi1 = nullptr; const float* lo1 = nullptr;   // tf32 head / tail of P1 / P2 (split-precision variant)
+  const float* hi2 = nullptr; const float* lo2 = nullptr;
 };
 
 // n seeded reciprocal searches P1 -> P2 -> P1 ... advanced in lock-step; converged pairs are appended to w.keys.
@@ -282,7 +295,7 @@ int run_recip_batch(const RecipWs& w, const RecipProblem* pr, int n, int d, int 
         const RecipState& st = w.st[p];
         items[p] = NnBatchItem{half == 0 ? q.P1 : q.P2, st.qidx[h & 1], st.counts + h, q.nseed,
                                half == 0 ? q.P2 : q.P1, half == 0 ? q.HW2 : q.HW1, half == 0 ? q.norm2 : q.norm1,
-                               st.packed[h & 1]};
+                               st.packed[h & 1], half == 0 ? q.hi2 : q.hi1, half == 0 ? q.lo2 : q.lo1};
       }
       int rc = ST3R_OK;
       if (use_tc) {
@@ -327,9 +340,11 @@ int sort_and_unique(const RecipWs& w, int key_cap, int HW1, int HW2, bool with_v
 extern "C" {
 
 size_t st3r_nn_argmax_ws_bytes(int M, int N, int d) {
-  (void)N; (void)d;
-  return st3r_align_up((size_t)max(M, 1) * sizeof(unsigned long long), 256) +
-         st3r_align_up((size_t)max(M, 1) * sizeof(int32_t), 256) + 1024;
+  size_t b = st3r_align_up((size_t)max(M, 1) * sizeof(unsigned long long), 256) +
+             st3r_align_up((size_t)max(M, 1) * sizeof(int32_t), 256) + 1024;
+  if (nn_tc_split_enabled() && nn_tc_supported(d))   // tf32 head / tail of the DB
+    b += 2 * st3r_align_up((size_t)max(N, 1) * d * sizeof(float), 256);
+  return b;
 }
 
 int st3r_nn_argmax(const float* Q, int M, const float* DB, int N, int d, int32_t* idx, float* best,
@@ -348,7 +363,15 @@ int st3r_nn_argmax(const float* Q, int M, const float* DB, int N, int d, int32_t
   if (use_tc && N > 0) {
     rc = nn_db_norm_launch(DB, N, d, bound, stream);
     if (rc) return rc;
-    rc = nn_tc_launch(Q, nullptr, nullptr, M, DB, N, d, bound, packed, stream);
+    float* hi = nullptr;
+    float* lo = nullptr;
+    if (nn_tc_split_enabled()) {
+      hi = a.take<float>((size_t)N * d);
+      lo = a.take<float>((size_t)N * d);
+      rc = nn_tc_split_launch(DB, N, d, hi, lo, stream);
+      if (rc) return rc;
+    }
+    rc = nn_tc_launch(Q, nullptr, nullptr, M, DB, N, d, bound, packed, stream, hi, lo);
   } else {
     rc = nn_simt_launch(Q, nullptr, nullptr, M, DB, N, d, packed, stream);
   }
@@ -418,7 +441,10 @@ int st3r_extract_corres_cap(int H1, int W1, int H2, int W2, int subsample) {
 
 size_t st3r_extract_corres_ws_bytes(int H1, int W1, int H2, int W2, int subsample, int max_iter) {
   int n1 = seed_count(H1, W1, subsample, nullptr), n2 = seed_count(H2, W2, subsample, nullptr);
-  return carve(nullptr, nullptr, 0, max(max(n1, n2), 1), max(2 * (n1 + n2), 1), max_iter, true, 4);
+  const int rows[4] = {H1 * W1, H2 * W2, H1 * W1, H2 * W2};
+  const bool split = nn_tc_split_enabled();     // the split-precision matcher only exists for d = 24
+  return carve(nullptr, nullptr, 0, max(max(n1, n2), 1), max(2 * (n1 + n2), 1), max_iter, true, 4, split ? rows : nullptr,
+               4, 24);
 }
 
 int st3r_extract_corres(const float* feat11, const float* feat21, const float* feat22, const float* feat12,
@@ -436,23 +462,31 @@ int st3r_extract_corres(const float* feat11, const float* feat21, const float* f
   int n1 = seed_count(H1, W1, subsample, &nx1), n2 = seed_count(H2, W2, subsample, &nx2);
   int cap = 2 * (n1 + n2);
   RecipWs w;
-  size_t need = carve(&w, ws, ws_bytes, max(max(n1, n2), 1), max(cap, 1), max_iter, false, 4);
+  const bool use_tc = (impl == ST3R_NN_TCGEN05) || (impl == ST3R_NN_AUTO && nn_tc_supported(d));
+  const bool split = use_tc && nn_tc_split_enabled() && nn_tc_supported(d);
+  const int rows[4] = {H1 * W1, H2 * W2, H1 * W1, H2 * W2};
+  size_t need = carve(&w, ws, ws_bytes, max(max(n1, n2), 1), max(cap, 1), max_iter, false, 4, split ? rows : nullptr, 4, d);
   ST3R_CHECK_ARG(ws && ws_bytes >= need, "st3r_extract_corres: workspace too small (%zu < %zu)", ws_bytes, need);
   ST3R_CHECK_CUDA(cudaMemsetAsync(w.nkeys, 0, 4 * sizeof(int32_t), stream));
   // sparse_ga.py:612-620 - two descriptor sets, each matched in both directions: four searches in lock-step.
-  const bool use_tc = (impl == ST3R_NN_TCGEN05) || (impl == ST3R_NN_AUTO && nn_tc_supported(d));
   const float* maps[4] = {feat11, feat21, feat12, feat22};
   if (use_tc) {
     for (int k = 0; k < 4; ++k) {
-      int rc = nn_db_norm_launch(maps[k], (k & 1) ? H2 * W2 : H1 * W1, d, w.norm_bound + k, stream);
+      int rc = nn_db_norm_launch(maps[k], rows[k], d, w.norm_bound + k, stream);
       if (rc) return rc;
+      if (split) {
+        rc = nn_tc_split_launch(maps[k], rows[k], d, w.split_hi[k], w.split_lo[k], stream);
+        if (rc) return rc;
+      }
     }
   }
+  const float* const* sh = w.split_hi;   // null unless `split`
+  const float* const* sl = w.split_lo;
   RecipProblem pr[4] = {
-      {feat11, H1 * W1, W1, feat21, H2 * W2, n1, nx1, nullptr, 0, 0, w.norm_bound + 0, w.norm_bound + 1},
-      {feat21, H2 * W2, W2, feat11, H1 * W1, n2, nx2, nullptr, 1, 0, w.norm_bound + 1, w.norm_bound + 0},
-      {feat12, H1 * W1, W1, feat22, H2 * W2, n1, nx1, nullptr, 0, 1, w.norm_bound + 2, w.norm_bound + 3},
-      {feat22, H2 * W2, W2, feat12, H1 * W1, n2, nx2, nullptr, 1, 1, w.norm_bound + 3, w.norm_bound + 2}};
+      {feat11, H1 * W1, W1, feat21, H2 * W2, n1, nx1, nullptr, 0, 0, w.norm_bound + 0, w.norm_bound + 1, sh[0], sl[0], sh[1], sl[1]},
+      {feat21, H2 * W2, W2, feat11, H1 * W1, n2, nx2, nullptr, 1, 0, w.norm_bound + 1, w.norm_bound + 0, sh[1], sl[1], sh[0], sl[0]},
+      {feat12, H1 * W1, W1, feat22, H2 * W2, n1, nx1, nullptr, 0, 1, w.norm_bound + 2, w.norm_bound + 3, sh[2], sl[2], sh[3], sl[3]},
+      {feat22, H2 * W2, W2, feat12, H1 * W1, n2, nx2, nullptr, 1, 1, w.norm_bound + 3, w.norm_bound + 2, sh[3], sl[3], sh[2], sl[2]}};
   {
     int rc = run_recip_batch(w, pr, 4, d, subsample, max_iter, cap, impl, stream);
     if (rc) return rc;

@@ -8,6 +8,7 @@ but every call runs hand-written sm_100a kernels through the C ABI of
 libstarst3r_b200.so (include/starst3r_b200.h).  There is no CPU fallback.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -53,6 +54,7 @@ def nn_argmax(Q, DB, impl="auto", return_score=False):
         return (idx, best) if return_score else idx
     if N == 0:
         raise ValueError("nn_argmax: empty database")
+    _apply_variant(lib)        # the workspace size depends on the split-precision switch
     ws = _ws(lib.st3r_nn_argmax_ws_bytes(M, N, d), Q.device)
     with torch.cuda.device(Q.device):
         rc = lib.st3r_nn_argmax(_lib.ptr(Q), M, _lib.ptr(DB), N, d, _lib.ptr(idx), _lib.ptr(best), _lib.ptr(ws),
@@ -285,9 +287,19 @@ class _ExtractPlan:
         self.xy2 = torch.empty((cap, 2), dtype=torch.int64, device=dev)
         self.conf = torch.empty(cap, dtype=torch.float32, device=dev)
         self.n_out = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.ws = _ws(lib.st3r_extract_corres_ws_bytes(H1, W1, H2, W2, subsample, max_iter), dev)
-        self.graphs = {}            # matcher variant (cooperative rare path or not) -> captured graph
+        self.ws_by_split = {}       # split-precision switch -> workspace (the split variant needs tf32 head / tail maps)
+        self.ws = None
+        self.graphs = {}            # matcher variant (cooperative rare path, split precision) -> captured graph
         self.lib, self.dev = lib, dev
+
+    def select(self, variant):
+        """Workspace for the matcher variant `variant` = (cooperative, split) that _apply_variant just switched on."""
+        split = variant[1]
+        if split not in self.ws_by_split:
+            H1, W1, H2, W2, d, subsample, impl, max_iter = self.key
+            self.ws_by_split[split] = _ws(self.lib.st3r_extract_corres_ws_bytes(H1, W1, H2, W2, subsample, max_iter),
+                                          self.dev)
+        self.ws = self.ws_by_split[split]
 
     def _launch(self):
         H1, W1, H2, W2, d, subsample, impl, max_iter = self.key
@@ -305,6 +317,7 @@ class _ExtractPlan:
                 if dst.data_ptr() != src.data_ptr():
                     dst.copy_(src, non_blocking=True)
             coop = _apply_variant(self.lib)
+            self.select(coop)
             if coop not in self.graphs:
                 self._launch()                      # eager warm-up (sets kernel attributes, loads modules)
                 torch.cuda.current_stream().synchronize()
@@ -324,13 +337,19 @@ USE_CUDA_GRAPHS = True
 # variant; smooth descriptor fields (real MASt3R maps) resolve ~once per row and DB range and run the warp-cooperative
 # one (2x faster there, ~14 % slower on random data).  True / False pin it.  Results are identical either way.
 NN_COOPERATIVE = "auto"
+# Split-precision variant of the tcgen05 matcher (st3r_nn_tc_set_split): 3 x TF32 products per score, ~40x narrower
+# exact-re-score band; meant for smooth descriptor fields.  Off by default: written after the round's GPU budget was
+# spent, not measured yet (tests/test_experimental_gpu.py).  ST3R_NN_SPLIT=1 in the environment switches it on.
+NN_SPLIT = os.environ.get("ST3R_NN_SPLIT", "0") == "1"
 _variant = {"on": False}
 
 
 def _apply_variant(lib):
+    """Selects the matcher variant for the next launches; returns the key (cooperative, split) it stands for."""
     on = _variant["on"] if NN_COOPERATIVE == "auto" else bool(NN_COOPERATIVE)
     lib.st3r_nn_tc_set_cooperative(int(on))
-    return on
+    lib.st3r_nn_tc_set_split(int(bool(NN_SPLIT)))
+    return (on, bool(NN_SPLIT))
 
 
 def _adapt_variant(lib):
@@ -369,7 +388,7 @@ def extract_correspondences_device(feats, qonfs, subsample=8, impl="auto", max_i
         for dst, src in zip(plan.feats + plan.qonfs, list(feats) + list(qonfs)):
             dst.copy_(src, non_blocking=True)
         with torch.cuda.device(dev):
-            _apply_variant(lib)
+            plan.select(_apply_variant(lib))
             plan._launch()
         return plan.xy1, plan.xy2, plan.conf, plan.n_out
     return plan.run([x.float() for x in feats], [x.float() for x in qonfs])
