@@ -287,9 +287,250 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
   }
 }
 
+
+// ---- variant 1 of the backward: per-warp record queues ----------------------------------------------------------
+// With the reference's 3e-3 initial scale a Gaussian covers ~12 pixels, so a (warp, Gaussian) visit of the kernel
+// above has ~3 of 32 lanes with a contribution, yet all lanes run the gradient arithmetic and the nine-value
+// butterfly (~100 of the ~125 instructions of a visit; ncu: 79 % issue-slot utilisation, i.e. the kernel is bound by
+// exactly these instructions).  Here the pixel-parallel pass only does what is sequential per pixel - the
+// transmittance, the colour behind, dL/dalpha - and every contributing lane appends a 12-byte record
+// (Gaussian slot, pixel lane, alpha T, vis dL/dalpha) to its warp's queue in shared memory.  The warp drains the
+// queue 32 records at a time with ALL lanes busy: one record per lane, the nine gradient terms, a segmented
+// suffix sum over equal Gaussian slots (records are appended in visit order, so equal slots are adjacent), and one
+// shared-memory update per segment head.  Visits with many contributing lanes (large splats: the log-normal scale
+// sweep) keep the direct butterfly, which is the efficient shape for them.
+constexpr int QW = 160;          // records per warp queue
+constexpr int DENSE_MIN = 12;    // visits with at least this many contributing lanes reduce directly
+
+// Warp-collective: reduces g[0..8] over the warp and adds the totals to a9[0..8] (shared memory).
+__device__ __forceinline__ void butterfly9_to_shared(const float* g, float* a9) {
+  const unsigned full = 0xffffffffu;
+  const int lane = lane_id();
+  float a[4], b2[2], c1;
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float send = h16 ? g[k] : g[k + 4];
+    float keep = h16 ? g[k + 4] : g[k];
+    a[k] = keep + __shfl_xor_sync(full, send, 16);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    float send = h8 ? a[k] : a[k + 2];
+    float keep = h8 ? a[k + 2] : a[k];
+    b2[k] = keep + __shfl_xor_sync(full, send, 8);
+  }
+  {
+    float send = h4 ? b2[0] : b2[1];
+    float keep = h4 ? b2[1] : b2[0];
+    c1 = keep + __shfl_xor_sync(full, send, 4);
+  }
+  c1 += __shfl_xor_sync(full, c1, 2);
+  c1 += __shfl_xor_sync(full, c1, 1);
+  const float g8 = warp_sum(g[8]);
+  const int vi = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
+  const bool ninth = lane == 1;
+  const float sum = ninth ? g8 : c1;
+  if (((lane & 3) == 0 || ninth) && sum != 0.f) atomicAdd(a9 + (ninth ? 8 : vi), sum);
+}
+
+// The nine gradient terms of one (pixel, Gaussian) contribution from fac = alpha T and w = vis dL/dalpha (w = 0 when
+// alpha was clamped to ALPHA_MAX): xy 2, opacity 1, conic 3, rgb 3 - same expressions as in raster_bwd_kernel.
+__device__ __forceinline__ void blend_grad_terms(const float4 A, const float4 B, float dx, float dy, float fac, float w,
+                                                 float vr, float vg, float vb, float* g) {
+  const float v_sigma = -A.z * w;
+  g[0] = v_sigma * (B.x * dx + B.y * dy);
+  g[1] = v_sigma * (B.y * dx + B.z * dy);
+  g[2] = w;
+  g[3] = 0.5f * v_sigma * dx * dx;
+  g[4] = v_sigma * dx * dy;
+  g[5] = 0.5f * v_sigma * dy * dy;
+  g[6] = fac * vr; g[7] = fac * vg; g[8] = fac * vb;
+}
+
+// Warp-collective drain of n queued records (see above).  px0 / py0: centre of the warp's first pixel.
+__device__ __forceinline__ void drain_queue(int n, const uint32_t* qk, const float* qf, const float* qv,
+                                            const float4* sA, const float4* sB, float (*acc)[9], float vr, float vg,
+                                            float vb, float px0, float py0) {
+  const unsigned full = 0xffffffffu;
+  const int lane = lane_id();
+  __syncwarp();                       // the records were written by other lanes
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    const bool have = i < n;
+    const uint32_t key = have ? qk[i] : 0xffffffe0u + (uint32_t)lane;   // padding: one-lane segments of zeros
+    const uint32_t t = key >> 5;
+    const int pl = (int)(key & 31u);
+    const float fac = have ? qf[i] : 0.f, w = have ? qv[i] : 0.f;
+    const float pvr = __shfl_sync(full, vr, pl), pvg = __shfl_sync(full, vg, pl), pvb = __shfl_sync(full, vb, pl);
+    float g[9];
+    if (have) {
+      const float4 A = sA[t], B = sB[t];
+      blend_grad_terms(A, B, A.x - (px0 + (float)(pl & 15)), A.y - (py0 + (float)(pl >> 4)), fac, w, pvr, pvg, pvb, g);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) g[k] = 0.f;
+    }
+    // segmented suffix sums: equal slots are adjacent, so "the lane `off` further carries my slot" implies that every
+    // lane in between does
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t tk = __shfl_down_sync(full, t, off);
+      const bool same = (lane + off < 32) && tk == t;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const float v = __shfl_down_sync(full, g[k], off);
+        if (same) g[k] += v;
+      }
+    }
+    const uint32_t tprev = __shfl_up_sync(full, t, 1);
+    if (have && (lane == 0 || tprev != t)) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        if (g[k] != 0.f) atomicAdd(&acc[t][k], g[k]);
+    }
+  }
+  __syncwarp();                       // the queue may be overwritten from here on
+}
+
+__global__ void __launch_bounds__(BLOCK)
+raster_bwd_queue_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
+                        const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
+                        const float4* __restrict__ geomB, const float4* __restrict__ rgb, int C, int W, int H,
+                        int tile_w, int tile_h, const float* __restrict__ alphas, const int32_t* __restrict__ last_ids,
+                        const float* __restrict__ v_render, const float* __restrict__ v_alphas,
+                        float4* __restrict__ v_geomA, float4* __restrict__ v_geomB, float4* __restrict__ v_rgb) {
+  __shared__ float4 sA[BLOCK], sB[BLOCK], sC[BLOCK];
+  __shared__ uint32_t sE[BLOCK];
+  __shared__ uint32_t sL[8][8];
+  __shared__ float acc[BLOCK][9];
+  __shared__ uint32_t qkey[8][QW];
+  __shared__ float qfac[8][QW], qvis[8][QW];
+  const int c = blockIdx.y, tile = blockIdx.x;
+  const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
+  const int tr = threadIdx.x;
+  const int i = tyi * TILE + (tr >> 4), j = txi * TILE + (tr & 15);
+  const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+  const bool inside = i < H && j < W;
+  const int wrp = tr >> 5, lane = tr & 31;
+  const float px0 = (float)(txi * TILE) + 0.5f, py0 = (float)(tyi * TILE + 2 * wrp) + 0.5f;
+  const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
+  if (rg.hi <= rg.lo) return;
+  const size_t p = ((size_t)c * H + min(i, H - 1)) * W + min(j, W - 1);
+  const float T_final = 1.0f - alphas[p];
+  float T = T_final;
+  float br = 0.f, bg = 0.f, bb = 0.f;
+  const int bin_final = inside ? last_ids[p] : 0;
+  float vr = 0.f, vg = 0.f, vb = 0.f, va = 0.f;
+  if (inside) {
+    vr = v_render[3 * p]; vg = v_render[3 * p + 1]; vb = v_render[3 * p + 2];
+    va = v_alphas ? v_alphas[p] : 0.f;
+  }
+  int warp_bin_final = bin_final;
+  for (int off = 16; off; off >>= 1) warp_bin_final = max(warp_bin_final, __shfl_xor_sync(0xffffffffu, warp_bin_final, off));
+  const uint32_t lanes_below = (1u << lane) - 1u;
+  uint32_t* qk = qkey[wrp];
+  float* qf = qfac[wrp];
+  float* qv = qvis[wrp];
+
+  const int nb = (rg.hi - rg.lo + BLOCK - 1) / BLOCK;
+  for (int b = 0; b < nb; ++b) {
+    __syncthreads();
+    const int batch_end = rg.hi - 1 - BLOCK * b;
+    const int bs = min(BLOCK, batch_end + 1 - rg.lo);
+    const int idx = batch_end - tr;
+    uint32_t m = 0;
+    if (idx >= rg.lo) {
+      uint32_t e = flatten[idx];
+      const float4 A = geomA[e], B = geomB[e];
+      sE[tr] = e;
+      sA[tr] = A;
+      sB[tr] = B;
+      sC[tr] = rgb[e];
+      m = row_mask(A, B, tyi * TILE);
+    }
+    publish_visit_lists(m, sL);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[tr][k] = 0.f;
+    __syncthreads();
+    int qlen = 0;                       // warp-uniform
+    const int t0 = max(0, batch_end - warp_bin_final);
+    for (int wi = t0 >> 5; wi < 8; ++wi) {
+      uint32_t bits = sL[wrp][wi];
+      if (wi == (t0 >> 5)) bits &= 0xffffffffu << (t0 & 31);
+      while (bits) {
+        const int t = wi * 32 + __ffs(bits) - 1;
+        bits &= bits - 1;
+        bool valid = inside && (batch_end - t <= bin_final);
+        float alpha = 0.f, opac = 0.f, vis = 0.f, dx = 0.f, dy = 0.f;
+        if (valid) {
+          const float4 A = sA[t], B = sB[t];
+          opac = A.z;
+          dx = A.x - px; dy = A.y - py;
+          const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
+          vis = __expf(-sigma);
+          alpha = fminf(ALPHA_MAX, opac * vis);
+          if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
+        }
+        const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+        if (!vm) continue;
+        float fac = 0.f, w = 0.f;
+        if (valid) {                    // the part that is sequential per pixel
+          const float ra = 1.0f / (1.0f - alpha);
+          T *= ra;
+          fac = alpha * T;
+          const float4 col = sC[t];
+          float v_alpha = (col.x * T - br * ra) * vr + (col.y * T - bg * ra) * vg + (col.z * T - bb * ra) * vb;
+          v_alpha += T_final * ra * va;
+          if (opac * vis <= ALPHA_MAX) w = vis * v_alpha;
+          br += col.x * fac; bg += col.y * fac; bb += col.z * fac;
+        }
+        const int nv = __popc(vm);
+        if (nv >= DENSE_MIN) {
+          float g[9];
+          blend_grad_terms(sA[t], sB[t], dx, dy, fac, w, vr, vg, vb, g);   // fac = w = 0 on the other lanes
+          butterfly9_to_shared(g, acc[t]);
+        } else {
+          if (qlen + nv > QW) {
+            drain_queue(qlen, qk, qf, qv, sA, sB, acc, vr, vg, vb, px0, py0);
+            qlen = 0;
+          }
+          if (valid) {
+            const int pos = qlen + __popc(vm & lanes_below);
+            qk[pos] = ((uint32_t)t << 5) | (uint32_t)lane;
+            qf[pos] = fac;
+            qv[pos] = w;
+          }
+          qlen += nv;
+        }
+      }
+    }
+    drain_queue(qlen, qk, qf, qv, sA, sB, acc, vr, vg, vb, px0, py0);
+    __syncthreads();
+    if (tr < bs) {
+      const uint32_t e = sE[tr];
+      const float* a = acc[tr];
+      if (a[0] != 0.f || a[1] != 0.f || a[2] != 0.f || a[3] != 0.f || a[4] != 0.f || a[5] != 0.f || a[6] != 0.f ||
+          a[7] != 0.f || a[8] != 0.f) {
+        atomicAdd(v_geomA + e, make_float4(a[0], a[1], a[2], 0.f));
+        atomicAdd(v_geomB + e, make_float4(a[3], a[4], a[5], 0.f));
+        atomicAdd(v_rgb + e, make_float4(a[6], a[7], a[8], 0.f));
+      }
+    }
+  }
+}
+
 }  // namespace
 
+static int g_raster_bwd_variant = 0;   // 0: per-visit butterfly (default), 1: per-warp record queues
+
 extern "C" {
+
+int st3r_gs_set_raster_variant(int variant) {
+  ST3R_CHECK_ARG(variant == 0 || variant == 1, "st3r_gs_set_raster_variant: unknown variant %d", variant);
+  g_raster_bwd_variant = variant;
+  return ST3R_OK;
+}
 
 int st3r_gs_raster_fwd(const int32_t* offsets, const int32_t* n_isect, const uint32_t* flatten_ids,
                        const float* geomA, const float* geomB, const float* rgb, int C, int width, int height,
@@ -322,10 +563,16 @@ int st3r_gs_raster_bwd(const int32_t* offsets, const int32_t* n_isect, const uin
                  "st3r_gs_raster_bwd: null pointer");
   const int tile_w = (width + TILE - 1) / TILE, tile_h = (height + TILE - 1) / TILE;
   dim3 grid(tile_w * tile_h, C);
-  raster_bwd_kernel<<<grid, BLOCK, 0, stream>>>(
-      offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
-      reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, alphas, last_ids, v_render, v_alphas,
-      reinterpret_cast<float4*>(v_geomA), reinterpret_cast<float4*>(v_geomB), reinterpret_cast<float4*>(v_rgb));
+  if (g_raster_bwd_variant == 1)
+    raster_bwd_queue_kernel<<<grid, BLOCK, 0, stream>>>(
+        offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
+        reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, alphas, last_ids, v_render, v_alphas,
+        reinterpret_cast<float4*>(v_geomA), reinterpret_cast<float4*>(v_geomB), reinterpret_cast<float4*>(v_rgb));
+  else
+    raster_bwd_kernel<<<grid, BLOCK, 0, stream>>>(
+        offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
+        reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, alphas, last_ids, v_render, v_alphas,
+        reinterpret_cast<float4*>(v_geomA), reinterpret_cast<float4*>(v_geomB), reinterpret_cast<float4*>(v_rgb));
   ST3R_CHECK_LAUNCH();
   return ST3R_OK;
 }

@@ -8,6 +8,7 @@ no CPU fallback.  PyTorch only owns the memory and the stream.
 """
 import ctypes
 import math
+import os
 
 import torch
 from tqdm import trange
@@ -22,6 +23,9 @@ TILE = 16
 # st3r_gs_isect -> st3r_radix_sort_pairs -> st3r_gs_offsets chain.  Both produce identical arrays.
 BINNING = "fused"
 EPS2D, NEAR, FAR, RADIUS_CLIP = 0.3, 0.01, 1e10, 0.0
+# Variant of the blend backward kernel (st3r_gs_set_raster_variant): 0 = per-visit warp reduction (every committed
+# measurement), 1 = per-warp record queues (written without GPU time; tests/test_experimental_gpu.py).
+RASTER_BWD_VARIANT = int(os.environ.get("ST3R_RASTER_VARIANT", "0"))
 
 
 class _Prof:
@@ -289,6 +293,7 @@ def _backward(fr, means, quats, scales, opacities, shN, v_render, v_alphas, reg_
         v_opac = torch.empty((N,), dtype=torch.float32, device=dev)
         v_sh = torch.empty((N, 4, 3), dtype=torch.float32, device=dev)
     st = _lib.stream_ptr()
+    _lib.check(lib.st3r_gs_set_raster_variant(int(RASTER_BWD_VARIANT)), "st3r_gs_set_raster_variant")
     with torch.cuda.device(dev):
         with _Prof("st3r_gs_raster_bwd"):
             _lib.check(lib.st3r_gs_raster_bwd(_lib.ptr(fr.offsets), _lib.ptr(fr.n_isect_dev), _lib.ptr(fr.vals),
