@@ -355,7 +355,9 @@ __device__ __forceinline__ void drain_queue(int n, const uint32_t* qk, const flo
   const unsigned full = 0xffffffffu;
   const int lane = lane_id();
   __syncwarp();                       // the records were written by other lanes
-  for (int base = 0; base < n; base += 32) {
+#pragma unroll 1
+  for (int base = 0; base < QW; base += 32) {
+    if (!__any_sync(full, base < n)) break;      // n is warp-uniform; the vote says so to the compiler
     const int i = base + lane;
     const bool have = i < n;
     const uint32_t key = have ? qk[i] : 0xffffffe0u + (uint32_t)lane;   // padding: one-lane segments of zeros
@@ -426,8 +428,7 @@ raster_bwd_queue_kernel(const int32_t* __restrict__ offsets, const int32_t* __re
     vr = v_render[3 * p]; vg = v_render[3 * p + 1]; vb = v_render[3 * p + 2];
     va = v_alphas ? v_alphas[p] : 0.f;
   }
-  int warp_bin_final = bin_final;
-  for (int off = 16; off; off >>= 1) warp_bin_final = max(warp_bin_final, __shfl_xor_sync(0xffffffffu, warp_bin_final, off));
+  const int warp_bin_final = __reduce_max_sync(0xffffffffu, bin_final);
   const uint32_t lanes_below = (1u << lane) - 1u;
   uint32_t* qk = qkey[wrp];
   float* qf = qfac[wrp];
@@ -456,7 +457,8 @@ raster_bwd_queue_kernel(const int32_t* __restrict__ offsets, const int32_t* __re
     int qlen = 0;                       // warp-uniform
     const int t0 = max(0, batch_end - warp_bin_final);
     for (int wi = t0 >> 5; wi < 8; ++wi) {
-      uint32_t bits = sL[wrp][wi];
+      // redux.sync returns the same word in a form the compiler knows to be warp-uniform (see the votes below)
+      uint32_t bits = __reduce_or_sync(0xffffffffu, sL[wrp][wi]);
       if (wi == (t0 >> 5)) bits &= 0xffffffffu << (t0 & 31);
       while (bits) {
         const int t = wi * 32 + __ffs(bits) - 1;
@@ -486,12 +488,14 @@ raster_bwd_queue_kernel(const int32_t* __restrict__ offsets, const int32_t* __re
           br += col.x * fac; bg += col.y * fac; bb += col.z * fac;
         }
         const int nv = __popc(vm);
-        if (nv >= DENSE_MIN) {
+        // (the votes only restate warp-uniform conditions in a form the compiler's divergence analysis accepts, so
+        // that the shuffles below are not wrapped in WARPSYNC / ENDCOLLECTIVE pairs)
+        if (__any_sync(0xffffffffu, nv >= DENSE_MIN)) {
           float g[9];
           blend_grad_terms(sA[t], sB[t], dx, dy, fac, w, vr, vg, vb, g);   // fac = w = 0 on the other lanes
           butterfly9_to_shared(g, acc[t]);
         } else {
-          if (qlen + nv > QW) {
+          if (__any_sync(0xffffffffu, qlen + nv > QW)) {
             drain_queue(qlen, qk, qf, qv, sA, sB, acc, vr, vg, vb, px0, py0);
             qlen = 0;
           }
