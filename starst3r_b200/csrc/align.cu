@@ -344,13 +344,19 @@ __device__ __forceinline__ float seg_eval(const St3rAlignProblem& pb, const Work
 // Warp-wide sum of a lane-private gradient record into the CTA table; the record restarts at zero.
 __device__ __forceinline__ void seg_flush(float* table, int img, float* acc) {
   if (img < 0) return;   // warp-uniform
+  // All shuffles first, then ONE shared-memory update pass by 17 lanes: a compare-and-swap loop between two shuffles
+  // would make the compiler wrap every later shuffle in a WARPSYNC / ENDCOLLECTIVE pair.
+  const int lane = lane_id();
+  float mine = 0.f;
 #pragma unroll
   for (int k = 0; k < NG; ++k) {
     float v = acc[k];
+#pragma unroll
     for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (lane_id() == 0 && v != 0.f) atomicAdd(table + img * NG + k, v);
+    if (lane == k) mine = v;
     acc[k] = 0.f;
   }
+  if (lane < NG && mine != 0.f) atomicAdd(table + img * NG + lane, mine);
 }
 
 template <int KIND>
@@ -366,7 +372,10 @@ align_loss_seg_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, fl
   const int n = KIND == 0 ? pb.n3 : (KIND == 1 ? pb.n2 : pb.nd);
   const int lane = lane_id();
   const long long wbeg = ((long long)blockIdx.x * (LOSS_THREADS / 32) + (threadIdx.x >> 5)) * per_warp;
-  const int begin = (int)(wbeg < n ? wbeg : n), end = (int)(wbeg + per_warp < n ? wbeg + per_warp : n);
+  // redux.sync / votes return warp-uniform values in a form the compiler's divergence analysis accepts, so the
+  // shuffles of seg_flush below are not wrapped in WARPSYNC / ENDCOLLECTIVE pairs
+  const int begin = __reduce_max_sync(0xffffffffu, (int)(wbeg < n ? wbeg : n));
+  const int end = __reduce_max_sync(0xffffffffu, (int)(wbeg + per_warp < n ? wbeg + per_warp : n));
   float acc1[NG], acc2[NG];
 #pragma unroll
   for (int k = 0; k < NG; ++k) acc1[k] = acc2[k] = 0.f;
@@ -379,7 +388,7 @@ align_loss_seg_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, fl
     e.i1 = e.i2 = -1;
     if (active) seg_load<KIND>(pb, ic, m, e);
     const int key = active ? ((e.i1 << 16) | e.i2) : -1;        // n_img < 2^15 (the shared table caps it far lower)
-    const int first = __shfl_sync(0xffffffffu, key, 0);         // lane 0 is active in every row
+    const int first = __reduce_max_sync(0xffffffffu, key);      // the common key when the row is uniform (keys >= 0)
     const bool uniform = __all_sync(0xffffffffu, !active || key == first);
     if (uniform) {
       const int f1 = first >> 16, f2 = first & 0xffff;
