@@ -27,12 +27,3 @@ done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:nn_tc_kernel --launch-skip 1 -c 1 -f -o $OUT/${TAG}_prof_nn_tc_M4096 \
     python scripts/prof_nn.py tcgen05 4096 > $OUT/ncu_nn_tc.log 2>&1
 ls -la $OUT
-
-# Opt-in kernel variants: parity first, then A/B timings.  bash scripts/gpu_round.sh <tag> variants
-if [ "${2:-}" = "variants" ]; then
-  echo "== experimental parity tests"
-  ST3R_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_experimental_gpu.py -m gpu -q 2>&1 | tail -25 | tee $OUT/${TAG}_pytest_experimental.txt
-  echo "== variant A/B"
-  timeout 900 python scripts/bench_variants.py > $OUT/${TAG}_variants.json 2> $OUT/${TAG}_variants.err
-  cat $OUT/${TAG}_variants.json; tail -5 $OUT/${TAG}_variants.err
-fi
