@@ -567,15 +567,15 @@ int st3r_align_optimize(const St3rAlignProblem* prob, float* pp, float* log_foca
   const int N = pb.n_img;
   const size_t table_bytes = (size_t)N * NG * sizeof(float);
   ST3R_CHECK_ARG(table_bytes <= 96 * 1024, "st3r_align_optimize: too many images for the shared-memory gradient table");
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (!attr.done()) {
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(align_loss3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(align_loss2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(align_lossd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(align_loss_seg_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(align_loss_seg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(align_loss_seg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
+    attr.mark();
   }
   Work w = carve(ws, N);
   Params p{pp, log_focal, quat, trans, log_size};

@@ -69,3 +69,16 @@ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
 }
 
 int st3r_num_sms();
+
+// "Has this call site already configured its kernels on the CURRENT device?"  Function attributes
+// (cudaFuncSetAttribute) belong to a device's context, so a process that works on two GPUs has to set them on both.
+struct PerDeviceOnce {
+  unsigned long long seen = 0;
+  static unsigned long long bit() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return 1ull << (d & 63);
+  }
+  bool done() const { return (seen & bit()) != 0; }
+  void mark() { seen |= bit(); }
+};

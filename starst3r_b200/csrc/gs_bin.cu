@@ -261,11 +261,11 @@ int st3r_gs_bin_tiles(const int32_t* radii, const float* geomA, int N, int C, in
   const int use_smem = n_tiles <= MAX_SMEM_TILES ? 1 : 0;
   const dim3 grid((N + ENTRIES_PER_CTA - 1) / ENTRIES_PER_CTA, C);
   const size_t sm_hist = use_smem ? sizeof(int32_t) * (size_t)n_tiles : 0, sm_emit = 2 * sm_hist;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (!attr_set.done()) {
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(tile_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(2 * sizeof(int32_t) * MAX_SMEM_TILES)));
-    attr_set = true;
+    attr_set.mark();
   }
   tile_hist_kernel<<<grid, BIN_THREADS, sm_hist, stream>>>(radii, gA, N, tile_size, tile_w, tile_h, w.counts, use_smem);
   ST3R_CHECK_LAUNCH();

@@ -241,10 +241,10 @@ __global__ void loss_finalize_kernel(const float* __restrict__ sums, const float
   *out = acc;
 }
 
-bool g_win_set = false;
+PerDeviceOnce g_win_set;   // __constant__ memory is per device
 
 int set_window() {
-  if (g_win_set) return ST3R_OK;
+  if (g_win_set.done()) return ST3R_OK;
   float g[11], s = 0.f;
   for (int k = 0; k < 11; ++k) {
     float d = (float)(k - 5);
@@ -253,7 +253,7 @@ int set_window() {
   }
   for (int k = 0; k < 11; ++k) g[k] /= s;
   ST3R_CHECK_CUDA(cudaMemcpyToSymbol(c_win, g, sizeof(g)));
-  g_win_set = true;
+  g_win_set.mark();
   return ST3R_OK;
 }
 
@@ -273,10 +273,10 @@ int st3r_gs_loss_fwd(const float* render, const float* truth, int C, int height,
   float coef = -ssim_fac / (3.0f * (float)(height - 10) * (float)(width - 10));
   dim3 grid((width + LT - 1) / LT, (height + LT - 1) / LT, C);
   constexpr size_t kSmemFwd = sizeof(float) * (6 * LW * LWP + 5 * LW * HSP);
-  static bool attr_fwd = false;
-  if (!attr_fwd) {
+  static PerDeviceOnce attr_fwd;
+  if (!attr_fwd.done()) {
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(ssim_l1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFwd));
-    attr_fwd = true;
+    attr_fwd.mark();
   }
   ssim_l1_fwd_kernel<<<grid, NT, kSmemFwd, stream>>>(render, truth, height, width, coef, dmaps, sums);
   ST3R_CHECK_LAUNCH();

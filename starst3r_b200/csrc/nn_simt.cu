@@ -189,11 +189,11 @@ template <int D>
 int launch_simt(const float* Q, const int32_t* qidx, const int32_t* count_ptr, int Mmax,
                 const float* DB, int N, unsigned long long* packed, cudaStream_t stream) {
   using Cfg = SimtCfg<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (!attr_set.done()) {
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_simt_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::SMEM));
-    attr_set = true;
+    attr_set.mark();
   }
   const int sms = st3r_num_sms();
   const int mtiles = (Mmax + TM - 1) / TM;

@@ -846,13 +846,13 @@ int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stre
   }
   if (m == 0) return ST3R_OK;
   for (int i = m; i < NN_MAX_BATCH; ++i) { prm.tmap[i] = prm.tmap[0]; prm.tmap_lo[i] = prm.tmap_lo[0]; prm.it[i] = prm.it[0]; }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (!attr_set.done()) {
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<false>::SMEM_DYN));
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<false>::SMEM_DYN));
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<true>::SMEM_DYN));
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(nn_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<true>::SMEM_DYN));
-    attr_set = true;
+    attr_set.mark();
   }
   auto launch = [&](dim3 grid, const NnTcParams& q) {
     if (split) {
