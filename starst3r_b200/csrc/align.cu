@@ -392,7 +392,7 @@ align_loss_seg_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, fl
     const bool uniform = __all_sync(0xffffffffu, !active || key == first);
     if (uniform) {
       const int f1 = first >> 16, f2 = first & 0xffff;
-      if (f1 != cur1 || f2 != cur2) {
+      if (__any_sync(0xffffffffu, f1 != cur1 || f2 != cur2)) {   // warp-uniform; the vote tells the compiler
         seg_flush(table, cur1, acc1);
         seg_flush(table, cur2, acc2);
         cur1 = f1; cur2 = f2;
