@@ -382,28 +382,29 @@ align_loss_seg_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, fl
   int cur1 = -1, cur2 = -1;      // image pair whose gradients acc1 / acc2 hold (warp-uniform)
   float loss = 0.f;
   for (int base = begin; base < end; base += 32) {
-    const int m = base + lane;
-    const bool active = m < end;
+    // Lanes past the end of the range (last row only) redo the range's last entry with weight zero: the loop body has
+    // no lane-dependent branch, so the warp provably stays converged for the shuffles of seg_flush.
+    const bool active = base + lane < end;
+    const int m = active ? base + lane : end - 1;
+    const float sc = active ? scale : 0.f;
     SegEntry<KIND> e;
-    e.i1 = e.i2 = -1;
-    if (active) seg_load<KIND>(pb, ic, m, e);
-    const int key = active ? ((e.i1 << 16) | e.i2) : -1;        // n_img < 2^15 (the shared table caps it far lower)
-    const int first = __reduce_max_sync(0xffffffffu, key);      // the common key when the row is uniform (keys >= 0)
-    const bool uniform = __all_sync(0xffffffffu, !active || key == first);
-    if (uniform) {
+    seg_load<KIND>(pb, ic, m, e);
+    const int key = (e.i1 << 16) | e.i2;                        // n_img < 2^15 (the shared table caps it far lower)
+    const int first = __reduce_max_sync(0xffffffffu, key);      // the common key when the row is uniform
+    if (__all_sync(0xffffffffu, key == first)) {
       const int f1 = first >> 16, f2 = first & 0xffff;
       if (__any_sync(0xffffffffu, f1 != cur1 || f2 != cur2)) {   // warp-uniform; the vote tells the compiler
         seg_flush(table, cur1, acc1);
         seg_flush(table, cur2, acc2);
         cur1 = f1; cur2 = f2;
       }
-      if (active) loss += seg_eval<KIND>(pb, w, m, e, gamma, offset, off_pow, scale, acc1, acc2);
+      loss += seg_eval<KIND>(pb, w, m, e, gamma, offset, off_pow, sc, acc1, acc2);
     } else {
       // a row that straddles two image pairs: per-row reduction like variant 0
       float g1[NG], g2[NG];
 #pragma unroll
       for (int k = 0; k < NG; ++k) g1[k] = g2[k] = 0.f;
-      if (active) loss += seg_eval<KIND>(pb, w, m, e, gamma, offset, off_pow, scale, g1, g2);
+      loss += seg_eval<KIND>(pb, w, m, e, gamma, offset, off_pow, sc, g1, g2);
       accum_image(table, e.i1, active, g1);
       accum_image(table, e.i2, active, g2);
     }
