@@ -2,7 +2,8 @@
 
 The reference is single-device; sharding is new capability:
   * MATCH: unordered image pairs are independent (sparse_ga.py:529 loop body) -> pair p goes to rank p mod G; the
-    only communication is the final gather of the variable-length correspondence lists.
+    only communication is the exchange of the per-pair results afterwards (reconstruct.forward_mast3r does this
+    under an initialised process group: reconstruct.SHARD_PAIRS).
   * RASTER training: camera views are sharded, the splat is replicated; per step ONE all-reduce (sum) of the
     per-Gaussian gradients (23 floats per Gaussian), then every rank applies the same Adam update.
   * ALIGN: replicas only (O(11 N) parameters, strictly sequential iterations): rank 0 computes, result is broadcast.

@@ -387,6 +387,92 @@ def symmetric_inference(model, img1, img2, device):
     return res11, res21, res22, res12
 
 
+def _pair_missing(memo, a, b):
+    return not ((a, b) in memo["fwd"] and (b, a) in memo["fwd"] and (a, b) in memo["corres"])
+
+
+def _compute_pair(memo, model, img1, img2, device, desc_conf, subsample):
+    """Inference + matching of one unordered image pair (sparse_ga.py:541-561); fills the memo."""
+    a, b = img1["instance"], img2["instance"]
+    res = symmetric_inference(model, img1, img2, device)
+    X11, X21, X22, X12 = [r["pts3d"][0].to(device).float().contiguous() for r in res]
+    C11, C21, C22, C12 = [r["conf"][0].to(device).float().contiguous() for r in res]
+    descs = [r["desc"][0].to(device) for r in res]
+    qonfs = [r[desc_conf][0].to(device) for r in res]
+    memo["fwd"][a, b] = (X11, C11, X21, C21)
+    memo["fwd"][b, a] = (X22, C22, X12, C12)
+    corres = match.extract_correspondences(descs, qonfs, device=device, subsample=subsample)
+    conf_score = (C11.mean() * C12.mean() * C21.mean() * C22.mean()).sqrt().sqrt()
+    memo["corres"][a, b] = ((float(conf_score), float(corres[2].sum()), len(corres[2])), corres)
+
+
+# Under an initialised torch.distributed group (one process per GPU) forward_mast3r computes only every G-th missing
+# pair on this rank - image pairs are independent (sparse_ga.py:529 loop body, SURVEY §8e) - and every pair's result
+# is broadcast from its owner, so that all ranks continue with the full memo (the alignment that follows runs as
+# replicas).  No collective touches the matching itself.  At BASELINE configs[3] sizes the replicated point maps no
+# longer fit one GPU; ownership by image (each rank keeps the maps of its images' canonical views) is the next step.
+SHARD_PAIRS = True
+
+
+def _exchange_pair(memo, a, b, owner, rank, device):
+    """Broadcast of one computed pair from its owner: a header (scores, n, map sizes), the eight maps as one flat fp32
+    tensor and the correspondence list."""
+    import torch.distributed as dist
+    head = torch.zeros(7, dtype=torch.float64, device=device)
+    if rank == owner:
+        score, (xy1, xy2, conf) = memo["corres"][a, b]
+        X11, _, X21, _ = memo["fwd"][a, b]
+        head = torch.tensor([score[0], score[1], float(score[2]), X11.shape[0], X11.shape[1], X21.shape[0], X21.shape[1]],
+                            dtype=torch.float64, device=device)
+        maps = torch.cat([t.reshape(-1) for t in memo["fwd"][a, b] + memo["fwd"][b, a]]).float().contiguous()
+    dist.broadcast(head, owner)
+    n, H1, W1, H2, W2 = (int(v) for v in head[2:].tolist())
+    sizes = [3 * H1 * W1, H1 * W1, 3 * H2 * W2, H2 * W2, 3 * H2 * W2, H2 * W2, 3 * H1 * W1, H1 * W1]
+    if rank != owner:
+        maps = torch.empty(sum(sizes), dtype=torch.float32, device=device)
+        xy1 = torch.empty((n, 2), dtype=torch.int64, device=device)
+        xy2 = torch.empty((n, 2), dtype=torch.int64, device=device)
+        conf = torch.empty(n, dtype=torch.float32, device=device)
+    xy = torch.cat([xy1.reshape(-1, 2), xy2.reshape(-1, 2)], dim=1).contiguous()        # [n, 4]
+    conf = conf.contiguous()
+    dist.broadcast(maps, owner)
+    if n > 0:                                   # (no zero-length collectives)
+        dist.broadcast(xy, owner)
+        dist.broadcast(conf, owner)
+    if rank != owner:
+        parts = torch.split(maps, sizes)
+        X11, C11, X21, C21 = parts[0].view(H1, W1, 3), parts[1].view(H1, W1), parts[2].view(H2, W2, 3), parts[3].view(H2, W2)
+        X22, C22, X12, C12 = parts[4].view(H2, W2, 3), parts[5].view(H2, W2), parts[6].view(H1, W1, 3), parts[7].view(H1, W1)
+        memo["fwd"][a, b] = (X11, C11, X21, C21)
+        memo["fwd"][b, a] = (X22, C22, X12, C12)
+        memo["corres"][a, b] = ((float(head[0]), float(head[1]), n), (xy[:, :2].contiguous(), xy[:, 2:].contiguous(), conf))
+
+
+def _forward_sharded(pairs, memo, model, device, desc_conf, subsample):
+    """Computes this rank's share of the missing pairs and exchanges all of them; returns the number computed here."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    todo, seen = [], set()
+    for k, (img1, img2) in enumerate(pairs):
+        a, b = img1["instance"], img2["instance"]
+        if frozenset((a, b)) not in seen and _pair_missing(memo, a, b) and (b, a) not in memo["corres"]:
+            seen.add(frozenset((a, b)))
+            todo.append(k)
+    box = [todo]
+    dist.broadcast_object_list(box, src=0)        # rank 0's list decides (caches may differ between ranks)
+    todo = box[0]
+    mine = 0
+    for j, k in enumerate(todo):
+        if j % world == rank:
+            img1, img2 = pairs[k]
+            _compute_pair(memo, model, img1, img2, device, desc_conf, subsample)
+            mine += 1
+    for j, k in enumerate(todo):
+        img1, img2 = pairs[k]
+        _exchange_pair(memo, img1["instance"], img2["instance"], j % world, rank, device)
+    return mine
+
+
 @torch.no_grad()
 def forward_mast3r(pairs, model, cache_path, desc_conf="desc_conf", device="cuda", subsample=8, **matching_kw):
     """sparse_ga.py:524-568.  Returns ({(name1, name2): ((key1, key2), key_corres)}, cache_path) where the keys index
@@ -394,32 +480,38 @@ def forward_mast3r(pairs, model, cache_path, desc_conf="desc_conf", device="cuda
     memo = _memo(cache_path)
     res_paths = {}
     fkw = dict(desc_conf=desc_conf, subsample=subsample)
-    for img1, img2 in pairs:
-        a, b = img1["instance"], img2["instance"]
-        if PERSIST_CACHE and cache_path:        # adopt entries another run (or the reference) left on disk
+    if PERSIST_CACHE and cache_path:            # adopt entries another run (or the reference) left on disk
+        for img1, img2 in pairs:
+            a, b = img1["instance"], img2["instance"]
             for key, kind in (((a, b), "fwd"), ((b, a), "fwd"), ((a, b), "corres"), ((b, a), "corres")):
                 store = memo["fwd" if kind == "fwd" else "corres"]
                 if key not in store:
                     got = _disk_get(_cache_file(cache_path, kind, *key, **fkw), device)
                     if got is not None:
                         store[key] = tuple(got) if kind == "fwd" else (tuple(got[0]), tuple(got[1]))
+    sharded = False
+    if SHARD_PAIRS and model is not None:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            before = set(memo["corres"])
+            _forward_sharded(pairs, memo, model, device, desc_conf, subsample)
+            sharded = True
+            if PERSIST_CACHE and cache_path and dist.get_rank() == 0:
+                for (a, b) in set(memo["corres"]) - before:
+                    _disk_put(_cache_file(cache_path, "fwd", a, b), memo["fwd"][a, b])
+                    _disk_put(_cache_file(cache_path, "fwd", b, a), memo["fwd"][b, a])
+                    _disk_put(_cache_file(cache_path, "corres", a, b, **fkw), memo["corres"][a, b])
+    for img1, img2 in pairs:
+        a, b = img1["instance"], img2["instance"]
         if (b, a) in memo["corres"] and (a, b) not in memo["corres"]:
             score, (xy1, xy2, confs) = memo["corres"][b, a]
             memo["corres"][a, b] = (score, (xy2, xy1, confs))                        # :538-540
-            _disk_put(cache_path and _cache_file(cache_path, "corres", a, b, **fkw), memo["corres"][a, b])
-        if not ((a, b) in memo["fwd"] and (b, a) in memo["fwd"] and (a, b) in memo["corres"]):
+            if not sharded or dist.get_rank() == 0:
+                _disk_put(cache_path and _cache_file(cache_path, "corres", a, b, **fkw), memo["corres"][a, b])
+        if _pair_missing(memo, a, b):
             if model is None:
                 continue
-            res = symmetric_inference(model, img1, img2, device)
-            X11, X21, X22, X12 = [r["pts3d"][0].to(device).float().contiguous() for r in res]
-            C11, C21, C22, C12 = [r["conf"][0].to(device).float().contiguous() for r in res]
-            descs = [r["desc"][0].to(device) for r in res]
-            qonfs = [r[desc_conf][0].to(device) for r in res]
-            memo["fwd"][a, b] = (X11, C11, X21, C21)
-            memo["fwd"][b, a] = (X22, C22, X12, C12)
-            corres = match.extract_correspondences(descs, qonfs, device=device, subsample=subsample)
-            conf_score = (C11.mean() * C12.mean() * C21.mean() * C22.mean()).sqrt().sqrt()
-            memo["corres"][a, b] = ((float(conf_score), float(corres[2].sum()), len(corres[2])), corres)
+            _compute_pair(memo, model, img1, img2, device, desc_conf, subsample)
             if PERSIST_CACHE and cache_path:
                 _disk_put(_cache_file(cache_path, "fwd", a, b), memo["fwd"][a, b])
                 _disk_put(_cache_file(cache_path, "fwd", b, a), memo["fwd"][b, a])

@@ -130,3 +130,70 @@ def test_sharded_views_gradient_sum_equals_full_gradient():
     res = [q.get(timeout=300) for _ in procs]
     [p.join(timeout=60) for p in procs]
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def _oracle_extract(descs, qonfs, device=None, subsample=8):
+    """CPU stand-in for match.extract_correspondences (which only runs on CUDA): the oracle restatement."""
+    from oracle import match_oracle as mo
+    xy1, xy2, conf = mo.extract_correspondences([d.cpu().numpy() for d in descs], [q.cpu().numpy() for q in qonfs], subsample)
+    return torch.from_numpy(xy1), torch.from_numpy(xy2), torch.from_numpy(conf)
+
+
+def _pairs_worker(rank, world, port, q):
+    """forward_mast3r under a process group: every rank computes only its share of the image pairs (inference +
+    matching) and ends with the full, identical memo."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from starst3r_b200 import match, synth
+        from starst3r_b200 import reconstruct as rc
+        torch.set_num_threads(1)
+        match.extract_correspondences = _oracle_extract          # test-only: the product path refuses CPU tensors
+        n, W, H = 4, 48, 32
+        net = synth.SyntheticMast3r(n, W, H, seed=0, device="cpu", arc_deg=90.0)
+        calls = []
+        orig = net.symmetric_inference
+        net.symmetric_inference = lambda a, b, device=None: (calls.append((a["idx"], b["idx"])), orig(a, b))[1]
+        imgs = rc.prepare_images_for_mast3r(net.images())
+        names = [f"{i}.png" for i in range(n)]
+
+        def run(tag, shard):
+            rc.SHARD_PAIRS = shard
+            calls.clear()
+            pairs = rc.convert_dust3r_pairs_naming(names, rc.make_pairs(imgs))
+            res, _ = rc.forward_mast3r(pairs, net, cache_path=tag, device="cpu")
+            return res, rc._memo(tag), list(calls)
+        res_s, memo_s, calls_s = run("sharded", True)
+        res_f, memo_f, calls_f = run("full", False)
+        assert len(calls_f) == 6 and len(calls_s) == 3, (calls_s, calls_f)          # 6 unordered pairs, half here
+        assert res_s == res_f
+        assert set(memo_s["fwd"]) == set(memo_f["fwd"]) and set(memo_s["corres"]) == set(memo_f["corres"])
+        for k in memo_f["fwd"]:
+            for x, y in zip(memo_s["fwd"][k], memo_f["fwd"][k]):
+                assert torch.equal(x, y), k
+        for k in memo_f["corres"]:
+            (s0, s1, sn), (a1, a2, ac) = memo_s["corres"][k]
+            (f0, f1, fn), (b1, b2, bc) = memo_f["corres"][k]
+            assert sn == fn and abs(s0 - f0) < 1e-6 and abs(s1 - f1) < 1e-4
+            assert torch.equal(a1, b1) and torch.equal(a2, b2) and torch.equal(ac, bc)
+            assert sn > 10
+        everyone = [None] * world
+        dist.all_gather_object(everyone, sorted(calls_s))
+        assert sorted(p for part in everyone for p in part) == sorted(calls_f)       # disjoint and complete
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_forward_mast3r_shards_pairs_and_exchanges_results():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pairs_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=600) for _ in procs]
+    [p.join(timeout=60) for p in procs]
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
