@@ -414,6 +414,16 @@ def _compute_pair(memo, model, img1, img2, device, desc_conf, subsample):
 SHARD_PAIRS = True
 
 
+def _shard_group():
+    """(rank, world size) when the work of this module is to be shared by the ranks of a process group, else None."""
+    if not SHARD_PAIRS:
+        return None
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size()
+    return None
+
+
 def _exchange_pair(memo, a, b, owner, rank, device):
     """Broadcast of one computed pair from its owner: a header (scores, n, map sizes), the eight maps as one flat fp32
     tensor and the correspondence list."""
@@ -604,11 +614,37 @@ def prepare_canonical_data(imgs, tmp_pairs, subsample, order_imgs=False, min_con
                 if cached is None:
                     pts.append(X)
                     cfs.append(C)
-        if cached is None:
+        def compute_canon():
             canon, canon2, cconf = canonical_view(torch.stack(pts), torch.stack(cfs), subsample, **kw)
             focal = estimate_focal_knowing_depth(canon[None], None, "weiszfeld", min_focal=0.5, max_focal=3.5)
             memo["canon"][img] = ((canon, canon2, cconf), focal)      # stays as computed on later add_images calls,
             _disk_put(cache_path and _cache_file(cache_path, "canon", img, subsample=subsample, kw=kw), memo["canon"][img])
+        group = _shard_group()
+        if group is None:
+            if cached is None:
+                compute_canon()
+        else:
+            # canonical views shard by image: image i belongs to rank i mod G, which streams its 2 (N - 1)
+            # pair entries and broadcasts the 5 floats per pixel + the focal; the vote keeps the collectives aligned
+            # when the ranks' memos differ
+            rank, world = group
+            import torch.distributed as dist
+            need = torch.tensor([1 if cached is None else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(need, op=dist.ReduceOp.MAX)
+            if int(need.item()):
+                owner = imgs.index(img) % world
+                Hc, Wc = pts[0].shape[:2] if pts else memo["canon"][img][0][1].shape
+                flat = torch.empty(5 * Hc * Wc + 1, dtype=torch.float32, device=device)
+                if rank == owner:
+                    if cached is None:
+                        compute_canon()
+                    (canon, canon2, cconf), focal = memo["canon"][img]
+                    flat = torch.cat([canon.reshape(-1), canon2.reshape(-1), cconf.reshape(-1), focal.reshape(-1)[:1]]).float().contiguous()
+                dist.broadcast(flat, owner)
+                if rank != owner:
+                    n = Hc * Wc
+                    memo["canon"][img] = ((flat[:3 * n].view(Hc, Wc, 3), flat[3 * n:4 * n].view(Hc, Wc),
+                                           flat[4 * n:5 * n].view(Hc, Wc)), flat[5 * n:5 * n + 1].clone())
         (canon, canon2, cconf), focal = memo["canon"][img]            # like the reference's file cache (quirk C-6)
         H, W = canon.shape[:2]
         pp = torch.tensor([W / 2, H / 2], device=device)

@@ -180,6 +180,30 @@ def _pairs_worker(rank, world, port, q):
         everyone = [None] * world
         dist.all_gather_object(everyone, sorted(calls_s))
         assert sorted(p for part in everyone for p in part) == sorted(calls_f)       # disjoint and complete
+        # canonical views: image i is computed by rank i mod G and broadcast (oracle stand-ins for the two kernels)
+        from oracle import align_oracle as ao
+        canon_calls = []
+
+        def canon_cpu(pts, cfs, subsample, mode="avg-angle"):
+            canon_calls.append(len(pts))
+            return ao.canonical_view(pts, cfs, subsample)
+        rc.canonical_view = canon_cpu
+        rc.estimate_focal_knowing_depth = lambda pts3d, pp, mode, min_focal, max_focal: ao.estimate_focal_weiszfeld(
+            pts3d[0], min_focal, max_focal).reshape(1)
+        out = {}
+        for tag, shard, res in (("sharded", True, res_s), ("full", False, res_f)):
+            rc.SHARD_PAIRS = shard
+            canon_calls.clear()
+            out[tag] = rc.prepare_canonical_data(names, res, 8, cache_path=tag, device="cpu", mode="avg-angle")
+            assert len(canon_calls) == (n // world if shard else n), (tag, canon_calls)
+        (_, ps_s, cv_s, _, p21_s), (_, ps_f, cv_f, _, p21_f) = out["sharded"], out["full"]
+        assert torch.equal(ps_s, ps_f)
+        for img in names:
+            pp_s, hw_s, f_s, core_s, _, idx_s, off_s = cv_s[img]
+            pp_f, hw_f, f_f, core_f, _, idx_f, off_f = cv_f[img]
+            assert hw_s == hw_f and torch.equal(f_s, f_f) and torch.equal(core_s, core_f)
+            for other in idx_f:
+                assert torch.equal(idx_s[other], idx_f[other]) and torch.equal(off_s[other], off_f[other])
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
