@@ -26,6 +26,10 @@ EPS2D, NEAR, FAR, RADIUS_CLIP = 0.3, 0.01, 1e10, 0.0
 # Variant of the blend backward kernel (st3r_gs_set_raster_variant): 0 = per-visit warp reduction (every committed
 # measurement), 1 = per-warp record queues (written without GPU time; tests/test_experimental_gpu.py).
 RASTER_BWD_VARIANT = int(os.environ.get("ST3R_RASTER_VARIANT", "0"))
+# run_3dgs_optim under a torch.distributed process group: shard the views over the ranks (splat replicated, gradients
+# summed over NVLink peer memory / NCCL).  Opt-in until it has run on a multi-GPU box (bench.py and
+# tests/test_dist_gpu.py drive the same train_step + PeerGradExchange combination by hand).
+SHARD_VIEWS = os.environ.get("ST3R_SHARD_VIEWS", "0") == "1"
 
 
 class _Prof:
@@ -781,6 +785,21 @@ def run_3dgs_optim(scene, iters, enable_pruning=False, loss_ssim_fac=0.2, loss_o
     params, states = bind()
     group = scene.optimizers["means"].param_groups[0]
     losses_dev = torch.zeros(max(iters, 1), dtype=torch.float32, device=dev)
+    # Sharded views: under a process group every rank renders the views i = rank mod G of the same,
+    # replicated splat; the sum of the per-Gaussian gradients over the ranks is the full gradient (the loss is a sum
+    # over views), so all replicas take the same Adam step.  Exchange: peer memory over NVLink fused with Adam
+    # (dist.PeerGradExchange), NCCL all-reduce if symmetric memory cannot be set up.
+    shard, hook = None, None
+    if SHARD_VIEWS:
+        from . import dist as _sd
+        rank, world_size = _sd.world()
+        if world_size > 1 and cams.shape[0] >= world_size:
+            if enable_pruning:
+                raise NotImplementedError("run_3dgs_optim with sharded views keeps the splat replicated; the MCMC strategy "
+                                          "draws random numbers per rank and would let the replicas diverge")
+            shard = _sd.shard_indices(cams.shape[0], rank, world_size)
+            truth = truth[shard].contiguous()
+            cams = cams[shard].contiguous()
     n_views = cams.shape[0]
 
     def get_plan():
@@ -788,6 +807,16 @@ def run_3dgs_optim(scene, iters, enable_pruning=False, loss_ssim_fac=0.2, loss_o
         if plan is None or not plan.matches(params["means"].shape[0], n_views, width, height, dev):
             plan = scene._gs_plan = TrainPlan(params["means"].shape[0], n_views, width, height, dev)
         return plan
+
+    if shard is not None:
+        plan = get_plan()
+        if plan.peer is None:
+            try:
+                plan.peer = _sd.PeerGradExchange(params["means"].shape[0], dev)
+            except Exception as e:      # noqa: BLE001 - e.g. no symmetric memory on this node
+                print(f"starst3r_b200.gs: symmetric memory unavailable ({e!r}); NCCL all-reduce of the gradients")
+        if plan.peer is None:
+            hook = lambda fr: _sd.allreduce_gradients(fr.grads)      # noqa: E731
 
     pbar = trange(iters, disable=not verbose)
     for step in pbar:
@@ -797,7 +826,7 @@ def run_3dgs_optim(scene, iters, enable_pruning=False, loss_ssim_fac=0.2, loss_o
         loss, fr = train_step(params, states, truth, cams, width, height, opt_step, lr=group["lr"],
                               betas=group["betas"], eps=group["eps"], loss_ssim_fac=loss_ssim_fac,
                               loss_opacity_fac=loss_opacity_fac, loss_scale_fac=loss_scale_fac, plan=get_plan(),
-                              loss_out=losses_dev[step])
+                              loss_out=losses_dev[step], grad_hook=hook)
         for k in names:
             scene.optimizers[k]._st(gz[k])["step"] += 1
         if verbose:
@@ -809,4 +838,7 @@ def run_3dgs_optim(scene, iters, enable_pruning=False, loss_ssim_fac=0.2, loss_o
     if iters <= 0:
         return []
     get_plan().poll(wait_all=True)
+    if shard is not None:               # the loss is a sum over views: add the ranks' shares
+        import torch.distributed as _dist
+        _dist.all_reduce(losses_dev)
     return losses_dev[:iters].cpu().tolist()

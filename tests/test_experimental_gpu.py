@@ -170,3 +170,65 @@ def test_raster_queue_equals_default_gradients(cuda_device, scale_mult):
     for a, b in zip(grads[0], grads[1]):
         assert torch.isfinite(b).all()
         assert (a - b).abs().max().item() <= 2e-4 * max(a.abs().max().item(), 1e-12)
+
+
+# ---- Scene.run_3dgs_optim with sharded views (gs.SHARD_VIEWS), 2 GPUs ------------------------------------------
+def _shard_views_worker(rank, world, port, out_dir):
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import starst3r_b200 as st
+    from starst3r_b200 import synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", device_id=dev)
+    W, H, C, N = 64, 48, 4, 3000
+    viewmats, Ks = synth.look_at_cameras(C, W, H)
+    sp = synth.random_splats(N, seed=3, scale_mode="rand")
+    sp["scales"] = sp["scales"] * 6
+    d = {k: v.to(dev) for k, v in sp.items()}
+    with torch.no_grad():
+        target, _, _ = st.gs.rasterization(d["means"], d["quats"], d["scales"], d["opacities"], d["shN"], viewmats.to(dev),
+                                           Ks.to(dev), W, H)
+    dist.broadcast(target, 0)        # identical ground truth on every rank
+
+    def make_scene():
+        scene = st.Scene(device=dev)
+        scene.imgs = [t.clamp(0, 1).cpu().numpy() for t in target]
+        scene.c2w = torch.linalg.inv(viewmats).to(dev)
+        scene.intrinsics = Ks.to(dev)
+        g = torch.Generator().manual_seed(0)
+        scene.dense_pts = [(sp["means"] + 0.01 * torch.randn(N, 3, generator=g)).to(dev)]
+        scene.dense_cols = [torch.rand(N, 3, generator=g)]
+        scene.init_3dgs(init_scale=2e-2)
+        return scene
+    st.gs.SHARD_VIEWS = True
+    sharded = make_scene()
+    losses_s = sharded.run_3dgs_optim(10)
+    st.gs.SHARD_VIEWS = False
+    res = {"losses_s": losses_s, "params_s": {k: v.detach().cpu() for k, v in sharded.gaussians.items()}}
+    if rank == 0:
+        full = make_scene()
+        res["losses_f"] = full.run_3dgs_optim(10)
+        res["params_f"] = {k: v.detach().cpu() for k, v in full.gaussians.items()}
+    torch.save(res, os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_run_3dgs_optim_sharded_views_matches_single_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_shard_views_worker, args=(2, 29741, str(tmp_path)), nprocs=2, join=True)
+    r = [torch.load(os.path.join(tmp_path, f"rank{k}.pt")) for k in range(2)]
+    for k in r[0]["params_s"]:
+        assert torch.equal(r[0]["params_s"][k], r[1]["params_s"][k]), f"replicas diverged: {k}"
+        assert torch.allclose(r[0]["params_s"][k], r[0]["params_f"][k], rtol=1e-4, atol=4e-4), k
+    assert r[0]["losses_s"] == r[1]["losses_s"]
+    for a, b in zip(r[0]["losses_s"], r[0]["losses_f"]):
+        assert abs(a - b) <= 1e-3 * abs(b), (a, b)
