@@ -368,7 +368,9 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "views_per_gpu": N_VIEWS, "gaussians": N_GAUSS, "image": [H, W],
                        "parallelism": f"views sharded dp{world}, {exchange}" if world > 1 else "single GPU",
-                       "l2": "256 MiB flush between timed steps"},
+                       "l2": "256 MiB flush between timed steps",
+                       # opt-in kernel variants (all 0 / False = the default kernels)
+                       "kernel_variants": _kernel_variants()},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
             "blends_per_sec": n_blend * world / (shares.get("st3r_gs_raster_fwd", float("nan")) * 1e-3),
@@ -487,6 +489,12 @@ def run_reference(args):
             "cpu_baseline": best,
             "e2e": {"value": best["value"], "unit": "Gaussians/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(line)
+
+
+def _kernel_variants():
+    from starst3r_b200 import gs, match
+    from starst3r_b200 import reconstruct as rc
+    return {"raster_bwd": int(gs.RASTER_BWD_VARIANT), "nn_split": bool(match.NN_SPLIT), "align": int(rc.ALIGN_VARIANT)}
 
 
 def main():
