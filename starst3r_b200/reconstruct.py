@@ -407,10 +407,9 @@ def _compute_pair(memo, model, img1, img2, device, desc_conf, subsample):
 
 
 # Under an initialised torch.distributed group (one process per GPU) forward_mast3r computes only every G-th missing
-# pair on this rank - image pairs are independent (sparse_ga.py:529 loop body) - and every pair's result
-# is broadcast from its owner, so that all ranks continue with the full memo (the alignment that follows runs as
-# replicas).  No collective touches the matching itself.  At BASELINE configs[3] sizes the replicated point maps no
-# longer fit one GPU; ownership by image (each rank keeps the maps of its images' canonical views) is the next step.
+# pair on this rank - image pairs are independent (sparse_ga.py:529 loop body) - and distributes every
+# pair from the rank that computed it (_exchange_pair): what the replicated optimiser reads goes to everybody, an
+# image's own full-resolution map only to the rank that owns the image.  No collective touches the matching itself.
 SHARD_PAIRS = True
 
 
@@ -424,41 +423,77 @@ def _shard_group():
     return None
 
 
-def _exchange_pair(memo, a, b, owner, rank, device):
-    """Broadcast of one computed pair from its owner: a header (scores, n, map sizes), the eight maps as one flat fp32
-    tensor and the correspondence list."""
+class _Sub:
+    """A map this rank only holds at the optimiser's resolution: [::subsample, ::subsample] of the original."""
+
+    def __init__(self, t, subsample):
+        self.t, self.subsample = t, subsample
+
+
+def _subsampled(x, subsample):
+    if isinstance(x, _Sub):
+        assert x.subsample == subsample, "map was exchanged at another subsampling"
+        return x.t
+    return x[::subsample, ::subsample]
+
+
+def _exchange_pair(memo, a, b, ia, ib, owner, rank, world, device, subsample):
+    """Distributes one computed pair from the rank that computed it (`owner`):
+      * to everybody (the optimiser runs as replicas): the scores, the correspondence list and the two cross maps
+        X21 / X12 at the optimiser's resolution ([::subsample, ::subsample]: all anybody reads of them, preds_21);
+      * image a's own full-resolution map (X11, C11) only to the rank that owns image a (index mod G), image b's
+        (X22, C22) only to the owner of b: they feed the canonical view of that image and nothing else.
+    Per pair 8 HW floats travel to at most two ranks instead of 16 HW floats to all of them, and a rank keeps the
+    full-resolution maps of its own images only (N / G images x 2 (N - 1) entries)."""
     import torch.distributed as dist
     head = torch.zeros(7, dtype=torch.float64, device=device)
     if rank == owner:
         score, (xy1, xy2, conf) = memo["corres"][a, b]
-        X11, _, X21, _ = memo["fwd"][a, b]
-        head = torch.tensor([score[0], score[1], float(score[2]), X11.shape[0], X11.shape[1], X21.shape[0], X21.shape[1]],
+        X11, C11, X21, C21 = memo["fwd"][a, b]
+        X22, C22, X12, C12 = memo["fwd"][b, a]
+        head = torch.tensor([score[0], score[1], float(score[2]), X11.shape[0], X11.shape[1], X22.shape[0], X22.shape[1]],
                             dtype=torch.float64, device=device)
-        maps = torch.cat([t.reshape(-1) for t in memo["fwd"][a, b] + memo["fwd"][b, a]]).float().contiguous()
+        small = torch.cat([_subsampled(t, subsample).reshape(-1) for t in (X21, C21, X12, C12)]).float().contiguous()
     dist.broadcast(head, owner)
     n, H1, W1, H2, W2 = (int(v) for v in head[2:].tolist())
-    sizes = [3 * H1 * W1, H1 * W1, 3 * H2 * W2, H2 * W2, 3 * H2 * W2, H2 * W2, 3 * H1 * W1, H1 * W1]
+    h1, w1 = len(range(0, H1, subsample)), len(range(0, W1, subsample))
+    h2, w2 = len(range(0, H2, subsample)), len(range(0, W2, subsample))
+    sizes = [3 * h2 * w2, h2 * w2, 3 * h1 * w1, h1 * w1]
     if rank != owner:
-        maps = torch.empty(sum(sizes), dtype=torch.float32, device=device)
+        small = torch.empty(sum(sizes), dtype=torch.float32, device=device)
         xy1 = torch.empty((n, 2), dtype=torch.int64, device=device)
         xy2 = torch.empty((n, 2), dtype=torch.int64, device=device)
         conf = torch.empty(n, dtype=torch.float32, device=device)
     xy = torch.cat([xy1.reshape(-1, 2), xy2.reshape(-1, 2)], dim=1).contiguous()        # [n, 4]
     conf = conf.contiguous()
-    dist.broadcast(maps, owner)
+    dist.broadcast(small, owner)
     if n > 0:                                   # (no zero-length collectives)
         dist.broadcast(xy, owner)
         dist.broadcast(conf, owner)
+    # full-resolution own maps: point to point, owner of the pair -> owner of the image
+    full = {}
+    for tag, idx, H, W in (("a", ia, H1, W1), ("b", ib, H2, W2)):
+        dst = idx % world
+        if rank == owner:
+            X, C = (X11, C11) if tag == "a" else (X22, C22)
+            if dst == owner:
+                full[tag] = (X, C)
+            else:
+                dist.send(torch.cat([X.reshape(-1), C.reshape(-1)]).float().contiguous(), dst)
+        elif rank == dst:
+            buf = torch.empty(4 * H * W, dtype=torch.float32, device=device)
+            dist.recv(buf, owner)
+            full[tag] = (buf[:3 * H * W].view(H, W, 3), buf[3 * H * W:].view(H, W))
+    parts = torch.split(small, sizes)
+    X21s, C21s = _Sub(parts[0].view(h2, w2, 3), subsample), _Sub(parts[1].view(h2, w2), subsample)
+    X12s, C12s = _Sub(parts[2].view(h1, w1, 3), subsample), _Sub(parts[3].view(h1, w1), subsample)
+    memo["fwd"][a, b] = full.get("a", (None, None)) + (X21s, C21s)
+    memo["fwd"][b, a] = full.get("b", (None, None)) + (X12s, C12s)
     if rank != owner:
-        parts = torch.split(maps, sizes)
-        X11, C11, X21, C21 = parts[0].view(H1, W1, 3), parts[1].view(H1, W1), parts[2].view(H2, W2, 3), parts[3].view(H2, W2)
-        X22, C22, X12, C12 = parts[4].view(H2, W2, 3), parts[5].view(H2, W2), parts[6].view(H1, W1, 3), parts[7].view(H1, W1)
-        memo["fwd"][a, b] = (X11, C11, X21, C21)
-        memo["fwd"][b, a] = (X22, C22, X12, C12)
         memo["corres"][a, b] = ((float(head[0]), float(head[1]), n), (xy[:, :2].contiguous(), xy[:, 2:].contiguous(), conf))
 
 
-def _forward_sharded(pairs, memo, model, device, desc_conf, subsample):
+def _forward_sharded(pairs, memo, model, device, desc_conf, subsample, cache_path=None):
     """Computes this rank's share of the missing pairs and exchanges all of them; returns the number computed here."""
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -472,14 +507,21 @@ def _forward_sharded(pairs, memo, model, device, desc_conf, subsample):
     dist.broadcast_object_list(box, src=0)        # rank 0's list decides (caches may differ between ranks)
     todo = box[0]
     mine = 0
+    fkw = dict(desc_conf=desc_conf, subsample=subsample)
     for j, k in enumerate(todo):
         if j % world == rank:
             img1, img2 = pairs[k]
+            a, b = img1["instance"], img2["instance"]
             _compute_pair(memo, model, img1, img2, device, desc_conf, subsample)
+            if PERSIST_CACHE and cache_path:    # the rank that computed a pair is the one that still holds all of it
+                _disk_put(_cache_file(cache_path, "fwd", a, b), memo["fwd"][a, b])
+                _disk_put(_cache_file(cache_path, "fwd", b, a), memo["fwd"][b, a])
+                _disk_put(_cache_file(cache_path, "corres", a, b, **fkw), memo["corres"][a, b])
             mine += 1
     for j, k in enumerate(todo):
         img1, img2 = pairs[k]
-        _exchange_pair(memo, img1["instance"], img2["instance"], j % world, rank, device)
+        _exchange_pair(memo, img1["instance"], img2["instance"], int(img1["idx"]), int(img2["idx"]), j % world, rank, world,
+                       device, subsample)
     return mine
 
 
@@ -503,14 +545,8 @@ def forward_mast3r(pairs, model, cache_path, desc_conf="desc_conf", device="cuda
     if SHARD_PAIRS and model is not None:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            before = set(memo["corres"])
-            _forward_sharded(pairs, memo, model, device, desc_conf, subsample)
+            _forward_sharded(pairs, memo, model, device, desc_conf, subsample, cache_path)
             sharded = True
-            if PERSIST_CACHE and cache_path and dist.get_rank() == 0:
-                for (a, b) in set(memo["corres"]) - before:
-                    _disk_put(_cache_file(cache_path, "fwd", a, b), memo["fwd"][a, b])
-                    _disk_put(_cache_file(cache_path, "fwd", b, a), memo["fwd"][b, a])
-                    _disk_put(_cache_file(cache_path, "corres", a, b, **fkw), memo["corres"][a, b])
     for img1, img2 in pairs:
         a, b = img1["instance"], img2["instance"]
         if (b, a) in memo["corres"] and (a, b) not in memo["corres"]:
@@ -600,14 +636,14 @@ def prepare_canonical_data(imgs, tmp_pairs, subsample, order_imgs=False, min_con
                 X, C, X2, C2 = memo["fwd"][key1]
                 score, (xy1, xy2, confs) = memo["corres"][key_corres]
                 pixels[img2] = xy1, confs
-                preds_21.setdefault(img, {})[img2] = (X2[::subsample, ::subsample].reshape(-1, 3),
-                                                      C2[::subsample, ::subsample].ravel())
+                preds_21.setdefault(img, {})[img2] = (_subsampled(X2, subsample).reshape(-1, 3),
+                                                      _subsampled(C2, subsample).ravel())
             if img == img2:
                 X, C, X2, C2 = memo["fwd"][key2]
                 score, (xy1, xy2, confs) = memo["corres"][key_corres]
                 pixels[img1] = xy2, confs
-                preds_21.setdefault(img, {})[img1] = (X2[::subsample, ::subsample].reshape(-1, 3),
-                                                      C2[::subsample, ::subsample].ravel())
+                preds_21.setdefault(img, {})[img1] = (_subsampled(X2, subsample).reshape(-1, 3),
+                                                      _subsampled(C2, subsample).ravel())
             if score is not None:
                 i, j = imgs.index(img1), imgs.index(img2)
                 pairwise_scores[i, j] = pairwise_scores[j, i] = score[2]
@@ -615,6 +651,9 @@ def prepare_canonical_data(imgs, tmp_pairs, subsample, order_imgs=False, min_con
                     pts.append(X)
                     cfs.append(C)
         def compute_canon():
+            if any(p is None for p in pts):
+                raise RuntimeError(f"the point maps of {img} are not resident on this rank (forward_mast3r distributed "
+                                   "them by image ownership); compute its canonical view on the owning rank")
             canon, canon2, cconf = canonical_view(torch.stack(pts), torch.stack(cfs), subsample, **kw)
             focal = estimate_focal_knowing_depth(canon[None], None, "weiszfeld", min_focal=0.5, max_focal=3.5)
             memo["canon"][img] = ((canon, canon2, cconf), focal)      # stays as computed on later add_images calls,
@@ -633,13 +672,17 @@ def prepare_canonical_data(imgs, tmp_pairs, subsample, order_imgs=False, min_con
             dist.all_reduce(need, op=dist.ReduceOp.MAX)
             if int(need.item()):
                 owner = imgs.index(img) % world
-                Hc, Wc = pts[0].shape[:2] if pts else memo["canon"][img][0][1].shape
-                flat = torch.empty(5 * Hc * Wc + 1, dtype=torch.float32, device=device)
+                hw = torch.zeros(2, dtype=torch.int64, device=device)
                 if rank == owner:
                     if cached is None:
                         compute_canon()
                     (canon, canon2, cconf), focal = memo["canon"][img]
+                    hw = torch.tensor(canon2.shape, dtype=torch.int64, device=device)
                     flat = torch.cat([canon.reshape(-1), canon2.reshape(-1), cconf.reshape(-1), focal.reshape(-1)[:1]]).float().contiguous()
+                dist.broadcast(hw, owner)
+                Hc, Wc = (int(v) for v in hw.tolist())
+                if rank != owner:
+                    flat = torch.empty(5 * Hc * Wc + 1, dtype=torch.float32, device=device)
                 dist.broadcast(flat, owner)
                 if rank != owner:
                     n = Hc * Wc
