@@ -165,7 +165,7 @@ def _pairs_worker(rank, world, port, q):
             return res, rc._memo(tag), list(calls)
         res_s, memo_s, calls_s = run("sharded", True)
         res_f, memo_f, calls_f = run("full", False)
-        assert len(calls_f) == 6 and len(calls_s) == 3, (calls_s, calls_f)          # 6 unordered pairs, half here
+        assert len(calls_f) == 6 and len(calls_s) == 6 // world, (calls_s, calls_f)  # 6 unordered pairs, 1/G of them here
         assert res_s == res_f
         assert set(memo_s["fwd"]) == set(memo_f["fwd"]) and set(memo_s["corres"]) == set(memo_f["corres"])
         # by-image ownership: image a's own full-resolution map lives only on rank index(a) mod G; the cross maps are
@@ -179,7 +179,7 @@ def _pairs_worker(rank, world, port, q):
             else:
                 assert Xs is None and Cs is None, (a, b)
             assert isinstance(X2s, rc._Sub) and torch.equal(X2s.t, X2[::8, ::8]) and torch.equal(C2s.t, C2[::8, ::8]), (a, b)
-        assert resident == len(memo_f["fwd"]) // world
+        assert resident == sum(n - 1 for i in range(n) if i % world == rank)         # my images x their ordered pairs
         for k in memo_f["corres"]:
             (s0, s1, sn), (a1, a2, ac) = memo_s["corres"][k]
             (f0, f1, fn), (b1, b2, bc) = memo_f["corres"][k]
@@ -204,7 +204,7 @@ def _pairs_worker(rank, world, port, q):
             rc.SHARD_PAIRS = shard
             canon_calls.clear()
             out[tag] = rc.prepare_canonical_data(names, res, 8, cache_path=tag, device="cpu", mode="avg-angle")
-            assert len(canon_calls) == (n // world if shard else n), (tag, canon_calls)
+            assert len(canon_calls) == (len(range(rank, n, world)) if shard else n), (tag, canon_calls)
         (_, ps_s, cv_s, _, p21_s), (_, ps_f, cv_f, _, p21_f) = out["sharded"], out["full"]
         assert torch.equal(ps_s, ps_f)
         for i1 in p21_f:
@@ -224,12 +224,13 @@ def _pairs_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_forward_mast3r_shards_pairs_and_exchanges_results():
+@pytest.mark.parametrize("world", [2, 3])
+def test_forward_mast3r_shards_pairs_and_exchanges_results(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_pairs_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_pairs_worker, args=(r, world, port, q)) for r in range(world)]
     [p.start() for p in procs]
     res = [q.get(timeout=600) for _ in procs]
     [p.join(timeout=60) for p in procs]
-    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
