@@ -38,35 +38,47 @@ struct Work {
   float* gscal;       // [2]: g (global scaling), number of images attaining the minimum size, the minimum size
 };
 
+// kStage (ALIGN variant bit 0, N <= CAM_STAGE_MAX): the per-image records the single-thread MST chain walks live in
+// shared memory for the duration of the kernel.  In HBM every edge of the chain is a store -> load round trip through
+// L2 (~10 us for 7 edges in the launch list of profiles/r01u); the serial scans also stop at min(N, block size).
+constexpr int CAM_STAGE_MAX = 128;
+
+template <bool kStage>
 __global__ void __launch_bounds__(CAM_THREADS)
 align_cam_fwd_kernel(St3rAlignProblem pb, Params p, Work w) {
   const int N = pb.n_img;
   if (w.sums[3] != 0.f) return;   // NaN loss seen: the reference breaks out of the loop (reconstruct.py:398-399)
   const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
   __shared__ float s_min[CAM_THREADS];
+  __shared__ AlignCamTmp s_tmp[kStage ? CAM_STAGE_MAX : 1];
+  AlignCamTmp* tmp = kStage ? s_tmp : w.tmp;
   float best = INFINITY;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    al_cam_local_fwd(ic[i], p.log_focal[i], p.log_size[i], p.quat + 4 * i, w.tmp[i]);
-    float s = w.tmp[i].s;
+    al_cam_local_fwd(ic[i], p.log_focal[i], p.log_size[i], p.quat + 4 * i, tmp[i]);
+    float s = tmp[i].s;
     best = fminf(best, s);
   }
   s_min[threadIdx.x] = best;
   __syncthreads();
   if (threadIdx.x == 0) {
     float b = INFINITY;
-    for (int t = 0; t < blockDim.x; ++t) b = fminf(b, s_min[t]);
+    const int nscan = kStage ? min(N, (int)blockDim.x) : (int)blockDim.x;   // threads >= N hold +inf
+    for (int t = 0; t < nscan; ++t) b = fminf(b, s_min[t]);
     // torch's sizes.min() backward splits the gradient evenly between tied minima (all sizes tie at the
     // first iteration, when every log_size is 0), so remember how many images attain the minimum.
     int ties = 0;
-    for (int i = 0; i < N; ++i) ties += (w.tmp[i].s == b) ? 1 : 0;
+    for (int i = 0; i < N; ++i) ties += (tmp[i].s == b) ? 1 : 0;
     w.gscal[0] = 1.0f / b;
     w.gscal[1] = (float)ties;
     w.gscal[2] = b;
-    al_chain_fwd(N, pb.root, pb.edges, w.tmp, p.trans);
+    al_chain_fwd(N, pb.root, pb.edges, tmp, p.trans);
   }
   __syncthreads();
   const float g = w.gscal[0];
-  for (int i = threadIdx.x; i < N; i += blockDim.x) al_cam_final_fwd(ic[i], p.pp + 2 * i, g, w.tmp[i], w.cam[i]);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    al_cam_final_fwd(ic[i], p.pp + 2 * i, g, tmp[i], w.cam[i]);
+    if (kStage) w.tmp[i] = tmp[i];     // the backward kernel reads the records from HBM
+  }
 }
 
 // Adds a thread's 17 camera-record gradients of image `img` into the CTA-wide shared table
@@ -425,6 +437,7 @@ __device__ __forceinline__ void adam_update(float* p, float g, float* m, float* 
 
 // camera-record gradients -> parameter gradients -> Adam -> quaternion re-normalisation; also finalises the
 // iteration's loss and clears the accumulators for the next iteration.
+template <bool kStage>
 __global__ void __launch_bounds__(CAM_THREADS)
 align_cam_bwd_kernel(St3rAlignProblem pb, Params p, AdamState ad, Work w, int train_mask, float lr_over_bc1,
                      float inv_sqrt_bc2, float omb1, float b2, float omb2, float eps, float dust3r_w,
@@ -432,11 +445,16 @@ align_cam_bwd_kernel(St3rAlignProblem pb, Params p, AdamState ad, Work w, int tr
   const int N = pb.n_img;
   const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
   __shared__ float s_gg[CAM_THREADS];
+  __shared__ AlignCamTmp s_tmp[kStage ? CAM_STAGE_MAX : 1];
+  __shared__ AlignCamGrad s_cg[kStage ? CAM_STAGE_MAX : 1];
   if (w.sums[3] != 0.f) return;
+  AlignCamTmp* tmp = kStage ? s_tmp : w.tmp;
+  AlignCamGrad* cg = kStage ? s_cg : w.cgrad;
   const float g = w.gscal[0];
   const float ties = w.gscal[1], smin = w.gscal[2];
   float gg = 0.f;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    if (kStage) tmp[i] = w.tmp[i];
     const float* gsrc = w.gcam + i * NG;
     float folded[NG];
     if (reps > 1) {     // variant 1: the loss CTAs spread their sums over `reps` replicas of the table
@@ -447,16 +465,17 @@ align_cam_bwd_kernel(St3rAlignProblem pb, Params p, AdamState ad, Work w, int tr
         for (int k = 0; k < NG; ++k) folded[k] += gsrc[(size_t)r * N * NG + k];
       gsrc = folded;
     }
-    al_cam_final_bwd(ic[i], p.pp + 2 * i, g, w.tmp[i], gsrc, w.cgrad[i]);
-    gg += w.cgrad[i].g_g;
+    al_cam_final_bwd(ic[i], p.pp + 2 * i, g, tmp[i], gsrc, cg[i]);
+    gg += cg[i].g_g;
   }
   s_gg[threadIdx.x] = gg;
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.f;
-    for (int k = 0; k < blockDim.x; ++k) t += s_gg[k];
+    const int nscan = kStage ? min(N, (int)blockDim.x) : (int)blockDim.x;   // threads >= N hold zero
+    for (int k = 0; k < nscan; ++k) t += s_gg[k];
     s_gg[0] = t;
-    al_chain_bwd(N, pb.root, pb.edges, w.tmp, p.trans, w.cgrad);
+    al_chain_bwd(N, pb.root, pb.edges, tmp, p.trans, cg);
     float loss = w.sums[0] + dust3r_w * w.sums[1];
     if (loss_hist) loss_hist[iter] = loss;
     if (loss != loss) w.sums[3] = 1.0f;   // NaN -> stop flag (reconstruct.py:398-399)
@@ -467,8 +486,8 @@ align_cam_bwd_kernel(St3rAlignProblem pb, Params p, AdamState ad, Work w, int tr
   const bool stop = false;  // the NaN iteration itself still steps, like the reference
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     float g_pp[2], g_lf, g_q[4], g_t[3], g_ls;
-    float extra = (w.tmp[i].s == smin) ? -gg_total * g * g / ties : 0.f;
-    al_cam_local_bwd(w.tmp[i], w.cgrad[i], extra, g_pp, &g_lf, g_q, g_t, &g_ls);
+    float extra = (tmp[i].s == smin) ? -gg_total * g * g / ties : 0.f;
+    al_cam_local_bwd(tmp[i], cg[i], extra, g_pp, &g_lf, g_q, g_t, &g_ls);
     if (grad_out) {
       float* o = grad_out + 11 * i;
       o[0] = g_pp[0]; o[1] = g_pp[1]; o[2] = g_lf; o[3] = g_q[0]; o[4] = g_q[1]; o[5] = g_q[2]; o[6] = g_q[3];
@@ -583,6 +602,7 @@ int st3r_align_optimize(const St3rAlignProblem* prob, float* pp, float* log_foca
   AdamState ad{adam_m, adam_v};
   const int variant = g_align_variant & 1;
   const int reps = variant == 1 ? ALIGN_REPL : 1;
+  const bool stage = variant == 1 && N <= CAM_STAGE_MAX;   // camera kernels with their records in shared memory
   ST3R_CHECK_CUDA(cudaMemsetAsync(w.gcam, 0, (size_t)N * NG * ALIGN_REPL * sizeof(float), stream));
   ST3R_CHECK_CUDA(cudaMemsetAsync(w.sums, 0, 4 * sizeof(float), stream));
 
@@ -613,7 +633,8 @@ int st3r_align_optimize(const St3rAlignProblem* prob, float* pp, float* log_foca
 
   const int iters = niter > 0 ? niter : 1;
   for (int it = 0; it < iters; ++it) {
-    align_cam_fwd_kernel<<<1, CAM_THREADS, 0, stream>>>(pb, p, w);
+    if (stage) align_cam_fwd_kernel<true><<<1, CAM_THREADS, 0, stream>>>(pb, p, w);
+    else align_cam_fwd_kernel<false><<<1, CAM_THREADS, 0, stream>>>(pb, p, w);
     ST3R_CHECK_LAUNCH();
     if (niter == 0) break;
     if (n_main > 0) {
@@ -644,10 +665,16 @@ int st3r_align_optimize(const St3rAlignProblem* prob, float* pp, float* log_foca
     }
     const int step = it + 1;
     const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
-    align_cam_bwd_kernel<<<1, CAM_THREADS, 0, stream>>>(pb, p, ad, w, train_mask, (float)((double)h_lr[it] / bc1),
-                                                        (float)(1.0 / sqrt(bc2)), (float)(1.0 - beta1), (float)beta2,
-                                                        (float)(1.0 - beta2), (float)eps, 1.0f, loss_hist, it,
-                                                        (it == iters - 1) ? grad_out : nullptr, reps);
+    if (stage)
+      align_cam_bwd_kernel<true><<<1, CAM_THREADS, 0, stream>>>(pb, p, ad, w, train_mask, (float)((double)h_lr[it] / bc1),
+                                                                (float)(1.0 / sqrt(bc2)), (float)(1.0 - beta1), (float)beta2,
+                                                                (float)(1.0 - beta2), (float)eps, 1.0f, loss_hist, it,
+                                                                (it == iters - 1) ? grad_out : nullptr, reps);
+    else
+      align_cam_bwd_kernel<false><<<1, CAM_THREADS, 0, stream>>>(pb, p, ad, w, train_mask, (float)((double)h_lr[it] / bc1),
+                                                                 (float)(1.0 / sqrt(bc2)), (float)(1.0 - beta1), (float)beta2,
+                                                                 (float)(1.0 - beta2), (float)eps, 1.0f, loss_hist, it,
+                                                                 (it == iters - 1) ? grad_out : nullptr, reps);
     ST3R_CHECK_LAUNCH();
   }
   if (cam_out) ST3R_CHECK_CUDA(cudaMemcpyAsync(cam_out, w.cam, (size_t)N * sizeof(AlignCam), cudaMemcpyDeviceToDevice, stream));
