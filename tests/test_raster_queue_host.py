@@ -7,7 +7,7 @@ The CUDA code itself is checked on the GPU by tests/test_experimental_gpu.py."""
 import numpy as np
 
 ALPHA_MIN, ALPHA_MAX, T_MIN = 1.0 / 255.0, 0.999, 1e-4
-QW, DENSE_MIN, BLOCK = 160, 12, 256
+QW, DENSE_MIN, BLOCK = 160, 8, 256
 
 
 def forward(px, py, A, B, col):
@@ -40,6 +40,24 @@ def contribution(px, py, Ak, Bk, colk, T, buf, T_final, v_rgb, v_a):
     v_alpha = float(((colk * T - buf * ra) * v_rgb).sum() + T_final * ra * v_a)
     w = vis * v_alpha if Ak[2] * vis <= ALPHA_MAX else 0.0
     return fac, w, T, buf + colk * fac
+
+
+def contribution_scalar(px, py, Ak, Bk, colk, T, behind_v, T_final, v_rgb, v_a):
+    """The same step the way raster_bwd_queue_kernel does it: the colour behind the Gaussian is carried as ONE scalar,
+    its dot product with the pixel's upstream colour gradient."""
+    dx, dy = Ak[0] - px, Ak[1] - py
+    sigma = 0.5 * (Bk[0] * dx * dx + Bk[2] * dy * dy) + Bk[1] * dx * dy
+    vis = np.exp(-sigma)
+    alpha = min(ALPHA_MAX, Ak[2] * vis)
+    if sigma < 0 or alpha < ALPHA_MIN:
+        return None
+    ra = 1.0 / (1.0 - alpha)
+    T = T * ra
+    fac = alpha * T
+    cv = float((colk * v_rgb).sum())
+    v_alpha = T * cv + ra * (T_final * v_a - behind_v)
+    w = vis * v_alpha if Ak[2] * vis <= ALPHA_MAX else 0.0
+    return fac, w, T, behind_v + fac * cv
 
 
 def grad_terms(Ak, Bk, dx, dy, fac, w, v_rgb):
@@ -98,8 +116,8 @@ def emulate_tile(A, B, col, T_final, last, v_rgb, v_a, stats):
                 for l, (px, py, i, j) in enumerate(lanes):
                     if batch_end - t > last[i, j]:
                         continue
-                    T, buf = state.get((i, j), (T_final[i, j], np.zeros(3)))
-                    r = contribution(px, py, As[t], Bs[t], cs[t], T, buf, T_final[i, j], v_rgb[i, j], v_a[i, j])
+                    T, buf = state.get((i, j), (T_final[i, j], 0.0))
+                    r = contribution_scalar(px, py, As[t], Bs[t], cs[t], T, buf, T_final[i, j], v_rgb[i, j], v_a[i, j])
                     if r is None:
                         continue
                     fac, w, T, buf = r
