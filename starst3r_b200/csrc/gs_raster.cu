@@ -375,9 +375,10 @@ __device__ __forceinline__ void drain_queue(int n, const uint32_t* qk, const flo
       for (int k = 0; k < 9; ++k) g[k] = 0.f;
     }
     // segmented suffix sums: equal slots are adjacent, so "the lane `off` further carries my slot" implies that every
-    // lane in between does
+    // lane in between does; a segment is one visit's records, fewer than DENSE_MIN, so log2(DENSE_MIN) steps suffice
+    static_assert((DENSE_MIN & (DENSE_MIN - 1)) == 0, "DENSE_MIN must be a power of two (scan depth)");
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
+    for (int off = 1; off < DENSE_MIN; off <<= 1) {
       const uint32_t tk = __shfl_down_sync(full, t, off);
       const bool same = (lane + off < 32) && tk == t;
 #pragma unroll
@@ -483,7 +484,10 @@ raster_bwd_queue_kernel(const int32_t* __restrict__ offsets, const int32_t* __re
         if (!vm) continue;
         float fac = 0.f, w = 0.f;
         if (valid) {                    // the part that is sequential per pixel
-          const float ra = 1.0f / (1.0f - alpha);
+          // 1 - alpha lies in [1e-3, 1]: rcp.approx (MUFU.RCP, 1 ulp) instead of the 15-instruction IEEE division;
+          // the error is of the size of the forward's own rounding of T
+          float ra;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(1.0f - alpha));
           T *= ra;
           fac = alpha * T;
           const float4 col = sC[t];

@@ -84,7 +84,7 @@ def drain(queue, A, B, acc, v_rgb_lanes, px0, py0, stats):
             else:
                 t[lane] = (0xFFFFFFE0 + lane) >> 5
         off = 1
-        while off < 32:
+        while off < DENSE_MIN:          # a segment is one visit's records: fewer than DENSE_MIN
             new = g.copy()
             for lane in range(32):
                 if lane + off < 32 and t[lane + off] == t[lane]:
