@@ -426,15 +426,35 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
   const uint32_t bar0 = smem_u32(smem + SMEM_BAR);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+#ifdef NN_TC_DECOUPLE
+  // Experiment (scripts/build_dbg.sh, not in the default build): one full / empty barrier pair per (query tile,
+  // accumulator stage) instead of per stage.  The two query tiles of a CTA then form two pipelines that only share the
+  // DB tile in shared memory: a tile's epilogue starts after ITS three UMMAs (192 instead of 384 tensor cycles into the
+  // round trip issue -> commit -> epilogue -> release -> issue that bounds the kernel, profiles/r01b_nn_tc_experiments.md)
+  // and its next UMMAs no longer wait for the other tile's epilogue warps.
+#ifdef NN_TC_EXP_NOMMA
+#error "NN_TC_DECOUPLE and NN_TC_EXP_NOMMA are separate experiments"
+#endif
+  constexpr int NACC = MH * ACC_STAGES;
+  auto tfull_bar = [&](int h, int a) { return bar0 + 8u * (2 * STAGES + h * ACC_STAGES + a); };
+  auto tempty_bar = [&](int h, int a) { return bar0 + 8u * (2 * STAGES + NACC + h * ACC_STAGES + a); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 8 * (2 * STAGES + 2 * NACC));
+#else
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + ACC_STAGES + a); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 8 * (2 * STAGES + 2 * ACC_STAGES));
+#endif
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+#ifdef NN_TC_DECOUPLE
+    for (int h = 0; h < MH; ++h)
+      for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(h, a), 1); mbar_init(tempty_bar(h, a), EPI_WARPS / MH); }
+#else
     for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+#endif
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WARP_MMA) {
@@ -485,9 +505,13 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
         uint32_t ph = (uint32_t)(t / STAGES) & 1u;
         int a = t % ACC_STAGES;
         uint32_t aph = (uint32_t)(t / ACC_STAGES) & 1u;
+#ifdef NN_TC_DECOUPLE
+        mbar_wait(full_bar(s), ph);
+#else
         mbar_wait(tempty_bar(a), aph ^ 1u);
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
+#endif
 #ifdef NN_TC_EXP_NOMMA   // timing experiment only (wrong results): TMA stream + barrier hand-offs, no tensor work
         mbar_arrive(empty_bar(s));
         mbar_arrive(tfull_bar(a));
@@ -495,6 +519,10 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
 #endif
 #pragma unroll
         for (int h = 0; h < MH; ++h) {
+#ifdef NN_TC_DECOUPLE
+          mbar_wait(tempty_bar(h, a), aph ^ 1u);
+          tc_fence_after();
+#endif
           const uint32_t d_tmem = tmem_base + (uint32_t)((h * ACC_STAGES + a) * BN);
 #pragma unroll
           for (int kk = 0; kk < DK / 8; ++kk) {
@@ -516,9 +544,14 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
               tc_mma_tf32(d_tmem, da, db, IDESC, 1u);
             }
           }
+#ifdef NN_TC_DECOUPLE
+          tc_commit(tfull_bar(h, a));   // this query tile's accumulator is ready for its epilogue warps
+#endif
         }
         tc_commit(empty_bar(s));   // smem stage free once these MMAs retire
+#ifndef NN_TC_DECOUPLE
         tc_commit(tfull_bar(a));   // accumulator ready for the epilogue
+#endif
       }
     }
   } else {
@@ -558,7 +591,11 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
 #ifdef NN_TC_DEBUG_CYCLES
       const long long c0 = clock64();
 #endif
+#ifdef NN_TC_DECOUPLE
+      mbar_wait(tfull_bar(half, a), aph);
+#else
       mbar_wait(tfull_bar(a), aph);
+#endif
       tc_fence_after();
 #ifdef NN_TC_DEBUG_CYCLES
       const long long c1 = clock64();
@@ -578,7 +615,11 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
 #endif
       tc_fence_before();
       __syncwarp();
+#ifdef NN_TC_DECOUPLE
+      if (lane == 0) mbar_arrive(tempty_bar(half, a));
+#else
       if (lane == 0) mbar_arrive(tempty_bar(a));      // one arrival per warp
+#endif
 #ifdef NN_TC_EXP_NOALU  // timing experiment only (wrong results): no arg-max arithmetic
       if (v[t & (EPI_COLS - 1)] == 123.456f) run_max = v[5];
       continue;
