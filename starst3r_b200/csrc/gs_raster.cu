@@ -10,8 +10,11 @@
 // vector atomicAdd per (tile, Gaussian) record to HBM.
 // Algorithmic bytes: fwd 40 B per intersection + 20 B per pixel;
 // bwd 40 B per intersection + 24 B per pixel + 36 B of gradient per visible (Gaussian, view).
+#ifndef ST3R_HOST_EMU   // tests/host/raster_emu_host.cpp runs the kernels of this file on the host (tests/host/simt_emu.h)
 #include "common.cuh"
 #include "gs.cuh"
+#define ST3R_EMU_COUNT(i)
+#endif                  // (there ST3R_EMU_COUNT(i) counts how often a code path ran: path coverage of the emulated run)
 
 namespace {
 
@@ -487,7 +490,11 @@ raster_bwd_queue_kernel(const int32_t* __restrict__ offsets, const int32_t* __re
           // 1 - alpha lies in [1e-3, 1]: rcp.approx (MUFU.RCP, 1 ulp) instead of the 15-instruction IEEE division;
           // the error is of the size of the forward's own rounding of T
           float ra;
+#ifdef ST3R_HOST_EMU
+          ra = 1.0f / (1.0f - alpha);
+#else
           asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(1.0f - alpha));
+#endif
           T *= ra;
           fac = alpha * T;
           const float4 col = sC[t];
@@ -500,14 +507,17 @@ raster_bwd_queue_kernel(const int32_t* __restrict__ offsets, const int32_t* __re
         // (the votes only restate warp-uniform conditions in a form the compiler's divergence analysis accepts, so
         // that the shuffles below are not wrapped in WARPSYNC / ENDCOLLECTIVE pairs)
         if (__any_sync(0xffffffffu, nv >= DENSE_MIN)) {
+          ST3R_EMU_COUNT(0);
           float g[9];
           blend_grad_terms(sA[t], sB[t], dx, dy, fac, w, vr, vg, vb, g);   // fac = w = 0 on the other lanes
           butterfly9_to_shared(g, acc[t]);
         } else {
           if (__any_sync(0xffffffffu, qlen + nv > QW)) {
+            ST3R_EMU_COUNT(1);
             drain_queue(qlen, qk, qf, qv, sA, sB, acc, vr, vg, vb, px0, py0);
             qlen = 0;
           }
+          ST3R_EMU_COUNT(2);
           if (valid) {
             const int pos = qlen + __popc(vm & lanes_below);
             qk[pos] = ((uint32_t)t << 5) | (uint32_t)lane;
@@ -535,6 +545,7 @@ raster_bwd_queue_kernel(const int32_t* __restrict__ offsets, const int32_t* __re
 
 }  // namespace
 
+#ifndef ST3R_HOST_EMU
 static int g_raster_bwd_variant = 0;   // 0: per-visit butterfly (default), 1: per-warp record queues
 
 extern "C" {
@@ -590,3 +601,4 @@ int st3r_gs_raster_bwd(const int32_t* offsets, const int32_t* n_isect, const uin
   return ST3R_OK;
 }
 }
+#endif  // ST3R_HOST_EMU

@@ -1,0 +1,226 @@
+// TEST-ONLY: a small SIMT emulator that runs the SOURCE of a CUDA kernel on the host, one CTA at a time, every CUDA
+// thread as a cooperatively scheduled fiber (ucontext) of ONE OS thread.  Block barriers and warp collectives are
+// rendezvous points: a fiber that reaches one yields until all its peers have arrived, so shuffles, votes, redux and
+// __syncthreads have their CUDA meaning, a missing peer shows up as a reported deadlock instead of a hang, and the
+// kernel's indexing / queueing / reduction logic is exercised exactly as written.  What it does NOT model: memory
+// consistency (one OS thread: every store is immediately visible), timing, bank conflicts, divergent collectives
+// (all 32 lanes of a warp must execute the same sequence of collectives - true of the kernels tested with it).
+// Used by tests/host/raster_emu_host.cpp; never part of the product library.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <functional>
+#include <vector>
+
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct uint3 { unsigned x, y, z; };
+struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static   // one CTA runs at a time; the harness re-zeroes nothing: kernels must initialise what they read
+
+namespace emu {
+
+constexpr int WARP = 32;
+constexpr size_t STACK = 256 * 1024;
+
+struct Fiber {
+  ucontext_t ctx;
+  std::vector<char> stack;
+  uint3 tid;
+  bool done = false;
+};
+
+struct WarpState {
+  uint64_t slot[WARP];     // values published by the lanes for the collective in flight
+  int arrived = 0;         // lanes that published
+  int departed = 0;        // lanes that consumed
+  unsigned generation = 0;
+};
+
+struct Cta {
+  std::vector<Fiber> fibers;
+  std::vector<WarpState> warps;
+  int bar_arrived = 0;
+  unsigned bar_generation = 0;
+  int bar_count_true = 0, bar_count_result = 0;
+  ucontext_t sched;
+  int cur = -1;
+  long progress = 0;       // arrivals, departures and exits: a scheduler round without any is a deadlock
+};
+
+static Cta* g_cta = nullptr;
+static uint3 g_blockIdx;
+static dim3 g_blockDim, g_gridDim;
+static std::function<void()> g_body;
+
+static inline Fiber& self() { return g_cta->fibers[g_cta->cur]; }
+static inline void yield() { swapcontext(&self().ctx, &g_cta->sched); }
+
+static void trampoline() {
+  g_body();
+  self().done = true;
+  ++g_cta->progress;
+  swapcontext(&self().ctx, &g_cta->sched);
+}
+
+// Runs `body` once per thread of a CTA of `nthreads` threads.  Returns false on deadlock (no fiber can progress).
+static bool run_cta(int nthreads, const std::function<void()>& body) {
+  Cta cta;
+  cta.fibers.resize(nthreads);
+  cta.warps.resize((nthreads + WARP - 1) / WARP);
+  g_cta = &cta;
+  g_body = body;
+  for (int t = 0; t < nthreads; ++t) {
+    Fiber& f = cta.fibers[t];
+    f.stack.resize(STACK);
+    f.tid = uint3{(unsigned)t, 0, 0};
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack.data();
+    f.ctx.uc_stack.ss_size = STACK;
+    f.ctx.uc_link = nullptr;
+    makecontext(&f.ctx, trampoline, 0);
+  }
+  int alive = nthreads;
+  while (alive > 0) {
+    alive = 0;
+    const long before = cta.progress;
+    for (int t = 0; t < nthreads; ++t) {
+      if (cta.fibers[t].done) continue;
+      ++alive;
+      cta.cur = t;
+      swapcontext(&cta.sched, &cta.fibers[t].ctx);
+    }
+    // fibers only block at rendezvous points: a round in which nobody arrived, departed or finished cannot be followed
+    // by a better one
+    if (alive > 0 && cta.progress == before) {
+      fprintf(stderr, "simt_emu: deadlock (%d fibers blocked at a barrier / warp collective)\n", alive);
+      g_cta = nullptr;
+      return false;
+    }
+  }
+  g_cta = nullptr;
+  return true;
+}
+
+// ---- block barrier
+static inline int syncthreads_count(int pred) {
+  Cta& c = *g_cta;
+  const unsigned gen = c.bar_generation;
+  c.bar_count_true += pred ? 1 : 0;
+  ++c.progress;
+  if (++c.bar_arrived == (int)c.fibers.size()) {
+    c.bar_arrived = 0;
+    c.bar_count_result = c.bar_count_true;
+    c.bar_count_true = 0;
+    ++c.bar_generation;
+  } else {
+    while (c.bar_generation == gen) yield();
+  }
+  return c.bar_count_result;
+}
+
+// ---- warp collectives: publish, wait for all 32 lanes, read, wait for all lanes to have read
+template <typename F>
+static inline uint64_t warp_collective(uint64_t v, F&& combine) {
+  Cta& c = *g_cta;
+  const int lane = self().tid.x % WARP;
+  WarpState& w = c.warps[self().tid.x / WARP];
+  const unsigned gen = w.generation;
+  w.slot[lane] = v;
+  ++w.arrived;
+  ++c.progress;
+  while (w.arrived < WARP && w.generation == gen) yield();
+  const uint64_t r = combine(w.slot, lane);
+  ++c.progress;
+  if (++w.departed == WARP) {
+    w.arrived = 0;
+    w.departed = 0;
+    ++w.generation;
+  } else {
+    while (w.generation == gen) yield();
+  }
+  return r;
+}
+
+}  // namespace emu
+
+#define threadIdx (emu::self().tid)
+#define blockIdx (emu::g_blockIdx)
+#define blockDim (emu::g_blockDim)
+#define gridDim (emu::g_gridDim)
+
+static inline uint64_t emu_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float emu_float(uint64_t b) { uint32_t u = (uint32_t)b; float f; memcpy(&f, &u, 4); return f; }
+
+static inline void __syncthreads() { emu::syncthreads_count(0); }
+static inline int __syncthreads_count(int p) { return emu::syncthreads_count(p); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_collective(0, [](const uint64_t*, int) { return (uint64_t)0; }); }
+
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  return (unsigned)emu::warp_collective(pred ? 1 : 0, [](const uint64_t* s, int) {
+    uint64_t m = 0;
+    for (int l = 0; l < 32; ++l) m |= (s[l] & 1) << l;
+    return m;
+  });
+}
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
+
+static inline uint64_t emu_shfl(uint64_t v, int src) {
+  return emu::warp_collective(v, [src](const uint64_t* s, int lane) { return (src >= 0 && src < 32) ? s[src] : s[lane]; });
+}
+static inline uint64_t emu_shfl_lane(uint64_t v, int mode, int arg) {   // per-lane source: 0 xor, 1 down, 2 up
+  return emu::warp_collective(v, [mode, arg](const uint64_t* s, int lane) {
+    int src = mode == 0 ? (lane ^ arg) : mode == 1 ? lane + arg : lane - arg;
+    return (src >= 0 && src < 32) ? s[src] : s[lane];
+  });
+}
+static inline float __shfl_sync(unsigned, float v, int src) { return emu_float(emu_shfl(emu_bits(v), src & 31)); }
+static inline int __shfl_sync(unsigned, int v, int src) { return (int)(uint32_t)emu_shfl((uint32_t)v, src & 31); }
+static inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return (unsigned)emu_shfl(v, src & 31); }
+static inline float __shfl_xor_sync(unsigned, float v, int m) { return emu_float(emu_shfl_lane(emu_bits(v), 0, m)); }
+static inline int __shfl_xor_sync(unsigned, int v, int m) { return (int)(uint32_t)emu_shfl_lane((uint32_t)v, 0, m); }
+static inline float __shfl_down_sync(unsigned, float v, int d) { return emu_float(emu_shfl_lane(emu_bits(v), 1, d)); }
+static inline unsigned __shfl_down_sync(unsigned, unsigned v, int d) { return (unsigned)emu_shfl_lane(v, 1, d); }
+static inline unsigned __shfl_up_sync(unsigned, unsigned v, int d) { return (unsigned)emu_shfl_lane(v, 2, d); }
+
+static inline unsigned __reduce_or_sync(unsigned, unsigned v) {
+  return (unsigned)emu::warp_collective(v, [](const uint64_t* s, int) { uint64_t r = 0; for (int l = 0; l < 32; ++l) r |= s[l]; return r; });
+}
+static inline int __reduce_max_sync(unsigned, int v) {
+  return (int)(int64_t)emu::warp_collective((uint64_t)(int64_t)v, [](const uint64_t* s, int) {
+    int64_t r = (int64_t)s[0];
+    for (int l = 1; l < 32; ++l) r = (int64_t)s[l] > r ? (int64_t)s[l] : r;
+    return (uint64_t)r;
+  });
+}
+
+static inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+#define __expf(x) expf(x)   // glibc declares __expf itself
+template <typename T> static inline T min(T a, T b) { return a < b ? a : b; }
+template <typename T> static inline T max(T a, T b) { return a > b ? a : b; }
+
+// one OS thread: plain read-modify-write
+static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+static inline float4 atomicAdd(float4* p, float4 v) {
+  float4 o = *p;
+  p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w;
+  return o;
+}
+
+static inline int lane_id() { return (int)(threadIdx.x & 31); }

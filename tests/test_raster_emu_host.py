@@ -1,0 +1,141 @@
+"""CPU: the blend kernels' OWN SOURCE (starst3r_b200/csrc/gs_raster.cu: raster_fwd_kernel, raster_bwd_kernel and the
+record-queue variant raster_bwd_queue_kernel) compiled for the host and executed thread by thread by a small SIMT
+emulator (tests/host/simt_emu.h: fibers, rendezvous semantics for __syncthreads / shuffles / votes / redux, deadlock
+detection), against a direct float64 evaluation of gsplat's rasterize_to_pixels forward / backward (SURVEY Appendix
+A.6).  This runs the code the GPU will run - indexing, visit lists, queue appends, drains, segmented scans, the dense
+bypass, barriers - without a GPU; what it cannot show is timing and memory-model behaviour."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from test_raster_queue_host import ALPHA_MAX, ALPHA_MIN, T_MIN, contribution, grad_terms
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TILE = 16
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = tmp_path_factory.mktemp("emu") / "libraster_emu.so"
+    src = os.path.join(ROOT, "tests", "host", "raster_emu_host.cpp")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src, "-o", str(out)], check=True)
+    return ctypes.CDLL(str(out))
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def make_frame(n, C, W, H, sigma_small, sigma_large, seed):
+    """Entries e = c * n + g with random 2-D Gaussians; per (camera, tile) lists sorted by depth."""
+    rng = np.random.default_rng(seed)
+    E = C * n
+    A = np.zeros((E, 4), np.float32)          # x, y, opacity, depth
+    B = np.zeros((E, 4), np.float32)          # conic a, b, c
+    col = np.zeros((E, 4), np.float32)
+    A[:, 0] = rng.uniform(-4, W + 4, E)
+    A[:, 1] = rng.uniform(-4, H + 4, E)
+    A[:, 2] = rng.uniform(0.05, 0.7, E)
+    A[:, 3] = rng.uniform(1, 10, E)
+    big = rng.random(E) < 0.15
+    s = np.where(big[:, None], sigma_large, sigma_small) * np.exp(0.3 * rng.standard_normal((E, 2)))
+    rho = rng.uniform(-0.5, 0.5, E)
+    cov = np.stack([s[:, 0] ** 2, rho * s[:, 0] * s[:, 1], s[:, 1] ** 2], 1)
+    det = cov[:, 0] * cov[:, 2] - cov[:, 1] ** 2
+    B[:, 0], B[:, 1], B[:, 2] = cov[:, 2] / det, -cov[:, 1] / det, cov[:, 0] / det
+    col[:, :3] = rng.uniform(0, 1, (E, 3))
+    radius = 3.5 * s.max(1) + 1
+    tw, th = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
+    flatten, offsets = [], []
+    for c in range(C):
+        for ty in range(th):
+            for tx in range(tw):
+                offsets.append(len(flatten))
+                e = np.arange(c * n, (c + 1) * n)
+                hit = ((A[e, 0] + radius[e] > tx * TILE) & (A[e, 0] - radius[e] < (tx + 1) * TILE) &
+                       (A[e, 1] + radius[e] > ty * TILE) & (A[e, 1] - radius[e] < (ty + 1) * TILE))
+                ids = e[hit]
+                flatten.extend(ids[np.argsort(A[ids, 3], kind="stable")].tolist())
+    return (A, B, col, np.asarray(offsets, np.int32), np.asarray([len(flatten)], np.int32),
+            np.asarray(flatten + [0], np.uint32), tw, th)
+
+
+def reference(A, B, col, offsets, n_isect, flatten, tw, th, C, W, H, v_render, v_alphas):
+    """float64, pixel by pixel: forward outputs and the gradients w.r.t. (x, y, opacity), conic and colour."""
+    A64, B64, c64 = A.astype(np.float64), B.astype(np.float64), col.astype(np.float64)[:, :3]
+    render = np.zeros((C, H, W, 3))
+    alphas = np.zeros((C, H, W))
+    g = np.zeros((A.shape[0], 9))
+    ends = list(offsets[1:]) + [int(n_isect[0])]
+    for c in range(C):
+        for i in range(H):
+            for j in range(W):
+                t = c * tw * th + (i // TILE) * tw + (j // TILE)
+                ids = flatten[offsets[t]:ends[t]]
+                px, py = j + 0.5, i + 0.5
+                T, last, rgb = 1.0, -1, np.zeros(3)
+                for k, e in enumerate(ids):
+                    dx, dy = A64[e, 0] - px, A64[e, 1] - py
+                    sigma = 0.5 * (B64[e, 0] * dx * dx + B64[e, 2] * dy * dy) + B64[e, 1] * dx * dy
+                    alpha = min(ALPHA_MAX, A64[e, 2] * np.exp(-sigma))
+                    if sigma < 0 or alpha < ALPHA_MIN:
+                        continue
+                    nT = T * (1 - alpha)
+                    if nT <= T_MIN:
+                        break
+                    rgb += c64[e] * alpha * T
+                    T, last = nT, k
+                render[c, i, j], alphas[c, i, j] = rgb, 1 - T
+                Tb, buf = T, np.zeros(3)
+                for k in range(last, -1, -1):
+                    e = ids[k]
+                    r = contribution(px, py, A64[e], B64[e], c64[e], Tb, buf, T, v_render[c, i, j], v_alphas[c, i, j])
+                    if r is None:
+                        continue
+                    fac, w, Tb, buf = r
+                    g[e] += grad_terms(A64[e], B64[e], A64[e, 0] - px, A64[e, 1] - py, fac, w, v_render[c, i, j])
+    return render, alphas, g
+
+
+@pytest.mark.parametrize("n,C,W,H,ss,sl,seed", [(420, 2, 40, 24, 0.8, 5.0, 0), (700, 1, 24, 24, 0.7, 3.0, 1)])
+def test_blend_kernels_on_the_simt_emulator(emu, n, C, W, H, ss, sl, seed):
+    A, B, col, offsets, n_isect, flatten, tw, th = make_frame(n, C, W, H, ss, sl, seed)
+    per_tile = np.diff(np.r_[offsets, n_isect])
+    assert per_tile.max() > 256 or n < 500            # the larger case walks more than one 256-Gaussian batch per tile
+    rng = np.random.default_rng(seed + 10)
+    v_render = rng.standard_normal((C, H, W, 3)).astype(np.float32)
+    v_alphas = rng.standard_normal((C, H, W)).astype(np.float32)
+    render = np.zeros((C, H, W, 3), np.float32)
+    alphas = np.zeros((C, H, W), np.float32)
+    last_ids = np.zeros((C, H, W), np.int32)
+    n_blend = np.zeros(1, np.uint64)
+    rc = emu.emu_raster_fwd(P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), C, W, H, P(render), P(alphas),
+                            P(last_ids), P(n_blend))
+    assert rc == 0, "deadlock in raster_fwd_kernel"
+    want_render, want_alphas, want_g = reference(A, B, col, offsets, n_isect, flatten, tw, th, C, W, H, v_render, v_alphas)
+    assert np.abs(render - want_render).max() < 2e-5 and np.abs(alphas - want_alphas).max() < 2e-5
+    assert int(n_blend[0]) > 5 * C * H * W
+    scale = np.abs(want_g).max(0) + 1e-12
+    got = {}
+    for variant in (0, 1):
+        vA = np.zeros_like(A)
+        vB = np.zeros_like(B)
+        vC = np.zeros_like(col)
+        rc = emu.emu_raster_bwd(variant, P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), C, W, H, P(alphas),
+                                P(last_ids), P(v_render), P(v_alphas), P(vA), P(vB), P(vC))
+        assert rc == 0, f"deadlock in the backward kernel, variant {variant}"
+        g = np.concatenate([vA[:, :3], vB[:, :3], vC[:, :3]], axis=1)
+        got[variant] = g
+        err = np.abs(g - want_g).max(0) / scale
+        assert err.max() < 2e-4, (variant, err)       # fp32 kernels (and fp32 forward state) vs the float64 evaluation
+        assert np.all(vA[:, 3] == 0) and np.all(vB[:, 3] == 0) and np.all(vC[:, 3] == 0)
+    assert (np.abs(got[0] - got[1]).max(0) / scale).max() < 1e-4
+    # path coverage of the queue kernel in this run (per-lane hits): dense bypass, mid-batch overflow drain, appends
+    counts = (ctypes.c_long * 8)()
+    emu.emu_counts(counts, 1)
+    assert counts[0] > 0 and counts[2] > 0, list(counts)
+    if per_tile.max() > 256:
+        assert counts[1] > 0, list(counts)
