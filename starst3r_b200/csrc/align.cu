@@ -12,7 +12,10 @@
 //   align_cam_bwd   (1 CTA)  camera-record gradients -> MST chain backward -> parameter gradients -> Adam
 // HBM traffic per iteration is the correspondence list (~40 B per correspondence slot); the
 // loop is latency-bound, so the figure of merit is iterations/s.
+#ifndef ST3R_HOST_EMU   // tests/host/align_emu_host.cpp runs the kernels of this file on the host (tests/host/simt_emu.h)
 #include "common.cuh"
+#define ST3R_DYN_SMEM(name) extern __shared__ float name[]
+#endif
 #include "align_math.cuh"
 #include "../../include/starst3r_b200.h"
 
@@ -134,7 +137,7 @@ __device__ __forceinline__ Anchor load_anchor(const St3rAlignProblem& pb, const 
 // loss_3d: sum conf * gamma(|P1 - P2|) / norm   (reconstruct.py:325-353)
 __global__ void __launch_bounds__(LOSS_THREADS)
 align_loss3d_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, float off_pow, float scale) {
-  extern __shared__ float table[];
+  ST3R_DYN_SMEM(table);
   if (w.sums[3] != 0.f) return;
   const int N = pb.n_img;
   const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
@@ -176,7 +179,7 @@ align_loss3d_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, floa
 // loss_2d: sum conf * gamma(|pix1 - reproj(K1 w2cam1, P2)|) / norm   (reconstruct.py:355-369)
 __global__ void __launch_bounds__(LOSS_THREADS)
 align_loss2d_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, float off_pow, float scale) {
-  extern __shared__ float table[];
+  ST3R_DYN_SMEM(table);
   if (w.sums[3] != 0.f) return;
   const int N = pb.n_img;
   const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
@@ -222,7 +225,7 @@ align_loss2d_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, floa
 // loss_dust3r: sum conf * gamma(|P1 - cam2w[img2] tgt|) / norm   (reconstruct.py:311-323)
 __global__ void __launch_bounds__(LOSS_THREADS)
 align_lossd_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, float off_pow, float scale) {
-  extern __shared__ float table[];
+  ST3R_DYN_SMEM(table);
   if (w.sums[3] != 0.f) return;
   const int N = pb.n_img;
   const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
@@ -375,7 +378,7 @@ template <int KIND>
 __global__ void __launch_bounds__(LOSS_THREADS)
 align_loss_seg_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, float off_pow, float scale, int per_warp,
                       float* loss_out) {
-  extern __shared__ float table[];
+  ST3R_DYN_SMEM(table);
   if (w.sums[3] != 0.f) return;
   const int N = pb.n_img;
   const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
@@ -539,6 +542,7 @@ __global__ void align_outputs_kernel(St3rAlignProblem pb, Work w, float* pts3d, 
   }
 }
 
+#ifndef ST3R_HOST_EMU
 Work carve(void* ws, int N) {
   WsAlloc a(ws, (size_t)-1);
   Work w;
@@ -550,9 +554,11 @@ Work carve(void* ws, int N) {
   w.gscal = a.take<float>(4);
   return w;
 }
+#endif  // ST3R_HOST_EMU
 
 }  // namespace
 
+#ifndef ST3R_HOST_EMU
 // bit 0: segmented accumulation in the loss kernels (align_loss_seg_kernel); bit 1: one thread-block cluster per image
 // in st3r_focal_weiszfeld (align_dense.cu).  0 = the variants every committed profile was measured with.
 static int g_align_variant = 0;
@@ -690,3 +696,4 @@ int st3r_align_optimize(const St3rAlignProblem* prob, float* pp, float* log_foca
 }
 
 }  // extern "C"
+#endif  // ST3R_HOST_EMU

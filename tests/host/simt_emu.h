@@ -197,6 +197,13 @@ static inline float __shfl_down_sync(unsigned, float v, int d) { return emu_floa
 static inline unsigned __shfl_down_sync(unsigned, unsigned v, int d) { return (unsigned)emu_shfl_lane(v, 1, d); }
 static inline unsigned __shfl_up_sync(unsigned, unsigned v, int d) { return (unsigned)emu_shfl_lane(v, 2, d); }
 
+static inline unsigned __match_any_sync(unsigned, int v) {
+  return (unsigned)emu::warp_collective((uint64_t)(uint32_t)v, [](const uint64_t* s, int lane) {
+    uint64_t m = 0;
+    for (int l = 0; l < 32; ++l) m |= (uint64_t)(s[l] == s[lane]) << l;
+    return m;
+  });
+}
 static inline unsigned __reduce_or_sync(unsigned, unsigned v) {
   return (unsigned)emu::warp_collective(v, [](const uint64_t* s, int) { uint64_t r = 0; for (int l = 0; l < 32; ++l) r |= s[l]; return r; });
 }
