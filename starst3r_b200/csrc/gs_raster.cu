@@ -484,7 +484,10 @@ raster_bwd_queue_kernel(const int32_t* __restrict__ offsets, const int32_t* __re
           if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
         }
         const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+        ST3R_EMU_COUNT(3);                 // visits (x 32 lanes)
         if (!vm) continue;
+        ST3R_EMU_COUNT(4);                 // visits with at least one contributing lane (x 32)
+        if (valid) ST3R_EMU_COUNT(5);      // contributing (pixel, Gaussian) pairs
         float fac = 0.f, w = 0.f;
         if (valid) {                    // the part that is sequential per pixel
           // 1 - alpha lies in [1e-3, 1]: rcp.approx (MUFU.RCP, 1 ulp) instead of the 15-instruction IEEE division;

@@ -8,6 +8,8 @@ static long g_emu_count[8];     // per-lane hits of the marked code paths of the
 #define ST3R_EMU_COUNT(i) (++g_emu_count[i])
 #include "../../starst3r_b200/csrc/gs_raster.cu"
 
+static int g_tile_stride = 1;   // > 1: only every g_tile_stride-th tile runs (statistics on samples of large frames)
+
 namespace {
 template <typename K>
 int run_grid(int tiles, int C, K&& kernel_body) {
@@ -15,6 +17,7 @@ int run_grid(int tiles, int C, K&& kernel_body) {
   emu::g_gridDim = dim3(tiles, C, 1);
   for (int c = 0; c < C; ++c)
     for (int t = 0; t < tiles; ++t) {
+      if (t % g_tile_stride) continue;
       emu::g_blockIdx = uint3{(unsigned)t, (unsigned)c, 0};
       if (!emu::run_cta(BLOCK, kernel_body)) return -1;
     }
@@ -23,6 +26,8 @@ int run_grid(int tiles, int C, K&& kernel_body) {
 }  // namespace
 
 extern "C" {
+
+void emu_set_tile_stride(int stride) { g_tile_stride = stride > 0 ? stride : 1; }
 
 void emu_counts(long* out8, int reset) {
   for (int i = 0; i < 8; ++i) { out8[i] = g_emu_count[i]; if (reset) g_emu_count[i] = 0; }
