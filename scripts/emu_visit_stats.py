@@ -76,7 +76,7 @@ def main():
           f"({100 * dense / max(contrib, 1):.0f} % dense, {100 * queued / max(contrib, 1):.0f} % queued)")
     empty = visits - contrib
     default = empty * 50 + contrib * 190
-    queue = empty * 50 + dense * 190 + queued * 110 + (pairs - dense * 8) * 5
+    queue = empty * 50 + dense * 190 + queued * 110 + max(pairs - dense * 20, 0) * 5.5
     print(f"static-count model (DESIGN.md §10): default {default / tiles:.0f}, queue variant {queue / tiles:.0f} warp "
           f"instructions per tile -> x{default / queue:.2f}")
 

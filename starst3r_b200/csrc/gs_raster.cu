@@ -303,8 +303,10 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
 // shared-memory update per segment head.  Visits with many contributing lanes (large splats: the log-normal scale
 // sweep) keep the direct butterfly, which is the efficient shape for them.
 constexpr int QW = 160;          // records per warp queue
-constexpr int DENSE_MIN = 8;     // visits with at least this many contributing lanes reduce directly (static SASS
-                                 // counts: ~11 instructions per queued record vs ~70 for one butterfly)
+constexpr int DENSE_MIN = 16;    // visits with at least this many contributing lanes reduce directly: a butterfly
+                                 // costs ~70 instructions more than a queued visit, a queued record ~5 (static
+                                 // SASS counts), and on the headline workload no 2 x 16 strip sees more than 15
+                                 // contributing lanes of a 3e-3 splat (scripts/emu_visit_stats.py)
 
 // Warp-collective: reduces g[0..8] over the warp and adds the totals to a9[0..8] (shared memory).
 __device__ __forceinline__ void butterfly9_to_shared(const float* g, float* a9) {

@@ -7,7 +7,7 @@ The CUDA code itself is checked on the GPU by tests/test_experimental_gpu.py."""
 import numpy as np
 
 ALPHA_MIN, ALPHA_MAX, T_MIN = 1.0 / 255.0, 0.999, 1e-4
-QW, DENSE_MIN, BLOCK = 160, 8, 256
+QW, DENSE_MIN, BLOCK = 160, 16, 256
 
 
 def forward(px, py, A, B, col):
