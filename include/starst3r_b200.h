@@ -173,8 +173,10 @@ ST3R_API int st3r_gs_raster_fwd(const int32_t* offsets, const int32_t* n_isect, 
                        cudaStream_t stream);
 /* Implementation variant of st3r_gs_raster_bwd for subsequent calls of this process: 0 (default) reduces the nine
  * gradient terms of every (warp, Gaussian) visit across the warp; 1 queues (Gaussian, pixel, alpha T, vis dL/dalpha)
- * records per warp and turns them into gradients 32 records at a time (meant for small splats, where 3 of 32 lanes
- * contribute per visit).  Same terms per (pixel, Gaussian); only the fp32 summation order differs. */
+ * records per warp and turns them into gradients 32 records at a time (meant for small splats, where few of the 32
+ * lanes contribute per visit); 2 evaluates alpha Gaussian-parallel over each splat's bounding box inside the tile
+ * into a shared-memory fragment pool, runs only the per-pixel recurrence in the visits and sums the gradients
+ * Gaussian-parallel again.  Same terms per (pixel, Gaussian); only the fp32 summation order differs. */
 ST3R_API int st3r_gs_set_raster_variant(int variant);
 /* rasterize_to_pixels backward: accumulates into v_geomA = (v_x, v_y, v_opacity, 0), v_geomB = v_conic,
  * v_rgb (all float4 [C*N], zeroed by the caller).  v_alphas may be NULL. */

@@ -59,7 +59,7 @@ def main():
     rng = np.random.default_rng(0)
     v_render = rng.standard_normal((1, H, W, 3)).astype(np.float32)
     vA, vB, vC = np.zeros_like(A), np.zeros_like(B), np.zeros_like(col)
-    counts = (ctypes.c_long * 8)()
+    counts = (ctypes.c_long * 16)()
     emu.emu_counts(counts, 1)
     assert emu.emu_raster_bwd(1, P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), 1, W, H, P(alphas), P(last_ids),
                               P(v_render), None, P(vA), P(vB), P(vC)) == 0
@@ -79,6 +79,14 @@ def main():
     queue = empty * 50 + dense * 190 + queued * 110 + max(pairs - dense * 20, 0) * 5.5
     print(f"static-count model (DESIGN.md §10): default {default / tiles:.0f}, queue variant {queue / tiles:.0f} warp "
           f"instructions per tile -> x{default / queue:.2f}")
+    # variant 2 (fragment pool)
+    vA[:], vB[:], vC[:] = 0, 0, 0
+    assert emu.emu_raster_bwd(2, P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), 1, W, H, P(alphas), P(last_ids),
+                              P(v_render), None, P(vA), P(vB), P(vC)) == 0
+    emu.emu_counts(counts, 1)
+    tested, visits2, dense2, frags = counts[8], counts[9] / 32, counts[6] / 32, counts[7]
+    print(f"fragment pool: {tested / max(per_tile.sum(), 1):.1f} box pixels tested per intersection in phase A, "
+          f"{visits2 / tiles:.0f} phase-B visits per tile ({dense2 / tiles:.1f} dense), {frags / tiles:.0f} pool fragments per tile")
 
 
 if __name__ == "__main__":

@@ -548,6 +548,259 @@ raster_bwd_queue_kernel(const int32_t* __restrict__ offsets, const int32_t* __re
   }
 }
 
+// ---- variant 2 of the backward: fragment pool -----------------------------------------------------------------------
+// Measured on the headline workload (scripts/emu_visit_stats.py): a tile sees 386 Gaussians in 842 (warp, Gaussian)
+// visits, every visit evaluates alpha on 32 lanes and 5.6 of them contribute.  Here the alpha test leaves the visits:
+//   A. Gaussian-parallel: four threads per Gaussian walk its bounding box inside the tile (conservative extents of
+//      the alpha >= 1/255 ellipse, ~7 x 7 pixels for a 3e-3 splat), write a 16-bit contribution mask per tile row and
+//      (alpha, vis) of every contributing pixel into the Gaussian's box-addressed slots of a shared-memory pool;
+//   B. pixel-parallel, as before back to front, but a warp only visits Gaussians whose masks touch its two rows and a
+//      lane only reads its slot, runs the per-pixel recurrence (transmittance, colour behind, dL/dalpha) and writes
+//      (alpha T, vis dL/dalpha) back: no alpha test, no gradient arithmetic, no reduction in the visit;
+//   C. Gaussian-parallel again: the four threads of a Gaussian turn its slots into the nine gradient sums in
+//      registers, two shuffles combine them: no atomics at all for these Gaussians.
+// Gaussians whose box has more than FRAG_SLOTS pixels (large splats) keep the dense path of raster_bwd_kernel inside
+// phase B (alpha on the fly, butterfly into the accumulators), in the same back-to-front order.
+constexpr int FG = 64;            // Gaussians per batch
+constexpr int FRAG_SLOTS = 64;    // pool slots per Gaussian = largest bounding box (pixels) that takes the pool path
+
+struct FragBox { uint8_t r0, c0, wc, nr; };    // first row / column of the box inside the tile, its width and height;
+constexpr int FRAG_BIG = 0x80;                  // nr & FRAG_BIG: more than FRAG_SLOTS pixels, dense path
+
+// 1 - alpha lies in [1e-3, 1]: rcp.approx (MUFU.RCP, 1 ulp) instead of the 15-instruction IEEE division
+__device__ __forceinline__ float fast_rcp(float x) {
+#ifdef ST3R_HOST_EMU
+  return 1.0f / x;
+#else
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#endif
+}
+
+__global__ void __launch_bounds__(BLOCK)
+raster_bwd_frag_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
+                       const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
+                       const float4* __restrict__ geomB, const float4* __restrict__ rgb, int C, int W, int H,
+                       int tile_w, int tile_h, const float* __restrict__ alphas, const int32_t* __restrict__ last_ids,
+                       const float* __restrict__ v_render, const float* __restrict__ v_alphas,
+                       float4* __restrict__ v_geomA, float4* __restrict__ v_geomB, float4* __restrict__ v_rgb) {
+  __shared__ float4 sA[FG], sB[FG], sC[FG];
+  __shared__ uint32_t sE[FG];
+  __shared__ uint16_t sMask[FG][TILE];
+  __shared__ FragBox sBox[FG];
+  __shared__ float2 sPool[FG][FRAG_SLOTS];
+  __shared__ float acc[FG][9];
+  __shared__ float4 sV[BLOCK];                 // upstream colour gradient of every pixel of the tile
+  const int c = blockIdx.y, tile = blockIdx.x;
+  const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
+  const int tr = threadIdx.x;
+  const int i = tyi * TILE + (tr >> 4), j = txi * TILE + (tr & 15);
+  const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+  const bool inside = i < H && j < W;
+  const int wrp = tr >> 5, lane = tr & 31;
+  const int myrow = tr >> 4, mycol = tr & 15;
+  const float px0 = (float)(txi * TILE) + 0.5f, py0 = (float)(tyi * TILE) + 0.5f;   // centre of the tile's first pixel
+  const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
+  if (rg.hi <= rg.lo) return;
+  const size_t p = ((size_t)c * H + min(i, H - 1)) * W + min(j, W - 1);
+  const float T_final = 1.0f - alphas[p];
+  float T = T_final;
+  float behind_v = 0.f;                        // (colour behind the current Gaussian) . (upstream colour gradient)
+  const int bin_final = inside ? last_ids[p] : 0;
+  float vr = 0.f, vg = 0.f, vb = 0.f, va = 0.f;
+  if (inside) {
+    vr = v_render[3 * p]; vg = v_render[3 * p + 1]; vb = v_render[3 * p + 2];
+    va = v_alphas ? v_alphas[p] : 0.f;
+  }
+  sV[tr] = make_float4(vr, vg, vb, 0.f);
+  const float tf_va = T_final * va;
+  const int gt = tr >> 2, gq = tr & 3;         // phases A and C: Gaussian slot and quarter of this thread
+
+  const int nb = (rg.hi - rg.lo + FG - 1) / FG;
+  for (int b = 0; b < nb; ++b) {
+    __syncthreads();
+    const int batch_end = rg.hi - 1 - FG * b;
+    const int bs = min(FG, batch_end + 1 - rg.lo);
+    if (tr < FG) {
+      FragBox box = {0, 0, 0, 0};
+      const int idx = batch_end - tr;
+      if (idx >= rg.lo) {
+        const uint32_t e = flatten[idx];
+        const float4 A = geomA[e], B = geomB[e];
+        sE[tr] = e;
+        sA[tr] = A;
+        sB[tr] = B;
+        sC[tr] = rgb[e];
+        // conservative box of the alpha >= 1/255 ellipse (see row_mask): rows r0..r1, columns c0..c1 of the tile
+        const float L = logf(255.0f * A.z);
+        const float det = B.x * B.z - B.y * B.y;
+        int r0 = 0, r1 = -1, c0 = 0, c1 = -1;
+        if (L > 0.f) {
+          if (det > 0.f) {
+            const float hy = sqrtf(2.0f * L * B.x / det) * 1.0005f + 2e-3f;
+            const float hx = sqrtf(2.0f * L * B.z / det) * 1.0005f + 2e-3f;
+            r0 = max(0, (int)fmaxf(ceilf(A.y - hy - py0), -1.0f));
+            r1 = min(TILE - 1, (int)fminf(floorf(A.y + hy - py0), (float)TILE));
+            c0 = max(0, (int)fmaxf(ceilf(A.x - hx - px0), -1.0f));
+            c1 = min(TILE - 1, (int)fminf(floorf(A.x + hx - px0), (float)TILE));
+          } else {
+            r1 = c1 = TILE - 1;               // degenerate conic: whole tile, dense path
+          }
+        }
+        if (r1 >= r0 && c1 >= c0) {
+          const int wc = c1 - c0 + 1, nr = r1 - r0 + 1;
+          box.r0 = (uint8_t)r0; box.c0 = (uint8_t)c0; box.wc = (uint8_t)wc;
+          box.nr = (uint8_t)(nr | ((wc * nr > FRAG_SLOTS || !(det > 0.f)) ? FRAG_BIG : 0));
+        }
+      }
+      sBox[tr] = box;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[tr][k] = 0.f;
+    }
+    __syncthreads();
+    // ---- phase A: contribution masks + (alpha, vis) per contributing pixel; thread = (Gaussian gt, rows gq, gq + 4, ..)
+    {
+      const FragBox box = sBox[gt];
+      const float4 A = sA[gt], B = sB[gt];
+      const int nr = box.nr & (FRAG_BIG - 1);
+      for (int r = gq; r < TILE; r += 4) {
+        uint32_t m = 0;
+        if (gt < bs && r >= box.r0 && r < box.r0 + nr) {
+          if (box.nr & FRAG_BIG) {
+            m = ((1u << box.wc) - 1u) << box.c0;                      // conservative: the dense path re-tests alpha
+          } else {
+            const float dy = A.y - (py0 + (float)r);
+            for (int k = 0; k < box.wc; ++k) {
+              const int slot = (r - box.r0) * box.wc + k;
+              const float dx = A.x - (px0 + (float)(box.c0 + k));
+              const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
+              const float vis = __expf(-sigma);
+              const float alpha = fminf(ALPHA_MAX, A.z * vis);
+              ST3R_EMU_COUNT(8);                 // box pixels tested in phase A
+              if (!(sigma < 0.f || alpha < ALPHA_MIN)) {
+                m |= 1u << (box.c0 + k);
+                sPool[gt][slot] = make_float2(alpha, vis);
+              }
+            }
+          }
+        }
+        sMask[gt][r] = (uint16_t)m;
+      }
+    }
+    __syncthreads();
+    // ---- phase B: per-pixel recurrence, back to front; a warp visits the Gaussians whose masks touch its two rows
+    uint32_t hit[FG / 32];
+#pragma unroll
+    for (int h = 0; h < FG / 32; ++h) {
+      const int t = h * 32 + lane;
+      hit[h] = __ballot_sync(0xffffffffu, (sMask[t][2 * wrp] | sMask[t][2 * wrp + 1]) != 0);
+    }
+#pragma unroll
+    for (int h = 0; h < FG / 32; ++h) {
+      uint32_t bits = hit[h];
+      while (bits) {
+        const int t = h * 32 + __ffs(bits) - 1;
+        bits &= bits - 1;
+        const FragBox box = sBox[t];
+        const bool live = inside && (batch_end - t <= bin_final);
+        ST3R_EMU_COUNT(9);                       // phase B visits (x 32 lanes)
+        if (box.nr & FRAG_BIG) {
+          // dense path: alpha on the fly, nine-value butterfly (as raster_bwd_kernel)
+          bool valid = live;
+          float alpha = 0.f, opac = 0.f, vis = 0.f, dx = 0.f, dy = 0.f;
+          if (valid) {
+            const float4 A = sA[t], B = sB[t];
+            opac = A.z;
+            dx = A.x - px; dy = A.y - py;
+            const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
+            vis = __expf(-sigma);
+            alpha = fminf(ALPHA_MAX, opac * vis);
+            if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
+          }
+          if (!__any_sync(0xffffffffu, valid)) continue;
+          float fac = 0.f, w = 0.f;
+          if (valid) {
+            const float ra = 1.0f / (1.0f - alpha);
+            T *= ra;
+            fac = alpha * T;
+            const float4 col = sC[t];
+            const float cv = col.x * vr + col.y * vg + col.z * vb;
+            const float v_alpha = T * cv + ra * (tf_va - behind_v);
+            if (opac * vis <= ALPHA_MAX) w = vis * v_alpha;
+            behind_v += fac * cv;
+          }
+          float g[9];
+          blend_grad_terms(sA[t], sB[t], dx, dy, fac, w, vr, vg, vb, g);
+          butterfly9_to_shared(g, acc[t]);
+          ST3R_EMU_COUNT(6);
+        } else if ((sMask[t][myrow] >> mycol) & 1u) {
+          const int slot = (myrow - box.r0) * box.wc + (mycol - box.c0);
+          float2 out = make_float2(0.f, 0.f);        // a covered pixel that ignores this Gaussian contributes nothing
+          if (live) {
+            const float2 av = sPool[t][slot];        // (alpha, vis) from phase A
+            const float ra = fast_rcp(1.0f - av.x);
+            T *= ra;
+            const float fac = av.x * T;
+            const float4 col = sC[t];
+            const float cv = col.x * vr + col.y * vg + col.z * vb;
+            const float v_alpha = T * cv + ra * (tf_va - behind_v);
+            behind_v += fac * cv;
+            out = make_float2(fac, (sA[t].z * av.y <= ALPHA_MAX) ? av.y * v_alpha : 0.f);
+          }
+          sPool[t][slot] = out;
+          ST3R_EMU_COUNT(7);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase C: the four threads of a Gaussian turn its slots into the nine sums
+    {
+      const FragBox box = sBox[gt];
+      float g9[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) g9[k] = 0.f;
+      if (gt < bs && !(box.nr & FRAG_BIG)) {
+        const float4 A = sA[gt], B = sB[gt];
+        for (int r = box.r0 + gq; r < box.r0 + box.nr; r += 4) {
+          uint32_t m = sMask[gt][r];
+          const float dy = A.y - (py0 + (float)r);
+          while (m) {
+            const int col = __ffs(m) - 1;
+            m &= m - 1;
+            const float2 fw = sPool[gt][(r - box.r0) * box.wc + (col - box.c0)];
+            const float4 v = sV[r * TILE + col];
+            float g[9];
+            blend_grad_terms(A, B, A.x - (px0 + (float)col), dy, fw.x, fw.y, v.x, v.y, v.z, g);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) g9[k] += g[k];
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {               // the four quarter threads are adjacent lanes
+        g9[k] += __shfl_xor_sync(0xffffffffu, g9[k], 1);
+        g9[k] += __shfl_xor_sync(0xffffffffu, g9[k], 2);
+      }
+      if (gq == 0 && gt < bs && !(box.nr & FRAG_BIG)) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[gt][k] += g9[k];
+      }
+    }
+    __syncthreads();
+    if (tr < bs) {
+      const uint32_t e = sE[tr];
+      const float* a = acc[tr];
+      if (a[0] != 0.f || a[1] != 0.f || a[2] != 0.f || a[3] != 0.f || a[4] != 0.f || a[5] != 0.f || a[6] != 0.f ||
+          a[7] != 0.f || a[8] != 0.f) {
+        atomicAdd(v_geomA + e, make_float4(a[0], a[1], a[2], 0.f));
+        atomicAdd(v_geomB + e, make_float4(a[3], a[4], a[5], 0.f));
+        atomicAdd(v_rgb + e, make_float4(a[6], a[7], a[8], 0.f));
+      }
+    }
+  }
+}
+
 }  // namespace
 
 #ifndef ST3R_HOST_EMU
@@ -556,7 +809,7 @@ static int g_raster_bwd_variant = 0;   // 0: per-visit butterfly (default), 1: p
 extern "C" {
 
 int st3r_gs_set_raster_variant(int variant) {
-  ST3R_CHECK_ARG(variant == 0 || variant == 1, "st3r_gs_set_raster_variant: unknown variant %d", variant);
+  ST3R_CHECK_ARG(variant >= 0 && variant <= 2, "st3r_gs_set_raster_variant: unknown variant %d", variant);
   g_raster_bwd_variant = variant;
   return ST3R_OK;
 }
@@ -592,7 +845,12 @@ int st3r_gs_raster_bwd(const int32_t* offsets, const int32_t* n_isect, const uin
                  "st3r_gs_raster_bwd: null pointer");
   const int tile_w = (width + TILE - 1) / TILE, tile_h = (height + TILE - 1) / TILE;
   dim3 grid(tile_w * tile_h, C);
-  if (g_raster_bwd_variant == 1)
+  if (g_raster_bwd_variant == 2)
+    raster_bwd_frag_kernel<<<grid, BLOCK, 0, stream>>>(
+        offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
+        reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, alphas, last_ids, v_render, v_alphas,
+        reinterpret_cast<float4*>(v_geomA), reinterpret_cast<float4*>(v_geomB), reinterpret_cast<float4*>(v_rgb));
+  else if (g_raster_bwd_variant == 1)
     raster_bwd_queue_kernel<<<grid, BLOCK, 0, stream>>>(
         offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
         reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, alphas, last_ids, v_render, v_alphas,

@@ -24,7 +24,8 @@ TILE = 16
 BINNING = "fused"
 EPS2D, NEAR, FAR, RADIUS_CLIP = 0.3, 0.01, 1e10, 0.0
 # Variant of the blend backward kernel (st3r_gs_set_raster_variant): 0 = per-visit warp reduction (every committed
-# measurement), 1 = per-warp record queues (written without GPU time; tests/test_experimental_gpu.py).
+# measurement), 1 = per-warp record queues, 2 = fragment pool (both written without GPU time, DESIGN.md §10;
+# tests/test_experimental_gpu.py, tests/test_raster_emu_host.py).
 RASTER_BWD_VARIANT = int(os.environ.get("ST3R_RASTER_VARIANT", "0"))
 # run_3dgs_optim under a torch.distributed process group: shard the views over the ranks (splat replicated, gradients
 # summed over NVLink peer memory / NCCL).  Opt-in until it has run on a multi-GPU box (bench.py and

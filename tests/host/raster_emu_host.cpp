@@ -4,7 +4,7 @@
 // Never linked into the product library.
 #include "simt_emu.h"
 #define ST3R_HOST_EMU 1
-static long g_emu_count[8];     // per-lane hits of the marked code paths of the kernels
+static long g_emu_count[16];     // per-lane hits of the marked code paths of the kernels
 #define ST3R_EMU_COUNT(i) (++g_emu_count[i])
 #include "../../starst3r_b200/csrc/gs_raster.cu"
 
@@ -29,8 +29,8 @@ extern "C" {
 
 void emu_set_tile_stride(int stride) { g_tile_stride = stride > 0 ? stride : 1; }
 
-void emu_counts(long* out8, int reset) {
-  for (int i = 0; i < 8; ++i) { out8[i] = g_emu_count[i]; if (reset) g_emu_count[i] = 0; }
+void emu_counts(long* out16, int reset) {
+  for (int i = 0; i < 16; ++i) { out16[i] = g_emu_count[i]; if (reset) g_emu_count[i] = 0; }
 }
 
 int emu_raster_fwd(const int32_t* offsets, const int32_t* n_isect, const uint32_t* flatten, const float* geomA,
@@ -43,14 +43,18 @@ int emu_raster_fwd(const int32_t* offsets, const int32_t* n_isect, const uint32_
   });
 }
 
-// variant 0: raster_bwd_kernel, 1: raster_bwd_queue_kernel
+// variant 0: raster_bwd_kernel, 1: raster_bwd_queue_kernel, 2: raster_bwd_frag_kernel
 int emu_raster_bwd(int variant, const int32_t* offsets, const int32_t* n_isect, const uint32_t* flatten,
                    const float* geomA, const float* geomB, const float* rgb, int C, int W, int H, const float* alphas,
                    const int32_t* last_ids, const float* v_render, const float* v_alphas, float* v_geomA, float* v_geomB,
                    float* v_rgb) {
   const int tile_w = (W + TILE - 1) / TILE, tile_h = (H + TILE - 1) / TILE;
   return run_grid(tile_w * tile_h, C, [&]() {
-    if (variant == 1)
+    if (variant == 2)
+      raster_bwd_frag_kernel(offsets, n_isect, flatten, (const float4*)geomA, (const float4*)geomB, (const float4*)rgb, C,
+                             W, H, tile_w, tile_h, alphas, last_ids, v_render, v_alphas, (float4*)v_geomA,
+                             (float4*)v_geomB, (float4*)v_rgb);
+    else if (variant == 1)
       raster_bwd_queue_kernel(offsets, n_isect, flatten, (const float4*)geomA, (const float4*)geomB, (const float4*)rgb, C,
                               W, H, tile_w, tile_h, alphas, last_ids, v_render, v_alphas, (float4*)v_geomA,
                               (float4*)v_geomB, (float4*)v_rgb);

@@ -120,7 +120,7 @@ def test_blend_kernels_on_the_simt_emulator(emu, n, C, W, H, ss, sl, seed):
     assert int(n_blend[0]) > 5 * C * H * W
     scale = np.abs(want_g).max(0) + 1e-12
     got = {}
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         vA = np.zeros_like(A)
         vB = np.zeros_like(B)
         vC = np.zeros_like(col)
@@ -133,9 +133,11 @@ def test_blend_kernels_on_the_simt_emulator(emu, n, C, W, H, ss, sl, seed):
         assert err.max() < 2e-4, (variant, err)       # fp32 kernels (and fp32 forward state) vs the float64 evaluation
         assert np.all(vA[:, 3] == 0) and np.all(vB[:, 3] == 0) and np.all(vC[:, 3] == 0)
     assert (np.abs(got[0] - got[1]).max(0) / scale).max() < 1e-4
+    assert (np.abs(got[0] - got[2]).max(0) / scale).max() < 1e-4
     # path coverage of the queue kernel in this run (per-lane hits): dense bypass, mid-batch overflow drain, appends
-    counts = (ctypes.c_long * 8)()
+    counts = (ctypes.c_long * 16)()
     emu.emu_counts(counts, 1)
     assert counts[0] > 0 and counts[2] > 0, list(counts)
+    assert counts[6] > 0 and counts[7] > 0, list(counts)     # fragment-pool variant: dense visits and pool slots
     if per_tile.max() > 256:
         assert counts[1] > 0, list(counts)
