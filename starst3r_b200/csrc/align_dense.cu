@@ -7,13 +7,15 @@
 //   clean_pointcloud(dust3r/cloud_opt/base_opt.py:369-405): lower the confidence of points that lie in front of a
 //                   more confident view's depth map; images are processed in order because image i reads the
 //                   already cleaned confidences of images j < i.
+#ifndef ST3R_HOST_EMU   // tests/host/dense_emu_host.cpp runs the kernels of this file on the host (tests/host/simt_emu.h)
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "../../include/starst3r_b200.h"
 
-namespace cg = cooperative_groups;
-
 int align_variant();   // align.cu (st3r_align_set_variant)
+#endif
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -219,6 +221,7 @@ clean_pointcloud_kernel(const float* __restrict__ pts_i, float* __restrict__ con
 
 }  // namespace
 
+#ifndef ST3R_HOST_EMU
 extern "C" {
 
 int st3r_canonical_view(const float* ptmaps, const float* confs, int n_entries, int H, int W, int subsample,
@@ -277,3 +280,4 @@ int st3r_clean_pointcloud(const float* pts3d, float* confs, const float* depthma
   return ST3R_OK;
 }
 }
+#endif  // ST3R_HOST_EMU

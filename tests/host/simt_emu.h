@@ -31,7 +31,11 @@ struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c 
 #define __noinline__
 #define __restrict__
 #define __launch_bounds__(...)
-#define __shared__ static   // one CTA runs at a time; the harness re-zeroes nothing: kernels must initialise what they read
+// Shared variables are function-local statics in a dedicated section: one CTA runs at a time (nothing is re-zeroed:
+// kernels must initialise what they read); a CLUSTER run keeps one copy of the section per CTA and swaps it in and out
+// when the scheduler moves from one CTA of the cluster to the next, which is also what map_shared_rank() resolves into.
+#define __shared__ static __attribute__((section("emu_shared")))
+extern "C" char __start_emu_shared[], __stop_emu_shared[];
 
 namespace emu {
 
@@ -40,8 +44,9 @@ constexpr size_t STACK = 256 * 1024;
 
 struct Fiber {
   ucontext_t ctx;
-  std::vector<char> stack;
+  char* stack = nullptr;   // malloc'ed, untouched until used
   uint3 tid;
+  int cta = 0;             // rank of the fiber's CTA inside its cluster
   bool done = false;
 };
 
@@ -52,19 +57,26 @@ struct WarpState {
   unsigned generation = 0;
 };
 
-struct Cta {
+struct BlockBarrier {
+  int arrived = 0;
+  unsigned generation = 0;
+  int count_true = 0, count_result = 0;
+};
+
+struct Cta {               // one CTA, or the CTAs of one cluster (threads_per_cta fibers each)
   std::vector<Fiber> fibers;
   std::vector<WarpState> warps;
-  int bar_arrived = 0;
-  unsigned bar_generation = 0;
-  int bar_count_true = 0, bar_count_result = 0;
+  std::vector<BlockBarrier> bars;      // one per CTA
+  BlockBarrier cluster_bar;
+  int threads_per_cta = 0, n_ctas = 1, live_cta = 0;
+  std::vector<std::vector<char>> shared_copy;   // cluster runs: the shared-memory section of every CTA
   ucontext_t sched;
   int cur = -1;
   long progress = 0;       // arrivals, departures and exits: a scheduler round without any is a deadlock
 };
 
 static Cta* g_cta = nullptr;
-static uint3 g_blockIdx;
+static uint3 g_blockIdx;          // of CTA 0 of the running cluster; blockIdx.x adds the fiber's rank
 static dim3 g_blockDim, g_gridDim;
 static std::function<void()> g_body;
 
@@ -78,30 +90,47 @@ static void trampoline() {
   swapcontext(&self().ctx, &g_cta->sched);
 }
 
-// Runs `body` once per thread of a CTA of `nthreads` threads.  Returns false on deadlock (no fiber can progress).
-static bool run_cta(int nthreads, const std::function<void()>& body) {
+static inline size_t shared_bytes() { return (size_t)(__stop_emu_shared - __start_emu_shared); }
+static void switch_cta(Cta& c, int next) {      // cluster runs: park the live CTA's shared memory, bring in the next one's
+  if (c.n_ctas == 1 || next == c.live_cta) return;
+  memcpy(c.shared_copy[c.live_cta].data(), __start_emu_shared, shared_bytes());
+  memcpy(__start_emu_shared, c.shared_copy[next].data(), shared_bytes());
+  c.live_cta = next;
+}
+
+// Runs `body` once per thread of a cluster of `n_ctas` CTAs of `nthreads` threads (n_ctas = 1: a plain CTA).
+// Returns false on deadlock (no fiber can progress).
+static bool run_cluster(int n_ctas, int nthreads, const std::function<void()>& body, size_t stack_bytes = STACK) {
   Cta cta;
-  cta.fibers.resize(nthreads);
-  cta.warps.resize((nthreads + WARP - 1) / WARP);
+  const int total = n_ctas * nthreads;
+  cta.fibers.resize(total);
+  cta.warps.resize((size_t)n_ctas * ((nthreads + WARP - 1) / WARP));
+  cta.bars.resize(n_ctas);
+  cta.threads_per_cta = nthreads;
+  cta.n_ctas = n_ctas;
+  if (n_ctas > 1) cta.shared_copy.assign(n_ctas, std::vector<char>(shared_bytes(), 0));
   g_cta = &cta;
   g_body = body;
-  for (int t = 0; t < nthreads; ++t) {
+  for (int t = 0; t < total; ++t) {
     Fiber& f = cta.fibers[t];
-    f.stack.resize(STACK);
-    f.tid = uint3{(unsigned)t, 0, 0};
+    f.stack = (char*)malloc(stack_bytes);
+    f.tid = uint3{(unsigned)(t % nthreads), 0, 0};
+    f.cta = t / nthreads;
     getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = f.stack.data();
-    f.ctx.uc_stack.ss_size = STACK;
+    f.ctx.uc_stack.ss_sp = f.stack;
+    f.ctx.uc_stack.ss_size = stack_bytes;
     f.ctx.uc_link = nullptr;
     makecontext(&f.ctx, trampoline, 0);
   }
-  int alive = nthreads;
+  auto release = [&]() { for (Fiber& f : cta.fibers) free(f.stack); g_cta = nullptr; };
+  int alive = total;
   while (alive > 0) {
     alive = 0;
     const long before = cta.progress;
-    for (int t = 0; t < nthreads; ++t) {
+    for (int t = 0; t < total; ++t) {
       if (cta.fibers[t].done) continue;
       ++alive;
+      switch_cta(cta, cta.fibers[t].cta);
       cta.cur = t;
       swapcontext(&cta.sched, &cta.fibers[t].ctx);
     }
@@ -109,29 +138,45 @@ static bool run_cta(int nthreads, const std::function<void()>& body) {
     // by a better one
     if (alive > 0 && cta.progress == before) {
       fprintf(stderr, "simt_emu: deadlock (%d fibers blocked at a barrier / warp collective)\n", alive);
-      g_cta = nullptr;
+      release();
       return false;
     }
   }
-  g_cta = nullptr;
+  release();
   return true;
 }
+static bool run_cta(int nthreads, const std::function<void()>& body) { return run_cluster(1, nthreads, body); }
 
-// ---- block barrier
+// ---- block barrier (of the calling fiber's CTA) and cluster barrier
+static inline int barrier_wait(BlockBarrier& b, int parties, int pred) {
+  Cta& c = *g_cta;
+  const unsigned gen = b.generation;
+  b.count_true += pred ? 1 : 0;
+  ++c.progress;
+  if (++b.arrived == parties) {
+    b.arrived = 0;
+    b.count_result = b.count_true;
+    b.count_true = 0;
+    ++b.generation;
+  } else {
+    while (b.generation == gen) yield();
+  }
+  return b.count_result;
+}
 static inline int syncthreads_count(int pred) {
   Cta& c = *g_cta;
-  const unsigned gen = c.bar_generation;
-  c.bar_count_true += pred ? 1 : 0;
-  ++c.progress;
-  if (++c.bar_arrived == (int)c.fibers.size()) {
-    c.bar_arrived = 0;
-    c.bar_count_result = c.bar_count_true;
-    c.bar_count_true = 0;
-    ++c.bar_generation;
-  } else {
-    while (c.bar_generation == gen) yield();
-  }
-  return c.bar_count_result;
+  return barrier_wait(c.bars[self().cta], c.threads_per_cta, pred);
+}
+static inline void cluster_sync() {
+  Cta& c = *g_cta;
+  barrier_wait(c.cluster_bar, c.threads_per_cta * c.n_ctas, 0);
+}
+// Address of a shared variable in CTA `rank` of the cluster (distributed shared memory).
+template <typename T>
+static inline T* map_shared_rank(T* p, int rank) {
+  Cta& c = *g_cta;
+  if (c.n_ctas == 1 || rank == c.live_cta) return p;
+  return reinterpret_cast<T*>(c.shared_copy[rank].data() + (reinterpret_cast<char*>(p) - __start_emu_shared));
 }
 
 // ---- warp collectives: publish, wait for all 32 lanes, read, wait for all lanes to have read
@@ -139,7 +184,7 @@ template <typename F>
 static inline uint64_t warp_collective(uint64_t v, F&& combine) {
   Cta& c = *g_cta;
   const int lane = self().tid.x % WARP;
-  WarpState& w = c.warps[self().tid.x / WARP];
+  WarpState& w = c.warps[(size_t)self().cta * ((c.threads_per_cta + WARP - 1) / WARP) + self().tid.x / WARP];
   const unsigned gen = w.generation;
   w.slot[lane] = v;
   ++w.arrived;
@@ -160,7 +205,7 @@ static inline uint64_t warp_collective(uint64_t v, F&& combine) {
 }  // namespace emu
 
 #define threadIdx (emu::self().tid)
-#define blockIdx (emu::g_blockIdx)
+#define blockIdx (uint3{emu::g_blockIdx.x + (unsigned)emu::self().cta, emu::g_blockIdx.y, emu::g_blockIdx.z})
 #define blockDim (emu::g_blockDim)
 #define gridDim (emu::g_gridDim)
 
@@ -233,3 +278,14 @@ static inline float4 atomicAdd(float4* p, float4 v) {
 }
 
 static inline int lane_id() { return (int)(threadIdx.x & 31); }
+
+// ---- the part of cooperative_groups the kernels use (thread-block clusters)
+namespace cooperative_groups {
+struct cluster_group {
+  unsigned block_rank() const { return (unsigned)emu::self().cta; }
+  void sync() const { emu::cluster_sync(); }
+  template <typename T> T* map_shared_rank(T* p, int rank) const { return emu::map_shared_rank(p, rank); }
+};
+static inline cluster_group this_cluster() { return cluster_group(); }
+}  // namespace cooperative_groups
+#define __cluster_dims__(...)
