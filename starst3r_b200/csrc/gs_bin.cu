@@ -15,8 +15,11 @@
 // Segments up to 4096 pairs are sorted in shared memory; longer ones in place in global memory (L2) by the same
 // comparator network.  The network is the "flip" form of bitonic sort, whose comparators all point the same way, so
 // padding to a power of two is virtual (+inf never moves).
+#ifndef ST3R_HOST_EMU   // tests/host/bin_emu_host.cpp runs the kernels of this file on the host (tests/host/simt_emu.h)
 #include "common.cuh"
 #include "gs.cuh"
+#define ST3R_DYN_SMEM_I32(name) extern __shared__ int32_t name[]
+#endif
 
 namespace {
 
@@ -45,7 +48,7 @@ constexpr int MAX_SMEM_TILES = 10240;      // 40 KB of counters; larger images f
 __global__ void __launch_bounds__(BIN_THREADS)
 tile_hist_kernel(const int32_t* __restrict__ radii, const float4* __restrict__ geomA, int N, int tile_size,
                  int tile_w, int tile_h, int32_t* __restrict__ counts, int use_smem) {
-  extern __shared__ int32_t s_cnt[];
+  ST3R_DYN_SMEM_I32(s_cnt);
   const int n_tiles = tile_w * tile_h;
   const int c = blockIdx.y;
   int32_t* row = counts + (size_t)c * n_tiles;
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(BIN_THREADS)
 tile_emit_kernel(const int32_t* __restrict__ radii, const float4* __restrict__ geomA, int N, int tile_size,
                  int tile_w, int tile_h, const int32_t* __restrict__ offsets, int32_t* __restrict__ cursor,
                  uint64_t* __restrict__ pairs, int n_cap, int use_smem) {
-  extern __shared__ int32_t s_cnt[];       // [n_tiles] local counts, then local cursors; [n_tiles] claimed bases
+  ST3R_DYN_SMEM_I32(s_cnt);                // [n_tiles] local counts, then local cursors; [n_tiles] claimed bases
   const int n_tiles = tile_w * tile_h;
   const int c = blockIdx.y;
   const size_t row = (size_t)c * n_tiles;
@@ -211,6 +214,7 @@ tile_sort_kernel(int32_t* offsets, const int32_t* __restrict__ total_ptr, int n_
   }
 }
 
+#ifndef ST3R_HOST_EMU
 struct BinWs {
   int32_t* counts; int32_t* cursor; uint64_t* pairs; void* scan_ws; size_t scan_bytes;
 };
@@ -226,9 +230,11 @@ size_t carve_bin(BinWs* w, void* ws, size_t ws_bytes, int n_cells, int n_cap, bo
   if (w) *w = t;
   return a.off + 256;
 }
+#endif  // ST3R_HOST_EMU
 
 }  // namespace
 
+#ifndef ST3R_HOST_EMU
 extern "C" {
 
 size_t st3r_gs_bin_ws_bytes(int C, int width, int height, int tile_size, int n_cap) {
@@ -281,3 +287,4 @@ int st3r_gs_bin_tiles(const int32_t* radii, const float* geomA, int N, int C, in
   return ST3R_OK;
 }
 }
+#endif  // ST3R_HOST_EMU

@@ -271,6 +271,8 @@ template <typename T> static inline T max(T a, T b) { return a > b ? a : b; }
 // one OS thread: plain read-modify-write
 static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
+static inline uint32_t __float_as_uint(float f) { return (uint32_t)emu_bits(f); }
 static inline float4 atomicAdd(float4* p, float4 v) {
   float4 o = *p;
   p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w;
