@@ -1,6 +1,10 @@
 // Shared helpers for the starst3r_b200 CUDA kernels (sm_100a only).
 #pragma once
+#ifdef ST3R_HOST_EMU            // test builds that run the library on a CPU SIMT emulator (tests/host/)
+#include "emu_cuda_shim.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 
@@ -57,7 +61,9 @@ struct WsAlloc {
   __host__ bool ok() const { return off <= cap; }
 };
 
+#ifndef ST3R_HOST_EMU            // (the emulator header brings its own)
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+#endif
 
 // Monotone map float -> uint32 (larger float -> larger uint).
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {

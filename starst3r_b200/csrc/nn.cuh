@@ -6,7 +6,7 @@
 __host__ __device__ __forceinline__ unsigned long long nn_pack_bits(uint32_t ordered, int j) {
   return ((unsigned long long)ordered << 32) | (unsigned long long)(0xffffffffu - (uint32_t)j);
 }
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(ST3R_HOST_EMU)
 __device__ __forceinline__ unsigned long long nn_pack(float s, int j) {
   return nn_pack_bits(float_to_ordered(s), j);
 }

@@ -17,6 +17,15 @@ constexpr int TM = 128;       // query rows per CTA
 constexpr int TN = 128;       // DB rows per smem tile
 constexpr int NTHREADS = 256; // 16 x 16 threads, 8 x 8 outputs each
 
+#ifdef ST3R_HOST_EMU   // CPU emulator build (tests/host/): the asynchronous copy completes on the spot
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  memset(smem_dst, 0, 16);
+  memcpy(smem_dst, gsrc, (size_t)src_bytes);
+}
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+#else
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(src_bytes));
@@ -24,6 +33,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+#define ST3R_DYN_SMEM_F32(name) extern __shared__ __align__(16) float name[]
+#endif
 
 // D = descriptor dim (multiple of 4).  LDB = padded smem row stride (floats), chosen
 // so that 8 consecutive rows hit 8 distinct 16-byte bank groups (LDB/4 odd).
@@ -42,7 +53,7 @@ nn_simt_kernel(const float* __restrict__ Qsrc, const int32_t* __restrict__ qidx,
                unsigned long long* __restrict__ packed) {
   using Cfg = SimtCfg<D>;
   constexpr int LDB = Cfg::LDB;
-  extern __shared__ __align__(16) float smem[];
+  ST3R_DYN_SMEM_F32(smem);
   float* As = smem;                 // [D][TM]  (k-major)
   float* Bs = smem + D * TM;        // [2][TN][LDB]
 

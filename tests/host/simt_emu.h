@@ -1,5 +1,5 @@
 // TEST-ONLY: a small SIMT emulator that runs the SOURCE of a CUDA kernel on the host, one CTA at a time, every CUDA
-// thread as a cooperatively scheduled fiber (ucontext) of ONE OS thread.  Block barriers and warp collectives are
+// thread as a cooperatively scheduled fiber of ONE OS thread.  Block barriers and warp collectives are
 // rendezvous points: a fiber that reaches one yields until all its peers have arrived, so shuffles, votes, redux and
 // __syncthreads have their CUDA meaning, a missing peer shows up as a reported deadlock instead of a hang, and the
 // kernel's indexing / queueing / reduction logic is exercised exactly as written.  What it does NOT model: memory
@@ -12,7 +12,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#if !defined(__x86_64__)
 #include <ucontext.h>
+#endif
 
 #include <functional>
 #include <vector>
@@ -42,8 +44,58 @@ namespace emu {
 constexpr int WARP = 32;
 constexpr size_t STACK = 256 * 1024;
 
+// Context switch.  glibc's swapcontext saves and restores the signal mask with a system call per switch, and a launch
+// sequence makes millions of switches; on x86-64 a fiber context is just a saved stack pointer (the callee-saved
+// registers are pushed on the fiber's own stack), elsewhere ucontext is used.
+#if defined(__x86_64__)
+struct Context { void* sp = nullptr; };
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.weak emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+static inline void context_switch(Context& from, Context& to) { emu_switch(&from.sp, to.sp); }
+static inline void context_init(Context& c, char* stack, size_t bytes, void (*entry)()) {
+  // initial frame: six zeroed callee-saved registers, then the entry point as return address; the stack pointer is
+  // 16-byte aligned + 8 at the entry's first instruction, as after a call
+  uintptr_t top = ((uintptr_t)stack + bytes) & ~(uintptr_t)15;
+  void** sp = (void**)(top - 8);
+  *--sp = (void*)entry;
+  for (int i = 0; i < 6; ++i) *--sp = nullptr;
+  c.sp = sp;
+}
+#else
+struct Context { ucontext_t uc; };
+static inline void context_switch(Context& from, Context& to) { swapcontext(&from.uc, &to.uc); }
+static inline void context_init(Context& c, char* stack, size_t bytes, void (*entry)()) {
+  getcontext(&c.uc);
+  c.uc.uc_stack.ss_sp = stack;
+  c.uc.uc_stack.ss_size = bytes;
+  c.uc.uc_link = nullptr;
+  makecontext(&c.uc, entry, 0);
+}
+#endif
+
 struct Fiber {
-  ucontext_t ctx;
+  Context ctx;
   char* stack = nullptr;   // malloc'ed, untouched until used
   uint3 tid;
   int cta = 0;             // rank of the fiber's CTA inside its cluster
@@ -70,7 +122,7 @@ struct Cta {               // one CTA, or the CTAs of one cluster (threads_per_c
   BlockBarrier cluster_bar;
   int threads_per_cta = 0, n_ctas = 1, live_cta = 0;
   std::vector<std::vector<char>> shared_copy;   // cluster runs: the shared-memory section of every CTA
-  ucontext_t sched;
+  Context sched;
   int cur = -1;
   long progress = 0;       // arrivals, departures and exits: a scheduler round without any is a deadlock
 };
@@ -81,13 +133,29 @@ static dim3 g_blockDim, g_gridDim;
 static std::function<void()> g_body;
 
 static inline Fiber& self() { return g_cta->fibers[g_cta->cur]; }
-static inline void yield() { swapcontext(&self().ctx, &g_cta->sched); }
+static inline void yield() { context_switch(self().ctx, g_cta->sched); }
 
 static void trampoline() {
   g_body();
   self().done = true;
   ++g_cta->progress;
-  swapcontext(&self().ctx, &g_cta->sched);
+  context_switch(self().ctx, g_cta->sched);
+  abort();     // a finished fiber is never resumed
+}
+
+// fiber stacks are recycled between launches (a launch sequence starts thousands of CTAs)
+static std::vector<char*> g_stack_pool;
+static size_t g_stack_pool_bytes = 0;
+static char* take_stack(size_t bytes) {
+  if (bytes != g_stack_pool_bytes) {
+    for (char* p : g_stack_pool) free(p);
+    g_stack_pool.clear();
+    g_stack_pool_bytes = bytes;
+  }
+  if (g_stack_pool.empty()) return (char*)malloc(bytes);
+  char* p = g_stack_pool.back();
+  g_stack_pool.pop_back();
+  return p;
 }
 
 static inline size_t shared_bytes() { return (size_t)(__stop_emu_shared - __start_emu_shared); }
@@ -113,16 +181,12 @@ static bool run_cluster(int n_ctas, int nthreads, const std::function<void()>& b
   g_body = body;
   for (int t = 0; t < total; ++t) {
     Fiber& f = cta.fibers[t];
-    f.stack = (char*)malloc(stack_bytes);
+    f.stack = take_stack(stack_bytes);
     f.tid = uint3{(unsigned)(t % nthreads), 0, 0};
     f.cta = t / nthreads;
-    getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = f.stack;
-    f.ctx.uc_stack.ss_size = stack_bytes;
-    f.ctx.uc_link = nullptr;
-    makecontext(&f.ctx, trampoline, 0);
+    context_init(f.ctx, f.stack, stack_bytes, trampoline);
   }
-  auto release = [&]() { for (Fiber& f : cta.fibers) free(f.stack); g_cta = nullptr; };
+  auto release = [&]() { for (Fiber& f : cta.fibers) g_stack_pool.push_back(f.stack); g_cta = nullptr; };
   int alive = total;
   while (alive > 0) {
     alive = 0;
@@ -132,7 +196,7 @@ static bool run_cluster(int n_ctas, int nthreads, const std::function<void()>& b
       ++alive;
       switch_cta(cta, cta.fibers[t].cta);
       cta.cur = t;
-      swapcontext(&cta.sched, &cta.fibers[t].ctx);
+      context_switch(cta.sched, cta.fibers[t].ctx);
     }
     // fibers only block at rendezvous points: a round in which nobody arrived, departed or finished cannot be followed
     // by a better one
@@ -272,7 +336,17 @@ template <typename T> static inline T max(T a, T b) { return a > b ? a : b; }
 static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; if (v > o) *p = v; return o; }
+static inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
+static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
+static inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
+static inline int atomicExch(int* p, int v) { int o = *p; *p = v; return o; }
 static inline uint32_t __float_as_uint(float f) { return (uint32_t)emu_bits(f); }
+static inline float __uint_as_float(uint32_t u) { return emu_float(u); }
+static inline int __float_as_int(float f) { return (int)(uint32_t)emu_bits(f); }
+static inline float __int_as_float(int i) { return emu_float((uint32_t)i); }
 static inline float4 atomicAdd(float4* p, float4 v) {
   float4 o = *p;
   p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w;
