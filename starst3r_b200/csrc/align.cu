@@ -12,8 +12,12 @@
 //   align_cam_bwd   (1 CTA)  camera-record gradients -> MST chain backward -> parameter gradients -> Adam
 // HBM traffic per iteration is the correspondence list (~40 B per correspondence slot); the
 // loop is latency-bound, so the figure of merit is iterations/s.
-#ifndef ST3R_HOST_EMU   // tests/host/align_emu_host.cpp runs the kernels of this file on the host (tests/host/simt_emu.h)
+// ST3R_HOST_EMU: test builds that run this file on a CPU SIMT emulator (tests/host/): align_emu_host.cpp includes the
+// kernels only, build_emu_lib.py (ST3R_EMU_WHOLE) compiles the entry points too, with their launches rewritten.
+#if !defined(ST3R_HOST_EMU) || defined(ST3R_EMU_WHOLE)
 #include "common.cuh"
+#endif
+#ifndef ST3R_HOST_EMU
 #define ST3R_DYN_SMEM(name) extern __shared__ float name[]
 #endif
 #include "align_math.cuh"
@@ -542,7 +546,7 @@ __global__ void align_outputs_kernel(St3rAlignProblem pb, Work w, float* pts3d, 
   }
 }
 
-#ifndef ST3R_HOST_EMU
+#if !defined(ST3R_HOST_EMU) || defined(ST3R_EMU_WHOLE)
 Work carve(void* ws, int N) {
   WsAlloc a(ws, (size_t)-1);
   Work w;
@@ -558,7 +562,7 @@ Work carve(void* ws, int N) {
 
 }  // namespace
 
-#ifndef ST3R_HOST_EMU
+#if !defined(ST3R_HOST_EMU) || defined(ST3R_EMU_WHOLE)
 // bit 0: segmented accumulation in the loss kernels (align_loss_seg_kernel); bit 1: one thread-block cluster per image
 // in st3r_focal_weiszfeld (align_dense.cu).  0 = the variants every committed profile was measured with.
 static int g_align_variant = 0;

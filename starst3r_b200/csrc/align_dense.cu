@@ -7,8 +7,12 @@
 //   clean_pointcloud(dust3r/cloud_opt/base_opt.py:369-405): lower the confidence of points that lie in front of a
 //                   more confident view's depth map; images are processed in order because image i reads the
 //                   already cleaned confidences of images j < i.
-#ifndef ST3R_HOST_EMU   // tests/host/dense_emu_host.cpp runs the kernels of this file on the host (tests/host/simt_emu.h)
+// ST3R_HOST_EMU: test builds that run this file on a CPU SIMT emulator (tests/host/): dense_emu_host.cpp includes the
+// kernels only, build_emu_lib.py (ST3R_EMU_WHOLE) compiles the entry points too, with their launches rewritten.
+#ifndef ST3R_HOST_EMU
 #include <cooperative_groups.h>
+#endif
+#if !defined(ST3R_HOST_EMU) || defined(ST3R_EMU_WHOLE)
 #include "common.cuh"
 #include "../../include/starst3r_b200.h"
 
@@ -221,7 +225,7 @@ clean_pointcloud_kernel(const float* __restrict__ pts_i, float* __restrict__ con
 
 }  // namespace
 
-#ifndef ST3R_HOST_EMU
+#if !defined(ST3R_HOST_EMU) || defined(ST3R_EMU_WHOLE)
 extern "C" {
 
 int st3r_canonical_view(const float* ptmaps, const float* confs, int n_entries, int H, int W, int subsample,

@@ -1,5 +1,5 @@
-"""TEST-ONLY: builds `libst3r_emu.so`, the C ABI of the MATCH path (api.cu, scan.cu, radix_sort.cu, recip.cu, nn_simt.cu)
-compiled for the HOST: every `kernel<<<grid, block, smem, stream>>>(args);` is rewritten into a call of the SIMT
+"""TEST-ONLY: builds `libst3r_emu.so`, the C ABI of the MATCH and ALIGN paths (api.cu, scan.cu, radix_sort.cu, recip.cu,
+nn_simt.cu, align.cu, align_dense.cu) compiled for the HOST: every `kernel<<<grid, block, smem, stream>>>(args);` is rewritten into a call of the SIMT
 emulator (tests/host/simt_emu.h through emu_cuda_shim.h), everything else - the entry points' launch sequences,
 workspace carving, device-side counters - is compiled as it stands.  The tcgen05 matcher cannot run there: its entry
 points are stubbed and ST3R_NN_AUTO resolves to the exact SIMT kernels.  Used by tests/test_match_emu_host.py."""
@@ -11,7 +11,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 CSRC = os.path.join(ROOT, "starst3r_b200", "csrc")
 HOST = os.path.join(ROOT, "tests", "host")
-SOURCES = ["api.cu", "scan.cu", "radix_sort.cu", "recip.cu", "nn_simt.cu"]
+SOURCES = ["api.cu", "scan.cu", "radix_sort.cu", "recip.cu", "nn_simt.cu", "align.cu", "align_dense.cu"]
+CLUSTER_KERNELS = {"focal_weiszfeld_cluster_kernel": "WZ_CLUSTER"}     # launched cluster by cluster
 
 STUBS = r'''
 // the tcgen05 matcher does not exist on the emulator
@@ -64,6 +65,11 @@ def rewrite(text):
             i += 1
         args = text[m.end():i - 1].strip()
         name = m.group(1)
+        if name in CLUSTER_KERNELS:
+            out += text[pos:m.start()] + (f"emu_launch_cluster({CLUSTER_KERNELS[name]}, dim3({cfg[0]}), dim3({cfg[1]}), "
+                                          f"[&]() {{ {name}({args}); }})")
+            pos, n = i, n + 1
+            continue
         if "<" in name:
             name = "(" + name + ")"
         out += text[pos:m.start()] + f"EMU_LAUNCH({name}, ({cfg[0]}), ({cfg[1]}), ({cfg[2]})" + (", " + args if args else "") + ")"
@@ -83,7 +89,7 @@ def build(out_dir):
         with open(cpp, "w") as fh:
             fh.write(text)
         obj = cpp[:-4] + ".o"
-        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-DST3R_HOST_EMU=1", "-I", CSRC, "-I", HOST, "-x", "c++", "-c", cpp,
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-DST3R_HOST_EMU=1", "-DST3R_EMU_WHOLE=1", "-I", CSRC, "-I", HOST, "-x", "c++", "-c", cpp,
                         "-o", obj], check=True)
         objs.append(obj)
     lib = os.path.join(out_dir, "libst3r_emu.so")

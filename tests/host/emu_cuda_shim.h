@@ -22,6 +22,9 @@ template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFunc
 // dynamic shared memory of the kernel being launched (one CTA at a time)
 alignas(16) static char emu_dyn_smem[128 * 1024];
 #define ST3R_DYN_SMEM_F32(name) float* name = reinterpret_cast<float*>(emu_dyn_smem)
+#define ST3R_DYN_SMEM(name) float* name = reinterpret_cast<float*>(emu_dyn_smem)
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 
 static bool g_emu_launch_failed = false;
 template <typename F>
@@ -37,3 +40,13 @@ static inline void emu_launch(dim3 grid, dim3 block, size_t smem, F&& body) {
       }
 }
 #define EMU_LAUNCH(kernel, grid, block, smem, ...) emu_launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); })
+// kernels declared with __cluster_dims__(n, 1, 1): the grid is walked cluster by cluster
+template <typename F>
+static inline void emu_launch_cluster(int cluster, dim3 grid, dim3 block, F&& body) {
+  emu::g_gridDim = grid;
+  emu::g_blockDim = block;
+  for (unsigned x = 0; x < grid.x; x += cluster) {
+    emu::g_blockIdx = uint3{x, 0, 0};
+    if (!emu::run_cluster(cluster, (int)block.x, body, 64 * 1024)) { g_emu_launch_failed = true; return; }
+  }
+}

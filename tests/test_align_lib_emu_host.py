@@ -1,0 +1,83 @@
+"""CPU: the ALIGN path of the C ABI (st3r_align_optimize, st3r_canonical_view, st3r_focal_weiszfeld, st3r_dense_points,
+st3r_clean_pointcloud) compiled for the host by tests/host/build_emu_lib.py - kernel launches rewritten onto the SIMT
+emulator - and driven through the PRODUCT's own Python glue (starst3r_b200.reconstruct) on CPU tensors.  The glue
+refuses anything but CUDA by design, so this test (and only the test) swaps the library handle, the stream getter and
+torch.cuda.device for host stand-ins; the checks are the ones tests/test_align_gpu.py makes on the B200, against the
+fixtures produced by the unmodified reference (oracle/gen_golden_align.py): canonical view, Weiszfeld focal, dense
+points, clean_pointcloud, loss + gradients vs autograd, and the 30 + 20 iteration trajectory - for the default kernels
+and for the opt-in variants (segmented loss kernels, staged camera kernels, cluster Weiszfeld)."""
+import contextlib
+import ctypes
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CPU = torch.device("cpu")
+
+
+@pytest.fixture(scope="module")
+def emu_lib(tmp_path_factory):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "host"))
+    import build_emu_lib
+    from starst3r_b200 import _lib
+    path, _ = build_emu_lib.build(str(tmp_path_factory.mktemp("emu_lib")))
+    lib = ctypes.CDLL(path)
+    for name, (restype, argtypes) in _lib.parse_header().items():
+        if hasattr(lib, name):
+            getattr(lib, name).restype = restype
+            getattr(lib, name).argtypes = argtypes
+    return lib
+
+
+@pytest.fixture(params=[0, 3], ids=["default-kernels", "variants"])
+def backend(request, emu_lib, monkeypatch):
+    from starst3r_b200 import _lib
+    from starst3r_b200 import reconstruct as rc
+    monkeypatch.setattr(_lib, "load", lambda: emu_lib)
+    monkeypatch.setattr(_lib, "stream_ptr", lambda: None)
+    monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
+    monkeypatch.setattr(_lib, "last_error", lambda: emu_lib.st3r_last_error().decode(errors="replace"))
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    monkeypatch.setattr(rc, "ALIGN_VARIANT", request.param)
+    yield emu_lib
+    assert emu_lib.st3r_emu_launch_failed() == 0, "emulator deadlock / unsupported launch"
+    emu_lib.st3r_align_set_variant(0)
+
+
+def test_canonical_view_focal_dense_clean_vs_reference(backend):
+    import test_align_gpu as t
+    t.test_canonical_view_focal_dense_clean_vs_reference(CPU)
+
+
+@pytest.mark.parametrize("name,mode", [("align_match3.pt", 0), ("align_match3.pt", 1), ("align_dust3r3.pt", 0)])
+def test_loss_and_gradients_vs_autograd(backend, name, mode):
+    import test_align_gpu as t
+    t.test_kernel_loss_and_gradients_vs_autograd(CPU, name, mode)
+
+
+@pytest.mark.parametrize("name", ["align_match3.pt", "align_dust3r3.pt"])
+def test_optimizer_trajectory_vs_reference(backend, name):
+    """The fixture's 30 coarse + 20 fine iterations through st3r_align_optimize: same state as the unmodified reference
+    (gauge-invariant comparison)."""
+    import test_align_gpu as t
+    from starst3r_b200 import reconstruct as rc
+    f = t.fx(name)
+    inp = f["inputs"]
+    tt, meta = rc.flatten_problem(list(inp["imgs"]), inp["imsizes"], inp["pps"].clone(), inp["base_focals"].clone(),
+                                  [c.clone() for c in inp["core_depth"]], inp["anchors"], inp["corres"], inp["corres2d"],
+                                  inp["preds_21"], inp["mst"], 5.0, CPU)
+    N = meta["N"]
+    params = dict(pps=(inp["pps"].detach().float() / meta["imsizes"]).contiguous(),
+                  log_focals=meta["base_focals"].log().contiguous(),
+                  quats=torch.tensor([[0.0, 0, 0, 1]]).repeat(N, 1).contiguous(), trans=torch.zeros(N, 3),
+                  log_sizes=torch.zeros(N))
+    n1, n2 = f["niter"]
+    res_c, hist1, _ = rc._optimize_phase(tt, meta, params, 0, 4 | 8 | 16, 1.1, f["lr"][0], n1, rc.cosine_schedule, 0.01, 1.1)
+    res_f, hist2, _ = rc._optimize_phase(tt, meta, params, 1, 4 | 8 | 16 | 2 | 1, 0.4, f["lr"][1], n2, rc.cosine_schedule, 0.01,
+                                         1.1)
+    assert torch.isfinite(hist1).all() and torch.isfinite(hist2).all() and hist1[-1] < hist1[0]
+    t.assert_same_up_to_gauge(t.cpu(res_c), f["out"]["short"]["coarse"], 1e-4)
+    t.assert_same_up_to_gauge(t.cpu(res_f), f["out"]["short"]["fine"], 1e-4)
