@@ -15,9 +15,13 @@
 // Segments up to 4096 pairs are sorted in shared memory; longer ones in place in global memory (L2) by the same
 // comparator network.  The network is the "flip" form of bitonic sort, whose comparators all point the same way, so
 // padding to a power of two is virtual (+inf never moves).
-#ifndef ST3R_HOST_EMU   // tests/host/bin_emu_host.cpp runs the kernels of this file on the host (tests/host/simt_emu.h)
+// ST3R_HOST_EMU: test builds that run this file on a CPU SIMT emulator (tests/host/): bin_emu_host.cpp includes the
+// kernels only, build_emu_lib.py (ST3R_EMU_WHOLE) compiles the entry point too, with its launches rewritten.
+#if !defined(ST3R_HOST_EMU) || defined(ST3R_EMU_WHOLE)
 #include "common.cuh"
 #include "gs.cuh"
+#endif
+#ifndef ST3R_HOST_EMU
 #define ST3R_DYN_SMEM_I32(name) extern __shared__ int32_t name[]
 #endif
 
@@ -214,7 +218,7 @@ tile_sort_kernel(int32_t* offsets, const int32_t* __restrict__ total_ptr, int n_
   }
 }
 
-#ifndef ST3R_HOST_EMU
+#if !defined(ST3R_HOST_EMU) || defined(ST3R_EMU_WHOLE)
 struct BinWs {
   int32_t* counts; int32_t* cursor; uint64_t* pairs; void* scan_ws; size_t scan_bytes;
 };
@@ -234,7 +238,7 @@ size_t carve_bin(BinWs* w, void* ws, size_t ws_bytes, int n_cells, int n_cap, bo
 
 }  // namespace
 
-#ifndef ST3R_HOST_EMU
+#if !defined(ST3R_HOST_EMU) || defined(ST3R_EMU_WHOLE)
 extern "C" {
 
 size_t st3r_gs_bin_ws_bytes(int C, int width, int height, int tile_size, int n_cap) {

@@ -27,6 +27,9 @@ constexpr int NT = 256;
 constexpr float C1 = 0.01f * 0.01f;
 constexpr float C2 = 0.03f * 0.03f;
 
+#ifndef ST3R_HOST_EMU            // (CPU emulator builds, tests/host/, define it themselves)
+#define ST3R_DYN_SMEM_F32(name) extern __shared__ float name[]
+#endif
 __constant__ float c_win[11];
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
@@ -59,7 +62,7 @@ __global__ void __launch_bounds__(NT)
 ssim_l1_fwd_kernel(const float* __restrict__ render, const float* __restrict__ truth, int H, int W,
                    float coef_ssim /* dLoss/dS per interior sample */, float* __restrict__ dmaps,
                    float* __restrict__ sums /* per view: [ssim_sum, l1_sum] */) {
-  extern __shared__ float smem[];
+  ST3R_DYN_SMEM_F32(smem);
   float* tx = smem;                         // [3][LW][LWP]
   float* ty = tx + 3 * LW * LWP;            // [3][LW][LWP]
   float* hs = ty + 3 * LW * LWP;            // [5][LW][HSP]
@@ -148,7 +151,7 @@ ssim_l1_fwd_kernel(const float* __restrict__ render, const float* __restrict__ t
 __global__ void __launch_bounds__(NT)
 ssim_l1_bwd_kernel(const float* __restrict__ render, const float* __restrict__ truth, const float* __restrict__ dmaps,
                    int H, int W, float coef_l1 /* (1-f) / (3HW) */, float* __restrict__ v_render) {
-  extern __shared__ float smem[];
+  ST3R_DYN_SMEM_F32(smem);
   float* tm = smem;                         // [3 derivatives][LW][LWP] of the current channel
   float* hs = tm + 3 * LW * LWP;            // [3][LW][HSP]
   const int c = blockIdx.z;

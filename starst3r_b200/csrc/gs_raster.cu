@@ -10,11 +10,15 @@
 // vector atomicAdd per (tile, Gaussian) record to HBM.
 // Algorithmic bytes: fwd 40 B per intersection + 20 B per pixel;
 // bwd 40 B per intersection + 24 B per pixel + 36 B of gradient per visible (Gaussian, view).
-#ifndef ST3R_HOST_EMU   // tests/host/raster_emu_host.cpp runs the kernels of this file on the host (tests/host/simt_emu.h)
+// ST3R_HOST_EMU: test builds that run this file on a CPU SIMT emulator (tests/host/): raster_emu_host.cpp includes the
+// kernels only, build_emu_lib.py (ST3R_EMU_WHOLE) compiles the entry points too, with their launches rewritten.
+#if !defined(ST3R_HOST_EMU) || defined(ST3R_EMU_WHOLE)
 #include "common.cuh"
 #include "gs.cuh"
-#define ST3R_EMU_COUNT(i)
-#endif                  // (there ST3R_EMU_COUNT(i) counts how often a code path ran: path coverage of the emulated run)
+#endif
+#ifndef ST3R_EMU_COUNT
+#define ST3R_EMU_COUNT(i)   // raster_emu_host.cpp counts how often a marked code path ran (path coverage of the emulated run)
+#endif
 
 namespace {
 
@@ -803,7 +807,7 @@ raster_bwd_frag_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
 
 }  // namespace
 
-#ifndef ST3R_HOST_EMU
+#if !defined(ST3R_HOST_EMU) || defined(ST3R_EMU_WHOLE)
 static int g_raster_bwd_variant = 0;   // 0: per-visit butterfly (default), 1: per-warp record queues
 
 extern "C" {

@@ -366,8 +366,7 @@ def rasterization(means, quats, scales, opacities, colors, viewmats, Ks, width, 
                                   "outside the B200 path")
     if kw:
         raise NotImplementedError(f"unsupported gsplat.rasterization options {sorted(kw)}: Starst3r uses the defaults")
-    if not means.is_cuda:
-        raise RuntimeError("starst3r_b200.gs.rasterization: tensors must live on a CUDA device (no CPU fallback)")
+    _lib.require_cuda(means, quats, scales, opacities, colors)      # raises: there is no CPU fallback
     cams = make_cams(viewmats.to(means.device), Ks.to(means.device))
     render, alpha, last_ids = _Rasterize.apply(means, quats, scales, opacities, colors, cams, int(width), int(height))
     info = _info(_Rasterize.last_frame, opacities)

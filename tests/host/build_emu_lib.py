@@ -11,7 +11,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 CSRC = os.path.join(ROOT, "starst3r_b200", "csrc")
 HOST = os.path.join(ROOT, "tests", "host")
-SOURCES = ["api.cu", "scan.cu", "radix_sort.cu", "recip.cu", "nn_simt.cu", "align.cu", "align_dense.cu"]
+SOURCES = ["api.cu", "scan.cu", "radix_sort.cu", "recip.cu", "nn_simt.cu", "align.cu", "align_dense.cu",
+           "gs_project.cu", "gs_bin.cu", "gs_raster.cu", "gs_backward.cu", "gs_loss.cu", "gs_adam.cu", "gs_mcmc.cu"]
 CLUSTER_KERNELS = {"focal_weiszfeld_cluster_kernel": "WZ_CLUSTER"}     # launched cluster by cluster
 
 STUBS = r'''
@@ -25,7 +26,6 @@ int nn_tc_launch(const float*, const int32_t*, const int32_t*, int, const float*
 int nn_tc_launch_batch(const NnBatchItem*, int, int, cudaStream_t) { st3r_set_error("tcgen05 is not emulated"); return ST3R_ERR_UNSUPPORTED; }
 int nn_db_norm_launch(const float*, int, int, float*, cudaStream_t) { return ST3R_OK; }
 int nn_tc_split_launch(const float*, int, int, float*, float*, cudaStream_t) { return ST3R_ERR_UNSUPPORTED; }
-int gs_tile_bits(int n_tiles) { int b = 1; while ((1 << b) < n_tiles) ++b; return b; }
 extern "C" int st3r_emu_launch_failed(void) { return g_emu_launch_failed ? 1 : 0; }
 '''
 
@@ -89,7 +89,7 @@ def build(out_dir):
         with open(cpp, "w") as fh:
             fh.write(text)
         obj = cpp[:-4] + ".o"
-        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-DST3R_HOST_EMU=1", "-DST3R_EMU_WHOLE=1", "-I", CSRC, "-I", HOST, "-x", "c++", "-c", cpp,
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-DST3R_HOST_EMU=1", "-DST3R_EMU_WHOLE=1", "-I", CSRC, "-I", HOST, "-x", "c++", "-c", cpp,
                         "-o", obj], check=True)
         objs.append(obj)
     lib = os.path.join(out_dir, "libst3r_emu.so")

@@ -23,6 +23,11 @@ template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFunc
 alignas(16) static char emu_dyn_smem[128 * 1024];
 #define ST3R_DYN_SMEM_F32(name) float* name = reinterpret_cast<float*>(emu_dyn_smem)
 #define ST3R_DYN_SMEM(name) float* name = reinterpret_cast<float*>(emu_dyn_smem)
+#define ST3R_DYN_SMEM_I32(name) int32_t* name = reinterpret_cast<int32_t*>(emu_dyn_smem)
+#define __constant__ static
+#define cudaMemcpyToSymbol(sym, src, n) (memcpy((void*)&(sym), (src), (n)), cudaSuccess)
+template <typename T> static inline T __ldcv(const T* p) { return *p; }
+template <typename T> static inline T __ldg(const T* p) { return *p; }
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 

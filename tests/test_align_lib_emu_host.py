@@ -6,45 +6,18 @@ torch.cuda.device for host stand-ins; the checks are the ones tests/test_align_g
 fixtures produced by the unmodified reference (oracle/gen_golden_align.py): canonical view, Weiszfeld focal, dense
 points, clean_pointcloud, loss + gradients vs autograd, and the 30 + 20 iteration trajectory - for the default kernels
 and for the opt-in variants (segmented loss kernels, staged camera kernels, cluster Weiszfeld)."""
-import contextlib
-import ctypes
-import os
-import sys
-
 import pytest
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CPU = torch.device("cpu")
 
 
-@pytest.fixture(scope="module")
-def emu_lib(tmp_path_factory):
-    sys.path.insert(0, os.path.join(ROOT, "tests", "host"))
-    import build_emu_lib
-    from starst3r_b200 import _lib
-    path, _ = build_emu_lib.build(str(tmp_path_factory.mktemp("emu_lib")))
-    lib = ctypes.CDLL(path)
-    for name, (restype, argtypes) in _lib.parse_header().items():
-        if hasattr(lib, name):
-            getattr(lib, name).restype = restype
-            getattr(lib, name).argtypes = argtypes
-    return lib
-
-
 @pytest.fixture(params=[0, 3], ids=["default-kernels", "variants"])
-def backend(request, emu_lib, monkeypatch):
-    from starst3r_b200 import _lib
+def backend(request, emu_backend, monkeypatch):
     from starst3r_b200 import reconstruct as rc
-    monkeypatch.setattr(_lib, "load", lambda: emu_lib)
-    monkeypatch.setattr(_lib, "stream_ptr", lambda: None)
-    monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
-    monkeypatch.setattr(_lib, "last_error", lambda: emu_lib.st3r_last_error().decode(errors="replace"))
-    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
     monkeypatch.setattr(rc, "ALIGN_VARIANT", request.param)
-    yield emu_lib
-    assert emu_lib.st3r_emu_launch_failed() == 0, "emulator deadlock / unsupported launch"
-    emu_lib.st3r_align_set_variant(0)
+    yield emu_backend
+    emu_backend.st3r_align_set_variant(0)
 
 
 def test_canonical_view_focal_dense_clean_vs_reference(backend):

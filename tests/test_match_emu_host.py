@@ -16,19 +16,9 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 SIMT = 1      # ST3R_NN_SIMT
 
 
-@pytest.fixture(scope="module")
-def lib(tmp_path_factory):
-    sys.path.insert(0, os.path.join(ROOT, "tests", "host"))
-    import build_emu_lib
-    from starst3r_b200 import _lib
-    path, n_launches = build_emu_lib.build(str(tmp_path_factory.mktemp("emu_lib")))
-    assert n_launches >= 15
-    lib = ctypes.CDLL(path)
-    for name, (restype, argtypes) in _lib.parse_header().items():
-        if hasattr(lib, name):
-            getattr(lib, name).restype = restype
-            getattr(lib, name).argtypes = argtypes
-    return lib
+@pytest.fixture
+def lib(emu_lib):
+    return emu_lib
 
 
 def P(a):
