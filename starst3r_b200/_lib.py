@@ -89,3 +89,13 @@ def require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise RuntimeError("starst3r_b200: tensors must live on a CUDA device (no CPU fallback)")
+
+
+def require_cuda_device(device, what="starst3r_b200"):
+    """The hot paths only exist as sm_100a kernels: any other device is refused loudly (no CPU fallback)."""
+    import torch
+    d = torch.device(device if device is not None else "cuda")
+    if d.type != "cuda":
+        raise RuntimeError(f"{what}: device={device!r} - the hot path only runs on CUDA (sm_100a); "
+                           "no CPU fallback is provided")
+    return d

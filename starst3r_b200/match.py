@@ -22,11 +22,7 @@ _IMPL = {"auto": 0, "simt": 1, "tcgen05": 2}
 
 
 def _dev(device):
-    d = torch.device(device if device is not None else "cuda")
-    if d.type != "cuda":
-        raise RuntimeError(f"starst3r_b200.match: device={device!r} - the hot path only runs on CUDA (sm_100a); "
-                           "no CPU fallback is provided")
-    return d
+    return _lib.require_cuda_device(device, "starst3r_b200.match")
 
 
 def _f32(x, device):

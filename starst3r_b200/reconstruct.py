@@ -252,9 +252,7 @@ def sparse_scene_optimizer_slam(imgs, subsample, imsizes, pps, base_focals, core
         raise NotImplementedError("sparse_scene_optimizer_slam on B200 implements the configuration Starst3r uses "
                                   "(reconstruct.py:56-70: opt_depth=False, depth_mode='add', no lora/exp depth, "
                                   "separate intrinsics, no per-image init)")
-    dev = torch.device(device)
-    if dev.type != "cuda":
-        raise RuntimeError("sparse_scene_optimizer_slam: the fused optimiser only runs on CUDA (no CPU fallback)")
+    dev = _lib.require_cuda_device(device, "sparse_scene_optimizer_slam")        # the fused optimiser has no CPU fallback
     assert len(mst[1]) == len(imgs) - 1
     N = len(imgs)
     t, meta = flatten_problem(imgs, imsizes, pps, base_focals, core_depth, anchors, corres, corres2d, preds_21, mst,

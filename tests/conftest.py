@@ -43,9 +43,9 @@ def emu_lib(tmp_path_factory):
     assert n_launches >= 50
     lib = ctypes.CDLL(path)
     for name, (restype, argtypes) in _lib.parse_header().items():
-        if hasattr(lib, name):
-            getattr(lib, name).restype = restype
-            getattr(lib, name).argtypes = argtypes
+        fn = getattr(lib, name)          # the emulated library exports the complete C ABI (tcgen05 entry points stubbed)
+        fn.restype = restype
+        fn.argtypes = argtypes
     return lib
 
 
@@ -59,6 +59,7 @@ def emu_backend(emu_lib, monkeypatch):
     monkeypatch.setattr(_lib, "load", lambda: emu_lib)
     monkeypatch.setattr(_lib, "stream_ptr", lambda: None)
     monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
+    monkeypatch.setattr(_lib, "require_cuda_device", lambda device, what="": torch.device(device if device is not None else "cpu"))
     monkeypatch.setattr(_lib, "last_error", lambda: emu_lib.st3r_last_error().decode(errors="replace"))
     monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
     yield emu_lib

@@ -27,6 +27,10 @@ int nn_tc_launch_batch(const NnBatchItem*, int, int, cudaStream_t) { st3r_set_er
 int nn_db_norm_launch(const float*, int, int, float*, cudaStream_t) { return ST3R_OK; }
 int nn_tc_split_launch(const float*, int, int, float*, float*, cudaStream_t) { return ST3R_ERR_UNSUPPORTED; }
 extern "C" int st3r_emu_launch_failed(void) { return g_emu_launch_failed ? 1 : 0; }
+extern "C" int st3r_nn_tc_set_cooperative(int) { return ST3R_OK; }
+extern "C" int st3r_nn_tc_set_split(int) { return ST3R_OK; }
+extern "C" int st3r_nn_tc_stats(unsigned long long* h_out2, int) { if (h_out2) h_out2[0] = h_out2[1] = 0; return ST3R_OK; }
+extern "C" int st3r_debug_nn_tc_cycles(unsigned long long* h_out4, int) { if (h_out4) for (int i = 0; i < 4; ++i) h_out4[i] = 0; return ST3R_OK; }
 '''
 
 

@@ -54,3 +54,31 @@ def test_optimizer_trajectory_vs_reference(backend, name):
     assert torch.isfinite(hist1).all() and torch.isfinite(hist2).all() and hist1[-1] < hist1[0]
     t.assert_same_up_to_gauge(t.cpu(res_c), f["out"]["short"]["coarse"], 1e-4)
     t.assert_same_up_to_gauge(t.cpu(res_f), f["out"]["short"]["fine"], 1e-4)
+
+
+def test_reconstruct_scene_end_to_end(emu_backend, monkeypatch):
+    """starster.reconstruct_scene on a synthetic 3-view scene, every stage through the product code and the emulated
+    library: matching (exact SIMT nearest neighbour, reciprocal search, merge), canonical views, MST, the sparse global
+    alignment, dense points + clean_pointcloud.  The recovered relative poses and focals match the scene's."""
+    import math
+    from starst3r_b200 import match, synth
+    from starst3r_b200 import reconstruct as rc
+    monkeypatch.setattr(match, "USE_CUDA_GRAPHS", False)
+    monkeypatch.setattr(rc, "SHARD_PAIRS", False)
+    W, H, n = 64, 48, 3
+    model = synth.SyntheticMast3r(n, W, H, seed=0, device="cpu", arc_deg=70.0)
+    imgs = model.images()
+    real = rc.run_sparse_ga
+    monkeypatch.setattr(rc, "run_sparse_ga", lambda *a, **kw: real(*a, **{**kw, "niter1": 150, "niter2": 60}))
+    scene, params = rc.reconstruct_scene(model, imgs, [f"{i}.png" for i in range(n)], CPU)
+    pts, depth, confs = scene.get_dense_pts3d(clean_depth=True)
+    assert len(pts) == n and pts[0].shape == (H * W, 3) and torch.isfinite(pts[0]).all()
+    gt = torch.linalg.inv(model.viewmats)
+    est = scene.cam2w.cpu()
+    rel_e = torch.linalg.inv(est[0:1]) @ est
+    rel_g = torch.linalg.inv(gt[0:1]) @ gt
+    for i in range(1, n):
+        cosang = ((rel_e[i, :3, :3].T @ rel_g[i, :3, :3]).trace().item() - 1) / 2
+        assert math.degrees(math.acos(max(-1.0, min(1.0, cosang)))) < 4.0
+        assert torch.nn.functional.cosine_similarity(rel_e[i, :3, 3], rel_g[i, :3, 3], dim=0).item() > 0.98
+    assert (scene.intrinsics[:, 0, 0].cpu() / (1.2 * max(W, H)) - 1).abs().max().item() < 0.1
