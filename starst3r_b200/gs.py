@@ -476,9 +476,7 @@ class MCMCStrategy:
         pass
 
     def step_post_backward(self, params, optimizers, state, step, info, lr):
-        dev = params["means"].device
-        if dev.type != "cuda":
-            raise RuntimeError("starst3r_b200.gs.MCMCStrategy needs the splats on a CUDA device (no CPU fallback)")
+        dev = _lib.require_cuda_device(params["means"].device, "starst3r_b200.gs.MCMCStrategy")   # no CPU fallback
         binoms = state["binoms"] = state["binoms"].to(dev).contiguous()
         if self.refine_start_iter < step < self.refine_stop_iter and step % self.refine_every == 0:
             n_relocated = self._relocate_gs(params, optimizers, binoms)
