@@ -19,7 +19,9 @@
 // register and raises the running bound (a column can only win if its approximate score is
 // >= best_exact - eps), and the list starts empty again.  (A first version flagged such rows for
 // an exact warp-per-row kernel: 100 ms per pair on the synthetic scene instead of 2.5 ms.)
+#ifndef ST3R_HOST_EMU   // (CPU emulator builds, tests/host/: a software model of TMA / mbarriers / tcgen05 stands in)
 #include <cuda.h>
+#endif
 #include "common.cuh"
 #include "nn.cuh"
 #include "../../include/starst3r_b200.h"
@@ -85,6 +87,9 @@ struct Lay {
 constexpr float DELTA_COEF_SPLIT = 1.0e-4f;   // 2 x (3 x 2^-20 products dropped + <= ~2e-5 fp32 accumulation), 2x margin
 
 // ------------------------------------------------------------------ PTX wrappers
+#ifdef ST3R_HOST_EMU
+#include "tcgen05_emu.h"
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -152,6 +157,23 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_mbarrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc_cols(uint32_t smem_result_addr) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result_addr), "n"(kCols) : "memory");
+}
+#define tmem_alloc(addr, cols) tmem_alloc_cols<cols>(addr)
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc_cols(uint32_t base) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(kCols) : "memory");
+}
+#define tmem_dealloc(base, cols) tmem_dealloc_cols<cols>(base)
+template <int kThreads>
+__device__ __forceinline__ void named_bar_sync_n() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
+#define named_bar_sync(count) named_bar_sync_n<count>()
+#endif  // ST3R_HOST_EMU
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
 #ifdef NN_TC_FMNMX3
   float d;
@@ -227,7 +249,11 @@ struct EpiCtx {
 };
 static_assert(sizeof(EpiCtx) == 24, "EpiCtx layout");
 
+#ifdef ST3R_HOST_EMU
+#define smem_raw (reinterpret_cast<uint8_t*>(emu_dyn_smem))
+#else
 extern __shared__ uint8_t smem_raw[];
+#endif
 __device__ __forceinline__ uint8_t* smem_base() {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 }
@@ -455,13 +481,11 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
 #else
     for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
 #endif
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tc_fence_mbarrier_init();
   }
   if (warp == WARP_MMA) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
-                 "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tmem_alloc(smem_u32((const void*)tmem_ptr_smem), TMEM_COLS);
+    tmem_relinquish();
   }
   // A tile: gather query rows, write the 128B-swizzled K-major layout (chunk ^= row & 7), zero pad.
   for (int e = threadIdx.x; e < BM * 8; e += NUM_THREADS) {
@@ -479,7 +503,7 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
     }
     *reinterpret_cast<float4*>(smem + SMEM_A + r * ROWB + ((c ^ (r & 7)) << 4)) = v;
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -577,7 +601,7 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
       EpiCtx* ctx = reinterpret_cast<EpiCtx*>(smem + SMEM_CTX) + slot;
       ctx->q = qrow; ctx->best = 0ull; ctx->delta = delta; ctx->resolves = 0;
       if (threadIdx.x == 0) *reinterpret_cast<const float**>(smem + SMEM_DBP) = DB;
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");                      // DB pointer visible to all
+      named_bar_sync(EPI_THREADS);                                                       // DB pointer visible to all
     }
 
 #ifdef NN_TC_DEBUG_CYCLES
@@ -731,7 +755,7 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
   __syncthreads();
   if (warp == WARP_MMA) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -757,6 +781,7 @@ __global__ void db_split_kernel(const float4* __restrict__ DB, size_t n4, float4
   }
 }
 
+#ifndef ST3R_HOST_EMU
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -772,6 +797,8 @@ EncodeTiledFn get_encode_fn() {
   }
   return fn;
 }
+
+#endif
 
 }  // namespace
 
@@ -832,6 +859,12 @@ int nn_db_norm_launch(const float* DB, int N, int d, float* out_bound, cudaStrea
   return ST3R_OK;
 }
 
+#ifdef ST3R_HOST_EMU
+static int encode_db_tmap(CUtensorMap* tmap, const float* DB, int N) {     // the software model's tensor map
+  tmap->base = DB; tmap->rows = N; tmap->cols = DK; tmap->box_cols = 32; tmap->box_rows = BN;
+  return ST3R_OK;
+}
+#else
 static int encode_db_tmap(CUtensorMap* tmap, const float* DB, int N) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) {
@@ -853,6 +886,8 @@ static int encode_db_tmap(CUtensorMap* tmap, const float* DB, int N) {
   }
   return ST3R_OK;
 }
+
+#endif
 
 int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stream) {
   ST3R_CHECK_ARG(n >= 1 && n <= NN_MAX_BATCH, "nn_tc: batch size must be 1..%d", NN_MAX_BATCH);

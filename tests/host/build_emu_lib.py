@@ -1,8 +1,8 @@
 """TEST-ONLY: builds `libst3r_emu.so`, the C ABI of the MATCH and ALIGN paths (api.cu, scan.cu, radix_sort.cu, recip.cu,
 nn_simt.cu, align.cu, align_dense.cu) compiled for the HOST: every `kernel<<<grid, block, smem, stream>>>(args);` is rewritten into a call of the SIMT
 emulator (tests/host/simt_emu.h through emu_cuda_shim.h), everything else - the entry points' launch sequences,
-workspace carving, device-side counters - is compiled as it stands.  The tcgen05 matcher cannot run there: its entry
-points are stubbed and ST3R_NN_AUTO resolves to the exact SIMT kernels.  Used by tests/test_match_emu_host.py."""
+workspace carving, device-side counters - is compiled as it stands.  The tcgen05 matcher runs against a software model of
+TMA / mbarriers / tensor memory / tcgen05.mma (tests/host/tcgen05_emu.h).  Used by tests/test_match_emu_host.py."""
 import os
 import re
 import subprocess
@@ -12,25 +12,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 CSRC = os.path.join(ROOT, "starst3r_b200", "csrc")
 HOST = os.path.join(ROOT, "tests", "host")
 SOURCES = ["api.cu", "scan.cu", "radix_sort.cu", "recip.cu", "nn_simt.cu", "align.cu", "align_dense.cu",
-           "gs_project.cu", "gs_bin.cu", "gs_raster.cu", "gs_backward.cu", "gs_loss.cu", "gs_adam.cu", "gs_mcmc.cu"]
+           "gs_project.cu", "gs_bin.cu", "gs_raster.cu", "gs_backward.cu", "gs_loss.cu", "gs_adam.cu", "gs_mcmc.cu", "nn_tc.cu"]
 CLUSTER_KERNELS = {"focal_weiszfeld_cluster_kernel": "WZ_CLUSTER"}     # launched cluster by cluster
 
 STUBS = r'''
-// the tcgen05 matcher does not exist on the emulator
 #include "common.cuh"
-#include "nn.cuh"
-bool nn_tc_supported(int) { return false; }
-bool nn_tc_split_enabled() { return false; }
-int nn_tc_launch(const float*, const int32_t*, const int32_t*, int, const float*, int, int, const float*, unsigned long long*,
-                 cudaStream_t, const float*, const float*) { st3r_set_error("tcgen05 is not emulated"); return ST3R_ERR_UNSUPPORTED; }
-int nn_tc_launch_batch(const NnBatchItem*, int, int, cudaStream_t) { st3r_set_error("tcgen05 is not emulated"); return ST3R_ERR_UNSUPPORTED; }
-int nn_db_norm_launch(const float*, int, int, float*, cudaStream_t) { return ST3R_OK; }
-int nn_tc_split_launch(const float*, int, int, float*, float*, cudaStream_t) { return ST3R_ERR_UNSUPPORTED; }
 extern "C" int st3r_emu_launch_failed(void) { return g_emu_launch_failed ? 1 : 0; }
-extern "C" int st3r_nn_tc_set_cooperative(int) { return ST3R_OK; }
-extern "C" int st3r_nn_tc_set_split(int) { return ST3R_OK; }
-extern "C" int st3r_nn_tc_stats(unsigned long long* h_out2, int) { if (h_out2) h_out2[0] = h_out2[1] = 0; return ST3R_OK; }
-extern "C" int st3r_debug_nn_tc_cycles(unsigned long long* h_out4, int) { if (h_out4) for (int i = 0; i < 4; ++i) h_out4[i] = 0; return ST3R_OK; }
 '''
 
 
@@ -80,7 +67,8 @@ def rewrite(text):
         pos, n = i, n + 1
 
 
-def build(out_dir):
+def build(out_dir, defines=()):
+    """`defines`: extra -D macros (e.g. the experiment switches of nn_tc.cu)."""
     os.makedirs(out_dir, exist_ok=True)
     objs, launches = [], 0
     files = [(s, open(os.path.join(CSRC, s)).read()) for s in SOURCES] + [("emu_stubs.cu", STUBS)]
@@ -93,7 +81,7 @@ def build(out_dir):
         with open(cpp, "w") as fh:
             fh.write(text)
         obj = cpp[:-4] + ".o"
-        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-DST3R_HOST_EMU=1", "-DST3R_EMU_WHOLE=1", "-I", CSRC, "-I", HOST, "-x", "c++", "-c", cpp,
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-DST3R_HOST_EMU=1", "-DST3R_EMU_WHOLE=1", *[f"-D{d}" for d in defines], "-I", CSRC, "-I", HOST, "-x", "c++", "-c", cpp,
                         "-o", obj], check=True)
         objs.append(obj)
     lib = os.path.join(out_dir, "libst3r_emu.so")

@@ -4,6 +4,7 @@
 // synchronous), kernel launches (rewritten from <<< >>> by tests/host/build_emu_lib.py) run CTA after CTA.
 #pragma once
 #define __CUDA_RUNTIME_H__      // include/starst3r_b200.h: cudaStream_t comes from here
+#include <map>
 #include "simt_emu.h"
 
 typedef int cudaError_t;
@@ -20,12 +21,14 @@ static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { 
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 
 // dynamic shared memory of the kernel being launched (one CTA at a time)
-alignas(16) static char emu_dyn_smem[128 * 1024];
+alignas(1024) static char emu_dyn_smem[256 * 1024];
 #define ST3R_DYN_SMEM_F32(name) float* name = reinterpret_cast<float*>(emu_dyn_smem)
 #define ST3R_DYN_SMEM(name) float* name = reinterpret_cast<float*>(emu_dyn_smem)
 #define ST3R_DYN_SMEM_I32(name) int32_t* name = reinterpret_cast<int32_t*>(emu_dyn_smem)
 #define __constant__ static
 #define cudaMemcpyToSymbol(sym, src, n) (memcpy((void*)&(sym), (src), (n)), cudaSuccess)
+#define cudaMemcpyFromSymbol(dst, sym, n) (memcpy((dst), (const void*)&(sym), (n)), cudaSuccess)
+#define __grid_constant__
 template <typename T> static inline T __ldcv(const T* p) { return *p; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };

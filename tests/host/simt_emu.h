@@ -302,6 +302,8 @@ static inline uint64_t emu_shfl_lane(uint64_t v, int mode, int arg) {   // per-l
 static inline float __shfl_sync(unsigned, float v, int src) { return emu_float(emu_shfl(emu_bits(v), src & 31)); }
 static inline int __shfl_sync(unsigned, int v, int src) { return (int)(uint32_t)emu_shfl((uint32_t)v, src & 31); }
 static inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return (unsigned)emu_shfl(v, src & 31); }
+static inline unsigned long long __shfl_sync(unsigned, unsigned long long v, int src) { return emu_shfl(v, src & 31); }
+static inline unsigned long long __shfl_xor_sync(unsigned, unsigned long long v, int m) { return emu_shfl_lane(v, 0, m); }
 static inline float __shfl_xor_sync(unsigned, float v, int m) { return emu_float(emu_shfl_lane(emu_bits(v), 0, m)); }
 static inline int __shfl_xor_sync(unsigned, int v, int m) { return (int)(uint32_t)emu_shfl_lane((uint32_t)v, 0, m); }
 static inline float __shfl_down_sync(unsigned, float v, int d) { return emu_float(emu_shfl_lane(emu_bits(v), 1, d)); }

@@ -101,3 +101,94 @@ def test_extract_correspondences_golden(lib):
     k = int(n_out[0])
     assert k == len(g["conf"])
     assert np.array_equal(xy1[:k], g["xy1"]) and np.array_equal(xy2[:k], g["xy2"]) and np.array_equal(conf[:k], g["conf"])
+
+
+# ---- the tcgen05 matcher on the software model of TMA / mbarriers / tensor memory / tcgen05.mma --------------------
+TCGEN05 = 2
+
+
+@pytest.fixture(params=[(0, 0), (1, 0), (0, 1), (1, 1)], ids=["plain", "cooperative", "split", "cooperative+split"])
+def tc_variant(request, lib):
+    coop, split = request.param
+    lib.st3r_nn_tc_set_cooperative(coop)
+    lib.st3r_nn_tc_set_split(split)
+    yield request.param
+    lib.st3r_nn_tc_set_cooperative(0)
+    lib.st3r_nn_tc_set_split(0)
+
+
+def nn_argmax_impl(lib, Q, DB, impl):
+    Q, DB = np.ascontiguousarray(Q, np.float32), np.ascontiguousarray(DB, np.float32)
+    M, d = Q.shape
+    idx, best = np.zeros(M, np.int32), np.zeros(M, np.float32)
+    ws = ws_of(lib.st3r_nn_argmax_ws_bytes(M, DB.shape[0], d))
+    ok(lib, lib.st3r_nn_argmax(P(Q), M, P(DB), DB.shape[0], d, P(idx), P(best), P(ws), ws.nbytes, impl, None))
+    return idx, best
+
+
+def test_tcgen05_kernel_source_on_the_software_model(lib, tc_variant):
+    """nn_tc_kernel's own source - TMA producer, MMA issuer, eight epilogue warps, the mbarrier protocol, descriptor and
+    tensor-memory addressing, candidate lists and exact re-scores - against the exact SIMT kernel: identical indices and
+    scores, for every variant (per-thread / warp-cooperative rare path, plain / split precision), on random descriptors,
+    on a smooth field (hundreds of near ties inside the TF32 band: lists overflow and are resolved on the spot), with
+    exact duplicates (ties -> lowest index) and with ragged sizes (partial tiles, rows beyond the last query tile)."""
+    g = np.load(os.path.join(GOLD, "match_nn.npz"))
+    idx, _ = nn_argmax_impl(lib, g["Q"], g["DB"], TCGEN05)
+    assert np.array_equal(idx, g["nnA"])
+    rng = np.random.default_rng(0)
+    unit = lambda x: x / np.linalg.norm(x, axis=-1, keepdims=True)      # noqa: E731
+    cases = {}
+    cases["random"] = (unit(rng.standard_normal((300, 24))), unit(rng.standard_normal((2500, 24))))
+    t = np.linspace(0, 1, 3000)[:, None]
+    field = unit(np.cos(t * rng.standard_normal((1, 24)) * 2.0 + rng.standard_normal((1, 24))))
+    cases["smooth"] = (field[::11][:270] + 1e-4 * rng.standard_normal((270, 24)), field)
+    dup = unit(rng.standard_normal((700, 24)))
+    cases["duplicates"] = (dup[5:140], np.concatenate([dup, dup[::-1], dup]))
+    cases["unnormalised"] = (3.0 * rng.standard_normal((129, 24)), 0.2 * rng.standard_normal((1000, 24)) - 0.1)
+    for name, (Q, DB) in cases.items():
+        Q, DB = Q.astype(np.float32), DB.astype(np.float32)
+        i_tc, b_tc = nn_argmax_impl(lib, Q, DB, TCGEN05)
+        i_ex, b_ex = nn_argmax_impl(lib, Q, DB, SIMT)
+        assert np.array_equal(i_tc, i_ex), name
+        assert np.array_equal(b_tc, b_ex), name
+    st = (ctypes.c_ulonglong * 2)()
+    ok(lib, lib.st3r_nn_tc_stats(st, 1))
+    if not tc_variant[1]:
+        assert st[1] > 0          # the smooth field forced exact list resolutions (the rare path ran)
+
+
+def test_extract_correspondences_golden_tcgen05(lib, tc_variant):
+    g = np.load(os.path.join(GOLD, "match_extract.npz"))
+    f = [np.ascontiguousarray(g[k]) for k in ("f11", "f21", "f22", "f12")]
+    q = [np.ascontiguousarray(g[k]) for k in ("q11", "q21", "q22", "q12")]
+    H1, W1, d = f[0].shape
+    H2, W2, _ = f[1].shape
+    cap = lib.st3r_extract_corres_cap(H1, W1, H2, W2, 8)
+    xy1, xy2 = np.zeros((cap, 2), np.int64), np.zeros((cap, 2), np.int64)
+    conf, n_out = np.zeros(cap, np.float32), np.zeros(1, np.int32)
+    ws = ws_of(lib.st3r_extract_corres_ws_bytes(H1, W1, H2, W2, 8, 10))
+    ok(lib, lib.st3r_extract_corres(P(f[0]), P(f[1]), P(f[2]), P(f[3]), P(q[0]), P(q[1]), P(q[2]), P(q[3]), H1, W1, H2, W2, d, 8,
+                                    10, P(xy1), P(xy2), P(conf), P(n_out), P(ws), ws.nbytes, TCGEN05, None))
+    k = int(n_out[0])
+    assert k == len(g["conf"])
+    assert np.array_equal(xy1[:k], g["xy1"]) and np.array_equal(xy2[:k], g["xy2"]) and np.array_equal(conf[:k], g["conf"])
+
+
+def test_tcgen05_decoupled_barrier_build(tmp_path):
+    """The -DNN_TC_DECOUPLE experiment build (one full / empty mbarrier pair per query tile and accumulator stage): the
+    changed hand-off protocol completes without a deadlock on the software model and returns the exact results."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "host"))
+    import build_emu_lib
+    from starst3r_b200 import _lib
+    path, _ = build_emu_lib.build(str(tmp_path), defines=("NN_TC_DECOUPLE",))
+    lib = ctypes.CDLL(path)
+    for name, (restype, argtypes) in _lib.parse_header().items():
+        getattr(lib, name).restype, getattr(lib, name).argtypes = restype, argtypes
+    rng = np.random.default_rng(2)
+    Q = rng.standard_normal((300, 24)).astype(np.float32)
+    DB = rng.standard_normal((2500, 24)).astype(np.float32)
+    for split in (0, 1):
+        lib.st3r_nn_tc_set_split(split)
+        i_tc, b_tc = nn_argmax_impl(lib, Q, DB, TCGEN05)
+        i_ex, b_ex = nn_argmax_impl(lib, Q, DB, SIMT)
+        assert np.array_equal(i_tc, i_ex) and np.array_equal(b_tc, b_ex)
