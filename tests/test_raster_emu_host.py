@@ -141,3 +141,35 @@ def test_blend_kernels_on_the_simt_emulator(emu, n, C, W, H, ss, sl, seed):
     assert counts[6] > 0 and counts[7] > 0, list(counts)     # fragment-pool variant: dense visits and pool slots
     if per_tile.max() > 256:
         assert counts[1] > 0, list(counts)
+
+
+def test_backward_variants_agree_on_edge_shapes(emu):
+    """Randomised sweep over the shapes that stress the bookkeeping: one Gaussian, list lengths around the batch sizes
+    (64 / 128 / 256 +- 1), images smaller than a tile and ragged ones, near-opaque splats (early termination, alpha
+    clamp) and almost transparent ones: the three backward kernels agree and none of them deadlocks."""
+    rng = np.random.default_rng(123)
+    for it in range(28):
+        n = int(rng.choice([1, 3, 17, 63, 64, 65, 127, 128, 129, 255, 256, 257, 400, 900]))
+        C, W, H = int(rng.integers(1, 3)), int(rng.choice([5, 16, 17, 31, 33, 48])), int(rng.choice([3, 16, 18, 32, 40]))
+        ss, sl = float(rng.choice([0.3, 0.8, 1.5, 3.0])), float(rng.choice([2.0, 5.0, 12.0]))
+        A, B, col, offsets, n_isect, flatten, tw, th = make_frame(n, C, W, H, ss, sl, int(rng.integers(1 << 30)))
+        u = rng.random()
+        if u < 0.3:
+            A[:, 2] = rng.uniform(0.9, 1.0, len(A))
+        elif u < 0.5:
+            A[:, 2] = rng.uniform(0.001, 0.01, len(A))
+        v_render = rng.standard_normal((C, H, W, 3)).astype(np.float32)
+        v_alphas = rng.standard_normal((C, H, W)).astype(np.float32)
+        render, alphas = np.zeros((C, H, W, 3), np.float32), np.zeros((C, H, W), np.float32)
+        last_ids, n_blend = np.zeros((C, H, W), np.int32), np.zeros(1, np.uint64)
+        assert emu.emu_raster_fwd(P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), C, W, H, P(render), P(alphas),
+                                  P(last_ids), P(n_blend)) == 0
+        outs = []
+        for variant in (0, 1, 2):
+            vA, vB, vC = np.zeros_like(A), np.zeros_like(B), np.zeros_like(col)
+            assert emu.emu_raster_bwd(variant, P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), C, W, H, P(alphas),
+                                      P(last_ids), P(v_render), P(v_alphas), P(vA), P(vB), P(vC)) == 0, (it, variant)
+            outs.append(np.concatenate([vA[:, :3], vB[:, :3], vC[:, :3]], axis=1))
+        scale = np.abs(outs[0]).max(0) + 1e-12
+        for variant in (1, 2):
+            assert (np.abs(outs[0] - outs[variant]).max(0) / scale).max() < 1e-4, (it, variant, n, C, W, H)
