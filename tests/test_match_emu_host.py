@@ -192,3 +192,38 @@ def test_tcgen05_decoupled_barrier_build(tmp_path):
         i_tc, b_tc = nn_argmax_impl(lib, Q, DB, TCGEN05)
         i_ex, b_ex = nn_argmax_impl(lib, Q, DB, SIMT)
         assert np.array_equal(i_tc, i_ex) and np.array_equal(b_tc, b_ex)
+
+
+def test_tcgen05_variants_on_edge_sizes(lib):
+    """Sizes around the tile boundaries (128 DB rows, 256 query rows per CTA), single rows, and inputs that stress the
+    candidate band (smooth fields, exact duplicates, badly scaled operands): every variant of the tcgen05 kernel returns
+    the exact kernel's indices and scores."""
+    rng = np.random.default_rng(7)
+    for it in range(14):
+        M = int(rng.choice([1, 2, 31, 33, 127, 128, 129, 255, 256, 257, 513]))
+        N = int(rng.choice([1, 2, 127, 128, 129, 256, 1000, 1024, 1025, 4097]))
+        kind = ["rand", "smooth", "dup", "scaled"][it % 4]
+        if kind == "rand":
+            Q, DB = rng.standard_normal((M, 24)), rng.standard_normal((N, 24))
+        elif kind == "smooth":
+            t = np.linspace(0, 1, N)[:, None]
+            DB = np.cos(t * rng.standard_normal((1, 24)) * 2 + rng.standard_normal((1, 24)))
+            Q = DB[rng.integers(0, N, M)] + 1e-4 * rng.standard_normal((M, 24))
+        elif kind == "dup":
+            base = rng.standard_normal((max(N // 3, 1), 24))
+            DB = np.concatenate([base, base, base, base])[:N]
+            Q = DB[rng.integers(0, N, M)]
+        else:
+            Q, DB = 50 * rng.standard_normal((M, 24)), 1e-3 * rng.standard_normal((N, 24)) + 0.5
+        Q, DB = Q.astype(np.float32), DB.astype(np.float32)
+        i_ex, b_ex = nn_argmax_impl(lib, Q, DB, SIMT)
+        try:
+            for coop in (0, 1):
+                for split in (0, 1):
+                    lib.st3r_nn_tc_set_cooperative(coop)
+                    lib.st3r_nn_tc_set_split(split)
+                    i_tc, b_tc = nn_argmax_impl(lib, Q, DB, TCGEN05)
+                    assert np.array_equal(i_tc, i_ex) and np.array_equal(b_tc, b_ex), (M, N, kind, coop, split)
+        finally:
+            lib.st3r_nn_tc_set_cooperative(0)
+            lib.st3r_nn_tc_set_split(0)
