@@ -146,6 +146,17 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// 1 - alpha lies in [1e-3, 1]: rcp.approx (MUFU.RCP, 1 ulp) instead of the 15-instruction IEEE division
+__device__ __forceinline__ float fast_rcp(float x) {
+#ifdef ST3R_HOST_EMU
+  return 1.0f / x;
+#else
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#endif
+}
+
 __global__ void __launch_bounds__(BLOCK)
 raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
                   const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
@@ -169,13 +180,17 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
   const size_t p = ((size_t)c * H + min(i, H - 1)) * W + min(j, W - 1);
   const float T_final = 1.0f - alphas[p];
   float T = T_final;
-  float br = 0.f, bg = 0.f, bb = 0.f;
+  // The colour accumulated behind the current Gaussian only enters dL/dalpha through its dot product with this pixel's
+  // upstream gradient: one running scalar instead of three colour sums,
+  // dL/dalpha = T (c . v) + (T_final v_a - behind . v) / (1 - alpha).
+  float behind_v = 0.f;
   const int bin_final = inside ? last_ids[p] : 0;
   float vr = 0.f, vg = 0.f, vb = 0.f, va = 0.f;
   if (inside) {
     vr = v_render[3 * p]; vg = v_render[3 * p + 1]; vb = v_render[3 * p + 2];
     va = v_alphas ? v_alphas[p] : 0.f;
   }
+  const float tf_va = T_final * va;
   int warp_bin_final = bin_final;
   for (int off = 16; off; off >>= 1) warp_bin_final = max(warp_bin_final, __shfl_xor_sync(0xffffffffu, warp_bin_final, off));
 
@@ -224,13 +239,13 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
       if (!__any_sync(0xffffffffu, valid)) continue;
       float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (valid) {
-        const float ra = 1.0f / (1.0f - alpha);
+        const float ra = fast_rcp(1.0f - alpha);
         T *= ra;
         const float fac = alpha * T;
         const float4 col = sC[t];
         g[6] = fac * vr; g[7] = fac * vg; g[8] = fac * vb;
-        float v_alpha = (col.x * T - br * ra) * vr + (col.y * T - bg * ra) * vg + (col.z * T - bb * ra) * vb;
-        v_alpha += T_final * ra * va;
+        const float cv = col.x * vr + col.y * vg + col.z * vb;
+        const float v_alpha = T * cv + ra * (tf_va - behind_v);
         if (opac * vis <= ALPHA_MAX) {
           const float v_sigma = -opac * vis * v_alpha;
           g[3] = 0.5f * v_sigma * dx * dx;
@@ -240,7 +255,7 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
           g[1] = v_sigma * (B.y * dx + B.z * dy);
           g[2] = vis * v_alpha;
         }
-        br += col.x * fac; bg += col.y * fac; bb += col.z * fac;
+        behind_v += fac * cv;
       }
       // Transposed butterfly: 8 of the 9 sums are reduced with 4+2+1+2 shuffles (instead of 8 x 5) by halving the
       // number of live values at each exchange; afterwards lane l holds the warp total of value (l >> 2) and the 8
@@ -570,17 +585,6 @@ constexpr int FRAG_SLOTS = 64;    // pool slots per Gaussian = largest bounding 
 
 struct FragBox { uint8_t r0, c0, wc, nr; };    // first row / column of the box inside the tile, its width and height;
 constexpr int FRAG_BIG = 0x80;                  // nr & FRAG_BIG: more than FRAG_SLOTS pixels, dense path
-
-// 1 - alpha lies in [1e-3, 1]: rcp.approx (MUFU.RCP, 1 ulp) instead of the 15-instruction IEEE division
-__device__ __forceinline__ float fast_rcp(float x) {
-#ifdef ST3R_HOST_EMU
-  return 1.0f / x;
-#else
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-#endif
-}
 
 __global__ void __launch_bounds__(BLOCK)
 raster_bwd_frag_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
