@@ -39,7 +39,7 @@ def raster_leg(dev, out):
     flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
     for scale_mode in ("init", "rand"):      # 3e-3 initial scale / exp(N(-4, 0.5)) sweep of SURVEY 8d
         params, states, truth, cams = bench.make_workload(dev, 0, scale_mode=scale_mode)
-        for variant in (0, 1, 2):
+        for variant in (0, 1, 2, 3):
             key = f"train_step_ms[{scale_mode}][raster_variant={variant}]"
             try:
                 gs.RASTER_BWD_VARIANT = variant
@@ -52,6 +52,13 @@ def raster_leg(dev, out):
                     it[0] += 1
                     gs.train_step(p, s, truth, cams, bench.W, bench.H, it[0], plan=plan)
                 out[key] = ev_time(step, 12, 10, flush)
+                gs.PROF = {}
+                for _ in range(5):
+                    flush.add_(1)
+                    step()
+                prof = gs.prof_summary()
+                gs.PROF = None
+                out[key + "[kernels_ms]"] = {k.replace("st3r_gs_", ""): round(v[1] / v[0], 4) for k, v in prof.items()}
             except Exception as e:
                 out[key] = "ERROR " + repr(e)[:300]
             finally:

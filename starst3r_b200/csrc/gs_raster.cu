@@ -310,6 +310,357 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
 }
 
 
+// The nine gradient terms of one (pixel, Gaussian) contribution from fac = alpha T and w = vis dL/dalpha (w = 0 when
+// alpha was clamped to ALPHA_MAX): xy 2, opacity 1, conic 3, rgb 3 - same expressions as in raster_bwd_kernel.
+__device__ __forceinline__ void blend_grad_terms(const float4 A, const float4 B, float dx, float dy, float fac, float w,
+                                                 float vr, float vg, float vb, float* g) {
+  const float v_sigma = -A.z * w;
+  g[0] = v_sigma * (B.x * dx + B.y * dy);
+  g[1] = v_sigma * (B.y * dx + B.z * dy);
+  g[2] = w;
+  g[3] = 0.5f * v_sigma * dx * dx;
+  g[4] = v_sigma * dx * dy;
+  g[5] = 0.5f * v_sigma * dy * dy;
+  g[6] = fac * vr; g[7] = fac * vg; g[8] = fac * vb;
+}
+
+// ---- fragment-pool kernels (forward and backward) --------------------------------------------------------------------
+// With the reference's 3e-3 initial scale a splat covers a handful of pixels, and the pixel-parallel walk above spends
+// its instructions on alpha tests that fail (forward: 4.5 % hit rate) and on warp reductions in which ~6 of 32 lanes
+// carry a value (ncu, round 1: both kernels issue-bound).  Here the work is split by what it is parallel in:
+//   A. Gaussian-parallel: the PTPG lanes that own a Gaussian of the batch walk its bounding box inside the tile
+//      (conservative extents of the alpha >= 1/255 ellipse, clipped to the tile and the image), evaluate alpha once per
+//      box pixel, store it in the Gaussian's run of a shared-memory pool (slots are handed out by a block-wide scan of
+//      the box areas, so small and tile-sized splats mix freely) and set the Gaussian's bit in the mask of every pixel
+//      that passes the test;
+//   B. pixel-parallel: every pixel walks the set bits of ITS OWN mask in depth order - no alpha test, no warp
+//      collective, only the recurrence that is sequential per pixel (transmittance, colour; backward: colour behind,
+//      dL/dalpha, results written back to the pool slot);
+//   C. (backward) Gaussian-parallel again: the lanes of a Gaussian turn its pool slots into the nine gradient sums in
+//      registers, two shuffles combine them, one vector atomic per (tile, Gaussian): no shared-memory atomics at all.
+// Results: same expressions in the same per-pixel order as the kernels above; the backward's per-Gaussian sums are
+// added in a different (fixed) order.
+#ifndef ST3R_POOL_FG
+#define ST3R_POOL_FG 64
+#endif
+constexpr int PG = ST3R_POOL_FG;       // Gaussians per batch
+constexpr int PTPG = BLOCK / PG;       // lanes per Gaussian in the Gaussian-parallel phases
+constexpr int PGW = 32 / PTPG;         // Gaussians per warp
+constexpr int PW = PG / 32;            // mask words per pixel
+constexpr int PSLOTS = PG * 32;        // pool slots per batch (a Gaussian takes at most 256)
+static_assert(PG == 64 || PG == 128, "pool batch: 64 or 128 Gaussians");
+
+struct PoolBox { int origin; uint32_t geo; };   // pool slot of tile pixel (row, col) = origin + row * wc + col;
+// geo = r0 | c0 << 4 | (wc - 1) << 8 | (nr - 1) << 12 | area << 16; 0: the Gaussian takes no part in this batch
+
+// Box of tile pixels (rows r0..r1, columns c0..c1, clipped to rmax / cmax) on which opac * exp(-sigma) >= 1/255 is
+// possible; see row_mask for the bound.  Returns the area (0: cannot contribute) and the packed geometry.
+__device__ __forceinline__ int pool_box(const float4 A, const float4 B, float px0, float py0, int rmax, int cmax,
+                                        uint32_t& geo) {
+  geo = 0;
+  const float L = logf(255.0f * A.z);
+  if (!(L > 0.f)) return 0;
+  int r0 = 0, r1 = rmax, c0 = 0, c1 = cmax;
+  const float det = B.x * B.z - B.y * B.y;
+  if (det > 0.f) {
+    const float hy = sqrtf(2.0f * L * B.x / det) * 1.0005f + 2e-3f;
+    const float hx = sqrtf(2.0f * L * B.z / det) * 1.0005f + 2e-3f;
+    // (NaN / inf extents fall through fmaxf / fminf to the whole tile)
+    r0 = max(0, (int)fmaxf(ceilf(A.y - hy - py0), -1.0f));
+    r1 = min(rmax, (int)fminf(floorf(A.y + hy - py0), (float)TILE));
+    c0 = max(0, (int)fmaxf(ceilf(A.x - hx - px0), -1.0f));
+    c1 = min(cmax, (int)fminf(floorf(A.x + hx - px0), (float)TILE));
+  }
+  if (r1 < r0 || c1 < c0) return 0;
+  const int wc = c1 - c0 + 1, nr = r1 - r0 + 1;
+  geo = (uint32_t)r0 | (uint32_t)c0 << 4 | (uint32_t)(wc - 1) << 8 | (uint32_t)(nr - 1) << 12 | (uint32_t)(wc * nr) << 16;
+  return wc * nr;
+}
+
+// Stage one batch: the lanes of Gaussian slot t = (warp, lane / PTPG) load it (same address: one transaction), derive
+// its box and get its pool run from a block-wide exclusive scan of the areas.  `have`: the slot holds a Gaussian.
+// Gaussians whose run would not fit into the pool are left to the next batch (geo = 0); *taken (shared, per warp) gets
+// the number of Gaussians of this warp that were staged.  Contains the batch's first barrier; returns its
+// __syncthreads_count(done_pred).
+__device__ __forceinline__ int pool_stage(bool have, uint32_t e, const float4* __restrict__ geomA,
+                                          const float4* __restrict__ geomB, const float4* __restrict__ rgb, float px0,
+                                          float py0, int rmax, int cmax, int done_pred, float4* sC, PoolBox* sBox,
+                                          uint32_t (*sMask)[BLOCK], int* sScan, int* sTake, float4& A, float4& B,
+                                          uint32_t& geo, int& base) {
+  const int tr = threadIdx.x, lane = tr & 31, wrp = tr >> 5;
+  const int t = wrp * PGW + lane / PTPG;
+  const bool lead = (lane % PTPG) == 0;
+  A = make_float4(0.f, 0.f, 0.f, 0.f);
+  B = A;
+  int area = 0;
+  geo = 0;
+  if (have) {
+    A = geomA[e];
+    B = geomB[e];
+    if (lead) sC[t] = rgb[e];
+    area = pool_box(A, B, px0, py0, rmax, cmax, geo);
+  }
+  // inclusive scan over the warp of the leaders' areas: every lane of a group ends up with its own Gaussian's total
+  int incl = lead ? area : 0;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = (int)__shfl_up_sync(0xffffffffu, (unsigned)incl, off);
+    if (lane >= off) incl += v;
+  }
+  if (lane == 31) sScan[wrp] = incl;
+#pragma unroll
+  for (int w = 0; w < PW; ++w) sMask[w][tr] = 0u;
+  const int n_done = __syncthreads_count(done_pred);
+  int before = 0;
+#pragma unroll
+  for (int k = 0; k < BLOCK / 32 - 1; ++k) before += (k < wrp) ? sScan[k] : 0;
+  base = before + incl - area;
+  const bool fits = have && base + area <= PSLOTS;       // monotone along t: a prefix of the batch is staged
+  if (!fits) geo = 0;
+  if (have && !fits && lead) ST3R_EMU_COUNT(12);             // Gaussians left to the next batch (pool full)
+  const uint32_t staged = __ballot_sync(0xffffffffu, lead && fits);
+  if (lane == 0) sTake[wrp] = __popc(staged);
+  if (lead) {
+    PoolBox bx;
+    const int wc = (int)((geo >> 8) & 15u) + 1;
+    bx.origin = base - (int)(geo & 15u) * wc - (int)((geo >> 4) & 15u);
+    bx.geo = geo;
+    sBox[t] = bx;
+  }
+  return n_done;
+}
+
+__global__ void __launch_bounds__(BLOCK)
+raster_fwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
+                       const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
+                       const float4* __restrict__ geomB, const float4* __restrict__ rgb, int C, int W, int H, int tile_w,
+                       int tile_h, float* __restrict__ render, float* __restrict__ alphas,
+                       int32_t* __restrict__ last_ids, unsigned long long* __restrict__ n_blend) {
+  __shared__ float4 sC[PG];
+  __shared__ PoolBox sBox[PG];
+  __shared__ uint32_t sMask[PW][BLOCK];
+  __shared__ float sPool[PSLOTS];
+  __shared__ int sScan[BLOCK / 32], sTake[BLOCK / 32];
+  const int c = blockIdx.y, tile = blockIdx.x;
+  const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
+  const int tr = threadIdx.x, lane = tr & 31, wrp = tr >> 5;
+  const int myrow = tr >> 4, mycol = tr & 15;
+  const int i = tyi * TILE + myrow, j = txi * TILE + mycol;
+  const bool inside = i < H && j < W;
+  const float px0 = (float)(txi * TILE) + 0.5f, py0 = (float)(tyi * TILE) + 0.5f;   // centre of the tile's first pixel
+  const int rmax = min(TILE, H - tyi * TILE) - 1, cmax = min(TILE, W - txi * TILE) - 1;
+  const int gq = lane % PTPG, t_own = wrp * PGW + lane / PTPG;
+  bool done = !inside;
+  const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
+  float T = 1.0f, pr = 0.f, pg = 0.f, pb = 0.f;
+  int cur = 0, blends = 0;
+  int pos = rg.lo;
+  while (pos < rg.hi) {
+    const int idx = pos + t_own;
+    const bool have = idx < rg.hi;
+    const uint32_t e = have ? flatten[idx] : 0u;
+    float4 A, B;
+    uint32_t geo;
+    int base;
+    const int n_done = pool_stage(have, e, geomA, geomB, rgb, px0, py0, rmax, cmax, done, sC, sBox, sMask, sScan, sTake,
+                                  A, B, geo, base);
+    if (n_done == BLOCK) break;
+    // ---- phase A: alpha of every box pixel, contribution bits
+    if (geo) {
+      const int wc = (int)((geo >> 8) & 15u) + 1, area = (int)(geo >> 16);
+      const int r0 = (int)(geo & 15u), c0 = (int)((geo >> 4) & 15u);
+      const float rwc = 1.0f / (float)wc;
+      const uint32_t bit = 1u << (t_own & 31);
+      for (int s = gq; s < area; s += PTPG) {
+        const int rr = (int)(((float)s + 0.5f) * rwc);          // s / wc (s < 256, wc <= 16: far from the rounding edge)
+        const int r = r0 + rr, cc = c0 + s - rr * wc;
+        const float dx = A.x - (px0 + (float)cc), dy = A.y - (py0 + (float)r);
+        const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
+        const float alpha = fminf(ALPHA_MAX, A.z * __expf(-sigma));
+        ST3R_EMU_COUNT(10);                                     // box pixels tested
+        if (!(sigma < 0.f || alpha < ALPHA_MIN)) {
+          sPool[base + s] = alpha;
+          atomicOr(&sMask[t_own >> 5][r * TILE + cc], bit);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase B: the pixel's own contributing Gaussians, front to back
+#pragma unroll
+    for (int w = 0; w < PW; ++w) {
+      uint32_t bits = sMask[w][tr];
+      while (bits && !done) {
+        const int t = w * 32 + __ffs(bits) - 1;
+        bits &= bits - 1;
+        const PoolBox bx = sBox[t];
+        const float alpha = sPool[bx.origin + myrow * ((int)((bx.geo >> 8) & 15u) + 1) + mycol];
+        const float nT = T * (1.0f - alpha);
+        if (nT <= T_MIN) { done = true; break; }
+        const float wgt = alpha * T;
+        const float4 col = sC[t];
+        pr += col.x * wgt; pg += col.y * wgt; pb += col.z * wgt;
+        cur = pos + t;
+        T = nT;
+        ++blends;
+      }
+    }
+    __syncthreads();
+    int take = 0;
+#pragma unroll
+    for (int k = 0; k < BLOCK / 32; ++k) take += sTake[k];
+    pos += take;
+  }
+  if (inside) {
+    const size_t p = ((size_t)c * H + i) * W + j;
+    render[3 * p] = pr; render[3 * p + 1] = pg; render[3 * p + 2] = pb;
+    alphas[p] = 1.0f - T;
+    last_ids[p] = cur;
+  }
+  if (n_blend) {
+    for (int off = 16; off; off >>= 1) blends += __shfl_xor_sync(0xffffffffu, blends, off);
+    if (lane == 0 && blends) atomicAdd(n_blend, (unsigned long long)blends);
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK)
+raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
+                       const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
+                       const float4* __restrict__ geomB, const float4* __restrict__ rgb, int C, int W, int H, int tile_w,
+                       int tile_h, const float* __restrict__ alphas, const int32_t* __restrict__ last_ids,
+                       const float* __restrict__ v_render, const float* __restrict__ v_alphas,
+                       float4* __restrict__ v_geomA, float4* __restrict__ v_geomB, float4* __restrict__ v_rgb) {
+  __shared__ float4 sC[PG];
+  __shared__ PoolBox sBox[PG];
+  __shared__ uint32_t sMask[PW][BLOCK];
+  __shared__ float2 sPool[PSLOTS];           // phase A: (alpha, vis or 0 when alpha was clamped); phase B: (alpha T, vis dL/dalpha)
+  __shared__ float4 sV[BLOCK];               // upstream colour gradient of every pixel of the tile
+  __shared__ int sScan[BLOCK / 32], sTake[BLOCK / 32];
+  const int c = blockIdx.y, tile = blockIdx.x;
+  const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
+  const int tr = threadIdx.x, lane = tr & 31, wrp = tr >> 5;
+  const int myrow = tr >> 4, mycol = tr & 15;
+  const int i = tyi * TILE + myrow, j = txi * TILE + mycol;
+  const bool inside = i < H && j < W;
+  const float px0 = (float)(txi * TILE) + 0.5f, py0 = (float)(tyi * TILE) + 0.5f;
+  const int rmax = min(TILE, H - tyi * TILE) - 1, cmax = min(TILE, W - txi * TILE) - 1;
+  const int gq = lane % PTPG, t_own = wrp * PGW + lane / PTPG;
+  const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
+  if (rg.hi <= rg.lo) return;
+  const size_t p = ((size_t)c * H + min(i, H - 1)) * W + min(j, W - 1);
+  const float T_final = 1.0f - alphas[p];
+  float T = T_final;
+  float behind_v = 0.f;                      // (colour behind the current Gaussian) . (upstream colour gradient)
+  const int bin_final = inside ? last_ids[p] : 0;
+  float vr = 0.f, vg = 0.f, vb = 0.f, va = 0.f;
+  if (inside) {
+    vr = v_render[3 * p]; vg = v_render[3 * p + 1]; vb = v_render[3 * p + 2];
+    va = v_alphas ? v_alphas[p] : 0.f;
+  }
+  sV[tr] = make_float4(vr, vg, vb, 0.f);
+  const float tf_va = T_final * va;
+  // nothing behind the last Gaussian any pixel of the tile blended takes part
+  int tile_last = __reduce_max_sync(0xffffffffu, bin_final);
+  if (lane == 0) sScan[wrp] = tile_last;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < BLOCK / 32; ++k) tile_last = max(tile_last, sScan[k]);
+  __syncthreads();                           // sScan is reused by the first pool_stage
+  int hi = min(rg.hi - 1, tile_last);        // slot t of a batch holds sorted position hi - t: ascending t = back to front
+  while (hi >= rg.lo) {
+    const int idx = hi - t_own;
+    const bool have = idx >= rg.lo;
+    const uint32_t e = have ? flatten[idx] : 0u;
+    float4 A, B;
+    uint32_t geo;
+    int base;
+    pool_stage(have, e, geomA, geomB, rgb, px0, py0, rmax, cmax, 0, sC, sBox, sMask, sScan, sTake, A, B, geo, base);
+    const int wc = (int)((geo >> 8) & 15u) + 1, area = (int)(geo >> 16);
+    const int r0 = (int)(geo & 15u), c0 = (int)((geo >> 4) & 15u);
+    const float rwc = 1.0f / (float)wc;
+    // ---- phase A
+    if (geo) {
+      const uint32_t bit = 1u << (t_own & 31);
+      for (int s = gq; s < area; s += PTPG) {
+        const int rr = (int)(((float)s + 0.5f) * rwc);
+        const int r = r0 + rr, cc = c0 + s - rr * wc;
+        const float dx = A.x - (px0 + (float)cc), dy = A.y - (py0 + (float)r);
+        const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
+        const float vis = __expf(-sigma);
+        const float alpha = fminf(ALPHA_MAX, A.z * vis);
+        float2 av = make_float2(0.f, 0.f);
+        if (!(sigma < 0.f || alpha < ALPHA_MIN)) {
+          av = make_float2(alpha, (A.z * vis <= ALPHA_MAX) ? vis : 0.f);
+          atomicOr(&sMask[t_own >> 5][r * TILE + cc], bit);
+        }
+        sPool[base + s] = av;                 // non-contributing slots read as "nothing" in phase C
+      }
+    }
+    __syncthreads();
+    // ---- phase B: per-pixel recurrence over the pixel's own contributing Gaussians, back to front
+#pragma unroll
+    for (int w = 0; w < PW; ++w) {
+      uint32_t bits = sMask[w][tr];
+      while (bits) {
+        const int t = w * 32 + __ffs(bits) - 1;
+        bits &= bits - 1;
+        const PoolBox bx = sBox[t];
+        const int slot = bx.origin + myrow * ((int)((bx.geo >> 8) & 15u) + 1) + mycol;
+        float2 out = make_float2(0.f, 0.f);   // a Gaussian behind this pixel's last blended one contributes nothing
+        if (hi - t <= bin_final) {
+          const float2 av = sPool[slot];
+          const float ra = fast_rcp(1.0f - av.x);
+          T *= ra;
+          const float fac = av.x * T;
+          const float4 col = sC[t];
+          const float cv = col.x * vr + col.y * vg + col.z * vb;
+          const float v_alpha = T * cv + ra * (tf_va - behind_v);
+          behind_v += fac * cv;
+          out = make_float2(fac, av.y * v_alpha);
+          ST3R_EMU_COUNT(11);                 // contributing (pixel, Gaussian) pairs
+        }
+        sPool[slot] = out;
+      }
+    }
+    __syncthreads();
+    // ---- phase C: the lanes of a Gaussian turn its slots into the nine sums
+    {
+      float g9[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) g9[k] = 0.f;
+      if (geo) {
+        for (int s = gq; s < area; s += PTPG) {
+          const float2 fw = sPool[base + s];
+          if (fw.x == 0.f && fw.y == 0.f) continue;
+          const int rr = (int)(((float)s + 0.5f) * rwc);
+          const int r = r0 + rr, cc = c0 + s - rr * wc;
+          const float4 v = sV[r * TILE + cc];
+          float g[9];
+          blend_grad_terms(A, B, A.x - (px0 + (float)cc), A.y - (py0 + (float)r), fw.x, fw.y, v.x, v.y, v.z, g);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) g9[k] += g[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {             // the lanes of a Gaussian are adjacent
+#pragma unroll
+        for (int off = 1; off < PTPG; off <<= 1) g9[k] += __shfl_xor_sync(0xffffffffu, g9[k], off);
+      }
+      if (gq == 0 && geo &&
+          (g9[0] != 0.f || g9[1] != 0.f || g9[2] != 0.f || g9[3] != 0.f || g9[4] != 0.f || g9[5] != 0.f ||
+           g9[6] != 0.f || g9[7] != 0.f || g9[8] != 0.f)) {
+        atomicAdd(v_geomA + e, make_float4(g9[0], g9[1], g9[2], 0.f));
+        atomicAdd(v_geomB + e, make_float4(g9[3], g9[4], g9[5], 0.f));
+        atomicAdd(v_rgb + e, make_float4(g9[6], g9[7], g9[8], 0.f));
+      }
+    }
+    int take = 0;
+#pragma unroll
+    for (int k = 0; k < BLOCK / 32; ++k) take += sTake[k];
+    hi -= take;
+  }
+}
+
+
 // ---- variant 1 of the backward: per-warp record queues ----------------------------------------------------------
 // With the reference's 3e-3 initial scale a Gaussian covers ~12 pixels, so a (warp, Gaussian) visit of the kernel
 // above has ~3 of 32 lanes with a contribution, yet all lanes run the gradient arithmetic and the nine-value
@@ -357,20 +708,6 @@ __device__ __forceinline__ void butterfly9_to_shared(const float* g, float* a9) 
   const bool ninth = lane == 1;
   const float sum = ninth ? g8 : c1;
   if (((lane & 3) == 0 || ninth) && sum != 0.f) atomicAdd(a9 + (ninth ? 8 : vi), sum);
-}
-
-// The nine gradient terms of one (pixel, Gaussian) contribution from fac = alpha T and w = vis dL/dalpha (w = 0 when
-// alpha was clamped to ALPHA_MAX): xy 2, opacity 1, conic 3, rgb 3 - same expressions as in raster_bwd_kernel.
-__device__ __forceinline__ void blend_grad_terms(const float4 A, const float4 B, float dx, float dy, float fac, float w,
-                                                 float vr, float vg, float vb, float* g) {
-  const float v_sigma = -A.z * w;
-  g[0] = v_sigma * (B.x * dx + B.y * dy);
-  g[1] = v_sigma * (B.y * dx + B.z * dy);
-  g[2] = w;
-  g[3] = 0.5f * v_sigma * dx * dx;
-  g[4] = v_sigma * dx * dy;
-  g[5] = 0.5f * v_sigma * dy * dy;
-  g[6] = fac * vr; g[7] = fac * vg; g[8] = fac * vb;
 }
 
 // Warp-collective drain of n queued records (see above).  px0 / py0: centre of the warp's first pixel.
@@ -812,12 +1149,13 @@ raster_bwd_frag_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
 }  // namespace
 
 #if !defined(ST3R_HOST_EMU) || defined(ST3R_EMU_WHOLE)
-static int g_raster_bwd_variant = 0;   // 0: per-visit butterfly (default), 1: per-warp record queues
+static int g_raster_bwd_variant = 0;   // 0: per-visit butterfly (default), 1: per-warp record queues, 2: fragment pool
+                                       // behind warp visits, 3: fragment-pool kernels (forward and backward)
 
 extern "C" {
 
 int st3r_gs_set_raster_variant(int variant) {
-  ST3R_CHECK_ARG(variant >= 0 && variant <= 2, "st3r_gs_set_raster_variant: unknown variant %d", variant);
+  ST3R_CHECK_ARG(variant >= 0 && variant <= 3, "st3r_gs_set_raster_variant: unknown variant %d", variant);
   g_raster_bwd_variant = variant;
   return ST3R_OK;
 }
@@ -833,10 +1171,16 @@ int st3r_gs_raster_fwd(const int32_t* offsets, const int32_t* n_isect, const uin
                  "st3r_gs_raster_fwd: null pointer");
   const int tile_w = (width + TILE - 1) / TILE, tile_h = (height + TILE - 1) / TILE;
   dim3 grid(tile_w * tile_h, C);
-  raster_fwd_kernel<<<grid, BLOCK, 0, stream>>>(offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA),
-                                                reinterpret_cast<const float4*>(geomB),
-                                                reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h,
-                                                render, alphas, last_ids, reinterpret_cast<unsigned long long*>(n_blend));
+  if (g_raster_bwd_variant == 3)
+    raster_fwd_pool_kernel<<<grid, BLOCK, 0, stream>>>(
+        offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
+        reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, render, alphas, last_ids,
+        reinterpret_cast<unsigned long long*>(n_blend));
+  else
+    raster_fwd_kernel<<<grid, BLOCK, 0, stream>>>(
+        offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
+        reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, render, alphas, last_ids,
+        reinterpret_cast<unsigned long long*>(n_blend));
   ST3R_CHECK_LAUNCH();
   return ST3R_OK;
 }
@@ -853,7 +1197,12 @@ int st3r_gs_raster_bwd(const int32_t* offsets, const int32_t* n_isect, const uin
                  "st3r_gs_raster_bwd: null pointer");
   const int tile_w = (width + TILE - 1) / TILE, tile_h = (height + TILE - 1) / TILE;
   dim3 grid(tile_w * tile_h, C);
-  if (g_raster_bwd_variant == 2)
+  if (g_raster_bwd_variant == 3)
+    raster_bwd_pool_kernel<<<grid, BLOCK, 0, stream>>>(
+        offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
+        reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, alphas, last_ids, v_render, v_alphas,
+        reinterpret_cast<float4*>(v_geomA), reinterpret_cast<float4*>(v_geomB), reinterpret_cast<float4*>(v_rgb));
+  else if (g_raster_bwd_variant == 2)
     raster_bwd_frag_kernel<<<grid, BLOCK, 0, stream>>>(
         offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
         reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, alphas, last_ids, v_render, v_alphas,

@@ -271,6 +271,7 @@ def _forward(means, quats, scales, opacities, shN, cams, width, height, count_bl
             with _Prof("st3r_gs_offsets"):
                 _lib.check(lib.st3r_gs_offsets(_lib.ptr(fr.keys), _lib.ptr(n_dev), n_cap, C, fr.W, fr.H, TILE,
                                                _lib.ptr(fr.offsets), st), "st3r_gs_offsets")
+        _lib.check(lib.st3r_gs_set_raster_variant(int(RASTER_BWD_VARIANT)), "st3r_gs_set_raster_variant")
         with _Prof("st3r_gs_raster_fwd"):
             _lib.check(lib.st3r_gs_raster_fwd(_lib.ptr(fr.offsets), _lib.ptr(n_dev), _lib.ptr(fr.vals),
                                               _lib.ptr(fr.geomA), _lib.ptr(fr.geomB), _lib.ptr(fr.rgb), C, fr.W, fr.H, TILE,

@@ -9,7 +9,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-__all__ = ("process_image", "load_image", "load_images", "prepare_images_for_mast3r")
+__all__ = ("make_pair_indices", "process_image", "load_image", "load_images", "prepare_images_for_mast3r")
 
 
 def make_pair_indices(n: int, symmetric: bool = True):

@@ -126,7 +126,7 @@ def test_split_identical_and_resolves_rarely_on_smooth_fields(cuda_device):
 
 
 # ---- queue variant of the blend backward (st3r_gs_set_raster_variant, gs.RASTER_BWD_VARIANT) -------------------
-@pytest.fixture(params=[1, 2], ids=["queue", "fragment-pool"])
+@pytest.fixture(params=[1, 2, 3], ids=["queue", "fragment-pool", "pool-kernels"])
 def raster_queue(request, monkeypatch):
     from starst3r_b200 import gs
     monkeypatch.setattr(gs, "RASTER_BWD_VARIANT", request.param)
@@ -157,7 +157,7 @@ def test_raster_queue_equals_default_gradients(cuda_device, scale_mult):
     v_render = torch.randn(3, 136, 200, 3, generator=g).to(dev)
     v_alpha = torch.randn(3, 136, 200, 1, generator=g).to(dev)
     grads = {}
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         gs.RASTER_BWD_VARIANT = variant
         try:
             leaves = [a.clone().requires_grad_(True) for a in args]
@@ -167,7 +167,7 @@ def test_raster_queue_equals_default_gradients(cuda_device, scale_mult):
             grads[variant] = [x.grad.clone() for x in leaves]
         finally:
             gs.RASTER_BWD_VARIANT = 0
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         for a, b in zip(grads[0], grads[variant]):
             assert torch.isfinite(b).all()
             assert (a - b).abs().max().item() <= 2e-4 * max(a.abs().max().item(), 1e-12), variant

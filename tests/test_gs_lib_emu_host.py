@@ -16,7 +16,7 @@ def backend(emu_backend):
     return emu_backend
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["default-bwd", "queue-bwd", "fragment-pool-bwd"])
+@pytest.fixture(params=[0, 1, 2, 3], ids=["default-bwd", "queue-bwd", "fragment-pool-bwd", "pool-kernels"])
 def backend_bwd(request, emu_backend, monkeypatch):
     from starst3r_b200 import gs
     monkeypatch.setattr(gs, "RASTER_BWD_VARIANT", request.param)

@@ -118,9 +118,17 @@ def test_blend_kernels_on_the_simt_emulator(emu, n, C, W, H, ss, sl, seed):
     want_render, want_alphas, want_g = reference(A, B, col, offsets, n_isect, flatten, tw, th, C, W, H, v_render, v_alphas)
     assert np.abs(render - want_render).max() < 2e-5 and np.abs(alphas - want_alphas).max() < 2e-5
     assert int(n_blend[0]) > 5 * C * H * W
+    # the fragment-pool forward: same per-pixel arithmetic in the same order => identical outputs, bit for bit
+    render2, alphas2 = np.zeros_like(render), np.zeros_like(alphas)
+    last2, n_blend2 = np.zeros_like(last_ids), np.zeros(1, np.uint64)
+    rc = emu.emu_raster_fwd_pool(P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), C, W, H, P(render2), P(alphas2),
+                                 P(last2), P(n_blend2))
+    assert rc == 0, "deadlock in raster_fwd_pool_kernel"
+    assert np.array_equal(render, render2) and np.array_equal(alphas, alphas2) and np.array_equal(last_ids, last2)
+    assert n_blend[0] == n_blend2[0]
     scale = np.abs(want_g).max(0) + 1e-12
     got = {}
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         vA = np.zeros_like(A)
         vB = np.zeros_like(B)
         vC = np.zeros_like(col)
@@ -134,6 +142,7 @@ def test_blend_kernels_on_the_simt_emulator(emu, n, C, W, H, ss, sl, seed):
         assert np.all(vA[:, 3] == 0) and np.all(vB[:, 3] == 0) and np.all(vC[:, 3] == 0)
     assert (np.abs(got[0] - got[1]).max(0) / scale).max() < 1e-4
     assert (np.abs(got[0] - got[2]).max(0) / scale).max() < 1e-4
+    assert (np.abs(got[0] - got[3]).max(0) / scale).max() < 1e-4
     # path coverage of the queue kernel in this run (per-lane hits): dense bypass, mid-batch overflow drain, appends
     counts = (ctypes.c_long * 16)()
     emu.emu_counts(counts, 1)
@@ -141,6 +150,8 @@ def test_blend_kernels_on_the_simt_emulator(emu, n, C, W, H, ss, sl, seed):
     assert counts[6] > 0 and counts[7] > 0, list(counts)     # fragment-pool variant: dense visits and pool slots
     if per_tile.max() > 256:
         assert counts[1] > 0, list(counts)
+    # fragment-pool kernels: box pixels tested, contributions, and Gaussians deferred because the pool was full
+    assert counts[10] > 0 and counts[11] > 0 and counts[12] > 0, list(counts)
 
 
 def test_backward_variants_agree_on_edge_shapes(emu):
@@ -164,12 +175,18 @@ def test_backward_variants_agree_on_edge_shapes(emu):
         last_ids, n_blend = np.zeros((C, H, W), np.int32), np.zeros(1, np.uint64)
         assert emu.emu_raster_fwd(P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), C, W, H, P(render), P(alphas),
                                   P(last_ids), P(n_blend)) == 0
+        render2, alphas2 = np.zeros_like(render), np.zeros_like(alphas)
+        last2, n_blend2 = np.zeros_like(last_ids), np.zeros(1, np.uint64)
+        assert emu.emu_raster_fwd_pool(P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), C, W, H, P(render2),
+                                       P(alphas2), P(last2), P(n_blend2)) == 0
+        assert np.array_equal(render, render2) and np.array_equal(alphas, alphas2), (it, n, C, W, H)
+        assert np.array_equal(last_ids, last2) and n_blend[0] == n_blend2[0], (it, n, C, W, H)
         outs = []
-        for variant in (0, 1, 2):
+        for variant in (0, 1, 2, 3):
             vA, vB, vC = np.zeros_like(A), np.zeros_like(B), np.zeros_like(col)
             assert emu.emu_raster_bwd(variant, P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), C, W, H, P(alphas),
                                       P(last_ids), P(v_render), P(v_alphas), P(vA), P(vB), P(vC)) == 0, (it, variant)
             outs.append(np.concatenate([vA[:, :3], vB[:, :3], vC[:, :3]], axis=1))
         scale = np.abs(outs[0]).max(0) + 1e-12
-        for variant in (1, 2):
+        for variant in (1, 2, 3):
             assert (np.abs(outs[0] - outs[variant]).max(0) / scale).max() < 1e-4, (it, variant, n, C, W, H)
