@@ -39,7 +39,7 @@ def raster_leg(dev, out):
     flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
     for scale_mode in ("init", "rand"):      # 3e-3 initial scale / exp(N(-4, 0.5)) sweep of SURVEY 8d
         params, states, truth, cams = bench.make_workload(dev, 0, scale_mode=scale_mode)
-        for variant in (0, 1, 2, 3):
+        for variant in [int(v) for v in os.environ.get("ST3R_VARIANTS", "0,1,2,3").split(",")]:
             key = f"train_step_ms[{scale_mode}][raster_variant={variant}]"
             try:
                 gs.RASTER_BWD_VARIANT = variant

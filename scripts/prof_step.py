@@ -1,4 +1,5 @@
 """Few train steps + one extract_correspondences call (for ncu launch lists / kernel captures)."""
+import os
 import sys
 import torch
 sys.path.insert(0, "/root/repo")
@@ -9,7 +10,7 @@ what = sys.argv[1] if len(sys.argv) > 1 else "both"
 if what in ("both", "step"):
     params, states, truth, cams = bench.make_workload(dev, 0)
     plan = gs.TrainPlan(bench.N_GAUSS, bench.N_VIEWS, bench.W, bench.H, dev)
-    for i in range(3):
+    for i in range(int(os.environ.get("ST3R_PROF_STEPS", "3"))):
         loss, fr = gs.train_step(params, states, truth, cams, bench.W, bench.H, i + 1, plan=plan)
     torch.cuda.synchronize()
 if what in ("both", "match"):

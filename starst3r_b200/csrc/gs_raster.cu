@@ -38,6 +38,24 @@ __device__ __forceinline__ TileRange tile_range(const int32_t* __restrict__ offs
   return r;
 }
 
+// sigma = 0.5 (a dx^2 + c dy^2) + b dx dy in ONE fixed evaluation order for every blend kernel of this file (explicit
+// fused multiply-adds; the compiler's own contraction choices could differ between kernels and flip a borderline
+// alpha >= 1/255 test between the forward and the backward pass).
+__device__ __forceinline__ float blend_sigma(float a, float b, float c, float dx, float dy) {
+  return fmaf(b * dx, dy, 0.5f * fmaf(a * dx, dx, (c * dy) * dy));
+}
+
+// exp(-sigma) as one ex2.approx (the value __expf returns wherever alpha can pass the 1/255 test).
+__device__ __forceinline__ float exp_neg(float sigma) {
+#ifdef ST3R_HOST_EMU
+  return expf(-sigma);
+#else
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(sigma * -1.4426950408889634f));
+  return r;
+#endif
+}
+
 // Conservative set of tile rows (bit i = row i of the 16x16 tile) on which a Gaussian can pass the
 // alpha >= 1/255 test: opac * exp(-sigma) >= 1/255  <=>  d^T Q d <= 2 ln(255 opac), whose bounding box has the
 // vertical half-extent sqrt(2 L cov_yy), cov_yy = a / (a c - b^2).  A small margin keeps the cull strictly
@@ -114,8 +132,8 @@ raster_fwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
         if (done) continue;
         const float4 A = sA[t], B = sB[t];
         const float dx = A.x - px, dy = A.y - py;
-        const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
-        const float alpha = fminf(ALPHA_MAX, A.z * __expf(-sigma));
+        const float sigma = blend_sigma(B.x, B.y, B.z, dx, dy);
+        const float alpha = fminf(ALPHA_MAX, A.z * exp_neg(sigma));
         if (sigma < 0.f || alpha < ALPHA_MIN) continue;
         const float nT = T * (1.0f - alpha);
         if (nT <= T_MIN) { done = true; continue; }
@@ -231,8 +249,8 @@ raster_bwd_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict
         B = sB[t];
         opac = A.z;
         dx = A.x - px; dy = A.y - py;
-        const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
-        vis = __expf(-sigma);
+        const float sigma = blend_sigma(B.x, B.y, B.z, dx, dy);
+        vis = exp_neg(sigma);
         alpha = fminf(ALPHA_MAX, opac * vis);
         if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
       }
@@ -328,43 +346,59 @@ __device__ __forceinline__ void blend_grad_terms(const float4 A, const float4 B,
 // With the reference's 3e-3 initial scale a splat covers a handful of pixels, and the pixel-parallel walk above spends
 // its instructions on alpha tests that fail (forward: 4.5 % hit rate) and on warp reductions in which ~6 of 32 lanes
 // carry a value (ncu, round 1: both kernels issue-bound).  Here the work is split by what it is parallel in:
-//   A. Gaussian-parallel: the PTPG lanes that own a Gaussian of the batch walk its bounding box inside the tile
-//      (conservative extents of the alpha >= 1/255 ellipse, clipped to the tile and the image), evaluate alpha once per
-//      box pixel, store it in the Gaussian's run of a shared-memory pool (slots are handed out by a block-wide scan of
-//      the box areas, so small and tile-sized splats mix freely) and set the Gaussian's bit in the mask of every pixel
-//      that passes the test;
+//   0. stage: thread t loads Gaussian t of the batch (up to PG per batch), derives its bounding box inside the tile
+//      (conservative extents of the alpha >= 1/255 ellipse, clipped to the tile and the image) and gets a run of pool
+//      slots, one per box pixel, from a block-wide exclusive scan of the box areas (small and tile-sized splats mix
+//      freely; what does not fit into the pool is left to the next batch).  The same scan compacts the Gaussians that
+//      have a box at all;
+//   A. slot-parallel: the S slots of the batch are cut into 256 equal chunks.  A thread finds the Gaussian its chunk
+//      starts in by binary search over the run offsets and walks its chunk in ONE flat loop (moving on to the next
+//      Gaussian of the compacted list is a predicated block, so all lanes of all warps run the same trip count): alpha
+//      once per box pixel, stored in the slot, and the Gaussian's bit set in the mask of every pixel that passes
+//      the alpha test;
 //   B. pixel-parallel: every pixel walks the set bits of ITS OWN mask in depth order - no alpha test, no warp
 //      collective, only the recurrence that is sequential per pixel (transmittance, colour; backward: colour behind,
-//      dL/dalpha, results written back to the pool slot);
-//   C. (backward) Gaussian-parallel again: the lanes of a Gaussian turn its pool slots into the nine gradient sums in
-//      registers, two shuffles combine them, one vector atomic per (tile, Gaussian): no shared-memory atomics at all.
-// Results: same expressions in the same per-pixel order as the kernels above; the backward's per-Gaussian sums are
-// added in a different (fixed) order.
-#ifndef ST3R_POOL_FG
-#define ST3R_POOL_FG 64
+//      dL/dalpha, results written back to the slot);
+//   C. (backward) slot-parallel again, same chunks: a thread accumulates the moments of its slots in registers and
+//      issues one vector atomic triple per Gaussian run it touches: no shared-memory atomics, no warp reductions.
+// Results: same expressions in the same per-pixel order as the kernels above (the forward is bit-identical); the
+// backward's per-Gaussian sums are added in a different order.
+#ifndef ST3R_POOL_PG
+#define ST3R_POOL_PG 256
 #endif
-constexpr int PG = ST3R_POOL_FG;       // Gaussians per batch
-constexpr int PTPG = BLOCK / PG;       // lanes per Gaussian in the Gaussian-parallel phases
-constexpr int PGW = 32 / PTPG;         // Gaussians per warp
+#ifndef ST3R_POOL_SLOTS
+#define ST3R_POOL_SLOTS (ST3R_POOL_PG * 16)
+#endif
+constexpr int PG = ST3R_POOL_PG;       // Gaussians per batch (one per thread of the first PG threads)
 constexpr int PW = PG / 32;            // mask words per pixel
-constexpr int PSLOTS = PG * 32;        // pool slots per batch (a Gaussian takes at most 256)
-static_assert(PG == 64 || PG == 128, "pool batch: 64 or 128 Gaussians");
+constexpr int PSLOTS = ST3R_POOL_SLOTS;   // pool slots per batch (a Gaussian takes at most 256)
+static_assert(PG == 64 || PG == 128 || PG == 256, "pool batch: 64, 128 or 256 Gaussians");
+static_assert(PSLOTS >= 256 && PSLOTS < (1 << 20), "the pool must hold a tile-sized box");
 
-struct PoolBox { int origin; uint32_t geo; };   // pool slot of tile pixel (row, col) = origin + row * wc + col;
-// geo = r0 | c0 << 4 | (wc - 1) << 8 | (nr - 1) << 12 | area << 16; 0: the Gaussian takes no part in this batch
+struct PoolBox { int base; uint32_t geo; };   // first pool slot; geo = r0 | c0 << 4 | (wc - 1) << 8 | (nr - 1) << 12 |
+                                               // area << 16 (0: the Gaussian takes no part in this batch)
+__device__ __forceinline__ int box_r0(uint32_t geo) { return (int)(geo & 15u); }
+__device__ __forceinline__ int box_c0(uint32_t geo) { return (int)((geo >> 4) & 15u); }
+__device__ __forceinline__ int box_wc(uint32_t geo) { return (int)((geo >> 8) & 15u) + 1; }
+__device__ __forceinline__ int box_area(uint32_t geo) { return (int)(geo >> 16); }
 
 // Box of tile pixels (rows r0..r1, columns c0..c1, clipped to rmax / cmax) on which opac * exp(-sigma) >= 1/255 is
-// possible; see row_mask for the bound.  Returns the area (0: cannot contribute) and the packed geometry.
+// possible; see row_mask for the bound (here with fast intrinsics and a wider safety margin: the box only has to
+// contain the ellipse).  Returns the area (0: cannot contribute) and the packed geometry.
 __device__ __forceinline__ int pool_box(const float4 A, const float4 B, float px0, float py0, int rmax, int cmax,
                                         uint32_t& geo) {
   geo = 0;
-  const float L = logf(255.0f * A.z);
-  if (!(L > 0.f)) return 0;
+  if (!(A.z > ALPHA_MIN)) return 0;                      // opac * exp(-sigma) <= opac < 1/255 (also NaN)
   int r0 = 0, r1 = rmax, c0 = 0, c1 = cmax;
   const float det = B.x * B.z - B.y * B.y;
   if (det > 0.f) {
-    const float hy = sqrtf(2.0f * L * B.x / det) * 1.0005f + 2e-3f;
-    const float hx = sqrtf(2.0f * L * B.z / det) * 1.0005f + 2e-3f;
+#ifdef ST3R_HOST_EMU
+    const float L2 = 2.0f * logf(255.0f * A.z) / det;
+#else
+    const float L2 = __fdividef(2.0f * __logf(255.0f * A.z), det);
+#endif
+    const float hy = sqrtf(L2 * B.x) * 1.001f + 4e-3f;
+    const float hx = sqrtf(L2 * B.z) * 1.001f + 4e-3f;
     // (NaN / inf extents fall through fmaxf / fminf to the whole tile)
     r0 = max(0, (int)fmaxf(ceilf(A.y - hy - py0), -1.0f));
     r1 = min(rmax, (int)fminf(floorf(A.y + hy - py0), (float)TILE));
@@ -377,58 +411,133 @@ __device__ __forceinline__ int pool_box(const float4 A, const float4 B, float px
   return wc * nr;
 }
 
-// Stage one batch: the lanes of Gaussian slot t = (warp, lane / PTPG) load it (same address: one transaction), derive
-// its box and get its pool run from a block-wide exclusive scan of the areas.  `have`: the slot holds a Gaussian.
-// Gaussians whose run would not fit into the pool are left to the next batch (geo = 0); *taken (shared, per warp) gets
-// the number of Gaussians of this warp that were staged.  Contains the batch's first barrier; returns its
-// __syncthreads_count(done_pred).
-__device__ __forceinline__ int pool_stage(bool have, uint32_t e, const float4* __restrict__ geomA,
-                                          const float4* __restrict__ geomB, const float4* __restrict__ rgb, float px0,
-                                          float py0, int rmax, int cmax, int done_pred, float4* sC, PoolBox* sBox,
-                                          uint32_t (*sMask)[BLOCK], int* sScan, int* sTake, float4& A, float4& B,
-                                          uint32_t& geo, int& base) {
+struct PoolBatch { int n, S, n_done; };   // Gaussians staged, pool slots handed out, barrier count of the caller's flag
+
+// Shared state of one batch (the kernels declare the arrays; the emulator needs function-local statics).
+struct PoolShared {
+  float4 *sA, *sB, *sC;
+  PoolBox* sBox;              // [BLOCK] by batch slot
+  uint8_t* sComp;             // [BLOCK] batch slots that have a box, in depth order
+  int* sCBase;                // [BLOCK] first pool slot of sComp[i] (ascending); INT_MAX behind the last one
+  uint32_t (*sMask)[BLOCK];   // [PW][BLOCK] bit t of word w of pixel p: Gaussian 32 w + t contributes to p
+  int* sScan;                 // [BLOCK / 32]
+  int* sTake;                 // [2 * BLOCK / 32]
+};
+
+// Stage one batch (two barriers).  `have`: this thread's slot holds Gaussian e.
+__device__ __forceinline__ PoolBatch pool_stage(bool have, uint32_t e, const float4* __restrict__ geomA,
+                                                const float4* __restrict__ geomB, const float4* __restrict__ rgb,
+                                                float px0, float py0, int rmax, int cmax, int done_pred,
+                                                const PoolShared& sh) {
+  const unsigned full = 0xffffffffu;
   const int tr = threadIdx.x, lane = tr & 31, wrp = tr >> 5;
-  const int t = wrp * PGW + lane / PTPG;
-  const bool lead = (lane % PTPG) == 0;
-  A = make_float4(0.f, 0.f, 0.f, 0.f);
-  B = A;
   int area = 0;
-  geo = 0;
+  uint32_t geo = 0;
   if (have) {
-    A = geomA[e];
-    B = geomB[e];
-    if (lead) sC[t] = rgb[e];
+    const float4 A = geomA[e], B = geomB[e];
+    sh.sA[tr] = A;
+    sh.sB[tr] = B;
+    sh.sC[tr] = rgb[e];
     area = pool_box(A, B, px0, py0, rmax, cmax, geo);
   }
-  // inclusive scan over the warp of the leaders' areas: every lane of a group ends up with its own Gaussian's total
-  int incl = lead ? area : 0;
+  // one scan for both prefixes: slots in the low 20 bits, Gaussians with a box above
+  const int mine = area | (area ? 1 << 20 : 0);
+  int incl = mine;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
-    const int v = (int)__shfl_up_sync(0xffffffffu, (unsigned)incl, off);
+    const int v = (int)__shfl_up_sync(full, (unsigned)incl, off);
     if (lane >= off) incl += v;
   }
-  if (lane == 31) sScan[wrp] = incl;
+  if (lane == 31) sh.sScan[wrp] = incl;
+  sh.sCBase[tr] = 0x7fffffff;
 #pragma unroll
-  for (int w = 0; w < PW; ++w) sMask[w][tr] = 0u;
-  const int n_done = __syncthreads_count(done_pred);
+  for (int w = 0; w < PW; ++w) sh.sMask[w][tr] = 0u;
+  PoolBatch pb;
+  pb.n_done = __syncthreads_count(done_pred);
   int before = 0;
 #pragma unroll
-  for (int k = 0; k < BLOCK / 32 - 1; ++k) before += (k < wrp) ? sScan[k] : 0;
-  base = before + incl - area;
+  for (int k = 0; k < BLOCK / 32 - 1; ++k) before += (k < wrp) ? sh.sScan[k] : 0;
+  const int excl = before + incl - mine;
+  const int base = excl & 0xfffff, ci = excl >> 20;
   const bool fits = have && base + area <= PSLOTS;       // monotone along t: a prefix of the batch is staged
-  if (!fits) geo = 0;
-  if (have && !fits && lead) ST3R_EMU_COUNT(12);             // Gaussians left to the next batch (pool full)
-  const uint32_t staged = __ballot_sync(0xffffffffu, lead && fits);
-  if (lane == 0) sTake[wrp] = __popc(staged);
-  if (lead) {
-    PoolBox bx;
-    const int wc = (int)((geo >> 8) & 15u) + 1;
-    bx.origin = base - (int)(geo & 15u) * wc - (int)((geo >> 4) & 15u);
-    bx.geo = geo;
-    sBox[t] = bx;
+  if (have && !fits) ST3R_EMU_COUNT(12);                  // Gaussians left to the next batch (pool full)
+  if (!fits) { geo = 0; area = 0; }
+  const uint32_t staged = __ballot_sync(full, fits);
+  const int top = __reduce_max_sync(full, fits ? base + area : 0);
+  if (lane == 0) {
+    sh.sTake[wrp] = __popc(staged);
+    sh.sTake[BLOCK / 32 + wrp] = top;
   }
-  return n_done;
+  PoolBox bx;
+  bx.base = base;
+  bx.geo = geo;
+  sh.sBox[tr] = bx;
+  if (area) {
+    sh.sComp[ci] = (uint8_t)tr;
+    sh.sCBase[ci] = base;
+  }
+  __syncthreads();
+  pb.n = 0;
+  pb.S = 0;
+#pragma unroll
+  for (int k = 0; k < BLOCK / 32; ++k) {
+    pb.n += sh.sTake[k];
+    pb.S = max(pb.S, sh.sTake[BLOCK / 32 + k]);
+  }
+  return pb;
 }
+
+// Candidates of the next batch: all PG while whole batches fit into the pool, else about twice what the pool took.
+__device__ __forceinline__ int pool_next_cand(int cand, int taken) {
+  return taken == cand ? min(PG, 2 * cand) : max(32, min(PG, 2 * taken));
+}
+
+// The chunk [s, s_end) of pool slots of this thread and the compacted index of the Gaussian its first slot is in.
+__device__ __forceinline__ bool pool_chunk(int S, const int* sCBase, int& s, int& s_end, int& ci) {
+  const int q = ((S + BLOCK - 1) / BLOCK) | 1;           // odd: the lanes of a warp write their slots to distinct banks
+  s = (int)threadIdx.x * q;
+  s_end = min(S, s + q);
+  if (s >= s_end) return false;
+  ci = 0;                                                 // largest ci with sCBase[ci] <= s (sCBase[0] = 0)
+#pragma unroll
+  for (int step = BLOCK / 2; step; step >>= 1)
+    if (sCBase[ci + step] <= s) ci += step;               // (index <= BLOCK - 1)
+  return true;
+}
+
+// Walk state of one thread inside the box of the Gaussian it is currently in.
+struct PoolWalk {
+  float4 A, B;
+  float pxc0, pxc, pyr;      // pixel-centre coordinates of the box's first column, the current column, the current row
+  int t, cc, wc, run_end, pix;   // batch slot, column inside the box, box width, first slot behind the box, tile pixel
+  // Enter the Gaussian sComp[ci] at its slot `s` (>= its first slot).
+  __device__ __forceinline__ void enter(const PoolShared& sh, int ci, int s, float px0, float py0) {
+    t = sh.sComp[ci];
+    const PoolBox bx = sh.sBox[t];
+    A = sh.sA[t];
+    B = sh.sB[t];
+    wc = box_wc(bx.geo);
+    run_end = bx.base + box_area(bx.geo);
+    const int o = s - bx.base;
+    int rr = 0;
+    cc = o;
+    if (o) {                                              // only a chunk's first Gaussian is entered mid-box
+      rr = (int)(((float)o + 0.5f) / (float)wc);          // o / wc (o < 256, wc <= 16: far from the rounding edge)
+      cc = o - rr * wc;
+    }
+    const int r0 = box_r0(bx.geo), c0 = box_c0(bx.geo);
+    pxc0 = px0 + (float)c0;
+    pxc = px0 + (float)(c0 + cc);
+    pyr = py0 + (float)(r0 + rr);
+    pix = (r0 + rr) * TILE + c0 + cc;
+  }
+  // Next slot of the same box.
+  __device__ __forceinline__ void step() {
+    pxc += 1.0f;
+    ++pix;
+    if (++cc == wc) { cc = 0; pxc = pxc0; pyr += 1.0f; pix += TILE - wc; }
+  }
+};
 
 __global__ void __launch_bounds__(BLOCK)
 raster_fwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
@@ -436,83 +545,90 @@ raster_fwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
                        const float4* __restrict__ geomB, const float4* __restrict__ rgb, int C, int W, int H, int tile_w,
                        int tile_h, float* __restrict__ render, float* __restrict__ alphas,
                        int32_t* __restrict__ last_ids, unsigned long long* __restrict__ n_blend) {
-  __shared__ float4 sC[PG];
-  __shared__ PoolBox sBox[PG];
+  __shared__ float4 sA[BLOCK], sB[BLOCK], sC[BLOCK];
+  __shared__ PoolBox sBox[BLOCK];
+  __shared__ uint8_t sComp[BLOCK];
+  __shared__ int sCBase[BLOCK];
   __shared__ uint32_t sMask[PW][BLOCK];
   __shared__ float sPool[PSLOTS];
-  __shared__ int sScan[BLOCK / 32], sTake[BLOCK / 32];
+  __shared__ int sScan[BLOCK / 32], sTake[2 * BLOCK / 32];
+  const PoolShared sh = {sA, sB, sC, sBox, sComp, sCBase, sMask, sScan, sTake};
   const int c = blockIdx.y, tile = blockIdx.x;
   const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
-  const int tr = threadIdx.x, lane = tr & 31, wrp = tr >> 5;
+  const int tr = threadIdx.x, lane = tr & 31;
   const int myrow = tr >> 4, mycol = tr & 15;
   const int i = tyi * TILE + myrow, j = txi * TILE + mycol;
   const bool inside = i < H && j < W;
   const float px0 = (float)(txi * TILE) + 0.5f, py0 = (float)(tyi * TILE) + 0.5f;   // centre of the tile's first pixel
   const int rmax = min(TILE, H - tyi * TILE) - 1, cmax = min(TILE, W - txi * TILE) - 1;
-  const int gq = lane % PTPG, t_own = wrp * PGW + lane / PTPG;
   bool done = !inside;
   const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
-  float T = 1.0f, pr = 0.f, pg = 0.f, pb = 0.f;
+  float T = 1.0f, pr = 0.f, pg = 0.f, pb_ = 0.f;
   int cur = 0, blends = 0;
-  int pos = rg.lo;
+  int pos = rg.lo, cand = PG;
   while (pos < rg.hi) {
-    const int idx = pos + t_own;
-    const bool have = idx < rg.hi;
+    const int idx = pos + tr;
+    const bool have = tr < cand && idx < rg.hi;
     const uint32_t e = have ? flatten[idx] : 0u;
-    float4 A, B;
-    uint32_t geo;
-    int base;
-    const int n_done = pool_stage(have, e, geomA, geomB, rgb, px0, py0, rmax, cmax, done, sC, sBox, sMask, sScan, sTake,
-                                  A, B, geo, base);
-    if (n_done == BLOCK) break;
+    const PoolBatch pb = pool_stage(have, e, geomA, geomB, rgb, px0, py0, rmax, cmax, done, sh);
+    if (pb.n_done == BLOCK) break;
     // ---- phase A: alpha of every box pixel, contribution bits
-    if (geo) {
-      const int wc = (int)((geo >> 8) & 15u) + 1, area = (int)(geo >> 16);
-      const int r0 = (int)(geo & 15u), c0 = (int)((geo >> 4) & 15u);
-      const float rwc = 1.0f / (float)wc;
-      const uint32_t bit = 1u << (t_own & 31);
-      for (int s = gq; s < area; s += PTPG) {
-        const int rr = (int)(((float)s + 0.5f) * rwc);          // s / wc (s < 256, wc <= 16: far from the rounding edge)
-        const int r = r0 + rr, cc = c0 + s - rr * wc;
-        const float dx = A.x - (px0 + (float)cc), dy = A.y - (py0 + (float)r);
-        const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
-        const float alpha = fminf(ALPHA_MAX, A.z * __expf(-sigma));
-        ST3R_EMU_COUNT(10);                                     // box pixels tested
-        if (!(sigma < 0.f || alpha < ALPHA_MIN)) {
-          sPool[base + s] = alpha;
-          atomicOr(&sMask[t_own >> 5][r * TILE + cc], bit);
+    {
+      int s, s_end, ci;
+      if (pool_chunk(pb.S, sCBase, s, s_end, ci)) {
+        PoolWalk wk;
+        wk.enter(sh, ci, s, px0, py0);
+        for (;;) {
+          const float dx = wk.A.x - wk.pxc, dy = wk.A.y - wk.pyr;
+          const float sigma = blend_sigma(wk.B.x, wk.B.y, wk.B.z, dx, dy);
+          const float alpha = fminf(ALPHA_MAX, wk.A.z * exp_neg(sigma));
+          ST3R_EMU_COUNT(10);                               // box pixels tested
+          if (!(sigma < 0.f || alpha < ALPHA_MIN)) {
+            sPool[s] = alpha;
+            atomicOr(&sMask[wk.t >> 5][wk.pix], 1u << (wk.t & 31));
+          }
+          if (++s == s_end) break;
+          if (s == wk.run_end) wk.enter(sh, ++ci, s, px0, py0);
+          else wk.step();
         }
       }
     }
     __syncthreads();
     // ---- phase B: the pixel's own contributing Gaussians, front to back
+    if (!done) {
+      uint32_t occ = 0;                       // words of this pixel's mask that hold a bit
 #pragma unroll
-    for (int w = 0; w < PW; ++w) {
-      uint32_t bits = sMask[w][tr];
-      while (bits && !done) {
+      for (int w = 0; w < PW; ++w) occ |= (sMask[w][tr] != 0u ? 1u : 0u) << w;
+      uint32_t bits = 0;
+      int w = 0;
+      for (;;) {
+        if (bits == 0u) {
+          if (occ == 0u) break;
+          w = __ffs(occ) - 1;
+          occ &= occ - 1;
+          bits = sMask[w][tr];
+        }
         const int t = w * 32 + __ffs(bits) - 1;
         bits &= bits - 1;
         const PoolBox bx = sBox[t];
-        const float alpha = sPool[bx.origin + myrow * ((int)((bx.geo >> 8) & 15u) + 1) + mycol];
+        const float alpha = sPool[bx.base + (myrow - box_r0(bx.geo)) * box_wc(bx.geo) + mycol - box_c0(bx.geo)];
         const float nT = T * (1.0f - alpha);
         if (nT <= T_MIN) { done = true; break; }
         const float wgt = alpha * T;
         const float4 col = sC[t];
-        pr += col.x * wgt; pg += col.y * wgt; pb += col.z * wgt;
+        pr += col.x * wgt; pg += col.y * wgt; pb_ += col.z * wgt;
         cur = pos + t;
         T = nT;
         ++blends;
       }
     }
-    __syncthreads();
-    int take = 0;
-#pragma unroll
-    for (int k = 0; k < BLOCK / 32; ++k) take += sTake[k];
-    pos += take;
+    pos += pb.n;
+    cand = pool_next_cand(cand, pb.n);
+    __syncthreads();          // the next stage overwrites sA / sB / sC / sBox before its first barrier
   }
   if (inside) {
     const size_t p = ((size_t)c * H + i) * W + j;
-    render[3 * p] = pr; render[3 * p + 1] = pg; render[3 * p + 2] = pb;
+    render[3 * p] = pr; render[3 * p + 1] = pg; render[3 * p + 2] = pb_;
     alphas[p] = 1.0f - T;
     last_ids[p] = cur;
   }
@@ -522,6 +638,22 @@ raster_fwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
   }
 }
 
+// One run of a Gaussian's slots summed by one thread -> gradient contribution.  m: sum u, u dx, u dy, u dx^2, u dx dy,
+// u dy^2 (u = vis dL/dalpha) and sum alpha T v_rgb.  With v_sigma = -opac u:  d/dxy = v_sigma Q d,
+// d/dconic = v_sigma (dx^2 / 2, dx dy, dy^2 / 2),  d/dopac = u.
+__device__ __forceinline__ void pool_emit(float* m, const float4 A, const float4 B, uint32_t e, float4* v_geomA,
+                                          float4* v_geomB, float4* v_rgb) {
+  if (m[0] != 0.f || m[1] != 0.f || m[2] != 0.f || m[3] != 0.f || m[4] != 0.f || m[5] != 0.f || m[6] != 0.f ||
+      m[7] != 0.f || m[8] != 0.f) {
+    const float no = -A.z;
+    atomicAdd(v_geomA + e, make_float4(no * (B.x * m[1] + B.y * m[2]), no * (B.y * m[1] + B.z * m[2]), m[0], 0.f));
+    atomicAdd(v_geomB + e, make_float4(0.5f * no * m[3], no * m[4], 0.5f * no * m[5], 0.f));
+    atomicAdd(v_rgb + e, make_float4(m[6], m[7], m[8], 0.f));
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) m[k] = 0.f;
+}
+
 __global__ void __launch_bounds__(BLOCK)
 raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
                        const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
@@ -529,12 +661,23 @@ raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
                        int tile_h, const float* __restrict__ alphas, const int32_t* __restrict__ last_ids,
                        const float* __restrict__ v_render, const float* __restrict__ v_alphas,
                        float4* __restrict__ v_geomA, float4* __restrict__ v_geomB, float4* __restrict__ v_rgb) {
-  __shared__ float4 sC[PG];
-  __shared__ PoolBox sBox[PG];
+  __shared__ float4 sA[BLOCK], sB[BLOCK], sC[BLOCK];
+  __shared__ uint32_t sE[BLOCK];
+  __shared__ PoolBox sBox[BLOCK];
+  __shared__ uint8_t sComp[BLOCK];
+  __shared__ int sCBase[BLOCK];
   __shared__ uint32_t sMask[PW][BLOCK];
-  __shared__ float2 sPool[PSLOTS];           // phase A: (alpha, vis or 0 when alpha was clamped); phase B: (alpha T, vis dL/dalpha)
+  // phase A: alpha / vis (0 when alpha was clamped); phase B: alpha T / vis dL/dalpha
+#ifdef ST3R_HOST_EMU
+  __shared__ float sPoolA[PSLOTS], sPoolV[PSLOTS];
+#else
+  extern __shared__ float pool_dyn[];        // 2 * PSLOTS floats (beyond the 48 KB of static shared memory)
+  float* const sPoolA = pool_dyn;
+  float* const sPoolV = pool_dyn + PSLOTS;
+#endif
   __shared__ float4 sV[BLOCK];               // upstream colour gradient of every pixel of the tile
-  __shared__ int sScan[BLOCK / 32], sTake[BLOCK / 32];
+  __shared__ int sScan[BLOCK / 32], sTake[2 * BLOCK / 32];
+  const PoolShared sh = {sA, sB, sC, sBox, sComp, sCBase, sMask, sScan, sTake};
   const int c = blockIdx.y, tile = blockIdx.x;
   const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
   const int tr = threadIdx.x, lane = tr & 31, wrp = tr >> 5;
@@ -543,7 +686,6 @@ raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
   const bool inside = i < H && j < W;
   const float px0 = (float)(txi * TILE) + 0.5f, py0 = (float)(tyi * TILE) + 0.5f;
   const int rmax = min(TILE, H - tyi * TILE) - 1, cmax = min(TILE, W - txi * TILE) - 1;
-  const int gq = lane % PTPG, t_own = wrp * PGW + lane / PTPG;
   const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
   if (rg.hi <= rg.lo) return;
   const size_t p = ((size_t)c * H + min(i, H - 1)) * W + min(j, W - 1);
@@ -566,100 +708,106 @@ raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
   for (int k = 0; k < BLOCK / 32; ++k) tile_last = max(tile_last, sScan[k]);
   __syncthreads();                           // sScan is reused by the first pool_stage
   int hi = min(rg.hi - 1, tile_last);        // slot t of a batch holds sorted position hi - t: ascending t = back to front
+  int cand = PG;
   while (hi >= rg.lo) {
-    const int idx = hi - t_own;
-    const bool have = idx >= rg.lo;
+    const int idx = hi - tr;
+    const bool have = tr < cand && idx >= rg.lo;
     const uint32_t e = have ? flatten[idx] : 0u;
-    float4 A, B;
-    uint32_t geo;
-    int base;
-    pool_stage(have, e, geomA, geomB, rgb, px0, py0, rmax, cmax, 0, sC, sBox, sMask, sScan, sTake, A, B, geo, base);
-    const int wc = (int)((geo >> 8) & 15u) + 1, area = (int)(geo >> 16);
-    const int r0 = (int)(geo & 15u), c0 = (int)((geo >> 4) & 15u);
-    const float rwc = 1.0f / (float)wc;
+    sE[tr] = e;
+    const PoolBatch pb = pool_stage(have, e, geomA, geomB, rgb, px0, py0, rmax, cmax, 0, sh);
+    int s0, s_end, ci0;
+    const bool work = pool_chunk(pb.S, sCBase, s0, s_end, ci0);
     // ---- phase A
-    if (geo) {
-      const uint32_t bit = 1u << (t_own & 31);
-      for (int s = gq; s < area; s += PTPG) {
-        const int rr = (int)(((float)s + 0.5f) * rwc);
-        const int r = r0 + rr, cc = c0 + s - rr * wc;
-        const float dx = A.x - (px0 + (float)cc), dy = A.y - (py0 + (float)r);
-        const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
-        const float vis = __expf(-sigma);
-        const float alpha = fminf(ALPHA_MAX, A.z * vis);
-        float2 av = make_float2(0.f, 0.f);
+    if (work) {
+      int s = s0, ci = ci0;
+      PoolWalk wk;
+      wk.enter(sh, ci, s, px0, py0);
+      for (;;) {
+        const float dx = wk.A.x - wk.pxc, dy = wk.A.y - wk.pyr;
+        const float sigma = blend_sigma(wk.B.x, wk.B.y, wk.B.z, dx, dy);
+        const float vis = exp_neg(sigma);
+        const float alpha = fminf(ALPHA_MAX, wk.A.z * vis);
+        float pa = 0.f, pv = 0.f;             // non-contributing slots read as "nothing" in phase C
         if (!(sigma < 0.f || alpha < ALPHA_MIN)) {
-          av = make_float2(alpha, (A.z * vis <= ALPHA_MAX) ? vis : 0.f);
-          atomicOr(&sMask[t_own >> 5][r * TILE + cc], bit);
+          pa = alpha;
+          pv = (wk.A.z * vis <= ALPHA_MAX) ? vis : 0.f;
+          atomicOr(&sMask[wk.t >> 5][wk.pix], 1u << (wk.t & 31));
         }
-        sPool[base + s] = av;                 // non-contributing slots read as "nothing" in phase C
+        sPoolA[s] = pa;
+        sPoolV[s] = pv;
+        if (++s == s_end) break;
+        if (s == wk.run_end) wk.enter(sh, ++ci, s, px0, py0);
+        else wk.step();
       }
     }
     __syncthreads();
     // ---- phase B: per-pixel recurrence over the pixel's own contributing Gaussians, back to front
+    {
+      uint32_t occ = 0;
 #pragma unroll
-    for (int w = 0; w < PW; ++w) {
-      uint32_t bits = sMask[w][tr];
-      while (bits) {
+      for (int w = 0; w < PW; ++w) occ |= (sMask[w][tr] != 0u ? 1u : 0u) << w;
+      uint32_t bits = 0;
+      int w = 0;
+      for (;;) {
+        if (bits == 0u) {
+          if (occ == 0u) break;
+          w = __ffs(occ) - 1;
+          occ &= occ - 1;
+          bits = sMask[w][tr];
+        }
         const int t = w * 32 + __ffs(bits) - 1;
         bits &= bits - 1;
         const PoolBox bx = sBox[t];
-        const int slot = bx.origin + myrow * ((int)((bx.geo >> 8) & 15u) + 1) + mycol;
-        float2 out = make_float2(0.f, 0.f);   // a Gaussian behind this pixel's last blended one contributes nothing
+        const int slot = bx.base + (myrow - box_r0(bx.geo)) * box_wc(bx.geo) + mycol - box_c0(bx.geo);
+        float fac = 0.f, u = 0.f;             // a Gaussian behind this pixel's last blended one contributes nothing
         if (hi - t <= bin_final) {
-          const float2 av = sPool[slot];
-          const float ra = fast_rcp(1.0f - av.x);
+          const float alpha = sPoolA[slot];
+          const float ra = fast_rcp(1.0f - alpha);
           T *= ra;
-          const float fac = av.x * T;
+          fac = alpha * T;
           const float4 col = sC[t];
           const float cv = col.x * vr + col.y * vg + col.z * vb;
           const float v_alpha = T * cv + ra * (tf_va - behind_v);
           behind_v += fac * cv;
-          out = make_float2(fac, av.y * v_alpha);
+          u = sPoolV[slot] * v_alpha;
           ST3R_EMU_COUNT(11);                 // contributing (pixel, Gaussian) pairs
         }
-        sPool[slot] = out;
+        sPoolA[slot] = fac;
+        sPoolV[slot] = u;
       }
     }
     __syncthreads();
-    // ---- phase C: the lanes of a Gaussian turn its slots into the nine sums
-    {
-      float g9[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) g9[k] = 0.f;
-      if (geo) {
-        for (int s = gq; s < area; s += PTPG) {
-          const float2 fw = sPool[base + s];
-          if (fw.x == 0.f && fw.y == 0.f) continue;
-          const int rr = (int)(((float)s + 0.5f) * rwc);
-          const int r = r0 + rr, cc = c0 + s - rr * wc;
-          const float4 v = sV[r * TILE + cc];
-          float g[9];
-          blend_grad_terms(A, B, A.x - (px0 + (float)cc), A.y - (py0 + (float)r), fw.x, fw.y, v.x, v.y, v.z, g);
-#pragma unroll
-          for (int k = 0; k < 9; ++k) g9[k] += g[k];
+    // ---- phase C: the chunk's slots summed per Gaussian run
+    if (work) {
+      int s = s0, ci = ci0;
+      PoolWalk wk;
+      wk.enter(sh, ci, s, px0, py0);
+      float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (;;) {
+        const float fac = sPoolA[s], u = sPoolV[s];
+        if (fac != 0.f || u != 0.f) {
+          const float dx = wk.A.x - wk.pxc, dy = wk.A.y - wk.pyr;
+          const float4 v = sV[wk.pix];
+          const float ux = u * dx, uy = u * dy;
+          m[0] += u; m[1] += ux; m[2] += uy;
+          m[3] += ux * dx; m[4] += ux * dy; m[5] += uy * dy;
+          m[6] += fac * v.x; m[7] += fac * v.y; m[8] += fac * v.z;
+        }
+        ++s;
+        if (s == s_end || s == wk.run_end) {
+          pool_emit(m, wk.A, wk.B, sE[wk.t], v_geomA, v_geomB, v_rgb);
+          if (s == s_end) break;
+          wk.enter(sh, ++ci, s, px0, py0);
+        } else {
+          wk.step();
         }
       }
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {             // the lanes of a Gaussian are adjacent
-#pragma unroll
-        for (int off = 1; off < PTPG; off <<= 1) g9[k] += __shfl_xor_sync(0xffffffffu, g9[k], off);
-      }
-      if (gq == 0 && geo &&
-          (g9[0] != 0.f || g9[1] != 0.f || g9[2] != 0.f || g9[3] != 0.f || g9[4] != 0.f || g9[5] != 0.f ||
-           g9[6] != 0.f || g9[7] != 0.f || g9[8] != 0.f)) {
-        atomicAdd(v_geomA + e, make_float4(g9[0], g9[1], g9[2], 0.f));
-        atomicAdd(v_geomB + e, make_float4(g9[3], g9[4], g9[5], 0.f));
-        atomicAdd(v_rgb + e, make_float4(g9[6], g9[7], g9[8], 0.f));
-      }
     }
-    int take = 0;
-#pragma unroll
-    for (int k = 0; k < BLOCK / 32; ++k) take += sTake[k];
-    hi -= take;
+    hi -= pb.n;
+    cand = pool_next_cand(cand, pb.n);
+    __syncthreads();                         // the next stage overwrites sA / sB / sC / sE / sBox before its first barrier
   }
 }
-
 
 // ---- variant 1 of the backward: per-warp record queues ----------------------------------------------------------
 // With the reference's 3e-3 initial scale a Gaussian covers ~12 pixels, so a (warp, Gaussian) visit of the kernel
@@ -1197,12 +1345,18 @@ int st3r_gs_raster_bwd(const int32_t* offsets, const int32_t* n_isect, const uin
                  "st3r_gs_raster_bwd: null pointer");
   const int tile_w = (width + TILE - 1) / TILE, tile_h = (height + TILE - 1) / TILE;
   dim3 grid(tile_w * tile_h, C);
-  if (g_raster_bwd_variant == 3)
-    raster_bwd_pool_kernel<<<grid, BLOCK, 0, stream>>>(
+  if (g_raster_bwd_variant == 3) {
+    static PerDeviceOnce once;
+    if (!once.done()) {
+      ST3R_CHECK_CUDA(cudaFuncSetAttribute(raster_bwd_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           2 * PSLOTS * (int)sizeof(float)));
+      once.mark();
+    }
+    raster_bwd_pool_kernel<<<grid, BLOCK, 2 * PSLOTS * sizeof(float), stream>>>(
         offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
         reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, alphas, last_ids, v_render, v_alphas,
         reinterpret_cast<float4*>(v_geomA), reinterpret_cast<float4*>(v_geomB), reinterpret_cast<float4*>(v_rgb));
-  else if (g_raster_bwd_variant == 2)
+  } else if (g_raster_bwd_variant == 2)
     raster_bwd_frag_kernel<<<grid, BLOCK, 0, stream>>>(
         offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
         reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, alphas, last_ids, v_render, v_alphas,

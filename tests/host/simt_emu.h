@@ -330,6 +330,7 @@ static inline int __reduce_max_sync(unsigned, int v) {
 
 static inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 #define __expf(x) expf(x)   // glibc declares __expf itself
 template <typename T> static inline T min(T a, T b) { return a < b ? a : b; }
 template <typename T> static inline T max(T a, T b) { return a > b ? a : b; }
