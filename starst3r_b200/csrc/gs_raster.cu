@@ -375,16 +375,9 @@ constexpr int PSLOTS = ST3R_POOL_SLOTS;   // pool slots per batch (a Gaussian ta
 static_assert(PG == 64 || PG == 128 || PG == 256, "pool batch: 64, 128 or 256 Gaussians");
 static_assert(PSLOTS >= 256 && PSLOTS < (1 << 20), "the pool must hold a tile-sized box");
 
-struct PoolBox { int base; uint32_t geo; };   // first pool slot; geo = r0 | c0 << 4 | (wc - 1) << 8 | (nr - 1) << 12 |
-                                               // area << 16 (0: the Gaussian takes no part in this batch)
-__device__ __forceinline__ int box_r0(uint32_t geo) { return (int)(geo & 15u); }
-__device__ __forceinline__ int box_c0(uint32_t geo) { return (int)((geo >> 4) & 15u); }
-__device__ __forceinline__ int box_wc(uint32_t geo) { return (int)((geo >> 8) & 15u) + 1; }
-__device__ __forceinline__ int box_area(uint32_t geo) { return (int)(geo >> 16); }
-
 // Box of tile pixels (rows r0..r1, columns c0..c1, clipped to rmax / cmax) on which opac * exp(-sigma) >= 1/255 is
 // possible; see row_mask for the bound (here with fast intrinsics and a wider safety margin: the box only has to
-// contain the ellipse).  Returns the area (0: cannot contribute) and the packed geometry.
+// contain the ellipse).  Returns the area (0: cannot contribute); geo = r0 | c0 << 4 | (wc - 1) << 8.
 __device__ __forceinline__ int pool_box(const float4 A, const float4 B, float px0, float py0, int rmax, int cmax,
                                         uint32_t& geo) {
   geo = 0;
@@ -407,37 +400,45 @@ __device__ __forceinline__ int pool_box(const float4 A, const float4 B, float px
   }
   if (r1 < r0 || c1 < c0) return 0;
   const int wc = c1 - c0 + 1, nr = r1 - r0 + 1;
-  geo = (uint32_t)r0 | (uint32_t)c0 << 4 | (uint32_t)(wc - 1) << 8 | (uint32_t)(nr - 1) << 12 | (uint32_t)(wc * nr) << 16;
+  geo = (uint32_t)r0 | (uint32_t)c0 << 4 | (uint32_t)(wc - 1) << 8;
   return wc * nr;
 }
 
 struct PoolBatch { int n, S, n_done; };   // Gaussians staged, pool slots handed out, barrier count of the caller's flag
 
-// Shared state of one batch (the kernels declare the arrays; the emulator needs function-local statics).
-struct PoolShared {
-  float4 *sA, *sB, *sC;
-  PoolBox* sBox;              // [BLOCK] by batch slot
-  uint8_t* sComp;             // [BLOCK] batch slots that have a box, in depth order
-  int* sCBase;                // [BLOCK] first pool slot of sComp[i] (ascending); INT_MAX behind the last one
-  uint32_t (*sMask)[BLOCK];   // [PW][BLOCK] bit t of word w of pixel p: Gaussian 32 w + t contributes to p
-  int* sScan;                 // [BLOCK / 32]
-  int* sTake;                 // [2 * BLOCK / 32]
+// Shared memory of one CTA.  kBwd: two pool values per slot, the entry ids and the tile's upstream gradients.
+template <bool kBwd>
+struct PoolSmem {
+  // per Gaussian WITH a box, in depth order (compacted): the record a slot walk loads when it enters the box
+  float4 recA[BLOCK];         // x, y, opacity, pixel-centre x of the box's first column
+  float4 recB[BLOCK];         // conic a, b, c, pixel-centre y of the box's first row
+  int4 recC[BLOCK];           // first slot behind the box, tile pixel of its first slot, wc | t << 5 | area << 13, entry
+  int cbase[BLOCK];           // first pool slot (ascending); INT_MAX behind the last compacted Gaussian
+  // per batch slot t (depth order)
+  float4 col[BLOCK];          // colour
+  int2 boxB[BLOCK];           // pool slot of tile pixel (row, col) = x + row * y + col
+  uint32_t mask[PW][BLOCK];   // bit t of word w of pixel p: Gaussian 32 w + t contributes to p
+  int scan[BLOCK / 32], take[2 * BLOCK / 32];
+  float poolA[PSLOTS];        // forward: alpha.  Backward, phase A: alpha; phase B: alpha T
+  float poolV[kBwd ? PSLOTS : 1];    // backward, phase A: vis (0 when alpha was clamped); phase B: vis dL/dalpha
+  float4 v[kBwd ? BLOCK : 1];        // backward: upstream colour gradient of every pixel of the tile
 };
 
 // Stage one batch (two barriers).  `have`: this thread's slot holds Gaussian e.
+template <bool kBwd>
 __device__ __forceinline__ PoolBatch pool_stage(bool have, uint32_t e, const float4* __restrict__ geomA,
                                                 const float4* __restrict__ geomB, const float4* __restrict__ rgb,
                                                 float px0, float py0, int rmax, int cmax, int done_pred,
-                                                const PoolShared& sh) {
+                                                PoolSmem<kBwd>& sm) {
   const unsigned full = 0xffffffffu;
   const int tr = threadIdx.x, lane = tr & 31, wrp = tr >> 5;
   int area = 0;
   uint32_t geo = 0;
+  float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
   if (have) {
-    const float4 A = geomA[e], B = geomB[e];
-    sh.sA[tr] = A;
-    sh.sB[tr] = B;
-    sh.sC[tr] = rgb[e];
+    A = geomA[e];
+    B = geomB[e];
+    sm.col[tr] = rgb[e];
     area = pool_box(A, B, px0, py0, rmax, cmax, geo);
   }
   // one scan for both prefixes: slots in the low 20 bits, Gaussians with a box above
@@ -448,41 +449,41 @@ __device__ __forceinline__ PoolBatch pool_stage(bool have, uint32_t e, const flo
     const int v = (int)__shfl_up_sync(full, (unsigned)incl, off);
     if (lane >= off) incl += v;
   }
-  if (lane == 31) sh.sScan[wrp] = incl;
-  sh.sCBase[tr] = 0x7fffffff;
+  if (lane == 31) sm.scan[wrp] = incl;
+  sm.cbase[tr] = 0x7fffffff;
 #pragma unroll
-  for (int w = 0; w < PW; ++w) sh.sMask[w][tr] = 0u;
+  for (int w = 0; w < PW; ++w) sm.mask[w][tr] = 0u;
   PoolBatch pb;
   pb.n_done = __syncthreads_count(done_pred);
   int before = 0;
 #pragma unroll
-  for (int k = 0; k < BLOCK / 32 - 1; ++k) before += (k < wrp) ? sh.sScan[k] : 0;
+  for (int k = 0; k < BLOCK / 32 - 1; ++k) before += (k < wrp) ? sm.scan[k] : 0;
   const int excl = before + incl - mine;
   const int base = excl & 0xfffff, ci = excl >> 20;
   const bool fits = have && base + area <= PSLOTS;       // monotone along t: a prefix of the batch is staged
   if (have && !fits) ST3R_EMU_COUNT(12);                  // Gaussians left to the next batch (pool full)
-  if (!fits) { geo = 0; area = 0; }
+  if (!fits) area = 0;
   const uint32_t staged = __ballot_sync(full, fits);
   const int top = __reduce_max_sync(full, fits ? base + area : 0);
   if (lane == 0) {
-    sh.sTake[wrp] = __popc(staged);
-    sh.sTake[BLOCK / 32 + wrp] = top;
+    sm.take[wrp] = __popc(staged);
+    sm.take[BLOCK / 32 + wrp] = top;
   }
-  PoolBox bx;
-  bx.base = base;
-  bx.geo = geo;
-  sh.sBox[tr] = bx;
   if (area) {
-    sh.sComp[ci] = (uint8_t)tr;
-    sh.sCBase[ci] = base;
+    const int r0 = (int)(geo & 15u), c0 = (int)((geo >> 4) & 15u), wc = (int)((geo >> 8) & 15u) + 1;
+    sm.boxB[tr] = make_int2(base - r0 * wc - c0, wc);
+    sm.recA[ci] = make_float4(A.x, A.y, A.z, px0 + (float)c0);
+    sm.recB[ci] = make_float4(B.x, B.y, B.z, py0 + (float)r0);
+    sm.recC[ci] = make_int4(base + area, r0 * TILE + c0, wc | tr << 5 | area << 13, (int)e);
+    sm.cbase[ci] = base;
   }
   __syncthreads();
   pb.n = 0;
   pb.S = 0;
 #pragma unroll
   for (int k = 0; k < BLOCK / 32; ++k) {
-    pb.n += sh.sTake[k];
-    pb.S = max(pb.S, sh.sTake[BLOCK / 32 + k]);
+    pb.n += sm.take[k];
+    pb.S = max(pb.S, sm.take[BLOCK / 32 + k]);
   }
   return pb;
 }
@@ -493,43 +494,48 @@ __device__ __forceinline__ int pool_next_cand(int cand, int taken) {
 }
 
 // The chunk [s, s_end) of pool slots of this thread and the compacted index of the Gaussian its first slot is in.
-__device__ __forceinline__ bool pool_chunk(int S, const int* sCBase, int& s, int& s_end, int& ci) {
+__device__ __forceinline__ bool pool_chunk(int S, const int* cbase, int& s, int& s_end, int& ci) {
   const int q = ((S + BLOCK - 1) / BLOCK) | 1;           // odd: the lanes of a warp write their slots to distinct banks
   s = (int)threadIdx.x * q;
   s_end = min(S, s + q);
   if (s >= s_end) return false;
-  ci = 0;                                                 // largest ci with sCBase[ci] <= s (sCBase[0] = 0)
+  ci = 0;                                                 // largest ci with cbase[ci] <= s (cbase[0] = 0)
 #pragma unroll
   for (int step = BLOCK / 2; step; step >>= 1)
-    if (sCBase[ci + step] <= s) ci += step;               // (index <= BLOCK - 1)
+    if (cbase[ci + step] <= s) ci += step;                // (index <= BLOCK - 1)
   return true;
 }
 
 // Walk state of one thread inside the box of the Gaussian it is currently in.
 struct PoolWalk {
-  float4 A, B;
+  float x, y, opac, qa, qb, qc;
   float pxc0, pxc, pyr;      // pixel-centre coordinates of the box's first column, the current column, the current row
-  int t, cc, wc, run_end, pix;   // batch slot, column inside the box, box width, first slot behind the box, tile pixel
-  // Enter the Gaussian sComp[ci] at its slot `s` (>= its first slot).
-  __device__ __forceinline__ void enter(const PoolShared& sh, int ci, int s, float px0, float py0) {
-    t = sh.sComp[ci];
-    const PoolBox bx = sh.sBox[t];
-    A = sh.sA[t];
-    B = sh.sB[t];
-    wc = box_wc(bx.geo);
-    run_end = bx.base + box_area(bx.geo);
-    const int o = s - bx.base;
-    int rr = 0;
-    cc = o;
-    if (o) {                                              // only a chunk's first Gaussian is entered mid-box
-      rr = (int)(((float)o + 0.5f) / (float)wc);          // o / wc (o < 256, wc <= 16: far from the rounding edge)
-      cc = o - rr * wc;
+  int cc, wc, run_end, pix;  // column inside the box, box width, first slot behind the box, current tile pixel
+  int t, e;                  // batch slot (depth order), entry id
+  // Enter compacted Gaussian ci at slot s (s > its first slot only for the first Gaussian of a chunk).
+  template <bool kBwd>
+  __device__ __forceinline__ void enter(const PoolSmem<kBwd>& sm, int ci, int s, bool first) {
+    const float4 ra = sm.recA[ci], rb = sm.recB[ci];
+    const int4 rc = sm.recC[ci];
+    x = ra.x; y = ra.y; opac = ra.z; pxc0 = ra.w;
+    qa = rb.x; qb = rb.y; qc = rb.z; pyr = rb.w;
+    run_end = rc.x;
+    pix = rc.y;
+    wc = rc.z & 31;
+    t = (rc.z >> 5) & 255;
+    e = rc.w;
+    cc = 0;
+    pxc = pxc0;
+    if (first) {
+      const int o = s - (run_end - (rc.z >> 13));
+      if (o) {
+        const int rr = (int)(((float)o + 0.5f) / (float)wc);      // o / wc (o < 256, wc <= 16: far from the rounding edge)
+        cc = o - rr * wc;
+        pxc = pxc0 + (float)cc;
+        pyr += (float)rr;
+        pix += rr * TILE + cc;
+      }
     }
-    const int r0 = box_r0(bx.geo), c0 = box_c0(bx.geo);
-    pxc0 = px0 + (float)c0;
-    pxc = px0 + (float)(c0 + cc);
-    pyr = py0 + (float)(r0 + rr);
-    pix = (r0 + rr) * TILE + c0 + cc;
   }
   // Next slot of the same box.
   __device__ __forceinline__ void step() {
@@ -539,20 +545,21 @@ struct PoolWalk {
   }
 };
 
+#ifdef ST3R_HOST_EMU
+#define POOL_SMEM(kBwd) __shared__ PoolSmem<kBwd> sm
+#else
+#define POOL_SMEM(kBwd)                               \
+  extern __shared__ __align__(16) char pool_smem_raw[]; \
+  PoolSmem<kBwd>& sm = *reinterpret_cast<PoolSmem<kBwd>*>(pool_smem_raw)
+#endif
+
 __global__ void __launch_bounds__(BLOCK)
 raster_fwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
                        const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
                        const float4* __restrict__ geomB, const float4* __restrict__ rgb, int C, int W, int H, int tile_w,
                        int tile_h, float* __restrict__ render, float* __restrict__ alphas,
                        int32_t* __restrict__ last_ids, unsigned long long* __restrict__ n_blend) {
-  __shared__ float4 sA[BLOCK], sB[BLOCK], sC[BLOCK];
-  __shared__ PoolBox sBox[BLOCK];
-  __shared__ uint8_t sComp[BLOCK];
-  __shared__ int sCBase[BLOCK];
-  __shared__ uint32_t sMask[PW][BLOCK];
-  __shared__ float sPool[PSLOTS];
-  __shared__ int sScan[BLOCK / 32], sTake[2 * BLOCK / 32];
-  const PoolShared sh = {sA, sB, sC, sBox, sComp, sCBase, sMask, sScan, sTake};
+  POOL_SMEM(false);
   const int c = blockIdx.y, tile = blockIdx.x;
   const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
   const int tr = threadIdx.x, lane = tr & 31;
@@ -570,25 +577,25 @@ raster_fwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
     const int idx = pos + tr;
     const bool have = tr < cand && idx < rg.hi;
     const uint32_t e = have ? flatten[idx] : 0u;
-    const PoolBatch pb = pool_stage(have, e, geomA, geomB, rgb, px0, py0, rmax, cmax, done, sh);
+    const PoolBatch pb = pool_stage<false>(have, e, geomA, geomB, rgb, px0, py0, rmax, cmax, done, sm);
     if (pb.n_done == BLOCK) break;
     // ---- phase A: alpha of every box pixel, contribution bits
     {
       int s, s_end, ci;
-      if (pool_chunk(pb.S, sCBase, s, s_end, ci)) {
+      if (pool_chunk(pb.S, sm.cbase, s, s_end, ci)) {
         PoolWalk wk;
-        wk.enter(sh, ci, s, px0, py0);
+        wk.enter(sm, ci, s, true);
         for (;;) {
-          const float dx = wk.A.x - wk.pxc, dy = wk.A.y - wk.pyr;
-          const float sigma = blend_sigma(wk.B.x, wk.B.y, wk.B.z, dx, dy);
-          const float alpha = fminf(ALPHA_MAX, wk.A.z * exp_neg(sigma));
+          const float dx = wk.x - wk.pxc, dy = wk.y - wk.pyr;
+          const float sigma = blend_sigma(wk.qa, wk.qb, wk.qc, dx, dy);
+          const float alpha = fminf(ALPHA_MAX, wk.opac * exp_neg(sigma));
           ST3R_EMU_COUNT(10);                               // box pixels tested
           if (!(sigma < 0.f || alpha < ALPHA_MIN)) {
-            sPool[s] = alpha;
-            atomicOr(&sMask[wk.t >> 5][wk.pix], 1u << (wk.t & 31));
+            sm.poolA[s] = alpha;
+            atomicOr(&sm.mask[wk.t >> 5][wk.pix], 1u << (wk.t & 31));
           }
           if (++s == s_end) break;
-          if (s == wk.run_end) wk.enter(sh, ++ci, s, px0, py0);
+          if (s == wk.run_end) wk.enter(sm, ++ci, s, false);
           else wk.step();
         }
       }
@@ -598,7 +605,7 @@ raster_fwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
     if (!done) {
       uint32_t occ = 0;                       // words of this pixel's mask that hold a bit
 #pragma unroll
-      for (int w = 0; w < PW; ++w) occ |= (sMask[w][tr] != 0u ? 1u : 0u) << w;
+      for (int w = 0; w < PW; ++w) occ |= (sm.mask[w][tr] != 0u ? 1u : 0u) << w;
       uint32_t bits = 0;
       int w = 0;
       for (;;) {
@@ -606,16 +613,16 @@ raster_fwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
           if (occ == 0u) break;
           w = __ffs(occ) - 1;
           occ &= occ - 1;
-          bits = sMask[w][tr];
+          bits = sm.mask[w][tr];
         }
         const int t = w * 32 + __ffs(bits) - 1;
         bits &= bits - 1;
-        const PoolBox bx = sBox[t];
-        const float alpha = sPool[bx.base + (myrow - box_r0(bx.geo)) * box_wc(bx.geo) + mycol - box_c0(bx.geo)];
+        const int2 bx = sm.boxB[t];
+        const float alpha = sm.poolA[bx.x + myrow * bx.y + mycol];
         const float nT = T * (1.0f - alpha);
         if (nT <= T_MIN) { done = true; break; }
         const float wgt = alpha * T;
-        const float4 col = sC[t];
+        const float4 col = sm.col[t];
         pr += col.x * wgt; pg += col.y * wgt; pb_ += col.z * wgt;
         cur = pos + t;
         T = nT;
@@ -624,7 +631,7 @@ raster_fwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
     }
     pos += pb.n;
     cand = pool_next_cand(cand, pb.n);
-    __syncthreads();          // the next stage overwrites sA / sB / sC / sBox before its first barrier
+    __syncthreads();          // the next stage overwrites col / boxB / the records before its first barrier
   }
   if (inside) {
     const size_t p = ((size_t)c * H + i) * W + j;
@@ -641,14 +648,14 @@ raster_fwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
 // One run of a Gaussian's slots summed by one thread -> gradient contribution.  m: sum u, u dx, u dy, u dx^2, u dx dy,
 // u dy^2 (u = vis dL/dalpha) and sum alpha T v_rgb.  With v_sigma = -opac u:  d/dxy = v_sigma Q d,
 // d/dconic = v_sigma (dx^2 / 2, dx dy, dy^2 / 2),  d/dopac = u.
-__device__ __forceinline__ void pool_emit(float* m, const float4 A, const float4 B, uint32_t e, float4* v_geomA,
-                                          float4* v_geomB, float4* v_rgb) {
+__device__ __forceinline__ void pool_emit(float* m, const PoolWalk& wk, float4* v_geomA, float4* v_geomB, float4* v_rgb) {
   if (m[0] != 0.f || m[1] != 0.f || m[2] != 0.f || m[3] != 0.f || m[4] != 0.f || m[5] != 0.f || m[6] != 0.f ||
       m[7] != 0.f || m[8] != 0.f) {
-    const float no = -A.z;
-    atomicAdd(v_geomA + e, make_float4(no * (B.x * m[1] + B.y * m[2]), no * (B.y * m[1] + B.z * m[2]), m[0], 0.f));
-    atomicAdd(v_geomB + e, make_float4(0.5f * no * m[3], no * m[4], 0.5f * no * m[5], 0.f));
-    atomicAdd(v_rgb + e, make_float4(m[6], m[7], m[8], 0.f));
+    const float no = -wk.opac;
+    atomicAdd(v_geomA + wk.e,
+              make_float4(no * (wk.qa * m[1] + wk.qb * m[2]), no * (wk.qb * m[1] + wk.qc * m[2]), m[0], 0.f));
+    atomicAdd(v_geomB + wk.e, make_float4(0.5f * no * m[3], no * m[4], 0.5f * no * m[5], 0.f));
+    atomicAdd(v_rgb + wk.e, make_float4(m[6], m[7], m[8], 0.f));
   }
 #pragma unroll
   for (int k = 0; k < 9; ++k) m[k] = 0.f;
@@ -661,23 +668,7 @@ raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
                        int tile_h, const float* __restrict__ alphas, const int32_t* __restrict__ last_ids,
                        const float* __restrict__ v_render, const float* __restrict__ v_alphas,
                        float4* __restrict__ v_geomA, float4* __restrict__ v_geomB, float4* __restrict__ v_rgb) {
-  __shared__ float4 sA[BLOCK], sB[BLOCK], sC[BLOCK];
-  __shared__ uint32_t sE[BLOCK];
-  __shared__ PoolBox sBox[BLOCK];
-  __shared__ uint8_t sComp[BLOCK];
-  __shared__ int sCBase[BLOCK];
-  __shared__ uint32_t sMask[PW][BLOCK];
-  // phase A: alpha / vis (0 when alpha was clamped); phase B: alpha T / vis dL/dalpha
-#ifdef ST3R_HOST_EMU
-  __shared__ float sPoolA[PSLOTS], sPoolV[PSLOTS];
-#else
-  extern __shared__ float pool_dyn[];        // 2 * PSLOTS floats (beyond the 48 KB of static shared memory)
-  float* const sPoolA = pool_dyn;
-  float* const sPoolV = pool_dyn + PSLOTS;
-#endif
-  __shared__ float4 sV[BLOCK];               // upstream colour gradient of every pixel of the tile
-  __shared__ int sScan[BLOCK / 32], sTake[2 * BLOCK / 32];
-  const PoolShared sh = {sA, sB, sC, sBox, sComp, sCBase, sMask, sScan, sTake};
+  POOL_SMEM(true);
   const int c = blockIdx.y, tile = blockIdx.x;
   const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
   const int tr = threadIdx.x, lane = tr & 31, wrp = tr >> 5;
@@ -698,45 +689,44 @@ raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
     vr = v_render[3 * p]; vg = v_render[3 * p + 1]; vb = v_render[3 * p + 2];
     va = v_alphas ? v_alphas[p] : 0.f;
   }
-  sV[tr] = make_float4(vr, vg, vb, 0.f);
+  sm.v[tr] = make_float4(vr, vg, vb, 0.f);
   const float tf_va = T_final * va;
   // nothing behind the last Gaussian any pixel of the tile blended takes part
   int tile_last = __reduce_max_sync(0xffffffffu, bin_final);
-  if (lane == 0) sScan[wrp] = tile_last;
+  if (lane == 0) sm.scan[wrp] = tile_last;
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < BLOCK / 32; ++k) tile_last = max(tile_last, sScan[k]);
-  __syncthreads();                           // sScan is reused by the first pool_stage
+  for (int k = 0; k < BLOCK / 32; ++k) tile_last = max(tile_last, sm.scan[k]);
+  __syncthreads();                           // scan[] is reused by the first pool_stage
   int hi = min(rg.hi - 1, tile_last);        // slot t of a batch holds sorted position hi - t: ascending t = back to front
   int cand = PG;
   while (hi >= rg.lo) {
     const int idx = hi - tr;
     const bool have = tr < cand && idx >= rg.lo;
     const uint32_t e = have ? flatten[idx] : 0u;
-    sE[tr] = e;
-    const PoolBatch pb = pool_stage(have, e, geomA, geomB, rgb, px0, py0, rmax, cmax, 0, sh);
+    const PoolBatch pb = pool_stage<true>(have, e, geomA, geomB, rgb, px0, py0, rmax, cmax, 0, sm);
     int s0, s_end, ci0;
-    const bool work = pool_chunk(pb.S, sCBase, s0, s_end, ci0);
+    const bool work = pool_chunk(pb.S, sm.cbase, s0, s_end, ci0);
     // ---- phase A
     if (work) {
       int s = s0, ci = ci0;
       PoolWalk wk;
-      wk.enter(sh, ci, s, px0, py0);
+      wk.enter(sm, ci, s, true);
       for (;;) {
-        const float dx = wk.A.x - wk.pxc, dy = wk.A.y - wk.pyr;
-        const float sigma = blend_sigma(wk.B.x, wk.B.y, wk.B.z, dx, dy);
+        const float dx = wk.x - wk.pxc, dy = wk.y - wk.pyr;
+        const float sigma = blend_sigma(wk.qa, wk.qb, wk.qc, dx, dy);
         const float vis = exp_neg(sigma);
-        const float alpha = fminf(ALPHA_MAX, wk.A.z * vis);
+        const float alpha = fminf(ALPHA_MAX, wk.opac * vis);
         float pa = 0.f, pv = 0.f;             // non-contributing slots read as "nothing" in phase C
         if (!(sigma < 0.f || alpha < ALPHA_MIN)) {
           pa = alpha;
-          pv = (wk.A.z * vis <= ALPHA_MAX) ? vis : 0.f;
-          atomicOr(&sMask[wk.t >> 5][wk.pix], 1u << (wk.t & 31));
+          pv = (wk.opac * vis <= ALPHA_MAX) ? vis : 0.f;
+          atomicOr(&sm.mask[wk.t >> 5][wk.pix], 1u << (wk.t & 31));
         }
-        sPoolA[s] = pa;
-        sPoolV[s] = pv;
+        sm.poolA[s] = pa;
+        sm.poolV[s] = pv;
         if (++s == s_end) break;
-        if (s == wk.run_end) wk.enter(sh, ++ci, s, px0, py0);
+        if (s == wk.run_end) wk.enter(sm, ++ci, s, false);
         else wk.step();
       }
     }
@@ -745,7 +735,7 @@ raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
     {
       uint32_t occ = 0;
 #pragma unroll
-      for (int w = 0; w < PW; ++w) occ |= (sMask[w][tr] != 0u ? 1u : 0u) << w;
+      for (int w = 0; w < PW; ++w) occ |= (sm.mask[w][tr] != 0u ? 1u : 0u) << w;
       uint32_t bits = 0;
       int w = 0;
       for (;;) {
@@ -753,27 +743,27 @@ raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
           if (occ == 0u) break;
           w = __ffs(occ) - 1;
           occ &= occ - 1;
-          bits = sMask[w][tr];
+          bits = sm.mask[w][tr];
         }
         const int t = w * 32 + __ffs(bits) - 1;
         bits &= bits - 1;
-        const PoolBox bx = sBox[t];
-        const int slot = bx.base + (myrow - box_r0(bx.geo)) * box_wc(bx.geo) + mycol - box_c0(bx.geo);
+        const int2 bx = sm.boxB[t];
+        const int slot = bx.x + myrow * bx.y + mycol;
         float fac = 0.f, u = 0.f;             // a Gaussian behind this pixel's last blended one contributes nothing
         if (hi - t <= bin_final) {
-          const float alpha = sPoolA[slot];
+          const float alpha = sm.poolA[slot];
           const float ra = fast_rcp(1.0f - alpha);
           T *= ra;
           fac = alpha * T;
-          const float4 col = sC[t];
+          const float4 col = sm.col[t];
           const float cv = col.x * vr + col.y * vg + col.z * vb;
           const float v_alpha = T * cv + ra * (tf_va - behind_v);
           behind_v += fac * cv;
-          u = sPoolV[slot] * v_alpha;
+          u = sm.poolV[slot] * v_alpha;
           ST3R_EMU_COUNT(11);                 // contributing (pixel, Gaussian) pairs
         }
-        sPoolA[slot] = fac;
-        sPoolV[slot] = u;
+        sm.poolA[slot] = fac;
+        sm.poolV[slot] = u;
       }
     }
     __syncthreads();
@@ -781,13 +771,13 @@ raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
     if (work) {
       int s = s0, ci = ci0;
       PoolWalk wk;
-      wk.enter(sh, ci, s, px0, py0);
+      wk.enter(sm, ci, s, true);
       float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (;;) {
-        const float fac = sPoolA[s], u = sPoolV[s];
+        const float fac = sm.poolA[s], u = sm.poolV[s];
         if (fac != 0.f || u != 0.f) {
-          const float dx = wk.A.x - wk.pxc, dy = wk.A.y - wk.pyr;
-          const float4 v = sV[wk.pix];
+          const float dx = wk.x - wk.pxc, dy = wk.y - wk.pyr;
+          const float4 v = sm.v[wk.pix];
           const float ux = u * dx, uy = u * dy;
           m[0] += u; m[1] += ux; m[2] += uy;
           m[3] += ux * dx; m[4] += ux * dy; m[5] += uy * dy;
@@ -795,9 +785,9 @@ raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
         }
         ++s;
         if (s == s_end || s == wk.run_end) {
-          pool_emit(m, wk.A, wk.B, sE[wk.t], v_geomA, v_geomB, v_rgb);
+          pool_emit(m, wk, v_geomA, v_geomB, v_rgb);
           if (s == s_end) break;
-          wk.enter(sh, ++ci, s, px0, py0);
+          wk.enter(sm, ++ci, s, false);
         } else {
           wk.step();
         }
@@ -805,7 +795,7 @@ raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
     }
     hi -= pb.n;
     cand = pool_next_cand(cand, pb.n);
-    __syncthreads();                         // the next stage overwrites sA / sB / sC / sE / sBox before its first barrier
+    __syncthreads();                         // the next stage overwrites col / boxB / the records before its first barrier
   }
 }
 
@@ -1319,12 +1309,18 @@ int st3r_gs_raster_fwd(const int32_t* offsets, const int32_t* n_isect, const uin
                  "st3r_gs_raster_fwd: null pointer");
   const int tile_w = (width + TILE - 1) / TILE, tile_h = (height + TILE - 1) / TILE;
   dim3 grid(tile_w * tile_h, C);
-  if (g_raster_bwd_variant == 3)
-    raster_fwd_pool_kernel<<<grid, BLOCK, 0, stream>>>(
+  if (g_raster_bwd_variant == 3) {
+    static PerDeviceOnce once;
+    if (!once.done()) {
+      ST3R_CHECK_CUDA(cudaFuncSetAttribute(raster_fwd_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(PoolSmem<false>)));
+      once.mark();
+    }
+    raster_fwd_pool_kernel<<<grid, BLOCK, sizeof(PoolSmem<false>), stream>>>(
         offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
         reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, render, alphas, last_ids,
         reinterpret_cast<unsigned long long*>(n_blend));
-  else
+  } else
     raster_fwd_kernel<<<grid, BLOCK, 0, stream>>>(
         offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
         reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, render, alphas, last_ids,
@@ -1349,10 +1345,10 @@ int st3r_gs_raster_bwd(const int32_t* offsets, const int32_t* n_isect, const uin
     static PerDeviceOnce once;
     if (!once.done()) {
       ST3R_CHECK_CUDA(cudaFuncSetAttribute(raster_bwd_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           2 * PSLOTS * (int)sizeof(float)));
+                                           (int)sizeof(PoolSmem<true>)));
       once.mark();
     }
-    raster_bwd_pool_kernel<<<grid, BLOCK, 2 * PSLOTS * sizeof(float), stream>>>(
+    raster_bwd_pool_kernel<<<grid, BLOCK, sizeof(PoolSmem<true>), stream>>>(
         offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
         reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, alphas, last_ids, v_render, v_alphas,
         reinterpret_cast<float4*>(v_geomA), reinterpret_cast<float4*>(v_geomB), reinterpret_cast<float4*>(v_rgb));

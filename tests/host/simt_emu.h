@@ -23,6 +23,10 @@ struct float2 { float x, y; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+struct int4 { int x, y, z, w; };
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 struct uint3 { unsigned x, y, z; };
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 
