@@ -171,12 +171,12 @@ ST3R_API int st3r_gs_raster_fwd(const int32_t* offsets, const int32_t* n_isect, 
                        const float* geomA, const float* geomB, const float* rgb, int C, int width, int height,
                        int tile_size, float* render, float* alphas, int32_t* last_ids, uint64_t* n_blend,
                        cudaStream_t stream);
-/* Implementation variant of st3r_gs_raster_bwd for subsequent calls of this process: 0 (default) reduces the nine
- * gradient terms of every (warp, Gaussian) visit across the warp; 1 queues (Gaussian, pixel, alpha T, vis dL/dalpha)
- * records per warp and turns them into gradients 32 records at a time (meant for small splats, where few of the 32
- * lanes contribute per visit); 2 evaluates alpha Gaussian-parallel over each splat's bounding box inside the tile
- * into a shared-memory fragment pool, runs only the per-pixel recurrence in the visits and sums the gradients
- * Gaussian-parallel again.  Same terms per (pixel, Gaussian); only the fp32 summation order differs. */
+/* Implementation of st3r_gs_raster_fwd / _bwd for subsequent calls of this process: 0 (default) = fragment-pool
+ * kernels (alpha evaluated once per pixel of each splat's bounding box inside the tile into a shared-memory pool,
+ * per-pixel recurrence over the pixel's own contributing Gaussians, gradients summed per Gaussian in registers; batches
+ * of tile-sized splats are walked pixel-parallel); 1 = visit-list kernels (every warp tests every Gaussian that can touch
+ * its two pixel rows; the first implementation, kept as an independent cross-check).  Same terms per (pixel, Gaussian):
+ * the forward outputs are bit-identical, the backward differs by fp32 summation order. */
 ST3R_API int st3r_gs_set_raster_variant(int variant);
 /* rasterize_to_pixels backward: accumulates into v_geomA = (v_x, v_y, v_opacity, 0), v_geomB = v_conic,
  * v_rgb (all float4 [C*N], zeroed by the caller).  v_alphas may be NULL. */

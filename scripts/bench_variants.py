@@ -39,10 +39,10 @@ def raster_leg(dev, out):
     flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
     for scale_mode in ("init", "rand"):      # 3e-3 initial scale / exp(N(-4, 0.5)) sweep of SURVEY 8d
         params, states, truth, cams = bench.make_workload(dev, 0, scale_mode=scale_mode)
-        for variant in [int(v) for v in os.environ.get("ST3R_VARIANTS", "0,1,2,3").split(",")]:
+        for variant in [int(v) for v in os.environ.get("ST3R_VARIANTS", "0,1").split(",")]:
             key = f"train_step_ms[{scale_mode}][raster_variant={variant}]"
             try:
-                gs.RASTER_BWD_VARIANT = variant
+                gs.RASTER_VARIANT = variant
                 p = {k: v.clone() for k, v in params.items()}
                 s = {k: (a.clone(), b.clone()) for k, (a, b) in states.items()}
                 plan = gs.TrainPlan(bench.N_GAUSS, bench.N_VIEWS, bench.W, bench.H, dev)
@@ -62,7 +62,7 @@ def raster_leg(dev, out):
             except Exception as e:
                 out[key] = "ERROR " + repr(e)[:300]
             finally:
-                gs.RASTER_BWD_VARIANT = 0
+                gs.RASTER_VARIANT = 0
 
 
 def align_leg(dev, out):

@@ -8,9 +8,9 @@ from starst3r_b200 import gs
 
 dev = torch.device("cuda:0")
 out = {}
-variants = [int(v) for v in os.environ.get("ST3R_VARIANTS", "0,3").split(",")]
+variants = [int(v) for v in os.environ.get("ST3R_VARIANTS", "1,0").split(",")]
 for variant in variants:
-    gs.RASTER_BWD_VARIANT = variant
+    gs.RASTER_VARIANT = variant
     params, states, truth, cams = bench.make_workload(dev, 0)
     plan = gs.TrainPlan(bench.N_GAUSS, bench.N_VIEWS, bench.W, bench.H, dev)
     flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)

@@ -8,7 +8,7 @@ from starst3r_b200 import gs, match, synth
 dev = torch.device("cuda:0")
 what = sys.argv[1] if len(sys.argv) > 1 else "both"
 if what in ("both", "step"):
-    params, states, truth, cams = bench.make_workload(dev, 0)
+    params, states, truth, cams = bench.make_workload(dev, 0, scale_mode=os.environ.get("ST3R_SCALE_MODE", "init"))
     plan = gs.TrainPlan(bench.N_GAUSS, bench.N_VIEWS, bench.W, bench.H, dev)
     for i in range(int(os.environ.get("ST3R_PROF_STEPS", "3"))):
         loss, fr = gs.train_step(params, states, truth, cams, bench.W, bench.H, i + 1, plan=plan)

@@ -342,480 +342,6 @@ __device__ __forceinline__ void blend_grad_terms(const float4 A, const float4 B,
   g[6] = fac * vr; g[7] = fac * vg; g[8] = fac * vb;
 }
 
-// ---- fragment-pool kernels (forward and backward) --------------------------------------------------------------------
-// With the reference's 3e-3 initial scale a splat covers a handful of pixels, and the pixel-parallel walk above spends
-// its instructions on alpha tests that fail (forward: 4.5 % hit rate) and on warp reductions in which ~6 of 32 lanes
-// carry a value (ncu, round 1: both kernels issue-bound).  Here the work is split by what it is parallel in:
-//   0. stage: thread t loads Gaussian t of the batch (up to PG per batch), derives its bounding box inside the tile
-//      (conservative extents of the alpha >= 1/255 ellipse, clipped to the tile and the image) and gets a run of pool
-//      slots, one per box pixel, from a block-wide exclusive scan of the box areas (small and tile-sized splats mix
-//      freely; what does not fit into the pool is left to the next batch).  The same scan compacts the Gaussians that
-//      have a box at all;
-//   A. slot-parallel: the S slots of the batch are cut into 256 equal chunks.  A thread finds the Gaussian its chunk
-//      starts in by binary search over the run offsets and walks its chunk in ONE flat loop (moving on to the next
-//      Gaussian of the compacted list is a predicated block, so all lanes of all warps run the same trip count): alpha
-//      once per box pixel, stored in the slot, and the Gaussian's bit set in the mask of every pixel that passes
-//      the alpha test;
-//   B. pixel-parallel: every pixel walks the set bits of ITS OWN mask in depth order - no alpha test, no warp
-//      collective, only the recurrence that is sequential per pixel (transmittance, colour; backward: colour behind,
-//      dL/dalpha, results written back to the slot);
-//   C. (backward) slot-parallel again, same chunks: a thread accumulates the moments of its slots in registers and
-//      issues one vector atomic triple per Gaussian run it touches: no shared-memory atomics, no warp reductions.
-// Results: same expressions in the same per-pixel order as the kernels above (the forward is bit-identical); the
-// backward's per-Gaussian sums are added in a different order.
-#ifndef ST3R_POOL_PG
-#define ST3R_POOL_PG 256
-#endif
-#ifndef ST3R_POOL_SLOTS
-#define ST3R_POOL_SLOTS (ST3R_POOL_PG * 16)
-#endif
-constexpr int PG = ST3R_POOL_PG;       // Gaussians per batch (one per thread of the first PG threads)
-constexpr int PW = PG / 32;            // mask words per pixel
-constexpr int PSLOTS = ST3R_POOL_SLOTS;   // pool slots per batch (a Gaussian takes at most 256)
-static_assert(PG == 64 || PG == 128 || PG == 256, "pool batch: 64, 128 or 256 Gaussians");
-static_assert(PSLOTS >= 256 && PSLOTS < (1 << 20), "the pool must hold a tile-sized box");
-
-// Box of tile pixels (rows r0..r1, columns c0..c1, clipped to rmax / cmax) on which opac * exp(-sigma) >= 1/255 is
-// possible; see row_mask for the bound (here with fast intrinsics and a wider safety margin: the box only has to
-// contain the ellipse).  Returns the area (0: cannot contribute); geo = r0 | c0 << 4 | (wc - 1) << 8.
-__device__ __forceinline__ int pool_box(const float4 A, const float4 B, float px0, float py0, int rmax, int cmax,
-                                        uint32_t& geo) {
-  geo = 0;
-  if (!(A.z > ALPHA_MIN)) return 0;                      // opac * exp(-sigma) <= opac < 1/255 (also NaN)
-  int r0 = 0, r1 = rmax, c0 = 0, c1 = cmax;
-  const float det = B.x * B.z - B.y * B.y;
-  if (det > 0.f) {
-#ifdef ST3R_HOST_EMU
-    const float L2 = 2.0f * logf(255.0f * A.z) / det;
-#else
-    const float L2 = __fdividef(2.0f * __logf(255.0f * A.z), det);
-#endif
-    const float hy = sqrtf(L2 * B.x) * 1.001f + 4e-3f;
-    const float hx = sqrtf(L2 * B.z) * 1.001f + 4e-3f;
-    // (NaN / inf extents fall through fmaxf / fminf to the whole tile)
-    r0 = max(0, (int)fmaxf(ceilf(A.y - hy - py0), -1.0f));
-    r1 = min(rmax, (int)fminf(floorf(A.y + hy - py0), (float)TILE));
-    c0 = max(0, (int)fmaxf(ceilf(A.x - hx - px0), -1.0f));
-    c1 = min(cmax, (int)fminf(floorf(A.x + hx - px0), (float)TILE));
-  }
-  if (r1 < r0 || c1 < c0) return 0;
-  const int wc = c1 - c0 + 1, nr = r1 - r0 + 1;
-  geo = (uint32_t)r0 | (uint32_t)c0 << 4 | (uint32_t)(wc - 1) << 8;
-  return wc * nr;
-}
-
-struct PoolBatch { int n, S, n_done; };   // Gaussians staged, pool slots handed out, barrier count of the caller's flag
-
-// Shared memory of one CTA.  kBwd: two pool values per slot, the entry ids and the tile's upstream gradients.
-template <bool kBwd>
-struct PoolSmem {
-  // per Gaussian WITH a box, in depth order (compacted): the record a slot walk loads when it enters the box
-  float4 recA[BLOCK];         // x, y, opacity, pixel-centre x of the box's first column
-  float4 recB[BLOCK];         // conic a, b, c, pixel-centre y of the box's first row
-  int4 recC[BLOCK];           // first slot behind the box, tile pixel of its first slot, wc | t << 5 | area << 13, entry
-  int cbase[BLOCK];           // first pool slot (ascending); INT_MAX behind the last compacted Gaussian
-  // per batch slot t (depth order)
-  float4 col[BLOCK];          // colour
-  int2 boxB[BLOCK];           // pool slot of tile pixel (row, col) = x + row * y + col
-  uint32_t mask[PW][BLOCK];   // bit t of word w of pixel p: Gaussian 32 w + t contributes to p
-  int scan[BLOCK / 32], take[2 * BLOCK / 32];
-  float poolA[PSLOTS];        // forward: alpha.  Backward, phase A: alpha; phase B: alpha T
-  float poolV[kBwd ? PSLOTS : 1];    // backward, phase A: vis (0 when alpha was clamped); phase B: vis dL/dalpha
-  float4 v[kBwd ? BLOCK : 1];        // backward: upstream colour gradient of every pixel of the tile
-};
-
-// Stage one batch (two barriers).  `have`: this thread's slot holds Gaussian e.
-template <bool kBwd>
-__device__ __forceinline__ PoolBatch pool_stage(bool have, uint32_t e, const float4* __restrict__ geomA,
-                                                const float4* __restrict__ geomB, const float4* __restrict__ rgb,
-                                                float px0, float py0, int rmax, int cmax, int done_pred,
-                                                PoolSmem<kBwd>& sm) {
-  const unsigned full = 0xffffffffu;
-  const int tr = threadIdx.x, lane = tr & 31, wrp = tr >> 5;
-  int area = 0;
-  uint32_t geo = 0;
-  float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
-  if (have) {
-    A = geomA[e];
-    B = geomB[e];
-    sm.col[tr] = rgb[e];
-    area = pool_box(A, B, px0, py0, rmax, cmax, geo);
-  }
-  // one scan for both prefixes: slots in the low 20 bits, Gaussians with a box above
-  const int mine = area | (area ? 1 << 20 : 0);
-  int incl = mine;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const int v = (int)__shfl_up_sync(full, (unsigned)incl, off);
-    if (lane >= off) incl += v;
-  }
-  if (lane == 31) sm.scan[wrp] = incl;
-  sm.cbase[tr] = 0x7fffffff;
-#pragma unroll
-  for (int w = 0; w < PW; ++w) sm.mask[w][tr] = 0u;
-  PoolBatch pb;
-  pb.n_done = __syncthreads_count(done_pred);
-  int before = 0;
-#pragma unroll
-  for (int k = 0; k < BLOCK / 32 - 1; ++k) before += (k < wrp) ? sm.scan[k] : 0;
-  const int excl = before + incl - mine;
-  const int base = excl & 0xfffff, ci = excl >> 20;
-  const bool fits = have && base + area <= PSLOTS;       // monotone along t: a prefix of the batch is staged
-  if (have && !fits) ST3R_EMU_COUNT(12);                  // Gaussians left to the next batch (pool full)
-  if (!fits) area = 0;
-  const uint32_t staged = __ballot_sync(full, fits);
-  const int top = __reduce_max_sync(full, fits ? base + area : 0);
-  if (lane == 0) {
-    sm.take[wrp] = __popc(staged);
-    sm.take[BLOCK / 32 + wrp] = top;
-  }
-  if (area) {
-    const int r0 = (int)(geo & 15u), c0 = (int)((geo >> 4) & 15u), wc = (int)((geo >> 8) & 15u) + 1;
-    sm.boxB[tr] = make_int2(base - r0 * wc - c0, wc);
-    sm.recA[ci] = make_float4(A.x, A.y, A.z, px0 + (float)c0);
-    sm.recB[ci] = make_float4(B.x, B.y, B.z, py0 + (float)r0);
-    sm.recC[ci] = make_int4(base + area, r0 * TILE + c0, wc | tr << 5 | area << 13, (int)e);
-    sm.cbase[ci] = base;
-  }
-  __syncthreads();
-  pb.n = 0;
-  pb.S = 0;
-#pragma unroll
-  for (int k = 0; k < BLOCK / 32; ++k) {
-    pb.n += sm.take[k];
-    pb.S = max(pb.S, sm.take[BLOCK / 32 + k]);
-  }
-  return pb;
-}
-
-// Candidates of the next batch: all PG while whole batches fit into the pool, else about twice what the pool took.
-__device__ __forceinline__ int pool_next_cand(int cand, int taken) {
-  return taken == cand ? min(PG, 2 * cand) : max(32, min(PG, 2 * taken));
-}
-
-// The chunk [s, s_end) of pool slots of this thread and the compacted index of the Gaussian its first slot is in.
-__device__ __forceinline__ bool pool_chunk(int S, const int* cbase, int& s, int& s_end, int& ci) {
-  const int q = ((S + BLOCK - 1) / BLOCK) | 1;           // odd: the lanes of a warp write their slots to distinct banks
-  s = (int)threadIdx.x * q;
-  s_end = min(S, s + q);
-  if (s >= s_end) return false;
-  ci = 0;                                                 // largest ci with cbase[ci] <= s (cbase[0] = 0)
-#pragma unroll
-  for (int step = BLOCK / 2; step; step >>= 1)
-    if (cbase[ci + step] <= s) ci += step;                // (index <= BLOCK - 1)
-  return true;
-}
-
-// Walk state of one thread inside the box of the Gaussian it is currently in.
-struct PoolWalk {
-  float x, y, opac, qa, qb, qc;
-  float pxc0, pxc, pyr;      // pixel-centre coordinates of the box's first column, the current column, the current row
-  int cc, wc, run_end, pix;  // column inside the box, box width, first slot behind the box, current tile pixel
-  int t, e;                  // batch slot (depth order), entry id
-  // Enter compacted Gaussian ci at slot s (s > its first slot only for the first Gaussian of a chunk).
-  template <bool kBwd>
-  __device__ __forceinline__ void enter(const PoolSmem<kBwd>& sm, int ci, int s, bool first) {
-    const float4 ra = sm.recA[ci], rb = sm.recB[ci];
-    const int4 rc = sm.recC[ci];
-    x = ra.x; y = ra.y; opac = ra.z; pxc0 = ra.w;
-    qa = rb.x; qb = rb.y; qc = rb.z; pyr = rb.w;
-    run_end = rc.x;
-    pix = rc.y;
-    wc = rc.z & 31;
-    t = (rc.z >> 5) & 255;
-    e = rc.w;
-    cc = 0;
-    pxc = pxc0;
-    if (first) {
-      const int o = s - (run_end - (rc.z >> 13));
-      if (o) {
-        const int rr = (int)(((float)o + 0.5f) / (float)wc);      // o / wc (o < 256, wc <= 16: far from the rounding edge)
-        cc = o - rr * wc;
-        pxc = pxc0 + (float)cc;
-        pyr += (float)rr;
-        pix += rr * TILE + cc;
-      }
-    }
-  }
-  // Next slot of the same box.
-  __device__ __forceinline__ void step() {
-    pxc += 1.0f;
-    ++pix;
-    if (++cc == wc) { cc = 0; pxc = pxc0; pyr += 1.0f; pix += TILE - wc; }
-  }
-};
-
-#ifdef ST3R_HOST_EMU
-#define POOL_SMEM(kBwd) __shared__ PoolSmem<kBwd> sm
-#else
-#define POOL_SMEM(kBwd)                               \
-  extern __shared__ __align__(16) char pool_smem_raw[]; \
-  PoolSmem<kBwd>& sm = *reinterpret_cast<PoolSmem<kBwd>*>(pool_smem_raw)
-#endif
-
-__global__ void __launch_bounds__(BLOCK)
-raster_fwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
-                       const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
-                       const float4* __restrict__ geomB, const float4* __restrict__ rgb, int C, int W, int H, int tile_w,
-                       int tile_h, float* __restrict__ render, float* __restrict__ alphas,
-                       int32_t* __restrict__ last_ids, unsigned long long* __restrict__ n_blend) {
-  POOL_SMEM(false);
-  const int c = blockIdx.y, tile = blockIdx.x;
-  const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
-  const int tr = threadIdx.x, lane = tr & 31;
-  const int myrow = tr >> 4, mycol = tr & 15;
-  const int i = tyi * TILE + myrow, j = txi * TILE + mycol;
-  const bool inside = i < H && j < W;
-  const float px0 = (float)(txi * TILE) + 0.5f, py0 = (float)(tyi * TILE) + 0.5f;   // centre of the tile's first pixel
-  const int rmax = min(TILE, H - tyi * TILE) - 1, cmax = min(TILE, W - txi * TILE) - 1;
-  bool done = !inside;
-  const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
-  float T = 1.0f, pr = 0.f, pg = 0.f, pb_ = 0.f;
-  int cur = 0, blends = 0;
-  int pos = rg.lo, cand = PG;
-  while (pos < rg.hi) {
-    const int idx = pos + tr;
-    const bool have = tr < cand && idx < rg.hi;
-    const uint32_t e = have ? flatten[idx] : 0u;
-    const PoolBatch pb = pool_stage<false>(have, e, geomA, geomB, rgb, px0, py0, rmax, cmax, done, sm);
-    if (pb.n_done == BLOCK) break;
-    // ---- phase A: alpha of every box pixel, contribution bits
-    {
-      int s, s_end, ci;
-      if (pool_chunk(pb.S, sm.cbase, s, s_end, ci)) {
-        PoolWalk wk;
-        wk.enter(sm, ci, s, true);
-        for (;;) {
-          const float dx = wk.x - wk.pxc, dy = wk.y - wk.pyr;
-          const float sigma = blend_sigma(wk.qa, wk.qb, wk.qc, dx, dy);
-          const float alpha = fminf(ALPHA_MAX, wk.opac * exp_neg(sigma));
-          ST3R_EMU_COUNT(10);                               // box pixels tested
-          if (!(sigma < 0.f || alpha < ALPHA_MIN)) {
-            sm.poolA[s] = alpha;
-            atomicOr(&sm.mask[wk.t >> 5][wk.pix], 1u << (wk.t & 31));
-          }
-          if (++s == s_end) break;
-          if (s == wk.run_end) wk.enter(sm, ++ci, s, false);
-          else wk.step();
-        }
-      }
-    }
-    __syncthreads();
-    // ---- phase B: the pixel's own contributing Gaussians, front to back
-    if (!done) {
-      uint32_t occ = 0;                       // words of this pixel's mask that hold a bit
-#pragma unroll
-      for (int w = 0; w < PW; ++w) occ |= (sm.mask[w][tr] != 0u ? 1u : 0u) << w;
-      uint32_t bits = 0;
-      int w = 0;
-      for (;;) {
-        if (bits == 0u) {
-          if (occ == 0u) break;
-          w = __ffs(occ) - 1;
-          occ &= occ - 1;
-          bits = sm.mask[w][tr];
-        }
-        const int t = w * 32 + __ffs(bits) - 1;
-        bits &= bits - 1;
-        const int2 bx = sm.boxB[t];
-        const float alpha = sm.poolA[bx.x + myrow * bx.y + mycol];
-        const float nT = T * (1.0f - alpha);
-        if (nT <= T_MIN) { done = true; break; }
-        const float wgt = alpha * T;
-        const float4 col = sm.col[t];
-        pr += col.x * wgt; pg += col.y * wgt; pb_ += col.z * wgt;
-        cur = pos + t;
-        T = nT;
-        ++blends;
-      }
-    }
-    pos += pb.n;
-    cand = pool_next_cand(cand, pb.n);
-    __syncthreads();          // the next stage overwrites col / boxB / the records before its first barrier
-  }
-  if (inside) {
-    const size_t p = ((size_t)c * H + i) * W + j;
-    render[3 * p] = pr; render[3 * p + 1] = pg; render[3 * p + 2] = pb_;
-    alphas[p] = 1.0f - T;
-    last_ids[p] = cur;
-  }
-  if (n_blend) {
-    for (int off = 16; off; off >>= 1) blends += __shfl_xor_sync(0xffffffffu, blends, off);
-    if (lane == 0 && blends) atomicAdd(n_blend, (unsigned long long)blends);
-  }
-}
-
-// One run of a Gaussian's slots summed by one thread -> gradient contribution.  m: sum u, u dx, u dy, u dx^2, u dx dy,
-// u dy^2 (u = vis dL/dalpha) and sum alpha T v_rgb.  With v_sigma = -opac u:  d/dxy = v_sigma Q d,
-// d/dconic = v_sigma (dx^2 / 2, dx dy, dy^2 / 2),  d/dopac = u.
-__device__ __forceinline__ void pool_emit(float* m, const PoolWalk& wk, float4* v_geomA, float4* v_geomB, float4* v_rgb) {
-  if (m[0] != 0.f || m[1] != 0.f || m[2] != 0.f || m[3] != 0.f || m[4] != 0.f || m[5] != 0.f || m[6] != 0.f ||
-      m[7] != 0.f || m[8] != 0.f) {
-    const float no = -wk.opac;
-    atomicAdd(v_geomA + wk.e,
-              make_float4(no * (wk.qa * m[1] + wk.qb * m[2]), no * (wk.qb * m[1] + wk.qc * m[2]), m[0], 0.f));
-    atomicAdd(v_geomB + wk.e, make_float4(0.5f * no * m[3], no * m[4], 0.5f * no * m[5], 0.f));
-    atomicAdd(v_rgb + wk.e, make_float4(m[6], m[7], m[8], 0.f));
-  }
-#pragma unroll
-  for (int k = 0; k < 9; ++k) m[k] = 0.f;
-}
-
-__global__ void __launch_bounds__(BLOCK)
-raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
-                       const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
-                       const float4* __restrict__ geomB, const float4* __restrict__ rgb, int C, int W, int H, int tile_w,
-                       int tile_h, const float* __restrict__ alphas, const int32_t* __restrict__ last_ids,
-                       const float* __restrict__ v_render, const float* __restrict__ v_alphas,
-                       float4* __restrict__ v_geomA, float4* __restrict__ v_geomB, float4* __restrict__ v_rgb) {
-  POOL_SMEM(true);
-  const int c = blockIdx.y, tile = blockIdx.x;
-  const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
-  const int tr = threadIdx.x, lane = tr & 31, wrp = tr >> 5;
-  const int myrow = tr >> 4, mycol = tr & 15;
-  const int i = tyi * TILE + myrow, j = txi * TILE + mycol;
-  const bool inside = i < H && j < W;
-  const float px0 = (float)(txi * TILE) + 0.5f, py0 = (float)(tyi * TILE) + 0.5f;
-  const int rmax = min(TILE, H - tyi * TILE) - 1, cmax = min(TILE, W - txi * TILE) - 1;
-  const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
-  if (rg.hi <= rg.lo) return;
-  const size_t p = ((size_t)c * H + min(i, H - 1)) * W + min(j, W - 1);
-  const float T_final = 1.0f - alphas[p];
-  float T = T_final;
-  float behind_v = 0.f;                      // (colour behind the current Gaussian) . (upstream colour gradient)
-  const int bin_final = inside ? last_ids[p] : 0;
-  float vr = 0.f, vg = 0.f, vb = 0.f, va = 0.f;
-  if (inside) {
-    vr = v_render[3 * p]; vg = v_render[3 * p + 1]; vb = v_render[3 * p + 2];
-    va = v_alphas ? v_alphas[p] : 0.f;
-  }
-  sm.v[tr] = make_float4(vr, vg, vb, 0.f);
-  const float tf_va = T_final * va;
-  // nothing behind the last Gaussian any pixel of the tile blended takes part
-  int tile_last = __reduce_max_sync(0xffffffffu, bin_final);
-  if (lane == 0) sm.scan[wrp] = tile_last;
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < BLOCK / 32; ++k) tile_last = max(tile_last, sm.scan[k]);
-  __syncthreads();                           // scan[] is reused by the first pool_stage
-  int hi = min(rg.hi - 1, tile_last);        // slot t of a batch holds sorted position hi - t: ascending t = back to front
-  int cand = PG;
-  while (hi >= rg.lo) {
-    const int idx = hi - tr;
-    const bool have = tr < cand && idx >= rg.lo;
-    const uint32_t e = have ? flatten[idx] : 0u;
-    const PoolBatch pb = pool_stage<true>(have, e, geomA, geomB, rgb, px0, py0, rmax, cmax, 0, sm);
-    int s0, s_end, ci0;
-    const bool work = pool_chunk(pb.S, sm.cbase, s0, s_end, ci0);
-    // ---- phase A
-    if (work) {
-      int s = s0, ci = ci0;
-      PoolWalk wk;
-      wk.enter(sm, ci, s, true);
-      for (;;) {
-        const float dx = wk.x - wk.pxc, dy = wk.y - wk.pyr;
-        const float sigma = blend_sigma(wk.qa, wk.qb, wk.qc, dx, dy);
-        const float vis = exp_neg(sigma);
-        const float alpha = fminf(ALPHA_MAX, wk.opac * vis);
-        float pa = 0.f, pv = 0.f;             // non-contributing slots read as "nothing" in phase C
-        if (!(sigma < 0.f || alpha < ALPHA_MIN)) {
-          pa = alpha;
-          pv = (wk.opac * vis <= ALPHA_MAX) ? vis : 0.f;
-          atomicOr(&sm.mask[wk.t >> 5][wk.pix], 1u << (wk.t & 31));
-        }
-        sm.poolA[s] = pa;
-        sm.poolV[s] = pv;
-        if (++s == s_end) break;
-        if (s == wk.run_end) wk.enter(sm, ++ci, s, false);
-        else wk.step();
-      }
-    }
-    __syncthreads();
-    // ---- phase B: per-pixel recurrence over the pixel's own contributing Gaussians, back to front
-    {
-      uint32_t occ = 0;
-#pragma unroll
-      for (int w = 0; w < PW; ++w) occ |= (sm.mask[w][tr] != 0u ? 1u : 0u) << w;
-      uint32_t bits = 0;
-      int w = 0;
-      for (;;) {
-        if (bits == 0u) {
-          if (occ == 0u) break;
-          w = __ffs(occ) - 1;
-          occ &= occ - 1;
-          bits = sm.mask[w][tr];
-        }
-        const int t = w * 32 + __ffs(bits) - 1;
-        bits &= bits - 1;
-        const int2 bx = sm.boxB[t];
-        const int slot = bx.x + myrow * bx.y + mycol;
-        float fac = 0.f, u = 0.f;             // a Gaussian behind this pixel's last blended one contributes nothing
-        if (hi - t <= bin_final) {
-          const float alpha = sm.poolA[slot];
-          const float ra = fast_rcp(1.0f - alpha);
-          T *= ra;
-          fac = alpha * T;
-          const float4 col = sm.col[t];
-          const float cv = col.x * vr + col.y * vg + col.z * vb;
-          const float v_alpha = T * cv + ra * (tf_va - behind_v);
-          behind_v += fac * cv;
-          u = sm.poolV[slot] * v_alpha;
-          ST3R_EMU_COUNT(11);                 // contributing (pixel, Gaussian) pairs
-        }
-        sm.poolA[slot] = fac;
-        sm.poolV[slot] = u;
-      }
-    }
-    __syncthreads();
-    // ---- phase C: the chunk's slots summed per Gaussian run
-    if (work) {
-      int s = s0, ci = ci0;
-      PoolWalk wk;
-      wk.enter(sm, ci, s, true);
-      float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (;;) {
-        const float fac = sm.poolA[s], u = sm.poolV[s];
-        if (fac != 0.f || u != 0.f) {
-          const float dx = wk.x - wk.pxc, dy = wk.y - wk.pyr;
-          const float4 v = sm.v[wk.pix];
-          const float ux = u * dx, uy = u * dy;
-          m[0] += u; m[1] += ux; m[2] += uy;
-          m[3] += ux * dx; m[4] += ux * dy; m[5] += uy * dy;
-          m[6] += fac * v.x; m[7] += fac * v.y; m[8] += fac * v.z;
-        }
-        ++s;
-        if (s == s_end || s == wk.run_end) {
-          pool_emit(m, wk, v_geomA, v_geomB, v_rgb);
-          if (s == s_end) break;
-          wk.enter(sm, ++ci, s, false);
-        } else {
-          wk.step();
-        }
-      }
-    }
-    hi -= pb.n;
-    cand = pool_next_cand(cand, pb.n);
-    __syncthreads();                         // the next stage overwrites col / boxB / the records before its first barrier
-  }
-}
-
-// ---- variant 1 of the backward: per-warp record queues ----------------------------------------------------------
-// With the reference's 3e-3 initial scale a Gaussian covers ~12 pixels, so a (warp, Gaussian) visit of the kernel
-// above has ~3 of 32 lanes with a contribution, yet all lanes run the gradient arithmetic and the nine-value
-// butterfly (~100 of the ~125 instructions of a visit; ncu: 79 % issue-slot utilisation, i.e. the kernel is bound by
-// exactly these instructions).  Here the pixel-parallel pass only does what is sequential per pixel - the
-// transmittance, the colour behind, dL/dalpha - and every contributing lane appends a 12-byte record
-// (Gaussian slot, pixel lane, alpha T, vis dL/dalpha) to its warp's queue in shared memory.  The warp drains the
-// queue 32 records at a time with ALL lanes busy: one record per lane, the nine gradient terms, a segmented
-// suffix sum over equal Gaussian slots (records are appended in visit order, so equal slots are adjacent), and one
-// shared-memory update per segment head.  Visits with many contributing lanes (large splats: the log-normal scale
-// sweep) keep the direct butterfly, which is the efficient shape for them.
-constexpr int QW = 160;          // records per warp queue
-constexpr int DENSE_MIN = 16;    // visits with at least this many contributing lanes reduce directly: a butterfly
-                                 // costs ~70 instructions more than a queued visit, a queued record ~5 (static
-                                 // SASS counts), and on the headline workload no 2 x 16 strip sees more than 15
-                                 // contributing lanes of a 3e-3 splat (scripts/emu_visit_stats.py)
-
 // Warp-collective: reduces g[0..8] over the warp and adds the totals to a9[0..8] (shared memory).
 __device__ __forceinline__ void butterfly9_to_shared(const float* g, float* a9) {
   const unsigned full = 0xffffffffu;
@@ -848,453 +374,596 @@ __device__ __forceinline__ void butterfly9_to_shared(const float* g, float* a9) 
   if (((lane & 3) == 0 || ninth) && sum != 0.f) atomicAdd(a9 + (ninth ? 8 : vi), sum);
 }
 
-// Warp-collective drain of n queued records (see above).  px0 / py0: centre of the warp's first pixel.
-__device__ __forceinline__ void drain_queue(int n, const uint32_t* qk, const float* qf, const float* qv,
-                                            const float4* sA, const float4* sB, float (*acc)[9], float vr, float vg,
-                                            float vb, float px0, float py0) {
-  const unsigned full = 0xffffffffu;
-  const int lane = lane_id();
-  __syncwarp();                       // the records were written by other lanes
-#pragma unroll 1
-  for (int base = 0; base < QW; base += 32) {
-    if (!__any_sync(full, base < n)) break;      // n is warp-uniform; the vote says so to the compiler
-    const int i = base + lane;
-    const bool have = i < n;
-    const uint32_t key = have ? qk[i] : 0xffffffe0u + (uint32_t)lane;   // padding: one-lane segments of zeros
-    const uint32_t t = key >> 5;
-    const int pl = (int)(key & 31u);
-    const float fac = have ? qf[i] : 0.f, w = have ? qv[i] : 0.f;
-    const float pvr = __shfl_sync(full, vr, pl), pvg = __shfl_sync(full, vg, pl), pvb = __shfl_sync(full, vb, pl);
-    float g[9];
-    if (have) {
-      const float4 A = sA[t], B = sB[t];
-      blend_grad_terms(A, B, A.x - (px0 + (float)(pl & 15)), A.y - (py0 + (float)(pl >> 4)), fac, w, pvr, pvg, pvb, g);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) g[k] = 0.f;
-    }
-    // segmented suffix sums: equal slots are adjacent, so "the lane `off` further carries my slot" implies that every
-    // lane in between does; a segment is one visit's records, fewer than DENSE_MIN, so log2(DENSE_MIN) steps suffice
-    static_assert((DENSE_MIN & (DENSE_MIN - 1)) == 0, "DENSE_MIN must be a power of two (scan depth)");
-#pragma unroll
-    for (int off = 1; off < DENSE_MIN; off <<= 1) {
-      const uint32_t tk = __shfl_down_sync(full, t, off);
-      const bool same = (lane + off < 32) && tk == t;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const float v = __shfl_down_sync(full, g[k], off);
-        if (same) g[k] += v;
-      }
-    }
-    const uint32_t tprev = __shfl_up_sync(full, t, 1);
-    if (have && (lane == 0 || tprev != t)) {
-#pragma unroll
-      for (int k = 0; k < 9; ++k)
-        if (g[k] != 0.f) atomicAdd(&acc[t][k], g[k]);
-    }
+// ---- fragment-pool kernels (forward and backward) --------------------------------------------------------------------
+// With the reference's 3e-3 initial scale a splat covers a handful of pixels, and the pixel-parallel walk above spends
+// its instructions on alpha tests that fail (forward: 4.5 % hit rate) and on warp reductions in which ~6 of 32 lanes
+// carry a value (ncu, round 1: both kernels issue-bound).  Here the work is split by what it is parallel in:
+//   0. stage: thread t loads Gaussian t of the batch (up to PG per batch), derives its bounding box inside the tile
+//      (conservative extents of the alpha >= 1/255 ellipse, clipped to the tile and the image) and gets a run of pool
+//      slots, one per box pixel, from a block-wide exclusive scan of the box areas (small and tile-sized splats mix
+//      freely; what does not fit into the pool is left to the next batch).  The same scan compacts the Gaussians that
+//      have a box at all; each leaves a 48-byte record (geometry, box, slots) in compacted = depth order;
+//   A. slot-parallel: the S slots of the batch are cut into 256 equal chunks.  A thread finds the Gaussian its chunk
+//      starts in by binary search over the run offsets and walks its chunk in ONE flat loop (moving on to the next
+//      record is a predicated block, so all lanes of all warps run the same trip count): alpha once per box pixel,
+//      stored in the slot, and the Gaussian's bit set in the mask of every pixel that passes the alpha test;
+//   B. pixel-parallel: every pixel walks the set bits of ITS OWN mask in depth order - no alpha test, no warp
+//      collective, only the recurrence that is sequential per pixel (transmittance, colour; backward: colour behind,
+//      dL/dalpha, results written back to the slot);
+//   C. (backward) slot-parallel again, same chunks: a thread accumulates the moments of its slots in registers and
+//      issues one vector atomic triple per Gaussian run it touches: no shared-memory atomics, no warp reductions.
+// Batches of LARGE splats (boxes of PDENSE pixels and more on average: most pixels of the tile pass the alpha test
+// anyway) skip the pool: the pixels walk the batch's records directly, a warp skipping the boxes that miss its two
+// rows (forward: gsplat's loop; backward: the nine-value warp reduction of raster_bwd_kernel per contributing visit).
+// Results: same expressions in the same per-pixel order as the kernels above (the forward is bit-identical); the
+// backward's per-Gaussian sums are added in a different order.
+#ifndef ST3R_POOL_PG
+#define ST3R_POOL_PG 256
+#endif
+#ifndef ST3R_POOL_SLOTS
+#define ST3R_POOL_SLOTS (ST3R_POOL_PG * 16)
+#endif
+#ifndef ST3R_POOL_DENSE
+#define ST3R_POOL_DENSE 96
+#endif
+constexpr int PG = ST3R_POOL_PG;          // Gaussians per batch (one per thread of the first PG threads)
+constexpr int PW = PG / 32;               // mask words per pixel
+constexpr int PSLOTS = ST3R_POOL_SLOTS;   // pool slots per batch (a Gaussian takes at most 256)
+constexpr int PDENSE = ST3R_POOL_DENSE;   // mean box area from which a batch is walked pixel-parallel
+static_assert(PG == 64 || PG == 128 || PG == 256, "pool batch: 64, 128 or 256 Gaussians");
+static_assert(PSLOTS >= 9 * BLOCK && PSLOTS < (1 << 20), "the pool doubles as the dense batches' [BLOCK][9] accumulators");
+
+// Box of tile pixels (rows r0..r1, columns c0..c1, clipped to rmax / cmax) on which opac * exp(-sigma) >= 1/255 is
+// possible; see row_mask for the bound (here with fast intrinsics and a wider safety margin: the box only has to
+// contain the ellipse).  Returns the area (0: cannot contribute); geo = r0 | c0 << 4 | (wc - 1) << 8 | (nr - 1) << 12.
+__device__ __forceinline__ int pool_box(const float4 A, const float4 B, float px0, float py0, int rmax, int cmax,
+                                        uint32_t& geo) {
+  geo = 0;
+  if (!(A.z > ALPHA_MIN)) return 0;                      // opac * exp(-sigma) <= opac < 1/255 (also NaN)
+  int r0 = 0, r1 = rmax, c0 = 0, c1 = cmax;
+  const float det = B.x * B.z - B.y * B.y;
+  if (det > 0.f) {
+#ifdef ST3R_HOST_EMU
+    const float L2 = 2.0f * logf(255.0f * A.z) / det;
+#else
+    const float L2 = __fdividef(2.0f * __logf(255.0f * A.z), det);
+#endif
+    const float hy = sqrtf(L2 * B.x) * 1.001f + 4e-3f;
+    const float hx = sqrtf(L2 * B.z) * 1.001f + 4e-3f;
+    // (NaN / inf extents fall through fmaxf / fminf to the whole tile)
+    r0 = max(0, (int)fmaxf(ceilf(A.y - hy - py0), -1.0f));
+    r1 = min(rmax, (int)fminf(floorf(A.y + hy - py0), (float)TILE));
+    c0 = max(0, (int)fmaxf(ceilf(A.x - hx - px0), -1.0f));
+    c1 = min(cmax, (int)fminf(floorf(A.x + hx - px0), (float)TILE));
   }
-  __syncwarp();                       // the queue may be overwritten from here on
+  if (r1 < r0 || c1 < c0) return 0;
+  const int wc = c1 - c0 + 1, nr = r1 - r0 + 1;
+  geo = (uint32_t)r0 | (uint32_t)c0 << 4 | (uint32_t)(wc - 1) << 8 | (uint32_t)(nr - 1) << 12;
+  return wc * nr;
 }
 
+// One staged batch: Gaussians taken from the sorted list, how many of them have a box (= records), pool slots handed
+// out (0 in a dense batch), whether the batch is walked pixel-parallel, barrier count of the caller's flag.
+struct PoolBatch { int n, nc, S, n_done; bool dense; };
+
+// Shared memory of one CTA.  kBwd: two pool values per slot and the tile's upstream gradients.
+template <bool kBwd>
+struct PoolSmem {
+  // per Gaussian WITH a box, in depth order (compacted): the record a walk loads when it enters the box
+  float4 recA[BLOCK];         // x, y, opacity, pixel-centre x of the box's first column
+  float4 recB[BLOCK];         // conic a, b, c, pixel-centre y of the box's first row
+  int4 recC[BLOCK];           // first slot behind the box | tile pixel of its first slot | wc, t << 5, area << 13,
+                              // r0 << 23, (nr - 1) << 27 | entry id
+  float4 col[BLOCK];          // colour
+  int cbase[BLOCK];           // first pool slot (ascending); INT_MAX behind the last record
+  int2 boxB[BLOCK];           // by batch slot t: pool slot of tile pixel (row, col) = x + row * (y & 31) + col; y >> 8: record
+  uint32_t mask[PW][BLOCK];   // bit t of word w of pixel p: Gaussian 32 w + t contributes to p
+  int scan[BLOCK / 32], take[BLOCK / 32];
+  uint32_t vlist[BLOCK / 32][BLOCK / 32];   // dense batches: bit ci of vlist[w]: record ci touches the rows of warp w
+  float poolA[PSLOTS];        // forward: alpha.  Backward, phase A: alpha; phase B: alpha T.  Dense backward: sums [BLOCK][9]
+  float poolV[kBwd ? PSLOTS : 1];    // backward, phase A: vis (0 when alpha was clamped); phase B: vis dL/dalpha
+  float4 v[kBwd ? BLOCK : 1];        // backward: upstream colour gradient of every pixel of the tile
+};
+
+// Stage one batch (two barriers).  `have`: this thread's slot holds Gaussian e.
+template <bool kBwd>
+__device__ __forceinline__ PoolBatch pool_stage(bool have, uint32_t e, const float4* __restrict__ geomA,
+                                                const float4* __restrict__ geomB, const float4* __restrict__ rgb,
+                                                float px0, float py0, int rmax, int cmax, int done_pred,
+                                                PoolSmem<kBwd>& sm) {
+  const unsigned full = 0xffffffffu;
+  const int tr = threadIdx.x, lane = tr & 31, wrp = tr >> 5;
+  int area = 0;
+  uint32_t geo = 0;
+  float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A, Cc = A;
+  if (have) {
+    A = geomA[e];
+    B = geomB[e];
+    Cc = rgb[e];
+    area = pool_box(A, B, px0, py0, rmax, cmax, geo);
+  }
+  // one scan for both prefixes: slots in the low 20 bits, Gaussians with a box above
+  const int mine = area | (area ? 1 << 20 : 0);
+  int incl = mine;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = (int)__shfl_up_sync(full, (unsigned)incl, off);
+    if (lane >= off) incl += v;
+  }
+  if (lane == 31) sm.scan[wrp] = incl;
+  sm.cbase[tr] = 0x7fffffff;
+#pragma unroll
+  for (int w = 0; w < PW; ++w) sm.mask[w][tr] = 0u;
+  PoolBatch pb;
+  pb.n_done = __syncthreads_count(done_pred);
+  int before = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < BLOCK / 32; ++k) {
+    const int v = sm.scan[k];
+    before += (k < wrp) ? v : 0;
+    total += v;
+  }
+  const int excl = before + incl - mine;
+  const int base = excl & 0xfffff, ci = excl >> 20;
+  // large splats: no pool, every candidate is taken
+  pb.dense = (total & 0xfffff) >= PDENSE * (total >> 20);
+  const bool fits = have && (pb.dense || base + area <= PSLOTS);   // monotone along t: a prefix of the batch is staged
+  if (have && !fits) ST3R_EMU_COUNT(12);                  // Gaussians left to the next batch (pool full)
+  if (!fits) area = 0;
+  const uint32_t staged = __ballot_sync(full, fits);
+  const uint32_t boxed = __ballot_sync(full, area != 0);
+  const int top = __reduce_max_sync(full, fits ? base + area : 0);
+  if (lane == 0) sm.take[wrp] = __popc(staged) | __popc(boxed) << 9 | top << 18;
+  if (area) {
+    const int r0 = (int)(geo & 15u), c0 = (int)((geo >> 4) & 15u), wc = (int)((geo >> 8) & 15u) + 1;
+    sm.boxB[tr] = make_int2(base - r0 * wc - c0, wc | ci << 8);
+    sm.recA[ci] = make_float4(A.x, A.y, A.z, px0 + (float)c0);
+    sm.recB[ci] = make_float4(B.x, B.y, B.z, py0 + (float)r0);
+    sm.recC[ci] = make_int4(base + area, r0 * TILE + c0,
+                            wc | tr << 5 | area << 13 | r0 << 23 | (int)((geo >> 12) & 15u) << 27, (int)e);
+    sm.col[ci] = Cc;
+    sm.cbase[ci] = base;
+  }
+  __syncthreads();
+  pb.n = 0;
+  pb.nc = 0;
+  pb.S = 0;
+#pragma unroll
+  for (int k = 0; k < BLOCK / 32; ++k) {
+    const int v = sm.take[k];
+    pb.n += v & 511;
+    pb.nc += (v >> 9) & 511;
+    pb.S = max(pb.S, v >> 18);
+  }
+  if (pb.dense) pb.S = 0;
+  return pb;
+}
+
+// Candidates of the next batch: all PG while whole batches fit into the pool, else about twice what the pool took.
+__device__ __forceinline__ int pool_next_cand(int cand, int taken) {
+  return taken == cand ? min(PG, 2 * cand) : max(32, min(PG, 2 * taken));
+}
+
+// The chunk [s, s_end) of pool slots of this thread and the record of the Gaussian its first slot is in.
+__device__ __forceinline__ bool pool_chunk(int S, const int* cbase, int& s, int& s_end, int& ci) {
+  const int q = ((S + BLOCK - 1) / BLOCK) | 1;           // odd: the lanes of a warp write their slots to distinct banks
+  s = (int)threadIdx.x * q;
+  s_end = min(S, s + q);
+  if (s >= s_end) return false;
+  ci = 0;                                                 // largest ci with cbase[ci] <= s (cbase[0] = 0)
+#pragma unroll
+  for (int step = BLOCK / 2; step; step >>= 1)
+    if (cbase[ci + step] <= s) ci += step;                // (index <= BLOCK - 1)
+  return true;
+}
+
+// Walk state of one thread inside the box of the Gaussian it is currently in.
+struct PoolWalk {
+  float x, y, opac, qa, qb, qc;
+  float pxc0, pxc, pyr;      // pixel-centre coordinates of the box's first column, the current column, the current row
+  int cc, wc, run_end, pix;  // column inside the box, box width, first slot behind the box, current tile pixel
+  int t, e;                  // batch slot (depth order), entry id
+  // Enter record ci at slot s (s > its first slot only for the first Gaussian of a chunk).
+  template <bool kBwd>
+  __device__ __forceinline__ void enter(const PoolSmem<kBwd>& sm, int ci, int s, bool first) {
+    const float4 ra = sm.recA[ci], rb = sm.recB[ci];
+    const int4 rc = sm.recC[ci];
+    x = ra.x; y = ra.y; opac = ra.z; pxc0 = ra.w;
+    qa = rb.x; qb = rb.y; qc = rb.z; pyr = rb.w;
+    run_end = rc.x;
+    pix = rc.y;
+    wc = rc.z & 31;
+    t = (rc.z >> 5) & 255;
+    e = rc.w;
+    cc = 0;
+    pxc = pxc0;
+    if (first) {
+      const int o = s - (run_end - ((rc.z >> 13) & 1023));
+      if (o) {
+        const int rr = (int)(((float)o + 0.5f) / (float)wc);      // o / wc (o < 256, wc <= 16: far from the rounding edge)
+        cc = o - rr * wc;
+        pxc = pxc0 + (float)cc;
+        pyr += (float)rr;
+        pix += rr * TILE + cc;
+      }
+    }
+  }
+  // Next slot of the same box.
+  __device__ __forceinline__ void step() {
+    pxc += 1.0f;
+    ++pix;
+    if (++cc == wc) { cc = 0; pxc = pxc0; pyr += 1.0f; pix += TILE - wc; }
+  }
+};
+
+// Dense batches: per-warp visit lists (warp w owns tile rows 2 w, 2 w + 1).  Thread ci holds the rows of record ci's box;
+// eight ballots per warp transpose that into vlist[w][word] (bit = record), and each warp walks only its set bits.
+template <bool kBwd>
+__device__ __forceinline__ void pool_visit_lists(PoolSmem<kBwd>& sm, int nc) {
+  const int tr = threadIdx.x;
+  uint32_t m = 0;
+  if (tr < nc) {
+    const int rcz = sm.recC[tr].z;
+    const int w0 = ((rcz >> 23) & 15) >> 1, w1 = (((rcz >> 23) & 15) + ((rcz >> 27) & 15)) >> 1;
+    m = ((2u << w1) - 1u) & ~((1u << w0) - 1u);
+  }
+  uint32_t mine = 0;
+#pragma unroll
+  for (int w = 0; w < BLOCK / 32; ++w) {
+    const uint32_t b = __ballot_sync(0xffffffffu, (m >> w) & 1u);
+    if (lane_id() == w) mine = b;
+  }
+  if (lane_id() < BLOCK / 32) sm.vlist[lane_id()][tr >> 5] = mine;
+  __syncthreads();
+}
+
+#ifdef ST3R_HOST_EMU
+#define POOL_SMEM(kBwd) __shared__ PoolSmem<kBwd> sm
+#else
+#define POOL_SMEM(kBwd)                                 \
+  extern __shared__ __align__(16) char pool_smem_raw[]; \
+  PoolSmem<kBwd>& sm = *reinterpret_cast<PoolSmem<kBwd>*>(pool_smem_raw)
+#endif
+
 __global__ void __launch_bounds__(BLOCK)
-raster_bwd_queue_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
-                        const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
-                        const float4* __restrict__ geomB, const float4* __restrict__ rgb, int C, int W, int H,
-                        int tile_w, int tile_h, const float* __restrict__ alphas, const int32_t* __restrict__ last_ids,
-                        const float* __restrict__ v_render, const float* __restrict__ v_alphas,
-                        float4* __restrict__ v_geomA, float4* __restrict__ v_geomB, float4* __restrict__ v_rgb) {
-  __shared__ float4 sA[BLOCK], sB[BLOCK], sC[BLOCK];
-  __shared__ uint32_t sE[BLOCK];
-  __shared__ uint32_t sL[8][8];
-  __shared__ float acc[BLOCK][9];
-  __shared__ uint32_t qkey[8][QW];
-  __shared__ float qfac[8][QW], qvis[8][QW];
+raster_fwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
+                       const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
+                       const float4* __restrict__ geomB, const float4* __restrict__ rgb, int C, int W, int H, int tile_w,
+                       int tile_h, float* __restrict__ render, float* __restrict__ alphas,
+                       int32_t* __restrict__ last_ids, unsigned long long* __restrict__ n_blend) {
+  POOL_SMEM(false);
   const int c = blockIdx.y, tile = blockIdx.x;
   const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
-  const int tr = threadIdx.x;
-  const int i = tyi * TILE + (tr >> 4), j = txi * TILE + (tr & 15);
-  const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+  const int tr = threadIdx.x, lane = tr & 31, wrp = tr >> 5;
+  const int myrow = tr >> 4, mycol = tr & 15;
+  const int i = tyi * TILE + myrow, j = txi * TILE + mycol;
   const bool inside = i < H && j < W;
-  const int wrp = tr >> 5, lane = tr & 31;
-  const float px0 = (float)(txi * TILE) + 0.5f, py0 = (float)(tyi * TILE + 2 * wrp) + 0.5f;
+  const float px0 = (float)(txi * TILE) + 0.5f, py0 = (float)(tyi * TILE) + 0.5f;   // centre of the tile's first pixel
+  const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+  const int rmax = min(TILE, H - tyi * TILE) - 1, cmax = min(TILE, W - txi * TILE) - 1;
+  bool done = !inside;
   const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
-  if (rg.hi <= rg.lo) return;
-  const size_t p = ((size_t)c * H + min(i, H - 1)) * W + min(j, W - 1);
-  const float T_final = 1.0f - alphas[p];
-  float T = T_final;
-  // The colour accumulated behind the current Gaussian only ever enters dL/dalpha through its dot product with this
-  // pixel's upstream gradient, so ONE running scalar replaces the three colour sums of raster_bwd_kernel:
-  // dL/dalpha = T (c . v) - (behind . v) / (1 - alpha) + T_final v_a / (1 - alpha).
-  float behind_v = 0.f;
-  const int bin_final = inside ? last_ids[p] : 0;
-  float vr = 0.f, vg = 0.f, vb = 0.f, va = 0.f;
-  if (inside) {
-    vr = v_render[3 * p]; vg = v_render[3 * p + 1]; vb = v_render[3 * p + 2];
-    va = v_alphas ? v_alphas[p] : 0.f;
-  }
-  const float tf_va = T_final * va;
-  const int warp_bin_final = __reduce_max_sync(0xffffffffu, bin_final);
-  const uint32_t lanes_below = (1u << lane) - 1u;
-  uint32_t* qk = qkey[wrp];
-  float* qf = qfac[wrp];
-  float* qv = qvis[wrp];
-
-  const int nb = (rg.hi - rg.lo + BLOCK - 1) / BLOCK;
-  for (int b = 0; b < nb; ++b) {
-    __syncthreads();
-    const int batch_end = rg.hi - 1 - BLOCK * b;
-    const int bs = min(BLOCK, batch_end + 1 - rg.lo);
-    const int idx = batch_end - tr;
-    uint32_t m = 0;
-    if (idx >= rg.lo) {
-      uint32_t e = flatten[idx];
-      const float4 A = geomA[e], B = geomB[e];
-      sE[tr] = e;
-      sA[tr] = A;
-      sB[tr] = B;
-      sC[tr] = rgb[e];
-      m = row_mask(A, B, tyi * TILE);
-    }
-    publish_visit_lists(m, sL);
+  float T = 1.0f, pr = 0.f, pg = 0.f, pb_ = 0.f;
+  int cur = 0, blends = 0;
+  int pos = rg.lo, cand = PG;
+  while (pos < rg.hi) {
+    const int idx = pos + tr;
+    const bool have = tr < cand && idx < rg.hi;
+    const uint32_t e = have ? flatten[idx] : 0u;
+    const PoolBatch pb = pool_stage<false>(have, e, geomA, geomB, rgb, px0, py0, rmax, cmax, done, sm);
+    if (pb.n_done == BLOCK) break;
+    if (pb.dense) {
+      // ---- large splats: every pixel walks the records that touch its warp's rows, front to back
+      pool_visit_lists(sm, pb.nc);
+      for (int wi = 0; wi < BLOCK / 32; ++wi) {
+        uint32_t bits = sm.vlist[wrp][wi];
+        if (bits && __all_sync(0xffffffffu, done)) break;
+        while (bits) {
+          const int ci = wi * 32 + __ffs(bits) - 1;
+          bits &= bits - 1;
+          ST3R_EMU_COUNT(13);                               // dense visits (x 32 lanes)
+          if (done) continue;
+          const float4 ra = sm.recA[ci], rb = sm.recB[ci];
+          const float dx = ra.x - px, dy = ra.y - py;
+          const float sigma = blend_sigma(rb.x, rb.y, rb.z, dx, dy);
+          const float alpha = fminf(ALPHA_MAX, ra.z * exp_neg(sigma));
+          if (sigma < 0.f || alpha < ALPHA_MIN) continue;
+          const float nT = T * (1.0f - alpha);
+          if (nT <= T_MIN) { done = true; continue; }
+          const float wgt = alpha * T;
+          const float4 col = sm.col[ci];
+          pr += col.x * wgt; pg += col.y * wgt; pb_ += col.z * wgt;
+          cur = pos + ((sm.recC[ci].z >> 5) & 255);
+          T = nT;
+          ++blends;
+        }
+      }
+    } else {
+      // ---- phase A: alpha of every box pixel, contribution bits
+      int s, s_end, ci;
+      if (pool_chunk(pb.S, sm.cbase, s, s_end, ci)) {
+        PoolWalk wk;
+        wk.enter(sm, ci, s, true);
+        for (;;) {
+          const float dx = wk.x - wk.pxc, dy = wk.y - wk.pyr;
+          const float sigma = blend_sigma(wk.qa, wk.qb, wk.qc, dx, dy);
+          const float alpha = fminf(ALPHA_MAX, wk.opac * exp_neg(sigma));
+          ST3R_EMU_COUNT(10);                               // box pixels tested
+          if (!(sigma < 0.f || alpha < ALPHA_MIN)) {
+            sm.poolA[s] = alpha;
+            atomicOr(&sm.mask[wk.t >> 5][wk.pix], 1u << (wk.t & 31));
+          }
+          if (++s == s_end) break;
+          if (s == wk.run_end) wk.enter(sm, ++ci, s, false);
+          else wk.step();
+        }
+      }
+      __syncthreads();
+      // ---- phase B: the pixel's own contributing Gaussians, front to back
+      if (!done) {
+        uint32_t occ = 0;                     // words of this pixel's mask that hold a bit
 #pragma unroll
-    for (int k = 0; k < 9; ++k) acc[tr][k] = 0.f;
-    __syncthreads();
-    int qlen = 0;                       // warp-uniform
-    const int t0 = max(0, batch_end - warp_bin_final);
-    for (int wi = t0 >> 5; wi < 8; ++wi) {
-      // redux.sync returns the same word in a form the compiler knows to be warp-uniform (see the votes below)
-      uint32_t bits = __reduce_or_sync(0xffffffffu, sL[wrp][wi]);
-      if (wi == (t0 >> 5)) bits &= 0xffffffffu << (t0 & 31);
-      while (bits) {
-        const int t = wi * 32 + __ffs(bits) - 1;
-        bits &= bits - 1;
-        bool valid = inside && (batch_end - t <= bin_final);
-        float alpha = 0.f, opac = 0.f, vis = 0.f, dx = 0.f, dy = 0.f;
-        if (valid) {
-          const float4 A = sA[t], B = sB[t];
-          opac = A.z;
-          dx = A.x - px; dy = A.y - py;
-          const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
-          vis = __expf(-sigma);
-          alpha = fminf(ALPHA_MAX, opac * vis);
-          if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
-        }
-        const uint32_t vm = __ballot_sync(0xffffffffu, valid);
-        ST3R_EMU_COUNT(3);                 // visits (x 32 lanes)
-        if (!vm) continue;
-        ST3R_EMU_COUNT(4);                 // visits with at least one contributing lane (x 32)
-        if (valid) ST3R_EMU_COUNT(5);      // contributing (pixel, Gaussian) pairs
-        float fac = 0.f, w = 0.f;
-        if (valid) {                    // the part that is sequential per pixel
-          // 1 - alpha lies in [1e-3, 1]: rcp.approx (MUFU.RCP, 1 ulp) instead of the 15-instruction IEEE division;
-          // the error is of the size of the forward's own rounding of T
-          float ra;
-#ifdef ST3R_HOST_EMU
-          ra = 1.0f / (1.0f - alpha);
-#else
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(1.0f - alpha));
-#endif
-          T *= ra;
-          fac = alpha * T;
-          const float4 col = sC[t];
-          const float cv = col.x * vr + col.y * vg + col.z * vb;
-          const float v_alpha = T * cv + ra * (tf_va - behind_v);
-          if (opac * vis <= ALPHA_MAX) w = vis * v_alpha;
-          behind_v += fac * cv;
-        }
-        const int nv = __popc(vm);
-        // (the votes only restate warp-uniform conditions in a form the compiler's divergence analysis accepts, so
-        // that the shuffles below are not wrapped in WARPSYNC / ENDCOLLECTIVE pairs)
-        if (__any_sync(0xffffffffu, nv >= DENSE_MIN)) {
-          ST3R_EMU_COUNT(0);
-          float g[9];
-          blend_grad_terms(sA[t], sB[t], dx, dy, fac, w, vr, vg, vb, g);   // fac = w = 0 on the other lanes
-          butterfly9_to_shared(g, acc[t]);
-        } else {
-          if (__any_sync(0xffffffffu, qlen + nv > QW)) {
-            ST3R_EMU_COUNT(1);
-            drain_queue(qlen, qk, qf, qv, sA, sB, acc, vr, vg, vb, px0, py0);
-            qlen = 0;
+        for (int w = 0; w < PW; ++w) occ |= (sm.mask[w][tr] != 0u ? 1u : 0u) << w;
+        uint32_t bits = 0;
+        int w = 0;
+        for (;;) {
+          if (bits == 0u) {
+            if (occ == 0u) break;
+            w = __ffs(occ) - 1;
+            occ &= occ - 1;
+            bits = sm.mask[w][tr];
           }
-          ST3R_EMU_COUNT(2);
-          if (valid) {
-            const int pos = qlen + __popc(vm & lanes_below);
-            qk[pos] = ((uint32_t)t << 5) | (uint32_t)lane;
-            qf[pos] = fac;
-            qv[pos] = w;
-          }
-          qlen += nv;
+          const int t = w * 32 + __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int2 bx = sm.boxB[t];
+          const float alpha = sm.poolA[bx.x + myrow * (bx.y & 31) + mycol];
+          const float nT = T * (1.0f - alpha);
+          if (nT <= T_MIN) { done = true; break; }
+          const float wgt = alpha * T;
+          const float4 col = sm.col[bx.y >> 8];
+          pr += col.x * wgt; pg += col.y * wgt; pb_ += col.z * wgt;
+          cur = pos + t;
+          T = nT;
+          ++blends;
         }
       }
     }
-    drain_queue(qlen, qk, qf, qv, sA, sB, acc, vr, vg, vb, px0, py0);
-    __syncthreads();
-    if (tr < bs) {
-      const uint32_t e = sE[tr];
-      const float* a = acc[tr];
-      if (a[0] != 0.f || a[1] != 0.f || a[2] != 0.f || a[3] != 0.f || a[4] != 0.f || a[5] != 0.f || a[6] != 0.f ||
-          a[7] != 0.f || a[8] != 0.f) {
-        atomicAdd(v_geomA + e, make_float4(a[0], a[1], a[2], 0.f));
-        atomicAdd(v_geomB + e, make_float4(a[3], a[4], a[5], 0.f));
-        atomicAdd(v_rgb + e, make_float4(a[6], a[7], a[8], 0.f));
-      }
-    }
+    pos += pb.n;
+    cand = pool_next_cand(cand, pb.n);
+    __syncthreads();          // the next stage overwrites the records before its first barrier
+  }
+  if (inside) {
+    const size_t p = ((size_t)c * H + i) * W + j;
+    render[3 * p] = pr; render[3 * p + 1] = pg; render[3 * p + 2] = pb_;
+    alphas[p] = 1.0f - T;
+    last_ids[p] = cur;
+  }
+  if (n_blend) {
+    for (int off = 16; off; off >>= 1) blends += __shfl_xor_sync(0xffffffffu, blends, off);
+    if (lane == 0 && blends) atomicAdd(n_blend, (unsigned long long)blends);
   }
 }
 
-// ---- variant 2 of the backward: fragment pool -----------------------------------------------------------------------
-// Measured on the headline workload (scripts/emu_visit_stats.py): a tile sees 386 Gaussians in 842 (warp, Gaussian)
-// visits, every visit evaluates alpha on 32 lanes and 5.6 of them contribute.  Here the alpha test leaves the visits:
-//   A. Gaussian-parallel: four threads per Gaussian walk its bounding box inside the tile (conservative extents of
-//      the alpha >= 1/255 ellipse, ~7 x 7 pixels for a 3e-3 splat), write a 16-bit contribution mask per tile row and
-//      (alpha, vis) of every contributing pixel into the Gaussian's box-addressed slots of a shared-memory pool;
-//   B. pixel-parallel, as before back to front, but a warp only visits Gaussians whose masks touch its two rows and a
-//      lane only reads its slot, runs the per-pixel recurrence (transmittance, colour behind, dL/dalpha) and writes
-//      (alpha T, vis dL/dalpha) back: no alpha test, no gradient arithmetic, no reduction in the visit;
-//   C. Gaussian-parallel again: the four threads of a Gaussian turn its slots into the nine gradient sums in
-//      registers, two shuffles combine them: no atomics at all for these Gaussians.
-// Gaussians whose box has more than FRAG_SLOTS pixels (large splats) keep the dense path of raster_bwd_kernel inside
-// phase B (alpha on the fly, butterfly into the accumulators), in the same back-to-front order.
-constexpr int FG = 64;            // Gaussians per batch
-constexpr int FRAG_SLOTS = 64;    // pool slots per Gaussian = largest bounding box (pixels) that takes the pool path
-
-struct FragBox { uint8_t r0, c0, wc, nr; };    // first row / column of the box inside the tile, its width and height;
-constexpr int FRAG_BIG = 0x80;                  // nr & FRAG_BIG: more than FRAG_SLOTS pixels, dense path
+// Sums of one Gaussian over a set of pixels -> gradient contribution.  m: sum u, u dx, u dy, u dx^2, u dx dy, u dy^2
+// (u = vis dL/dalpha) and sum alpha T v_rgb.  With v_sigma = -opac u:  d/dxy = v_sigma Q d,
+// d/dconic = v_sigma (dx^2 / 2, dx dy, dy^2 / 2),  d/dopac = u.
+__device__ __forceinline__ void pool_emit(const float* m, float opac, float qa, float qb, float qc, int e,
+                                          float4* v_geomA, float4* v_geomB, float4* v_rgb) {
+  const float no = -opac;
+  atomicAdd(v_geomA + e, make_float4(no * (qa * m[1] + qb * m[2]), no * (qb * m[1] + qc * m[2]), m[0], 0.f));
+  atomicAdd(v_geomB + e, make_float4(0.5f * no * m[3], no * m[4], 0.5f * no * m[5], 0.f));
+  atomicAdd(v_rgb + e, make_float4(m[6], m[7], m[8], 0.f));
+}
 
 __global__ void __launch_bounds__(BLOCK)
-raster_bwd_frag_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
+raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
                        const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
-                       const float4* __restrict__ geomB, const float4* __restrict__ rgb, int C, int W, int H,
-                       int tile_w, int tile_h, const float* __restrict__ alphas, const int32_t* __restrict__ last_ids,
+                       const float4* __restrict__ geomB, const float4* __restrict__ rgb, int C, int W, int H, int tile_w,
+                       int tile_h, const float* __restrict__ alphas, const int32_t* __restrict__ last_ids,
                        const float* __restrict__ v_render, const float* __restrict__ v_alphas,
                        float4* __restrict__ v_geomA, float4* __restrict__ v_geomB, float4* __restrict__ v_rgb) {
-  __shared__ float4 sA[FG], sB[FG], sC[FG];
-  __shared__ uint32_t sE[FG];
-  __shared__ uint16_t sMask[FG][TILE];
-  __shared__ FragBox sBox[FG];
-  __shared__ float2 sPool[FG][FRAG_SLOTS];
-  __shared__ float acc[FG][9];
-  __shared__ float4 sV[BLOCK];                 // upstream colour gradient of every pixel of the tile
+  POOL_SMEM(true);
   const int c = blockIdx.y, tile = blockIdx.x;
   const int tyi = tile / tile_w, txi = tile - tyi * tile_w;
-  const int tr = threadIdx.x;
-  const int i = tyi * TILE + (tr >> 4), j = txi * TILE + (tr & 15);
-  const float px = (float)j + 0.5f, py = (float)i + 0.5f;
-  const bool inside = i < H && j < W;
-  const int wrp = tr >> 5, lane = tr & 31;
+  const int tr = threadIdx.x, lane = tr & 31, wrp = tr >> 5;
   const int myrow = tr >> 4, mycol = tr & 15;
-  const float px0 = (float)(txi * TILE) + 0.5f, py0 = (float)(tyi * TILE) + 0.5f;   // centre of the tile's first pixel
+  const int i = tyi * TILE + myrow, j = txi * TILE + mycol;
+  const bool inside = i < H && j < W;
+  const float px0 = (float)(txi * TILE) + 0.5f, py0 = (float)(tyi * TILE) + 0.5f;
+  const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+  const int rmax = min(TILE, H - tyi * TILE) - 1, cmax = min(TILE, W - txi * TILE) - 1;
   const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
   if (rg.hi <= rg.lo) return;
   const size_t p = ((size_t)c * H + min(i, H - 1)) * W + min(j, W - 1);
   const float T_final = 1.0f - alphas[p];
   float T = T_final;
-  float behind_v = 0.f;                        // (colour behind the current Gaussian) . (upstream colour gradient)
-  const int bin_final = inside ? last_ids[p] : 0;
+  float behind_v = 0.f;                      // (colour behind the current Gaussian) . (upstream colour gradient)
+  const int bin_final = inside ? last_ids[p] : -1;
   float vr = 0.f, vg = 0.f, vb = 0.f, va = 0.f;
   if (inside) {
     vr = v_render[3 * p]; vg = v_render[3 * p + 1]; vb = v_render[3 * p + 2];
     va = v_alphas ? v_alphas[p] : 0.f;
   }
-  sV[tr] = make_float4(vr, vg, vb, 0.f);
+  sm.v[tr] = make_float4(vr, vg, vb, 0.f);
   const float tf_va = T_final * va;
-  const int gt = tr >> 2, gq = tr & 3;         // phases A and C: Gaussian slot and quarter of this thread
-
-  const int nb = (rg.hi - rg.lo + FG - 1) / FG;
-  for (int b = 0; b < nb; ++b) {
-    __syncthreads();
-    const int batch_end = rg.hi - 1 - FG * b;
-    const int bs = min(FG, batch_end + 1 - rg.lo);
-    if (tr < FG) {
-      FragBox box = {0, 0, 0, 0};
-      const int idx = batch_end - tr;
-      if (idx >= rg.lo) {
-        const uint32_t e = flatten[idx];
-        const float4 A = geomA[e], B = geomB[e];
-        sE[tr] = e;
-        sA[tr] = A;
-        sB[tr] = B;
-        sC[tr] = rgb[e];
-        // conservative box of the alpha >= 1/255 ellipse (see row_mask): rows r0..r1, columns c0..c1 of the tile
-        const float L = logf(255.0f * A.z);
-        const float det = B.x * B.z - B.y * B.y;
-        int r0 = 0, r1 = -1, c0 = 0, c1 = -1;
-        if (L > 0.f) {
-          if (det > 0.f) {
-            const float hy = sqrtf(2.0f * L * B.x / det) * 1.0005f + 2e-3f;
-            const float hx = sqrtf(2.0f * L * B.z / det) * 1.0005f + 2e-3f;
-            r0 = max(0, (int)fmaxf(ceilf(A.y - hy - py0), -1.0f));
-            r1 = min(TILE - 1, (int)fminf(floorf(A.y + hy - py0), (float)TILE));
-            c0 = max(0, (int)fmaxf(ceilf(A.x - hx - px0), -1.0f));
-            c1 = min(TILE - 1, (int)fminf(floorf(A.x + hx - px0), (float)TILE));
-          } else {
-            r1 = c1 = TILE - 1;               // degenerate conic: whole tile, dense path
-          }
-        }
-        if (r1 >= r0 && c1 >= c0) {
-          const int wc = c1 - c0 + 1, nr = r1 - r0 + 1;
-          box.r0 = (uint8_t)r0; box.c0 = (uint8_t)c0; box.wc = (uint8_t)wc;
-          box.nr = (uint8_t)(nr | ((wc * nr > FRAG_SLOTS || !(det > 0.f)) ? FRAG_BIG : 0));
-        }
+  // nothing behind the last Gaussian any pixel of the tile blended takes part
+  int tile_last = __reduce_max_sync(0xffffffffu, bin_final);
+  if (lane == 0) sm.scan[wrp] = tile_last;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < BLOCK / 32; ++k) tile_last = max(tile_last, sm.scan[k]);
+  __syncthreads();                           // scan[] is reused by the first pool_stage
+  int hi = min(rg.hi - 1, tile_last);        // slot t of a batch holds sorted position hi - t: ascending t = back to front
+  int cand = PG;
+  while (hi >= rg.lo) {
+    const int idx = hi - tr;
+    const bool have = tr < cand && idx >= rg.lo;
+    const uint32_t e = have ? flatten[idx] : 0u;
+    const PoolBatch pb = pool_stage<true>(have, e, geomA, geomB, rgb, px0, py0, rmax, cmax, 0, sm);
+    if (pb.dense) {
+      // ---- large splats: every pixel walks the records back to front; nine-value warp reduction per contributing
+      // visit into shared-memory sums, one vector atomic triple per record at the end
+      float (*acc)[9] = reinterpret_cast<float (*)[9]>(sm.poolA);
+      if (tr < pb.nc) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[tr][k] = 0.f;
       }
-      sBox[tr] = box;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) acc[tr][k] = 0.f;
-    }
-    __syncthreads();
-    // ---- phase A: contribution masks + (alpha, vis) per contributing pixel; thread = (Gaussian gt, rows gq, gq + 4, ..)
-    {
-      const FragBox box = sBox[gt];
-      const float4 A = sA[gt], B = sB[gt];
-      const int nr = box.nr & (FRAG_BIG - 1);
-      for (int r = gq; r < TILE; r += 4) {
-        uint32_t m = 0;
-        if (gt < bs && r >= box.r0 && r < box.r0 + nr) {
-          if (box.nr & FRAG_BIG) {
-            m = ((1u << box.wc) - 1u) << box.c0;                      // conservative: the dense path re-tests alpha
-          } else {
-            const float dy = A.y - (py0 + (float)r);
-            for (int k = 0; k < box.wc; ++k) {
-              const int slot = (r - box.r0) * box.wc + k;
-              const float dx = A.x - (px0 + (float)(box.c0 + k));
-              const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
-              const float vis = __expf(-sigma);
-              const float alpha = fminf(ALPHA_MAX, A.z * vis);
-              ST3R_EMU_COUNT(8);                 // box pixels tested in phase A
-              if (!(sigma < 0.f || alpha < ALPHA_MIN)) {
-                m |= 1u << (box.c0 + k);
-                sPool[gt][slot] = make_float2(alpha, vis);
-              }
-            }
-          }
-        }
-        sMask[gt][r] = (uint16_t)m;
-      }
-    }
-    __syncthreads();
-    // ---- phase B: per-pixel recurrence, back to front; a warp visits the Gaussians whose masks touch its two rows
-    uint32_t hit[FG / 32];
-#pragma unroll
-    for (int h = 0; h < FG / 32; ++h) {
-      const int t = h * 32 + lane;
-      hit[h] = __ballot_sync(0xffffffffu, (sMask[t][2 * wrp] | sMask[t][2 * wrp + 1]) != 0);
-    }
-#pragma unroll
-    for (int h = 0; h < FG / 32; ++h) {
-      uint32_t bits = hit[h];
-      while (bits) {
-        const int t = h * 32 + __ffs(bits) - 1;
-        bits &= bits - 1;
-        const FragBox box = sBox[t];
-        const bool live = inside && (batch_end - t <= bin_final);
-        ST3R_EMU_COUNT(9);                       // phase B visits (x 32 lanes)
-        if (box.nr & FRAG_BIG) {
-          // dense path: alpha on the fly, nine-value butterfly (as raster_bwd_kernel)
-          bool valid = live;
-          float alpha = 0.f, opac = 0.f, vis = 0.f, dx = 0.f, dy = 0.f;
+      pool_visit_lists(sm, pb.nc);          // (its barrier also publishes the zeroed sums)
+      for (int wi = 0; wi < BLOCK / 32; ++wi) {
+        uint32_t bits = sm.vlist[wrp][wi];
+        while (bits) {
+          const int ci = wi * 32 + __ffs(bits) - 1;
+          bits &= bits - 1;
+          const float4 ra = sm.recA[ci], rb = sm.recB[ci];
+          bool valid = hi - ((sm.recC[ci].z >> 5) & 255) <= bin_final;
+          float alpha = 0.f, vis = 0.f;
+          const float dx = ra.x - px, dy = ra.y - py;
           if (valid) {
-            const float4 A = sA[t], B = sB[t];
-            opac = A.z;
-            dx = A.x - px; dy = A.y - py;
-            const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
-            vis = __expf(-sigma);
-            alpha = fminf(ALPHA_MAX, opac * vis);
+            const float sigma = blend_sigma(rb.x, rb.y, rb.z, dx, dy);
+            vis = exp_neg(sigma);
+            alpha = fminf(ALPHA_MAX, ra.z * vis);
             if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
           }
           if (!__any_sync(0xffffffffu, valid)) continue;
-          float fac = 0.f, w = 0.f;
+          ST3R_EMU_COUNT(14);                 // dense backward visits with a contributing lane
+          float fac = 0.f, u = 0.f;
           if (valid) {
-            const float ra = 1.0f / (1.0f - alpha);
+            const float ra_ = fast_rcp(1.0f - alpha);
+            T *= ra_;
+            fac = alpha * T;
+            const float4 col = sm.col[ci];
+            const float cv = col.x * vr + col.y * vg + col.z * vb;
+            const float v_alpha = T * cv + ra_ * (tf_va - behind_v);
+            behind_v += fac * cv;
+            if (ra.z * vis <= ALPHA_MAX) u = vis * v_alpha;
+          }
+          const float ux = u * dx, uy = u * dy;
+          const float g[9] = {u, ux, uy, ux * dx, ux * dy, uy * dy, fac * vr, fac * vg, fac * vb};
+          butterfly9_to_shared(g, acc[ci]);
+        }
+      }
+      __syncthreads();
+      if (tr < pb.nc) {
+        const float* m = acc[tr];
+        if (m[0] != 0.f || m[1] != 0.f || m[2] != 0.f || m[3] != 0.f || m[4] != 0.f || m[5] != 0.f || m[6] != 0.f ||
+            m[7] != 0.f || m[8] != 0.f) {
+          const float4 ra = sm.recA[tr], rb = sm.recB[tr];
+          pool_emit(m, ra.z, rb.x, rb.y, rb.z, sm.recC[tr].w, v_geomA, v_geomB, v_rgb);
+        }
+      }
+    } else {
+      int s0, s_end, ci0;
+      const bool work = pool_chunk(pb.S, sm.cbase, s0, s_end, ci0);
+      // ---- phase A
+      if (work) {
+        int s = s0, ci = ci0;
+        PoolWalk wk;
+        wk.enter(sm, ci, s, true);
+        for (;;) {
+          const float dx = wk.x - wk.pxc, dy = wk.y - wk.pyr;
+          const float sigma = blend_sigma(wk.qa, wk.qb, wk.qc, dx, dy);
+          const float vis = exp_neg(sigma);
+          const float alpha = fminf(ALPHA_MAX, wk.opac * vis);
+          float pa = 0.f, pv = 0.f;           // non-contributing slots read as "nothing" in phase C
+          if (!(sigma < 0.f || alpha < ALPHA_MIN)) {
+            pa = alpha;
+            pv = (wk.opac * vis <= ALPHA_MAX) ? vis : 0.f;
+            atomicOr(&sm.mask[wk.t >> 5][wk.pix], 1u << (wk.t & 31));
+          }
+          sm.poolA[s] = pa;
+          sm.poolV[s] = pv;
+          if (++s == s_end) break;
+          if (s == wk.run_end) wk.enter(sm, ++ci, s, false);
+          else wk.step();
+        }
+      }
+      __syncthreads();
+      // ---- phase B: per-pixel recurrence over the pixel's own contributing Gaussians, back to front
+      {
+        uint32_t occ = 0;
+#pragma unroll
+        for (int w = 0; w < PW; ++w) occ |= (sm.mask[w][tr] != 0u ? 1u : 0u) << w;
+        uint32_t bits = 0;
+        int w = 0;
+        for (;;) {
+          if (bits == 0u) {
+            if (occ == 0u) break;
+            w = __ffs(occ) - 1;
+            occ &= occ - 1;
+            bits = sm.mask[w][tr];
+          }
+          const int t = w * 32 + __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int2 bx = sm.boxB[t];
+          const int slot = bx.x + myrow * (bx.y & 31) + mycol;
+          float fac = 0.f, u = 0.f;           // a Gaussian behind this pixel's last blended one contributes nothing
+          if (hi - t <= bin_final) {
+            const float alpha = sm.poolA[slot];
+            const float ra = fast_rcp(1.0f - alpha);
             T *= ra;
             fac = alpha * T;
-            const float4 col = sC[t];
-            const float cv = col.x * vr + col.y * vg + col.z * vb;
-            const float v_alpha = T * cv + ra * (tf_va - behind_v);
-            if (opac * vis <= ALPHA_MAX) w = vis * v_alpha;
-            behind_v += fac * cv;
-          }
-          float g[9];
-          blend_grad_terms(sA[t], sB[t], dx, dy, fac, w, vr, vg, vb, g);
-          butterfly9_to_shared(g, acc[t]);
-          ST3R_EMU_COUNT(6);
-        } else if ((sMask[t][myrow] >> mycol) & 1u) {
-          const int slot = (myrow - box.r0) * box.wc + (mycol - box.c0);
-          float2 out = make_float2(0.f, 0.f);        // a covered pixel that ignores this Gaussian contributes nothing
-          if (live) {
-            const float2 av = sPool[t][slot];        // (alpha, vis) from phase A
-            const float ra = fast_rcp(1.0f - av.x);
-            T *= ra;
-            const float fac = av.x * T;
-            const float4 col = sC[t];
+            const float4 col = sm.col[bx.y >> 8];
             const float cv = col.x * vr + col.y * vg + col.z * vb;
             const float v_alpha = T * cv + ra * (tf_va - behind_v);
             behind_v += fac * cv;
-            out = make_float2(fac, (sA[t].z * av.y <= ALPHA_MAX) ? av.y * v_alpha : 0.f);
+            u = sm.poolV[slot] * v_alpha;
+            ST3R_EMU_COUNT(11);               // contributing (pixel, Gaussian) pairs
           }
-          sPool[t][slot] = out;
-          ST3R_EMU_COUNT(7);
+          sm.poolA[slot] = fac;
+          sm.poolV[slot] = u;
+        }
+      }
+      __syncthreads();
+      // ---- phase C: the chunk's slots summed per Gaussian run
+      if (work) {
+        int s = s0, ci = ci0;
+        PoolWalk wk;
+        wk.enter(sm, ci, s, true);
+        float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        bool any = false;
+        for (;;) {
+          const float fac = sm.poolA[s], u = sm.poolV[s];
+          if (fac != 0.f || u != 0.f) {
+            const float dx = wk.x - wk.pxc, dy = wk.y - wk.pyr;
+            const float4 v = sm.v[wk.pix];
+            const float ux = u * dx, uy = u * dy;
+            m[0] += u; m[1] += ux; m[2] += uy;
+            m[3] += ux * dx; m[4] += ux * dy; m[5] += uy * dy;
+            m[6] += fac * v.x; m[7] += fac * v.y; m[8] += fac * v.z;
+            any = true;
+          }
+          ++s;
+          if (s == s_end || s == wk.run_end) {
+            if (any) {
+              pool_emit(m, wk.opac, wk.qa, wk.qb, wk.qc, wk.e, v_geomA, v_geomB, v_rgb);
+#pragma unroll
+              for (int k = 0; k < 9; ++k) m[k] = 0.f;
+              any = false;
+            }
+            if (s == s_end) break;
+            wk.enter(sm, ++ci, s, false);
+          } else {
+            wk.step();
+          }
         }
       }
     }
-    __syncthreads();
-    // ---- phase C: the four threads of a Gaussian turn its slots into the nine sums
-    {
-      const FragBox box = sBox[gt];
-      float g9[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) g9[k] = 0.f;
-      if (gt < bs && !(box.nr & FRAG_BIG)) {
-        const float4 A = sA[gt], B = sB[gt];
-        for (int r = box.r0 + gq; r < box.r0 + box.nr; r += 4) {
-          uint32_t m = sMask[gt][r];
-          const float dy = A.y - (py0 + (float)r);
-          while (m) {
-            const int col = __ffs(m) - 1;
-            m &= m - 1;
-            const float2 fw = sPool[gt][(r - box.r0) * box.wc + (col - box.c0)];
-            const float4 v = sV[r * TILE + col];
-            float g[9];
-            blend_grad_terms(A, B, A.x - (px0 + (float)col), dy, fw.x, fw.y, v.x, v.y, v.z, g);
-#pragma unroll
-            for (int k = 0; k < 9; ++k) g9[k] += g[k];
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {               // the four quarter threads are adjacent lanes
-        g9[k] += __shfl_xor_sync(0xffffffffu, g9[k], 1);
-        g9[k] += __shfl_xor_sync(0xffffffffu, g9[k], 2);
-      }
-      if (gq == 0 && gt < bs && !(box.nr & FRAG_BIG)) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) acc[gt][k] += g9[k];
-      }
-    }
-    __syncthreads();
-    if (tr < bs) {
-      const uint32_t e = sE[tr];
-      const float* a = acc[tr];
-      if (a[0] != 0.f || a[1] != 0.f || a[2] != 0.f || a[3] != 0.f || a[4] != 0.f || a[5] != 0.f || a[6] != 0.f ||
-          a[7] != 0.f || a[8] != 0.f) {
-        atomicAdd(v_geomA + e, make_float4(a[0], a[1], a[2], 0.f));
-        atomicAdd(v_geomB + e, make_float4(a[3], a[4], a[5], 0.f));
-        atomicAdd(v_rgb + e, make_float4(a[6], a[7], a[8], 0.f));
-      }
-    }
+    hi -= pb.n;
+    cand = pool_next_cand(cand, pb.n);
+    __syncthreads();                         // the next stage overwrites the records before its first barrier
   }
 }
 
 }  // namespace
 
 #if !defined(ST3R_HOST_EMU) || defined(ST3R_EMU_WHOLE)
-static int g_raster_bwd_variant = 0;   // 0: per-visit butterfly (default), 1: per-warp record queues, 2: fragment pool
-                                       // behind warp visits, 3: fragment-pool kernels (forward and backward)
+static int g_raster_variant = 0;   // 0: fragment-pool kernels (default), 1: visit-list kernels (cross-check, A/B timing)
 
 extern "C" {
 
 int st3r_gs_set_raster_variant(int variant) {
-  ST3R_CHECK_ARG(variant >= 0 && variant <= 3, "st3r_gs_set_raster_variant: unknown variant %d", variant);
-  g_raster_bwd_variant = variant;
+  ST3R_CHECK_ARG(variant == 0 || variant == 1, "st3r_gs_set_raster_variant: unknown variant %d", variant);
+  g_raster_variant = variant;
   return ST3R_OK;
 }
 
@@ -1309,7 +978,10 @@ int st3r_gs_raster_fwd(const int32_t* offsets, const int32_t* n_isect, const uin
                  "st3r_gs_raster_fwd: null pointer");
   const int tile_w = (width + TILE - 1) / TILE, tile_h = (height + TILE - 1) / TILE;
   dim3 grid(tile_w * tile_h, C);
-  if (g_raster_bwd_variant == 3) {
+  const float4 *gA = reinterpret_cast<const float4*>(geomA), *gB = reinterpret_cast<const float4*>(geomB),
+               *gC = reinterpret_cast<const float4*>(rgb);
+  unsigned long long* nb = reinterpret_cast<unsigned long long*>(n_blend);
+  if (g_raster_variant == 0) {
     static PerDeviceOnce once;
     if (!once.done()) {
       ST3R_CHECK_CUDA(cudaFuncSetAttribute(raster_fwd_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1317,14 +989,11 @@ int st3r_gs_raster_fwd(const int32_t* offsets, const int32_t* n_isect, const uin
       once.mark();
     }
     raster_fwd_pool_kernel<<<grid, BLOCK, sizeof(PoolSmem<false>), stream>>>(
-        offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
-        reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, render, alphas, last_ids,
-        reinterpret_cast<unsigned long long*>(n_blend));
-  } else
-    raster_fwd_kernel<<<grid, BLOCK, 0, stream>>>(
-        offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
-        reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, render, alphas, last_ids,
-        reinterpret_cast<unsigned long long*>(n_blend));
+        offsets, n_isect, flatten_ids, gA, gB, gC, C, width, height, tile_w, tile_h, render, alphas, last_ids, nb);
+  } else {
+    raster_fwd_kernel<<<grid, BLOCK, 0, stream>>>(offsets, n_isect, flatten_ids, gA, gB, gC, C, width, height, tile_w,
+                                                  tile_h, render, alphas, last_ids, nb);
+  }
   ST3R_CHECK_LAUNCH();
   return ST3R_OK;
 }
@@ -1341,7 +1010,11 @@ int st3r_gs_raster_bwd(const int32_t* offsets, const int32_t* n_isect, const uin
                  "st3r_gs_raster_bwd: null pointer");
   const int tile_w = (width + TILE - 1) / TILE, tile_h = (height + TILE - 1) / TILE;
   dim3 grid(tile_w * tile_h, C);
-  if (g_raster_bwd_variant == 3) {
+  const float4 *gA = reinterpret_cast<const float4*>(geomA), *gB = reinterpret_cast<const float4*>(geomB),
+               *gC = reinterpret_cast<const float4*>(rgb);
+  float4 *vA = reinterpret_cast<float4*>(v_geomA), *vB = reinterpret_cast<float4*>(v_geomB),
+         *vC = reinterpret_cast<float4*>(v_rgb);
+  if (g_raster_variant == 0) {
     static PerDeviceOnce once;
     if (!once.done()) {
       ST3R_CHECK_CUDA(cudaFuncSetAttribute(raster_bwd_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1349,24 +1022,12 @@ int st3r_gs_raster_bwd(const int32_t* offsets, const int32_t* n_isect, const uin
       once.mark();
     }
     raster_bwd_pool_kernel<<<grid, BLOCK, sizeof(PoolSmem<true>), stream>>>(
-        offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
-        reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, alphas, last_ids, v_render, v_alphas,
-        reinterpret_cast<float4*>(v_geomA), reinterpret_cast<float4*>(v_geomB), reinterpret_cast<float4*>(v_rgb));
-  } else if (g_raster_bwd_variant == 2)
-    raster_bwd_frag_kernel<<<grid, BLOCK, 0, stream>>>(
-        offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
-        reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, alphas, last_ids, v_render, v_alphas,
-        reinterpret_cast<float4*>(v_geomA), reinterpret_cast<float4*>(v_geomB), reinterpret_cast<float4*>(v_rgb));
-  else if (g_raster_bwd_variant == 1)
-    raster_bwd_queue_kernel<<<grid, BLOCK, 0, stream>>>(
-        offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
-        reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, alphas, last_ids, v_render, v_alphas,
-        reinterpret_cast<float4*>(v_geomA), reinterpret_cast<float4*>(v_geomB), reinterpret_cast<float4*>(v_rgb));
-  else
-    raster_bwd_kernel<<<grid, BLOCK, 0, stream>>>(
-        offsets, n_isect, flatten_ids, reinterpret_cast<const float4*>(geomA), reinterpret_cast<const float4*>(geomB),
-        reinterpret_cast<const float4*>(rgb), C, width, height, tile_w, tile_h, alphas, last_ids, v_render, v_alphas,
-        reinterpret_cast<float4*>(v_geomA), reinterpret_cast<float4*>(v_geomB), reinterpret_cast<float4*>(v_rgb));
+        offsets, n_isect, flatten_ids, gA, gB, gC, C, width, height, tile_w, tile_h, alphas, last_ids, v_render, v_alphas,
+        vA, vB, vC);
+  } else {
+    raster_bwd_kernel<<<grid, BLOCK, 0, stream>>>(offsets, n_isect, flatten_ids, gA, gB, gC, C, width, height, tile_w,
+                                                  tile_h, alphas, last_ids, v_render, v_alphas, vA, vB, vC);
+  }
   ST3R_CHECK_LAUNCH();
   return ST3R_OK;
 }

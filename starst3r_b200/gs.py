@@ -23,10 +23,9 @@ TILE = 16
 # st3r_gs_isect -> st3r_radix_sort_pairs -> st3r_gs_offsets chain.  Both produce identical arrays.
 BINNING = "fused"
 EPS2D, NEAR, FAR, RADIUS_CLIP = 0.3, 0.01, 1e10, 0.0
-# Variant of the blend backward kernel (st3r_gs_set_raster_variant): 0 = per-visit warp reduction (every committed
-# measurement), 1 = per-warp record queues, 2 = fragment pool (both written without GPU time, DESIGN.md §10;
-# tests/test_experimental_gpu.py, tests/test_raster_emu_host.py).
-RASTER_BWD_VARIANT = int(os.environ.get("ST3R_RASTER_VARIANT", "0"))
+# Implementation of the blend kernels (st3r_gs_set_raster_variant): 0 = fragment-pool kernels (default), 1 = visit-list
+# kernels (the first implementation, kept as an independent cross-check; tests/test_gs_gpu.py compares the two).
+RASTER_VARIANT = int(os.environ.get("ST3R_RASTER_VARIANT", "0"))
 # run_3dgs_optim under a torch.distributed process group: shard the views over the ranks (splat replicated, gradients
 # summed over NVLink peer memory / NCCL).  Opt-in until it has run on a multi-GPU box (bench.py and
 # tests/test_dist_gpu.py drive the same train_step + PeerGradExchange combination by hand).
@@ -271,7 +270,7 @@ def _forward(means, quats, scales, opacities, shN, cams, width, height, count_bl
             with _Prof("st3r_gs_offsets"):
                 _lib.check(lib.st3r_gs_offsets(_lib.ptr(fr.keys), _lib.ptr(n_dev), n_cap, C, fr.W, fr.H, TILE,
                                                _lib.ptr(fr.offsets), st), "st3r_gs_offsets")
-        _lib.check(lib.st3r_gs_set_raster_variant(int(RASTER_BWD_VARIANT)), "st3r_gs_set_raster_variant")
+        _lib.check(lib.st3r_gs_set_raster_variant(int(RASTER_VARIANT)), "st3r_gs_set_raster_variant")
         with _Prof("st3r_gs_raster_fwd"):
             _lib.check(lib.st3r_gs_raster_fwd(_lib.ptr(fr.offsets), _lib.ptr(n_dev), _lib.ptr(fr.vals),
                                               _lib.ptr(fr.geomA), _lib.ptr(fr.geomB), _lib.ptr(fr.rgb), C, fr.W, fr.H, TILE,
@@ -299,7 +298,7 @@ def _backward(fr, means, quats, scales, opacities, shN, v_render, v_alphas, reg_
         v_opac = torch.empty((N,), dtype=torch.float32, device=dev)
         v_sh = torch.empty((N, 4, 3), dtype=torch.float32, device=dev)
     st = _lib.stream_ptr()
-    _lib.check(lib.st3r_gs_set_raster_variant(int(RASTER_BWD_VARIANT)), "st3r_gs_set_raster_variant")
+    _lib.check(lib.st3r_gs_set_raster_variant(int(RASTER_VARIANT)), "st3r_gs_set_raster_variant")
     with torch.cuda.device(dev):
         with _Prof("st3r_gs_raster_bwd"):
             _lib.check(lib.st3r_gs_raster_bwd(_lib.ptr(fr.offsets), _lib.ptr(fr.n_isect_dev), _lib.ptr(fr.vals),

@@ -1,4 +1,4 @@
-// TEST-ONLY: the blend kernels of starst3r_b200/csrc/gs_raster.cu (forward, default backward, record-queue backward)
+// TEST-ONLY: the blend kernels of starst3r_b200/csrc/gs_raster.cu (fragment-pool pair and visit-list pair)
 // compiled for the host and executed thread by thread by the SIMT emulator in simt_emu.h, so that the CPU test-suite
 // runs the kernels' own source - indexing, visit lists, queues, segmented scans, barriers - against the oracle.
 // Never linked into the product library.
@@ -33,45 +33,31 @@ void emu_counts(long* out16, int reset) {
   for (int i = 0; i < 16; ++i) { out16[i] = g_emu_count[i]; if (reset) g_emu_count[i] = 0; }
 }
 
-int emu_raster_fwd(const int32_t* offsets, const int32_t* n_isect, const uint32_t* flatten, const float* geomA,
+// variant 0: fragment-pool kernels (default), 1: visit-list kernels
+int emu_raster_fwd(int variant, const int32_t* offsets, const int32_t* n_isect, const uint32_t* flatten, const float* geomA,
                    const float* geomB, const float* rgb, int C, int W, int H, float* render, float* alphas,
                    int32_t* last_ids, unsigned long long* n_blend) {
   const int tile_w = (W + TILE - 1) / TILE, tile_h = (H + TILE - 1) / TILE;
   return run_grid(tile_w * tile_h, C, [&]() {
-    raster_fwd_kernel(offsets, n_isect, flatten, (const float4*)geomA, (const float4*)geomB, (const float4*)rgb, C, W, H,
-                      tile_w, tile_h, render, alphas, last_ids, n_blend);
+    if (variant == 0)
+      raster_fwd_pool_kernel(offsets, n_isect, flatten, (const float4*)geomA, (const float4*)geomB, (const float4*)rgb, C,
+                             W, H, tile_w, tile_h, render, alphas, last_ids, n_blend);
+    else
+      raster_fwd_kernel(offsets, n_isect, flatten, (const float4*)geomA, (const float4*)geomB, (const float4*)rgb, C, W, H,
+                        tile_w, tile_h, render, alphas, last_ids, n_blend);
   });
 }
 
-int emu_raster_fwd_pool(const int32_t* offsets, const int32_t* n_isect, const uint32_t* flatten, const float* geomA,
-                        const float* geomB, const float* rgb, int C, int W, int H, float* render, float* alphas,
-                        int32_t* last_ids, unsigned long long* n_blend) {
-  const int tile_w = (W + TILE - 1) / TILE, tile_h = (H + TILE - 1) / TILE;
-  return run_grid(tile_w * tile_h, C, [&]() {
-    raster_fwd_pool_kernel(offsets, n_isect, flatten, (const float4*)geomA, (const float4*)geomB, (const float4*)rgb, C, W,
-                           H, tile_w, tile_h, render, alphas, last_ids, n_blend);
-  });
-}
-
-// variant 3: raster_bwd_pool_kernel; variant 0: raster_bwd_kernel, 1: raster_bwd_queue_kernel, 2: raster_bwd_frag_kernel
 int emu_raster_bwd(int variant, const int32_t* offsets, const int32_t* n_isect, const uint32_t* flatten,
                    const float* geomA, const float* geomB, const float* rgb, int C, int W, int H, const float* alphas,
                    const int32_t* last_ids, const float* v_render, const float* v_alphas, float* v_geomA, float* v_geomB,
                    float* v_rgb) {
   const int tile_w = (W + TILE - 1) / TILE, tile_h = (H + TILE - 1) / TILE;
   return run_grid(tile_w * tile_h, C, [&]() {
-    if (variant == 3)
+    if (variant == 0)
       raster_bwd_pool_kernel(offsets, n_isect, flatten, (const float4*)geomA, (const float4*)geomB, (const float4*)rgb, C,
                              W, H, tile_w, tile_h, alphas, last_ids, v_render, v_alphas, (float4*)v_geomA,
                              (float4*)v_geomB, (float4*)v_rgb);
-    else if (variant == 2)
-      raster_bwd_frag_kernel(offsets, n_isect, flatten, (const float4*)geomA, (const float4*)geomB, (const float4*)rgb, C,
-                             W, H, tile_w, tile_h, alphas, last_ids, v_render, v_alphas, (float4*)v_geomA,
-                             (float4*)v_geomB, (float4*)v_rgb);
-    else if (variant == 1)
-      raster_bwd_queue_kernel(offsets, n_isect, flatten, (const float4*)geomA, (const float4*)geomB, (const float4*)rgb, C,
-                              W, H, tile_w, tile_h, alphas, last_ids, v_render, v_alphas, (float4*)v_geomA,
-                              (float4*)v_geomB, (float4*)v_rgb);
     else
       raster_bwd_kernel(offsets, n_isect, flatten, (const float4*)geomA, (const float4*)geomB, (const float4*)rgb, C, W, H,
                         tile_w, tile_h, alphas, last_ids, v_render, v_alphas, (float4*)v_geomA, (float4*)v_geomB,

@@ -125,54 +125,6 @@ def test_split_identical_and_resolves_rarely_on_smooth_fields(cuda_device):
         lib.st3r_nn_tc_set_split(0)
 
 
-# ---- queue variant of the blend backward (st3r_gs_set_raster_variant, gs.RASTER_BWD_VARIANT) -------------------
-@pytest.fixture(params=[1, 2, 3], ids=["queue", "fragment-pool", "pool-kernels"])
-def raster_queue(request, monkeypatch):
-    from starst3r_b200 import gs
-    monkeypatch.setattr(gs, "RASTER_BWD_VARIANT", request.param)
-    yield
-    from starst3r_b200 import _lib
-    _lib.load().st3r_gs_set_raster_variant(0)
-
-
-def test_raster_queue_backward_vs_autograd(cuda_device, raster_queue):
-    import test_gs_gpu as t
-    t.test_rasterization_backward_vs_autograd(cuda_device)
-    t.test_train_steps_vs_oracle(cuda_device)
-    t.test_train_plan_matches_unplanned(cuda_device)
-
-
-@pytest.mark.parametrize("scale_mult", [1.0, 8.0, 40.0])
-def test_raster_queue_equals_default_gradients(cuda_device, scale_mult):
-    """Both variants on the same frame, from splats a fraction of a pixel wide (every visit goes through the queues)
-    to splats that cover whole tiles (every visit takes the dense path): gradients agree to fp32 summation order."""
-    import torch
-    from starst3r_b200 import gs, synth
-    sp = synth.random_splats(20_000, seed=4)
-    sp["scales"] = sp["scales"] * scale_mult
-    viewmats, Ks = synth.look_at_cameras(3, 200, 136)
-    dev = cuda_device
-    args = [sp[k].to(dev) for k in ("means", "quats", "scales", "opacities", "shN")]
-    g = torch.Generator().manual_seed(1)
-    v_render = torch.randn(3, 136, 200, 3, generator=g).to(dev)
-    v_alpha = torch.randn(3, 136, 200, 1, generator=g).to(dev)
-    grads = {}
-    for variant in (0, 1, 2, 3):
-        gs.RASTER_BWD_VARIANT = variant
-        try:
-            leaves = [a.clone().requires_grad_(True) for a in args]
-            render, alpha, _ = gs.rasterization(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], viewmats.to(dev),
-                                                Ks.to(dev), 200, 136, sh_degree=1)
-            ((render * v_render).sum() + (alpha * v_alpha).sum()).backward()
-            grads[variant] = [x.grad.clone() for x in leaves]
-        finally:
-            gs.RASTER_BWD_VARIANT = 0
-    for variant in (1, 2, 3):
-        for a, b in zip(grads[0], grads[variant]):
-            assert torch.isfinite(b).all()
-            assert (a - b).abs().max().item() <= 2e-4 * max(a.abs().max().item(), 1e-12), variant
-
-
 # ---- Scene.run_3dgs_optim with sharded views (gs.SHARD_VIEWS), 2 GPUs ------------------------------------------
 def _shard_views_worker(rank, world, port, out_dir):
     import sys

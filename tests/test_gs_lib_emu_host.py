@@ -4,7 +4,7 @@ tests/host/build_emu_lib.py - kernel launches rewritten onto the SIMT emulator -
 Python glue (starst3r_b200.gs) on CPU tensors.  The glue refuses anything but CUDA by design, so this test (and only the
 test) swaps the library handle, the stream getter and torch.cuda.device for host stand-ins.  The checks are the ones
 tests/test_gs_gpu.py makes on the B200 against the oracle: bin indices bit-exact, RGB / alpha, gradients vs autograd,
-loss, Adam, whole training steps - for the default blend backward and for the two opt-in variants."""
+loss, Adam, whole training steps - for both blend kernel pairs (fragment-pool, visit-list)."""
 import pytest
 import torch
 
@@ -16,10 +16,10 @@ def backend(emu_backend):
     return emu_backend
 
 
-@pytest.fixture(params=[0, 1, 2, 3], ids=["default-bwd", "queue-bwd", "fragment-pool-bwd", "pool-kernels"])
+@pytest.fixture(params=[0, 1], ids=["pool-kernels", "visit-list-kernels"])
 def backend_bwd(request, emu_backend, monkeypatch):
     from starst3r_b200 import gs
-    monkeypatch.setattr(gs, "RASTER_BWD_VARIANT", request.param)
+    monkeypatch.setattr(gs, "RASTER_VARIANT", request.param)
     yield emu_backend
     emu_backend.st3r_gs_set_raster_variant(0)
 

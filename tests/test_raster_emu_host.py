@@ -1,9 +1,10 @@
-"""CPU: the blend kernels' OWN SOURCE (starst3r_b200/csrc/gs_raster.cu: raster_fwd_kernel, raster_bwd_kernel and the
-record-queue variant raster_bwd_queue_kernel) compiled for the host and executed thread by thread by a small SIMT
-emulator (tests/host/simt_emu.h: fibers, rendezvous semantics for __syncthreads / shuffles / votes / redux, deadlock
-detection), against a direct float64 evaluation of gsplat's rasterize_to_pixels forward / backward (SURVEY Appendix
-A.6).  This runs the code the GPU will run - indexing, visit lists, queue appends, drains, segmented scans, the dense
-bypass, barriers - without a GPU; what it cannot show is timing and memory-model behaviour."""
+"""CPU: the blend kernels' OWN SOURCE (starst3r_b200/csrc/gs_raster.cu: the fragment-pool pair raster_fwd_pool_kernel /
+raster_bwd_pool_kernel that the library launches, and the visit-list pair raster_fwd_kernel / raster_bwd_kernel kept as
+cross-check) compiled for the host and executed thread by thread by a small SIMT emulator (tests/host/simt_emu.h:
+fibers, rendezvous semantics for __syncthreads / shuffles / votes / redux, deadlock detection), against a direct float64
+evaluation of gsplat's rasterize_to_pixels forward / backward.  This runs the code the GPU will
+run - indexing, scans, compaction, slot walks, masks, dense batches, barriers - without a GPU; what it cannot show is
+timing and memory-model behaviour."""
 import ctypes
 import os
 import subprocess
@@ -11,10 +12,33 @@ import subprocess
 import numpy as np
 import pytest
 
-from test_raster_queue_host import ALPHA_MAX, ALPHA_MIN, T_MIN, contribution, grad_terms
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TILE = 16
+ALPHA_MIN, ALPHA_MAX, T_MIN = 1.0 / 255.0, 0.999, 1e-4
+POOL, VISIT = 0, 1          # st3r_gs_set_raster_variant values
+
+
+def contribution(px, py, Ak, Bk, colk, T, buf, T_final, v_rgb, v_a):
+    """Backward step for one (pixel, Gaussian), back to front: returns None or (alpha T, vis dL/dalpha, new T, new buf)."""
+    dx, dy = Ak[0] - px, Ak[1] - py
+    sigma = 0.5 * (Bk[0] * dx * dx + Bk[2] * dy * dy) + Bk[1] * dx * dy
+    vis = np.exp(-sigma)
+    alpha = min(ALPHA_MAX, Ak[2] * vis)
+    if sigma < 0 or alpha < ALPHA_MIN:
+        return None
+    ra = 1.0 / (1.0 - alpha)
+    T = T * ra
+    fac = alpha * T
+    v_alpha = float(((colk * T - buf * ra) * v_rgb).sum() + T_final * ra * v_a)
+    w = vis * v_alpha if Ak[2] * vis <= ALPHA_MAX else 0.0
+    return fac, w, T, buf + colk * fac
+
+
+def grad_terms(Ak, Bk, dx, dy, fac, w, v_rgb):
+    """d/d(x, y, opacity), d/d(conic a, b, c), d/d(rgb) of one (pixel, Gaussian) contribution."""
+    vs = -Ak[2] * w
+    return np.array([vs * (Bk[0] * dx + Bk[1] * dy), vs * (Bk[1] * dx + Bk[2] * dy), w, 0.5 * vs * dx * dx,
+                     vs * dx * dy, 0.5 * vs * dy * dy, fac * v_rgb[0], fac * v_rgb[1], fac * v_rgb[2]])
 
 
 @pytest.fixture(scope="module")
@@ -29,7 +53,7 @@ def P(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def make_frame(n, C, W, H, sigma_small, sigma_large, seed):
+def make_frame(n, C, W, H, sigma_small, sigma_large, seed, big_frac=0.15):
     """Entries e = c * n + g with random 2-D Gaussians; per (camera, tile) lists sorted by depth."""
     rng = np.random.default_rng(seed)
     E = C * n
@@ -40,7 +64,7 @@ def make_frame(n, C, W, H, sigma_small, sigma_large, seed):
     A[:, 1] = rng.uniform(-4, H + 4, E)
     A[:, 2] = rng.uniform(0.05, 0.7, E)
     A[:, 3] = rng.uniform(1, 10, E)
-    big = rng.random(E) < 0.15
+    big = rng.random(E) < big_frac
     s = np.where(big[:, None], sigma_large, sigma_small) * np.exp(0.3 * rng.standard_normal((E, 2)))
     rho = rng.uniform(-0.5, 0.5, E)
     cov = np.stack([s[:, 0] ** 2, rho * s[:, 0] * s[:, 1], s[:, 1] ** 2], 1)
@@ -100,70 +124,82 @@ def reference(A, B, col, offsets, n_isect, flatten, tw, th, C, W, H, v_render, v
     return render, alphas, g
 
 
-@pytest.mark.parametrize("n,C,W,H,ss,sl,seed", [(420, 2, 40, 24, 0.8, 5.0, 0), (700, 1, 24, 24, 0.7, 3.0, 1)])
-def test_blend_kernels_on_the_simt_emulator(emu, n, C, W, H, ss, sl, seed):
-    A, B, col, offsets, n_isect, flatten, tw, th = make_frame(n, C, W, H, ss, sl, seed)
-    per_tile = np.diff(np.r_[offsets, n_isect])
-    assert per_tile.max() > 256 or n < 500            # the larger case walks more than one 256-Gaussian batch per tile
-    rng = np.random.default_rng(seed + 10)
-    v_render = rng.standard_normal((C, H, W, 3)).astype(np.float32)
-    v_alphas = rng.standard_normal((C, H, W)).astype(np.float32)
+def run_fwd(emu, variant, frame, C, W, H):
+    A, B, col, offsets, n_isect, flatten, tw, th = frame
     render = np.zeros((C, H, W, 3), np.float32)
     alphas = np.zeros((C, H, W), np.float32)
     last_ids = np.zeros((C, H, W), np.int32)
     n_blend = np.zeros(1, np.uint64)
-    rc = emu.emu_raster_fwd(P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), C, W, H, P(render), P(alphas),
+    rc = emu.emu_raster_fwd(variant, P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), C, W, H, P(render), P(alphas),
                             P(last_ids), P(n_blend))
-    assert rc == 0, "deadlock in raster_fwd_kernel"
-    want_render, want_alphas, want_g = reference(A, B, col, offsets, n_isect, flatten, tw, th, C, W, H, v_render, v_alphas)
-    assert np.abs(render - want_render).max() < 2e-5 and np.abs(alphas - want_alphas).max() < 2e-5
-    assert int(n_blend[0]) > 5 * C * H * W
-    # the fragment-pool forward: same per-pixel arithmetic in the same order => identical outputs, bit for bit
-    render2, alphas2 = np.zeros_like(render), np.zeros_like(alphas)
-    last2, n_blend2 = np.zeros_like(last_ids), np.zeros(1, np.uint64)
-    rc = emu.emu_raster_fwd_pool(P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), C, W, H, P(render2), P(alphas2),
-                                 P(last2), P(n_blend2))
-    assert rc == 0, "deadlock in raster_fwd_pool_kernel"
-    assert np.array_equal(render, render2) and np.array_equal(alphas, alphas2) and np.array_equal(last_ids, last2)
-    assert n_blend[0] == n_blend2[0]
-    scale = np.abs(want_g).max(0) + 1e-12
-    got = {}
-    for variant in (0, 1, 2, 3):
-        vA = np.zeros_like(A)
-        vB = np.zeros_like(B)
-        vC = np.zeros_like(col)
-        rc = emu.emu_raster_bwd(variant, P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), C, W, H, P(alphas),
-                                P(last_ids), P(v_render), P(v_alphas), P(vA), P(vB), P(vC))
-        assert rc == 0, f"deadlock in the backward kernel, variant {variant}"
-        g = np.concatenate([vA[:, :3], vB[:, :3], vC[:, :3]], axis=1)
-        got[variant] = g
-        err = np.abs(g - want_g).max(0) / scale
-        assert err.max() < 2e-4, (variant, err)       # fp32 kernels (and fp32 forward state) vs the float64 evaluation
-        assert np.all(vA[:, 3] == 0) and np.all(vB[:, 3] == 0) and np.all(vC[:, 3] == 0)
-    assert (np.abs(got[0] - got[1]).max(0) / scale).max() < 1e-4
-    assert (np.abs(got[0] - got[2]).max(0) / scale).max() < 1e-4
-    assert (np.abs(got[0] - got[3]).max(0) / scale).max() < 1e-4
-    # path coverage of the queue kernel in this run (per-lane hits): dense bypass, mid-batch overflow drain, appends
+    assert rc == 0, f"deadlock in the forward kernel, variant {variant}"
+    return render, alphas, last_ids, int(n_blend[0])
+
+
+def run_bwd(emu, variant, frame, C, W, H, alphas, last_ids, v_render, v_alphas):
+    A, B, col, offsets, n_isect, flatten, tw, th = frame
+    vA, vB, vC = np.zeros_like(A), np.zeros_like(B), np.zeros_like(col)
+    rc = emu.emu_raster_bwd(variant, P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), C, W, H, P(alphas),
+                            P(last_ids), P(v_render), P(v_alphas), P(vA), P(vB), P(vC))
+    assert rc == 0, f"deadlock in the backward kernel, variant {variant}"
+    assert np.all(vA[:, 3] == 0) and np.all(vB[:, 3] == 0) and np.all(vC[:, 3] == 0)
+    return np.concatenate([vA[:, :3], vB[:, :3], vC[:, :3]], axis=1)
+
+
+# small splats + 15 % tile-sized ones (pool batches, pool overflow); mostly tile-sized ones (dense batches); > 256 per tile
+@pytest.mark.parametrize("n,C,W,H,ss,sl,big,seed", [(420, 2, 40, 24, 0.8, 5.0, 0.15, 0), (700, 1, 24, 24, 0.7, 3.0, 0.15, 1),
+                                                    (300, 1, 40, 24, 0.8, 7.0, 0.9, 2)])
+def test_blend_kernels_on_the_simt_emulator(emu, n, C, W, H, ss, sl, big, seed):
+    frame = make_frame(n, C, W, H, ss, sl, seed, big)
+    A, B, col, offsets, n_isect, flatten, tw, th = frame
+    per_tile = np.diff(np.r_[offsets, n_isect])
+    rng = np.random.default_rng(seed + 10)
+    v_render = rng.standard_normal((C, H, W, 3)).astype(np.float32)
+    v_alphas = rng.standard_normal((C, H, W)).astype(np.float32)
     counts = (ctypes.c_long * 16)()
     emu.emu_counts(counts, 1)
-    assert counts[0] > 0 and counts[2] > 0, list(counts)
-    assert counts[6] > 0 and counts[7] > 0, list(counts)     # fragment-pool variant: dense visits and pool slots
-    if per_tile.max() > 256:
-        assert counts[1] > 0, list(counts)
-    # fragment-pool kernels: box pixels tested, contributions, and Gaussians deferred because the pool was full
-    assert counts[10] > 0 and counts[11] > 0 and counts[12] > 0, list(counts)
+    render, alphas, last_ids, n_blend = run_fwd(emu, POOL, frame, C, W, H)
+    want_render, want_alphas, want_g = reference(A, B, col, offsets, n_isect, flatten, tw, th, C, W, H, v_render, v_alphas)
+    assert np.abs(render - want_render).max() < 2e-5 and np.abs(alphas - want_alphas).max() < 2e-5
+    assert n_blend > 5 * C * H * W
+    # the visit-list forward: same per-pixel arithmetic in the same order => identical outputs, bit for bit
+    render2, alphas2, last2, n_blend2 = run_fwd(emu, VISIT, frame, C, W, H)
+    assert np.array_equal(render, render2) and np.array_equal(alphas, alphas2) and np.array_equal(last_ids, last2)
+    assert n_blend == n_blend2
+    scale = np.abs(want_g).max(0) + 1e-12
+    got = {}
+    for variant in (POOL, VISIT):
+        g = run_bwd(emu, variant, frame, C, W, H, alphas, last_ids, v_render, v_alphas)
+        got[variant] = g
+        err = np.abs(g - want_g).max(0) / scale
+        # fp32 kernels (and fp32 forward state: long per-pixel chains under tile-sized splats) vs the float64 evaluation;
+        # both kernel pairs show the same deviation to three digits
+        assert err.max() < 5e-4, (variant, err)
+    assert (np.abs(got[POOL] - got[VISIT]).max(0) / scale).max() < 1e-4
+    # path coverage of the fragment-pool kernels in this run (per-lane hits)
+    emu.emu_counts(counts, 1)
+    if big < 0.5:
+        # box pixels tested, contributions, Gaussians deferred because the pool was full
+        assert counts[10] > 0 and counts[11] > 0 and counts[12] > 0, list(counts)
+    else:
+        assert counts[13] > 0 and counts[14] > 0, list(counts)    # dense batches, forward and backward
+    if n >= 700:
+        assert per_tile.max() > 256                  # more than one batch per tile
 
 
-def test_backward_variants_agree_on_edge_shapes(emu):
-    """Randomised sweep over the shapes that stress the bookkeeping: one Gaussian, list lengths around the batch sizes
-    (64 / 128 / 256 +- 1), images smaller than a tile and ragged ones, near-opaque splats (early termination, alpha
-    clamp) and almost transparent ones: the three backward kernels agree and none of them deadlocks."""
+def test_blend_kernel_pairs_agree_on_edge_shapes(emu):
+    """Randomised sweep over the shapes that stress the bookkeeping: one Gaussian, list lengths around the batch size
+    (256 +- 1) and the candidate-count steps (32 / 64 / 128), images smaller than a tile and ragged ones, near-opaque
+    splats (early termination, alpha clamp), almost transparent ones (no box at all), all sizes of splats: the two
+    kernel pairs agree (forward bit for bit) and none of them deadlocks."""
     rng = np.random.default_rng(123)
-    for it in range(28):
-        n = int(rng.choice([1, 3, 17, 63, 64, 65, 127, 128, 129, 255, 256, 257, 400, 900]))
+    for it in range(32):
+        n = int(rng.choice([1, 3, 17, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 400, 900]))
         C, W, H = int(rng.integers(1, 3)), int(rng.choice([5, 16, 17, 31, 33, 48])), int(rng.choice([3, 16, 18, 32, 40]))
         ss, sl = float(rng.choice([0.3, 0.8, 1.5, 3.0])), float(rng.choice([2.0, 5.0, 12.0]))
-        A, B, col, offsets, n_isect, flatten, tw, th = make_frame(n, C, W, H, ss, sl, int(rng.integers(1 << 30)))
+        big = float(rng.choice([0.0, 0.15, 0.5, 1.0]))
+        frame = make_frame(n, C, W, H, ss, sl, int(rng.integers(1 << 30)), big)
+        A = frame[0]
         u = rng.random()
         if u < 0.3:
             A[:, 2] = rng.uniform(0.9, 1.0, len(A))
@@ -171,22 +207,10 @@ def test_backward_variants_agree_on_edge_shapes(emu):
             A[:, 2] = rng.uniform(0.001, 0.01, len(A))
         v_render = rng.standard_normal((C, H, W, 3)).astype(np.float32)
         v_alphas = rng.standard_normal((C, H, W)).astype(np.float32)
-        render, alphas = np.zeros((C, H, W, 3), np.float32), np.zeros((C, H, W), np.float32)
-        last_ids, n_blend = np.zeros((C, H, W), np.int32), np.zeros(1, np.uint64)
-        assert emu.emu_raster_fwd(P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), C, W, H, P(render), P(alphas),
-                                  P(last_ids), P(n_blend)) == 0
-        render2, alphas2 = np.zeros_like(render), np.zeros_like(alphas)
-        last2, n_blend2 = np.zeros_like(last_ids), np.zeros(1, np.uint64)
-        assert emu.emu_raster_fwd_pool(P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), C, W, H, P(render2),
-                                       P(alphas2), P(last2), P(n_blend2)) == 0
+        render, alphas, last_ids, n_blend = run_fwd(emu, POOL, frame, C, W, H)
+        render2, alphas2, last2, n_blend2 = run_fwd(emu, VISIT, frame, C, W, H)
         assert np.array_equal(render, render2) and np.array_equal(alphas, alphas2), (it, n, C, W, H)
-        assert np.array_equal(last_ids, last2) and n_blend[0] == n_blend2[0], (it, n, C, W, H)
-        outs = []
-        for variant in (0, 1, 2, 3):
-            vA, vB, vC = np.zeros_like(A), np.zeros_like(B), np.zeros_like(col)
-            assert emu.emu_raster_bwd(variant, P(offsets), P(n_isect), P(flatten), P(A), P(B), P(col), C, W, H, P(alphas),
-                                      P(last_ids), P(v_render), P(v_alphas), P(vA), P(vB), P(vC)) == 0, (it, variant)
-            outs.append(np.concatenate([vA[:, :3], vB[:, :3], vC[:, :3]], axis=1))
-        scale = np.abs(outs[0]).max(0) + 1e-12
-        for variant in (1, 2, 3):
-            assert (np.abs(outs[0] - outs[variant]).max(0) / scale).max() < 1e-4, (it, variant, n, C, W, H)
+        assert np.array_equal(last_ids, last2) and n_blend == n_blend2, (it, n, C, W, H)
+        outs = [run_bwd(emu, v, frame, C, W, H, alphas, last_ids, v_render, v_alphas) for v in (POOL, VISIT)]
+        scale = np.abs(outs[1]).max(0) + 1e-12
+        assert (np.abs(outs[0] - outs[1]).max(0) / scale).max() < 1e-4, (it, n, C, W, H)
