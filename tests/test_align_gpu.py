@@ -153,6 +153,16 @@ def test_canonical_view_focal_dense_clean_vs_reference(cuda_device):
     assert n_changed > 50 and n_diff <= max(1, n_changed // 200)    # ties in the rounded projection may flip
 
 
+@pytest.mark.parametrize("name", ["align_match3.pt", "align_dust3r3.pt"])
+def test_pipeline_index_plumbing_vs_reference(cuda_device, name):
+    """the repository's forward_mast3r -> prepare_canonical_data ->
+    compute_min_spanning_tree -> condense_data on the fixture's synthetic model equal what the unmodified reference
+    produced (tests/pipeline_parity.py): pairwise scores, MST, anchors, slices and block indices exactly; canonical
+    views, focals, core depths, offsets and confidences to fp32 rounding."""
+    from pipeline_parity import check_pipeline_vs_reference
+    check_pipeline_vs_reference(cuda_device, name)
+
+
 def test_scene_add_images_end_to_end(cuda_device):
     """Scene.add_images (full 500 + 200 iterations) on a synthetic 4-view scene recovers the camera geometry;
     then the 3DGS stage runs on the reconstructed points (the reference's main.py sequence)."""

@@ -56,6 +56,19 @@ def test_optimizer_trajectory_vs_reference(backend, name):
     t.assert_same_up_to_gauge(t.cpu(res_f), f["out"]["short"]["fine"], 1e-4)
 
 
+@pytest.mark.parametrize("name", ["align_match3.pt", "align_dust3r3.pt"])
+def test_pipeline_index_plumbing_vs_reference(emu_backend, monkeypatch, name):
+    """SURVEY 8 rows a6 / a8 / a9 / a10 on the CPU: the repository's forward_mast3r -> prepare_canonical_data ->
+    compute_min_spanning_tree -> condense_data (product code + emulated library) on the fixture's synthetic model against
+    the arrays the unmodified reference produced (tests/pipeline_parity.py)."""
+    from pipeline_parity import check_pipeline_vs_reference
+    from starst3r_b200 import match
+    from starst3r_b200 import reconstruct as rc
+    monkeypatch.setattr(match, "USE_CUDA_GRAPHS", False)
+    monkeypatch.setattr(rc, "SHARD_PAIRS", False)
+    check_pipeline_vs_reference(CPU, name)
+
+
 def test_reconstruct_scene_end_to_end(emu_backend, monkeypatch):
     """starster.reconstruct_scene on a synthetic 3-view scene, every stage through the product code and the emulated
     library: matching (exact SIMT nearest neighbour, reciprocal search, merge), canonical views, MST, the sparse global

@@ -58,6 +58,25 @@ def test_nn_argmax_golden(lib):
     assert np.allclose(best, want, rtol=1e-6)
 
 
+def test_bruteforce_reciprocal_nns_and_cdist_matcher(emu_backend, golden):
+    """SURVEY 8 row a2 on the CPU: match.bruteforce_reciprocal_nns / match.cdistMatcher.query (fast_nn.py:16-84) through
+    the product's Python glue and the emulated library - both arg-max directions, int64 numpy results, (None, []) for an
+    empty query - against the reference's golden vectors (the GPU run of the same check: tests/test_match_gpu.py)."""
+    import torch
+    from starst3r_b200 import match
+    g = golden("match_nn.npz")
+    Q, DB = torch.from_numpy(g["Q"]), torch.from_numpy(g["DB"])
+    nnA, nnB = match.bruteforce_reciprocal_nns(Q, DB, device="cpu", dist="dot", block_size=2 ** 13, impl="simt")
+    assert nnA.dtype == np.int64 and np.array_equal(nnA, g["nnA"]) and np.array_equal(nnB, g["nnB"])
+    assert np.array_equal(nnA, g["nnA_blk"]) and np.array_equal(nnB, g["nnB_blk"])
+    m = match.cdistMatcher(DB, device="cpu")
+    dis, nn = m.query(Q, dist="dot", block_size=2 ** 13, impl="simt")
+    assert dis is None and np.array_equal(nn, g["nnA"])
+    assert m.query(Q[:0], dist="dot", impl="simt") == (None, [])
+    with pytest.raises(ValueError):
+        match.bruteforce_reciprocal_nns(Q, DB, device="cpu", dist="cosine")
+
+
 def test_merge_corres_golden(lib):
     g = np.load(os.path.join(GOLD, "match_merge.npz"))
     n = len(g["idx1"])

@@ -139,6 +139,31 @@ def test_fast_reciprocal_nns_vs_oracle(cuda_device, impl, H, W, noise):
     assert np.array_equal(i1, r1) and np.array_equal(i2, r2)
 
 
+def test_bruteforce_reciprocal_nns_and_cdist_matcher(golden, cuda_device):
+    """SURVEY 8 rows a1 / a2 through the reference-named entry points (fast_nn.py:16-84): bruteforce_reciprocal_nns
+    returns BOTH arg-max directions as int64 numpy arrays, cdistMatcher.query returns (None, nnA) and (None, []) for
+    an empty query - against the reference's golden vectors (single block and 8192-blocked call are the same integers)."""
+    from starst3r_b200 import match
+    g = golden("match_nn.npz")
+    Q, DB = torch.from_numpy(g["Q"]), torch.from_numpy(g["DB"])
+    for impl in IMPLS:
+        nnA, nnB = match.bruteforce_reciprocal_nns(Q, DB, device=cuda_device, dist="dot", block_size=2 ** 13, impl=impl)
+        assert isinstance(nnA, np.ndarray) and nnA.dtype == np.int64 and nnB.dtype == np.int64
+        assert np.array_equal(nnA, g["nnA"]) and np.array_equal(nnB, g["nnB"])
+        assert np.array_equal(nnA, g["nnA_blk"]) and np.array_equal(nnB, g["nnB_blk"])
+        nnA, nnB = match.bruteforce_reciprocal_nns(g["Q"], g["DB"], device=cuda_device, dist="dot", impl=impl)   # numpy in
+        assert np.array_equal(nnA, g["nnA"]) and np.array_equal(nnB, g["nnB"])
+        m = match.cdistMatcher(DB, device=cuda_device)
+        dis, nn = m.query(Q, dist="dot", block_size=2 ** 13, impl=impl)
+        assert dis is None and nn.dtype == np.int64 and np.array_equal(nn, g["nnA"])
+        dis, nn = m.query(Q[:0], dist="dot", block_size=2 ** 13, impl=impl)           # fast_nn.py:79-80
+        assert dis is None and nn == []
+    with pytest.raises(ValueError):
+        match.bruteforce_reciprocal_nns(Q, DB, device=cuda_device, dist="cosine")      # fast_nn.py:36-37
+    with pytest.raises(NotImplementedError):                                           # CPU-only reference branch
+        match.bruteforce_reciprocal_nns(Q, DB, device=cuda_device, dist="l2")
+
+
 def test_edge_cases(cuda_device):
     from starst3r_b200 import match
     P = torch.ones(3, 3, 24)
@@ -147,6 +172,44 @@ def test_edge_cases(cuda_device):
     P = torch.ones(16, 16, 24)
     i1, i2 = match.fast_reciprocal_NNs(P, P, 8, ret_xy=False, device=cuda_device, dist="dot")
     assert list(i1) == [0] and list(i2) == [0]
+
+
+def _smooth_maps(H, W, n, seed):
+    """Descriptor fields like real MASt3R maps (and the synthetic scene): smooth functions of the pixel position plus a
+    little noise, so ~100 DB columns per query row lie inside the TF32 error band of the best score."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    X = torch.stack([xx / W, yy / H, (xx + yy) / (W + H)], -1)
+    freq = torch.randn(24, 3, generator=g) * 2.5
+    return [torch.nn.functional.normalize(torch.cos(X @ freq.T + 0.01 * k) + 0.003 * torch.randn(H, W, 24, generator=g),
+                                          dim=-1) for k in range(n)]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("kind", ["random", "smooth"])
+def test_full_size_vs_oracle(cuda_device, impl, kind):
+    """BASELINE configs[1] sizes against the C oracle itself (not the other kernel): one M = 4096 x N = 262 144 arg-max
+    (where the TF32 band of the tcgen05 kernel holds the most columns) with bit-identical indices AND scores, and one
+    512 x 512 fast_reciprocal_NNs, on random descriptors and on smooth fields (the rare path's stress case)."""
+    from starst3r_b200 import match
+    if kind == "random":
+        g = torch.Generator().manual_seed(5)
+        A = torch.nn.functional.normalize(torch.randn(512, 512, 24, generator=g), dim=-1)
+        B = torch.nn.functional.normalize(A + 0.3 * torch.randn(512, 512, 24, generator=g), dim=-1)
+    else:
+        A, B = _smooth_maps(512, 512, 2, seed=7)
+    An, Bn = A.numpy(), B.numpy()
+    ys, xs = np.mgrid[4:512:8, 4:512:8].reshape(2, -1)
+    Q = An.reshape(-1, 24)[np.sort(xs + 512 * ys)]                       # the 4096 seed rows of the first NN call
+    ref_idx, ref_best = mo.nn_argmax_dot_c(Q, Bn.reshape(-1, 24))
+    idx, best = match.nn_argmax(torch.from_numpy(Q).to(cuda_device), B.reshape(-1, 24).to(cuda_device), impl=impl,
+                                return_score=True)
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)
+    assert np.array_equal(best.cpu().numpy(), ref_best)
+    r1, r2 = mo.fast_reciprocal_nns(An, Bn, 8)
+    i1, i2 = match.fast_reciprocal_NNs(A, B, 8, ret_xy=False, device=cuda_device, dist="dot", impl=impl)
+    assert len(r1) > (1000 if kind == "random" else 50)
+    assert np.array_equal(i1, r1) and np.array_equal(i2, r2)
 
 
 @pytest.mark.parametrize("impl", IMPLS)
