@@ -6,7 +6,8 @@ The reference is single-device; sharding is new capability (SURVE
     under an initialised process group: reconstruct.SHARD_PAIRS).
   * RASTER training: camera views are sharded, the splat is replicated; per step ONE all-reduce (sum) of the
     per-Gaussian gradients (23 floats per Gaussian), then every rank applies the same Adam update.
-  * ALIGN: replicas only (O(11 N) parameters, strictly sequential iterations): rank 0 computes, result is broadcast.
+  * ALIGN: does not shard (O(11 N) parameters, strictly sequential iterations): rank 0 runs the optimiser and
+    broadcasts parameters and results (reconstruct._broadcast_alignment), so every rank continues from the same state.
 """
 import torch
 import torch.distributed as dist

@@ -97,9 +97,15 @@ class TrainPlan:
     """Persistent device buffers for repeated frames of one shape: no allocation and NO host synchronisation per
     frame.  gsplat (and the un-planned path below) reads the intersection count back every frame to size the sort
     buffers exactly; here they have a capacity (HEADROOM x the last known count), the kernels clamp to it on the
-    device, and the count is copied to pinned memory asynchronously and checked one frame later: an overflow raises
-    (loudly, never truncates silently) and a count above 80 % of the capacity grows the buffers."""
+    device, and the count is copied to pinned memory asynchronously and checked one frame later.  A frame can only be
+    rendered truncated if the count grows by more than HEADROOM within the two frames the host runs ahead, so the plan
+    keeps the count under watch: its first SYNC_FRAMES frames, and SYNC_FRAMES frames after any frame-to-frame growth
+    above GROWTH_WATCH, read the count back BEFORE binning (the exact-size discipline of gsplat: the buffers are grown
+    first, nothing is truncated, nothing wrong reaches the optimiser); a count above 80 % of the capacity grows the
+    buffers for the next frame; an overflow that still gets through raises (loudly, never truncates silently)."""
     HEADROOM = 1.5
+    SYNC_FRAMES = 8
+    GROWTH_WATCH = 0.05
 
     def __init__(self, N, C, width, height, device):
         lib = _lib.load()
@@ -136,6 +142,17 @@ class TrainPlan:
         self._pending = []                                              # (event, slot, capacity at launch)
         self._slot = 0
         self.last_n_isect = None
+        self._sync_left = self.SYNC_FRAMES                              # frames that still read the count synchronously
+
+    def sync_mode(self):
+        return self._sync_left > 0
+
+    def _observe(self, n):
+        """Book-keeping of one known count: growth watch + capacity for the next frame."""
+        prev = self.last_n_isect
+        if prev and n > (1.0 + self.GROWTH_WATCH) * prev:
+            self._sync_left = max(self._sync_left, self.SYNC_FRAMES)
+        self.last_n_isect = n
 
     def matches(self, N, C, width, height, device):
         return (self.N, self.C, self.W, self.H) == (N, C, int(width), int(height)) and self.dev == device
@@ -159,7 +176,7 @@ class TrainPlan:
             ev, slot, cap = self._pending.pop(0)
             ev.synchronize()
             n = int(self._host[slot])
-            self.last_n_isect = n
+            self._observe(n)
             if n > 0.8 * self.cap:
                 torch.cuda.current_stream().synchronize()
                 self._alloc_isect(max(int(self.HEADROOM * n), 1024))
@@ -169,10 +186,12 @@ class TrainPlan:
 
     def after_scan(self):
         """Called right after the scan of a frame: capacity bookkeeping without stalling the device."""
-        if self.cap == 0:                       # first frame of this plan: size from the true count (one sync)
+        if self.cap == 0 or self._sync_left > 0:   # watched frame: the true count decides BEFORE anything is binned
             n = int(self.n_raw.item())
-            self.last_n_isect = n
-            self._alloc_isect(max(int(self.HEADROOM * n), 1024))
+            self._observe(n)
+            self._sync_left = max(self._sync_left - 1, 0)
+            if n > 0.8 * self.cap:
+                self._alloc_isect(max(int(self.HEADROOM * n), 1024))
         else:
             slot = self._slot = (self._slot + 1) % self._host.numel()
             self._host[slot:slot + 1].copy_(self.n_raw, non_blocking=True)
@@ -216,7 +235,7 @@ def _forward(means, quats, scales, opacities, shN, cams, width, height, count_bl
         # The per-entry scan (torch.cumsum of tiles_per_gauss in gsplat) gives the emission offsets of the generic chain
         # and the intersection total.  The fused binning does not need the offsets and reports the total itself, so a
         # sized plan skips the scan altogether.
-        late_count = plan is not None and plan.cap > 0 and BINNING == "fused"
+        late_count = plan is not None and plan.cap > 0 and BINNING == "fused" and not plan.sync_mode()
         if not late_count:
             ws = plan.scan_ws if plan is not None else _ws(lib.st3r_scan_ws_bytes(C * N), dev)
             with _Prof("st3r_exclusive_scan_i32"):
@@ -769,19 +788,38 @@ def run_3dgs_optim(scene, iters, enable_pruning=False, loss_ssim_fac=0.2, loss_o
     cams = make_cams(scene.w2c.to(dev), scene.intrinsics.to(dev))
     names = ("means", "scales", "quats", "opacities", "shN")
 
+    def opt_state(k):
+        """Adam state of tensor k: FusedAdam's own record, or the `state` dict of a torch.optim.Adam the user swapped in
+        (the reference lets users replace scene.optimizers[k], gs.py:37)."""
+        opt = scene.optimizers[k]
+        if isinstance(opt, FusedAdam):
+            return opt._st(gz[k])
+        st = opt.state[gz[k]]
+        if not st:
+            st.update(step=torch.zeros(()), exp_avg=torch.zeros_like(gz[k].data), exp_avg_sq=torch.zeros_like(gz[k].data))
+        return st
+
     def bind():
         """Raw views of the splat tensors and their Adam moments (re-bound after the strategy replaced them)."""
         params = {k: gz[k].data for k in names}
         states = {}
         for k in names:
-            opt = scene.optimizers[k]
-            st = opt._st(gz[k]) if isinstance(opt, FusedAdam) else opt.state.setdefault(gz[k], dict(
-                step=torch.zeros(()), exp_avg=torch.zeros_like(gz[k].data), exp_avg_sq=torch.zeros_like(gz[k].data)))
+            st = opt_state(k)
             states[k] = (st["exp_avg"], st["exp_avg_sq"])
         return params, states
 
     params, states = bind()
     group = scene.optimizers["means"].param_groups[0]
+    # the fused Adam kernel applies ONE (lr, betas, eps, step) to the five tensors of its launch
+    for k in names:
+        g_k = scene.optimizers[k].param_groups[0]
+        if (g_k["lr"], tuple(g_k["betas"]), g_k["eps"]) != (group["lr"], tuple(group["betas"]), group["eps"]) or \
+                g_k.get("weight_decay", 0) or g_k.get("amsgrad", False) or \
+                int(opt_state(k)["step"]) != int(opt_state("means")["step"]):
+            raise NotImplementedError(
+                f"run_3dgs_optim: scene.optimizers[{k!r}] differs from scene.optimizers['means'] (lr / betas / eps / step "
+                "count) or uses weight decay / amsgrad; the fused per-Gaussian Adam of this package applies one set of "
+                "hyper-parameters to all splat tensors, as starster/gs.py:37 sets them up")
     losses_dev = torch.zeros(max(iters, 1), dtype=torch.float32, device=dev)
     # Sharded views (SURVEY §8e): under a process group every rank renders the views i = rank mod G of the same,
     # replicated splat; the sum of the per-Gaussian gradients over the ranks is the full gradient (the loss is a sum
@@ -807,6 +845,18 @@ def run_3dgs_optim(scene, iters, enable_pruning=False, loss_ssim_fac=0.2, loss_o
         return plan
 
     if shard is not None:
+        # replicas must BE replicas: same number of Gaussians everywhere, rank 0's values and Adam moments on every rank
+        # (the ranks may have arrived here through slightly different reconstructions)
+        import torch.distributed as _dist
+        n_here = torch.tensor([params["means"].shape[0], -params["means"].shape[0]], dtype=torch.int64, device=dev)
+        _dist.all_reduce(n_here, op=_dist.ReduceOp.MAX)
+        if int(n_here[0]) != -int(n_here[1]):
+            raise RuntimeError(f"run_3dgs_optim with sharded views: the ranks hold different splats ({-int(n_here[1])} .. "
+                               f"{int(n_here[0])} Gaussians); initialise the scene identically on every rank")
+        for k in names:
+            _dist.broadcast(params[k], 0)
+            _dist.broadcast(states[k][0], 0)
+            _dist.broadcast(states[k][1], 0)
         plan = get_plan()
         if plan.peer is None:
             try:
@@ -820,13 +870,13 @@ def run_3dgs_optim(scene, iters, enable_pruning=False, loss_ssim_fac=0.2, loss_o
     for step in pbar:
         if enable_pruning:
             scene.strategy.step_pre_backward(scene.gaussians, scene.optimizers, scene.strategy_state, step, None)
-        opt_step = int(scene.optimizers["means"]._st(gz["means"])["step"].item()) + 1
+        opt_step = int(opt_state("means")["step"]) + 1
         loss, fr = train_step(params, states, truth, cams, width, height, opt_step, lr=group["lr"],
                               betas=group["betas"], eps=group["eps"], loss_ssim_fac=loss_ssim_fac,
                               loss_opacity_fac=loss_opacity_fac, loss_scale_fac=loss_scale_fac, plan=get_plan(),
                               loss_out=losses_dev[step], grad_hook=hook)
         for k in names:
-            scene.optimizers[k]._st(gz[k])["step"] += 1
+            opt_state(k)["step"] += 1
         if verbose:
             pbar.set_description(f"Gsplat optimization: loss={loss.item()}")
         if enable_pruning:

@@ -234,6 +234,22 @@ def _optimize_phase(t, meta, params, mode, train_mask, gamma, lr_base, niter, sc
     return res, loss_hist[:niter], grad
 
 
+def _broadcast_alignment(params, res_coarse, res_fine, src=0):
+    """Rank `src`'s optimiser state and results to every rank of the group: one flat fp32 broadcast."""
+    import torch.distributed as dist
+    tensors = [params[k] for k in ("pps", "log_focals", "quats", "trans", "log_sizes")]
+    for res in (res_coarse, res_fine):
+        if res is not None:
+            tensors += [res["intrinsics"], res["cam2w"], *res["depthmaps"], *res["pts3d"]]
+    flat = torch.cat([x.reshape(-1).float() for x in tensors]).contiguous()
+    dist.broadcast(flat, src)
+    off = 0
+    for x in tensors:
+        n = x.numel()
+        x.copy_(flat[off:off + n].view_as(x))
+        off += n
+
+
 def sparse_scene_optimizer_slam(imgs, subsample, imsizes, pps, base_focals, core_depth, anchors, corres, corres2d,
                                 preds_21, canonical_paths, mst, cache_path=None,
                                 lr1=0.2, niter1=500, loss1=gamma_loss(1.1),
@@ -270,17 +286,26 @@ def sparse_scene_optimizer_slam(imgs, subsample, imsizes, pps, base_focals, core
             if n:
                 params[k][:n] = torch.stack([torch.as_tensor(x).detach().reshape(-1) for x in prev[:n]]).to(dev).reshape(
                     params[k][:n].shape)
-    res_coarse, hist1, _ = _optimize_phase(t, meta, params, 0, 4 | 8 | 16, _gamma_of(loss1), lr1, niter1, schedule,
+    # Under a process group the optimiser runs on rank 0 only and its result is broadcast (O(11 N) parameters,
+    # strictly sequential iterations).  Replicas would NOT stay identical: the kernels sum losses and gradients with fp32
+    # atomics, and Adam turns that rounding noise into an O(lr) walk along the gauge directions,
+    # so cameras, dense points and the splat built from them could differ between ranks.
+    group = _shard_group()
+    lead = group is None or group[0] == 0
+    n1, n2 = (niter1, niter2) if lead else (0, 0)          # the other ranks only shape the result buffers
+    res_coarse, hist1, _ = _optimize_phase(t, meta, params, 0, 4 | 8 | 16, _gamma_of(loss1), lr1, n1, schedule,
                                            loss_dust3r_w, _gamma_of(lossd))
-    if verbose and niter1:
+    if verbose and n1:
         print(f">> final loss = {float(hist1[-1])}")
     res_fine = None
     if niter2:
         mask = 4 | 8 | 16 | 2 | (1 if opt_pp else 0)
-        res_fine, hist2, _ = _optimize_phase(t, meta, params, 1, mask, _gamma_of(loss2), lr2, niter2, schedule,
+        res_fine, hist2, _ = _optimize_phase(t, meta, params, 1, mask, _gamma_of(loss2), lr2, n2, schedule,
                                              loss_dust3r_w, _gamma_of(lossd))
-        if verbose:
+        if verbose and n2:
             print(f">> final loss = {float(hist2[-1])}")
+    if group is not None:
+        _broadcast_alignment(params, res_coarse, res_fine)
     if verbose:
         f = params["log_focals"].exp().clip(min=torch.as_tensor(0.25 * meta["imsizes"].norm(dim=1)).to(dev),
                                             max=torch.as_tensor(10 * meta["imsizes"].norm(dim=1)).to(dev))
@@ -318,6 +343,16 @@ def _memo(cache_path):
 #   corres_conf=<desc_conf>_subsample=<S>/<a>-<b>.pth = ((conf_score, sum conf, n), (xy1, xy2, conf))    sparse_ga.py:561
 #   canon_views/<md5 img>_subsample=<S>_kw=<kw>.pth  = ((canon, canon2, cconf), focal)                   sparse_ga.py:706
 PERSIST_CACHE = False
+
+
+def clear_cache(cache_path=None):
+    """Releases the device-resident pair / canonical-view memo of `cache_path` (all of them when None).  The reference
+    keeps these tensors in files under cache_dir (sparse_ga.py:533-561,643); here they live in HBM - about
+    N (N - 1) 8 H W 4 bytes per reconstruction - until the owning Scene goes away or this is called."""
+    if cache_path is None:
+        _MEMO.clear()
+    else:
+        _MEMO.pop(cache_path, None)
 
 
 def _md5(name):
@@ -885,7 +920,13 @@ def reconstruct_scene(model, imgs, filelist, device, optim_params=None, tmpdir=N
     import tempfile
     imgs = prepare_images_for_mast3r(imgs)
     pairs = make_pairs(imgs, scene_graph="complete", prefilter=None, symmetrize=True)
-    if tmpdir is None:
+    private = tmpdir is None
+    if private:
         tmpdir = tempfile.mkdtemp()
-    return run_sparse_ga(filelist, pairs, tmpdir, model, lr1=0.07, niter1=500, lr2=0.014, niter2=200, device=device,
-                         opt_depth=False, matching_conf_thr=5, shared_intrinsics=False, optim_params=optim_params)
+    scene, optim_params = run_sparse_ga(filelist, pairs, tmpdir, model, lr1=0.07, niter1=500, lr2=0.014, niter2=200,
+                                        device=device, opt_depth=False, matching_conf_thr=5, shared_intrinsics=False,
+                                        optim_params=optim_params)
+    if private:     # nobody else can name this cache: its device-resident memo goes when the result object goes
+        import weakref
+        weakref.finalize(scene, clear_cache, tmpdir)
+    return scene, optim_params

@@ -16,6 +16,7 @@ class Scene:
 
     def __init__(self, cache_dir: Optional[str] = None, device="cuda"):
         self.device = device
+        self._own_cache = cache_dir is None      # a private cache: its device-resident memo dies with the scene
         self.cache_dir = cache_dir if cache_dir is not None else tempfile.mkdtemp()
         self.raw_imgs = []
         self.imgs = []
@@ -28,6 +29,14 @@ class Scene:
         self.gs_optims = None
         self.gs_strategy = None
         self.gs_state = None
+
+    def __del__(self):
+        if getattr(self, "_own_cache", False):
+            try:
+                from .reconstruct import clear_cache
+                clear_cache(self.cache_dir)
+            except Exception:       # noqa: BLE001 - interpreter shutdown
+                pass
 
     @property
     def dense_pts_flat(self):

@@ -234,3 +234,74 @@ def test_forward_mast3r_shards_pairs_and_exchanges_results(world):
     res = [q.get(timeout=600) for _ in procs]
     [p.join(timeout=60) for p in procs]
     assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
+def _align_worker(rank, world, port, q):
+    """sparse_scene_optimizer_slam under a process group: rank 0 alone runs the optimiser, every rank ends with rank 0's
+    parameters and results (the kernels' fp32 atomics make independent replicas drift apart along the gauge)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import numpy as np
+        from starst3r_b200 import _lib
+        from starst3r_b200 import reconstruct as rc
+        torch.set_num_threads(1)
+        fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "align_match3.pt"),
+                        weights_only=False)
+        inp = fx["inputs"]
+        _lib.require_cuda_device = lambda device, what="": torch.device("cpu")     # test-only: host stand-ins below
+        seen = []
+
+        def fake_phase(t, meta, params, mode, train_mask, gamma, lr_base, niter, schedule, dust3r_w, lossd_gamma,
+                       want_grad=False):
+            """Stand-in for the CUDA optimiser: results and parameter updates that depend on the rank that ran it."""
+            seen.append((mode, niter))
+            N = meta["N"]
+            if niter:
+                params["trans"] += 1.0 + rank
+                params["quats"] += 0.25 * (1 + rank)
+            val = 1000.0 * rank + 10.0 * mode + niter
+            aoff, coff = meta["aoff"], np.cumsum([0] + meta["n_core"])
+            res = dict(intrinsics=torch.full((N, 3, 3), val), cam2w=torch.full((N, 4, 4), val + 1),
+                       depthmaps=[torch.full((int(coff[i + 1] - coff[i]),), val + 2) for i in range(N)],
+                       pts3d=[torch.full((int(aoff[i + 1] - aoff[i]), 3), val + 3) for i in range(N)])
+            return res, torch.zeros(max(niter, 1))[:niter], None
+        rc._optimize_phase = fake_phase
+        out = {}
+        for shard in (True, False):
+            rc.SHARD_PAIRS = shard
+            seen.clear()
+            _, res_c, res_f, params_ret = rc.sparse_scene_optimizer_slam(
+                list(inp["imgs"]), 8, inp["imsizes"], inp["pps"].clone(), inp["base_focals"].clone(),
+                [c.clone() for c in inp["core_depth"]], inp["anchors"], inp["corres"], inp["corres2d"], inp["preds_21"],
+                None, inp["mst"], lr1=0.07, niter1=30, lr2=0.014, niter2=20, device="cpu", opt_depth=False,
+                shared_intrinsics=False, matching_conf_thr=5.0, verbose=False)
+            out[shard] = (list(seen), res_c, res_f, params_ret)
+        seen_s, res_c, res_f, pr = out[True]
+        assert seen_s == ([(0, 30), (1, 20)] if rank == 0 else [(0, 0), (1, 0)]), seen_s      # only rank 0 iterates
+        # every rank holds what rank 0 computed: parameters after both phases, results of both phases
+        assert all(torch.equal(x, torch.full_like(x, 2.0)) for x in pr["trans"])
+        assert all(torch.allclose(x, torch.tensor([0.5, 0.5, 0.5, 1.5])) for x in pr["quats"])
+        assert float(res_c["intrinsics"][0, 0, 0]) == 30.0 and float(res_c["cam2w"][0, 0, 0]) == 31.0
+        assert float(res_f["intrinsics"][0, 0, 0]) == 30.0 and float(res_f["pts3d"][0][0, 0]) == 33.0
+        assert all(float(d[0]) == 32.0 for d in res_f["depthmaps"])
+        # without sharding (SHARD_PAIRS off) the call is the single-process one: every rank iterates for itself
+        assert out[False][0] == [(0, 30), (1, 20)]
+        assert float(out[False][2]["intrinsics"][0, 0, 0]) == 1000.0 * rank + 30.0
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_alignment_runs_on_rank0_and_is_broadcast():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_align_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=600) for _ in procs]
+    [p.join(timeout=60) for p in procs]
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res

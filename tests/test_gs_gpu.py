@@ -420,6 +420,32 @@ def test_train_plan_matches_unplanned(cuda_device):
     assert fb.n_isect <= plan.cap and plan.last_n_isect == fb.n_isect
 
 
+def test_train_plan_watches_the_intersection_count(cuda_device):
+    """The plan's first frames, and the frames after any growth of the count above GROWTH_WATCH, read the count back
+    before binning (nothing truncated can reach the optimiser); quiet stretches run without host synchronisation."""
+    from starst3r_b200 import gs
+    sp, viewmats, Ks, W, H = small_scene(n=800, C=3, seed=6)
+    truth = torch.rand(3, H, W, 3, generator=torch.Generator().manual_seed(1)).to(cuda_device)
+    cams = gs.make_cams(viewmats.to(cuda_device), Ks.to(cuda_device))
+    p = {k: v.clone().to(cuda_device).contiguous() for k, v in sp.items()}
+    st = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in p.items()}
+    plan = gs.TrainPlan(800, 3, W, H, cuda_device)
+    assert plan.sync_mode()
+    for i in range(gs.TrainPlan.SYNC_FRAMES + 2):
+        gs.train_step(p, st, truth, cams, W, H, i + 1, plan=plan, lr=1e-5)
+    plan.poll(wait_all=True)
+    assert not plan.sync_mode()                       # quiet: asynchronous counts from here on
+    n0 = plan.last_n_isect
+    p["scales"] *= 1.25                               # ~1.5x the intersections: seen one frame late, inside the headroom
+    gs.train_step(p, st, truth, cams, W, H, 20, plan=plan, lr=1e-5)
+    plan.poll(wait_all=True)
+    assert plan.last_n_isect > (1 + gs.TrainPlan.GROWTH_WATCH) * n0 and plan.sync_mode()
+    p["scales"] *= 2.0                                # far beyond the headroom, but the frame is watched: buffers grow first
+    _, fr = gs.train_step(p, st, truth, cams, W, H, 21, plan=plan, lr=1e-5)
+    plan.poll(wait_all=True)
+    assert fr.n_isect == plan.last_n_isect <= plan.cap and fr.n_isect > 2 * n0
+
+
 def test_scene_api_run_3dgs_optim(cuda_device):
     """Scene.init_3dgs / run_3dgs_optim / render_3dgs_original with the reference's call pattern (main.py:77-88):
     the loss decreases and the API objects have the reference's shape."""
