@@ -494,7 +494,8 @@ def run_reference(args):
 def _kernel_variants():
     from starst3r_b200 import gs, match
     from starst3r_b200 import reconstruct as rc
-    return {"raster_bwd": int(gs.RASTER_VARIANT), "nn_split": bool(match.NN_SPLIT), "align": int(rc.ALIGN_VARIANT)}
+    return {"raster": int(gs.RASTER_VARIANT), "nn_split": match.NN_SPLIT, "nn_cooperative": match.NN_COOPERATIVE,
+            "align": int(rc.ALIGN_VARIANT)}
 
 
 def main():

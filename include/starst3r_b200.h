@@ -68,6 +68,10 @@ ST3R_API int st3r_nn_tc_set_cooperative(int on);
  * on, st3r_nn_argmax_ws_bytes and st3r_extract_corres_ws_bytes include two [rows, 24] float arrays per descriptor
  * map; st3r_recip_nn always runs the plain variant. */
 ST3R_API int st3r_nn_tc_set_split(int on);
+/* Diagnostic: candidate-band width (relative to |q| max|db|) of the plain / split-precision tcgen05 kernel for the
+ * launches that follow; 0 restores the built-in value.  scripts/nn_split_margin.py narrows the band until results stop
+ * being exact, which measures the tensor core's real error and hence the safety margin of the built-in values. */
+ST3R_API int st3r_debug_nn_tc_set_delta_coef(float plain, float split);
 
 /* ------------------------------------------------------------------ MATCH */
 

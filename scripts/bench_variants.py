@@ -109,7 +109,7 @@ def match_leg(dev, out, model=None):
                 except Exception as e:
                     out[key] = "ERROR " + repr(e)[:300]
                 finally:
-                    match.NN_COOPERATIVE, match.NN_SPLIT = "auto", False
+                    match.NN_COOPERATIVE, match.NN_SPLIT = "auto", "auto"
 
 
 def main():

@@ -391,6 +391,7 @@ struct NnTcParams {
   NnBatchItem it[NN_MAX_BATCH];
   int tiles_per_chunk;
   int dynamic;
+  float delta_coef;                    // width of the candidate band relative to |q| max|db| (DELTA_COEF / DELTA_COEF_SPLIT)
 };
 
 template <bool kCoop, bool kSplit>
@@ -594,7 +595,7 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
       float n2 = 0.f;
 #pragma unroll
       for (int k = 0; k < DK; ++k) n2 = fmaf(qrow[k], qrow[k], n2);
-      delta = (kSplit ? DELTA_COEF_SPLIT : DELTA_COEF) * sqrtf(n2) * sqrtf(*db_norm2_max) + 1e-30f;
+      delta = prm.delta_coef * sqrtf(n2) * sqrtf(*db_norm2_max) + 1e-30f;
     }
     float run_max = row_ok ? -INFINITY : INFINITY;  // padded rows never trigger
     {
@@ -806,6 +807,17 @@ bool nn_tc_supported(int d) { return d == DK; }
 
 static int g_nn_tc_coop = 0;
 static int g_nn_tc_split = 0;
+static float g_nn_tc_delta_coef[2] = {0.f, 0.f};   // diagnostic overrides (0: DELTA_COEF / DELTA_COEF_SPLIT)
+
+// Diagnostic (scripts/nn_split_margin.py): overrides the width of the candidate band of the plain / split-precision
+// kernel for subsequent launches, 0 restores the built-in value.  With a band narrower than the tensor core's real
+// error the result is no longer guaranteed exact - that is what the script measures.
+extern "C" int st3r_debug_nn_tc_set_delta_coef(float plain, float split) {
+  ST3R_CHECK_ARG(plain >= 0.f && split >= 0.f, "st3r_debug_nn_tc_set_delta_coef: negative coefficient");
+  g_nn_tc_delta_coef[0] = plain;
+  g_nn_tc_delta_coef[1] = split;
+  return ST3R_OK;
+}
 
 bool nn_tc_split_enabled() { return g_nn_tc_split != 0; }
 
@@ -921,6 +933,8 @@ int nn_tc_launch_batch(const NnBatchItem* items, int n, int d, cudaStream_t stre
     ++m;
   }
   if (m == 0) return ST3R_OK;
+  prm.delta_coef = split ? (g_nn_tc_delta_coef[1] > 0.f ? g_nn_tc_delta_coef[1] : DELTA_COEF_SPLIT)
+                         : (g_nn_tc_delta_coef[0] > 0.f ? g_nn_tc_delta_coef[0] : DELTA_COEF);
   for (int i = m; i < NN_MAX_BATCH; ++i) { prm.tmap[i] = prm.tmap[0]; prm.tmap_lo[i] = prm.tmap_lo[0]; prm.it[i] = prm.it[0]; }
   static PerDeviceOnce attr_set;
   if (!attr_set.done()) {

@@ -328,35 +328,62 @@ class _ExtractPlan:
 _PLANS = {}
 USE_CUDA_GRAPHS = True
 
-# Variant of the tcgen05 matcher's rare path (st3r_nn_tc_set_cooperative): "auto" follows the statistics the kernels
-# collect (exact list resolutions per scanned row): random-like descriptors resolve ~never and run the per-thread
-# variant; smooth descriptor fields (real MASt3R maps) resolve ~once per row and DB range and run the warp-cooperative
-# one (2x faster there, ~14 % slower on random data).  True / False pin it.  Results are identical either way.
+# The tcgen05 matcher scores with TF32 tensor-core products and re-scores, exactly, every column inside the error band
+# of the running maximum.  How many columns that is depends on the data, and two switches adapt the kernel to it - the
+# results are identical in every combination (the exact fp32 re-score decides):
+#   * st3r_nn_tc_set_split: split precision (hi.hi + hi.lo + lo.hi, 3 x the tensor work, ~40x narrower band).  Measured
+#     on the B200 (profiles/r02n_nn_margin.json, r02a_variants.json): smooth descriptor fields - real MASt3R maps, the
+#     synthetic scene - 8.0 -> 4.5 ms per 512 x 512 pair; random descriptors 2.5 -> 3.3 ms.  The band keeps a 256x
+#     margin over the largest error the tensor core ever showed and 4x over the worst-case bound.
+#   * st3r_nn_tc_set_cooperative: warp-cooperative resolution of full candidate lists (2x on smooth fields when the
+#     split is off, ~14 % slower on random data).
+# "auto" follows the statistics the kernels collect (exact list resolutions per scanned query row): random-like
+# descriptors resolve ~never and run the plain per-thread variant; fields that resolve more than once per two rows
+# switch to split precision (and back when its own, ~40x smaller, ratio says the data changed).  True / False pin a
+# switch (ST3R_NN_SPLIT=0/1 in the environment pins the split).
 NN_COOPERATIVE = "auto"
-# Split-precision variant of the tcgen05 matcher (st3r_nn_tc_set_split): 3 x TF32 products per score, ~40x narrower
-# exact-re-score band; meant for smooth descriptor fields.  Off by default: written after the round's GPU budget was
-# spent, not measured yet (tests/test_experimental_gpu.py).  ST3R_NN_SPLIT=1 in the environment switches it on.
-NN_SPLIT = os.environ.get("ST3R_NN_SPLIT", "0") == "1"
-_variant = {"on": False}
+NN_SPLIT = {"0": False, "1": True}.get(os.environ.get("ST3R_NN_SPLIT", ""), "auto")
+_variant = {"on": False, "split": False, "probe_in": 0}
+# Resolutions per query row of the PLAIN kernel: above -> split on, below -> split off.  Measured (B200,
+# profiles/r02o_nn_margin.json): random descriptors 0.0, the synthetic scene 5.4, smooth fields 244; the split kernel itself
+# resolves ~never on anything but the smoothest fields, so its own statistics cannot tell when to switch back: while
+# the split is on, every SPLIT_PROBE_EVERY-th call runs the plain kernel once as a probe.
+SPLIT_ON_RATIO, SPLIT_OFF_RATIO, SPLIT_PROBE_EVERY = 0.5, 0.1, 64
 
 
 def _apply_variant(lib):
     """Selects the matcher variant for the next launches; returns the key (cooperative, split) it stands for."""
-    on = _variant["on"] if NN_COOPERATIVE == "auto" else bool(NN_COOPERATIVE)
+    split = _variant["split"] if NN_SPLIT == "auto" else bool(NN_SPLIT)
+    if NN_SPLIT == "auto" and split:
+        _variant["probe_in"] -= 1
+        if _variant["probe_in"] <= 0:
+            split = False                        # probe: one call with the plain kernel, _adapt_variant reads its ratio
+    on = (_variant["on"] and not split) if NN_COOPERATIVE == "auto" else bool(NN_COOPERATIVE)
     lib.st3r_nn_tc_set_cooperative(int(on))
-    lib.st3r_nn_tc_set_split(int(bool(NN_SPLIT)))
-    return (on, bool(NN_SPLIT))
+    lib.st3r_nn_tc_set_split(int(split))
+    _variant["ran_split"] = split
+    return (on, split)
 
 
 def _adapt_variant(lib):
     """Called where the host has just synchronised anyway (the correspondence count was read back)."""
-    if NN_COOPERATIVE != "auto":
+    if NN_COOPERATIVE != "auto" and NN_SPLIT != "auto":
         return
     st = (ctypes.c_ulonglong * 2)()
     _lib.check(lib.st3r_nn_tc_stats(st, 1), "st3r_nn_tc_stats")
     rows, resolves = int(st[0]), int(st[1])
-    if rows >= 256:
-        ratio = resolves / rows          # exact list resolutions per query row
+    if rows < 256 or _variant.get("ran_split"):
+        return                       # (the split kernel's own ratio says nothing about the plain band)
+    ratio = resolves / rows          # exact list resolutions per query row of the plain kernel
+    if NN_SPLIT == "auto":
+        if ratio > SPLIT_ON_RATIO:
+            _variant["split"] = True
+            _variant["probe_in"] = SPLIT_PROBE_EVERY
+        elif ratio < SPLIT_OFF_RATIO:
+            _variant["split"] = False
+        elif _variant["split"]:
+            _variant["probe_in"] = SPLIT_PROBE_EVERY
+    if NN_COOPERATIVE == "auto":
         if ratio > 0.5:
             _variant["on"] = True
         elif ratio < 0.1:

@@ -185,9 +185,11 @@ def problem_struct(t, meta):
 
 
 # Variants of the ALIGN kernels (bit mask of st3r_align_set_variant): bit 0 = segmented register accumulation +
-# replicated gradient tables in the loss kernels, bit 1 = one thread-block cluster per image in the Weiszfeld focal
-# kernel.  0 = the variants all committed measurements were taken with.  ST3R_ALIGN_VARIANT sets the initial value.
-ALIGN_VARIANT = int(os.environ.get("ST3R_ALIGN_VARIANT", "0"))
+# replicated gradient tables in the loss kernels and staged camera kernels, bit 1 = one thread-block cluster per image in
+# the Weiszfeld focal kernel.  Both on by default (B200, profiles/r02a_variants.json: reconstruct_scene 0.388 -> 0.356 s
+# on 8 views 512 x 512); 0 = the first implementation, kept as cross-check (tests/test_align_gpu.py runs both).
+# ST3R_ALIGN_VARIANT sets the initial value.
+ALIGN_VARIANT = int(os.environ.get("ST3R_ALIGN_VARIANT", "3"))
 
 
 def _optimize_phase(t, meta, params, mode, train_mask, gamma, lr_base, niter, schedule, dust3r_w, lossd_gamma,

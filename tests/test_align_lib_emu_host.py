@@ -12,7 +12,7 @@ import torch
 CPU = torch.device("cpu")
 
 
-@pytest.fixture(params=[0, 3], ids=["default-kernels", "variants"])
+@pytest.fixture(params=[3, 0], ids=["default-kernels", "first-implementation"])
 def backend(request, emu_backend, monkeypatch):
     from starst3r_b200 import reconstruct as rc
     monkeypatch.setattr(rc, "ALIGN_VARIANT", request.param)

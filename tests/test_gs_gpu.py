@@ -443,7 +443,7 @@ def test_train_plan_watches_the_intersection_count(cuda_device):
     p["scales"] *= 2.0                                # far beyond the headroom, but the frame is watched: buffers grow first
     _, fr = gs.train_step(p, st, truth, cams, W, H, 21, plan=plan, lr=1e-5)
     plan.poll(wait_all=True)
-    assert fr.n_isect == plan.last_n_isect <= plan.cap and fr.n_isect > 2 * n0
+    assert fr.n_isect == plan.last_n_isect <= plan.cap and fr.n_isect > 1.5 * n0
 
 
 def test_scene_api_run_3dgs_optim(cuda_device):

@@ -235,22 +235,40 @@ def test_full_size_properties(cuda_device, impl):
     assert np.array_equal(s1, np.sort(x + 512 * y)) and np.array_equal(s1, s2)
 
 
-def test_cooperative_variant_identical_and_auto_selected(cuda_device):
-    """The warp-cooperative rare path (st3r_nn_tc_set_cooperative) returns bit-identical correspondences on random
-    AND on smooth descriptor fields (many near-tie columns per row), and "auto" follows the kernels' statistics
-    (exact list resolutions per query row: > 0.5 switches it on, < 0.1 off)."""
+@pytest.fixture
+def nn_split(monkeypatch):
+    from starst3r_b200 import match
+    monkeypatch.setattr(match, "NN_SPLIT", True)
+    yield
+    from starst3r_b200 import _lib
+    _lib.load().st3r_nn_tc_set_split(0)
+
+
+def test_split_precision_variant_vs_oracle(golden, cuda_device, nn_split):
+    """The split-precision tcgen05 kernel (what "auto" selects on smooth descriptor fields) pinned against the oracle
+    and the reference's golden vectors on its own: every shape of the arg-max sweep, ties, unnormalised inputs,
+    extract_correspondences, and the full-size checks."""
+    for M, N in [(1, 1), (2, 5), (7, 129), (128, 128), (129, 4097), (300, 20000), (1000, 66000)]:
+        test_nn_argmax_vs_oracle(cuda_device, "tcgen05", M, N)
+    test_nn_argmax_golden(golden, cuda_device, "tcgen05")
+    test_nn_argmax_unnormalised_and_negative(cuda_device, "tcgen05")
+    test_extract_correspondences_golden(golden, cuda_device, "tcgen05")
+    test_full_size_vs_oracle(cuda_device, "tcgen05", "smooth")
+    test_full_size_properties(cuda_device, "tcgen05")
+
+
+def test_matcher_variants_identical_and_auto_selected(cuda_device):
+    """The tcgen05 matcher's data-dependent switches - warp-cooperative rare path (st3r_nn_tc_set_cooperative) and split
+    precision (st3r_nn_tc_set_split) - return bit-identical correspondences in every combination, on random AND on
+    smooth descriptor fields (many near-tie columns per row), and "auto" follows the kernels' statistics (exact list
+    resolutions per query row): smooth fields switch the split on, random ones switch it off again."""
     import ctypes
     from starst3r_b200 import _lib, match, synth
     lib = _lib.load()
     H = W = 256
-    g = torch.Generator().manual_seed(0)
-    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
-    X = torch.stack([xx / W, yy / H, (xx + yy) / (W + H)], -1)
-    freq = torch.randn(24, 3, generator=g) * 2.5
-    smooth = lambda salt: torch.nn.functional.normalize(                                       # noqa: E731
-        torch.cos(X @ freq.T + salt) + 0.003 * torch.randn(H, W, 24, generator=g), dim=-1).to(cuda_device)
+    smooth = [m.to(cuda_device) for m in _smooth_maps(H, W, 4, seed=0)]
     A, B = synth.descriptor_pair(H, W, seed=3, device=cuda_device)
-    cases = {"random": [A, B, B, A], "smooth": [smooth(0.0), smooth(0.01), smooth(0.02), smooth(0.03)]}
+    cases = {"random": [A, B, B, A], "smooth": smooth}
     q = [torch.ones(H, W, device=cuda_device) for _ in range(4)]
     out, ratio = {}, {}
 
@@ -259,24 +277,36 @@ def test_cooperative_variant_identical_and_auto_selected(cuda_device):
         _lib.check(lib.st3r_nn_tc_stats(st, 1), "stats")
         return int(st[1]) / max(int(st[0]), 1)
     try:
-        for mode in (False, True):
-            match.NN_COOPERATIVE = mode
-            for name, feats in cases.items():
-                stats()
-                out[name, mode] = [t.cpu() for t in match.extract_correspondences(feats, q, 8, device=cuda_device)]
-                ratio[name, mode] = stats()
+        for coop in (False, True):
+            for split in (False, True):
+                match.NN_COOPERATIVE, match.NN_SPLIT = coop, split
+                for name, feats in cases.items():
+                    stats()
+                    out[name, coop, split] = [t.cpu() for t in match.extract_correspondences(feats, q, 8, device=cuda_device)]
+                    ratio[name, coop, split] = stats()
         for name in cases:
-            for a, b in zip(out[name, False], out[name, True]):
-                assert torch.equal(a, b), name
-            assert out[name, False][0].shape[0] > 50
-        assert ratio["random", False] < 0.1 < 0.5 < ratio["smooth", False], ratio      # the regimes the switch separates
-        match.NN_COOPERATIVE = "auto"
-        match._variant["on"] = False
+            for key, val in out.items():
+                if key[0] == name:
+                    for a, b in zip(out[name, False, False], val):
+                        assert torch.equal(a, b), key
+            assert out[name, False, False][0].shape[0] > 50
+        # the regimes the switches separate
+        assert ratio["random", False, False] < 0.1 < match.SPLIT_ON_RATIO < ratio["smooth", False, False], ratio
+        assert ratio["smooth", False, True] < 0.1 * ratio["smooth", False, False], ratio
+        assert ratio["random", False, False] < match.SPLIT_OFF_RATIO, ratio
+        match.NN_COOPERATIVE = match.NN_SPLIT = "auto"
+        match._variant.update(on=False, split=False, probe_in=0)
         stats()
         match.extract_correspondences(cases["smooth"], q, 8, device=cuda_device)
-        assert match._variant["on"] is True
+        assert match._variant["split"] is True                       # plain kernel resolved > 0.5 lists per row
+        for _ in range(3):                                           # ... and stays on while the data stays smooth
+            match.extract_correspondences(cases["smooth"], q, 8, device=cuda_device)
+            assert match._variant["split"] is True and match._variant["ran_split"] is True
+        match._variant["probe_in"] = 1                               # the next call is the periodic plain-kernel probe
         match.extract_correspondences(cases["random"], q, 8, device=cuda_device)
-        assert match._variant["on"] is False
+        assert match._variant["ran_split"] is False and match._variant["split"] is False
+        match.extract_correspondences(cases["random"], q, 8, device=cuda_device)
+        assert match._variant["split"] is False and match._variant["on"] is False
     finally:
-        match.NN_COOPERATIVE = "auto"
-        match._variant["on"] = False
+        match.NN_COOPERATIVE = match.NN_SPLIT = "auto"
+        match._variant.update(on=False, split=False, probe_in=0)
