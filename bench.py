@@ -7,8 +7,10 @@ Headline line (`metric` = Gaussians/s rasterised): one *step* = one 3DGS trainin
 starster/gs.py:143-161 on BASELINE.json configs[1] (8 views of 512x512, 200 k Gaussians): render all views,
 L1+SSIM loss, backward, Adam.  `match` carries the second half of BASELINE.json's metric (512x512 image pairs
 matched per second, extract_correspondences of sparse_ga.py:595-630).  Inputs are synthetic.
-At N > 1 every rank renders its own 8 views of the replicated splat (weak scaling), the per-Gaussian gradients
-are all-reduced over NCCL and Adam is replicated; image pairs are independent and shard without a collective.
+At N > 1 every rank renders 8 views of the replicated splat (weak scaling; every rank gets the SAME 8 truth images,
+so the work per rank is identical at every N and the per-N values are an iso-work measurement), the per-Gaussian
+gradients are summed over NVLink peer memory and Adam is replicated; image pairs are independent and shard without a
+collective.
 """
 import argparse
 import json
@@ -28,6 +30,7 @@ N_GAUSS, N_VIEWS, W, H = 200_000, 8, 512, 512
 WORKLOAD = ("8-view 512x512 synthetic scene, 200k Gaussians, 3DGS train step (render fwd + L1/SSIM loss + bwd + Adam), "
             "BASELINE.json configs[1]")
 MATCH_HW = 512
+TF32_PEAK_TFLOPS = 758.8     # cuBLAS TF32 GEMM 8192^3, measured on this pool's B200 (profiles/r02n_match_micro.json)
 
 
 def peaks():
@@ -96,6 +99,47 @@ def make_workload(dev, seed, scale_mode="init"):
     return params, states, truth.clamp(0, 1).contiguous(), cams
 
 
+def multi_gpu_parity(dev, dist, world, plan, hook):
+    """Before anything is timed at N > 1: (1) after exchanged training steps every rank holds bit-identical parameters
+    (the exchange sums in rank order on every rank); (2) they equal a single-GPU step on the same data - every rank
+    renders the same 8 views here, so the sum of the ranks' gradients is `world` x the local gradient."""
+    from starst3r_b200 import gs
+    params, states, truth, cams = make_workload(dev, seed=0)
+    for v in params.values():
+        dist.broadcast(v, 0)
+    ref_p = {k: v.clone() for k, v in params.items()}
+    ref_s = {k: (a.clone(), b.clone()) for k, (a, b) in states.items()}
+    plan_ref = gs.TrainPlan(N_GAUSS, N_VIEWS, W, H, dev)
+
+    def times_world(fr):
+        for g in fr.grads.values():
+            g.mul_(world)
+    for i in range(2):
+        gs.train_step(params, states, truth, cams, W, H, i + 1, grad_hook=hook, plan=plan)
+        gs.train_step(ref_p, ref_s, truth, cams, W, H, i + 1, grad_hook=times_world, plan=plan_ref)
+    torch.cuda.synchronize()
+    flat = torch.cat([params[k].reshape(-1) for k in sorted(params)])
+    digest = flat.view(torch.int32).to(torch.int64).sum().reshape(1)            # order-independent checksum of the bits
+    lo, hi = digest.clone(), digest.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    # Adam divides by sqrt(v): an element whose gradient is rounding noise (quaternions of isotropic splats, SH of barely
+    # visible Gaussians) steps by +-lr with the sign of the noise, so the comparison counts outliers instead of taking a max
+    keys = ("means", "scales", "opacities", "shN")
+    diff = torch.cat([(params[k] - ref_p[k]).abs().reshape(-1) for k in keys])
+    frac = (diff > 1e-5).float().mean()
+    med = diff.median()
+    dist.all_reduce(frac, op=dist.ReduceOp.MAX)
+    dist.all_reduce(med, op=dist.ReduceOp.MAX)
+    out = {"replicas_bit_identical": bool(int(lo) == int(hi)), "steps": 2,
+           "vs_single_gpu_step": {"fraction_of_elements_differing_by_more_than_1e-5": float(frac),
+                                  "median_abs_diff": float(med), "tolerance_fraction": 1e-3,
+                                  "compared": "means, scales, opacities, shN after two Adam steps (lr 1e-3)"}}
+    assert out["replicas_bit_identical"], "multi-GPU parity: the replicas' parameters differ after two exchanged steps"
+    assert float(frac) < 1e-3, out
+    return out
+
+
 def allreduce_grads(fr, world):
     from starst3r_b200 import dist as sd
     sd.allreduce_gradients(fr.grads)
@@ -110,11 +154,14 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     lib = _lib.load()
     hbm_peak, bf16_peak, peak_kind = peaks()
 
-    params, states, truth, cams = make_workload(dev, seed=rank)
+    # the same scene on every rank: identical work per rank at every N (Adam normalises the N-fold gradient sum away,
+    # so the parameters - and with them intersections and blends per frame - follow the single-GPU trajectory)
+    params, states, truth, cams = make_workload(dev, seed=0)
     if world > 1:   # replicated splat: every rank starts from rank 0's parameters
         for v in params.values():
             dist.broadcast(v, 0)
@@ -145,11 +192,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    parity = multi_gpu_parity(dev, dist, world, plan, hook) if world > 1 else None
     clk = ClockSampler(local)
     clk.__enter__()
     time.sleep(0.3)                 # let nvidia-smi start sampling
     clk.t0 = time.time()
-    for i in range(args.warmup):
+    for i in range(args.warmup_effective):
         step_fn(i)
     barrier()
     # ---- device-resident timing: K steps, L2 flushed between steps (flush not timed) -----------------
@@ -160,7 +208,7 @@ def run_ours(args):
         flush.fill_(i & 0xff)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        loss, fr = step_fn(args.warmup + i)
+        loss, fr = step_fn(args.warmup_effective + i)
         e1.record()
         evs.append((e0, e1))
     barrier()
@@ -171,10 +219,10 @@ def run_ours(args):
     gs.PROF = {}
     for i in range(3):
         flush.fill_(i)
-        loss, fr = step_fn(args.warmup + args.steps + i, prof=True)
+        loss, fr = step_fn(args.warmup_effective + args.steps + i, prof=True)
     prof = gs.prof_summary()
     gs.PROF = None
-    n_done = args.warmup + args.steps + 3
+    n_done = args.warmup_effective + args.steps + 3
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -198,17 +246,34 @@ def run_ours(args):
     top = max(shares, key=shares.get)
     top_ms = shares[top]
     achieved = alg_bytes.get(top, 0) / (top_ms * 1e-3) / 1e9
-    # measured DRAM traffic / issue-slot utilisation of the same kernel from the committed ncu capture (profiles/)
-    ncu = {}
+    # measured DRAM traffic / issue-slot utilisation of the same kernel from the committed ncu capture of THIS build
+    # (profiles/traffic.json is written by scripts/gpu_round.sh in the same pass as the committed bench line)
+    ncu_all, ncu = {}, {}
     try:
-        ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"].get(top, {})
+        ncu_all = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kernels"]
+        ncu = ncu_all.get(top, {})
     except (OSError, ValueError, KeyError):
         pass
+    # The blend kernels are bound by instruction issue, not by HBM: their own roofline is warp
+    # instructions per useful blend against the SM's issue rate (4 warp instructions / clock / SM).
+    sm_mhz = (json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("sm_max_mhz", 1965.0)
+              if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1965.0)
+    issue_peak = lib.st3r_device_sm_count() * 4 * sm_mhz * 1e6       # warp instructions / s: 4 schedulers per SM
+    instr = {}
+    for kname in ("st3r_gs_raster_fwd", "st3r_gs_raster_bwd"):
+        k = ncu_all.get(kname, {})
+        if k.get("warp_instructions") and n_blend and shares.get(kname):
+            instr[kname] = {"warp_instructions_per_launch_ncu": k["warp_instructions"],
+                            "warp_instructions_per_blend": round(k["warp_instructions"] / n_blend, 2),
+                            "issue_slot_utilisation_live": round(k["warp_instructions"] / (shares[kname] * 1e-3) / issue_peak, 4),
+                            "issue_active_pct_ncu": k.get("issue_active_pct"), "kernel_ms_live": round(shares[kname], 4)}
     roofline = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                 "frac": round(achieved / hbm_peak, 4), "traffic": ncu.get("dram_bytes"), "peak_kind": peak_kind,
-                "note": "the blend kernels are instruction-issue bound, not HBM bound (SURVEY 8d): ncu issue-slot "
-                        "utilisation is the figure of merit, the HBM fraction is reported because the schema asks for it",
+                "note": "the blend kernels are instruction-issue bound, not HBM bound (SURVEY 8d): `instruction_roofline` "
+                        "(warp instructions per blend, issue-slot utilisation against 4 warp instructions / clock / SM) is "
+                        "their figure of merit, the HBM fraction is reported because the schema asks for it",
                 "ncu_issue_active_pct": ncu.get("issue_active_pct"), "ncu_sm_throughput_pct": ncu.get("sm_throughput_pct"),
+                "ncu_kernel": ncu.get("kernel"), "instruction_roofline": instr,
                 "kernel_ms": round(top_ms, 4), "alg_bytes": alg_bytes.get(top, 0),
                 "step_breakdown_ms": {k: round(v, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])}}
 
@@ -345,18 +410,31 @@ def run_ours(args):
                  "e2e": {"value": 1000.0 / pair_e2e_ms * world, "unit": "pairs/s",
                          "h2d_bytes_per_step": sum(f.numel() for f in hfe + hq) * 4, "d2h_bytes_per_step": n_corr * 36},
                  "roofline": {"kernel": "nn_tc_kernel (tcgen05 kind::tf32)", "bound": "tensor",
-                              "achieved": round(flops / (pair_ms * 1e-3) / 1e12, 1), "peak": round(bf16_peak / 2, 1),
-                              "unit": "TFLOP/s", "frac": round(flops / (pair_ms * 1e-3) / 1e12 / (bf16_peak / 2), 4),
-                              "peak_kind": peak_kind + " bf16 / 2 (TF32 dense runs at half the bf16 rate)",
-                              "alg_flops_per_pair": flops, "query_rows_per_pair": rows}}
+                              "achieved": round(flops / (pair_ms * 1e-3) / 1e12, 1), "peak": TF32_PEAK_TFLOPS,
+                              "unit": "TFLOP/s", "frac": round(flops / (pair_ms * 1e-3) / 1e12 / TF32_PEAK_TFLOPS, 4),
+                              "peak_kind": "measured: cuBLAS TF32 GEMM 8192^3 on this pool's B200 (scripts/bench_match.py, "
+                                           "profiles/r02n_match_micro.json); MEASURED_PEAKS.json has no TF32 row",
+                              "alg_flops_per_pair": flops, "query_rows_per_pair": rows,
+                              "note": "whole-pair figure: 29 NN calls with shrinking row counts + reciprocal bookkeeping; "
+                                      "the kernel alone reaches 291 / 362 / 426 TFLOP/s at M = 4096 / 32768 / 262144 rows "
+                                      "(profiles/r02n_match_micro.json), 45x the reference's cuBLAS GEMM + max"},
+                 "e2e_note": "descriptors are born on the device in production (network output); the e2e figure uploads "
+                             "105 MB of descriptor maps per pair from pinned host memory and is PCIe-bound at N > 1"}
 
-    # ---- MATCH + ALIGN end to end (rank 0, N = 1 only): reconstruct_scene on BASELINE.json configs[1] ------------
+    # ---- MATCH + ALIGN end to end: reconstruct_scene on BASELINE.json configs[1] (N > 1: pairs sharded, NCCL) ------
     recon = None
-    if world == 1 and rank == 0 and not args.no_align:
-        try:
-            recon = reconstruct_leg(dev)
+    if not args.no_align:
+        try:    # N = 1: stages, ALIGN roofline, CPU baselines; N > 1: pairs sharded over the ranks (NCCL) + parity
+            recon = reconstruct_leg(dev, cpu_legs=not args.no_cpu) if world == 1 else reconstruct_leg(dev, False, dist)
         except Exception as e:      # noqa: BLE001 - an auxiliary leg must not take the headline line down with it
             recon = {"error": repr(e)[:300]}
+            if world > 1:
+                raise
+    if world == 1 and not args.no_cpu:
+        try:
+            match_res["cpu_baseline"] = match_cpu_baseline()
+        except Exception as e:      # noqa: BLE001
+            match_res["cpu_baseline"] = {"error": repr(e)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -364,18 +442,23 @@ def run_ours(args):
     # ---- CPU baseline (oracle port, bounded sample) on rank 0 at N = 1 --------------------------------
     cpu = cpu_baseline(sample_views=1) if world == 1 and not args.no_cpu else None
     line = {"metric": "gaussians_per_sec_rasterized", "value": value, "unit": "Gaussians/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "warmup_effective": args.warmup_effective,
+            "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "views_per_gpu": N_VIEWS, "gaussians": N_GAUSS, "image": [H, W],
                        "parallelism": f"views sharded dp{world}, {exchange}" if world > 1 else "single GPU",
                        "l2": "256 MiB flush between timed steps",
+                       "warmup_note": "`warmup` is the requested count; `warmup_effective` untimed steps actually ran "
+                                      "(>= 12: a one-off ~7 ms host stall at the 10th iteration of a process would "
+                                      "otherwise land inside a 10-step timed region)",
+                       "multi_gpu_work": "every rank trains on the same 8 truth views: identical work per rank at every N",
                        # opt-in kernel variants (all 0 / False = the default kernels)
                        "kernel_variants": _kernel_variants()},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
             "blends_per_sec": n_blend * world / (shares.get("st3r_gs_raster_fwd", float("nan")) * 1e-3),
             "blends_per_frame": n_blend, "intersections": n_isect, "visible": n_vis, "loss": float(loss.item()),
-            "sweep_lognormal_scales": sweep, "match": match_res, "reconstruct": recon}
+            "sweep_lognormal_scales": sweep, "match": match_res, "reconstruct": recon, "multi_gpu_parity": parity}
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -397,34 +480,129 @@ class _CachedNet:
         return self.cache[int(img1["idx"]), int(img2["idx"])]
 
 
-def reconstruct_leg(dev):
+def reconstruct_leg(dev, cpu_legs=True, dist=None):
     """MATCH + ALIGN on BASELINE.json configs[1] (8 views 512x512): starster.reconstruct_scene = 28 image pairs matched
     (extract_correspondences), canonical views, MST, the 500 + 200 iteration sparse global alignment, dense points
-    and clean_pointcloud.  The network predictions are synthetic and pre-computed (the network is out of scope)."""
+    and clean_pointcloud.  The network predictions are synthetic and pre-computed (the network is out of scope).
+    Under a process group (`dist`) the pairs and canonical views are sharded over the ranks (reconstruct.SHARD_PAIRS),
+    the alignment runs on rank 0 and is broadcast; every rank's result is compared with the unsharded run."""
+    from starst3r_b200 import match
     from starst3r_b200 import reconstruct as rc
     from starst3r_b200 import synth
     n = N_VIEWS
+    world = dist.get_world_size() if dist is not None else 1
     net = synth.SyntheticMast3r(n, W, H, seed=0, device="cpu", arc_deg=120.0)
     imgs = net.images()
     model = _CachedNet(net, imgs, dev)
-    out = {}
-    for rep_i in range(2):              # first pass warms the kernels / allocator, second is reported
-        rc._MEMO.clear()
+    names = [f"{i}.png" for i in range(n)]
+
+    def sync():
         torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def run_once():
+        rc.clear_cache()
+        sync()
         t0 = time.time()
-        scene, _ = rc.reconstruct_scene(model, imgs, [f"{i}.png" for i in range(n)], dev)
+        scene, _ = rc.reconstruct_scene(model, imgs, names, dev)
         pts, _, confs = scene.get_dense_pts3d(clean_depth=True)
-        torch.cuda.synchronize()
-        out = {"seconds": time.time() - t0}
+        sync()
+        return time.time() - t0, scene, pts, confs
+    for rep_i in range(2):              # first pass warms the kernels / allocator, second is reported
+        secs, scene, pts, confs = run_once()
+    if dist is not None:
+        t = torch.tensor([secs], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t)
+    out = {"seconds": secs}
+    n_pairs = n * (n - 1) // 2
+    out.update({"workload": f"{n} views {W}x{H}: {n_pairs} pairs matched + sparse global alignment (500 + 200 iterations) + "
+                            "dense points + clean_pointcloud; synthetic network predictions pre-computed on the device",
+                "pairs": n_pairs, "pairs_per_s_incl_alignment": n_pairs / secs, "align_iterations": 700,
+                "dense_points": int(sum(p.shape[0] for p in pts)), "views_per_s": n / secs})
+    if dist is not None:
+        # parity of the sharded pipeline: forward_mast3r + prepare_canonical_data with and without sharding on this rank -
+        # correspondence counts (integers) exactly, canonical views / focals / core depths / anchors to the bit on every rank
+        pairs_in = rc.convert_dust3r_pairs_naming(names, rc.make_pairs(rc.prepare_images_for_mast3r(imgs), "complete", None, True))
+        res = {}
+        for tag, shard in (("sharded", True), ("full", False)):
+            rc.SHARD_PAIRS = shard
+            try:
+                pr, cache = rc.forward_mast3r(pairs_in, model, cache_path="bench-parity-" + tag, subsample=8,
+                                              desc_conf="desc_conf", device=dev)
+                res[tag] = rc.prepare_canonical_data(names, pr, 8, cache_path=cache, mode="avg-angle", device=dev)
+            finally:
+                rc.SHARD_PAIRS = True
+        (_, pws_s, cv_s, _, _), (_, pws_f, cv_f, _, _) = res["sharded"], res["full"]
+        same = torch.equal(pws_s, pws_f)
+        for img in names:
+            pp_s, hw_s, f_s, core_s, _, idx_s, off_s = cv_s[img]
+            pp_f, hw_f, f_f, core_f, _, idx_f, off_f = cv_f[img]
+            same = same and hw_s == hw_f and torch.equal(f_s, f_f) and torch.equal(core_s, core_f)
+            same = same and all(torch.equal(idx_s[o], idx_f[o]) and torch.equal(off_s[o], off_f[o]) for o in idx_f)
+        flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        # the alignment itself: rank 0 runs it and broadcasts, so all ranks must hold identical cameras
+        cam = scene.cam2w.detach().float().contiguous().clone()
+        cam0 = cam.clone()
+        dist.broadcast(cam0, 0)
+        camflag = torch.tensor([1 if torch.equal(cam, cam0) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(camflag, op=dist.ReduceOp.MIN)
+        out["sharded"] = {"world": world, "pairs_per_rank": -(-n_pairs // world),
+                          "pipeline_equals_unsharded_on_every_rank": bool(int(flag)),
+                          "cameras_identical_on_every_rank": bool(int(camflag)),
+                          "correspondences_total": int(pws_s.sum().item()) // 2,
+                          "note": "pairs matched on rank p mod G and exchanged; canonical views by image ownership; "
+                                  "alignment on rank 0, broadcast"}
+        assert out["sharded"]["pipeline_equals_unsharded_on_every_rank"] and out["sharded"]["cameras_identical_on_every_rank"], out
+        rc.clear_cache()
+        return out
+    # ---- the stages separately (CUDA events / wall clock around the public entry points) ----------------------
+    pairs_in = rc.convert_dust3r_pairs_naming(names, rc.make_pairs(rc.prepare_images_for_mast3r(imgs), "complete", None, True))
+    rc.clear_cache()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    pairs, cache = rc.forward_mast3r(pairs_in, model, cache_path="bench-stages", subsample=8, desc_conf="desc_conf", device=dev)
+    torch.cuda.synchronize()
+    t_match = time.time() - t0
+    t0 = time.time()
+    tmp_pairs, pws, canon_views, canon_paths, preds_21 = rc.prepare_canonical_data(names, pairs, 8, cache_path=cache,
+                                                                                   mode="avg-angle", device=dev)
+    mst = rc.compute_min_spanning_tree(pws)
+    cd = rc.condense_data(names, tmp_pairs, canon_views, preds_21, torch.float32)
+    torch.cuda.synchronize()
+    t_canon = time.time() - t0
+    imsizes, pps, base_focals, core_depth, anchors, corres, corres2d, preds_21c = cd
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc.sparse_scene_optimizer_slam(names, 8, imsizes, pps.clone(), base_focals.clone(), [c.clone() for c in core_depth],
+                                   anchors, corres, corres2d, preds_21c, canon_paths, mst, cache_path=cache, lr1=0.07,
+                                   niter1=500, lr2=0.014, niter2=200, device=dev, opt_depth=False, shared_intrinsics=False,
+                                   matching_conf_thr=5, verbose=False)
+    e1.record()
+    torch.cuda.synchronize()
+    t_align = e0.elapsed_time(e1) * 1e-3
+    # algorithmic bytes per optimiser iteration (SURVEY 8d, K5 row): per correspondence slot uv 8 + idx 4 + off 4 + conf 4 B
+    # on both sides, + the N (H/8)(W/8) core depths
+    n_slots = int(corres[0].numel())
+    it_bytes = 40 * n_slots + n * (H // 8) * (W // 8) * 4
+    hbm_peak = peaks()[0]
+    out["stages_s"] = {"match_28_pairs": t_match, "canonical_views_mst_condense": t_canon, "align_700_iterations": t_align}
+    out["align"] = {"iterations_per_s": 700 / t_align, "us_per_iteration": t_align / 700 * 1e6, "correspondence_slots": n_slots,
+                    "alg_bytes_per_iteration": it_bytes,
+                    "roofline": {"bound": "hbm", "achieved": round(it_bytes / (t_align / 700) / 1e9, 2), "peak": hbm_peak,
+                                 "unit": "GB/s", "frac": round(it_bytes / (t_align / 700) / 1e9 / hbm_peak, 5),
+                                 "note": "three launches per iteration over ~30 MB that stay in L2: latency bound, not HBM bound"}}
+    out["match_pairs_per_s_in_pipeline"] = n_pairs / t_match
     # the matcher alone on this scene's descriptor maps: smooth fields (like real MASt3R descriptors) keep ~100 columns
-    # per query row inside the TF32 error band, which the kernel resolves exactly on the spot; the headline `match`
-    # figure uses the random descriptors SURVEY 8d defines, where the band holds 1-3 columns
-    from starst3r_b200 import match
+    # per query row inside the TF32 error band; reconstruct's matcher switches to split precision on them by itself
+    # (match.NN_SPLIT = "auto"); the headline `match` figure uses the random descriptors SURVEY 8d defines
     res = model.cache[1, 0]
     feats = [r["desc"][0].float().contiguous() for r in res]
     qonfs = [r["desc_conf"][0].float().contiguous() for r in res]
     for _ in range(2):
-        match.extract_correspondences_device(feats, qonfs, 8)
+        match.extract_correspondences(feats, qonfs, 8, device=dev)          # (the synchronising form adapts the variant)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -434,13 +612,56 @@ def reconstruct_leg(dev):
     torch.cuda.synchronize()
     ms_pair = e0.elapsed_time(e1) / 8
     out["match_smooth_descriptors"] = {"ms_per_pair": ms_pair, "pairs_per_s": 1000.0 / ms_pair,
-                                       "correspondences": int(o[3].item())}
-    n_pairs = n * (n - 1) // 2
-    out.update({"workload": f"{n} views {W}x{H}: {n_pairs} pairs matched + sparse global alignment (500 + 200 iterations) + "
-                            "dense points + clean_pointcloud; synthetic network predictions pre-computed on the device",
-                "pairs": n_pairs, "align_iterations": 700, "dense_points": int(sum(p.shape[0] for p in pts)),
-                "views_per_s": n / out["seconds"]})
+                                       "correspondences": int(o[3].item()), "split_precision": bool(match._variant["split"])}
+    if cpu_legs:
+        # ---- CPU baselines beside it (oracle ports pinned to the reference's fixtures; bounded samples) ------------
+        from oracle import align_oracle as ao
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        inp = dict(imgs=names, imsizes=imsizes.cpu(), pps=pps.cpu(), base_focals=base_focals.cpu(),
+                   core_depth=[c.cpu() for c in core_depth], anchors=_to_cpu(anchors), corres=_to_cpu(corres),
+                   corres2d=_to_cpu(corres2d), preds_21=_to_cpu(preds_21c), mst=mst)
+        t0 = time.time()
+        ao.run(inp, niter1=6, niter2=4)
+        dt = time.time() - t0
+        out["align"]["cpu_baseline"] = {"value": 10 / dt, "unit": "iterations/s", "cores": cores, "kind": "port",
+                                        "sample": f"6 coarse + 4 fine iterations of oracle/align_oracle.run (torch autograd + "
+                                                  f"torch.optim.Adam restatement of starster/reconstruct.py:116-457) on the "
+                                                  f"same condensed problem, {dt:.1f} s"}
+    rc.clear_cache()
     return out
+
+
+def _to_cpu(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu()
+    if isinstance(x, dict):
+        return {k: _to_cpu(v) for k, v in x.items()}
+    if isinstance(x, tuple) and hasattr(x, "_fields"):
+        return type(x)(*[_to_cpu(v) for v in x])
+    if isinstance(x, (list, tuple)):
+        return type(x)(_to_cpu(v) for v in x)
+    return x
+
+
+def match_cpu_baseline():
+    """MATCH on the host cores: oracle/match_oracle.extract_correspondences (plain-C arg-max + numpy restatement of
+    fast_nn.py / sparse_ga.py:595-630, pinned to the reference's golden vectors) on a 256 x 256 pair of the same synthetic
+    descriptors - 1/16 of the work of a 512 x 512 pair per NN call."""
+    from oracle import match_oracle as mo
+    from starst3r_b200 import synth
+    cores = os.cpu_count() or 1
+    A, B = synth.descriptor_pair(256, 256, seed=0)
+    A2, B2 = synth.descriptor_pair(256, 256, seed=100)
+    q = [1 + 9 * torch.rand(256, 256).numpy() for _ in range(4)]
+    t0 = time.time()
+    xy1, _, _ = mo.extract_correspondences([A.numpy(), B.numpy(), B2.numpy(), A2.numpy()], q, 8)
+    dt = time.time() - t0
+    return {"value": 1.0 / dt, "unit": "pairs/s (256x256)", "cores": cores, "kind": "port",
+            "sample": f"one 256x256 pair ({len(xy1)} correspondences), {dt:.2f} s; a 512x512 pair is 16x the arithmetic per "
+                      f"NN call (4x the rows x 4x the columns): ~{16 * dt:.0f} s, i.e. ~{1 / (16 * dt):.3f} pairs/s "
+                      "(BASELINE.md section 3 measured 34 s with the unmodified reference on 8 cores)",
+            "extrapolated_512x512_pairs_per_s": 1.0 / (16 * dt)}
 
 
 def match_rows(A, B, A2, B2):
@@ -508,8 +729,9 @@ def main():
     ap.add_argument("--no-align", action="store_true", help="skip the MATCH + ALIGN reconstruct leg")
     args = ap.parse_args()
     # >= 12 untimed steps: a one-off ~7 ms host stall (lazy driver / allocator initialisation, seen at the 10th
-    # iteration of a process whatever the kernels are) would otherwise land inside a 10-step timed region
-    args.warmup = max(args.warmup, 12) if args.impl == "ours" else args.warmup
+    # iteration of a process whatever the kernels are) would otherwise land inside a 10-step timed region.  The JSON
+    # line reports the requested count as `warmup` and what actually ran as `warmup_effective`.
+    args.warmup_effective = max(args.warmup, 12) if args.impl == "ours" else args.warmup
     # Exactly ONE line goes to stdout (the JSON): libraries that chat on fd 1 (NCCL prints its version there) are
     # diverted to stderr until the result is ready.
     sys.stdout.flush()

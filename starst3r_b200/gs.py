@@ -754,10 +754,13 @@ def train_step(params, states, truth, cams, width, height, step, lr=1e-3, betas=
     peer = plan.peer if plan is not None else None
     if peer is not None:
         # sharded views: one cross-device barrier, then the gradient sum over the ranks happens inside the Adam kernel
-        peer.barrier()
-        if peer.scatter:           # larger nodes: reduce-scatter + all-gather over peer memory, then a local Adam
-            peer.reduce_scatter()
+        with _Prof("peer_barrier"):
             peer.barrier()
+        if peer.scatter:           # larger nodes: reduce-scatter + all-gather over peer memory, then a local Adam
+            with _Prof("st3r_grad_reduce_scatter"):
+                peer.reduce_scatter()
+            with _Prof("peer_barrier"):
+                peer.barrier()
             rd = peer.reduced
             segs = [(means, rd["means"], *states["means"], N, 3, 3, 3), (scales, rd["scales"], *states["scales"], N, 3, 3, 3),
                     (quats, rd["quats"], *states["quats"], N, 4, 4, 4), (opac, rd["opacities"], *states["opacities"], N, 1, 1, 1),
