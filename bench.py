@@ -83,17 +83,19 @@ class ClockSampler:
                 "samples": len(sm), "window": "warm-up + timed steps + e2e + match legs (GPU busy throughout)"}
 
 
-def make_workload(dev, seed, scale_mode="init"):
+def make_workload(dev, seed, scale_mode="init", n_gauss=None, n_views=None, width=None, height=None):
     from starst3r_b200 import gs, synth
-    viewmats, Ks = synth.look_at_cameras(N_VIEWS, W, H, device=dev)
-    target = synth.random_splats(N_GAUSS, seed=seed, scale_mode=scale_mode, device=dev)
+    n_gauss, n_views = n_gauss or N_GAUSS, n_views or N_VIEWS
+    width, height = width or W, height or H
+    viewmats, Ks = synth.look_at_cameras(n_views, width, height, device=dev)
+    target = synth.random_splats(n_gauss, seed=seed, scale_mode=scale_mode, device=dev)
     with torch.no_grad():
         truth, _, _ = gs.rasterization(target["means"], target["quats"], target["scales"], target["opacities"],
-                                       target["shN"], viewmats, Ks, W, H)
+                                       target["shN"], viewmats, Ks, width, height)
     g = torch.Generator().manual_seed(seed + 1)
     params = {k: v.clone().contiguous() for k, v in target.items()}
-    params["means"] += 0.01 * torch.randn(N_GAUSS, 3, generator=g).to(dev)        # start off the optimum
-    params["shN"] += 0.1 * torch.randn(N_GAUSS, 24, 3, generator=g).to(dev)
+    params["means"] += 0.01 * torch.randn(n_gauss, 3, generator=g).to(dev)        # start off the optimum
+    params["shN"] += 0.1 * torch.randn(n_gauss, 24, 3, generator=g).to(dev)
     states = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in params.items()}
     cams = gs.make_cams(viewmats, Ks)
     return params, states, truth.clamp(0, 1).contiguous(), cams
@@ -140,6 +142,64 @@ def multi_gpu_parity(dev, dist, world, plan, hook):
     return out
 
 
+LARGE_CONFIGS = {   # BASELINE.json configs[2] / configs[3]: 8 views per GPU of the named scene, splat replicated
+    4: dict(name="configs[2]: 32 views 1024x768, 1M Gaussians, 4 GPUs", n_gauss=1_000_000, width=1024, height=768),
+    8: dict(name="configs[3]: 64 views 1920x1072 (1080p cropped to /16), 3M Gaussians, 8 GPUs", n_gauss=3_000_000,
+            width=1920, height=1072),
+}
+
+
+def large_config_leg(dev, dist, world):
+    """The training step at the size BASELINE.json names for this GPU count: 8 views per rank, the splat replicated,
+    gradients exchanged over peer memory / NVLS.  3 + 5 steps (device-timed, max over ranks); per-entry-point breakdown
+    with the exchange; achieved bytes/s of the exchange per GPU."""
+    from starst3r_b200 import dist as sd
+    from starst3r_b200 import gs
+    cfg = LARGE_CONFIGS[world]
+    ng, w, h = cfg["n_gauss"], cfg["width"], cfg["height"]
+    params, states, truth, cams = make_workload(dev, seed=0, n_gauss=ng, n_views=N_VIEWS, width=w, height=h)
+    for v in params.values():
+        dist.broadcast(v, 0)
+    plan = gs.TrainPlan(ng, N_VIEWS, w, h, dev)
+    plan.peer = sd.PeerGradExchange(ng, dev)
+    for i in range(3):
+        gs.train_step(params, states, truth, cams, w, h, i + 1, plan=plan)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(5):
+        gs.train_step(params, states, truth, cams, w, h, 4 + i, plan=plan)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gs.PROF = {}
+    for i in range(3):
+        _, fr = gs.train_step(params, states, truth, cams, w, h, 9 + i, plan=plan, count_blends=True)
+    prof = gs.prof_summary()
+    gs.PROF = None
+    shares = {k: v[1] / max(v[0], 1) for k, v in prof.items()}
+    ex_ms = sum(v for k, v in shares.items() if k in ("peer_barrier", "st3r_grad_reduce_scatter"))
+    # peer_barrier is recorded twice per step in the reduce-scatter form: prof_summary averages per call
+    ex_ms = shares.get("st3r_grad_reduce_scatter", 0.0) + 2 * shares.get("peer_barrier", 0.0)
+    grad_bytes = 4 * sd.PeerGradExchange.FLOATS * ng
+    nvls = bool(plan.peer.multimem)
+    per_gpu = grad_bytes / world * 2 if nvls else grad_bytes * 2 * (world - 1) / world
+    out = {"workload": cfg["name"] + f"; {N_VIEWS} views per GPU", "ms_per_step": float(t),
+           "gaussians_per_sec": ng * N_VIEWS * world / (float(t) * 1e-3), "intersections_per_rank": fr.n_isect,
+           "blends_per_frame_per_rank": int(fr.n_blend.item()),
+           "step_breakdown_ms": {k: round(v, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])},
+           "exchange": {"form": "NVLS multimem reduce-scatter + all-gather" if nvls else "P2P reduce-scatter + all-gather",
+                        "gradient_bytes": grad_bytes, "ms_per_step_incl_two_barriers": round(ex_ms, 4),
+                        "nvlink_bytes_per_gpu_per_step": int(per_gpu),
+                        "achieved_GBps_per_gpu": round(per_gpu / max(shares.get("st3r_grad_reduce_scatter", 1e-9), 1e-9) / 1e6, 1)}}
+    del params, states, truth, plan
+    torch.cuda.empty_cache()
+    return out
+
+
 def allreduce_grads(fr, world):
     from starst3r_b200 import dist as sd
     sd.allreduce_gradients(fr.grads)
@@ -175,9 +235,14 @@ def run_ours(args):
         try:
             from starst3r_b200 import dist as sd
             plan.peer = sd.PeerGradExchange(N_GAUSS, dev)
-            exchange = ("P2P reduce-scatter + all-gather of the gradient sum over NVLink peer memory (st3r_grad_reduce_scatter) "
-                        "+ Adam" if plan.peer.scatter else
-                        "fused P2P gradient sum + Adam (st3r_adam_step_peers, NVLink peer loads)")
+            if plan.peer.scatter and plan.peer.multimem:
+                exchange = ("in-switch reduce-scatter + all-gather of the gradient sum (NVLS: multimem.ld_reduce / multimem.st on "
+                            "NVSwitch multicast memory, st3r_grad_reduce_multimem) + Adam")
+            elif plan.peer.scatter:
+                exchange = ("P2P reduce-scatter + all-gather of the gradient sum over NVLink peer memory "
+                            "(st3r_grad_reduce_scatter) + Adam")
+            else:
+                exchange = "fused P2P gradient sum + Adam (st3r_adam_step_peers, NVLink peer loads)"
         except Exception as e:      # noqa: BLE001
             print(f"bench: symmetric memory unavailable ({e!r}); using NCCL all-reduce", file=sys.stderr)
             hook = lambda fr: allreduce_grads(fr, world)
@@ -430,6 +495,9 @@ def run_ours(args):
             recon = {"error": repr(e)[:300]}
             if world > 1:
                 raise
+    large = None
+    if world in LARGE_CONFIGS and not args.no_large:
+        large = large_config_leg(dev, dist, world)
     if world == 1 and not args.no_cpu:
         try:
             match_res["cpu_baseline"] = match_cpu_baseline()
@@ -458,7 +526,8 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu,
             "blends_per_sec": n_blend * world / (shares.get("st3r_gs_raster_fwd", float("nan")) * 1e-3),
             "blends_per_frame": n_blend, "intersections": n_isect, "visible": n_vis, "loss": float(loss.item()),
-            "sweep_lognormal_scales": sweep, "match": match_res, "reconstruct": recon, "multi_gpu_parity": parity}
+            "sweep_lognormal_scales": sweep, "match": match_res, "reconstruct": recon, "multi_gpu_parity": parity,
+            "baseline_config_at_this_gpu_count": large}
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -727,6 +796,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-align", action="store_true", help="skip the MATCH + ALIGN reconstruct leg")
+    ap.add_argument("--no-large", action="store_true", help="skip the configs[2] / configs[3] sized leg at N = 4 / 8")
     args = ap.parse_args()
     # >= 12 untimed steps: a one-off ~7 ms host stall (lazy driver / allocator initialisation, seen at the 10th
     # iteration of a process whatever the kernels are) would otherwise land inside a 10-step timed region.  The JSON

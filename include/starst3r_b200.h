@@ -239,6 +239,13 @@ ST3R_API int st3r_adam_step_peers(int n_seg, float* const* h_params, const long 
 ST3R_API int st3r_grad_reduce_scatter(int world, int rank, const float* const* h_peer_grad_bases,
                              float* const* h_peer_reduced_bases, int64_t n_floats, cudaStream_t stream);
 
+/* NVLS form of st3r_grad_reduce_scatter: `mc_grads` / `mc_reduced` are the MULTICAST addresses of the symmetric gradient
+ * and `reduced` buffers (NVSwitch multicast objects, e.g. torch symmetric memory's multicast_ptr).  This rank sums its
+ * 1/world slice inside the switch (multimem.ld_reduce) and stores it to every rank (multimem.st): L / G floats in and
+ * L / G out per GPU.  Replicas receive identical values; the in-switch summation order is unspecified. */
+ST3R_API int st3r_grad_reduce_multimem(int world, int rank, const float* mc_grads, float* mc_reduced, int64_t n_floats,
+                              cudaStream_t stream);
+
 /* ------------------------------------------------------------------ MCMC strategy
  * gsplat.MCMCStrategy as driven by starster/gs.py:43-45 (construction), :146-147 (step_pre_backward, a no-op for
  * MCMC) and :163-164 (step_post_backward(..., lr=1e-3)); gsplat 1.4 strategy/mcmc.py + strategy/ops.py semantics

