@@ -186,15 +186,23 @@ def large_config_leg(dev, dist, world):
     ex_ms = shares.get("st3r_grad_reduce_scatter", 0.0) + 2 * shares.get("peer_barrier", 0.0)
     grad_bytes = 4 * sd.PeerGradExchange.FLOATS * ng
     nvls = bool(plan.peer.multimem)
-    per_gpu = grad_bytes / world * 2 if nvls else grad_bytes * 2 * (world - 1) / world
+    # NVLink bytes LEAVING each GPU per step.  Peer loads / stores: it serves the other ranks' reads of its buffer
+    # ((G-1)/G L) and stores its reduced slice to G-1 peers ((G-1)/G L).  NVLS: the switch pulls every element once from
+    # every GPU (L) and the GPU sends its reduced slice once, the switch replicates it (L / G); what NVLS saves is the
+    # receiving side: L / G + (G-1)/G L in instead of 2 (G-1)/G L.
+    egress = grad_bytes + grad_bytes / world if nvls else 2 * grad_bytes * (world - 1) / world
+    ingress = grad_bytes if nvls else 2 * grad_bytes * (world - 1) / world
+    rs_ms = shares.get("st3r_grad_reduce_scatter", 0.0)
     out = {"workload": cfg["name"] + f"; {N_VIEWS} views per GPU", "ms_per_step": float(t),
            "gaussians_per_sec": ng * N_VIEWS * world / (float(t) * 1e-3), "intersections_per_rank": fr.n_isect,
            "blends_per_frame_per_rank": int(fr.n_blend.item()),
            "step_breakdown_ms": {k: round(v, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])},
            "exchange": {"form": "NVLS multimem reduce-scatter + all-gather" if nvls else "P2P reduce-scatter + all-gather",
                         "gradient_bytes": grad_bytes, "ms_per_step_incl_two_barriers": round(ex_ms, 4),
-                        "nvlink_bytes_per_gpu_per_step": int(per_gpu),
-                        "achieved_GBps_per_gpu": round(per_gpu / max(shares.get("st3r_grad_reduce_scatter", 1e-9), 1e-9) / 1e6, 1)}}
+                        "nvlink_egress_bytes_per_gpu_per_step": int(egress), "nvlink_ingress_bytes_per_gpu_per_step": int(ingress),
+                        "achieved_egress_GBps_per_gpu": round(egress / max(rs_ms, 1e-9) / 1e6, 1),
+                        "nvlink5_peak_GBps_per_direction": 900.0,
+                        "share_of_step": round(ex_ms / float(t), 4)}}
     del params, states, truth, plan
     torch.cuda.empty_cache()
     return out
