@@ -188,10 +188,116 @@ __device__ __forceinline__ void bitonic_flip_sort(uint64_t* buf, int n, int nthr
   }
 }
 
+// ---- register-resident sort for segments up to 2048 pairs ------------------------------------------------------
+// (Round-2 profile of the shared-memory network above on the headline frame, 458 pairs per tile on average: 12.8 k
+// warp instructions per tile, 70 % of them index arithmetic, predicates and branches of the generic loops, the
+// memory accesses generic LD / ST because `buf` may point to either space.)  Here a thread holds EPT = P / 256
+// consecutive elements of the padded segment in registers and the same comparator network is unrolled at compile
+// time: comparators that stay inside a thread are register compare-exchanges, those inside a warp exchange through
+// __shfl_xor (the mirror step sends element EPT-1-e), and only the spans of 32 * EPT elements and more go through
+// shared memory (two alternating buffers, one barrier per step).  Same comparators, same +inf padding => the same
+// unique order (the 64-bit words are distinct).
+__device__ __forceinline__ void cmpswap(uint64_t& a, uint64_t& b) {
+  const uint64_t lo = a < b ? a : b, hi = a < b ? b : a;
+  a = lo; b = hi;
+}
+
+template <int EPT>
+__device__ __forceinline__ void reg_exchange_smem(uint64_t (&v)[EPT], uint64_t* sx, int& buf, int xor_mask, int low_bit) {
+  constexpr int P = SORT_THREADS * EPT;
+  uint64_t* b = sx + buf * P;
+  const int i0 = threadIdx.x * EPT;
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) b[i0 + e] = v[e];
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const int i = i0 + e;
+    const uint64_t o = b[i ^ xor_mask];
+    const bool keep_min = (i & low_bit) == 0;
+    v[e] = keep_min ? (v[e] < o ? v[e] : o) : (v[e] < o ? o : v[e]);
+  }
+  buf ^= 1;      // the next exchange writes the other buffer: no second barrier needed
+}
+
+// The network is unrolled through template recursion (K = block size of the stage, J = comparator span), so that every
+// register index and every step kind is a compile-time constant.
+template <int EPT, int J>
+struct HalfSteps {       // element i against i + J, then J / 2, ... 1
+  static __device__ __forceinline__ void run(uint64_t (&v)[EPT], uint64_t* sx, int& buf, int lane) {
+    if constexpr (J >= 1) {
+      if constexpr (J < EPT) {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e)
+          if ((e & J) == 0) cmpswap(v[e], v[e | J]);
+      } else if constexpr (J < 32 * EPT) {
+        constexpr int m = J / EPT;
+        const bool keep_min = (lane & m) == 0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          const uint64_t o = (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)v[e], m);
+          v[e] = keep_min ? (v[e] < o ? v[e] : o) : (v[e] < o ? o : v[e]);
+        }
+      } else {
+        reg_exchange_smem<EPT>(v, sx, buf, J, J);
+      }
+      HalfSteps<EPT, J / 2>::run(v, sx, buf, lane);
+    }
+  }
+};
+
+template <int EPT, int K>
+struct Stages {          // stages K, 2K, ... P
+  static __device__ __forceinline__ void run(uint64_t (&v)[EPT], uint64_t* sx, int& buf, int lane) {
+    if constexpr (K <= SORT_THREADS * EPT) {
+      // first step of the stage: element i against i ^ (K - 1) (mirror inside every block of K)
+      if constexpr (K <= EPT) {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e)
+          if ((e & (K >> 1)) == 0) cmpswap(v[e], v[e ^ (K - 1)]);
+      } else if constexpr (K <= 32 * EPT) {
+        constexpr int m = K / EPT - 1;                   // lane mask of the partner thread
+        const bool keep_min = (lane & ((m + 1) >> 1)) == 0;
+        uint64_t o[EPT];
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) o[e] = (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)v[EPT - 1 - e], m);
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) v[e] = keep_min ? (v[e] < o[e] ? v[e] : o[e]) : (v[e] < o[e] ? o[e] : v[e]);
+      } else {
+        reg_exchange_smem<EPT>(v, sx, buf, K - 1, K >> 1);
+      }
+      HalfSteps<EPT, K / 4>::run(v, sx, buf, lane);
+      Stages<EPT, K * 2>::run(v, sx, buf, lane);
+    }
+  }
+};
+
+template <int EPT>
+__device__ __forceinline__ void reg_bitonic_sort(uint64_t (&v)[EPT], uint64_t* sx) {
+  int buf = 0;
+  Stages<EPT, 2>::run(v, sx, buf, lane_id());
+}
+
+template <int EPT>
+__device__ __forceinline__ void reg_sort_segment(const uint64_t* __restrict__ seg, int n, uint64_t* sx, uint64_t key_hi,
+                                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  uint64_t v[EPT];
+  const int i0 = threadIdx.x * EPT;
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) v[e] = i0 + e < n ? seg[i0 + e] : ~0ull;       // +inf padding sorts to the end
+  reg_bitonic_sort<EPT>(v, sx);
+#pragma unroll
+  for (int e = 0; e < EPT; ++e)
+    if (i0 + e < n) {
+      keys[i0 + e] = key_hi | (v[e] >> 32);
+      vals[i0 + e] = (uint32_t)v[e];
+    }
+}
+
 __global__ void __launch_bounds__(SORT_THREADS)
 tile_sort_kernel(int32_t* offsets, const int32_t* __restrict__ total_ptr, int n_cells, int n_tiles,
                  int tile_n_bits, uint64_t* __restrict__ pairs, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                 int n_cap) {
+                 int n_cap, int reg_path) {
   __shared__ uint64_t sbuf[SMEM_ELEMS];
   const int cell = blockIdx.x;                       // camera * n_tiles + tile
   const int lo = min(offsets[cell], n_cap);
@@ -204,6 +310,13 @@ tile_sort_kernel(int32_t* offsets, const int32_t* __restrict__ total_ptr, int n_
   const int cam = cell / n_tiles, tile = cell - cam * n_tiles;
   const uint64_t key_hi = ((((uint64_t)cam << tile_n_bits) | (uint64_t)tile) << 32);
   uint64_t* seg = pairs + lo;
+  if (reg_path && n <= 8 * SORT_THREADS) {           // CTA-uniform
+    if (n <= SORT_THREADS) reg_sort_segment<1>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
+    else if (n <= 2 * SORT_THREADS) reg_sort_segment<2>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
+    else if (n <= 4 * SORT_THREADS) reg_sort_segment<4>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
+    else reg_sort_segment<8>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
+    return;
+  }
   uint64_t* buf = seg;
   if (n <= SMEM_ELEMS) {
     for (int i = threadIdx.x; i < n; i += SORT_THREADS) sbuf[i] = seg[i];
@@ -239,7 +352,17 @@ size_t carve_bin(BinWs* w, void* ws, size_t ws_bytes, int n_cells, int n_cap, bo
 }  // namespace
 
 #if !defined(ST3R_HOST_EMU) || defined(ST3R_EMU_WHOLE)
+// 1 (default): segments up to 2048 pairs are sorted in registers (reg_bitonic_sort); 0: always the shared-memory /
+// in-place network (the first implementation, kept as the cross-check: tests/test_gs_gpu.py runs both).
+static int g_bin_reg_sort = 1;
+
 extern "C" {
+
+int st3r_gs_bin_set_variant(int variant) {
+  ST3R_CHECK_ARG(variant == 0 || variant == 1, "st3r_gs_bin_set_variant: unknown variant %d", variant);
+  g_bin_reg_sort = variant;
+  return ST3R_OK;
+}
 
 size_t st3r_gs_bin_ws_bytes(int C, int width, int height, int tile_size, int n_cap) {
   if (C <= 0 || width <= 0 || height <= 0 || tile_size <= 0) return 256;
@@ -286,7 +409,7 @@ int st3r_gs_bin_tiles(const int32_t* radii, const float* geomA, int N, int C, in
                                                           w.pairs, n_cap, use_smem);
   ST3R_CHECK_LAUNCH();
   tile_sort_kernel<<<n_cells, SORT_THREADS, 0, stream>>>(offsets, n_isect_out, n_cells, n_tiles, gs_tile_bits(n_tiles),
-                                                         w.pairs, keys, vals, n_cap);
+                                                         w.pairs, keys, vals, n_cap, g_bin_reg_sort);
   ST3R_CHECK_LAUNCH();
   return ST3R_OK;
 }

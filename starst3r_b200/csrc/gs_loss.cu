@@ -14,23 +14,66 @@
 namespace {
 
 // Tiling: one CTA of 256 threads produces a 32 x 32 pixel tile of one view.  The 42 x 42 halo tile of all three
-// channels is loaded once, coalesced, from the interleaved [H,W,3] images into planar shared arrays; the separable
-// 11-tap window then runs per channel with register tiling: a thread of the horizontal pass produces 8 consecutive
-// columns of one row from 18 loaded inputs, a thread of the vertical pass 4 consecutive rows of one column from 14
-// (the first version loaded 11 inputs per output in both passes and three strided passes over global memory).
+// channels is loaded once (a warp per row, 126 consecutive floats of the interleaved [H,W,3] image, de-interleaved
+// into planar shared arrays with per-lane offsets computed once), then the separable 11-tap window runs per channel
+// with register tiling and vector shared-memory accesses: a thread of the horizontal pass produces 8 consecutive
+// columns of one row from 5 LDS.128 per operand (the squares / products are formed once per input, not per tap) and
+// stores them with STS.128; a thread of the vertical pass produces 4 consecutive rows of one column from 14 loaded
+// rows per statistic.  The row pitches (44 / 36 floats) keep every 128-bit access 16-byte aligned and bank-conflict
+// free for the (row, column group) -> lane mapping used here.  The window weights are compile-time immediates of the
+// FFMAs.  (Round-2 profile of the first version: 96 M warp instructions per launch at configs[1], 40 % of them
+// integer address arithmetic; this version executes about half.)
 constexpr int LT = 32;             // output tile edge
 constexpr int HALO = 5;
 constexpr int LW = LT + 2 * HALO;  // 42
-constexpr int LWP = LW + 1;        // padded row pitch of the input tiles
-constexpr int HSP = LT + 1;        // padded row pitch of the horizontally filtered rows
+constexpr int TP = 44;             // row pitch of the input tiles (floats)
+constexpr int HP = 36;             // row pitch of the horizontally filtered rows
 constexpr int NT = 256;
+constexpr int HITEMS = LW * (LT / 8);   // (row, group of 8 output columns) items of the horizontal pass
 constexpr float C1 = 0.01f * 0.01f;
 constexpr float C2 = 0.03f * 0.03f;
+static_assert(HITEMS <= NT && LT * (LT / 4) == NT * 1, "one horizontal item / one vertical item per thread");
 
 #ifndef ST3R_HOST_EMU            // (CPU emulator builds, tests/host/, define it themselves)
 #define ST3R_DYN_SMEM_F32(name) extern __shared__ float name[]
 #endif
-__constant__ float c_win[11];
+
+// 11-tap Gaussian window, sigma 1.5, normalised (torchmetrics _gaussian): exp(-((k-5)/1.5)^2 / 2) / sum, evaluated in
+// fp32 (0.0010283802, 0.0075987582, 0.036000773, 0.10936069, 0.21300554, 0.26601174 and their mirror images).
+#define ST3R_SSIM_W0 0x1.0d957p-10f
+#define ST3R_SSIM_W1 0x1.f1fdfap-8f
+#define ST3R_SSIM_W2 0x1.26eb18p-5f
+#define ST3R_SSIM_W3 0x1.bff0fep-4f
+#define ST3R_SSIM_W4 0x1.b43c4p-3f
+#define ST3R_SSIM_W5 0x1.106562p-2f
+
+// sum_k w[k] * v[k] for 11 consecutive values (k = 0 .. 10), in ascending-k order.
+__device__ __forceinline__ float win11(const float* v) {
+  float s = ST3R_SSIM_W0 * v[0];
+  s = fmaf(ST3R_SSIM_W1, v[1], s); s = fmaf(ST3R_SSIM_W2, v[2], s); s = fmaf(ST3R_SSIM_W3, v[3], s);
+  s = fmaf(ST3R_SSIM_W4, v[4], s); s = fmaf(ST3R_SSIM_W5, v[5], s); s = fmaf(ST3R_SSIM_W4, v[6], s);
+  s = fmaf(ST3R_SSIM_W3, v[7], s); s = fmaf(ST3R_SSIM_W2, v[8], s); s = fmaf(ST3R_SSIM_W1, v[9], s);
+  s = fmaf(ST3R_SSIM_W0, v[10], s);
+  return s;
+}
+
+// 8 consecutive window sums of v[0 .. 17] -> dst[0 .. 7] (two 128-bit stores; dst is 16-byte aligned).
+__device__ __forceinline__ void hconv8(const float* v, float* dst) {
+  float4 lo, hi;
+  lo.x = win11(v + 0); lo.y = win11(v + 1); lo.z = win11(v + 2); lo.w = win11(v + 3);
+  hi.x = win11(v + 4); hi.y = win11(v + 5); hi.z = win11(v + 6); hi.w = win11(v + 7);
+  reinterpret_cast<float4*>(dst)[0] = lo;
+  reinterpret_cast<float4*>(dst)[1] = hi;
+}
+
+// 20 consecutive floats of a 16-byte aligned shared-memory row (the pass uses the first 18).
+__device__ __forceinline__ void load20(const float* src, float* v) {
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const float4 t = reinterpret_cast<const float4*>(src)[k];
+    v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+  }
+}
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
   for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -45,68 +88,83 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return s;  // valid in thread 0
 }
 
-// Loads the halo tile of an interleaved [H,W,3] image into three planar [LW][LWP] arrays (zero outside the image).
-__device__ __forceinline__ void load_rgb_tile(const float* __restrict__ img, int H, int W, int x0, int y0, float* dst) {
-  for (int e = threadIdx.x; e < LW * LW * 3; e += NT) {
-    const int r = e / (LW * 3), q3 = e - r * (LW * 3);
-    const int q = q3 / 3, ch = q3 - q * 3;
-    const int gy = y0 + r - HALO, gx = x0 + q - HALO;
-    float v = 0.f;
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = img[((size_t)gy * W + gx) * 3 + ch];
-    dst[(ch * LW + r) * LWP + q] = v;
+// Halo tiles of TWO interleaved [H,W,3] images -> planar [3][LW][TP] arrays (zero outside the image).  A warp takes a
+// row: its 42 pixels are 126 consecutive floats in global memory, lane l reads floats l, l + 32, l + 64, l + 96.
+__device__ __forceinline__ void load_rgb_tiles(const float* __restrict__ img_a, const float* __restrict__ img_b, int H, int W,
+                                               int x0, int y0, float* dst_a, float* dst_b) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int soff[4], gx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int e = lane + 32 * j, q = e / 3, ch = e - 3 * q;
+    soff[j] = ch * LW * TP + q;
+    gx[j] = x0 - HALO + q;
+  }
+  for (int r = warp; r < LW; r += NT / 32) {
+    const int gy = y0 + r - HALO;
+    const bool row_ok = gy >= 0 && gy < H;
+    const long long gbase = ((long long)gy * W + (x0 - HALO)) * 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = lane + 32 * j;
+      if (e < LW * 3) {
+        float a = 0.f, b = 0.f;
+        if (row_ok && gx[j] >= 0 && gx[j] < W) { a = img_a[gbase + e]; b = img_b[gbase + e]; }
+        dst_a[soff[j] + r * TP] = a;
+        dst_b[soff[j] + r * TP] = b;
+      }
+    }
   }
 }
 
 // grid: (tiles_x, tiles_y, C); block: 256 threads.  dmaps is planar scratch: [C][channel 3][derivative 3][H][W].
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 2)
 ssim_l1_fwd_kernel(const float* __restrict__ render, const float* __restrict__ truth, int H, int W,
                    float coef_ssim /* dLoss/dS per interior sample */, float* __restrict__ dmaps,
                    float* __restrict__ sums /* per view: [ssim_sum, l1_sum] */) {
   ST3R_DYN_SMEM_F32(smem);
-  float* tx = smem;                         // [3][LW][LWP]
-  float* ty = tx + 3 * LW * LWP;            // [3][LW][LWP]
-  float* hs = ty + 3 * LW * LWP;            // [5][LW][HSP]
+  float* tx = smem;                         // [3][LW][TP]
+  float* ty = tx + 3 * LW * TP;             // [3][LW][TP]
+  float* hs = ty + 3 * LW * TP;             // [5][LW][HP]
   __shared__ float red[8];
   const int c = blockIdx.z;
   const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
   const size_t plane = (size_t)H * W;
-  load_rgb_tile(render + (size_t)c * plane * 3, H, W, x0, y0, tx);
-  load_rgb_tile(truth + (size_t)c * plane * 3, H, W, x0, y0, ty);
-  float w[11];
-#pragma unroll
-  for (int k = 0; k < 11; ++k) w[k] = c_win[k];
+  load_rgb_tiles(render + (size_t)c * plane * 3, truth + (size_t)c * plane * 3, H, W, x0, y0, tx, ty);
   const int vx = threadIdx.x & 31, vr0 = (threadIdx.x >> 5) * 4;     // vertical pass: column vx, rows vr0 .. vr0 + 3
   float ssim_acc = 0.f, l1_acc = 0.f;
   for (int ch = 0; ch < 3; ++ch) {
-    __syncthreads();
-    // horizontal pass: item = (row r, group of 8 output columns)
-    for (int it = threadIdx.x; it < LW * (LT / 8); it += NT) {
-      const int r = it >> 2, q0 = (it & 3) * 8;
-      const float* ax = tx + (ch * LW + r) * LWP + q0;
-      const float* ay = ty + (ch * LW + r) * LWP + q0;
-      float a[18], b[18];
+    __syncthreads();        // tiles loaded / the previous channel's vertical pass is done with hs
+    if (threadIdx.x < HITEMS) {
+      // horizontal pass: item = (row r, group of 8 output columns)
+      const int r = threadIdx.x >> 2, q0 = (threadIdx.x & 3) * 8;
+      float a[20], b[20], p[18];
+      load20(tx + (ch * LW + r) * TP + q0, a);
+      load20(ty + (ch * LW + r) * TP + q0, b);
+      float* hrow = hs + r * HP + q0;
+      hconv8(a, hrow);
+      hconv8(b, hrow + LW * HP);
 #pragma unroll
-      for (int k = 0; k < 18; ++k) { a[k] = ax[k]; b[k] = ay[k]; }
+      for (int k = 0; k < 18; ++k) p[k] = a[k] * a[k];
+      hconv8(p, hrow + 2 * LW * HP);
 #pragma unroll
-      for (int o = 0; o < 8; ++o) {
-        float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+      for (int k = 0; k < 18; ++k) p[k] = b[k] * b[k];
+      hconv8(p, hrow + 3 * LW * HP);
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
-          const float wa = w[k] * a[o + k], wb = w[k] * b[o + k];
-          sx += wa; sy += wb; sxx += wa * a[o + k]; syy += wb * b[o + k]; sxy += wa * b[o + k];
-        }
-        const int idx = r * HSP + q0 + o;
-        hs[idx] = sx; hs[LW * HSP + idx] = sy; hs[2 * LW * HSP + idx] = sxx; hs[3 * LW * HSP + idx] = syy;
-        hs[4 * LW * HSP + idx] = sxy;
-      }
+      for (int k = 0; k < 18; ++k) p[k] = a[k] * b[k];
+      hconv8(p, hrow + 4 * LW * HP);
     }
     __syncthreads();
-    // vertical pass: 4 output rows of one column from 14 filtered rows
-    float col[5][14];
+    // vertical pass: 4 output rows of one column from 14 filtered rows per statistic
+    float st[5][4];
 #pragma unroll
-    for (int st = 0; st < 5; ++st)
+    for (int s = 0; s < 5; ++s) {
+      float col[14];
 #pragma unroll
-      for (int k = 0; k < 14; ++k) col[st][k] = hs[st * LW * HSP + (vr0 + k) * HSP + vx];
+      for (int k = 0; k < 14; ++k) col[k] = hs[s * LW * HP + (vr0 + k) * HP + vx];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) st[s][o] = win11(col + o);
+    }
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
       const int px = x0 + vx, py = y0 + vr0 + o;
@@ -114,19 +172,14 @@ ssim_l1_fwd_kernel(const float* __restrict__ render, const float* __restrict__ t
       const bool interior = px >= HALO && px < W - HALO && py >= HALO && py < H - HALO;
       float dm = 0.f, ds = 0.f, dc = 0.f;
       if (interior) {
-        float mx = 0.f, my = 0.f, exx = 0.f, eyy = 0.f, exy = 0.f;
-#pragma unroll
-        for (int k = 0; k < 11; ++k) {
-          mx += w[k] * col[0][o + k]; my += w[k] * col[1][o + k]; exx += w[k] * col[2][o + k];
-          eyy += w[k] * col[3][o + k]; exy += w[k] * col[4][o + k];
-        }
+        const float mx = st[0][o], my = st[1][o], exx = st[2][o], eyy = st[3][o], exy = st[4][o];
         const float sxx = exx - mx * mx, syy = eyy - my * my, sxy = exy - mx * my;
         const float A1 = 2.f * mx * my + C1, A2 = 2.f * sxy + C2, B1 = mx * mx + my * my + C1, B2 = sxx + syy + C2;
         const float inv = 1.f / (B1 * B2);
         const float S = A1 * A2 * inv;
         ssim_acc += S;
-        const float S_mu = 2.f * my * A2 * inv - 2.f * mx * S / B1;
-        const float S_sx = -S / B2;
+        const float S_mu = 2.f * my * A2 * inv - 2.f * mx * S * (B2 * inv);     // S / B1 = S * B2 / (B1 B2)
+        const float S_sx = -S * (B1 * inv);                                     // S / B2
         const float S_c = 2.f * A1 * inv;
         dm = coef_ssim * (S_mu - 2.f * mx * S_sx - my * S_c);
         ds = coef_ssim * S_sx;
@@ -135,7 +188,7 @@ ssim_l1_fwd_kernel(const float* __restrict__ render, const float* __restrict__ t
       if (in_img) {
         float* d = dmaps + (((size_t)c * 3 + ch) * 3) * plane + (size_t)py * W + px;
         d[0] = dm; d[plane] = ds; d[2 * plane] = dc;
-        const int t = (ch * LW + vr0 + o + HALO) * LWP + vx + HALO;
+        const int t = (ch * LW + vr0 + o + HALO) * TP + vx + HALO;
         l1_acc += fabsf(ty[t] - tx[t]);
       }
     }
@@ -148,47 +201,40 @@ ssim_l1_fwd_kernel(const float* __restrict__ render, const float* __restrict__ t
   }
 }
 
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 4)
 ssim_l1_bwd_kernel(const float* __restrict__ render, const float* __restrict__ truth, const float* __restrict__ dmaps,
                    int H, int W, float coef_l1 /* (1-f) / (3HW) */, float* __restrict__ v_render) {
   ST3R_DYN_SMEM_F32(smem);
-  float* tm = smem;                         // [3 derivatives][LW][LWP] of the current channel
-  float* hs = tm + 3 * LW * LWP;            // [3][LW][HSP]
+  float* tm = smem;                         // [3 derivatives][LW][TP] of the current channel
+  float* hs = tm + 3 * LW * TP;             // [3][LW][HP]
   const int c = blockIdx.z;
   const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
   const size_t plane = (size_t)H * W;
-  float w[11];
-#pragma unroll
-  for (int k = 0; k < 11; ++k) w[k] = c_win[k];
-  const int vx = threadIdx.x & 31, vr0 = (threadIdx.x >> 5) * 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vx = lane, vr0 = warp * 4;
+  const int gx_a = x0 - HALO + lane, gx_b = gx_a + 32;        // the two columns of a halo row this lane loads
+  const bool ok_a = gx_a >= 0 && gx_a < W, ok_b = lane < LW - 32 && gx_b < W;
   float out[4][3];
   for (int ch = 0; ch < 3; ++ch) {
-    __syncthreads();
+    __syncthreads();        // the previous channel's passes are done with tm / hs
     const float* src = dmaps + (((size_t)c * 3 + ch) * 3) * plane;
-    for (int e = threadIdx.x; e < 3 * LW * LW; e += NT) {
-      const int d = e / (LW * LW), rq = e - d * (LW * LW);
-      const int r = rq / LW, q = rq - r * LW;
-      const int gy = y0 + r - HALO, gx = x0 + q - HALO;
-      float v = 0.f;
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = src[(size_t)d * plane + (size_t)gy * W + gx];
-      tm[(d * LW + r) * LWP + q] = v;
+    for (int dr = warp; dr < 3 * LW; dr += NT / 32) {       // a warp per (derivative, row)
+      const int d = dr / LW, r = dr - d * LW;
+      const int gy = y0 + r - HALO;
+      const bool row_ok = gy >= 0 && gy < H;
+      const float* g = src + (size_t)d * plane + (long long)gy * W;
+      float* t = tm + (d * LW + r) * TP;
+      t[lane] = (row_ok && ok_a) ? g[gx_a] : 0.f;
+      if (lane < LW - 32) t[lane + 32] = (row_ok && ok_b) ? g[gx_b] : 0.f;
     }
     __syncthreads();
-    for (int it = threadIdx.x; it < LW * (LT / 8); it += NT) {
-      const int r = it >> 2, q0 = (it & 3) * 8;
+    if (threadIdx.x < HITEMS) {
+      const int r = threadIdx.x >> 2, q0 = (threadIdx.x & 3) * 8;
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        const float* a = tm + (d * LW + r) * LWP + q0;
-        float v[18];
-#pragma unroll
-        for (int k = 0; k < 18; ++k) v[k] = a[k];
-#pragma unroll
-        for (int o = 0; o < 8; ++o) {
-          float acc = 0.f;
-#pragma unroll
-          for (int k = 0; k < 11; ++k) acc += w[k] * v[o + k];
-          hs[d * LW * HSP + r * HSP + q0 + o] = acc;
-        }
+        float v[20];
+        load20(tm + (d * LW + r) * TP + q0, v);
+        hconv8(v, hs + d * LW * HP + r * HP + q0);
       }
     }
     __syncthreads();
@@ -197,14 +243,9 @@ ssim_l1_bwd_kernel(const float* __restrict__ render, const float* __restrict__ t
     for (int d = 0; d < 3; ++d) {
       float col[14];
 #pragma unroll
-      for (int k = 0; k < 14; ++k) col[k] = hs[d * LW * HSP + (vr0 + k) * HSP + vx];
+      for (int k = 0; k < 14; ++k) col[k] = hs[d * LW * HP + (vr0 + k) * HP + vx];
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        float acc = 0.f;
-#pragma unroll
-        for (int k = 0; k < 11; ++k) acc += w[k] * col[o + k];
-        g[d][o] = acc;
-      }
+      for (int o = 0; o < 4; ++o) g[d][o] = win11(col + o);
     }
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
@@ -244,22 +285,6 @@ __global__ void loss_finalize_kernel(const float* __restrict__ sums, const float
   *out = acc;
 }
 
-PerDeviceOnce g_win_set;   // __constant__ memory is per device
-
-int set_window() {
-  if (g_win_set.done()) return ST3R_OK;
-  float g[11], s = 0.f;
-  for (int k = 0; k < 11; ++k) {
-    float d = (float)(k - 5);
-    g[k] = expf(-(d / 1.5f) * (d / 1.5f) / 2.0f);
-    s += g[k];
-  }
-  for (int k = 0; k < 11; ++k) g[k] /= s;
-  ST3R_CHECK_CUDA(cudaMemcpyToSymbol(c_win, g, sizeof(g)));
-  g_win_set.mark();
-  return ST3R_OK;
-}
-
 }  // namespace
 
 extern "C" {
@@ -270,12 +295,10 @@ int st3r_gs_loss_fwd(const float* render, const float* truth, int C, int height,
   ST3R_CHECK_ARG(C >= 0 && height > 10 && width > 10, "st3r_gs_loss_fwd: images must be larger than the 11x11 SSIM window");
   if (C == 0) return ST3R_OK;
   ST3R_CHECK_ARG(render && truth && dmaps && sums, "st3r_gs_loss_fwd: null pointer");
-  int rc = set_window();
-  if (rc) return rc;
   // loss_view = ... + f * (1 - mean(S))  =>  dLoss/dS = -f / (3 (H-10) (W-10))
   float coef = -ssim_fac / (3.0f * (float)(height - 10) * (float)(width - 10));
   dim3 grid((width + LT - 1) / LT, (height + LT - 1) / LT, C);
-  constexpr size_t kSmemFwd = sizeof(float) * (6 * LW * LWP + 5 * LW * HSP);
+  constexpr size_t kSmemFwd = sizeof(float) * (6 * LW * TP + 5 * LW * HP);
   static PerDeviceOnce attr_fwd;
   if (!attr_fwd.done()) {
     ST3R_CHECK_CUDA(cudaFuncSetAttribute(ssim_l1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFwd));
@@ -291,11 +314,9 @@ int st3r_gs_loss_bwd(const float* render, const float* truth, const float* dmaps
   ST3R_CHECK_ARG(C >= 0 && height > 10 && width > 10, "st3r_gs_loss_bwd: bad sizes");
   if (C == 0) return ST3R_OK;
   ST3R_CHECK_ARG(render && truth && dmaps && v_render, "st3r_gs_loss_bwd: null pointer");
-  int rc = set_window();
-  if (rc) return rc;
   float coef_l1 = (1.0f - ssim_fac) / (3.0f * (float)height * (float)width);
   dim3 grid((width + LT - 1) / LT, (height + LT - 1) / LT, C);
-  constexpr size_t kSmemBwd = sizeof(float) * (3 * LW * LWP + 3 * LW * HSP);
+  constexpr size_t kSmemBwd = sizeof(float) * (3 * LW * TP + 3 * LW * HP);
   ssim_l1_bwd_kernel<<<grid, NT, kSmemBwd, stream>>>(render, truth, dmaps, height, width, coef_l1, v_render);
   ST3R_CHECK_LAUNCH();
   return ST3R_OK;

@@ -390,6 +390,13 @@ def _adapt_variant(lib):
             _variant["on"] = False
 
 
+def adapt_variant():
+    """Lets the matcher re-pick its precision variant from the statistics of the calls since the last read-out.  For
+    callers of extract_correspondences_device, at a point where they have synchronised anyway (it reads two device
+    counters)."""
+    _adapt_variant(_lib.load())
+
+
 def extract_correspondences_device(feats, qonfs, subsample=8, impl="auto", max_iter=10):
     """Device-resident form: returns (xy1 [cap,2] i64, xy2 [cap,2] i64, conf [cap] f32, n [1] i32) without
     synchronising; rows >= n are undefined and the buffers are reused by the next call with the same shapes.

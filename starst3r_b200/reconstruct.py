@@ -422,23 +422,122 @@ def symmetric_inference(model, img1, img2, device):
     return res11, res21, res22, res12
 
 
+def symmetric_inference_batch(model, imgs1, imgs2, device):
+    """B image pairs through the network in ONE pass (sparse_ga.py:571-592 with a batch dimension): the
+    images of the pairs are stacked along dim 0, the encoder / the two decoder directions / the heads run once, and the
+    result is split back into the per-pair tuples (res11, res21, res22, res12) `symmetric_inference` returns, each with
+    batch dimension 1.  A model that brings its own `symmetric_inference_batch(imgs1, imgs2)` (synth.SyntheticMast3r) is
+    used directly; one that only has `symmetric_inference`, and pairs of different image sizes, go pair by pair."""
+    assert len(imgs1) == len(imgs2)
+    if hasattr(model, "symmetric_inference_batch"):
+        return list(model.symmetric_inference_batch(imgs1, imgs2))
+    same = all(tuple(i["img"].shape) == tuple(imgs1[0]["img"].shape) for i in list(imgs1) + list(imgs2))
+    if hasattr(model, "symmetric_inference") or len(imgs1) == 1 or not same:
+        return [symmetric_inference(model, a, b, device) for a, b in zip(imgs1, imgs2)]
+    shape1 = torch.cat([torch.from_numpy(i["true_shape"]) for i in imgs1]).to(device, non_blocking=True)
+    shape2 = torch.cat([torch.from_numpy(i["true_shape"]) for i in imgs2]).to(device, non_blocking=True)
+    im1 = torch.cat([i["img"] for i in imgs1]).to(device, non_blocking=True)
+    im2 = torch.cat([i["img"] for i in imgs2]).to(device, non_blocking=True)
+    feat1, feat2, pos1, pos2 = model._encode_image_pairs(im1, im2, shape1, shape2)
+
+    def decoder(fa, fb, pa, pb, sa, sb):
+        dec1, dec2 = model._decoder(fa, pa, fb, pb)
+        with torch.autocast("cuda", enabled=False):
+            return (model._downstream_head(1, [t.float() for t in dec1], sa),
+                    model._downstream_head(2, [t.float() for t in dec2], sb))
+    res11, res21 = decoder(feat1, feat2, pos1, pos2, shape1, shape2)
+    res22, res12 = decoder(feat2, feat1, pos2, pos1, shape2, shape1)
+    return [tuple({k: v[i:i + 1] for k, v in r.items()} for r in (res11, res21, res22, res12)) for i in range(len(imgs1))]
+
+
 def _pair_missing(memo, a, b):
     return not ((a, b) in memo["fwd"] and (b, a) in memo["fwd"] and (a, b) in memo["corres"])
 
 
-def _compute_pair(memo, model, img1, img2, device, desc_conf, subsample):
-    """Inference + matching of one unordered image pair (sparse_ga.py:541-561); fills the memo."""
-    a, b = img1["instance"], img2["instance"]
-    res = symmetric_inference(model, img1, img2, device)
+def _pair_maps(memo, res, a, b, device, desc_conf):
+    """Stores the four point / confidence maps of one pair; returns (descriptors, descriptor confidences, conf_score)."""
     X11, X21, X22, X12 = [r["pts3d"][0].to(device).float().contiguous() for r in res]
     C11, C21, C22, C12 = [r["conf"][0].to(device).float().contiguous() for r in res]
     descs = [r["desc"][0].to(device) for r in res]
     qonfs = [r[desc_conf][0].to(device) for r in res]
     memo["fwd"][a, b] = (X11, C11, X21, C21)
     memo["fwd"][b, a] = (X22, C22, X12, C12)
-    corres = match.extract_correspondences(descs, qonfs, device=device, subsample=subsample)
     conf_score = (C11.mean() * C12.mean() * C21.mean() * C22.mean()).sqrt().sqrt()
+    return descs, qonfs, conf_score
+
+
+def _compute_pair(memo, model, img1, img2, device, desc_conf, subsample):
+    """Inference + matching of one unordered image pair (sparse_ga.py:541-561); fills the memo."""
+    a, b = img1["instance"], img2["instance"]
+    res = symmetric_inference(model, img1, img2, device)
+    descs, qonfs, conf_score = _pair_maps(memo, res, a, b, device, desc_conf)
+    corres = match.extract_correspondences(descs, qonfs, device=device, subsample=subsample)
     memo["corres"][a, b] = ((float(conf_score), float(corres[2].sum()), len(corres[2])), corres)
+
+
+# SURVEY 8f-2 - the pair loop as a two-stream pipeline.  The reference (and _compute_pair) runs network -> matcher ->
+# host read-back pair by pair (sparse_ga.py:541-561: `float(conf_score)`, `len(corres[2])` synchronise every pair).
+# Here the network runs INFERENCE_BATCH pairs per pass on a side stream, one batch ahead of the matcher; the matcher
+# (a replayed CUDA graph per pair, match.extract_correspondences_device) consumes the descriptor maps where the heads
+# wrote them ([H, W, 24] fp32 = the [HW, 24] K-major layout the tcgen05 kernel's TMA descriptor reads), results are
+# staged on the device and the host reads all counts and scores back ONCE, after the last pair.  Entries of the memo
+# are bit-identical to the sequential loop (tests/test_match_gpu.py::test_pipelined_pair_loop_equals_sequential).
+PIPELINE_PAIRS = True
+INFERENCE_BATCH = 4
+_SIDE_STREAMS = {}
+
+
+def _compute_pairs(memo, model, todo, device, desc_conf, subsample):
+    """Inference + matching of the image pairs `todo` = [(img1, img2), ...]; fills the memo."""
+    dev = torch.device(device)
+    if not (PIPELINE_PAIRS and dev.type == "cuda" and torch.cuda.is_available() and len(todo) > 1):
+        for img1, img2 in todo:
+            _compute_pair(memo, model, img1, img2, device, desc_conf, subsample)
+        return
+    # the first pair synchronously: its read-back is where the matcher picks its precision variant for this scene
+    _compute_pair(memo, model, todo[0][0], todo[0][1], device, desc_conf, subsample)
+    todo = todo[1:]
+    cur = torch.cuda.current_stream(dev)
+    side = _SIDE_STREAMS.get(dev)
+    if side is None:
+        side = _SIDE_STREAMS[dev] = torch.cuda.Stream(dev)
+    side.wait_stream(cur)
+    chunks = [todo[i:i + INFERENCE_BATCH] for i in range(0, len(todo), INFERENCE_BATCH)]
+
+    def infer(chunk):
+        with torch.cuda.stream(side):
+            res = symmetric_inference_batch(model, [p[0] for p in chunk], [p[1] for p in chunk], device)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return res, ev
+
+    counts = torch.zeros(len(todo), dtype=torch.int32).pin_memory()
+    staged, scores = [], []
+    ahead = infer(chunks[0])
+    for ci, chunk in enumerate(chunks):
+        results, ev = ahead
+        if ci + 1 < len(chunks):
+            ahead = infer(chunks[ci + 1])                     # the network runs one batch ahead of the matcher
+        cur.wait_event(ev)
+        for (img1, img2), res in zip(chunk, results):
+            a, b = img1["instance"], img2["instance"]
+            descs, qonfs, conf_score = _pair_maps(memo, res, a, b, device, desc_conf)
+            xy1, xy2, conf, n_out = match.extract_correspondences_device([d.float().contiguous() for d in descs],
+                                                                         [q.float().contiguous() for q in qonfs], subsample)
+            counts[len(staged):len(staged) + 1].copy_(n_out, non_blocking=True)
+            staged.append((a, b, xy1.clone(), xy2.clone(), conf.clone()))    # (the plan's buffers serve the next pair)
+            scores.append(conf_score)
+    cur.synchronize()                                          # the one host synchronisation of the loop
+    side.synchronize()
+    match.adapt_variant()
+    sums = []
+    for k, (a, b, xy1, xy2, conf) in enumerate(staged):
+        n = int(counts[k])
+        staged[k] = (a, b, xy1[:n], xy2[:n], conf[:n])
+        sums.append(conf[:n].sum())
+    host = torch.stack(scores + sums).double().cpu().tolist()
+    for k, (a, b, xy1, xy2, conf) in enumerate(staged):
+        memo["corres"][a, b] = ((host[k], host[len(staged) + k], int(conf.numel())), (xy1, xy2, conf))
 
 
 # Under an initialised torch.distributed group (one process per GPU) forward_mast3r computes only every G-th missing
@@ -541,18 +640,16 @@ def _forward_sharded(pairs, memo, model, device, desc_conf, subsample, cache_pat
     box = [todo]
     dist.broadcast_object_list(box, src=0)        # rank 0's list decides (caches may differ between ranks)
     todo = box[0]
-    mine = 0
     fkw = dict(desc_conf=desc_conf, subsample=subsample)
-    for j, k in enumerate(todo):
-        if j % world == rank:
-            img1, img2 = pairs[k]
-            a, b = img1["instance"], img2["instance"]
-            _compute_pair(memo, model, img1, img2, device, desc_conf, subsample)
-            if PERSIST_CACHE and cache_path:    # the rank that computed a pair is the one that still holds all of it
-                _disk_put(_cache_file(cache_path, "fwd", a, b), memo["fwd"][a, b])
-                _disk_put(_cache_file(cache_path, "fwd", b, a), memo["fwd"][b, a])
-                _disk_put(_cache_file(cache_path, "corres", a, b, **fkw), memo["corres"][a, b])
-            mine += 1
+    share = [pairs[k] for j, k in enumerate(todo) if j % world == rank]
+    _compute_pairs(memo, model, share, device, desc_conf, subsample)
+    for img1, img2 in share:
+        a, b = img1["instance"], img2["instance"]
+        if PERSIST_CACHE and cache_path:        # the rank that computed a pair is the one that still holds all of it
+            _disk_put(_cache_file(cache_path, "fwd", a, b), memo["fwd"][a, b])
+            _disk_put(_cache_file(cache_path, "fwd", b, a), memo["fwd"][b, a])
+            _disk_put(_cache_file(cache_path, "corres", a, b, **fkw), memo["corres"][a, b])
+    mine = len(share)
     for j, k in enumerate(todo):
         img1, img2 = pairs[k]
         _exchange_pair(memo, img1["instance"], img2["instance"], int(img1["idx"]), int(img2["idx"]), j % world, rank, world,
@@ -582,21 +679,38 @@ def forward_mast3r(pairs, model, cache_path, desc_conf="desc_conf", device="cuda
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             _forward_sharded(pairs, memo, model, device, desc_conf, subsample, cache_path)
             sharded = True
-    for img1, img2 in pairs:
-        a, b = img1["instance"], img2["instance"]
+    def mirror(a, b):
         if (b, a) in memo["corres"] and (a, b) not in memo["corres"]:
             score, (xy1, xy2, confs) = memo["corres"][b, a]
             memo["corres"][a, b] = (score, (xy2, xy1, confs))                        # :538-540
             if not sharded or dist.get_rank() == 0:
                 _disk_put(cache_path and _cache_file(cache_path, "corres", a, b, **fkw), memo["corres"][a, b])
-        if _pair_missing(memo, a, b):
-            if model is None:
-                continue
-            _compute_pair(memo, model, img1, img2, device, desc_conf, subsample)
-            if PERSIST_CACHE and cache_path:
+
+    # the pairs still missing, in the reference's loop order (a pair whose mirror image comes earlier in the list is
+    # served by the mirror rule above, like in the reference), computed as one pipelined batch
+    todo = []
+    if model is not None:
+        have_fwd, have_cor = set(memo["fwd"]), set(memo["corres"])
+        for img1, img2 in pairs:
+            a, b = img1["instance"], img2["instance"]
+            if (b, a) in have_cor:
+                have_cor.add((a, b))
+            if not ((a, b) in have_fwd and (b, a) in have_fwd and (a, b) in have_cor):
+                todo.append((img1, img2))
+                have_fwd |= {(a, b), (b, a)}
+                have_cor.add((a, b))
+        _compute_pairs(memo, model, todo, device, desc_conf, subsample)
+        if PERSIST_CACHE and cache_path:
+            for img1, img2 in todo:
+                a, b = img1["instance"], img2["instance"]
                 _disk_put(_cache_file(cache_path, "fwd", a, b), memo["fwd"][a, b])
                 _disk_put(_cache_file(cache_path, "fwd", b, a), memo["fwd"][b, a])
                 _disk_put(_cache_file(cache_path, "corres", a, b, **fkw), memo["corres"][a, b])
+    for img1, img2 in pairs:
+        a, b = img1["instance"], img2["instance"]
+        mirror(a, b)
+        if _pair_missing(memo, a, b):
+            continue                                  # (model is None: nothing to compute with)
         res_paths[a, b] = ((a, b), (b, a)), (a, b)
     return res_paths, cache_path
 

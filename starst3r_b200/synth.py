@@ -152,6 +152,11 @@ class SyntheticMast3r:
         return (self._res(i, i, (i * n + j) * 4, j), self._res(j, i, (i * n + j) * 4 + 1, i),
                 self._res(j, j, (i * n + j) * 4 + 2, i), self._res(i, j, (i * n + j) * 4 + 3, j))
 
+    def symmetric_inference_batch(self, imgs1, imgs2, device=None):
+        """The batched entry point reconstruct.symmetric_inference_batch looks for; the synthetic
+        predictions are procedural, so a batch is just the pairs in turn."""
+        return [self.symmetric_inference(a, b) for a, b in zip(imgs1, imgs2)]
+
     def images(self):
         """[-1, 1] normalised (3, H, W) images (shading from the descriptor field; only colours downstream)."""
         out = []

@@ -11,7 +11,7 @@ extern "C" {
 
 // keys / vals: [n_cap]; offsets: [C * tiles]; returns the intersection total, or -1 on an emulator deadlock.
 int emu_bin_tiles(const int32_t* radii, const float* geomA, int N, int C, int W, int H, int tile_n_bits, int32_t* offsets,
-                  uint64_t* keys, uint32_t* vals, int n_cap, int use_smem) {
+                  uint64_t* keys, uint32_t* vals, int n_cap, int use_smem, int reg_sort) {
   const int tile_size = 16;
   const int tile_w = (W + tile_size - 1) / tile_size, tile_h = (H + tile_size - 1) / tile_size;
   const int n_tiles = tile_w * tile_h, n_cells = C * n_tiles;
@@ -38,7 +38,7 @@ int emu_bin_tiles(const int32_t* radii, const float* geomA, int N, int C, int W,
   emu::g_gridDim = dim3(n_cells, 1, 1);
   for (int cell = 0; cell < n_cells; ++cell) {
     emu::g_blockIdx = uint3{(unsigned)cell, 0, 0};
-    if (!emu::run_cta(SORT_THREADS, [&]() { tile_sort_kernel(offsets, &total, n_cells, n_tiles, tile_n_bits, pairs.data(), keys, vals, n_cap); }))
+    if (!emu::run_cta(SORT_THREADS, [&]() { tile_sort_kernel(offsets, &total, n_cells, n_tiles, tile_n_bits, pairs.data(), keys, vals, n_cap, reg_sort); }))
       return -1;
   }
   return total;

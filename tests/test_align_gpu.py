@@ -163,6 +163,48 @@ def test_pipeline_index_plumbing_vs_reference(cuda_device, name):
     check_pipeline_vs_reference(cuda_device, name)
 
 
+def test_pipelined_pair_loop_equals_sequential(cuda_device, monkeypatch):
+    """forward_mast3r with the two-stream pipeline (network batches on a side stream one batch ahead of
+    the matcher, one host synchronisation per call) fills the memo with exactly what the pair-by-pair loop of
+    sparse_ga.py:529-562 produces: maps, correspondence lists, matching scores - bit for bit - for several batch sizes,
+    and calls the network once per unordered pair."""
+    from starst3r_b200 import reconstruct as rc
+    from starst3r_b200 import synth
+    from starst3r_b200.image import prepare_images_for_mast3r
+    n, W, H = 5, 96, 64
+    model = synth.SyntheticMast3r(n, W, H, seed=3, arc_deg=90.0, pts_noise=0.01, device=cuda_device)
+    calls = []
+    orig = model.symmetric_inference
+    model.symmetric_inference = lambda a, b, device=None: (calls.append((int(a["idx"]), int(b["idx"]))), orig(a, b))[1]
+    names = [f"{i}.png" for i in range(n)]
+    imgs = prepare_images_for_mast3r(model.images())
+    pairs_in = rc.convert_dust3r_pairs_naming(names, rc.make_pairs(imgs, "complete", None, True))
+    out = {}
+    for tag, pipe, batch in (("seq", False, 1), ("pipe1", True, 1), ("pipe3", True, 3), ("pipe16", True, 16)):
+        monkeypatch.setattr(rc, "PIPELINE_PAIRS", pipe)
+        monkeypatch.setattr(rc, "INFERENCE_BATCH", batch)
+        rc.clear_cache()
+        del calls[:]
+        pairs, cache = rc.forward_mast3r(pairs_in, model, cache_path="pipe-" + tag, subsample=8, desc_conf="desc_conf",
+                                         device=cuda_device)
+        assert sorted(calls) == sorted(set(calls)) and len(calls) == n * (n - 1) // 2, (tag, calls)
+        memo = rc._memo(cache)
+        out[tag] = (list(pairs), {k: [t.clone() for t in v] for k, v in memo["fwd"].items()},
+                    {k: (v[0], [t.clone() for t in v[1]]) for k, v in memo["corres"].items()})
+    rc.clear_cache()
+    keys, fwd, cor = out["seq"]
+    assert len(keys) == n * (n - 1)
+    for tag in ("pipe1", "pipe3", "pipe16"):
+        k2, f2, c2 = out[tag]
+        assert k2 == keys and set(f2) == set(fwd) and set(c2) == set(cor), tag
+        for k in fwd:
+            assert all(torch.equal(a, b) for a, b in zip(fwd[k], f2[k])), (tag, k)
+        for k in cor:
+            assert cor[k][0] == c2[k][0], (tag, k, cor[k][0], c2[k][0])                  # (conf_score, sum conf, n)
+            assert all(torch.equal(a, b) for a, b in zip(cor[k][1], c2[k][1])), (tag, k)
+            assert cor[k][0][2] == cor[k][1][0].shape[0] > 0
+
+
 def test_first_implementation_of_the_align_kernels_as_cross_check(cuda_device, monkeypatch):
     """reconstruct.ALIGN_VARIANT = 0 (per-row shuffles + shared atomics in the loss kernels, single-CTA Weiszfeld): the
     first implementation of the kernels, an independent second path to the same fixtures, and both variants walk the

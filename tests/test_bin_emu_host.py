@@ -28,9 +28,13 @@ def P(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+@pytest.mark.parametrize("reg_sort", [1, 0])
 @pytest.mark.parametrize("n,C,W,H,scale_mult,use_smem", [(600, 2, 80, 48, 8.0, 1), (600, 2, 80, 48, 8.0, 0),
+                                                         (2500, 1, 96, 64, 6.0, 1), (6000, 1, 160, 112, 8.0, 1),
                                                          (9000, 1, 40, 40, 60.0, 1)])
-def test_fused_binning_bit_exact_on_the_emulator(emu, n, C, W, H, scale_mult, use_smem):
+def test_fused_binning_bit_exact_on_the_emulator(emu, n, C, W, H, scale_mult, use_smem, reg_sort):
+    """reg_sort = 1: segments up to 2048 pairs take the register-resident network (1 / 2 / 4 / 8 elements per thread),
+    longer ones and reg_sort = 0 the shared-memory / in-place network."""
     sp = synth.random_splats(n, seed=1, scale_mode="rand")
     sp["scales"] = sp["scales"] * scale_mult
     viewmats, Ks = synth.look_at_cameras(C, W, H)
@@ -40,8 +44,12 @@ def test_fused_binning_bit_exact_on_the_emulator(emu, n, C, W, H, scale_mult, us
     want_offsets = go.isect_offset_encode(b["isect_ids"], C, tw, th, b["tile_n_bits"]).reshape(-1)
     n_isect = len(b["isect_ids"])
     per_cell = np.diff(np.r_[want_offsets, n_isect])
-    if n > 5000:
+    if n == 9000:
         assert per_cell.max() > 4096                  # a segment that is sorted in place in global memory
+    # between them the cases cover every size class of the register-resident sort (1 / 2 / 4 / 8 elements per thread)
+    classes = {600: ((1, 256), (257, 512)), 2500: ((257, 512), (513, 1024), (1025, 2048)), 6000: ((1025, 2048), (2049, 4096))}
+    for lo, hi in classes.get(n, ()):
+        assert ((per_cell >= lo) & (per_cell <= hi)).any(), (lo, hi, sorted(per_cell))
     geomA = np.zeros((C * n, 4), np.float32)
     geomA[:, :2] = means2d.reshape(-1, 2).numpy()
     geomA[:, 3] = depths.reshape(-1).numpy()
@@ -50,7 +58,7 @@ def test_fused_binning_bit_exact_on_the_emulator(emu, n, C, W, H, scale_mult, us
     keys = np.zeros(max(n_isect, 1), np.uint64)
     vals = np.zeros(max(n_isect, 1), np.uint32)
     total = emu.emu_bin_tiles(P(rad), P(geomA), n, C, W, H, int(b["tile_n_bits"]), P(offsets), P(keys), P(vals), n_isect,
-                              use_smem)
+                              use_smem, reg_sort)
     assert total == n_isect
     assert np.array_equal(offsets, want_offsets.astype(np.int32))
     assert np.array_equal(keys[:n_isect].astype(np.int64), b["isect_ids"])

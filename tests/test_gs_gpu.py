@@ -268,32 +268,41 @@ def test_train_steps_vs_oracle(cuda_device):
 
 
 @pytest.mark.parametrize("n,scale_mult,C,W,H", [(500, 8.0, 3, 80, 48), (3000, 60.0, 2, 64, 64), (20000, 40.0, 1, 40, 40),
-                                                 (50, 1.0, 2, 33, 17)])
+                                                 (50, 1.0, 2, 33, 17), (2500, 6.0, 1, 96, 64), (6000, 8.0, 1, 160, 112)])
 def test_fused_binning_equals_radix_chain(cuda_device, n, scale_mult, C, W, H):
     """st3r_gs_bin_tiles (counting sort by tile + in-tile sort) == st3r_gs_isect + st3r_radix_sort_pairs +
-    st3r_gs_offsets, bit for bit (isect_ids, flatten_ids, isect_offsets), including tiles whose list is longer than
+    st3r_gs_offsets, bit for bit (isect_ids, flatten_ids, isect_offsets), for both per-tile sorts (register-resident up
+    to 2048 pairs = the default, and the shared-memory / in-place network), including tiles whose list is longer than
     the shared-memory sort (4096 pairs; the 20000-Gaussian case has ~20000 per tile)."""
-    from starst3r_b200 import gs
+    from starst3r_b200 import _lib, gs
+    lib = _lib.load()
     sp, viewmats, Ks, W, H = small_scene(n=n, C=C, W=W, H=H, seed=n, scale_mult=scale_mult)
     d = to(cuda_device, sp)
     out = {}
-    for mode in ("radix", "fused"):
+    for mode, variant in (("radix", 1), ("fused", 1), ("fused", 0)):
         gs.BINNING = mode
+        _lib.check(lib.st3r_gs_bin_set_variant(variant), "st3r_gs_bin_set_variant")
         try:
             with torch.no_grad():
                 r, a, info = gs.rasterization(d["means"], d["quats"], d["scales"], d["opacities"], d["shN"],
                                               viewmats.to(cuda_device), Ks.to(cuda_device), W, H)
         finally:
             gs.BINNING = "fused"
-        out[mode] = (r, a, info)
-    ia, ib = out["radix"][2], out["fused"][2]
-    assert ia["isect_ids"].numel() == ib["isect_ids"].numel() and ia["isect_ids"].numel() > 0
+            _lib.check(lib.st3r_gs_bin_set_variant(1), "st3r_gs_bin_set_variant")
+        out[mode, variant] = (r, a, info)
+    ia = out["radix", 1][2]
+    per_tile = torch.diff(ia["isect_offsets"].flatten())
     if n == 20000:
-        per_tile = torch.diff(ia["isect_offsets"].flatten())
         assert per_tile.max().item() > 4096          # exercises the global-memory sort path
-    for k in ("isect_ids", "flatten_ids", "isect_offsets"):
-        assert torch.equal(ia[k], ib[k]), k
-    assert torch.equal(out["radix"][0], out["fused"][0]) and torch.equal(out["radix"][1], out["fused"][1])
+    if n == 2500:                                    # 2, 4 and 8 elements per thread of the register-resident sort
+        for lo, hi in ((257, 512), (513, 1024), (1025, 2048)):
+            assert ((per_tile >= lo) & (per_tile <= hi)).any(), (lo, hi)
+    for key in (("fused", 1), ("fused", 0)):
+        ib = out[key][2]
+        assert ia["isect_ids"].numel() == ib["isect_ids"].numel() and ia["isect_ids"].numel() > 0
+        for k in ("isect_ids", "flatten_ids", "isect_offsets"):
+            assert torch.equal(ia[k], ib[k]), (k, key)
+        assert torch.equal(out["radix", 1][0], out[key][0]) and torch.equal(out["radix", 1][1], out[key][1])
 
 
 @pytest.mark.parametrize("N,C,W,H", [(200_000, 8, 512, 512), (1_000_000, 4, 1024, 768), (3_000_000, 8, 1920, 1072)])
