@@ -284,31 +284,42 @@ align_lossd_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, float
 // warp walks a contiguous range and keeps the two images' gradients in REGISTERS while the pair does not change -
 // the vjp helpers accumulate straight into them - and reduces across lanes only when the pair changes or its range
 // ends.  The grid is ~4x smaller and CTA b adds its table into replica b % ALIGN_REPL, which align_cam_bwd folds.
-template <int KIND> struct SegEntry { Anchor a1, a2; int i1, i2; };
+template <int KIND> struct SegEntry {
+  Anchor a1, a2; int i1, i2;
+  float x[3];       // KIND 1: the pixel in image 1; KIND 2: the regression target in image 2's camera frame
+  float conf;
+};
 
 template <int KIND>
 __device__ __forceinline__ void seg_load(const St3rAlignProblem& pb, const AlignImgConst* ic, int m, SegEntry<KIND>& e) {
+  e.x[0] = e.x[1] = e.x[2] = 0.f;
   if (KIND == 0) {
     e.a1 = load_anchor(pb, ic, pb.e3_a1[m]); e.a2 = load_anchor(pb, ic, pb.e3_a2[m]);
     e.i1 = e.a1.img; e.i2 = e.a2.img;
+    e.conf = pb.e3_conf[m];
   } else if (KIND == 1) {
     e.i1 = pb.e2_img1[m];
     e.a2 = load_anchor(pb, ic, pb.e2_a2[m]);
     e.i2 = e.a2.img;
+    e.x[0] = pb.e2_pix[2 * m]; e.x[1] = pb.e2_pix[2 * m + 1];
+    e.conf = pb.e2_conf[m];
   } else {
     e.a1 = load_anchor(pb, ic, pb.ed_a1[m]);
     e.i1 = e.a1.img;
     e.i2 = pb.ed_img2[m];
+    e.x[0] = pb.ed_tgt[3 * m]; e.x[1] = pb.ed_tgt[3 * m + 1]; e.x[2] = pb.ed_tgt[3 * m + 2];
+    e.conf = pb.ed_conf[m];
   }
 }
 
-// Loss of entry m; ADDS its gradients w.r.t. the two camera records into g1 / g2.  Same arithmetic as the bodies of
-// align_loss3d / align_loss2d / align_lossd above.
+// Loss of one entry; ADDS its gradients w.r.t. the two camera records into g1 / g2.  Same arithmetic as the bodies of
+// align_loss3d / align_loss2d / align_lossd above.  `cams`: the camera table (global memory or a shared-memory copy).
 template <int KIND>
-__device__ __forceinline__ float seg_eval(const St3rAlignProblem& pb, const Work& w, int m, const SegEntry<KIND>& e,
-                                          float gamma, float offset, float off_pow, float scale, float* g1, float* g2) {
-  const AlignCam c1 = w.cam[e.i1], c2 = w.cam[e.i2];
+__device__ __forceinline__ float seg_eval(const AlignCam* cams, const SegEntry<KIND>& e, float gamma, float offset,
+                                          float off_pow, float scale, float* g1, float* g2) {
+  const AlignCam c1 = cams[e.i1], c2 = cams[e.i2];
   float dl;
+  const float cw = e.conf * scale;
   if (KIND == 0) {
     float P1[3], P2[3], pc1[3], pc2[3], z1, z2, D1, D2, o1, o2;
     al_anchor_point(c1, e.a1.u, e.a1.v, e.a1.core, e.a1.off, P1, pc1, &z1, &D1, &o1);
@@ -316,7 +327,6 @@ __device__ __forceinline__ float seg_eval(const St3rAlignProblem& pb, const Work
     const float d[3] = {P1[0] - P2[0], P1[1] - P2[1], P1[2] - P2[2]};
     const float dist = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
     const float l = al_gamma_loss(dist, gamma, offset, off_pow, &dl);
-    const float cw = pb.e3_conf[m] * scale;
     const float k = dist > 0.f ? cw * dl / dist : 0.f;
     const float GP1[3] = {k * d[0], k * d[1], k * d[2]}, GP2[3] = {-k * d[0], -k * d[1], -k * d[2]};
     al_anchor_point_vjp(c1, e.a1.u, e.a1.v, e.a1.core, e.a1.off, pc1, z1, D1, o1, GP1, g1);
@@ -328,10 +338,9 @@ __device__ __forceinline__ float seg_eval(const St3rAlignProblem& pb, const Work
     float uv[2];
     AlignReproj q;
     al_reproj(c1, P2, uv, q);
-    const float d[2] = {pb.e2_pix[2 * m] - uv[0], pb.e2_pix[2 * m + 1] - uv[1]};
+    const float d[2] = {e.x[0] - uv[0], e.x[1] - uv[1]};
     const float dist = sqrtf(d[0] * d[0] + d[1] * d[1]);
     const float l = al_gamma_loss(dist, gamma, offset, off_pow, &dl);
-    const float cw = pb.e2_conf[m] * scale;
     const float k = dist > 0.f ? cw * dl / dist : 0.f;
     const float Guv[2] = {-k * d[0], -k * d[1]};
     float GP[3];
@@ -341,14 +350,13 @@ __device__ __forceinline__ float seg_eval(const St3rAlignProblem& pb, const Work
   } else {
     float P1[3], pc1[3], z1, D1, o1;
     al_anchor_point(c1, e.a1.u, e.a1.v, e.a1.core, e.a1.off, P1, pc1, &z1, &D1, &o1);
-    const float tg[3] = {pb.ed_tgt[3 * m], pb.ed_tgt[3 * m + 1], pb.ed_tgt[3 * m + 2]};
+    const float tg[3] = {e.x[0], e.x[1], e.x[2]};
     float T[3];
     al_mat3_vec(c2.R, tg, T);
     T[0] += c2.t[0]; T[1] += c2.t[1]; T[2] += c2.t[2];
     const float d[3] = {P1[0] - T[0], P1[1] - T[1], P1[2] - T[2]};
     const float dist = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
     const float l = al_gamma_loss(dist, gamma, offset, off_pow, &dl);
-    const float cw = pb.ed_conf[m] * scale;
     const float k = dist > 0.f ? cw * dl / dist : 0.f;
     const float GP1[3] = {k * d[0], k * d[1], k * d[2]};
     al_anchor_point_vjp(c1, e.a1.u, e.a1.v, e.a1.core, e.a1.off, pc1, z1, D1, o1, GP1, g1);
@@ -417,13 +425,13 @@ align_loss_seg_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, fl
         seg_flush(table, cur2, acc2);
         cur1 = f1; cur2 = f2;
       }
-      loss += seg_eval<KIND>(pb, w, m, e, gamma, offset, off_pow, sc, acc1, acc2);
+      loss += seg_eval<KIND>(w.cam, e, gamma, offset, off_pow, sc, acc1, acc2);
     } else {
       // a row that straddles two image pairs: per-row reduction like variant 0
       float g1[NG], g2[NG];
 #pragma unroll
       for (int k = 0; k < NG; ++k) g1[k] = g2[k] = 0.f;
-      loss += seg_eval<KIND>(pb, w, m, e, gamma, offset, off_pow, sc, g1, g2);
+      loss += seg_eval<KIND>(w.cam, e, gamma, offset, off_pow, sc, g1, g2);
       accum_image(table, e.i1, active, g1);
       accum_image(table, e.i2, active, g2);
     }

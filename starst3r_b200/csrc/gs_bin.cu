@@ -197,25 +197,40 @@ __device__ __forceinline__ void bitonic_flip_sort(uint64_t* buf, int n, int nthr
 // __shfl_xor (the mirror step sends element EPT-1-e), and only the spans of 32 * EPT elements and more go through
 // shared memory (two alternating buffers, one barrier per step).  Same comparators, same +inf padding => the same
 // unique order (the 64-bit words are distinct).
+// (FP64 min / max would order these words too - a positive finite fp32 depth in the high half makes the word a positive
+// finite double - but sm_100a has no DMNMX: fmin(double) expands to DSETP + selects, slower than the integer compare.)
+constexpr uint64_t SORT_PAD = ~0ull;                      // +inf padding: above every word, never moves
+__device__ __forceinline__ uint64_t kmin(uint64_t a, uint64_t b) { return a < b ? a : b; }
+__device__ __forceinline__ uint64_t kmax(uint64_t a, uint64_t b) { return a < b ? b : a; }
 __device__ __forceinline__ void cmpswap(uint64_t& a, uint64_t& b) {
-  const uint64_t lo = a < b ? a : b, hi = a < b ? b : a;
+  const uint64_t lo = kmin(a, b), hi = kmax(a, b);
   a = lo; b = hi;
 }
 
+// Warps whose elements are all padding (index >= n_act, the segment length rounded up to a warp's 32 * EPT elements)
+// sit the network out: padding never moves (every comparator puts the minimum at the lower index and the padding
+// holds the highest indices), so a comparator with such an element is a no-op for both sides.  They only keep the
+// block barriers of the shared-memory steps company.  The work then scales with ceil(n / (32 EPT)) warps, not with P.
 template <int EPT>
-__device__ __forceinline__ void reg_exchange_smem(uint64_t (&v)[EPT], uint64_t* sx, int& buf, int xor_mask, int low_bit) {
+__device__ __forceinline__ void reg_exchange_smem(uint64_t (&v)[EPT], uint64_t* sx, int& buf, int xor_mask, int low_bit,
+                                                  bool active, int n_act) {
   constexpr int P = SORT_THREADS * EPT;
   uint64_t* b = sx + buf * P;
   const int i0 = threadIdx.x * EPT;
+  if (active) {
 #pragma unroll
-  for (int e = 0; e < EPT; ++e) b[i0 + e] = v[e];
+    for (int e = 0; e < EPT; ++e) b[i0 + e] = v[e];
+  }
   __syncthreads();
+  if (active) {
 #pragma unroll
-  for (int e = 0; e < EPT; ++e) {
-    const int i = i0 + e;
-    const uint64_t o = b[i ^ xor_mask];
-    const bool keep_min = (i & low_bit) == 0;
-    v[e] = keep_min ? (v[e] < o ? v[e] : o) : (v[e] < o ? o : v[e]);
+    for (int e = 0; e < EPT; ++e) {
+      const int i = i0 + e, partner = i ^ xor_mask;
+      if (partner < n_act) {
+        const uint64_t o = b[partner];
+        v[e] = (i & low_bit) == 0 ? kmin(v[e], o) : kmax(v[e], o);
+      }
+    }
   }
   buf ^= 1;      // the next exchange writes the other buffer: no second barrier needed
 }
@@ -224,74 +239,85 @@ __device__ __forceinline__ void reg_exchange_smem(uint64_t (&v)[EPT], uint64_t* 
 // register index and every step kind is a compile-time constant.
 template <int EPT, int J>
 struct HalfSteps {       // element i against i + J, then J / 2, ... 1
-  static __device__ __forceinline__ void run(uint64_t (&v)[EPT], uint64_t* sx, int& buf, int lane) {
+  static __device__ __forceinline__ void run(uint64_t (&v)[EPT], uint64_t* sx, int& buf, int lane, bool active, int n_act) {
     if constexpr (J >= 1) {
       if constexpr (J < EPT) {
+        if (active) {
 #pragma unroll
-        for (int e = 0; e < EPT; ++e)
-          if ((e & J) == 0) cmpswap(v[e], v[e | J]);
+          for (int e = 0; e < EPT; ++e)
+            if ((e & J) == 0) cmpswap(v[e], v[e | J]);
+        }
       } else if constexpr (J < 32 * EPT) {
-        constexpr int m = J / EPT;
-        const bool keep_min = (lane & m) == 0;
+        if (active) {
+          constexpr int m = J / EPT;
+          const bool keep_min = (lane & m) == 0;
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-          const uint64_t o = (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)v[e], m);
-          v[e] = keep_min ? (v[e] < o ? v[e] : o) : (v[e] < o ? o : v[e]);
+          for (int e = 0; e < EPT; ++e) {
+            const uint64_t o = (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)v[e], m);
+            v[e] = keep_min ? kmin(v[e], o) : kmax(v[e], o);
+          }
         }
       } else {
-        reg_exchange_smem<EPT>(v, sx, buf, J, J);
+        reg_exchange_smem<EPT>(v, sx, buf, J, J, active, n_act);
       }
-      HalfSteps<EPT, J / 2>::run(v, sx, buf, lane);
+      HalfSteps<EPT, J / 2>::run(v, sx, buf, lane, active, n_act);
     }
   }
 };
 
 template <int EPT, int K>
 struct Stages {          // stages K, 2K, ... P
-  static __device__ __forceinline__ void run(uint64_t (&v)[EPT], uint64_t* sx, int& buf, int lane) {
+  static __device__ __forceinline__ void run(uint64_t (&v)[EPT], uint64_t* sx, int& buf, int lane, bool active, int n_act) {
     if constexpr (K <= SORT_THREADS * EPT) {
       // first step of the stage: element i against i ^ (K - 1) (mirror inside every block of K)
       if constexpr (K <= EPT) {
+        if (active) {
 #pragma unroll
-        for (int e = 0; e < EPT; ++e)
-          if ((e & (K >> 1)) == 0) cmpswap(v[e], v[e ^ (K - 1)]);
+          for (int e = 0; e < EPT; ++e)
+            if ((e & (K >> 1)) == 0) cmpswap(v[e], v[e ^ (K - 1)]);
+        }
       } else if constexpr (K <= 32 * EPT) {
-        constexpr int m = K / EPT - 1;                   // lane mask of the partner thread
-        const bool keep_min = (lane & ((m + 1) >> 1)) == 0;
-        uint64_t o[EPT];
+        if (active) {
+          constexpr int m = K / EPT - 1;                   // lane mask of the partner thread
+          const bool keep_min = (lane & ((m + 1) >> 1)) == 0;
+          uint64_t o[EPT];
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) o[e] = (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)v[EPT - 1 - e], m);
+          for (int e = 0; e < EPT; ++e) o[e] = (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)v[EPT - 1 - e], m);
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) v[e] = keep_min ? (v[e] < o[e] ? v[e] : o[e]) : (v[e] < o[e] ? o[e] : v[e]);
+          for (int e = 0; e < EPT; ++e) v[e] = keep_min ? kmin(v[e], o[e]) : kmax(v[e], o[e]);
+        }
       } else {
-        reg_exchange_smem<EPT>(v, sx, buf, K - 1, K >> 1);
+        reg_exchange_smem<EPT>(v, sx, buf, K - 1, K >> 1, active, n_act);
       }
-      HalfSteps<EPT, K / 4>::run(v, sx, buf, lane);
-      Stages<EPT, K * 2>::run(v, sx, buf, lane);
+      HalfSteps<EPT, K / 4>::run(v, sx, buf, lane, active, n_act);
+      Stages<EPT, K * 2>::run(v, sx, buf, lane, active, n_act);
     }
   }
 };
 
 template <int EPT>
-__device__ __forceinline__ void reg_bitonic_sort(uint64_t (&v)[EPT], uint64_t* sx) {
+__device__ __forceinline__ void reg_bitonic_sort(uint64_t (&v)[EPT], uint64_t* sx, int n) {
   int buf = 0;
-  Stages<EPT, 2>::run(v, sx, buf, lane_id());
+  const int n_act = (n + 32 * EPT - 1) / (32 * EPT) * (32 * EPT);
+  const bool active = (int)threadIdx.x * EPT < n_act;              // warp-uniform
+  Stages<EPT, 2>::run(v, sx, buf, lane_id(), active, n_act);
 }
 
 template <int EPT>
-__device__ __forceinline__ void reg_sort_segment(const uint64_t* __restrict__ seg, int n, uint64_t* sx, uint64_t key_hi,
+__device__ __forceinline__ bool reg_sort_segment(const uint64_t* __restrict__ seg, int n, uint64_t* sx, uint64_t key_hi,
                                                  uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   uint64_t v[EPT];
   const int i0 = threadIdx.x * EPT;
 #pragma unroll
-  for (int e = 0; e < EPT; ++e) v[e] = i0 + e < n ? seg[i0 + e] : ~0ull;       // +inf padding sorts to the end
-  reg_bitonic_sort<EPT>(v, sx);
+  for (int e = 0; e < EPT; ++e) v[e] = i0 + e < n ? seg[i0 + e] : SORT_PAD;    // padding sorts to the end
+  reg_bitonic_sort<EPT>(v, sx, n);
 #pragma unroll
   for (int e = 0; e < EPT; ++e)
     if (i0 + e < n) {
       keys[i0 + e] = key_hi | (v[e] >> 32);
       vals[i0 + e] = (uint32_t)v[e];
     }
+  return true;
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
@@ -311,11 +337,12 @@ tile_sort_kernel(int32_t* offsets, const int32_t* __restrict__ total_ptr, int n_
   const uint64_t key_hi = ((((uint64_t)cam << tile_n_bits) | (uint64_t)tile) << 32);
   uint64_t* seg = pairs + lo;
   if (reg_path && n <= 8 * SORT_THREADS) {           // CTA-uniform
-    if (n <= SORT_THREADS) reg_sort_segment<1>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
-    else if (n <= 2 * SORT_THREADS) reg_sort_segment<2>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
-    else if (n <= 4 * SORT_THREADS) reg_sort_segment<4>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
-    else reg_sort_segment<8>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
-    return;
+    bool done;
+    if (n <= SORT_THREADS) done = reg_sort_segment<1>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
+    else if (n <= 2 * SORT_THREADS) done = reg_sort_segment<2>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
+    else if (n <= 4 * SORT_THREADS) done = reg_sort_segment<4>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
+    else done = reg_sort_segment<8>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
+    if (done) return;
   }
   uint64_t* buf = seg;
   if (n <= SMEM_ELEMS) {

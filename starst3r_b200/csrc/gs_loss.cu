@@ -88,6 +88,24 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return s;  // valid in thread 0
 }
 
+// 4-byte asynchronous global -> shared copies (LDGSTS): the halo tiles never pass through registers, and a whole tile
+// is in flight behind one wait.  `valid` = false writes a zero (src-size 0; the address is not dereferenced).
+#ifdef ST3R_HOST_EMU
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool valid) { *smem_dst = valid ? *gsrc : 0.f; }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+#else
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+#endif
+
 // Halo tiles of TWO interleaved [H,W,3] images -> planar [3][LW][TP] arrays (zero outside the image).  A warp takes a
 // row: its 42 pixels are 126 consecutive floats in global memory, lane l reads floats l, l + 32, l + 64, l + 96.
 __device__ __forceinline__ void load_rgb_tiles(const float* __restrict__ img_a, const float* __restrict__ img_b, int H, int W,
@@ -103,22 +121,23 @@ __device__ __forceinline__ void load_rgb_tiles(const float* __restrict__ img_a, 
   for (int r = warp; r < LW; r += NT / 32) {
     const int gy = y0 + r - HALO;
     const bool row_ok = gy >= 0 && gy < H;
-    const long long gbase = ((long long)gy * W + (x0 - HALO)) * 3;
+    const long long gbase = row_ok ? ((long long)gy * W + (x0 - HALO)) * 3 : 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int e = lane + 32 * j;
       if (e < LW * 3) {
-        float a = 0.f, b = 0.f;
-        if (row_ok && gx[j] >= 0 && gx[j] < W) { a = img_a[gbase + e]; b = img_b[gbase + e]; }
-        dst_a[soff[j] + r * TP] = a;
-        dst_b[soff[j] + r * TP] = b;
+        const bool ok = row_ok && gx[j] >= 0 && gx[j] < W;
+        const long long gi = ok ? gbase + e : 0;
+        cp_async4(dst_a + soff[j] + r * TP, img_a + gi, ok);
+        cp_async4(dst_b + soff[j] + r * TP, img_b + gi, ok);
       }
     }
   }
+  cp_async_commit();
 }
 
 // grid: (tiles_x, tiles_y, C); block: 256 threads.  dmaps is planar scratch: [C][channel 3][derivative 3][H][W].
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 3)
 ssim_l1_fwd_kernel(const float* __restrict__ render, const float* __restrict__ truth, int H, int W,
                    float coef_ssim /* dLoss/dS per interior sample */, float* __restrict__ dmaps,
                    float* __restrict__ sums /* per view: [ssim_sum, l1_sum] */) {
@@ -133,6 +152,7 @@ ssim_l1_fwd_kernel(const float* __restrict__ render, const float* __restrict__ t
   load_rgb_tiles(render + (size_t)c * plane * 3, truth + (size_t)c * plane * 3, H, W, x0, y0, tx, ty);
   const int vx = threadIdx.x & 31, vr0 = (threadIdx.x >> 5) * 4;     // vertical pass: column vx, rows vr0 .. vr0 + 3
   float ssim_acc = 0.f, l1_acc = 0.f;
+  cp_async_wait<0>();
   for (int ch = 0; ch < 3; ++ch) {
     __syncthreads();        // tiles loaded / the previous channel's vertical pass is done with hs
     if (threadIdx.x < HITEMS) {
@@ -201,12 +221,14 @@ ssim_l1_fwd_kernel(const float* __restrict__ render, const float* __restrict__ t
   }
 }
 
-__global__ void __launch_bounds__(NT, 4)
+// Backward: the three derivative planes of a channel are brought in with cp.async into one of two tile buffers while
+// the previous channel is being filtered (the loads of channel ch + 1 are issued before channel ch waits for its own).
+__global__ void __launch_bounds__(NT, 3)
 ssim_l1_bwd_kernel(const float* __restrict__ render, const float* __restrict__ truth, const float* __restrict__ dmaps,
                    int H, int W, float coef_l1 /* (1-f) / (3HW) */, float* __restrict__ v_render) {
   ST3R_DYN_SMEM_F32(smem);
-  float* tm = smem;                         // [3 derivatives][LW][TP] of the current channel
-  float* hs = tm + 3 * LW * TP;             // [3][LW][HP]
+  float* tm0 = smem;                        // [2 buffers][3 derivatives][LW][TP]
+  float* hs = tm0 + 2 * 3 * LW * TP;        // [3][LW][HP]
   const int c = blockIdx.z;
   const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
   const size_t plane = (size_t)H * W;
@@ -214,20 +236,38 @@ ssim_l1_bwd_kernel(const float* __restrict__ render, const float* __restrict__ t
   const int vx = lane, vr0 = warp * 4;
   const int gx_a = x0 - HALO + lane, gx_b = gx_a + 32;        // the two columns of a halo row this lane loads
   const bool ok_a = gx_a >= 0 && gx_a < W, ok_b = lane < LW - 32 && gx_b < W;
-  float out[4][3];
-  for (int ch = 0; ch < 3; ++ch) {
-    __syncthreads();        // the previous channel's passes are done with tm / hs
+  auto issue_tile = [&](int ch) {           // a warp per (derivative, row) of the halo tile
     const float* src = dmaps + (((size_t)c * 3 + ch) * 3) * plane;
-    for (int dr = warp; dr < 3 * LW; dr += NT / 32) {       // a warp per (derivative, row)
+    float* tm = tm0 + (ch & 1) * 3 * LW * TP;
+    for (int dr = warp; dr < 3 * LW; dr += NT / 32) {
       const int d = dr / LW, r = dr - d * LW;
       const int gy = y0 + r - HALO;
       const bool row_ok = gy >= 0 && gy < H;
-      const float* g = src + (size_t)d * plane + (long long)gy * W;
-      float* t = tm + (d * LW + r) * TP;
-      t[lane] = (row_ok && ok_a) ? g[gx_a] : 0.f;
-      if (lane < LW - 32) t[lane + 32] = (row_ok && ok_b) ? g[gx_b] : 0.f;
+      const float* g = src + (size_t)d * plane + (row_ok ? (long long)gy * W : 0);
+      float* t = tm + dr * TP;               // (d * LW + r) * TP
+      cp_async4(t + lane, g + (row_ok && ok_a ? gx_a : 0), row_ok && ok_a);
+      if (lane < LW - 32) cp_async4(t + lane + 32, g + (row_ok && ok_b ? gx_b : 0), row_ok && ok_b);
     }
-    __syncthreads();
+    cp_async_commit();
+  };
+  issue_tile(0);
+#pragma unroll 1
+  for (int ch = 0; ch < 3; ++ch) {
+    const float* tm = tm0 + (ch & 1) * 3 * LW * TP;
+    // buffer (ch + 1) & 1 was last read by the horizontal pass of channel ch - 1, which every thread left before the
+    // barrier that preceded that channel's vertical pass
+    if (ch + 1 < 3) { issue_tile(ch + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    float xr[4], yt[4];                      // render / truth pixels of the vertical pass, in flight during the filters
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int px = x0 + vx, py = y0 + vr0 + o;
+      xr[o] = yt[o] = 0.f;
+      if (px < W && py < H) {
+        const size_t p = (((size_t)c * H + py) * W + px) * 3 + ch;
+        xr[o] = render[p]; yt[o] = truth[p];
+      }
+    }
+    __syncthreads();        // this channel's tile has landed; the previous channel's vertical pass is done with hs
     if (threadIdx.x < HITEMS) {
       const int r = threadIdx.x >> 2, q0 = (threadIdx.x & 3) * 8;
 #pragma unroll
@@ -250,23 +290,12 @@ ssim_l1_bwd_kernel(const float* __restrict__ render, const float* __restrict__ t
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
       const int px = x0 + vx, py = y0 + vr0 + o;
-      float r = 0.f;
       if (px < W && py < H) {
-        const size_t p = (((size_t)c * H + py) * W + px) * 3 + ch;
-        const float x = render[p], y = truth[p];
+        const float x = xr[o], y = yt[o];
         const float dd = y - x;
         const float gl1 = dd > 0.f ? -coef_l1 : (dd < 0.f ? coef_l1 : 0.f);
-        r = g[0][o] + 2.f * x * g[1][o] + y * g[2][o] + gl1;
+        v_render[(((size_t)c * H + py) * W + px) * 3 + ch] = g[0][o] + 2.f * x * g[1][o] + y * g[2][o] + gl1;
       }
-      out[o][ch] = r;
-    }
-  }
-#pragma unroll
-  for (int o = 0; o < 4; ++o) {
-    const int px = x0 + vx, py = y0 + vr0 + o;
-    if (px < W && py < H) {
-      float* dst = v_render + (((size_t)c * H + py) * W + px) * 3;
-      dst[0] = out[o][0]; dst[1] = out[o][1]; dst[2] = out[o][2];
     }
   }
 }
@@ -316,7 +345,12 @@ int st3r_gs_loss_bwd(const float* render, const float* truth, const float* dmaps
   ST3R_CHECK_ARG(render && truth && dmaps && v_render, "st3r_gs_loss_bwd: null pointer");
   float coef_l1 = (1.0f - ssim_fac) / (3.0f * (float)height * (float)width);
   dim3 grid((width + LT - 1) / LT, (height + LT - 1) / LT, C);
-  constexpr size_t kSmemBwd = sizeof(float) * (3 * LW * TP + 3 * LW * HP);
+  constexpr size_t kSmemBwd = sizeof(float) * (6 * LW * TP + 3 * LW * HP);
+  static PerDeviceOnce attr_bwd;
+  if (!attr_bwd.done()) {
+    ST3R_CHECK_CUDA(cudaFuncSetAttribute(ssim_l1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBwd));
+    attr_bwd.mark();
+  }
   ssim_l1_bwd_kernel<<<grid, NT, kSmemBwd, stream>>>(render, truth, dmaps, height, width, coef_l1, v_render);
   ST3R_CHECK_LAUNCH();
   return ST3R_OK;

@@ -92,83 +92,100 @@ def flatten_problem(imgs, imsizes, pps, base_focals, core_depth, anchors, corres
                     matching_conf_thr=5.0, device="cpu"):
     """condense_data output (sparse_ga.py:729-814) -> flat arrays for st3r_align_optimize (see St3rAlignProblem).
     Follows reconstruct.py:141-309: pp normalisation (:170), median-normalised core depth (:176-177), focal bounds
-    (:203-205), matching_check (:283-290), loss3d / dust3r slice split and corres2d filtering (:291-309)."""
+    (:203-205), matching_check (:283-290), loss3d / dust3r slice split and corres2d filtering (:291-309).
+    Everything is assembled on `device` (the correspondence data is born there): the per-slice index ranges are expanded
+    with one repeat_interleave per array instead of one arange per slice, and the host reads back twice - the per-image
+    medians / per-slice maximum confidences that decide the layout, then the three confidence sums."""
     dev = torch.device(device)
     N = len(imgs)
-    imsizes_f = imsizes.detach().float().cpu()
-    base_f = torch.as_tensor(base_focals).detach().float().cpu().reshape(-1)
-    core = [c.detach().float().cpu().reshape(-1) for c in core_depth]
-    median = torch.stack([c.median() for c in core])
-    core_n = [c / m for c, m in zip(core, median)]
+    i32, i64 = torch.int32, torch.int64
+
+    def f32(x):
+        return torch.as_tensor(x).detach().to(dev, torch.float32)
+
+    def cat(xs, dtype, shape_tail=()):
+        if xs:
+            return torch.cat(xs).to(dtype).contiguous()
+        return torch.zeros((0,) + shape_tail, dtype=dtype, device=dev)
+
+    def expand(starts, lens):
+        """[starts[0], starts[0] + 1, ..., starts[0] + lens[0] - 1, starts[1], ...] as int32 on the device."""
+        total = int(sum(lens))
+        if total == 0:
+            return torch.zeros(0, dtype=i32, device=dev)
+        lens_t = torch.tensor(lens, dtype=i64, device=dev)
+        base = torch.tensor(starts, dtype=i64, device=dev) - (torch.cumsum(lens_t, 0) - lens_t)
+        return (torch.arange(total, device=dev) + torch.repeat_interleave(base, lens_t, output_size=total)).to(i32)
+
+    def repeat(vals, lens):
+        total = int(sum(lens))
+        if total == 0:
+            return torch.zeros(0, dtype=i32, device=dev)
+        return torch.repeat_interleave(torch.tensor(vals, dtype=i32, device=dev), torch.tensor(lens, dtype=i64, device=dev),
+                                       output_size=total)
+
+    core = [f32(c).reshape(-1) for c in core_depth]
+    med_t = torch.stack([c.median() for c in core])
+    core_n = torch.cat([c / m for c, m in zip(core, med_t)]).contiguous()
+    n_core = [int(c.numel()) for c in core]
+    _, _, slices = corres
+    smax = [f32(s[8]).max() for s in slices]
+    # first read-back: medians, per-slice maximum confidence, image sizes, base focals
+    head = torch.cat([med_t, torch.stack(smax) if smax else med_t[:0], f32(imsizes).reshape(-1), f32(base_focals).reshape(-1)]).cpu()
+    S = len(slices)
+    median, smax_h = head[:N].clone(), head[N:N + S]
+    imsizes_f, base_f = head[N + S:N + S + 2 * N].reshape(N, 2).clone(), head[N + S + 2 * N:].clone()
+    assert base_f.numel() == N
     diag = imsizes_f.norm(dim=1)
     img_names = list(imgs)
     ic_host = np.zeros(N, dtype=[("W", "f4"), ("H", "f4"), ("bf", "f4"), ("med", "f4"), ("minf", "f4"), ("maxf", "f4"),
                                  ("off", "i4"), ("n", "i4")])
     off = 0
     for i in range(N):
-        ic_host[i] = (imsizes_f[i, 0], imsizes_f[i, 1], base_f[i], median[i], 0.25 * diag[i], 10 * diag[i], off,
-                      core_n[i].numel())
-        off += core_n[i].numel()
+        ic_host[i] = (imsizes_f[i, 0], imsizes_f[i, 1], base_f[i], median[i], 0.25 * diag[i], 10 * diag[i], off, n_core[i])
+        off += n_core[i]
     # anchors
-    aoff, a_img, a_uv, a_k, a_off = [0], [], [], [], []
+    aoff = [0]
     for i in range(N):
-        pix, idx, offs = anchors[i]
-        n = len(idx)
-        aoff.append(aoff[-1] + n)
-        a_img.append(torch.full((n,), i, dtype=torch.int32))
-        a_uv.append(pix.detach().cpu().float()[:, :2])
-        a_k.append(idx.detach().cpu().to(torch.int32))
-        a_off.append(offs.detach().cpu().float())
+        aoff.append(aoff[-1] + len(anchors[i][1]))
     n_anchor = aoff[-1]
-    _, _, slices = corres
-    ok = {(s[0], s[4]): bool(s[8].max() > matching_conf_thr) for s in slices}
-    e3a1, e3a2, e3c, eda1, edi2, edt, edc = [], [], [], [], [], [], []
+    counts = [aoff[i + 1] - aoff[i] for i in range(N)]
+    ok = {(s[0], s[4]): bool(smax_h[k] > matching_conf_thr) for k, s in enumerate(slices)}
+    s3a, s3b, l3, e3c = [], [], [], []
+    sda, ldd, vdi, edt, edc = [], [], [], [], []
     for s in slices:
         i1, sl1, i2, sl2, confs = s[0], _sl(s[1]), s[4], _sl(s[5]), s[8]
         if ok[i1, i2]:
-            e3a1.append(aoff[i1] + torch.arange(sl1.start, sl1.stop, dtype=torch.int32))
-            e3a2.append(aoff[i2] + torch.arange(sl2.start, sl2.stop, dtype=torch.int32))
-            e3c.append(confs.detach().cpu().float())
+            s3a.append(aoff[i1] + sl1.start); s3b.append(aoff[i2] + sl2.start); l3.append(sl1.stop - sl1.start)
+            e3c.append(f32(confs))
         else:
             tgt, tc = preds_21[img_names[i2]][img_names[i1]]
-            n1 = aoff[i1 + 1] - aoff[i1]
-            eda1.append(aoff[i1] + torch.arange(n1, dtype=torch.int32))
-            edi2.append(torch.full((n1,), i2, dtype=torch.int32))
-            edt.append(tgt.detach().cpu().float())
-            edc.append(tc.detach().cpu().float())
-    e2i, e2p, e2a, e2c = [], [], [], []
+            sda.append(aoff[i1]); ldd.append(counts[i1]); vdi.append(i2)
+            edt.append(f32(tgt)); edc.append(f32(tc))
+    v2i, s2a, l2, e2p, e2c = [], [], [], [], []
     for img1, pix1, confs, _, sls in corres2d:
         cur = 0
         for img2, sl2 in sls:
             sl2 = _sl(sl2)
             n = sl2.stop - sl2.start
             if ok[img1, img2]:
-                e2i.append(torch.full((n,), img1, dtype=torch.int32))
-                e2p.append(pix1[cur:cur + n].detach().cpu().float())
-                e2c.append(confs[cur:cur + n].detach().cpu().float())
-                e2a.append(aoff[img2] + torch.arange(sl2.start, sl2.stop, dtype=torch.int32))
+                v2i.append(img1); s2a.append(aoff[img2] + sl2.start); l2.append(n)
+                e2p.append(f32(pix1[cur:cur + n])); e2c.append(f32(confs[cur:cur + n]))
             cur += n
-
-    def cat(xs, dtype, shape_tail=()):
-        if xs:
-            return torch.cat(xs).to(dtype).contiguous()
-        return torch.zeros((0,) + shape_tail, dtype=dtype)
     t = dict(
-        img_const=torch.from_numpy(ic_host.view(np.uint8).reshape(N, -1).copy()),
-        core=torch.cat(core_n).contiguous(),
-        edges=torch.tensor([[int(a), int(b)] for a, b in mst[1]], dtype=torch.int32).reshape(-1).contiguous()
-        if len(mst[1]) else torch.zeros(0, dtype=torch.int32),
-        anc_img=cat(a_img, torch.int32), anc_uv=cat(a_uv, torch.float32, (2,)), anc_k=cat(a_k, torch.int32),
-        anc_off=cat(a_off, torch.float32),
-        e3_a1=cat(e3a1, torch.int32), e3_a2=cat(e3a2, torch.int32), e3_conf=cat(e3c, torch.float32),
-        e2_img1=cat(e2i, torch.int32), e2_pix=cat(e2p, torch.float32, (2,)), e2_a2=cat(e2a, torch.int32),
-        e2_conf=cat(e2c, torch.float32),
-        ed_a1=cat(eda1, torch.int32), ed_img2=cat(edi2, torch.int32), ed_tgt=cat(edt, torch.float32, (3,)),
-        ed_conf=cat(edc, torch.float32))
-    meta = dict(N=N, root=int(mst[0]), n_anchor=n_anchor, aoff=aoff, n_core=[c.numel() for c in core_n],
-                norm3=float(t["e3_conf"].sum()), norm2=float(t["e2_conf"].sum()), normd=float(t["ed_conf"].sum()),
+        img_const=torch.from_numpy(ic_host.view(np.uint8).reshape(N, -1).copy()).to(dev),
+        core=core_n,
+        edges=(torch.tensor([[int(a), int(b)] for a, b in mst[1]], dtype=i32).reshape(-1).contiguous()
+               if len(mst[1]) else torch.zeros(0, dtype=i32)).to(dev),
+        anc_img=repeat(list(range(N)), counts), anc_uv=cat([f32(anchors[i][0])[:, :2] for i in range(N)], torch.float32, (2,)),
+        anc_k=cat([anchors[i][1].detach().to(dev) for i in range(N)], i32), anc_off=cat([f32(anchors[i][2]) for i in range(N)], torch.float32),
+        e3_a1=expand(s3a, l3), e3_a2=expand(s3b, l3), e3_conf=cat(e3c, torch.float32),
+        e2_img1=repeat(v2i, l2), e2_pix=cat(e2p, torch.float32, (2,)), e2_a2=expand(s2a, l2), e2_conf=cat(e2c, torch.float32),
+        ed_a1=expand(sda, ldd), ed_img2=repeat(vdi, ldd), ed_tgt=cat(edt, torch.float32, (3,)), ed_conf=cat(edc, torch.float32))
+    norms = torch.stack([t["e3_conf"].sum(), t["e2_conf"].sum(), t["ed_conf"].sum()]).tolist()      # second read-back
+    meta = dict(N=N, root=int(mst[0]), n_anchor=n_anchor, aoff=aoff, n_core=n_core,
+                norm3=float(norms[0]), norm2=float(norms[1]), normd=float(norms[2]),
                 median=median, imsizes=imsizes_f, base_focals=base_f)
-    t = {k: v.to(dev) for k, v in t.items()}
     return t, meta
 
 
