@@ -318,13 +318,20 @@ typedef struct {
 } St3rAlignProblem;
 
 ST3R_API size_t st3r_align_ws_bytes(int n_img);
+/* Workspace size that additionally lets st3r_align_optimize run all `niter` iterations of a call as ONE cooperative
+ * launch (variant bit 2 of st3r_align_set_variant): packed per-entry records of the loss terms, per-CTA gradient rows,
+ * the schedule.  With the smaller st3r_align_ws_bytes workspace the loop runs as three launches per iteration. */
+ST3R_API size_t st3r_align_ws_bytes_for(const St3rAlignProblem* prob, int niter);
 ST3R_API int st3r_align_cam_floats(void);          /* floats per camera record in cam_out: R(9) t(3) f cx cy A B bf pad(2) */
 ST3R_API int st3r_align_img_const_bytes(void);
 /* Implementation variants for subsequent ALIGN calls of this process (bit mask, 0 = default).  Bit 0: the
  * per-correspondence loss kernels of st3r_align_optimize keep the gradients of the current image pair in registers
  * along a contiguous entry range and spread the CTA sums over replicated tables (default: every row of 32 entries
  * is reduced across the warp).  Bit 1: st3r_focal_weiszfeld runs one 8-CTA thread-block cluster per image (default:
- * one CTA).  Same arithmetic per element; only the floating-point summation order differs. */
+ * one CTA).  Bit 2: the whole loop of st3r_align_optimize is ONE cooperative launch - optimiser state replicated in the
+ * shared memory of every CTA, entries packed once per call, one grid barrier per iteration (needs the workspace of
+ * st3r_align_ws_bytes_for and at most 64 images; otherwise the call falls back to three launches per iteration).
+ * Same arithmetic per element; only the floating-point summation order differs. */
 ST3R_API int st3r_align_set_variant(int variant);
 /* Runs `niter` iterations (mode 0: loss_3d, mode 1: loss_2d; both + dust3r_w * loss_dust3r) on the raw parameters
  * pp [N,2] (normalised principal points), log_focal [N], quat [N,4] (XYZW), trans [N,3], log_size [N]; Adam moments

@@ -14,6 +14,7 @@
 // loop is latency-bound, so the figure of merit is iterations/s.
 // ST3R_HOST_EMU: test builds that run this file on a CPU SIMT emulator (tests/host/): align_emu_host.cpp includes the
 // kernels only, build_emu_lib.py (ST3R_EMU_WHOLE) compiles the entry points too, with their launches rewritten.
+#include <vector>
 #if !defined(ST3R_HOST_EMU) || defined(ST3R_EMU_WHOLE)
 #include "common.cuh"
 #endif
@@ -535,6 +536,294 @@ align_cam_bwd_kernel(St3rAlignProblem pb, Params p, AdamState ad, Work w, int tr
   }
 }
 
+// ---- variant 4 (bit 2): the whole optimisation loop in ONE cooperative launch ------------------------------------
+// Launch-per-iteration (above): three dependent launches per iteration, two of them single-CTA kernels whose work is
+// a serial chain over the images, and loss kernels that chase four dependent loads per entry (entry -> anchor ->
+// image record -> core depth): 89 / 106 us per coarse / fine iteration at 8 views 512 x 512 (profiles/r02w), for
+// ~25 MB of entry data that should stream in a few microseconds.  Here:
+//   * align_pack_kernel resolves the indirections ONCE per call (anchors and core depths are constants of the problem):
+//     three float4 per entry, read with coalesced 128-bit loads, the next row prefetched while the current one is
+//     evaluated;
+//   * every CTA keeps its OWN copy of the optimiser state (parameters, Adam moments, camera records) in shared memory
+//     and runs the camera forward, the MST chain, the camera backward and Adam redundantly - they are O(N) and
+//     deterministic, so all copies stay bit-identical without any exchange;
+//   * the only exchange per iteration is the per-image gradient table: each CTA writes the sums of its slice of the
+//     entries to its own row of a [2][grid][17 N + 2] buffer, one grid-wide barrier (a monotonic counter in global
+//     memory; the launch is cooperative, so all CTAs are resident), and every CTA adds the rows in the same order.
+//     The two halves of the buffer alternate between iterations, which makes that single barrier sufficient.
+// N <= PERSIST_MAX_IMG (the shared-memory copies are static arrays); larger problems take the path above.
+constexpr int PERSIST_THREADS = 512;
+constexpr int PERSIST_MAX_IMG = 64;
+
+// Packed entry: a = anchor 1 (u, v, core, off) [KIND 1: the pixel], b = anchor 2 [KIND 2: the regression target],
+// x = (conf, bits of (img1 << 16 | img2), -, -).
+template <int KIND>
+__global__ void __launch_bounds__(256)
+align_pack_kernel(St3rAlignProblem pb, float4* __restrict__ out, int n) {
+  const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  SegEntry<KIND> e;
+  seg_load<KIND>(pb, ic, m, e);
+  float4 a, b;
+  if (KIND == 1) a = make_float4(e.x[0], e.x[1], 0.f, 0.f);
+  else a = make_float4(e.a1.u, e.a1.v, e.a1.core, e.a1.off);
+  if (KIND == 2) b = make_float4(e.x[0], e.x[1], e.x[2], 0.f);
+  else b = make_float4(e.a2.u, e.a2.v, e.a2.core, e.a2.off);
+  out[m] = a;
+  out[(size_t)n + m] = b;
+  out[2 * (size_t)n + m] = make_float4(e.conf, __int_as_float((e.i1 << 16) | e.i2), 0.f, 0.f);
+}
+
+template <int KIND>
+__device__ __forceinline__ void seg_unpack(const float4& a, const float4& b, const float4& x, SegEntry<KIND>& e) {
+  const int key = __float_as_int(x.y);
+  e.i1 = key >> 16; e.i2 = key & 0xffff;
+  e.conf = x.x;
+  e.x[0] = e.x[1] = e.x[2] = 0.f;
+  if (KIND == 1) { e.x[0] = a.x; e.x[1] = a.y; }
+  else { e.a1.img = e.i1; e.a1.u = a.x; e.a1.v = a.y; e.a1.core = a.z; e.a1.off = a.w; }
+  if (KIND == 2) { e.x[0] = b.x; e.x[1] = b.y; e.x[2] = b.z; }
+  else { e.a2.img = e.i2; e.a2.u = b.x; e.a2.v = b.y; e.a2.core = b.z; e.a2.off = b.w; }
+}
+
+struct PersistArgs {
+  St3rAlignProblem pb; Params p; AdamState ad; Work w;
+  const float4* pk_main; int n_main;          // packed entries of the main loss (KIND 0 or 1)
+  const float4* pk_d; int n_d;                // packed entries of the dust3r term (KIND 2)
+  float gamma, off_m, offp_m, scale_main, gamma_d, off_d, offp_d, scale_d;
+  int train_mask; float omb1, b2, omb2, eps;
+  const float2* sched;                        // [niter]: (lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t))
+  int niter; float* loss_hist; float* grad_out;
+  float* partial;                             // [2][grid][17 N + 2]
+  unsigned* bar;                              // grid barrier counter (zero at launch)
+};
+
+#ifndef ST3R_HOST_EMU
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();                          // this CTA's partial sums are visible before its arrival
+    atomicAdd(bar, 1u);
+    unsigned v, spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (++spins > (1u << 27)) __trap();     // a protocol bug becomes a CUDA error instead of a hung GPU
+    } while (v < target);
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ float ld_l2(const float* p) { return __ldcg(p); }     // L2 is the point of coherence between SMs
+#else
+__device__ __forceinline__ void grid_barrier(unsigned*, unsigned) { emu::cluster_sync(); }   // the grid runs as one emulated cluster
+__device__ __forceinline__ float ld_l2(const float* p) { return *p; }
+#endif
+
+// One warp walks rows [begin, end) of a packed entry array (32 entries per row) with the segmented register
+// accumulation of align_loss_seg_kernel; returns the lane's loss share.
+template <int KIND>
+__device__ __forceinline__ float persist_walk(const float4* __restrict__ pk, int n, int begin, int end, const AlignCam* cams,
+                                              float* table, float gamma, float offset, float off_pow, float scale) {
+  const int lane = lane_id();
+  float acc1[NG], acc2[NG];
+#pragma unroll
+  for (int k = 0; k < NG; ++k) acc1[k] = acc2[k] = 0.f;
+  int cur1 = -1, cur2 = -1;
+  float loss = 0.f;
+  float4 na, nb, nx;
+  {
+    const int m = begin + lane < end ? begin + lane : end - 1;
+    if (begin < end) { na = pk[m]; nb = pk[(size_t)n + m]; nx = pk[2 * (size_t)n + m]; }
+  }
+  for (int base = begin; base < end; base += 32) {
+    const bool active = base + lane < end;
+    const float4 a = na, b = nb, x = nx;
+    if (base + 32 < end) {                     // prefetch the next row while this one is evaluated
+      const int m = base + 32 + lane < end ? base + 32 + lane : end - 1;
+      na = pk[m]; nb = pk[(size_t)n + m]; nx = pk[2 * (size_t)n + m];
+    }
+    const float sc = active ? scale : 0.f;     // lanes past the end redo the last entry with weight zero
+    SegEntry<KIND> e;
+    seg_unpack<KIND>(a, b, x, e);
+    const int key = (e.i1 << 16) | e.i2;
+    const int first = __reduce_max_sync(0xffffffffu, key);
+    if (__all_sync(0xffffffffu, key == first)) {
+      const int f1 = first >> 16, f2 = first & 0xffff;
+      if (__any_sync(0xffffffffu, f1 != cur1 || f2 != cur2)) {
+        seg_flush(table, cur1, acc1);
+        seg_flush(table, cur2, acc2);
+        cur1 = f1; cur2 = f2;
+      }
+      loss += seg_eval<KIND>(cams, e, gamma, offset, off_pow, sc, acc1, acc2);
+    } else {
+      float g1[NG], g2[NG];
+#pragma unroll
+      for (int k = 0; k < NG; ++k) g1[k] = g2[k] = 0.f;
+      loss += seg_eval<KIND>(cams, e, gamma, offset, off_pow, sc, g1, g2);
+      accum_image(table, e.i1, active, g1);
+      accum_image(table, e.i2, active, g2);
+    }
+  }
+  seg_flush(table, cur1, acc1);
+  seg_flush(table, cur2, acc2);
+  return loss;
+}
+
+// The CTA's copy of the optimiser state.  (File scope rather than inside the kernel template: the CPU emulator of
+// tests/host keeps one copy of the shared-memory section per CTA, and function-local statics of a template are
+// emitted outside that section.)
+__shared__ AlignCam s_cam[PERSIST_MAX_IMG];
+__shared__ AlignCamTmp s_tmp[PERSIST_MAX_IMG];
+__shared__ AlignCamGrad s_cg[PERSIST_MAX_IMG];
+__shared__ float s_par[11 * PERSIST_MAX_IMG], s_m[11 * PERSIST_MAX_IMG], s_v[11 * PERSIST_MAX_IMG];
+__shared__ float s_table[NG * PERSIST_MAX_IMG], s_gsum[NG * PERSIST_MAX_IMG];
+__shared__ int s_edges[2 * PERSIST_MAX_IMG];
+__shared__ float s_red[PERSIST_THREADS / 32][2];
+__shared__ float s_scal[8];                    // g, ties, smin, loss main, loss dust3r, stop flag, sum of g_g
+
+template <int KIND_MAIN>
+__global__ void __launch_bounds__(PERSIST_THREADS, 1)
+align_persist_kernel(const PersistArgs a) {
+  const St3rAlignProblem& pb = a.pb;
+  const int N = pb.n_img, tid = threadIdx.x, nthr = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
+  // shared copy of the optimiser state: [pp 2N | log_focal N | quat 4N | trans 3N | log_size N], moments [N][11]
+  float* s_pp = s_par, *s_lf = s_par + 2 * N, *s_q = s_par + 3 * N, *s_tr = s_par + 7 * N, *s_ls = s_par + 10 * N;
+  for (int i = tid; i < 2 * N; i += nthr) s_pp[i] = a.p.pp[i];
+  for (int i = tid; i < N; i += nthr) { s_lf[i] = a.p.log_focal[i]; s_ls[i] = a.p.log_size[i]; }
+  for (int i = tid; i < 4 * N; i += nthr) s_q[i] = a.p.quat[i];
+  for (int i = tid; i < 3 * N; i += nthr) s_tr[i] = a.p.trans[i];
+  for (int i = tid; i < 11 * N; i += nthr) { s_m[i] = a.ad.m[i]; s_v[i] = a.ad.v[i]; }
+  for (int i = tid; i < 2 * (N - 1); i += nthr) s_edges[i] = pb.edges[i];
+  if (tid == 0) s_scal[5] = 0.f;
+  // this CTA's slice of the entry rows, split over its warps
+  const long long gw = (long long)blockIdx.x * nwarps + warp, tw = (long long)gridDim.x * nwarps;
+  auto slice = [&](int n, int& begin, int& end) {
+    const long long per = ((n + tw - 1) / tw + 31) / 32 * 32;
+    const long long b0 = gw * per, e0 = b0 + per;
+    begin = __reduce_max_sync(0xffffffffu, (int)(b0 < n ? b0 : n));       // (warp-uniform values the compiler can see)
+    end = __reduce_max_sync(0xffffffffu, (int)(e0 < n ? e0 : n));
+  };
+  int mb, me, db, de;
+  slice(a.n_main, mb, me);
+  slice(a.n_d, db, de);
+  const int row_len = NG * N + 2;
+  __syncthreads();
+
+  for (int it = 0; it < a.niter; ++it) {
+    if (s_scal[5] != 0.f) break;               // NaN loss seen (identical in every CTA): reconstruct.py:398-399
+    // ---- camera forward (redundant in every CTA)
+    float best = INFINITY;
+    for (int i = tid; i < N; i += nthr) {
+      al_cam_local_fwd(ic[i], s_lf[i], s_ls[i], s_q + 4 * i, s_tmp[i]);
+      best = fminf(best, s_tmp[i].s);
+    }
+    for (int off = 16; off; off >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if (lane == 0) s_red[warp][0] = best;
+    for (int e = tid; e < NG * N; e += nthr) s_table[e] = 0.f;
+    __syncthreads();
+    if (tid == 0) {
+      float b = INFINITY;
+      for (int k = 0; k < nwarps; ++k) b = fminf(b, s_red[k][0]);
+      int ties = 0;                            // torch's min() backward splits the gradient between tied minima
+      for (int i = 0; i < N; ++i) ties += (s_tmp[i].s == b) ? 1 : 0;
+      s_scal[0] = 1.0f / b; s_scal[1] = (float)ties; s_scal[2] = b;
+      al_chain_fwd(N, pb.root, s_edges, s_tmp, s_tr);
+    }
+    __syncthreads();
+    const float g = s_scal[0];
+    for (int i = tid; i < N; i += nthr) al_cam_final_fwd(ic[i], s_pp + 2 * i, g, s_tmp[i], s_cam[i]);
+    __syncthreads();
+    if (blockIdx.x == 0)                       // the records of the LAST forward are the result (reconstruct.py:379-380)
+      for (int i = tid; i < N * (int)(sizeof(AlignCam) / 4); i += nthr)
+        reinterpret_cast<float*>(a.w.cam)[i] = reinterpret_cast<const float*>(s_cam)[i];
+    // ---- loss + gradient table of this CTA's slice
+    float l_main = 0.f, l_d = 0.f;
+    if (a.n_main > 0)
+      l_main = persist_walk<KIND_MAIN>(a.pk_main, a.n_main, mb, me, s_cam, s_table, a.gamma, a.off_m, a.offp_m, a.scale_main);
+    if (a.n_d > 0)
+      l_d = persist_walk<2>(a.pk_d, a.n_d, db, de, s_cam, s_table, a.gamma_d, a.off_d, a.offp_d, a.scale_d);
+    for (int off = 16; off; off >>= 1) {
+      l_main += __shfl_xor_sync(0xffffffffu, l_main, off);
+      l_d += __shfl_xor_sync(0xffffffffu, l_d, off);
+    }
+    if (lane == 0) { s_red[warp][0] = l_main; s_red[warp][1] = l_d; }
+    __syncthreads();
+    float* mine = a.partial + ((size_t)(it & 1) * gridDim.x + blockIdx.x) * row_len;
+    for (int e = tid; e < NG * N; e += nthr) mine[e] = s_table[e];
+    if (tid == 0) {
+      float s0 = 0.f, s1 = 0.f;
+      for (int k = 0; k < nwarps; ++k) { s0 += s_red[k][0]; s1 += s_red[k][1]; }
+      mine[NG * N] = s0; mine[NG * N + 1] = s1;
+    }
+    grid_barrier(a.bar, (unsigned)(it + 1) * gridDim.x);
+    // ---- every CTA adds the rows in the same order: identical sums everywhere
+    const float* rows = a.partial + (size_t)(it & 1) * gridDim.x * row_len;
+    for (int e = tid; e < row_len; e += nthr) {
+      float v = 0.f;
+      for (unsigned c = 0; c < gridDim.x; ++c) v += ld_l2(rows + (size_t)c * row_len + e);
+      if (e < NG * N) s_gsum[e] = v; else s_scal[3 + (e - NG * N)] = v;
+    }
+    __syncthreads();
+    // ---- camera backward + Adam (redundant in every CTA)
+    float gg = 0.f;
+    for (int i = tid; i < N; i += nthr) {
+      al_cam_final_bwd(ic[i], s_pp + 2 * i, g, s_tmp[i], s_gsum + i * NG, s_cg[i]);
+      gg += s_cg[i].g_g;
+    }
+    for (int off = 16; off; off >>= 1) gg += __shfl_xor_sync(0xffffffffu, gg, off);
+    if (lane == 0) s_red[warp][0] = gg;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+      for (int k = 0; k < nwarps; ++k) t += s_red[k][0];
+      s_scal[6] = t;
+      al_chain_bwd(N, pb.root, s_edges, s_tmp, s_tr, s_cg);
+      const float loss = s_scal[3] + s_scal[4];            // the dust3r weight is folded into scale_d
+      if (blockIdx.x == 0 && a.loss_hist) a.loss_hist[it] = loss;
+      if (loss != loss) s_scal[5] = 1.0f;                   // NaN: this iteration still steps, the next one stops
+    }
+    __syncthreads();
+    const float gg_total = s_scal[6], ties = s_scal[1], smin = s_scal[2];
+    const float2 sch = a.sched[it];
+    for (int i = tid; i < N; i += nthr) {
+      float g_pp[2], g_lf, g_q[4], g_t[3], g_ls;
+      const float extra = (s_tmp[i].s == smin) ? -gg_total * g * g / ties : 0.f;
+      al_cam_local_bwd(s_tmp[i], s_cg[i], extra, g_pp, &g_lf, g_q, g_t, &g_ls);
+      if (a.grad_out && blockIdx.x == 0 && it == a.niter - 1) {
+        float* o = a.grad_out + 11 * i;
+        o[0] = g_pp[0]; o[1] = g_pp[1]; o[2] = g_lf; o[3] = g_q[0]; o[4] = g_q[1]; o[5] = g_q[2]; o[6] = g_q[3];
+        o[7] = g_t[0]; o[8] = g_t[1]; o[9] = g_t[2]; o[10] = g_ls;
+      }
+      float* m = s_m + 11 * i;
+      float* v = s_v + 11 * i;
+      if (a.train_mask & 1) {
+        adam_update(s_pp + 2 * i, g_pp[0], m + 0, v + 0, sch.x, sch.y, a.omb1, a.b2, a.omb2, a.eps);
+        adam_update(s_pp + 2 * i + 1, g_pp[1], m + 1, v + 1, sch.x, sch.y, a.omb1, a.b2, a.omb2, a.eps);
+      }
+      if (a.train_mask & 2) adam_update(s_lf + i, g_lf, m + 2, v + 2, sch.x, sch.y, a.omb1, a.b2, a.omb2, a.eps);
+      if (a.train_mask & 4)
+        for (int k = 0; k < 4; ++k) adam_update(s_q + 4 * i + k, g_q[k], m + 3 + k, v + 3 + k, sch.x, sch.y, a.omb1, a.b2, a.omb2, a.eps);
+      if (a.train_mask & 8)
+        for (int k = 0; k < 3; ++k) adam_update(s_tr + 3 * i + k, g_t[k], m + 7 + k, v + 7 + k, sch.x, sch.y, a.omb1, a.b2, a.omb2, a.eps);
+      if (a.train_mask & 16) adam_update(s_ls + i, g_ls, m + 10, v + 10, sch.x, sch.y, a.omb1, a.b2, a.omb2, a.eps);
+      float* q = s_q + 4 * i;                                // quats[i].data[:] /= quats[i].data.norm()  (:394-395)
+      const float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+      q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0) {                                      // the state after the last step goes back to the caller
+    for (int i = tid; i < 2 * N; i += nthr) a.p.pp[i] = s_pp[i];
+    for (int i = tid; i < N; i += nthr) { a.p.log_focal[i] = s_lf[i]; a.p.log_size[i] = s_ls[i]; }
+    for (int i = tid; i < 4 * N; i += nthr) a.p.quat[i] = s_q[i];
+    for (int i = tid; i < 3 * N; i += nthr) a.p.trans[i] = s_tr[i];
+    for (int i = tid; i < 11 * N; i += nthr) { a.ad.m[i] = s_m[i]; a.ad.v[i] = s_v[i]; }
+    if (tid == 0 && s_scal[5] != 0.f) a.w.sums[3] = 1.0f;
+  }
+}
+
 // pts3d of every anchor + dense depth maps from the last forward's camera records.
 __global__ void align_outputs_kernel(St3rAlignProblem pb, Work w, float* pts3d, float* depthmaps, int n_core_total) {
   const AlignImgConst* ic = reinterpret_cast<const AlignImgConst*>(pb.img_const);
@@ -579,7 +868,7 @@ int align_variant() { return g_align_variant; }
 extern "C" {
 
 int st3r_align_set_variant(int variant) {
-  ST3R_CHECK_ARG(variant >= 0 && variant <= 3, "st3r_align_set_variant: unknown variant %d", variant);
+  ST3R_CHECK_ARG(variant >= 0 && variant <= 7, "st3r_align_set_variant: unknown variant %d", variant);
   g_align_variant = variant;
   return ST3R_OK;
 }
@@ -588,6 +877,29 @@ size_t st3r_align_ws_bytes(int n_img) {
   size_t n = (size_t)(n_img > 0 ? n_img : 1);
   return st3r_align_up(n * sizeof(AlignCam), 256) + st3r_align_up(n * sizeof(AlignCamTmp), 256) +
          st3r_align_up(n * sizeof(AlignCamGrad), 256) + st3r_align_up(n * NG * ALIGN_REPL * sizeof(float), 256) + 4096;
+}
+
+// Workspace that also lets st3r_align_optimize run its loop as ONE cooperative launch (variant bit 2): the packed
+// entries of the loss terms, the per-CTA gradient rows, the schedule and the barrier word.  One carving routine serves
+// the size query (null base) and the call.
+struct PersistWs { float4* pk_main; float4* pk_d; float* partial; float2* sched; unsigned* bar; };
+static size_t carve_persist(PersistWs* out, void* base, const St3rAlignProblem& pb, int niter) {
+  WsAlloc a(base, (size_t)-1);
+  const size_t n_main = (size_t)(pb.n3 > pb.n2 ? pb.n3 : pb.n2);
+  const size_t row = (size_t)NG * (pb.n_img > 0 ? pb.n_img : 1) + 2;
+  PersistWs w;
+  w.pk_main = a.take<float4>(3 * n_main + 1);
+  w.pk_d = a.take<float4>(3 * (size_t)(pb.nd > 0 ? pb.nd : 0) + 1);
+  w.partial = a.take<float>(2 * row * (size_t)st3r_num_sms());
+  w.sched = a.take<float2>((size_t)(niter > 0 ? niter : 1));
+  w.bar = a.take<unsigned>(64);
+  if (out) *out = w;
+  return st3r_align_up(a.off, 256);
+}
+static size_t persist_extra_bytes(const St3rAlignProblem& pb, int niter) { return carve_persist(nullptr, nullptr, pb, niter); }
+size_t st3r_align_ws_bytes_for(const St3rAlignProblem* prob, int niter) {
+  if (!prob) return 0;
+  return st3r_align_ws_bytes(prob->n_img) + persist_extra_bytes(*prob, niter);
 }
 int st3r_align_cam_floats(void) { return (int)(sizeof(AlignCam) / sizeof(float)); }
 int st3r_align_img_const_bytes(void) { return (int)sizeof(AlignImgConst); }
@@ -650,6 +962,65 @@ int st3r_align_optimize(const St3rAlignProblem* prob, float* pp, float* log_foca
   };
 
   const int iters = niter > 0 ? niter : 1;
+  const bool dust = pb.nd > 0 && dust3r_w != 0.f;
+  const bool persist = (g_align_variant & 4) && niter > 0 && N <= PERSIST_MAX_IMG && N < 32768 &&
+                       (n_main > 0 || dust) && ws_bytes >= st3r_align_ws_bytes(N) + persist_extra_bytes(pb, niter);
+  if (persist) {
+    // ---- one cooperative launch for the whole loop (see align_persist_kernel)
+    PersistWs pw;
+    carve_persist(&pw, static_cast<char*>(ws) + st3r_align_ws_bytes(N), pb, niter);
+    float4* pk_main = pw.pk_main;
+    float4* pk_d = pw.pk_d;
+    float* partial = pw.partial;
+    float2* sched = pw.sched;
+    unsigned* bar = pw.bar;
+    std::vector<float2> h_sched((size_t)niter);
+    for (int it = 0; it < niter; ++it) {
+      const double bc1 = 1.0 - pow(beta1, (double)(it + 1)), bc2 = 1.0 - pow(beta2, (double)(it + 1));
+      h_sched[it] = make_float2((float)((double)h_lr[it] / bc1), (float)(1.0 / sqrt(bc2)));
+    }
+    // (h_sched is pageable: the call returns once the buffer has been staged, so the local vector may go away)
+    ST3R_CHECK_CUDA(cudaMemcpyAsync(sched, h_sched.data(), sizeof(float2) * (size_t)niter, cudaMemcpyHostToDevice, stream));
+    ST3R_CHECK_CUDA(cudaMemsetAsync(bar, 0, 64, stream));
+    if (n_main > 0) {
+      if (mode == 0) align_pack_kernel<0><<<(n_main + 255) / 256, 256, 0, stream>>>(pb, pk_main, n_main);
+      else align_pack_kernel<1><<<(n_main + 255) / 256, 256, 0, stream>>>(pb, pk_main, n_main);
+      ST3R_CHECK_LAUNCH();
+    }
+    if (dust) {
+      align_pack_kernel<2><<<(pb.nd + 255) / 256, 256, 0, stream>>>(pb, pk_d, pb.nd);
+      ST3R_CHECK_LAUNCH();
+    }
+    PersistArgs pa;
+    pa.pb = pb; pa.p = p; pa.ad = ad; pa.w = w;
+    pa.pk_main = pk_main; pa.n_main = n_main; pa.pk_d = pk_d; pa.n_d = dust ? pb.nd : 0;
+    pa.gamma = gamma; pa.off_m = off_m; pa.offp_m = offp_m; pa.scale_main = scale_main;
+    pa.gamma_d = gamma_dust3r; pa.off_d = off_d; pa.offp_d = offp_d; pa.scale_d = scale_d * dust3r_w;
+    pa.train_mask = train_mask; pa.omb1 = (float)(1.0 - beta1); pa.b2 = (float)beta2; pa.omb2 = (float)(1.0 - beta2);
+    pa.eps = (float)eps; pa.sched = sched; pa.niter = niter; pa.loss_hist = loss_hist; pa.grad_out = grad_out;
+    pa.partial = partial; pa.bar = bar;
+    // enough CTAs that a warp walks ~4 rows of 32 entries, at most one CTA per SM (all resident: the barrier needs it)
+    const long long rows = ((long long)n_main + pa.n_d + 31) / 32;
+#ifdef ST3R_HOST_EMU
+    long long want = (rows + 7) / 8;                       // (test builds: several CTAs even on the small fixtures)
+#else
+    long long want = (rows + 4 * (PERSIST_THREADS / 32) - 1) / (4 * (PERSIST_THREADS / 32));
+#endif
+    int grid = (int)(want < 1 ? 1 : (want > st3r_num_sms() ? st3r_num_sms() : want));
+#ifdef ST3R_HOST_EMU
+    if (grid > 4) grid = 4;                                // the emulator runs the grid as one cluster of fibers
+    if (mode == 0) emu_launch_cluster(grid, dim3(grid), dim3(PERSIST_THREADS), [&]() { align_persist_kernel<0>(pa); });
+    else emu_launch_cluster(grid, dim3(grid), dim3(PERSIST_THREADS), [&]() { align_persist_kernel<1>(pa); });
+#else
+    void* kargs[] = {(void*)&pa};
+    const void* fn = mode == 0 ? (const void*)align_persist_kernel<0> : (const void*)align_persist_kernel<1>;
+    int per_sm = 0;
+    ST3R_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PERSIST_THREADS, 0));
+    ST3R_CHECK_ARG(per_sm >= 1, "st3r_align_optimize: the persistent kernel does not fit on an SM");
+    ST3R_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PERSIST_THREADS), kargs, 0, stream));
+#endif
+    ST3R_CHECK_LAUNCH();
+  } else
   for (int it = 0; it < iters; ++it) {
     if (stage) align_cam_fwd_kernel<true><<<1, CAM_THREADS, 0, stream>>>(pb, p, w);
     else align_cam_fwd_kernel<false><<<1, CAM_THREADS, 0, stream>>>(pb, p, w);

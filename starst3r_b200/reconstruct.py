@@ -203,10 +203,12 @@ def problem_struct(t, meta):
 
 # Variants of the ALIGN kernels (bit mask of st3r_align_set_variant): bit 0 = segmented register accumulation +
 # replicated gradient tables in the loss kernels and staged camera kernels, bit 1 = one thread-block cluster per image in
-# the Weiszfeld focal kernel.  Both on by default (B200, profiles/r02a_variants.json: reconstruct_scene 0.388 -> 0.356 s
-# on 8 views 512 x 512); 0 = the first implementation, kept as cross-check (tests/test_align_gpu.py runs both).
+# the Weiszfeld focal kernel (B200, profiles/r02a_variants.json: reconstruct_scene 0.388 -> 0.356 s on 8 views 512 x 512),
+# bit 2 = the whole optimisation loop of a phase as ONE cooperative launch (optimiser state replicated in every CTA's
+# shared memory, entries packed once, one grid barrier per iteration; up to 64 images).  All on by default; 0 = the
+# first implementation and 3 = the launch-per-iteration loop, kept as cross-checks (tests/test_align_gpu.py runs them).
 # ST3R_ALIGN_VARIANT sets the initial value.
-ALIGN_VARIANT = int(os.environ.get("ST3R_ALIGN_VARIANT", "3"))
+ALIGN_VARIANT = int(os.environ.get("ST3R_ALIGN_VARIANT", "7"))
 
 
 def _optimize_phase(t, meta, params, mode, train_mask, gamma, lr_base, niter, schedule, dust3r_w, lossd_gamma,
@@ -227,7 +229,7 @@ def _optimize_phase(t, meta, params, mode, train_mask, gamma, lr_base, niter, sc
     pts3d = torch.empty(max(meta["n_anchor"], 1), 3, device=dev)
     depth = torch.empty(max(int(t["core"].numel()), 1), device=dev)
     grad = torch.zeros(N, 11, device=dev) if want_grad else None
-    ws = torch.empty(lib.st3r_align_ws_bytes(N), dtype=torch.uint8, device=dev)
+    ws = torch.empty(lib.st3r_align_ws_bytes_for(ctypes.byref(prob), niter), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         rc = lib.st3r_align_optimize(ctypes.byref(prob), _lib.ptr(params["pps"]), _lib.ptr(params["log_focals"]),
                                      _lib.ptr(params["quats"]), _lib.ptr(params["trans"]), _lib.ptr(params["log_sizes"]),

@@ -206,23 +206,27 @@ def test_pipelined_pair_loop_equals_sequential(cuda_device, monkeypatch):
 
 
 def test_first_implementation_of_the_align_kernels_as_cross_check(cuda_device, monkeypatch):
-    """reconstruct.ALIGN_VARIANT = 0 (per-row shuffles + shared atomics in the loss kernels, single-CTA Weiszfeld): the
-    first implementation of the kernels, an independent second path to the same fixtures, and both variants walk the
-    same loss history up to fp32 summation order."""
+    """reconstruct.ALIGN_VARIANT = 3 (the loop as three launches per iteration) and 0 (per-row shuffles + shared atomics
+    in the loss kernels, single-CTA Weiszfeld: the first implementation): independent second and third paths to the
+    same fixtures as the default (7: the loop as one cooperative launch), and all of them walk the same loss history up
+    to fp32 summation order."""
     from starst3r_b200 import reconstruct as rc
     out = {}
-    for v in (3, 0):
+    for v in (7, 3, 0):
         monkeypatch.setattr(rc, "ALIGN_VARIANT", v)
         _, res_c, _, _ = run_slam(fx("align_match3.pt"), cuda_device, 30, 0)
         out[v] = cpu(res_c)
-    assert torch.allclose(out[0]["intrinsics"], out[3]["intrinsics"], rtol=1e-4, atol=1e-3)
-    for a, b in zip(out[0]["depthmaps"], out[3]["depthmaps"]):
-        assert torch.allclose(a, b, rtol=1e-3, atol=1e-4)
+    for v in (3, 7):
+        assert torch.allclose(out[0]["intrinsics"], out[v]["intrinsics"], rtol=1e-4, atol=1e-3)
+        for a, b in zip(out[0]["depthmaps"], out[v]["depthmaps"]):
+            assert torch.allclose(a, b, rtol=1e-3, atol=1e-4)
+    for v in (3, 0):
+        monkeypatch.setattr(rc, "ALIGN_VARIANT", v)
+        for name in ("align_match3.pt", "align_dust3r3.pt"):
+            test_optimizer_vs_reference(cuda_device, name)
+            test_kernel_loss_and_gradients_vs_autograd(cuda_device, name, 0)
+        test_kernel_loss_and_gradients_vs_autograd(cuda_device, "align_match3.pt", 1)
     monkeypatch.setattr(rc, "ALIGN_VARIANT", 0)
-    for name in ("align_match3.pt", "align_dust3r3.pt"):
-        test_optimizer_vs_reference(cuda_device, name)
-        test_kernel_loss_and_gradients_vs_autograd(cuda_device, name, 0)
-    test_kernel_loss_and_gradients_vs_autograd(cuda_device, "align_match3.pt", 1)
     test_canonical_view_focal_dense_clean_vs_reference(cuda_device)
 
 

@@ -5,14 +5,15 @@ refuses anything but CUDA by design, so this test (and only the test) swaps the 
 torch.cuda.device for host stand-ins; the checks are the ones tests/test_align_gpu.py makes on the B200, against the
 fixtures produced by the unmodified reference (oracle/gen_golden_align.py): canonical view, Weiszfeld focal, dense
 points, clean_pointcloud, loss + gradients vs autograd, and the 30 + 20 iteration trajectory - for the default kernels
-and for the opt-in variants (segmented loss kernels, staged camera kernels, cluster Weiszfeld)."""
+for the default kernels (the optimisation loop as one cooperative launch: the emulator runs its grid as one cluster of
+fibers, the grid barrier as a cluster barrier), the launch-per-iteration loop and the first implementation."""
 import pytest
 import torch
 
 CPU = torch.device("cpu")
 
 
-@pytest.fixture(params=[3, 0], ids=["default-kernels", "first-implementation"])
+@pytest.fixture(params=[7, 3, 0], ids=["default-kernels", "launch-per-iteration", "first-implementation"])
 def backend(request, emu_backend, monkeypatch):
     from starst3r_b200 import reconstruct as rc
     monkeypatch.setattr(rc, "ALIGN_VARIANT", request.param)
