@@ -6,8 +6,13 @@ release current when Starst3r 0.4.0 was published).  gsplat is neither vendored 
 /root/reference nor installable here, and the reference holds no test or golden vector for
 it, so this file restates the published algorithm (gsplat's
 fully_fused_projection / spherical_harmonics / isect_tiles / isect_offset_encode /
-rasterize_to_pixels and its _torch_impl references) and is pinned only by closed-form
-known-answer tests (tests/test_gs_oracle.py).  Call sites anchored: starster/gs.py:76-87
+rasterize_to_pixels and its _torch_impl references) and is held only by (1) closed-form
+known-answer tests (tests/test_gs_math_host.py), (2) an independent float64 derivation from the
+definitions (oracle/gs_second.py, tests/test_gs_second_derivation.py: radii, tile counts and
+blend counts exactly, images to 3e-5, SSIM through torchmetrics' literal pad-filter-crop
+procedure, finite differences of this file's own autograd gradients) and (3) the hook for the
+real pin: tests/golden/raster_*.npz, which oracle/gen_golden_raster.py writes on a machine that
+has gsplat 1.4 + torchmetrics (absent here: the test that reads them is skipped with that reason).  Call sites anchored: starster/gs.py:76-87
 (rasterization), :126-136 (loss), :37,159-161 (Adam).
 
 Everything is fp32 PyTorch on CPU.  Index-producing arithmetic (projection -> radii ->

@@ -23,4 +23,8 @@ for v in dbg nold bn128 bn32 decouple; do
   nvcc $FLAGS $D -c starst3r_b200/csrc/nn_tc.cu -o $B/nn_tc_var_$v.o
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o starst3r_b200/libstarst3r_b200_$v.so $OBJS $B/nn_tc_var_$v.o -cudart static -lpthread -ldl -lrt
 done
+# libstarst3r_b200_aligntime.so: per-phase cycle counts of the persistent ALIGN kernel (printed by the kernel)
+OBJS2=$(ls $B/*.o | grep -v "/align.o" | grep -v _var_)
+nvcc $FLAGS -DALIGN_PERSIST_TIMING -c starst3r_b200/csrc/align.cu -o $B/align_var_time.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o starst3r_b200/libstarst3r_b200_aligntime.so $OBJS2 $B/align_var_time.o -cudart static -lpthread -ldl -lrt
 ls -la starst3r_b200/*.so

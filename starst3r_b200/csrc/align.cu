@@ -387,6 +387,51 @@ __device__ __forceinline__ void seg_flush(float* table, int img, float* acc) {
   if (lane < NG && mine != 0.f) atomicAdd(table + img * NG + lane, mine);
 }
 
+// One row of 32 entries into the register accumulators acc1 / acc2 of the image pair (cur1, cur2).  Entries are
+// emitted pair by pair, so a row almost always belongs to ONE image pair; a row that straddles two (or more) pairs is
+// walked once per pair, the other lanes redoing the pair's first entry with weight zero - the first version handed such a row to per-lane
+// shared-memory atomics (34 CAS loops per lane, 32-way contended: ~100 k cycles for ONE row, measured with the
+// per-phase counters of the persistent kernel, and every CTA of the grid waits for it at the barrier).
+template <int KIND>
+__device__ __forceinline__ float seg_row(const AlignCam* cams, float* table, SegEntry<KIND>& e, float gamma, float offset,
+                                         float off_pow, float sc, float* acc1, float* acc2, int& cur1, int& cur2) {
+  const int key = (e.i1 << 16) | e.i2;                       // n_img < 2^15 (the shared table caps it far lower)
+  unsigned todo = 0xffffffffu;
+  float loss = 0.f;
+  while (todo) {                                             // warp-uniform: one pass per distinct image pair of the row
+    const int leader = __ffs(todo) - 1;
+    const int k = __shfl_sync(0xffffffffu, key, leader);
+    const bool mine = key == k;
+    const unsigned grp = __ballot_sync(0xffffffffu, mine);
+    todo &= ~grp;
+    const int f1 = k >> 16, f2 = k & 0xffff;
+    if (f1 != cur1 || f2 != cur2) {
+      seg_flush(table, cur1, acc1);
+      seg_flush(table, cur2, acc2);
+      cur1 = f1; cur2 = f2;
+    }
+    SegEntry<KIND> g = e;
+    float wgt = sc;
+    if (grp != 0xffffffffu) {
+      // the lanes of another pair redo the leader's entry with weight zero: arithmetic that is known to be finite with
+      // this pair's cameras (their own entry, seen from the wrong camera, could divide by a zero depth: 0 x inf = NaN)
+      SegEntry<KIND> l;
+      l.a1.u = __shfl_sync(0xffffffffu, e.a1.u, leader); l.a1.v = __shfl_sync(0xffffffffu, e.a1.v, leader);
+      l.a1.core = __shfl_sync(0xffffffffu, e.a1.core, leader); l.a1.off = __shfl_sync(0xffffffffu, e.a1.off, leader);
+      l.a2.u = __shfl_sync(0xffffffffu, e.a2.u, leader); l.a2.v = __shfl_sync(0xffffffffu, e.a2.v, leader);
+      l.a2.core = __shfl_sync(0xffffffffu, e.a2.core, leader); l.a2.off = __shfl_sync(0xffffffffu, e.a2.off, leader);
+      l.x[0] = __shfl_sync(0xffffffffu, e.x[0], leader); l.x[1] = __shfl_sync(0xffffffffu, e.x[1], leader);
+      l.x[2] = __shfl_sync(0xffffffffu, e.x[2], leader);
+      l.conf = __shfl_sync(0xffffffffu, e.conf, leader);
+      l.a1.img = f1; l.a2.img = f2;
+      if (!mine) { g = l; wgt = 0.f; }
+    }
+    g.i1 = f1; g.i2 = f2;
+    loss += seg_eval<KIND>(cams, g, gamma, offset, off_pow, wgt, acc1, acc2);
+  }
+  return loss;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(LOSS_THREADS)
 align_loss_seg_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, float off_pow, float scale, int per_warp,
@@ -417,25 +462,7 @@ align_loss_seg_kernel(St3rAlignProblem pb, Work w, float gamma, float offset, fl
     const float sc = active ? scale : 0.f;
     SegEntry<KIND> e;
     seg_load<KIND>(pb, ic, m, e);
-    const int key = (e.i1 << 16) | e.i2;                        // n_img < 2^15 (the shared table caps it far lower)
-    const int first = __reduce_max_sync(0xffffffffu, key);      // the common key when the row is uniform
-    if (__all_sync(0xffffffffu, key == first)) {
-      const int f1 = first >> 16, f2 = first & 0xffff;
-      if (__any_sync(0xffffffffu, f1 != cur1 || f2 != cur2)) {   // warp-uniform; the vote tells the compiler
-        seg_flush(table, cur1, acc1);
-        seg_flush(table, cur2, acc2);
-        cur1 = f1; cur2 = f2;
-      }
-      loss += seg_eval<KIND>(w.cam, e, gamma, offset, off_pow, sc, acc1, acc2);
-    } else {
-      // a row that straddles two image pairs: per-row reduction like variant 0
-      float g1[NG], g2[NG];
-#pragma unroll
-      for (int k = 0; k < NG; ++k) g1[k] = g2[k] = 0.f;
-      loss += seg_eval<KIND>(w.cam, e, gamma, offset, off_pow, sc, g1, g2);
-      accum_image(table, e.i1, active, g1);
-      accum_image(table, e.i2, active, g2);
-    }
+    loss += seg_row<KIND>(w.cam, table, e, gamma, offset, off_pow, sc, acc1, acc2, cur1, cur2);
   }
   seg_flush(table, cur1, acc1);
   seg_flush(table, cur2, acc2);
@@ -645,28 +672,61 @@ __device__ __forceinline__ float persist_walk(const float4* __restrict__ pk, int
     const float sc = active ? scale : 0.f;     // lanes past the end redo the last entry with weight zero
     SegEntry<KIND> e;
     seg_unpack<KIND>(a, b, x, e);
-    const int key = (e.i1 << 16) | e.i2;
-    const int first = __reduce_max_sync(0xffffffffu, key);
-    if (__all_sync(0xffffffffu, key == first)) {
-      const int f1 = first >> 16, f2 = first & 0xffff;
-      if (__any_sync(0xffffffffu, f1 != cur1 || f2 != cur2)) {
-        seg_flush(table, cur1, acc1);
-        seg_flush(table, cur2, acc2);
-        cur1 = f1; cur2 = f2;
-      }
-      loss += seg_eval<KIND>(cams, e, gamma, offset, off_pow, sc, acc1, acc2);
-    } else {
-      float g1[NG], g2[NG];
-#pragma unroll
-      for (int k = 0; k < NG; ++k) g1[k] = g2[k] = 0.f;
-      loss += seg_eval<KIND>(cams, e, gamma, offset, off_pow, sc, g1, g2);
-      accum_image(table, e.i1, active, g1);
-      accum_image(table, e.i2, active, g2);
-    }
+    loss += seg_row<KIND>(cams, table, e, gamma, offset, off_pow, sc, acc1, acc2, cur1, cur2);
   }
   seg_flush(table, cur1, acc1);
   seg_flush(table, cur2, acc2);
   return loss;
+}
+
+// The MST chain of al_chain_fwd / al_chain_bwd with the 9 + 3 elements of an edge spread over the lanes of ONE warp
+// (same expressions element by element): an edge costs one shared-memory round trip instead of ~100 dependent ones in
+// a single thread - the chains were 7 k + 10 k of the persistent kernel's 170 k cycles per iteration at 8 images.
+__device__ __forceinline__ void chain_fwd_warp(int N, int root, const int* edges, AlignCamTmp* tmp, const float* trans) {
+  const int l = lane_id();
+  if (l < 9) tmp[root].TR[l] = tmp[root].relR[l];
+  else if (l < 12) tmp[root].Tt[l - 9] = trans[3 * root + l - 9];
+  __syncwarp();
+  for (int e = 0; e < N - 1; ++e) {
+    const int i = edges[2 * e], j = edges[2 * e + 1];
+    const float* A = tmp[i].TR;
+    if (l < 9) {
+      const int a = l / 3, b = l - 3 * a;
+      const float* B = tmp[j].relR;
+      tmp[j].TR[l] = A[3 * a] * B[b] + A[3 * a + 1] * B[3 + b] + A[3 * a + 2] * B[6 + b];
+    } else if (l < 12) {
+      const int k = l - 9;
+      const float* v = trans + 3 * j;
+      tmp[j].Tt[k] = (A[3 * k] * v[0] + A[3 * k + 1] * v[1] + A[3 * k + 2] * v[2]) + tmp[i].Tt[k];
+    }
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ void chain_bwd_warp(int N, const int* edges, const AlignCamTmp* tmp, const float* trans,
+                                               AlignCamGrad* grads) {
+  const int l = lane_id();
+  for (int e = N - 2; e >= 0; --e) {
+    const int i = edges[2 * e], j = edges[2 * e + 1];
+    const float* GTRj = grads[j].GTR;
+    const float* GTtj = grads[j].GTt;
+    float up = 0.f, down = 0.f;      // new value of the parent's / the child's element this lane owns
+    if (l < 9) {
+      const int a = l / 3, b = l - 3 * a;
+      float s = GTtj[a] * trans[3 * j + b];
+      for (int k = 0; k < 3; ++k) s += GTRj[3 * a + k] * tmp[j].relR[3 * b + k];
+      up = grads[i].GTR[l] + s;
+      down = tmp[i].TR[a] * GTRj[b] + tmp[i].TR[3 + a] * GTRj[3 + b] + tmp[i].TR[6 + a] * GTRj[6 + b];
+    } else if (l < 12) {
+      const int k = l - 9;
+      up = grads[i].GTt[k] + GTtj[k];
+      down = tmp[i].TR[k] * GTtj[0] + tmp[i].TR[3 + k] * GTtj[1] + tmp[i].TR[6 + k] * GTtj[2];
+    }
+    __syncwarp();                    // everybody has read the child's old gradients
+    if (l < 9) { grads[i].GTR[l] = up; grads[j].GTR[l] = down; }
+    else if (l < 12) { grads[i].GTt[l - 9] = up; grads[j].GTt[l - 9] = down; }
+    __syncwarp();
+  }
 }
 
 // The CTA's copy of the optimiser state.  (File scope rather than inside the kernel template: the CPU emulator of
@@ -676,7 +736,7 @@ __shared__ AlignCam s_cam[PERSIST_MAX_IMG];
 __shared__ AlignCamTmp s_tmp[PERSIST_MAX_IMG];
 __shared__ AlignCamGrad s_cg[PERSIST_MAX_IMG];
 __shared__ float s_par[11 * PERSIST_MAX_IMG], s_m[11 * PERSIST_MAX_IMG], s_v[11 * PERSIST_MAX_IMG];
-__shared__ float s_table[NG * PERSIST_MAX_IMG], s_gsum[NG * PERSIST_MAX_IMG];
+__shared__ float s_table[NG * PERSIST_MAX_IMG + 32], s_gsum[NG * PERSIST_MAX_IMG];   // (the table doubles as the reduction scratch)
 __shared__ int s_edges[2 * PERSIST_MAX_IMG];
 __shared__ float s_red[PERSIST_THREADS / 32][2];
 __shared__ float s_scal[8];                    // g, ties, smin, loss main, loss dust3r, stop flag, sum of g_g
@@ -711,6 +771,13 @@ align_persist_kernel(const PersistArgs a) {
   const int row_len = NG * N + 2;
   __syncthreads();
 
+#ifdef ALIGN_PERSIST_TIMING      // development aid (scripts/build_dbg.sh): cycles per phase seen by thread 0 of the first / last CTA
+  long long tc[6] = {0, 0, 0, 0, 0, 0};
+#define PT_MARK(k) do { if (tid == 0) { const long long now_ = clock64(); tc[k] += now_ - tlast; tlast = now_; } } while (0)
+  long long tlast = clock64();
+#else
+#define PT_MARK(k) do { } while (0)
+#endif
   for (int it = 0; it < a.niter; ++it) {
     if (s_scal[5] != 0.f) break;               // NaN loss seen (identical in every CTA): reconstruct.py:398-399
     // ---- camera forward (redundant in every CTA)
@@ -723,13 +790,14 @@ align_persist_kernel(const PersistArgs a) {
     if (lane == 0) s_red[warp][0] = best;
     for (int e = tid; e < NG * N; e += nthr) s_table[e] = 0.f;
     __syncthreads();
-    if (tid == 0) {
-      float b = INFINITY;
-      for (int k = 0; k < nwarps; ++k) b = fminf(b, s_red[k][0]);
+    if (warp == 0) {
+      float b = lane < nwarps ? s_red[lane][0] : INFINITY;
+      for (int off = 16; off; off >>= 1) b = fminf(b, __shfl_xor_sync(0xffffffffu, b, off));
       int ties = 0;                            // torch's min() backward splits the gradient between tied minima
-      for (int i = 0; i < N; ++i) ties += (s_tmp[i].s == b) ? 1 : 0;
-      s_scal[0] = 1.0f / b; s_scal[1] = (float)ties; s_scal[2] = b;
-      al_chain_fwd(N, pb.root, s_edges, s_tmp, s_tr);
+      for (int i = lane; i < N; i += 32) ties += (s_tmp[i].s == b) ? 1 : 0;
+      ties = __reduce_add_sync(0xffffffffu, ties);
+      if (lane == 0) { s_scal[0] = 1.0f / b; s_scal[1] = (float)ties; s_scal[2] = b; }
+      chain_fwd_warp(N, pb.root, s_edges, s_tmp, s_tr);
     }
     __syncthreads();
     const float g = s_scal[0];
@@ -738,6 +806,7 @@ align_persist_kernel(const PersistArgs a) {
     if (blockIdx.x == 0)                       // the records of the LAST forward are the result (reconstruct.py:379-380)
       for (int i = tid; i < N * (int)(sizeof(AlignCam) / 4); i += nthr)
         reinterpret_cast<float*>(a.w.cam)[i] = reinterpret_cast<const float*>(s_cam)[i];
+    PT_MARK(0);
     // ---- loss + gradient table of this CTA's slice
     float l_main = 0.f, l_d = 0.f;
     if (a.n_main > 0)
@@ -757,15 +826,42 @@ align_persist_kernel(const PersistArgs a) {
       for (int k = 0; k < nwarps; ++k) { s0 += s_red[k][0]; s1 += s_red[k][1]; }
       mine[NG * N] = s0; mine[NG * N + 1] = s1;
     }
+    PT_MARK(1);
     grid_barrier(a.bar, (unsigned)(it + 1) * gridDim.x);
+    PT_MARK(2);
     // ---- every CTA adds the rows in the same order: identical sums everywhere
+    // The row's values are cut into chunks of 32 (one per lane: coalesced 128-byte reads of L2) and the warps of a
+    // chunk share the CTAs' rows; eight loads are in flight per lane, the additions keep the row order.  (First
+    // version: one thread per value walking all rows - a chain of gridDim.x dependent L2 round trips, 22 k cycles per
+    // iteration; lanes across ROWS instead made every 4-byte read fetch its own 32-byte sector: 50 k.)
     const float* rows = a.partial + (size_t)(it & 1) * gridDim.x * row_len;
-    for (int e = tid; e < row_len; e += nthr) {
+    const int nchunks = (row_len + 31) / 32;
+    const int G = nwarps / nchunks > 0 ? nwarps / nchunks : 1;          // warps per chunk
+    float* part = s_table;                                              // [G][row_len] scratch (the table is published)
+    for (int w2 = warp; w2 < G * nchunks; w2 += nwarps) {
+      const int chunk = w2 % nchunks, g2 = w2 / nchunks, e = chunk * 32 + lane;
       float v = 0.f;
-      for (unsigned c = 0; c < gridDim.x; ++c) v += ld_l2(rows + (size_t)c * row_len + e);
+      if (e < row_len) {
+        unsigned c = g2;
+        for (; c + 7 * G < gridDim.x; c += 8 * G) {
+          float t[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = ld_l2(rows + (size_t)(c + j * G) * row_len + e);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v += t[j];
+        }
+        for (; c < gridDim.x; c += G) v += ld_l2(rows + (size_t)c * row_len + e);
+        part[g2 * row_len + e] = v;
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < row_len; e += nthr) {
+      float v = part[e];
+      for (int g2 = 1; g2 < G; ++g2) v += part[g2 * row_len + e];
       if (e < NG * N) s_gsum[e] = v; else s_scal[3 + (e - NG * N)] = v;
     }
     __syncthreads();
+    PT_MARK(3);
     // ---- camera backward + Adam (redundant in every CTA)
     float gg = 0.f;
     for (int i = tid; i < N; i += nthr) {
@@ -775,14 +871,16 @@ align_persist_kernel(const PersistArgs a) {
     for (int off = 16; off; off >>= 1) gg += __shfl_xor_sync(0xffffffffu, gg, off);
     if (lane == 0) s_red[warp][0] = gg;
     __syncthreads();
-    if (tid == 0) {
-      float t = 0.f;
-      for (int k = 0; k < nwarps; ++k) t += s_red[k][0];
-      s_scal[6] = t;
-      al_chain_bwd(N, pb.root, s_edges, s_tmp, s_tr, s_cg);
-      const float loss = s_scal[3] + s_scal[4];            // the dust3r weight is folded into scale_d
-      if (blockIdx.x == 0 && a.loss_hist) a.loss_hist[it] = loss;
-      if (loss != loss) s_scal[5] = 1.0f;                   // NaN: this iteration still steps, the next one stops
+    if (warp == 0) {
+      if (lane == 0) {
+        float t = 0.f;
+        for (int k = 0; k < nwarps; ++k) t += s_red[k][0];
+        s_scal[6] = t;
+        const float loss = s_scal[3] + s_scal[4];          // the dust3r weight is folded into scale_d
+        if (blockIdx.x == 0 && a.loss_hist) a.loss_hist[it] = loss;
+        if (loss != loss) s_scal[5] = 1.0f;                 // NaN: this iteration still steps, the next one stops
+      }
+      chain_bwd_warp(N, s_edges, s_tmp, s_tr, s_cg);
     }
     __syncthreads();
     const float gg_total = s_scal[6], ties = s_scal[1], smin = s_scal[2];
@@ -813,7 +911,13 @@ align_persist_kernel(const PersistArgs a) {
       q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
     }
     __syncthreads();
+    PT_MARK(4);
   }
+#ifdef ALIGN_PERSIST_TIMING
+  if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1 || blockIdx.x == gridDim.x / 2))
+    printf("align_persist cta %d niter %d cycles/iter: cam_fwd %lld walk+publish %lld barrier %lld reduce %lld bwd+adam %lld\n",
+           (int)blockIdx.x, a.niter, tc[0] / a.niter, tc[1] / a.niter, tc[2] / a.niter, tc[3] / a.niter, tc[4] / a.niter);
+#endif
   if (blockIdx.x == 0) {                                      // the state after the last step goes back to the caller
     for (int i = tid; i < 2 * N; i += nthr) a.p.pp[i] = s_pp[i];
     for (int i = tid; i < N; i += nthr) { a.p.log_focal[i] = s_lf[i]; a.p.log_size[i] = s_ls[i]; }

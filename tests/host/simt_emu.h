@@ -332,6 +332,14 @@ static inline int __reduce_max_sync(unsigned, int v) {
   });
 }
 
+static inline int __reduce_add_sync(unsigned, int v) {
+  return (int)(int64_t)emu::warp_collective((uint64_t)(int64_t)v, [](const uint64_t* s, int) {
+    int64_t r = 0;
+    for (int l = 0; l < 32; ++l) r += (int64_t)s[l];
+    return (uint64_t)r;
+  });
+}
+
 static inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
