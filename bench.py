@@ -661,16 +661,21 @@ def reconstruct_leg(dev, cpu_legs=True, dist=None):
     torch.cuda.synchronize()
     t_align = e0.elapsed_time(e1) * 1e-3
     # algorithmic bytes per optimiser iteration: per correspondence slot uv 8 + idx 4 + off 4 + conf 4 B
-    # on both sides, + the N (H/8)(W/8) core depths
+    # on both sides, + the N (H/8)(W/8) core depths.  (The one-launch loop streams its packed form: 48 B per entry of the
+    # phase's loss term - 545 k entries in the coarse phase, 1.09 M in the fine one - which stay L2-resident.)
     n_slots = int(corres[0].numel())
     it_bytes = 40 * n_slots + n * (H // 8) * (W // 8) * 4
+    one_launch = bool(int(rc.ALIGN_VARIANT) & 4)
     hbm_peak = peaks()[0]
     out["stages_s"] = {"match_28_pairs": t_match, "canonical_views_mst_condense": t_canon, "align_700_iterations": t_align}
     out["align"] = {"iterations_per_s": 700 / t_align, "us_per_iteration": t_align / 700 * 1e6, "correspondence_slots": n_slots,
                     "alg_bytes_per_iteration": it_bytes,
                     "roofline": {"bound": "hbm", "achieved": round(it_bytes / (t_align / 700) / 1e9, 2), "peak": hbm_peak,
                                  "unit": "GB/s", "frac": round(it_bytes / (t_align / 700) / 1e9 / hbm_peak, 5),
-                                 "note": "three launches per iteration over ~30 MB that stay in L2: latency bound, not HBM bound"}}
+                                 "note": ("the 500 + 200 iterations run as two cooperative launches (optimiser state in shared memory, one grid "
+                                          "barrier per iteration); ~26 MB of packed entries per iteration stay in L2: the loop is bound "
+                                          "by the per-entry arithmetic and the barrier latency, not by HBM") if one_launch else
+                                 "three launches per iteration over ~30 MB that stay in L2: latency bound, not HBM bound"}}
     out["match_pairs_per_s_in_pipeline"] = n_pairs / t_match
     # the matcher alone on this scene's descriptor maps: smooth fields (like real MASt3R descriptors) keep ~100 columns
     # per query row inside the TF32 error band; reconstruct's matcher switches to split precision on them by itself

@@ -27,9 +27,11 @@ EPS2D, NEAR, FAR, RADIUS_CLIP = 0.3, 0.01, 1e10, 0.0
 # kernels (the first implementation, kept as an independent cross-check; tests/test_gs_gpu.py compares the two).
 RASTER_VARIANT = int(os.environ.get("ST3R_RASTER_VARIANT", "0"))
 # run_3dgs_optim under a torch.distributed process group: shard the views over the ranks (splat replicated, gradients
-# summed over NVLink peer memory / NCCL).  Opt-in until it has run on a multi-GPU box (bench.py and
-# tests/test_dist_gpu.py drive the same train_step + PeerGradExchange combination by hand).
-SHARD_VIEWS = os.environ.get("ST3R_SHARD_VIEWS", "0") == "1"
+# summed over NVLink peer memory / NVSwitch multimem / NCCL).  Validated on 2 / 4 / 8 B200s (replicas bit-identical and
+# equal to the single-GPU run: tests/test_dist_gpu.py, bench.py --gpus N), so it is the default whenever a process group
+# of more than one rank exists; with the MCMC strategy on (enable_pruning=True: per-rank random draws would split the
+# replicas) the ranks train as plain replicas instead.  ST3R_SHARD_VIEWS=0 / 1 forces it off / on (1 + pruning raises).
+SHARD_VIEWS = {"0": False, "1": True}.get(os.environ.get("ST3R_SHARD_VIEWS", ""), "auto")
 
 
 class _Prof:
@@ -829,7 +831,7 @@ def run_3dgs_optim(scene, iters, enable_pruning=False, loss_ssim_fac=0.2, loss_o
     # over views), so all replicas take the same Adam step.  Exchange: peer memory over NVLink fused with Adam
     # (dist.PeerGradExchange), NCCL all-reduce if symmetric memory cannot be set up.
     shard, hook = None, None
-    if SHARD_VIEWS:
+    if SHARD_VIEWS is True or (SHARD_VIEWS == "auto" and not enable_pruning):
         from . import dist as _sd
         rank, world_size = _sd.world()
         if world_size > 1 and cams.shape[0] >= world_size:
