@@ -389,6 +389,10 @@ def run_ours(args):
             truth_dev[b].copy_(truth_host, non_blocking=True)
             ready[b].record(copy_stream)
 
+    for b in (0, 1):        # untimed: each of the two device buffers gets its captured iteration (gs.TRAIN_GRAPH) before the clock starts
+        truth_dev[b].copy_(truth_host, non_blocking=True)
+        step_fn(n_done, images=truth_dev[b])
+        n_done += 1
     barrier()
     for b in (0, 1):
         freed[b].record(main_stream)
@@ -531,6 +535,7 @@ def run_ours(args):
                        # opt-in kernel variants (all 0 / False = the default kernels)
                        "kernel_variants": _kernel_variants()},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "graph_replays": int(plan.graph_replays),
             "roofline": roofline, "cpu_baseline": cpu,
             "blends_per_sec": n_blend * world / (shares.get("st3r_gs_raster_fwd", float("nan")) * 1e-3),
             "blends_per_frame": n_blend, "intersections": n_isect, "visible": n_vis, "loss": float(loss.item()),
@@ -798,7 +803,7 @@ def _kernel_variants():
     from starst3r_b200 import gs, match
     from starst3r_b200 import reconstruct as rc
     return {"raster": int(gs.RASTER_VARIANT), "nn_split": match.NN_SPLIT, "nn_cooperative": match.NN_COOPERATIVE,
-            "align": int(rc.ALIGN_VARIANT)}
+            "align": int(rc.ALIGN_VARIANT), "train_step_cuda_graph": bool(gs.TRAIN_GRAPH)}
 
 
 def main():

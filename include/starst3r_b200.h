@@ -49,6 +49,8 @@ ST3R_API int st3r_abi_version(void);
 ST3R_API int st3r_device_sm_count(void);
 /* Number of CUDA kernels this library has launched in this process (all entry points). */
 ST3R_API uint64_t st3r_launch_count(void);
+/* Adds n to that counter: a replayed CUDA graph launches the kernels that were counted once, at capture. */
+ST3R_API void st3r_launch_count_add(uint64_t n);
 
 /* Diagnostic: cycle counters of the tcgen05 matcher's epilogue warp in CTA 0, h_out4 (HOST) = {tiles, cycles
  * waiting for an accumulator, cycles in the arg-max epilogue, cycles of the whole tile loop}; reset != 0 clears. */
@@ -225,6 +227,15 @@ ST3R_API int st3r_adam_step(int n_seg, float* const* h_params, const float* cons
                    float* const* h_exp_avg_sq, const int* h_rows, const int* h_cols, const int* h_ld_param,
                    const int* h_ld_grad, double lr, double beta1, double beta2, double eps, int step,
                    cudaStream_t stream);
+
+/* st3r_adam_step with the step number kept on the device: *steps_done (device int32) is the number of completed steps;
+ * the update uses step = *steps_done + 1 (bias corrections evaluated on the device in double precision, like the host
+ * form) and then increments the counter.  The call carries no per-step scalar, so a captured CUDA graph of the whole
+ * training iteration replays unchanged (gs.TrainPlan). */
+ST3R_API int st3r_adam_step_dev(int n_seg, float* const* h_params, const float* const* h_grads, float* const* h_exp_avg,
+                       float* const* h_exp_avg_sq, const int* h_rows, const int* h_cols, const int* h_ld_param,
+                       const int* h_ld_grad, double lr, double beta1, double beta2, double eps, int32_t* steps_done,
+                       cudaStream_t stream);
 
 /* Multi-GPU form of st3r_adam_step: gradient all-reduce fused with the Adam update over peer memory.  Every rank
  * keeps its per-Gaussian gradients in a symmetric buffer mapped by all ranks (NVLink P2P); h_peer_grad_bases[r] is

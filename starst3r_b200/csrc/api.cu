@@ -29,4 +29,5 @@ const char* st3r_last_error(void) { return g_err; }
 int st3r_abi_version(void) { return ST3R_ABI_VERSION; }
 int st3r_device_sm_count(void) { return st3r_num_sms(); }
 uint64_t st3r_launch_count(void) { return g_st3r_launches; }
+void st3r_launch_count_add(uint64_t n) { g_st3r_launches += n; }
 }

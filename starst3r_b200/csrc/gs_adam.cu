@@ -34,6 +34,40 @@ adam_kernel(AdamSegs segs, float lr_over_bc1, float inv_sqrt_bc2, float one_minu
     sg.v[ip] = v;
   }
 }
+// The same update with the step number kept ON THE DEVICE (steps_done = number of completed steps): the bias
+// corrections are evaluated by thread 0 of every block in double precision exactly as the host entry point does, so the
+// launch carries no per-step scalar and a captured CUDA graph of the whole training iteration can be replayed
+// unchanged (gs.TrainPlan's graph mode).  adam_advance_kernel increments the counter after the update.
+__global__ void __launch_bounds__(256)
+adam_dev_kernel(AdamSegs segs, const int* __restrict__ steps_done, double lr, double beta1, double beta2,
+                float one_minus_b1, float b2, float one_minus_b2, float eps) {
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const double step = (double)(*steps_done + 1);
+    const double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
+    s_bc[0] = (float)(lr / bc1);
+    s_bc[1] = (float)(1.0 / sqrt(bc2));
+  }
+  __syncthreads();
+  const float lr_over_bc1 = s_bc[0], inv_sqrt_bc2 = s_bc[1];
+  const AdamSeg sg = segs.s[blockIdx.y];
+  const long long total = (long long)sg.rows * sg.cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / sg.cols), c = (int)(i - (long long)r * sg.cols);
+    const size_t ip = (size_t)r * sg.ld_p + c, ig = (size_t)r * sg.ld_g + c;
+    const float g = sg.g[ig];
+    float m = sg.m[ip], v = sg.v[ip];
+    m = m + (g - m) * one_minus_b1;
+    v = v * b2 + one_minus_b2 * g * g;
+    const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
+    sg.p[ip] = sg.p[ip] - lr_over_bc1 * (m / denom);
+    sg.m[ip] = m;
+    sg.v[ip] = v;
+  }
+}
+__global__ void adam_advance_kernel(int* steps_done) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *steps_done += 1;
+}
 // Fused gradient all-reduce + Adam over peer memory (multi-GPU training, SURVEY.md §8e: views are sharded, the splat is
 // replicated, the only exchange is the sum of the per-Gaussian gradients).  Every rank's gradients live at the same
 // offsets of a symmetric buffer that all ranks map (NVLink P2P through NVSwitch); this kernel reads element i of every
@@ -208,6 +242,36 @@ extern "C" int st3r_adam_step_peers(int n_seg, float* const* params, const long 
   adam_peer_kernel<<<dim3(blocks, n_seg), 256, 0, stream>>>(segs, peers, goff, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)),
                                                            (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
                                                            (float)eps);
+  ST3R_CHECK_LAUNCH();
+  return ST3R_OK;
+}
+
+extern "C" int st3r_adam_step_dev(int n_seg, float* const* params, const float* const* grads, float* const* exp_avg,
+                                  float* const* exp_avg_sq, const int* rows, const int* cols, const int* ld_param,
+                                  const int* ld_grad, double lr, double beta1, double beta2, double eps,
+                                  int32_t* steps_done, cudaStream_t stream) {
+  ST3R_CHECK_ARG(n_seg >= 0 && n_seg <= 8 && steps_done, "st3r_adam_step_dev: bad args (n_seg <= 8, steps_done != NULL)");
+  if (n_seg == 0) return ST3R_OK;
+  ST3R_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && rows && cols && ld_param && ld_grad, "st3r_adam_step_dev: null");
+  AdamSegs segs;
+  segs.n = n_seg;
+  long long max_total = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    ST3R_CHECK_ARG(params[i] && grads[i] && exp_avg[i] && exp_avg_sq[i] && rows[i] >= 0 && cols[i] > 0,
+                   "st3r_adam_step_dev: bad segment %d", i);
+    segs.s[i] = AdamSeg{params[i], grads[i], exp_avg[i], exp_avg_sq[i], rows[i], cols[i], ld_param[i], ld_grad[i]};
+    long long t = (long long)rows[i] * cols[i];
+    if (t > max_total) max_total = t;
+  }
+  if (max_total > 0) {
+    int blocks = (int)((max_total + 255) / 256);
+    int cap = st3r_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    adam_dev_kernel<<<dim3(blocks, n_seg), 256, 0, stream>>>(segs, steps_done, lr, beta1, beta2, (float)(1.0 - beta1),
+                                                            (float)beta2, (float)(1.0 - beta2), (float)eps);
+    ST3R_CHECK_LAUNCH();
+  }
+  adam_advance_kernel<<<1, 32, 0, stream>>>(steps_done);
   ST3R_CHECK_LAUNCH();
   return ST3R_OK;
 }

@@ -34,6 +34,13 @@ RASTER_VARIANT = int(os.environ.get("ST3R_RASTER_VARIANT", "0"))
 SHARD_VIEWS = {"0": False, "1": True}.get(os.environ.get("ST3R_SHARD_VIEWS", ""), "auto")
 
 
+# Steady-state iterations of train_step (a sized TrainPlan, no strategy hook, one GPU) are captured once as a CUDA graph
+# and replayed: the ~25 host calls of an iteration (14 kernel launches through ctypes + the torch plumbing) cost more
+# host time than the 1.8 ms the kernels need, so the un-captured loop runs at the host's pace whenever the host hiccups.
+# ST3R_TRAIN_GRAPH=0 keeps every iteration eager (the cross-check: tests compare the two).
+TRAIN_GRAPH = os.environ.get("ST3R_TRAIN_GRAPH", "1") == "1"
+
+
 class _Prof:
     """Optional per-entry-point CUDA-event timing (bench.py's roofline leg): `gs.PROF = {}` turns it on; each C-ABI
     call then appends (start, end) events on the launching stream under its name."""
@@ -145,6 +152,14 @@ class TrainPlan:
         self._slot = 0
         self.last_n_isect = None
         self._sync_left = self.SYNC_FRAMES                              # frames that still read the count synchronously
+        # graph mode (train_step): captured iterations keyed by the tensors they touch, device-side Adam step counter
+        self.steps_done = torch.zeros(1, dtype=i32, device=device)
+        self._steps_done_host = None
+        self.loss_buf = torch.zeros((), dtype=f32, device=device)
+        self._graphs = {}
+        self._epoch = 0                                                 # bumped when the intersection buffers move
+        self._capturing = False
+        self.graph_replays = 0
 
     def sync_mode(self):
         return self._sync_left > 0
@@ -169,10 +184,14 @@ class TrainPlan:
         self.sort_ws = _ws(lib.st3r_radix_sort_ws_bytes(self.cap), self.dev)
         self.bin_ws = _ws(lib.st3r_gs_bin_ws_bytes(self.C, self.W, self.H, TILE, self.cap), self.dev)
         self.n_total = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._epoch += 1
+        self._graphs.clear()            # captured iterations point into the old buffers
 
     def poll(self, wait_all=False):
         """Checks the counts of earlier frames (waits for all but the newest, so the host stays at most one frame
         ahead of the device).  Raises on overflow; grows the capacity for the NEXT frame when it runs tight."""
+        if self._capturing:
+            return
         keep = 0 if wait_all else 1
         while len(self._pending) > keep:
             ev, slot, cap = self._pending.pop(0)
@@ -197,10 +216,52 @@ class TrainPlan:
         else:
             slot = self._slot = (self._slot + 1) % self._host.numel()
             self._host[slot:slot + 1].copy_(self.n_raw, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            self._pending.append((ev, slot, self.cap))
+            if not self._capturing:     # a captured iteration: graph_step records the event after every replay
+                ev = torch.cuda.Event()
+                ev.record()
+                self._pending.append((ev, slot, self.cap))
         torch.clamp(self.n_raw, max=self.cap, out=self.n_clamped)
+
+    def graph_step(self, params, states, truth, cams, width, height, step, hyper, loss_out):
+        """One steady-state iteration as a CUDA-graph replay (captured on first use for this set of tensors).  Returns
+        None when the iteration has to run eagerly (count under watch, buffers not sized yet)."""
+        self.poll()
+        if self.cap == 0 or self.sync_mode() or BINNING != "fused":
+            return None
+        names = ("means", "scales", "quats", "opacities", "shN")
+        key = (self._epoch, int(RASTER_VARIANT), truth.data_ptr(), cams.data_ptr(), tuple(params[k].data_ptr() for k in names),
+               tuple(t.data_ptr() for k in names for t in states[k]), tuple(params[k].shape for k in names), hyper)
+        ent = self._graphs.get(key)
+        lib = _lib.load()
+        if ent is None:
+            if len(self._graphs) >= 8:
+                self._graphs.clear()
+            lr, betas, eps, f_ssim, f_opac, f_scale = hyper
+            graph = torch.cuda.CUDAGraph()
+            n0 = lib.st3r_launch_count()
+            self._capturing = True
+            try:
+                with torch.cuda.graph(graph):
+                    _, fr = _train_step_eager(params, states, truth, cams, width, height, None, lr, betas, eps, f_ssim,
+                                              f_opac, f_scale, False, None, self, self.loss_buf)
+            finally:
+                self._capturing = False
+            ent = self._graphs[key] = (graph, fr, self._slot, int(lib.st3r_launch_count() - n0))
+        graph, fr, slot, launches = ent
+        if self._steps_done_host != step - 1:
+            self.steps_done.fill_(step - 1)
+        graph.replay()
+        self._steps_done_host = step
+        self.graph_replays += 1
+        lib.st3r_launch_count_add(launches)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending.append((ev, slot, self.cap))
+        fr._n_isect = None
+        if loss_out is not None:
+            loss_out.copy_(self.loss_buf)
+            return loss_out, fr
+        return self.loss_buf.clone(), fr
 
 
 def _forward(means, quats, scales, opacities, shN, cams, width, height, count_blends=False, plan=None):
@@ -426,8 +487,9 @@ class FusedAdam:
                             st["exp_avg_sq"].view(-1), 1, n, n, n)], g["lr"], g["betas"], g["eps"], int(st["step"].item()))
 
 
-def adam_step(segments, lr, betas, eps, step):
-    """segments: list of (param, grad, exp_avg, exp_avg_sq, rows, cols, ld_param, ld_grad) device tensors."""
+def adam_step(segments, lr, betas, eps, step, steps_done=None):
+    """segments: list of (param, grad, exp_avg, exp_avg_sq, rows, cols, ld_param, ld_grad) device tensors.
+    steps_done (device int32 tensor) instead of `step`: the step number lives on the device (st3r_adam_step_dev)."""
     lib = _lib.load()
     n = len(segments)
     PP = ctypes.c_void_p * n
@@ -440,9 +502,14 @@ def adam_step(segments, lr, betas, eps, step):
     ldp, ldg = II(*[int(s[6]) for s in segments]), II(*[int(s[7]) for s in segments])
     dev = segments[0][0].device
     with torch.cuda.device(dev), _Prof("st3r_adam_step"):
-        rc = lib.st3r_adam_step(n, p, g, m, v, rows, cols, ldp, ldg, ctypes.c_double(lr), ctypes.c_double(betas[0]),
-                                ctypes.c_double(betas[1]), ctypes.c_double(eps),
-                                int(step), _lib.stream_ptr())
+        if steps_done is not None:
+            rc = lib.st3r_adam_step_dev(n, p, g, m, v, rows, cols, ldp, ldg, ctypes.c_double(lr), ctypes.c_double(betas[0]),
+                                        ctypes.c_double(betas[1]), ctypes.c_double(eps), _lib.ptr(steps_done),
+                                        _lib.stream_ptr())
+        else:
+            rc = lib.st3r_adam_step(n, p, g, m, v, rows, cols, ldp, ldg, ctypes.c_double(lr), ctypes.c_double(betas[0]),
+                                    ctypes.c_double(betas[1]), ctypes.c_double(eps),
+                                    int(step), _lib.stream_ptr())
     _lib.check(rc, "st3r_adam_step")
 
 
@@ -722,7 +789,22 @@ def train_step(params, states, truth, cams, width, height, step, lr=1e-3, betas=
     """One fused iteration of gs.py:143-161 (without the strategy hooks): render all C views, loss, backward, Adam.
     params: dict of contiguous fp32 device tensors (means, scales, quats, opacities, shN), updated in place;
     states: dict name -> (exp_avg, exp_avg_sq).  With a TrainPlan the iteration allocates nothing and never
-    synchronises with the host.  Returns (loss tensor [] on device, frame)."""
+    synchronises with the host, and once the plan's buffers are sized it is one CUDA-graph replay (TRAIN_GRAPH).
+    Returns (loss tensor [] on device, frame)."""
+    if (TRAIN_GRAPH and plan is not None and plan.peer is None and grad_hook is None and not count_blends and PROF is None
+            and params["means"].is_cuda):
+        hyper = (float(lr), (float(betas[0]), float(betas[1])), float(eps), float(loss_ssim_fac), float(loss_opacity_fac),
+                 float(loss_scale_fac))
+        out = plan.graph_step(params, states, truth, cams, width, height, int(step), hyper, loss_out)
+        if out is not None:
+            return out
+    return _train_step_eager(params, states, truth, cams, width, height, step, lr, betas, eps, loss_ssim_fac,
+                             loss_opacity_fac, loss_scale_fac, count_blends, grad_hook, plan, loss_out)
+
+
+def _train_step_eager(params, states, truth, cams, width, height, step, lr, betas, eps, loss_ssim_fac, loss_opacity_fac,
+                      loss_scale_fac, count_blends, grad_hook, plan, loss_out):
+    """The iteration launch by launch.  step=None (graph capture): Adam reads the step from plan.steps_done."""
     lib = _lib.load()
     means, quats, scales, opac, shN = (params[k] for k in ("means", "quats", "scales", "opacities", "shN"))
     dev = means.device
@@ -773,7 +855,7 @@ def train_step(params, states, truth, cams, width, height, step, lr=1e-3, betas=
                             peer.peer_bases(), lr, betas, eps, step)
         peer.advance()
     else:
-        adam_step(segs, lr, betas, eps, step)
+        adam_step(segs, lr, betas, eps, step, steps_done=plan.steps_done if step is None else None)
     loss = loss_out if loss_out is not None else torch.empty((), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.st3r_gs_loss_finalize(_lib.ptr(sums), _lib.ptr(reg), C, H, W, _f(loss_ssim_fac), _f(reg_o), _f(reg_s),

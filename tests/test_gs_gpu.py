@@ -232,6 +232,26 @@ def test_fused_adam_vs_torch(cuda_device):
     assert torch.allclose(st["exp_avg_sq"].cpu(), opt_ref.state[ref]["exp_avg_sq"], rtol=1e-5, atol=1e-9)
 
 
+def test_adam_step_dev_equals_host_form(cuda_device):
+    """st3r_adam_step_dev (step number on the device, bias corrections evaluated there: the form a captured CUDA graph
+    replays) == st3r_adam_step, step by step, and the counter advances."""
+    from starst3r_b200 import gs
+    g = torch.Generator().manual_seed(3)
+    p0 = torch.randn(777, 5, generator=g)
+    pa, pb = p0.clone().to(cuda_device), p0.clone().to(cuda_device)
+    ma, va, mb, vb = (torch.zeros_like(pa) for _ in range(4))
+    done = torch.full((1,), 0, dtype=torch.int32, device=cuda_device)
+    for step in list(range(1, 7)) + [1000, 1001]:
+        if step == 1000:
+            done.fill_(999)
+        gr = (torch.randn(777, 5, generator=g) * (10.0 ** ((step % 5) - 2))).to(cuda_device)
+        gs.adam_step([(pa, gr, ma, va, 777, 5, 5, 5)], 1e-3, (0.9, 0.999), 1e-8, step)
+        gs.adam_step([(pb, gr, mb, vb, 777, 5, 5, 5)], 1e-3, (0.9, 0.999), 1e-8, None, steps_done=done)
+        assert int(done.item()) == step
+        assert torch.equal(ma, mb) and torch.equal(va, vb)
+        assert (pa - pb).abs().max().item() <= 1e-9, step
+
+
 # ------------------------------------------------------------------------------------------ full train step
 def test_train_steps_vs_oracle(cuda_device):
     """Three iterations of gs.py:143-161 (render 3 views, loss, backward, Adam): loss, gradients and updated
@@ -449,6 +469,42 @@ def test_train_plan_matches_unplanned(cuda_device):
     lb, fb = gs.train_step(pb, sb, truth, cams, W, H, 10, plan=plan)
     plan.poll(wait_all=True)
     assert fb.n_isect <= plan.cap and plan.last_n_isect == fb.n_isect
+
+
+def test_train_graph_replay_matches_eager(cuda_device, monkeypatch):
+    """Steady-state iterations replayed as a CUDA graph (TrainPlan.graph_step) against the same iterations launched one
+    by one: same losses and parameters up to the order of the fp32 gradient atomics; the graph survives a second set of
+    truth images (second capture), a step-number jump, and a re-sized plan."""
+    from starst3r_b200 import _lib, gs
+    lib = _lib.load()
+    sp, viewmats, Ks, W, H = small_scene(n=800, C=3, seed=8)
+    g = torch.Generator().manual_seed(1)
+    truths = [torch.rand(3, H, W, 3, generator=g).to(cuda_device) for _ in range(2)]
+    cams = gs.make_cams(viewmats.to(cuda_device), Ks.to(cuda_device))
+
+    def run(graph):
+        monkeypatch.setattr(gs, "TRAIN_GRAPH", graph)
+        p = {k: v.clone().to(cuda_device).contiguous() for k, v in sp.items()}
+        st = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in p.items()}
+        plan = gs.TrainPlan(800, 3, W, H, cuda_device)
+        losses, n0 = [], lib.st3r_launch_count()
+        steps = list(range(1, 21)) + [40, 41, 42]
+        for i, step in enumerate(steps):
+            loss, fr = gs.train_step(p, st, truths[i & 1], cams, W, H, step, plan=plan, lr=1e-4)
+            losses.append(loss)
+        plan.poll(wait_all=True)
+        assert fr.n_isect == plan.last_n_isect
+        return p, st, [x.item() for x in losses], plan, lib.st3r_launch_count() - n0
+    pe, se, le, plan_e, launches_e = run(False)
+    pg, sg, lg, plan_g, launches_g = run(True)
+    assert plan_e.graph_replays == 0 and plan_g.graph_replays == 23 - gs.TrainPlan.SYNC_FRAMES and len(plan_g._graphs) == 2
+    assert int(plan_g.steps_done.item()) == 42
+    assert launches_g >= launches_e                 # replays are counted (+ the counter kernel of the device-step Adam)
+    for a, b in zip(le, lg):
+        assert abs(a - b) <= 1e-5 * abs(a)
+    for k in pe:
+        assert torch.allclose(pe[k], pg[k], rtol=1e-4, atol=1e-5), k
+        assert torch.allclose(se[k][1], sg[k][1], rtol=1e-3, atol=1e-12), k
 
 
 def test_train_plan_watches_the_intersection_count(cuda_device):
