@@ -382,6 +382,82 @@ __device__ __noinline__ float resolve_full_lists(int slot, bool need, float run_
   return run_max;
 }
 
+// Arg-max arithmetic of NCH * 32 consecutive accumulator columns held in registers (columns col_base ...; `probe`: a
+// max-only probe tile).  Hot path: three-input max instructions and ONE test, straight-line; the cold paths append
+// near-maximum columns to the row's candidate list (see absorb_candidates / resolve_full_lists).
+template <bool kCoop, bool kSplit, int NCH>
+__device__ __forceinline__ void epi_cols(float* v, const bool probe, const int col_base, const int n_end, const int slot,
+                                         const float delta, float& run_max, int& cnt) {
+  float cm[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) cm[c] = chunk_max(v + c * 32);
+  float tmax = cm[0];
+#pragma unroll
+  for (int c = 1; c < NCH; ++c) tmax = fmaxf(tmax, cm[c]);
+  if (probe) {
+    run_max = fmaxf(run_max, tmax);          // probe tiles are always full tiles
+  } else {
+    const bool ragged = col_base + (NCH * 32) > n_end;
+    if (kCoop) {
+      if (__builtin_expect(__any_sync(0xffffffffu, ragged || tmax >= run_max - delta), 0)) {
+        // Cold path, taken by the whole warp together (see resolve_full_lists).
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          float* x = v + c * 32;
+          float cmax = cm[c];
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col_base + c * 32 + i >= n_end) x[i] = -INFINITY;
+            cmax = chunk_max(x);
+          }
+          uint32_t rem = 0;                    // flagged columns still to be listed
+          if (cmax >= run_max - delta) {
+            run_max = fmaxf(run_max, cmax);
+            const float thr = run_max - delta;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) rem |= (x[i] >= thr ? 1u : 0u) << i;
+            const unsigned long long r = absorb_no_resolve<kSplit>(slot, cnt, rem, col_base + c * 32, cmax, thr);
+            cnt = (int)(uint32_t)r;
+            rem = (uint32_t)(r >> 32);
+          }
+          while (__any_sync(0xffffffffu, rem != 0)) {      // some lane's list is full of live candidates
+            run_max = resolve_full_lists<kSplit>(slot, rem != 0, run_max);
+            if (rem) {
+              const unsigned long long r = absorb_no_resolve<kSplit>(slot, 0, rem, col_base + c * 32, cmax, run_max - delta);
+              cnt = (int)(uint32_t)r;
+              rem = (uint32_t)(r >> 32);
+            }
+          }
+        }
+      }
+    } else if (__builtin_expect(ragged || tmax >= run_max - delta, 0)) {
+      // Cold path (a few times per row, or the single ragged tile of the DB).
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        float* x = v + c * 32;
+        float cmax = cm[c];
+        if (ragged) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col_base + c * 32 + i >= n_end) x[i] = -INFINITY;
+          cmax = chunk_max(x);
+        }
+        if (cmax >= run_max - delta) {
+          run_max = fmaxf(run_max, cmax);
+          const float thr = run_max - delta;
+          uint32_t mask = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mask |= (x[i] >= thr ? 1u : 0u) << i;
+          const unsigned long long r = absorb_candidates<kSplit>(slot, cnt, mask, col_base + c * 32, cmax, run_max);
+          cnt = (int)(uint32_t)r;
+          run_max = __uint_as_float((uint32_t)(r >> 32));
+        }
+      }
+    }
+  }
+}
+
 // Statistics for the host's choice of variant: [0] query rows scanned, [1] exact list resolutions.
 __device__ unsigned long long g_nn_tc_stats[2];
 
@@ -649,76 +725,7 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
       if (v[t & (EPI_COLS - 1)] == 123.456f) run_max = v[5];
       continue;
 #endif
-      // Hot path: three-input max instructions and ONE test per tile, straight-line.
-      float cm[EPI_CHUNKS];
-#pragma unroll
-      for (int c = 0; c < EPI_CHUNKS; ++c) cm[c] = chunk_max(v + c * 32);
-      float tmax = cm[0];
-#pragma unroll
-      for (int c = 1; c < EPI_CHUNKS; ++c) tmax = fmaxf(tmax, cm[c]);
-      if (t < n_probe) {
-        run_max = fmaxf(run_max, tmax);          // probe tiles are always full tiles
-      } else {
-        const int col_base = n_begin + (t - n_probe) * BN;
-        const bool ragged = col_base + EPI_COLS > n_end;
-        if (kCoop) {
-          if (__builtin_expect(__any_sync(0xffffffffu, ragged || tmax >= run_max - delta), 0)) {
-            // Cold path, taken by the whole warp together (see resolve_full_lists).
-#pragma unroll
-            for (int c = 0; c < EPI_CHUNKS; ++c) {
-              float* x = v + c * 32;
-              float cmax = cm[c];
-              if (ragged) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (col_base + c * 32 + i >= n_end) x[i] = -INFINITY;
-                cmax = chunk_max(x);
-              }
-              uint32_t rem = 0;                    // flagged columns still to be listed
-              if (cmax >= run_max - delta) {
-                run_max = fmaxf(run_max, cmax);
-                const float thr = run_max - delta;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) rem |= (x[i] >= thr ? 1u : 0u) << i;
-                const unsigned long long r = absorb_no_resolve<kSplit>(slot, cnt, rem, col_base + c * 32, cmax, thr);
-                cnt = (int)(uint32_t)r;
-                rem = (uint32_t)(r >> 32);
-              }
-              while (__any_sync(0xffffffffu, rem != 0)) {      // some lane's list is full of live candidates
-                run_max = resolve_full_lists<kSplit>(slot, rem != 0, run_max);
-                if (rem) {
-                  const unsigned long long r = absorb_no_resolve<kSplit>(slot, 0, rem, col_base + c * 32, cmax, run_max - delta);
-                  cnt = (int)(uint32_t)r;
-                  rem = (uint32_t)(r >> 32);
-                }
-              }
-            }
-          }
-        } else if (__builtin_expect(ragged || tmax >= run_max - delta, 0)) {
-          // Cold path (a few times per row, or the single ragged tile of the DB).
-#pragma unroll
-          for (int c = 0; c < EPI_CHUNKS; ++c) {
-            float* x = v + c * 32;
-            float cmax = cm[c];
-            if (ragged) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col_base + c * 32 + i >= n_end) x[i] = -INFINITY;
-              cmax = chunk_max(x);
-            }
-            if (cmax >= run_max - delta) {
-              run_max = fmaxf(run_max, cmax);
-              const float thr = run_max - delta;
-              uint32_t mask = 0;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) mask |= (x[i] >= thr ? 1u : 0u) << i;
-              const unsigned long long r = absorb_candidates<kSplit>(slot, cnt, mask, col_base + c * 32, cmax, run_max);
-              cnt = (int)(uint32_t)r;
-              run_max = __uint_as_float((uint32_t)(r >> 32));
-            }
-          }
-        }
-      }
+      epi_cols<kCoop, kSplit, EPI_CHUNKS>(v, t < n_probe, n_begin + (t - n_probe) * BN, n_end, slot, delta, run_max, cnt);
 #ifdef NN_TC_DEBUG_CYCLES
       c_wait += (unsigned long long)(c1 - c0);
       c_epi += (unsigned long long)(clock64() - c1);

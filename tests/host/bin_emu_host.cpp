@@ -18,7 +18,7 @@ int emu_bin_tiles(const int32_t* radii, const float* geomA, int N, int C, int W,
   std::vector<int32_t> counts(n_cells, 0), cursor(n_cells, 0);
   std::vector<uint64_t> pairs(n_cap > 0 ? n_cap : 1, 0);
   const float4* gA = (const float4*)geomA;
-  const int gx = (N + ENTRIES_PER_CTA - 1) / ENTRIES_PER_CTA;
+  const int gx = (N + MIN_ENTRIES_PER_CTA - 1) / MIN_ENTRIES_PER_CTA;
   auto grid2 = [&](const std::function<void()>& body) {
     emu::g_blockDim = dim3(BIN_THREADS, 1, 1);
     emu::g_gridDim = dim3(gx, C, 1);
@@ -29,10 +29,10 @@ int emu_bin_tiles(const int32_t* radii, const float* geomA, int N, int C, int W,
       }
     return true;
   };
-  if (!grid2([&]() { tile_hist_kernel(radii, gA, N, tile_size, tile_w, tile_h, counts.data(), use_smem); })) return -1;
+  if (!grid2([&]() { tile_hist_kernel(radii, gA, N, tile_size, tile_w, tile_h, counts.data(), use_smem, MIN_ENTRIES_PER_CTA); })) return -1;
   int32_t total = 0;
   for (int i = 0; i < n_cells; ++i) { offsets[i] = total; total += counts[i]; }
-  if (!grid2([&]() { tile_emit_kernel(radii, gA, N, tile_size, tile_w, tile_h, offsets, cursor.data(), pairs.data(), n_cap, use_smem); }))
+  if (!grid2([&]() { tile_emit_kernel(radii, gA, N, tile_size, tile_w, tile_h, offsets, cursor.data(), pairs.data(), n_cap, use_smem, MIN_ENTRIES_PER_CTA); }))
     return -1;
   emu::g_blockDim = dim3(SORT_THREADS, 1, 1);
   emu::g_gridDim = dim3(n_cells, 1, 1);
