@@ -24,6 +24,7 @@
 #ifndef ST3R_HOST_EMU
 #define ST3R_DYN_SMEM_I32(name) extern __shared__ int32_t name[]
 #endif
+#include "bitonic_reg.cuh"
 
 namespace {
 
@@ -188,129 +189,15 @@ __device__ __forceinline__ void bitonic_flip_sort(uint64_t* buf, int n, int nthr
   }
 }
 
-// ---- register-resident sort for segments up to 2048 pairs ------------------------------------------------------
-// (Round-2 profile of the shared-memory network above on the headline frame, 458 pairs per tile on average: 12.8 k
-// warp instructions per tile, 70 % of them index arithmetic, predicates and branches of the generic loops, the
-// memory accesses generic LD / ST because `buf` may point to either space.)  Here a thread holds EPT = P / 256
-// consecutive elements of the padded segment in registers and the same comparator network is unrolled at compile
-// time: comparators that stay inside a thread are register compare-exchanges, those inside a warp exchange through
-// __shfl_xor (the mirror step sends element EPT-1-e), and only the spans of 32 * EPT elements and more go through
-// shared memory (two alternating buffers, one barrier per step).  Same comparators, same +inf padding => the same
-// unique order (the 64-bit words are distinct).
-// (FP64 min / max would order these words too - a positive finite fp32 depth in the high half makes the word a positive
-// finite double - but sm_100a has no DMNMX: fmin(double) expands to DSETP + selects, slower than the integer compare.)
-constexpr uint64_t SORT_PAD = ~0ull;                      // +inf padding: above every word, never moves
-__device__ __forceinline__ uint64_t kmin(uint64_t a, uint64_t b) { return a < b ? a : b; }
-__device__ __forceinline__ uint64_t kmax(uint64_t a, uint64_t b) { return a < b ? b : a; }
-__device__ __forceinline__ void cmpswap(uint64_t& a, uint64_t& b) {
-  const uint64_t lo = kmin(a, b), hi = kmax(a, b);
-  a = lo; b = hi;
-}
-
-// Warps whose elements are all padding (index >= n_act, the segment length rounded up to a warp's 32 * EPT elements)
-// sit the network out: padding never moves (every comparator puts the minimum at the lower index and the padding
-// holds the highest indices), so a comparator with such an element is a no-op for both sides.  They only keep the
-// block barriers of the shared-memory steps company.  The work then scales with ceil(n / (32 EPT)) warps, not with P.
-template <int EPT>
-__device__ __forceinline__ void reg_exchange_smem(uint64_t (&v)[EPT], uint64_t* sx, int& buf, int xor_mask, int low_bit,
-                                                  bool active, int n_act) {
-  constexpr int P = SORT_THREADS * EPT;
-  uint64_t* b = sx + buf * P;
-  const int i0 = threadIdx.x * EPT;
-  if (active) {
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) b[i0 + e] = v[e];
-  }
-  __syncthreads();
-  if (active) {
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-      const int i = i0 + e, partner = i ^ xor_mask;
-      if (partner < n_act) {
-        const uint64_t o = b[partner];
-        v[e] = (i & low_bit) == 0 ? kmin(v[e], o) : kmax(v[e], o);
-      }
-    }
-  }
-  buf ^= 1;      // the next exchange writes the other buffer: no second barrier needed
-}
-
-// The network is unrolled through template recursion (K = block size of the stage, J = comparator span), so that every
-// register index and every step kind is a compile-time constant.
-template <int EPT, int J>
-struct HalfSteps {       // element i against i + J, then J / 2, ... 1
-  static __device__ __forceinline__ void run(uint64_t (&v)[EPT], uint64_t* sx, int& buf, int lane, bool active, int n_act) {
-    if constexpr (J >= 1) {
-      if constexpr (J < EPT) {
-        if (active) {
-#pragma unroll
-          for (int e = 0; e < EPT; ++e)
-            if ((e & J) == 0) cmpswap(v[e], v[e | J]);
-        }
-      } else if constexpr (J < 32 * EPT) {
-        if (active) {
-          constexpr int m = J / EPT;
-          const bool keep_min = (lane & m) == 0;
-#pragma unroll
-          for (int e = 0; e < EPT; ++e) {
-            const uint64_t o = (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)v[e], m);
-            v[e] = keep_min ? kmin(v[e], o) : kmax(v[e], o);
-          }
-        }
-      } else {
-        reg_exchange_smem<EPT>(v, sx, buf, J, J, active, n_act);
-      }
-      HalfSteps<EPT, J / 2>::run(v, sx, buf, lane, active, n_act);
-    }
-  }
-};
-
-template <int EPT, int K>
-struct Stages {          // stages K, 2K, ... P
-  static __device__ __forceinline__ void run(uint64_t (&v)[EPT], uint64_t* sx, int& buf, int lane, bool active, int n_act) {
-    if constexpr (K <= SORT_THREADS * EPT) {
-      // first step of the stage: element i against i ^ (K - 1) (mirror inside every block of K)
-      if constexpr (K <= EPT) {
-        if (active) {
-#pragma unroll
-          for (int e = 0; e < EPT; ++e)
-            if ((e & (K >> 1)) == 0) cmpswap(v[e], v[e ^ (K - 1)]);
-        }
-      } else if constexpr (K <= 32 * EPT) {
-        if (active) {
-          constexpr int m = K / EPT - 1;                   // lane mask of the partner thread
-          const bool keep_min = (lane & ((m + 1) >> 1)) == 0;
-          uint64_t o[EPT];
-#pragma unroll
-          for (int e = 0; e < EPT; ++e) o[e] = (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)v[EPT - 1 - e], m);
-#pragma unroll
-          for (int e = 0; e < EPT; ++e) v[e] = keep_min ? kmin(v[e], o[e]) : kmax(v[e], o[e]);
-        }
-      } else {
-        reg_exchange_smem<EPT>(v, sx, buf, K - 1, K >> 1, active, n_act);
-      }
-      HalfSteps<EPT, K / 4>::run(v, sx, buf, lane, active, n_act);
-      Stages<EPT, K * 2>::run(v, sx, buf, lane, active, n_act);
-    }
-  }
-};
-
-template <int EPT>
-__device__ __forceinline__ void reg_bitonic_sort(uint64_t (&v)[EPT], uint64_t* sx, int n) {
-  int buf = 0;
-  const int n_act = (n + 32 * EPT - 1) / (32 * EPT) * (32 * EPT);
-  const bool active = (int)threadIdx.x * EPT < n_act;              // warp-uniform
-  Stages<EPT, 2>::run(v, sx, buf, lane_id(), active, n_act);
-}
-
+// ---- register-resident sort for segments up to 2048 pairs: bitonic_reg.cuh (256 threads, two exchange buffers) -------
 template <int EPT>
 __device__ __forceinline__ bool reg_sort_segment(const uint64_t* __restrict__ seg, int n, uint64_t* sx, uint64_t key_hi,
                                                  uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   uint64_t v[EPT];
   const int i0 = threadIdx.x * EPT;
 #pragma unroll
-  for (int e = 0; e < EPT; ++e) v[e] = i0 + e < n ? seg[i0 + e] : SORT_PAD;    // padding sorts to the end
-  reg_bitonic_sort<EPT>(v, sx, n);
+  for (int e = 0; e < EPT; ++e) v[e] = i0 + e < n ? seg[i0 + e] : st3r_sort::SORT_PAD;    // padding sorts to the end
+  st3r_sort::reg_bitonic_sort<SORT_THREADS, EPT, 2>(v, sx, n);
 #pragma unroll
   for (int e = 0; e < EPT; ++e)
     if (i0 + e < n) {

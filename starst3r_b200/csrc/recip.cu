@@ -11,6 +11,10 @@
 #include "nn.cuh"
 #include "radix_sort.cuh"
 #include "recip.cuh"
+#include "bitonic_reg.cuh"
+#ifndef ST3R_HOST_EMU
+#define ST3R_DYN_SMEM_U64(name) extern __shared__ __align__(16) uint64_t name[]
+#endif
 
 namespace {
 
@@ -187,6 +191,90 @@ unique_sorted(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ va
   if (threadIdx.x == 0) *out.n_out = carry_s;
 }
 
+// One-CTA sort + unique for lists of up to 16384 keys - every 512 x 512 pair: 2 (n1 + n2) = 16384 candidates.  The
+// generic chain (two LSD radix sorts = 19 launches of a handful of CTAs + the single-CTA compaction) cost ~250 us of a
+// 2.45 ms pair; here the keys are sorted in registers (bitonic_reg.cuh: 1024 threads x EPT words, shuffles inside a warp,
+// one shared-memory buffer for the longer spans) and compacted by the same CTA.  The sorted word is the key itself, or -
+// when the caller wants the position of the first occurrence (merge_corres) - the key fields squeezed together with the
+// element's position in the low bits, which reproduces the order of the stable radix sort exactly.
+//   word = a << sh_a | b << sh_b | set << bv | position,  sh_b = 1 + bv,  (bv = 0, sh_a = 33: the raw key)
+constexpr int SMALL_SORT_THREADS = 1024;
+constexpr int SMALL_SORT_MAX = 16 * SMALL_SORT_THREADS;
+
+template <int EPT>
+__global__ void __launch_bounds__(SMALL_SORT_THREADS)
+small_sort_unique(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const int32_t* __restrict__ nkeys,
+                  int cap, int sh_a, int bv, UniqueOut out) {
+  ST3R_DYN_SMEM_U64(sx);                       // [SMALL_SORT_THREADS * EPT] exchange buffer
+  __shared__ int warp_sums[32];
+  __shared__ uint64_t warp_last[32];
+  const int n = min(*nkeys, cap);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sh_b = 1 + bv;
+  const uint64_t b_mask = (1ull << (sh_a - sh_b)) - 1ull;
+  uint64_t v[EPT];
+  const int i0 = threadIdx.x * EPT;
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    uint64_t w = st3r_sort::SORT_PAD;
+    if (i0 + e < n) {
+      const uint64_t k = keys[i0 + e];
+      w = bv ? ((k >> 33) << sh_a) | (((k >> 1) & 0xffffffffull) << sh_b) | ((k & 1ull) << bv) | (uint64_t)vals[i0 + e] : k;
+    }
+    v[e] = w;
+  }
+  st3r_sort::reg_bitonic_sort<SMALL_SORT_THREADS, EPT, 1>(v, sx, n);
+  // first element of every run of equal (a, b): ordered compaction
+  uint64_t prev = (uint64_t)__shfl_up_sync(0xffffffffu, (unsigned long long)v[EPT - 1], 1);
+  if (lane == 31) warp_last[warp] = v[EPT - 1];
+  __syncthreads();
+  if (lane == 0 && warp > 0) prev = warp_last[warp - 1];
+  int flags = 0, cnt = 0;
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const uint64_t p = e == 0 ? prev : v[e - 1];
+    const bool f = i0 + e < n && (i0 + e == 0 || (p >> sh_b) != (v[e] >> sh_b));
+    flags |= (f ? 1 : 0) << e;
+    cnt += f ? 1 : 0;
+  }
+  int x = cnt;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, off);
+    if (lane >= off) x += y;
+  }
+  if (lane == 31) warp_sums[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = warp_sums[lane];
+    int xs = w;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, xs, off);
+      if (lane >= off) xs += y;
+    }
+    warp_sums[lane] = xs - w;
+    if (lane == 31) *out.n_out = xs;
+  }
+  __syncthreads();
+  int pos = warp_sums[warp] + x - cnt;
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    if (!((flags >> e) & 1)) continue;
+    const uint64_t k = v[e];
+    const uint32_t a = (uint32_t)(k >> sh_a), b = (uint32_t)((k >> sh_b) & b_mask);
+    const int set = (int)((k >> bv) & 1ull);
+    if (out.idx1) { out.idx1[pos] = (int32_t)a; out.idx2[pos] = (int32_t)b; }
+    if (out.index) out.index[pos] = (int32_t)(k & ((1ull << bv) - 1ull));
+    if (out.xy1) {
+      out.xy1[2 * pos] = a % out.W1; out.xy1[2 * pos + 1] = a / out.W1;
+      out.xy2[2 * pos] = b % out.W2; out.xy2[2 * pos + 1] = b / out.W2;
+    }
+    if (out.conf) out.conf[pos] = sqrtf(out.q1[set][a] * out.q2[set][b]);
+    ++pos;
+  }
+}
+
 __global__ void nn_decode(const unsigned long long* __restrict__ packed, int M, int32_t* idx, float* best) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
@@ -315,10 +403,40 @@ int run_recip_batch(const RecipWs& w, const RecipProblem* pr, int n, int d, int 
   return ST3R_OK;
 }
 
+// 1 (default): lists of up to 16384 keys are sorted and compacted by one CTA (small_sort_unique); 0: always the radix
+// chain (the first implementation, kept as the cross-check: st3r_recip_set_variant, tests/test_match_gpu.py runs both).
+int g_small_sort = 1;
+
 int sort_and_unique(const RecipWs& w, int key_cap, int HW1, int HW2, bool with_vals, const UniqueOut& out,
                     cudaStream_t stream) {
   // keys: idx1<<33 | idx2<<1 | set.  LSD: low field [0, 1+bits2) then high field [33, 33+bits1).
   int b2 = bits_for(HW2) + 1, b1 = bits_for(HW1);
+  const int bv = with_vals ? bits_for(key_cap) : 0;
+  if (g_small_sort && key_cap <= SMALL_SORT_MAX && b1 + b2 + bv < 64) {
+    // (with positions the fields are squeezed together: a above b above set above the position)
+    const int sh_a = with_vals ? b2 + bv : 33;
+    static PerDeviceOnce attr_set;
+    if (!attr_set.done()) {
+      ST3R_CHECK_CUDA(cudaFuncSetAttribute(small_sort_unique<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(sizeof(uint64_t) * SMALL_SORT_MAX)));
+      ST3R_CHECK_CUDA(cudaFuncSetAttribute(small_sort_unique<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(sizeof(uint64_t) * SMALL_SORT_MAX / 2)));
+      attr_set.mark();
+    }
+    const uint32_t* vv = with_vals ? w.vals : nullptr;
+    if (key_cap <= SMALL_SORT_THREADS)
+      small_sort_unique<1><<<1, SMALL_SORT_THREADS, sizeof(uint64_t) * SMALL_SORT_THREADS, stream>>>(w.keys, vv, w.nkeys, key_cap, sh_a, bv, out);
+    else if (key_cap <= 2 * SMALL_SORT_THREADS)
+      small_sort_unique<2><<<1, SMALL_SORT_THREADS, sizeof(uint64_t) * SMALL_SORT_THREADS * 2, stream>>>(w.keys, vv, w.nkeys, key_cap, sh_a, bv, out);
+    else if (key_cap <= 4 * SMALL_SORT_THREADS)
+      small_sort_unique<4><<<1, SMALL_SORT_THREADS, sizeof(uint64_t) * SMALL_SORT_THREADS * 4, stream>>>(w.keys, vv, w.nkeys, key_cap, sh_a, bv, out);
+    else if (key_cap <= 8 * SMALL_SORT_THREADS)
+      small_sort_unique<8><<<1, SMALL_SORT_THREADS, sizeof(uint64_t) * SMALL_SORT_THREADS * 8, stream>>>(w.keys, vv, w.nkeys, key_cap, sh_a, bv, out);
+    else
+      small_sort_unique<16><<<1, SMALL_SORT_THREADS, sizeof(uint64_t) * SMALL_SORT_THREADS * 16, stream>>>(w.keys, vv, w.nkeys, key_cap, sh_a, bv, out);
+    ST3R_CHECK_LAUNCH();
+    return ST3R_OK;
+  }
   uint32_t* v = with_vals ? w.vals : nullptr;
   uint32_t* va = with_vals ? w.vals_alt : nullptr;
   int rc = radix_sort_pairs(w.keys, v, w.keys_alt, va, w.nkeys, key_cap, 0, b2, w.sort_ws,
@@ -414,6 +532,12 @@ int st3r_recip_nn(const float* P1, int H1, int W1, const float* P2, int H2, int 
   UniqueOut out = {};
   out.idx1 = out_idx1; out.idx2 = out_idx2; out.n_out = n_out; out.W1 = W1; out.W2 = W2;
   return sort_and_unique(w, nseed, H1 * W1, H2 * W2, false, out, stream);
+}
+
+int st3r_recip_set_variant(int variant) {
+  ST3R_CHECK_ARG(variant == 0 || variant == 1, "st3r_recip_set_variant: unknown variant %d", variant);
+  g_small_sort = variant;
+  return ST3R_OK;
 }
 
 size_t st3r_merge_corres_ws_bytes(int n) { return carve(nullptr, nullptr, 0, 1, max(n, 1), 1, true); }

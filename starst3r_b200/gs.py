@@ -37,6 +37,9 @@ SHARD_VIEWS = {"0": False, "1": True}.get(os.environ.get("ST3R_SHARD_VIEWS", "")
 # Steady-state iterations of train_step (a sized TrainPlan, no strategy hook, one GPU) are captured once as a CUDA graph
 # and replayed: the ~25 host calls of an iteration (14 kernel launches through ctypes + the torch plumbing) cost more
 # host time than the 1.8 ms the kernels need, so the un-captured loop runs at the host's pace whenever the host hiccups.
+# Sharded views on 4 and more GPUs are captured too (two graphs, one per parity of the alternating gradient buffers: the
+# cross-device barriers, the in-switch / peer-memory reduce-scatter and Adam are all stream-ordered kernels); the fused
+# P2P gradient sum + Adam of 2-GPU runs takes the step number as a launch argument and stays eager.
 # ST3R_TRAIN_GRAPH=0 keeps every iteration eager (the cross-check: tests compare the two).
 TRAIN_GRAPH = os.environ.get("ST3R_TRAIN_GRAPH", "1") == "1"
 
@@ -230,7 +233,8 @@ class TrainPlan:
             return None
         names = ("means", "scales", "quats", "opacities", "shN")
         key = (self._epoch, int(RASTER_VARIANT), truth.data_ptr(), cams.data_ptr(), tuple(params[k].data_ptr() for k in names),
-               tuple(t.data_ptr() for k in names for t in states[k]), tuple(params[k].shape for k in names), hyper)
+               tuple(t.data_ptr() for k in names for t in states[k]), tuple(params[k].shape for k in names), hyper,
+               (id(self.peer), self.peer.step & 1) if self.peer is not None else None)   # gradient buffers alternate
         ent = self._graphs.get(key)
         lib = _lib.load()
         if ent is None:
@@ -241,7 +245,8 @@ class TrainPlan:
             n0 = lib.st3r_launch_count()
             self._capturing = True
             try:
-                with torch.cuda.graph(graph):
+                # (thread-local capture mode: NCCL's watchdog thread may query its events meanwhile)
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     _, fr = _train_step_eager(params, states, truth, cams, width, height, None, lr, betas, eps, f_ssim,
                                               f_opac, f_scale, False, None, self, self.loss_buf)
             finally:
@@ -253,6 +258,8 @@ class TrainPlan:
         graph.replay()
         self._steps_done_host = step
         self.graph_replays += 1
+        if self.peer is not None:
+            self.peer.advance()
         lib.st3r_launch_count_add(launches)
         ev = torch.cuda.Event()
         ev.record()
@@ -791,8 +798,8 @@ def train_step(params, states, truth, cams, width, height, step, lr=1e-3, betas=
     states: dict name -> (exp_avg, exp_avg_sq).  With a TrainPlan the iteration allocates nothing and never
     synchronises with the host, and once the plan's buffers are sized it is one CUDA-graph replay (TRAIN_GRAPH).
     Returns (loss tensor [] on device, frame)."""
-    if (TRAIN_GRAPH and plan is not None and plan.peer is None and grad_hook is None and not count_blends and PROF is None
-            and params["means"].is_cuda):
+    if (TRAIN_GRAPH and plan is not None and (plan.peer is None or plan.peer.scatter) and grad_hook is None
+            and not count_blends and PROF is None and params["means"].is_cuda):
         hyper = (float(lr), (float(betas[0]), float(betas[1])), float(eps), float(loss_ssim_fac), float(loss_opacity_fac),
                  float(loss_scale_fac))
         out = plan.graph_step(params, states, truth, cams, width, height, int(step), hyper, loss_out)
@@ -849,11 +856,12 @@ def _train_step_eager(params, states, truth, cams, width, height, step, lr, beta
             segs = [(means, rd["means"], *states["means"], N, 3, 3, 3), (scales, rd["scales"], *states["scales"], N, 3, 3, 3),
                     (quats, rd["quats"], *states["quats"], N, 4, 4, 4), (opac, rd["opacities"], *states["opacities"], N, 1, 1, 1),
                     (shN, rd["sh"], *states["shN"], N, 12, shN.shape[1] * 3, 12)]
-            adam_step(segs, lr, betas, eps, step)
+            adam_step(segs, lr, betas, eps, step, steps_done=plan.steps_done if step is None else None)
         else:
             adam_step_peers(segs, [peer.offsets[k] for k in ("means", "scales", "quats", "opacities", "sh")],
                             peer.peer_bases(), lr, betas, eps, step)
-        peer.advance()
+        if not plan._capturing:        # (a captured iteration: graph_step advances the parity after every replay)
+            peer.advance()
     else:
         adam_step(segs, lr, betas, eps, step, steps_done=plan.steps_done if step is None else None)
     loss = loss_out if loss_out is not None else torch.empty((), dtype=torch.float32, device=dev)

@@ -25,6 +25,7 @@ alignas(1024) static char emu_dyn_smem[256 * 1024];
 #define ST3R_DYN_SMEM_F32(name) float* name = reinterpret_cast<float*>(emu_dyn_smem)
 #define ST3R_DYN_SMEM(name) float* name = reinterpret_cast<float*>(emu_dyn_smem)
 #define ST3R_DYN_SMEM_I32(name) int32_t* name = reinterpret_cast<int32_t*>(emu_dyn_smem)
+#define ST3R_DYN_SMEM_U64(name) uint64_t* name = reinterpret_cast<uint64_t*>(emu_dyn_smem)
 #define __constant__ static
 #define cudaMemcpyToSymbol(sym, src, n) (memcpy((void*)&(sym), (src), (n)), cudaSuccess)
 #define cudaMemcpyFromSymbol(dst, sym, n) (memcpy((dst), (const void*)&(sym), (n)), cudaSuccess)

@@ -313,6 +313,8 @@ static inline int __shfl_xor_sync(unsigned, int v, int m) { return (int)(uint32_
 static inline float __shfl_down_sync(unsigned, float v, int d) { return emu_float(emu_shfl_lane(emu_bits(v), 1, d)); }
 static inline unsigned __shfl_down_sync(unsigned, unsigned v, int d) { return (unsigned)emu_shfl_lane(v, 1, d); }
 static inline unsigned __shfl_up_sync(unsigned, unsigned v, int d) { return (unsigned)emu_shfl_lane(v, 2, d); }
+static inline unsigned long long __shfl_up_sync(unsigned, unsigned long long v, int d) { return emu_shfl_lane(v, 2, d); }
+static inline int __shfl_up_sync(unsigned, int v, int d) { return (int)(uint32_t)emu_shfl_lane((uint32_t)v, 2, d); }
 
 static inline unsigned __match_any_sync(unsigned, int v) {
   return (unsigned)emu::warp_collective((uint64_t)(uint32_t)v, [](const uint64_t* s, int lane) {

@@ -69,9 +69,26 @@ def _worker(rank, world, port, out_dir):
     plan_e.peer.multimem = nvls
     for i in range(steps):
         gs.train_step(pe, se, tr, cams, W, H, i + 1, plan=plan_e)
+    # F / G: the reduce-scatter form past the plan's synchronous frames, replayed as a CUDA graph (two captured
+    # iterations, one per parity of the alternating gradient buffers) and launched one by one
+    long_steps = gs.TrainPlan.SYNC_FRAMES + 7
+    graph_runs = {}
+    for tag, graph in (("f", True), ("g", False)):
+        gs.TRAIN_GRAPH = graph
+        pf, sf = fresh()
+        plan_f = gs.TrainPlan(N, len(mine), W, H, dev)
+        plan_f.peer = sd.PeerGradExchange(N, dev)
+        plan_f.peer.scatter = True
+        plan_f.peer.multimem = nvls
+        for i in range(long_steps):
+            gs.train_step(pf, sf, tr, cams, W, H, i + 1, plan=plan_f, lr=1e-4)
+        plan_f.poll(wait_all=True)
+        graph_runs[tag] = {k: v.cpu() for k, v in pf.items()}
+        graph_runs[tag + "_replays"] = plan_f.graph_replays
+    gs.TRAIN_GRAPH = True
     torch.cuda.synchronize()
     res = {"a": {k: v.cpu() for k, v in pa.items()}, "b": {k: v.cpu() for k, v in pb.items()},
-           "d": {k: v.cpu() for k, v in pd.items()}, "e": {k: v.cpu() for k, v in pe.items()}, "nvls": nvls}
+           "d": {k: v.cpu() for k, v in pd.items()}, "e": {k: v.cpu() for k, v in pe.items()}, "nvls": nvls, **graph_runs}
     if rank == 0:   # single-GPU training over ALL views: the oracle of the sharded path
         pc, sc = fresh()
         for i in range(steps):
@@ -106,3 +123,6 @@ def test_peer_exchange_matches_allreduce_and_single_gpu(tmp_path):
         assert same_training(r[0]["d"][k], r[0]["b"][k], 2e-5), k       # the two exchange forms sum in the same order
         assert same_training(r[0]["a"][k], r[0]["b"][k], 2e-5), k       # NCCL all-reduce vs peer loads
         assert same_training(r[0]["c"][k], r[0]["b"][k], 2e-4), k       # single-GPU training on all views
+        assert torch.equal(r[0]["f"][k], r[1]["f"][k]), f"replicas diverged (CUDA-graph replay): {k}"
+        assert same_training(r[0]["f"][k], r[0]["g"][k], 2e-5), k       # graph replay vs launch by launch (lr 1e-4, 15 steps)
+    assert r[0]["f_replays"] == r[1]["f_replays"] == 7 and r[0]["g_replays"] == 0

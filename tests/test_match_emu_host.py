@@ -90,6 +90,32 @@ def test_merge_corres_golden(lib):
     assert np.array_equal(o1[:k], g["out1"]) and np.array_equal(o2[:k], g["out2"]) and np.array_equal(oi[:k], g["index"])
 
 
+@pytest.mark.parametrize("n", [1, 700, 1500, 3000, 6000, 12000, 16384, 17000])
+def test_merge_corres_one_cta_sort_every_instance(lib, n):
+    """The one-CTA register sort + unique (small_sort_unique<1 / 2 / 4 / 8 / 16>, 1024 emulated threads) and, beyond 16384
+    keys and with st3r_recip_set_variant(0), the radix chain: unique pairs and first-occurrence indices == np.unique."""
+    sys.path.insert(0, ROOT)
+    from oracle import match_oracle as mo
+    rng = np.random.default_rng(n)
+    hw = 300 * 200
+    pool1, pool2 = rng.integers(0, hw, size=max(n // 3, 1)), rng.integers(0, hw, size=max(n // 3, 1))
+    pick = rng.integers(0, len(pool1), size=n)
+    idx1 = pool1[pick].astype(np.int32)
+    idx2 = np.where(rng.random(n) < 0.7, pool2[pick], rng.integers(0, hw, size=n)).astype(np.int32)
+    want = mo.merge_corres(idx1, idx2, ret_xy=False, ret_index=True)
+    for variant in ((1, 0) if n in (700, 6000) else (1,)):
+        lib.st3r_recip_set_variant(variant)
+        o1, o2, oi, n_out = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(1, np.int32)
+        ws = ws_of(lib.st3r_merge_corres_ws_bytes(n))
+        try:
+            ok(lib, lib.st3r_merge_corres(P(idx1), P(idx2), n, hw, hw, P(o1), P(o2), P(oi), P(n_out), P(ws), ws.nbytes, None))
+        finally:
+            lib.st3r_recip_set_variant(1)
+        k = int(n_out[0])
+        assert k == len(want[0]), (variant, k, len(want[0]))
+        assert np.array_equal(o1[:k], want[0]) and np.array_equal(o2[:k], want[1]) and np.array_equal(oi[:k], want[2])
+
+
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
 def test_fast_reciprocal_nns_golden(lib, tag):
     g = np.load(os.path.join(GOLD, "match_recip.npz"))

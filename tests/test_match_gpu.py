@@ -113,6 +113,33 @@ def test_merge_corres_golden(golden, cuda_device):
     assert len(o1) == 0
 
 
+@pytest.mark.parametrize("n", [1, 5, 1000, 1025, 4096, 5000, 16384, 16385, 40000])
+def test_merge_corres_both_sort_variants_vs_numpy(cuda_device, n):
+    """st3r_merge_corres with the one-CTA register sort (lists up to 16384 keys: the default) and with the radix chain
+    (st3r_recip_set_variant(0), also the path of longer lists) against the oracle's np.unique restatement of
+    fast_nn.py:87-106: unique pairs in (idx1, idx2) order and the index of each pair's FIRST occurrence - many
+    duplicates, so the stability of the order is observable."""
+    from oracle import match_oracle as mo
+    from starst3r_b200 import _lib, match
+    lib = _lib.load()
+    rng = np.random.default_rng(n)
+    hw = 512 * 512
+    pool1 = rng.integers(0, hw, size=max(n // 3, 1), dtype=np.int64)
+    pool2 = rng.integers(0, hw, size=max(n // 3, 1), dtype=np.int64)
+    pick = rng.integers(0, len(pool1), size=n)
+    idx1 = pool1[pick].astype(np.int32)
+    idx2 = np.where(rng.random(n) < 0.7, pool2[pick], rng.integers(0, hw, size=n)).astype(np.int32)
+    want = mo.merge_corres(idx1, idx2, ret_xy=False, ret_index=True)
+    try:
+        for variant in (1, 0):
+            _lib.check(lib.st3r_recip_set_variant(variant), "st3r_recip_set_variant")
+            got = match.merge_corres(idx1, idx2, (512, 512), (512, 512), ret_xy=False, ret_index=True, device=cuda_device)
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b), (variant, n)
+    finally:
+        _lib.check(lib.st3r_recip_set_variant(1), "st3r_recip_set_variant")
+
+
 @pytest.mark.parametrize("impl", IMPLS)
 def test_extract_correspondences_golden(golden, cuda_device, impl):
     from starst3r_b200 import match
@@ -124,6 +151,16 @@ def test_extract_correspondences_golden(golden, cuda_device, impl):
     assert xy1.dtype == torch.int64 and conf.dtype == torch.float32 and xy1.is_cuda
     assert np.array_equal(xy1.cpu().numpy(), g["xy1"]) and np.array_equal(xy2.cpu().numpy(), g["xy2"])
     assert np.array_equal(conf.cpu().numpy(), g["conf"])
+    from starst3r_b200 import _lib
+    lib = _lib.load()
+    try:        # the radix chain instead of the one-CTA sort + unique: identical
+        _lib.check(lib.st3r_recip_set_variant(0), "st3r_recip_set_variant")
+        r = match.extract_correspondences([T(g["f11"]), T(g["f21"]), T(g["f22"]), T(g["f12"])],
+                                          [T(g["q11"]), T(g["q21"]), T(g["q22"]), T(g["q12"])],
+                                          subsample=8, device=cuda_device, impl=impl)
+    finally:
+        _lib.check(lib.st3r_recip_set_variant(1), "st3r_recip_set_variant")
+    assert torch.equal(r[0], xy1) and torch.equal(r[1], xy2) and torch.equal(r[2], conf)
 
 
 @pytest.mark.parametrize("impl", IMPLS)
