@@ -26,6 +26,16 @@
 #include "nn.cuh"
 #include "../../include/starst3r_b200.h"
 
+// Default: one UMMA-issuing warp per query tile with per-(query tile, accumulator stage) barriers, so that the two
+// accumulator pipelines of a CTA only share the DB tile in shared memory (B200, M = 262144: 7.73 -> 7.45 ms, split
+// precision pairs 5.09 -> 4.72 ms against ONE issuing thread for both tiles).  -DNN_TC_ONE_ISSUER restores the single
+// MMA thread with shared barriers (the instrumented timing experiments of scripts/build_dbg.sh are written against it);
+// -DNN_TC_ONE_ISSUER -DNN_TC_DECOUPLE is that thread with the per-tile barriers (measured slower than both).
+#if !defined(NN_TC_ONE_ISSUER)
+#define NN_TC_TWO_ISSUERS
+#define NN_TC_DECOUPLE
+#endif
+
 namespace {
 
 // One CTA per SM scores MH = 2 query tiles of 128 rows against ONE stream of DB tiles: every DB tile that TMA brings
@@ -52,7 +62,12 @@ constexpr int EPI_CHUNKS = EPI_COLS / 32;
 constexpr int EPI_THREADS = BM;                 // one thread per query row
 constexpr int EPI_WARPS = EPI_THREADS / 32;
 constexpr int WARP_TMA = EPI_WARPS, WARP_MMA = EPI_WARPS + 1;
-constexpr int NUM_THREADS = EPI_THREADS + 64;
+#ifdef NN_TC_TWO_ISSUERS
+constexpr int MMA_WARPS = MH;                   // one UMMA-issuing warp per query tile
+#else
+constexpr int MMA_WARPS = 1;
+#endif
+constexpr int NUM_THREADS = EPI_THREADS + 32 + 32 * MMA_WARPS;
 constexpr int TMEM_COLS = MH * ACC_STAGES * BN;  // 512: the whole tensor memory of the SM
 constexpr int MAX_TILES_PER_CHUNK = 65536 / BN;
 constexpr int MAX_PROBE = 1024 / BN;  // max-only probe tiles per CTA (see the kernel)
@@ -551,7 +566,11 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
+#if defined(NN_TC_TWO_ISSUERS)
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), MH); }   // one commit per query tile
+#else
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+#endif
 #ifdef NN_TC_DECOUPLE
     for (int h = 0; h < MH; ++h)
       for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(h, a), 1); mbar_init(tempty_bar(h, a), EPI_WARPS / MH); }
@@ -598,6 +617,31 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
         if (kSplit) tma_load_2d(sB + s * L::STAGE_BYTES + BN * ROWB, tmap_db_lo, 0, seq_col(t), full_bar(s));
       }
     }
+#ifdef NN_TC_TWO_ISSUERS
+  } else if (warp >= WARP_MMA) {
+    // ===== one UMMA issuer per query tile: the two accumulator pipelines only share the DB tile in shared memory =====
+    if (lane == 0) {
+      const int h = warp - WARP_MMA;
+      for (int t = 0; t < nseq; ++t) {
+        const int s = t % STAGES, a = t % ACC_STAGES;
+        mbar_wait(tempty_bar(h, a), ((uint32_t)(t / ACC_STAGES) & 1u) ^ 1u);
+        mbar_wait(full_bar(s), (uint32_t)(t / STAGES) & 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)((h * ACC_STAGES + a) * BN);
+#pragma unroll
+        for (int part = 0; part < (kSplit ? 3 : 1); ++part) {      // hi_q . hi_d (+ hi_q . lo_d + lo_q . hi_d, see Lay)
+#pragma unroll
+          for (int kk = 0; kk < DK / 8; ++kk) {
+            const uint64_t da = make_smem_desc(sA + (part == 2 ? BM * ROWB : 0) + h * UM * ROWB + kk * 32);
+            const uint64_t db = make_smem_desc(sB + s * L::STAGE_BYTES + (part == 1 ? BN * ROWB : 0) + kk * 32);
+            tc_mma_tf32(d_tmem, da, db, IDESC, (part > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        tc_commit(empty_bar(s));            // (one arrival per query tile: the stage is free when both have retired)
+        tc_commit(tfull_bar(h, a));
+      }
+    }
+#endif
   } else if (warp == WARP_MMA) {
     // ===== MMA issuer =====
     if (lane == 0) {
@@ -714,11 +758,21 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
       for (int c = 0; c < EPI_CHUNKS; ++c) tc_ld32(taddr + c * 32, v + c * 32);
       tc_wait_ld();
 #endif
+#ifdef NN_TC_DEBUG_CYCLES
+#ifdef NN_TC_DEBUG_LDONLY   // (tcgen05.wait::ld compiles to scoreboard waits at the consumers: touch the last register of every load)
+      {
+        const float sink = (v[31] + v[EPI_COLS / 2 - 1]) + (v[EPI_COLS - 33] + v[EPI_COLS - 1]);
+        *reinterpret_cast<volatile float*>(smem + SMEM_DBP + 8) = sink;      // (in-order issue: the store waits for the data)
+      }
+#endif
+      const long long c2 = clock64();      // accumulator columns in registers
+#endif
       tc_fence_before();
+#if defined(NN_TC_DECOUPLE)
       __syncwarp();
-#ifdef NN_TC_DECOUPLE
       if (lane == 0) mbar_arrive(tempty_bar(half, a));
 #else
+      __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(a));      // one arrival per warp
 #endif
 #ifdef NN_TC_EXP_NOALU  // timing experiment only (wrong results): no arg-max arithmetic
@@ -728,7 +782,11 @@ nn_tc_kernel(const __grid_constant__ NnTcParams prm) {
       epi_cols<kCoop, kSplit, EPI_CHUNKS>(v, t < n_probe, n_begin + (t - n_probe) * BN, n_end, slot, delta, run_max, cnt);
 #ifdef NN_TC_DEBUG_CYCLES
       c_wait += (unsigned long long)(c1 - c0);
+#ifdef NN_TC_DEBUG_LDONLY     // slot [2] = the TMEM read alone (issue of the four tcgen05.ld .. wait::ld)
+      c_epi += (unsigned long long)(c2 - c1);
+#else
       c_epi += (unsigned long long)(clock64() - c1);
+#endif
 #endif
     }
 #ifdef NN_TC_DEBUG_CYCLES

@@ -219,13 +219,15 @@ def test_extract_correspondences_golden_tcgen05(lib, tc_variant):
     assert np.array_equal(xy1[:k], g["xy1"]) and np.array_equal(xy2[:k], g["xy2"]) and np.array_equal(conf[:k], g["conf"])
 
 
-def test_tcgen05_decoupled_barrier_build(tmp_path):
-    """The -DNN_TC_DECOUPLE experiment build (one full / empty mbarrier pair per query tile and accumulator stage): the
-    changed hand-off protocol completes without a deadlock on the software model and returns the exact results."""
+@pytest.mark.parametrize("define", [("NN_TC_ONE_ISSUER",), ("NN_TC_ONE_ISSUER", "NN_TC_DECOUPLE")], ids=["one-issuer", "one-issuer-decoupled"])
+def test_tcgen05_decoupled_barrier_build(tmp_path, define):
+    """The default build has one UMMA-issuing warp per query tile; -DNN_TC_ONE_ISSUER (one MMA thread, shared accumulator
+    barriers: the first structure, kept for the instrumented experiments) and -DNN_TC_ONE_ISSUER -DNN_TC_DECOUPLE (that
+    thread with per-tile barriers) must complete without a deadlock on the software model and return the exact results."""
     sys.path.insert(0, os.path.join(ROOT, "tests", "host"))
     import build_emu_lib
     from starst3r_b200 import _lib
-    path, _ = build_emu_lib.build(str(tmp_path), defines=("NN_TC_DECOUPLE",))
+    path, _ = build_emu_lib.build(str(tmp_path), defines=define)
     lib = ctypes.CDLL(path)
     for name, (restype, argtypes) in _lib.parse_header().items():
         getattr(lib, name).restype, getattr(lib, name).argtypes = restype, argtypes
