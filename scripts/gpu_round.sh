@@ -32,6 +32,13 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
     python scripts/prof_step.py step > $OUT/ncu_step.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/${TAG}_launches_match_pair.csv \
     python scripts/prof_step.py match > $OUT/ncu_match.log 2>&1
+echo "== MATCH microbenchmark (BASELINE configs[4]: tcgen05 vs SIMT vs cuBLAS GEMM + max, measured peaks)"
+timeout 600 python scripts/bench_match.py > $OUT/${TAG}_match_micro.json 2> $OUT/${TAG}_match_micro.err
+python - <<PY
+import json
+d = json.load(open("$OUT/${TAG}_match_micro.json"))
+print(d["peaks_tflops"], {k: round(v["tcgen05"]["tflops"], 1) for k, v in d["nn_argmax"].items()}, d["all_pairs_tcgen05"])
+PY
 echo "== SASS evidence (tcgen05 / TMA / TMEM mnemonics of the shipped library)"
 cuobjdump -sass starst3r_b200/libstarst3r_b200.so 2>/dev/null | grep -oE "UTCHMMA[A-Z0-9_.]*|UTCBAR[A-Z0-9_.]*|UTMALDG[A-Z0-9_.]*|LDTM[A-Z0-9_.]*|UTCATOMSWS[A-Z0-9_.]*|SYNCS[A-Z0-9_.]*|ATOMS\.OR|REDG\.E\.ADD\.F32x4[A-Z0-9_.]*" \
     | sort | uniq -c | sort -rn > $OUT/${TAG}_sass_mnemonics.txt
