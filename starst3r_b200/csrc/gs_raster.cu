@@ -397,21 +397,51 @@ __device__ __forceinline__ void butterfly9_to_shared(const float* g, float* a9) 
 // rows (forward: gsplat's loop; backward: the nine-value warp reduction of raster_bwd_kernel per contributing visit).
 // Results: same expressions in the same per-pixel order as the kernels above (the forward is bit-identical); the
 // backward's per-Gaussian sums are added in a different order.
-#ifndef ST3R_POOL_PG
-#define ST3R_POOL_PG 256
+// Batch geometry, per kernel (B200 sweeps at configs[1], `scripts/build_variants.sh` + `scripts/gpu_libvar.sh`,
+// profiles/r02af_pool_sweeps.jsonl): the forward is fastest with 256 Gaussians / 4096 slots per batch; the backward, whose
+// pool holds two values per slot, with 128 Gaussians / 2304 slots and 48 registers (5 CTAs per SM instead of 3:
+// 0.753 -> 0.709 ms with the 3e-3 initial scales, 1.688 -> 1.507 ms with log-normal scales).  A slot count of (odd
+// number) x BLOCK keeps every thread's chunk full when a batch fills the pool (see pool_chunk).
+// -DST3R_POOL_PG / -DST3R_POOL_SLOTS set both kernels (A/B builds).
+#ifdef ST3R_POOL_PG
+#define ST3R_POOL_PG_FWD ST3R_POOL_PG
+#define ST3R_POOL_PG_BWD ST3R_POOL_PG
 #endif
-#ifndef ST3R_POOL_SLOTS
-#define ST3R_POOL_SLOTS (ST3R_POOL_PG * 16)
+#ifdef ST3R_POOL_SLOTS
+#define ST3R_POOL_SLOTS_FWD ST3R_POOL_SLOTS
+#define ST3R_POOL_SLOTS_BWD ST3R_POOL_SLOTS
+#endif
+#ifndef ST3R_POOL_PG_FWD
+#define ST3R_POOL_PG_FWD 256
+#endif
+#ifndef ST3R_POOL_SLOTS_FWD
+#define ST3R_POOL_SLOTS_FWD 4096
+#endif
+#ifndef ST3R_POOL_PG_BWD
+#define ST3R_POOL_PG_BWD 128
+#endif
+#ifndef ST3R_POOL_SLOTS_BWD
+#define ST3R_POOL_SLOTS_BWD 2304
 #endif
 #ifndef ST3R_POOL_DENSE
 #define ST3R_POOL_DENSE 96
 #endif
-constexpr int PG = ST3R_POOL_PG;          // Gaussians per batch (one per thread of the first PG threads)
-constexpr int PW = PG / 32;               // mask words per pixel
-constexpr int PSLOTS = ST3R_POOL_SLOTS;   // pool slots per batch (a Gaussian takes at most 256)
+#ifndef ST3R_POOL_MINB_FWD
+#define ST3R_POOL_MINB_FWD 1
+#endif
+#ifndef ST3R_POOL_MINB_BWD
+#define ST3R_POOL_MINB_BWD 5
+#endif
+template <bool kBwd>
+struct PoolCfg {
+  static constexpr int PG = kBwd ? ST3R_POOL_PG_BWD : ST3R_POOL_PG_FWD;              // Gaussians per batch (one per thread of the first PG threads)
+  static constexpr int PW = PG / 32;                                                 // mask words per pixel
+  static constexpr int PSLOTS = kBwd ? ST3R_POOL_SLOTS_BWD : ST3R_POOL_SLOTS_FWD;    // pool slots per batch (a Gaussian takes at most 256)
+  static_assert(PG == 64 || PG == 128 || PG == 256, "pool batch: 64, 128 or 256 Gaussians");
+  static_assert(PSLOTS >= 9 * PG && PSLOTS >= 256 && PSLOTS < (1 << 20),
+                "the pool doubles as the dense batches' [PG][9] accumulators and holds any one box");
+};
 constexpr int PDENSE = ST3R_POOL_DENSE;   // mean box area from which a batch is walked pixel-parallel
-static_assert(PG == 64 || PG == 128 || PG == 256, "pool batch: 64, 128 or 256 Gaussians");
-static_assert(PSLOTS >= 9 * BLOCK && PSLOTS < (1 << 20), "the pool doubles as the dense batches' [BLOCK][9] accumulators");
 
 // Box of tile pixels (rows r0..r1, columns c0..c1, clipped to rmax / cmax) on which opac * exp(-sigma) >= 1/255 is
 // possible; see row_mask for the bound (here with fast intrinsics and a wider safety margin: the box only has to
@@ -449,18 +479,19 @@ struct PoolBatch { int n, nc, S, n_done; bool dense; };
 // Shared memory of one CTA.  kBwd: two pool values per slot and the tile's upstream gradients.
 template <bool kBwd>
 struct PoolSmem {
+  static constexpr int PG = PoolCfg<kBwd>::PG, PW = PoolCfg<kBwd>::PW, PSLOTS = PoolCfg<kBwd>::PSLOTS;
   // per Gaussian WITH a box, in depth order (compacted): the record a walk loads when it enters the box
-  float4 recA[BLOCK];         // x, y, opacity, pixel-centre x of the box's first column
-  float4 recB[BLOCK];         // conic a, b, c, pixel-centre y of the box's first row
-  int4 recC[BLOCK];           // first slot behind the box | tile pixel of its first slot | wc, t << 5, area << 13,
+  float4 recA[PG];            // x, y, opacity, pixel-centre x of the box's first column
+  float4 recB[PG];            // conic a, b, c, pixel-centre y of the box's first row
+  int4 recC[PG];              // first slot behind the box | tile pixel of its first slot | wc, t << 5, area << 13,
                               // r0 << 23, (nr - 1) << 27 | entry id
-  float4 col[BLOCK];          // colour
+  float4 col[PG];             // colour
   int cbase[BLOCK];           // first pool slot (ascending); INT_MAX behind the last record
-  int2 boxB[BLOCK];           // by batch slot t: pool slot of tile pixel (row, col) = x + row * (y & 31) + col; y >> 8: record
+  int2 boxB[PG];              // by batch slot t: pool slot of tile pixel (row, col) = x + row * (y & 31) + col; y >> 8: record
   uint32_t mask[PW][BLOCK];   // bit t of word w of pixel p: Gaussian 32 w + t contributes to p
   int scan[BLOCK / 32], take[BLOCK / 32];
   uint32_t vlist[BLOCK / 32][BLOCK / 32];   // dense batches: bit ci of vlist[w]: record ci touches the rows of warp w
-  float poolA[PSLOTS];        // forward: alpha.  Backward, phase A: alpha; phase B: alpha T.  Dense backward: sums [BLOCK][9]
+  float poolA[PSLOTS];        // forward: alpha.  Backward, phase A: alpha; phase B: alpha T.  Dense backward: sums [PG][9]
   float poolV[kBwd ? PSLOTS : 1];    // backward, phase A: vis (0 when alpha was clamped); phase B: vis dL/dalpha
   float4 v[kBwd ? BLOCK : 1];        // backward: upstream colour gradient of every pixel of the tile
 };
@@ -471,6 +502,7 @@ __device__ __forceinline__ PoolBatch pool_stage(bool have, uint32_t e, const flo
                                                 const float4* __restrict__ geomB, const float4* __restrict__ rgb,
                                                 float px0, float py0, int rmax, int cmax, int done_pred,
                                                 PoolSmem<kBwd>& sm) {
+  constexpr int PW = PoolCfg<kBwd>::PW, PSLOTS = PoolCfg<kBwd>::PSLOTS;
   const unsigned full = 0xffffffffu;
   const int tr = threadIdx.x, lane = tr & 31, wrp = tr >> 5;
   int area = 0;
@@ -540,13 +572,17 @@ __device__ __forceinline__ PoolBatch pool_stage(bool have, uint32_t e, const flo
 }
 
 // Candidates of the next batch: all PG while whole batches fit into the pool, else about twice what the pool took.
+template <bool kBwd>
 __device__ __forceinline__ int pool_next_cand(int cand, int taken) {
+  constexpr int PG = PoolCfg<kBwd>::PG;
   return taken == cand ? min(PG, 2 * cand) : max(32, min(PG, 2 * taken));
 }
 
 // The chunk [s, s_end) of pool slots of this thread and the record of the Gaussian its first slot is in.
 __device__ __forceinline__ bool pool_chunk(int S, const int* cbase, int& s, int& s_end, int& ci) {
-  const int q = ((S + BLOCK - 1) / BLOCK) | 1;           // odd: the lanes of a warp write their slots to distinct banks
+  // odd: the lanes of a warp write their slots to distinct banks (even lengths, i.e. 2- / 4-way conflicts but up to
+  // one slot less per thread, measured 1.3 % slower on the B200: profiles/r02af_pool_sweeps.jsonl)
+  const int q = ((S + BLOCK - 1) / BLOCK) | 1;
   s = (int)threadIdx.x * q;
   s_end = min(S, s + q);
   if (s >= s_end) return false;
@@ -625,7 +661,7 @@ __device__ __forceinline__ void pool_visit_lists(PoolSmem<kBwd>& sm, int nc) {
   PoolSmem<kBwd>& sm = *reinterpret_cast<PoolSmem<kBwd>*>(pool_smem_raw)
 #endif
 
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, ST3R_POOL_MINB_FWD)
 raster_fwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
                        const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
                        const float4* __restrict__ geomB, const float4* __restrict__ rgb, int C, int W, int H, int tile_w,
@@ -645,6 +681,7 @@ raster_fwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
   const TileRange rg = tile_range(offsets, n_isect, c * tile_w * tile_h + tile, C * tile_w * tile_h);
   float T = 1.0f, pr = 0.f, pg = 0.f, pb_ = 0.f;
   int cur = 0, blends = 0;
+  constexpr int PG = PoolCfg<false>::PG, PW = PoolCfg<false>::PW;
   int pos = rg.lo, cand = PG;
   while (pos < rg.hi) {
     const int idx = pos + tr;
@@ -729,7 +766,7 @@ raster_fwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
       }
     }
     pos += pb.n;
-    cand = pool_next_cand(cand, pb.n);
+    cand = pool_next_cand<false>(cand, pb.n);
     __syncthreads();          // the next stage overwrites the records before its first barrier
   }
   if (inside) {
@@ -755,7 +792,7 @@ __device__ __forceinline__ void pool_emit(const float* m, float opac, float qa, 
   atomicAdd(v_rgb + e, make_float4(m[6], m[7], m[8], 0.f));
 }
 
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, ST3R_POOL_MINB_BWD)
 raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_isect,
                        const uint32_t* __restrict__ flatten, const float4* __restrict__ geomA,
                        const float4* __restrict__ geomB, const float4* __restrict__ rgb, int C, int W, int H, int tile_w,
@@ -794,6 +831,7 @@ raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
   for (int k = 0; k < BLOCK / 32; ++k) tile_last = max(tile_last, sm.scan[k]);
   __syncthreads();                           // scan[] is reused by the first pool_stage
   int hi = min(rg.hi - 1, tile_last);        // slot t of a batch holds sorted position hi - t: ascending t = back to front
+  constexpr int PG = PoolCfg<true>::PG, PW = PoolCfg<true>::PW;
   int cand = PG;
   while (hi >= rg.lo) {
     const int idx = hi - tr;
@@ -949,7 +987,7 @@ raster_bwd_pool_kernel(const int32_t* __restrict__ offsets, const int32_t* __res
       }
     }
     hi -= pb.n;
-    cand = pool_next_cand(cand, pb.n);
+    cand = pool_next_cand<true>(cand, pb.n);
     __syncthreads();                         // the next stage overwrites the records before its first barrier
   }
 }
