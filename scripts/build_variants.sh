@@ -9,6 +9,8 @@ STEM=${SRC%.cu}
 python -m starst3r_b200.build > /dev/null
 B=starst3r_b200/build
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr"
+# the two files whose arithmetic must not be FMA-contracted (starst3r_b200/build.py NO_FMAD)
+case $SRC in gs_project.cu|gs_backward.cu) FLAGS="$FLAGS -fmad=false";; esac
 OBJS=$(ls $B/*.o | grep -v "/$STEM.o" | grep -v _var_)
 for spec in "$@"; do
   name=${spec%%=*}; D=${spec#*=}

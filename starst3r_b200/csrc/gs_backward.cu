@@ -16,7 +16,10 @@
 
 namespace {
 
-__global__ void __launch_bounds__(128)
+// 4 CTAs per SM (128 registers instead of 165) and the next camera's screen-space gradients requested before the current
+// camera's are consumed: 0.094 -> 0.079 ms at configs[1] (B200 A/B of 1 / 4 / 5 / 6 CTAs per SM with and without the
+// prefetch: profiles/r02ag_libvar.jsonl; 5 and 6 spill and lose).
+__global__ void __launch_bounds__(128, 4)
 gs_project_bwd_kernel(const float* __restrict__ means, const float* __restrict__ quats,
                       const float* __restrict__ scales, const float* __restrict__ opacities,
                       const float* __restrict__ shN, int sh_stride, const GsCam* __restrict__ cams, int N, int C,
@@ -45,10 +48,18 @@ gs_project_bwd_kernel(const float* __restrict__ means, const float* __restrict__
 #pragma unroll
     for (int k = 0; k < 12; ++k) vsh[k] = 0.f;
 
+    // the next camera's screen-space gradients are in flight while this camera's are turned into parameter gradients
+    int r_nx = C > 0 ? radii[g] : 0;
+    float4 a_nx = make_float4(0.f, 0.f, 0.f, 0.f), b_nx = a_nx, c_nx = a_nx;
+    if (C > 0) { a_nx = v_geomA[g]; b_nx = v_geomB[g]; c_nx = v_rgb[g]; }
     for (int c = 0; c < C; ++c) {
-      const size_t e = (size_t)c * N + g;
-      if (radii[e] <= 0) continue;
-      const float4 gA = v_geomA[e], gB = v_geomB[e], gC = v_rgb[e];
+      const int r_cur = r_nx;
+      const float4 gA = a_nx, gB = b_nx, gC = c_nx;
+      if (c + 1 < C) {
+        const size_t e1 = (size_t)(c + 1) * N + g;
+        r_nx = radii[e1]; a_nx = v_geomA[e1]; b_nx = v_geomB[e1]; c_nx = v_rgb[e1];
+      }
+      if (r_cur <= 0) continue;
       GsCam cam = cams[c];
       GsProj o;
       GsProjTmp t;

@@ -252,6 +252,44 @@ def test_adam_step_dev_equals_host_form(cuda_device):
         assert (pa - pb).abs().max().item() <= 1e-9, step
 
 
+def test_adam_layouts_bit_identical(cuda_device):
+    """Every memory layout the kernel distinguishes (flat float4 + scalar tail, strided rows moved as float4 - the shN
+    [N, 24, 3] segment of gs.py:37 -, strided scalar rows, unaligned bases) gives the bits of the plain contiguous
+    update."""
+    from starst3r_b200 import gs
+    g = torch.Generator().manual_seed(11)
+    hp = (1e-3, (0.9, 0.999), 1e-8)
+
+    def run(rows, cols, ld_p, ld_g, off=0):
+        grad = torch.randn(rows, cols, generator=g)
+        p0 = torch.randn(rows, cols, generator=g)
+        # reference: contiguous tensors
+        pr, mr, vr = p0.clone().to(cuda_device), torch.zeros(rows, cols, device=cuda_device), torch.zeros(rows, cols, device=cuda_device)
+        gr = grad.to(cuda_device)
+        # layout under test: rows inside wider buffers, optionally shifted by `off` floats
+        P = torch.full((rows * ld_p + off + 8,), 7.0, device=cuda_device)
+        M, V = torch.zeros_like(P), torch.zeros_like(P)
+        G = torch.full((rows * ld_g + off + 8,), 9.0, device=cuda_device)
+        pv = P[off:off + rows * ld_p].view(rows, ld_p)
+        gv = G[off:off + rows * ld_g].view(rows, ld_g)
+        pv[:, :cols] = pr
+        gv[:, :cols] = gr
+        for step in (1, 2, 3):
+            gs.adam_step([(pr, gr, mr, vr, rows, cols, cols, cols)], *hp, step)
+            gs.adam_step([(P[off:], G[off:], M[off:], V[off:], rows, cols, ld_p, ld_g)], *hp, step)
+        mv, vv = M[off:off + rows * ld_p].view(rows, ld_p), V[off:off + rows * ld_p].view(rows, ld_p)
+        assert torch.equal(pv[:, :cols], pr) and torch.equal(mv[:, :cols], mr) and torch.equal(vv[:, :cols], vr)
+        if ld_p > cols:                      # the padding of every row is untouched
+            assert bool((pv[:, cols:] == 7.0).all()) and bool((mv[:, cols:] == 0).all())
+        assert bool((P[off + rows * ld_p:] == 7.0).all())
+
+    run(1001, 3, 3, 3)            # flat, 3003 floats: float4 body + 3-element tail
+    run(500, 12, 72, 12)          # the shN segment: 12 of 72 floats per row, float4 rows
+    run(333, 3, 5, 3)             # strided scalar rows
+    run(257, 4, 4, 4, off=1)      # base addresses not 16-byte aligned
+    run(64, 8, 12, 8, off=2)
+
+
 # ------------------------------------------------------------------------------------------ full train step
 def test_train_steps_vs_oracle(cuda_device):
     """Three iterations of gs.py:143-161 (render 3 views, loss, backward, Adam): loss, gradients and updated

@@ -40,6 +40,7 @@ def test_loss_and_adam(backend):
     t.test_loss_forward_backward_vs_oracle(CPU)
     t.test_fused_adam_vs_torch(CPU)
     t.test_adam_step_dev_equals_host_form(CPU)
+    t.test_adam_layouts_bit_identical(CPU)
 
 
 def test_train_steps_vs_oracle(backend_bwd):
