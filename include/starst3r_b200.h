@@ -173,9 +173,11 @@ ST3R_API int st3r_gs_offsets(const uint64_t* keys, const int32_t* n_isect, int n
  * [C, tile_h, tile_w] int32; *n_isect_out (device) = true number of intersections; keys / vals capacity n_cap (pairs
  * beyond it are dropped and offsets is clamped to it; n_cap = 0 only counts). */
 ST3R_API size_t st3r_gs_bin_ws_bytes(int C, int width, int height, int tile_size, int n_cap);
-/* Implementation variant of the per-tile sort for subsequent calls of this process.  1 (default): segments of up to
- * 2048 pairs are sorted in registers (warp shuffles, shared memory only for the longest spans); 0: the shared-memory /
- * in-place comparator network for every segment.  Same comparator network, identical outputs. */
+/* Implementation variant of the per-tile sort for subsequent calls of this process.  2 (default): segments of up to
+ * 2048 pairs are sorted in registers through 32-bit surrogate keys (leading depth bits | position) and the full
+ * (depth, entry) order is restored by odd-even passes in shared memory; 1: the same segments as 64-bit words (warp
+ * shuffles, shared memory only for the longest spans); 0: the shared-memory / in-place comparator network for every
+ * segment.  Identical outputs. */
 ST3R_API int st3r_gs_bin_set_variant(int variant);
 ST3R_API int st3r_gs_bin_tiles(const int32_t* radii, const float* geomA, int N, int C, int width, int height, int tile_size,
                       int32_t* offsets, int32_t* n_isect_out, uint64_t* keys, uint32_t* vals, int n_cap, void* ws,

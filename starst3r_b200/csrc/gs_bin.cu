@@ -207,6 +207,60 @@ __device__ __forceinline__ bool reg_sort_segment(const uint64_t* __restrict__ se
   return true;
 }
 
+// The same segments through 32-bit surrogate keys (default).  73 % of the 64-bit network's instructions are the compare +
+// select pairs of its comparators (sm_100a has no 64-bit integer min / max); a 32-bit comparator is two instructions and
+// a shuffle step moves one register.  Surrogate = the depth bits with their 11 lowest bits replaced by the element's
+// position in the unsorted segment: unique, monotone in the depth, and it names the element.  Sorting the surrogates
+// orders the segment up to the elements whose depths agree in the 21 leading bits (sign, exponent, 12 mantissa bits: a
+// few pairs per tile); the full (depth, entry) words are then gathered in that order into shared memory and odd-even
+// transposition passes finish the job - one pass fixes runs of two, the loop ends after the first pass without a swap, and
+// a depth distribution that keeps it busy (thousands of equal depths) falls back to the shared-memory network.  The result
+// is the ascending order of the full words, i.e. bit-identical to the 64-bit network and to the radix chain.
+constexpr int SUR_IDX_BITS = 11;
+constexpr int SUR_MAX_PASSES = 12;
+static_assert(8 * SORT_THREADS <= (1 << SUR_IDX_BITS), "a segment position must fit into the surrogate's index bits");
+static_assert(SMEM_ELEMS >= 2 * 8 * SORT_THREADS, "16 KB of exchange buffers + 16 KB for the repair passes");
+template <int EPT>
+__device__ __forceinline__ void reg_sort_segment32(const uint64_t* __restrict__ seg, int n, uint64_t* sbuf, uint64_t key_hi,
+                                                   uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  constexpr uint32_t IDX_MASK = (1u << SUR_IDX_BITS) - 1u;
+  uint32_t k[EPT];
+  const int i0 = threadIdx.x * EPT;
+#pragma unroll
+  for (int e = 0; e < EPT; ++e)
+    k[e] = i0 + e < n ? (((uint32_t)(seg[i0 + e] >> 32) & ~IDX_MASK) | (uint32_t)(i0 + e)) : 0xffffffffu;
+  st3r_sort::reg_bitonic_sort<SORT_THREADS, EPT, 2, uint32_t>(k, reinterpret_cast<uint32_t*>(sbuf), n);
+  uint64_t* s = sbuf + 8 * SORT_THREADS;          // behind the exchange buffers (2 x 2048 x 4 bytes)
+#pragma unroll
+  for (int e = 0; e < EPT; ++e)
+    if (i0 + e < n) s[i0 + e] = seg[k[e] & IDX_MASK];
+  __syncthreads();
+  for (int pass = 0;; ++pass) {
+    int swapped = 0;
+#pragma unroll
+    for (int parity = 0; parity < 2; ++parity) {
+      for (int p = 2 * (int)threadIdx.x + parity; p + 1 < n; p += 2 * SORT_THREADS) {
+        const uint64_t a = s[p], b = s[p + 1];
+        if (a > b) { s[p] = b; s[p + 1] = a; swapped = 1; }
+      }
+      __syncthreads();
+    }
+    if (__syncthreads_count(swapped) == 0) break;
+    if (pass + 1 == SUR_MAX_PASSES) {
+      bitonic_flip_sort(s, n, SORT_THREADS);
+      __syncthreads();
+      break;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < EPT; ++e)
+    if (i0 + e < n) {
+      const uint64_t w = s[i0 + e];
+      keys[i0 + e] = key_hi | (w >> 32);
+      vals[i0 + e] = (uint32_t)w;
+    }
+}
+
 __global__ void __launch_bounds__(SORT_THREADS)
 tile_sort_kernel(int32_t* offsets, const int32_t* __restrict__ total_ptr, int n_cells, int n_tiles,
                  int tile_n_bits, uint64_t* __restrict__ pairs, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
@@ -224,6 +278,13 @@ tile_sort_kernel(int32_t* offsets, const int32_t* __restrict__ total_ptr, int n_
   const uint64_t key_hi = ((((uint64_t)cam << tile_n_bits) | (uint64_t)tile) << 32);
   uint64_t* seg = pairs + lo;
   if (reg_path && n <= 8 * SORT_THREADS) {           // CTA-uniform
+    if (reg_path == 2) {
+      if (n <= SORT_THREADS) reg_sort_segment32<1>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
+      else if (n <= 2 * SORT_THREADS) reg_sort_segment32<2>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
+      else if (n <= 4 * SORT_THREADS) reg_sort_segment32<4>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
+      else reg_sort_segment32<8>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
+      return;
+    }
     bool done;
     if (n <= SORT_THREADS) done = reg_sort_segment<1>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
     else if (n <= 2 * SORT_THREADS) done = reg_sort_segment<2>(seg, n, sbuf, key_hi, keys + lo, vals + lo);
@@ -266,14 +327,18 @@ size_t carve_bin(BinWs* w, void* ws, size_t ws_bytes, int n_cells, int n_cap, bo
 }  // namespace
 
 #if !defined(ST3R_HOST_EMU) || defined(ST3R_EMU_WHOLE)
-// 1 (default): segments up to 2048 pairs are sorted in registers (reg_bitonic_sort); 0: always the shared-memory /
-// in-place network (the first implementation, kept as the cross-check: tests/test_gs_gpu.py runs both).
-static int g_bin_reg_sort = 1;
+// 2 (default): segments up to 2048 pairs are sorted in registers through 32-bit surrogate keys + repair passes
+// (reg_sort_segment32); 1: in registers as 64-bit words (reg_bitonic_sort); 0: always the shared-memory / in-place network
+// (the first implementation).  1 and 0 stay as cross-checks: tests/test_gs_gpu.py runs all three.
+#ifndef ST3R_BIN_DEFAULT
+#define ST3R_BIN_DEFAULT 2
+#endif
+static int g_bin_reg_sort = ST3R_BIN_DEFAULT;
 
 extern "C" {
 
 int st3r_gs_bin_set_variant(int variant) {
-  ST3R_CHECK_ARG(variant == 0 || variant == 1, "st3r_gs_bin_set_variant: unknown variant %d", variant);
+  ST3R_CHECK_ARG(variant >= 0 && variant <= 2, "st3r_gs_bin_set_variant: unknown variant %d", variant);
   g_bin_reg_sort = variant;
   return ST3R_OK;
 }

@@ -28,17 +28,25 @@ def P(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-@pytest.mark.parametrize("reg_sort", [1, 0])
+@pytest.mark.parametrize("reg_sort", [2, 1, 0])
 @pytest.mark.parametrize("n,C,W,H,scale_mult,use_smem", [(600, 2, 80, 48, 8.0, 1), (600, 2, 80, 48, 8.0, 0),
                                                          (2500, 1, 96, 64, 6.0, 1), (6000, 1, 160, 112, 8.0, 1),
-                                                         (9000, 1, 40, 40, 60.0, 1)])
+                                                         (9000, 1, 40, 40, 60.0, 1), (2501, 1, 96, 64, 6.0, 1),
+                                                         (2502, 1, 96, 64, 6.0, 1)])
 def test_fused_binning_bit_exact_on_the_emulator(emu, n, C, W, H, scale_mult, use_smem, reg_sort):
-    """reg_sort = 1: segments up to 2048 pairs take the register-resident network (1 / 2 / 4 / 8 elements per thread),
-    longer ones and reg_sort = 0 the shared-memory / in-place network."""
+    """reg_sort = 2: segments up to 2048 pairs are sorted in registers through 32-bit surrogate keys and repaired by
+    odd-even passes (n = 2501: depths quantised to 1/64, runs of equal leading bits AND exact ties that the entry index
+    must break; n = 2502: four distinct depths, which exhausts the passes and takes the fallback); reg_sort = 1: the
+    64-bit register-resident network (1 / 2 / 4 / 8 elements per thread); longer segments and reg_sort = 0 the
+    shared-memory / in-place network."""
     sp = synth.random_splats(n, seed=1, scale_mode="rand")
     sp["scales"] = sp["scales"] * scale_mult
     viewmats, Ks = synth.look_at_cameras(C, W, H)
     radii, means2d, depths, conics = go.project(sp["means"], sp["quats"], sp["scales"], viewmats, Ks, W, H)
+    if n == 2501:
+        depths = torch.round(depths * 64.0) / 64.0 + 1.0 / 128.0
+    if n == 2502:
+        depths = torch.round(depths * 0.5) * 2.0 + 1.0
     tw, th = (W + 15) // 16, (H + 15) // 16
     b = go.isect_tiles(means2d, radii, depths, 16, tw, th)
     want_offsets = go.isect_offset_encode(b["isect_ids"], C, tw, th, b["tile_n_bits"]).reshape(-1)

@@ -329,15 +329,15 @@ def test_train_steps_vs_oracle(cuda_device):
                                                  (50, 1.0, 2, 33, 17), (2500, 6.0, 1, 96, 64), (6000, 8.0, 1, 160, 112)])
 def test_fused_binning_equals_radix_chain(cuda_device, n, scale_mult, C, W, H):
     """st3r_gs_bin_tiles (counting sort by tile + in-tile sort) == st3r_gs_isect + st3r_radix_sort_pairs +
-    st3r_gs_offsets, bit for bit (isect_ids, flatten_ids, isect_offsets), for both per-tile sorts (register-resident up
-    to 2048 pairs = the default, and the shared-memory / in-place network), including tiles whose list is longer than
+    st3r_gs_offsets, bit for bit (isect_ids, flatten_ids, isect_offsets), for all three per-tile sorts (32-bit surrogate
+    keys + repair passes = the default, the 64-bit register-resident network, the shared-memory / in-place network), including tiles whose list is longer than
     the shared-memory sort (4096 pairs; the 20000-Gaussian case has ~20000 per tile)."""
     from starst3r_b200 import _lib, gs
     lib = _lib.load()
     sp, viewmats, Ks, W, H = small_scene(n=n, C=C, W=W, H=H, seed=n, scale_mult=scale_mult)
     d = to(cuda_device, sp)
     out = {}
-    for mode, variant in (("radix", 1), ("fused", 1), ("fused", 0)):
+    for mode, variant in (("radix", 2), ("fused", 2), ("fused", 1), ("fused", 0)):
         gs.BINNING = mode
         _lib.check(lib.st3r_gs_bin_set_variant(variant), "st3r_gs_bin_set_variant")
         try:
@@ -346,21 +346,68 @@ def test_fused_binning_equals_radix_chain(cuda_device, n, scale_mult, C, W, H):
                                               viewmats.to(cuda_device), Ks.to(cuda_device), W, H)
         finally:
             gs.BINNING = "fused"
-            _lib.check(lib.st3r_gs_bin_set_variant(1), "st3r_gs_bin_set_variant")
+            _lib.check(lib.st3r_gs_bin_set_variant(2), "st3r_gs_bin_set_variant")
         out[mode, variant] = (r, a, info)
-    ia = out["radix", 1][2]
+    ia = out["radix", 2][2]
     per_tile = torch.diff(ia["isect_offsets"].flatten())
     if n == 20000:
         assert per_tile.max().item() > 4096          # exercises the global-memory sort path
     if n == 2500:                                    # 2, 4 and 8 elements per thread of the register-resident sort
         for lo, hi in ((257, 512), (513, 1024), (1025, 2048)):
             assert ((per_tile >= lo) & (per_tile <= hi)).any(), (lo, hi)
-    for key in (("fused", 1), ("fused", 0)):
+    for key in (("fused", 2), ("fused", 1), ("fused", 0)):
         ib = out[key][2]
         assert ia["isect_ids"].numel() == ib["isect_ids"].numel() and ia["isect_ids"].numel() > 0
         for k in ("isect_ids", "flatten_ids", "isect_offsets"):
             assert torch.equal(ia[k], ib[k]), (k, key)
-        assert torch.equal(out["radix", 1][0], out[key][0]) and torch.equal(out["radix", 1][1], out[key][1])
+        assert torch.equal(out["radix", 2][0], out[key][0]) and torch.equal(out["radix", 2][1], out[key][1])
+
+
+@pytest.mark.parametrize("levels", [0, 64, 3])
+def test_tile_sort_variants_with_tied_depths(cuda_device, levels):
+    """st3r_gs_bin_tiles on synthetic (radius, centre, depth) records, the three per-tile sorts bit for bit: continuous
+    depths, depths on 64 levels (runs of equal leading bits AND exact ties, which the entry index breaks) and on 3 levels
+    (the repair passes of the surrogate-key sort give up and the shared-memory network finishes)."""
+    from starst3r_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5 + levels)
+    N, C, W, H = 6000, 2, 128, 96
+    tw, th = W // 16, H // 16
+    radii = torch.randint(1, 40, (C * N,), generator=g, dtype=torch.int32)
+    radii[torch.rand(C * N, generator=g) < 0.1] = 0
+    geomA = torch.zeros(C * N, 4)
+    geomA[:, 0] = torch.rand(C * N, generator=g) * W
+    geomA[:, 1] = torch.rand(C * N, generator=g) * H
+    depth = 0.5 + 9.5 * torch.rand(C * N, generator=g)
+    if levels:
+        depth = 0.5 + torch.floor(depth * levels / 10.0) * (10.0 / levels)
+    geomA[:, 3] = depth
+    radii, geomA = radii.to(cuda_device), geomA.to(cuda_device)
+    res = {}
+    try:
+        for variant in (2, 1, 0):
+            _lib.check(lib.st3r_gs_bin_set_variant(variant), "st3r_gs_bin_set_variant")
+            offsets = torch.zeros(C * tw * th, dtype=torch.int32, device=cuda_device)
+            n_dev = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+            ws = torch.empty(lib.st3r_gs_bin_ws_bytes(C, W, H, 16, 0), dtype=torch.uint8, device=cuda_device)
+            with torch.cuda.device(cuda_device):
+                _lib.check(lib.st3r_gs_bin_tiles(_lib.ptr(radii), _lib.ptr(geomA), N, C, W, H, 16, _lib.ptr(offsets), _lib.ptr(n_dev),
+                                                 None, None, 0, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "count")
+                n = int(n_dev.item())
+                keys = torch.zeros(n, dtype=torch.int64, device=cuda_device)
+                vals = torch.zeros(n, dtype=torch.int32, device=cuda_device)
+                ws = torch.empty(lib.st3r_gs_bin_ws_bytes(C, W, H, 16, n), dtype=torch.uint8, device=cuda_device)
+                _lib.check(lib.st3r_gs_bin_tiles(_lib.ptr(radii), _lib.ptr(geomA), N, C, W, H, 16, _lib.ptr(offsets), _lib.ptr(n_dev),
+                                                 _lib.ptr(keys), _lib.ptr(vals), n, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "bin")
+            res[variant] = (offsets.cpu(), keys.cpu(), vals.cpu())
+    finally:
+        _lib.check(lib.st3r_gs_bin_set_variant(2), "st3r_gs_bin_set_variant")
+    per_tile = torch.diff(res[0][0])
+    assert ((per_tile > 256) & (per_tile <= 2048)).any()
+    assert (torch.diff(res[0][1]) >= 0).all()                   # sorted by (camera, tile, depth)
+    for variant in (2, 1):
+        for a, b in zip(res[variant], res[0]):
+            assert torch.equal(a, b), variant
 
 
 def test_golden_vectors_from_gsplat_when_present(cuda_device):
