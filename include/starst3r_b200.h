@@ -101,9 +101,10 @@ ST3R_API int st3r_recip_nn(const float* P1, int H1, int W1, const float* P2, int
                   int32_t* n_out, void* ws, size_t ws_bytes, int impl, cudaStream_t stream);
 
 /* Implementation variant of the sort + unique step of st3r_merge_corres / st3r_recip_nn / st3r_extract_corres for
- * subsequent calls of this process.  1 (default): lists of up to 16384 keys (every pair up to 512 x 512 at subsample 8)
- * are sorted in registers and compacted by one CTA in one launch; 0: two LSD radix sorts + a compaction kernel for every
- * size (the generic chain, also the path of longer lists).  Identical outputs. */
+ * subsequent calls of this process.  2 (default): lists of up to 16384 keys (every pair up to 512 x 512 at subsample 8)
+ * are sorted in registers and compacted by one CTA in one launch, through 32-bit surrogate words (idx1 | position)
+ * and repair passes where idx1 and the position fit into 32 bits; 1: the same CTA on the 64-bit words; 0: two LSD radix
+ * sorts + a compaction kernel for every size (the generic chain, also the path of longer lists).  Identical outputs. */
 ST3R_API int st3r_recip_set_variant(int variant);
 
 /* merge_corres(idx1, idx2, ret_xy=False, ret_index=True) (fast_nn.py:87-106):

@@ -1,4 +1,5 @@
-"""Timing of st3r_merge_corres (device part only) with the one-CTA sort (variant 1) and the radix chain (variant 0)."""
+"""Timing of st3r_merge_corres (device part only) with the one-CTA sort (variant 2: 32-bit surrogate words + repair
+passes, variant 1: 64-bit words) and the radix chain (variant 0)."""
 import ctypes
 import json
 import sys
@@ -21,7 +22,7 @@ for n in (1024, 2048, 4096, 8192, 16384):
     n_out = torch.zeros(1, dtype=torch.int32, device=dev)
     ws = torch.empty(lib.st3r_merge_corres_ws_bytes(n), dtype=torch.uint8, device=dev)
     row = {}
-    for variant in (1, 0):
+    for variant in (2, 1, 0):
         lib.st3r_recip_set_variant(variant)
 
         def run():
@@ -36,7 +37,7 @@ for n in (1024, 2048, 4096, 8192, 16384):
             run()
         e1.record()
         torch.cuda.synchronize()
-        row["one_cta_us" if variant else "radix_us"] = round(e0.elapsed_time(e1) / 50 * 1e3, 1)
-    lib.st3r_recip_set_variant(1)
+        row[{2: "one_cta_surrogate_us", 1: "one_cta_us", 0: "radix_us"}[variant]] = round(e0.elapsed_time(e1) / 50 * 1e3, 1)
+    lib.st3r_recip_set_variant(2)
     out[n] = row
 print(json.dumps(out))

@@ -201,10 +201,19 @@ unique_sorted(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ va
 constexpr int SMALL_SORT_THREADS = 1024;
 constexpr int SMALL_SORT_MAX = 16 * SMALL_SORT_THREADS;
 
+// sur_bits > 0: the network runs on 32-bit surrogate words  a << sur_bits | position in the input  (one-instruction
+// 32-bit min / max instead of two compares + four selects per 64-bit comparator, one register per shuffle), which orders
+// the list by `a` and names every element; the full words are then gathered in that order into the (now free) exchange
+// buffer and odd-even transposition passes restore the order inside the runs of equal `a` - a correspondence usually
+// appears twice, from the two search directions, already in the right order, so the loop ends after a pass or two.  A
+// list that keeps the passes busy (a degenerate map where thousands of seeds meet in one pixel) is handed to the 64-bit
+// network.  Either way the result is the ascending order of the full words.
+constexpr int SMALL_SORT_MAX_PASSES = 16;
+
 template <int EPT>
 __global__ void __launch_bounds__(SMALL_SORT_THREADS)
 small_sort_unique(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const int32_t* __restrict__ nkeys,
-                  int cap, int sh_a, int bv, UniqueOut out) {
+                  int cap, int sh_a, int bv, int sur_bits, UniqueOut out) {
   ST3R_DYN_SMEM_U64(sx);                       // [SMALL_SORT_THREADS * EPT] exchange buffer
   __shared__ int warp_sums[32];
   __shared__ uint64_t warp_last[32];
@@ -212,18 +221,45 @@ small_sort_unique(const uint64_t* __restrict__ keys, const uint32_t* __restrict_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sh_b = 1 + bv;
   const uint64_t b_mask = (1ull << (sh_a - sh_b)) - 1ull;
+  auto full_word = [&](int i) -> uint64_t {
+    const uint64_t k = keys[i];
+    return bv ? ((k >> 33) << sh_a) | (((k >> 1) & 0xffffffffull) << sh_b) | ((k & 1ull) << bv) | (uint64_t)vals[i] : k;
+  };
   uint64_t v[EPT];
   const int i0 = threadIdx.x * EPT;
+  bool sorted = false;                         // CTA-uniform
+  if (sur_bits) {
+    uint32_t sw[EPT];
 #pragma unroll
-  for (int e = 0; e < EPT; ++e) {
-    uint64_t w = st3r_sort::SORT_PAD;
-    if (i0 + e < n) {
-      const uint64_t k = keys[i0 + e];
-      w = bv ? ((k >> 33) << sh_a) | (((k >> 1) & 0xffffffffull) << sh_b) | ((k & 1ull) << bv) | (uint64_t)vals[i0 + e] : k;
+    for (int e = 0; e < EPT; ++e)
+      sw[e] = i0 + e < n ? ((uint32_t)(keys[i0 + e] >> 33) << sur_bits) | (uint32_t)(i0 + e) : 0xffffffffu;
+    st3r_sort::reg_bitonic_sort<SMALL_SORT_THREADS, EPT, 1, uint32_t>(sw, reinterpret_cast<uint32_t*>(sx), n);
+    __syncthreads();
+    const uint32_t pos_mask = (1u << sur_bits) - 1u;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e)
+      if (i0 + e < n) sx[i0 + e] = full_word((int)(sw[e] & pos_mask));
+    __syncthreads();
+    for (int pass = 0; pass < SMALL_SORT_MAX_PASSES && !sorted; ++pass) {
+      int swapped = 0;
+#pragma unroll
+      for (int parity = 0; parity < 2; ++parity) {
+        for (int p = 2 * (int)threadIdx.x + parity; p + 1 < n; p += 2 * SMALL_SORT_THREADS) {
+          const uint64_t a = sx[p], b = sx[p + 1];
+          if (a > b) { sx[p] = b; sx[p + 1] = a; swapped = 1; }
+        }
+        __syncthreads();
+      }
+      sorted = __syncthreads_count(swapped) == 0;
     }
-    v[e] = w;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) v[e] = i0 + e < n ? sx[i0 + e] : st3r_sort::SORT_PAD;
+    __syncthreads();                           // everyone holds its words before a fallback sort reuses the buffer
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) v[e] = i0 + e < n ? full_word(i0 + e) : st3r_sort::SORT_PAD;
   }
-  st3r_sort::reg_bitonic_sort<SMALL_SORT_THREADS, EPT, 1>(v, sx, n);
+  if (!sorted) st3r_sort::reg_bitonic_sort<SMALL_SORT_THREADS, EPT, 1>(v, sx, n);
   // first element of every run of equal (a, b): ordered compaction
   uint64_t prev = (uint64_t)__shfl_up_sync(0xffffffffu, (unsigned long long)v[EPT - 1], 1);
   if (lane == 31) warp_last[warp] = v[EPT - 1];
@@ -403,9 +439,10 @@ int run_recip_batch(const RecipWs& w, const RecipProblem* pr, int n, int d, int 
   return ST3R_OK;
 }
 
-// 1 (default): lists of up to 16384 keys are sorted and compacted by one CTA (small_sort_unique); 0: always the radix
-// chain (the first implementation, kept as the cross-check: st3r_recip_set_variant, tests/test_match_gpu.py runs both).
-int g_small_sort = 1;
+// 2 (default): lists of up to 16384 keys are sorted and compacted by one CTA (small_sort_unique) through 32-bit surrogate
+// words where the fields fit; 1: the same CTA on the 64-bit words; 0: always the radix chain (the first implementation).
+// 1 and 0 stay as cross-checks: st3r_recip_set_variant, tests/test_match_gpu.py runs all of them.
+int g_small_sort = 2;
 
 int sort_and_unique(const RecipWs& w, int key_cap, int HW1, int HW2, bool with_vals, const UniqueOut& out,
                     cudaStream_t stream) {
@@ -424,16 +461,18 @@ int sort_and_unique(const RecipWs& w, int key_cap, int HW1, int HW2, bool with_v
       attr_set.mark();
     }
     const uint32_t* vv = with_vals ? w.vals : nullptr;
+    const int pos_bits = bits_for(key_cap);
+    const int sur = (g_small_sort == 2 && b1 + pos_bits <= 32) ? pos_bits : 0;
     if (key_cap <= SMALL_SORT_THREADS)
-      small_sort_unique<1><<<1, SMALL_SORT_THREADS, sizeof(uint64_t) * SMALL_SORT_THREADS, stream>>>(w.keys, vv, w.nkeys, key_cap, sh_a, bv, out);
+      small_sort_unique<1><<<1, SMALL_SORT_THREADS, sizeof(uint64_t) * SMALL_SORT_THREADS, stream>>>(w.keys, vv, w.nkeys, key_cap, sh_a, bv, sur, out);
     else if (key_cap <= 2 * SMALL_SORT_THREADS)
-      small_sort_unique<2><<<1, SMALL_SORT_THREADS, sizeof(uint64_t) * SMALL_SORT_THREADS * 2, stream>>>(w.keys, vv, w.nkeys, key_cap, sh_a, bv, out);
+      small_sort_unique<2><<<1, SMALL_SORT_THREADS, sizeof(uint64_t) * SMALL_SORT_THREADS * 2, stream>>>(w.keys, vv, w.nkeys, key_cap, sh_a, bv, sur, out);
     else if (key_cap <= 4 * SMALL_SORT_THREADS)
-      small_sort_unique<4><<<1, SMALL_SORT_THREADS, sizeof(uint64_t) * SMALL_SORT_THREADS * 4, stream>>>(w.keys, vv, w.nkeys, key_cap, sh_a, bv, out);
+      small_sort_unique<4><<<1, SMALL_SORT_THREADS, sizeof(uint64_t) * SMALL_SORT_THREADS * 4, stream>>>(w.keys, vv, w.nkeys, key_cap, sh_a, bv, sur, out);
     else if (key_cap <= 8 * SMALL_SORT_THREADS)
-      small_sort_unique<8><<<1, SMALL_SORT_THREADS, sizeof(uint64_t) * SMALL_SORT_THREADS * 8, stream>>>(w.keys, vv, w.nkeys, key_cap, sh_a, bv, out);
+      small_sort_unique<8><<<1, SMALL_SORT_THREADS, sizeof(uint64_t) * SMALL_SORT_THREADS * 8, stream>>>(w.keys, vv, w.nkeys, key_cap, sh_a, bv, sur, out);
     else
-      small_sort_unique<16><<<1, SMALL_SORT_THREADS, sizeof(uint64_t) * SMALL_SORT_THREADS * 16, stream>>>(w.keys, vv, w.nkeys, key_cap, sh_a, bv, out);
+      small_sort_unique<16><<<1, SMALL_SORT_THREADS, sizeof(uint64_t) * SMALL_SORT_THREADS * 16, stream>>>(w.keys, vv, w.nkeys, key_cap, sh_a, bv, sur, out);
     ST3R_CHECK_LAUNCH();
     return ST3R_OK;
   }
@@ -535,7 +574,7 @@ int st3r_recip_nn(const float* P1, int H1, int W1, const float* P2, int H2, int 
 }
 
 int st3r_recip_set_variant(int variant) {
-  ST3R_CHECK_ARG(variant == 0 || variant == 1, "st3r_recip_set_variant: unknown variant %d", variant);
+  ST3R_CHECK_ARG(variant >= 0 && variant <= 2, "st3r_recip_set_variant: unknown variant %d", variant);
   g_small_sort = variant;
   return ST3R_OK;
 }

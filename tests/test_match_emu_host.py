@@ -90,10 +90,13 @@ def test_merge_corres_golden(lib):
     assert np.array_equal(o1[:k], g["out1"]) and np.array_equal(o2[:k], g["out2"]) and np.array_equal(oi[:k], g["index"])
 
 
-@pytest.mark.parametrize("n", [1, 700, 1500, 3000, 6000, 12000, 16384, 17000])
+@pytest.mark.parametrize("n", [1, 700, 1500, 3000, 6000, 12000, 16384, 17000, 2999, 5999])
 def test_merge_corres_one_cta_sort_every_instance(lib, n):
-    """The one-CTA register sort + unique (small_sort_unique<1 / 2 / 4 / 8 / 16>, 1024 emulated threads) and, beyond 16384
-    keys and with st3r_recip_set_variant(0), the radix chain: unique pairs and first-occurrence indices == np.unique."""
+    """The one-CTA register sort + unique (small_sort_unique<1 / 2 / 4 / 8 / 16>, 1024 emulated threads; variant 2 = through
+    32-bit surrogate words + repair passes, variant 1 = on the 64-bit words) and, beyond 16384 keys and with
+    st3r_recip_set_variant(0), the radix chain: unique pairs and first-occurrence indices == np.unique.  n = 2999: every
+    idx1 from a pool of five values (runs far longer than the repair passes: the 64-bit network finishes); n = 5999: idx1
+    from a pool of 1500 (runs of ~4 in arbitrary idx2 order)."""
     sys.path.insert(0, ROOT)
     from oracle import match_oracle as mo
     rng = np.random.default_rng(n)
@@ -102,15 +105,20 @@ def test_merge_corres_one_cta_sort_every_instance(lib, n):
     pick = rng.integers(0, len(pool1), size=n)
     idx1 = pool1[pick].astype(np.int32)
     idx2 = np.where(rng.random(n) < 0.7, pool2[pick], rng.integers(0, hw, size=n)).astype(np.int32)
+    if n == 2999:
+        idx1 = pool1[:5][rng.integers(0, 5, size=n)].astype(np.int32)
+    if n == 5999:
+        idx1 = pool1[:1500][rng.integers(0, 1500, size=n)].astype(np.int32)
+        idx2 = rng.integers(0, hw, size=n).astype(np.int32)
     want = mo.merge_corres(idx1, idx2, ret_xy=False, ret_index=True)
-    for variant in ((1, 0) if n in (700, 6000) else (1,)):
+    for variant in ((2, 1, 0) if n in (700, 6000) else (2, 1) if n in (16384, 2999) else (2,)):
         lib.st3r_recip_set_variant(variant)
         o1, o2, oi, n_out = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(1, np.int32)
         ws = ws_of(lib.st3r_merge_corres_ws_bytes(n))
         try:
             ok(lib, lib.st3r_merge_corres(P(idx1), P(idx2), n, hw, hw, P(o1), P(o2), P(oi), P(n_out), P(ws), ws.nbytes, None))
         finally:
-            lib.st3r_recip_set_variant(1)
+            lib.st3r_recip_set_variant(2)
         k = int(n_out[0])
         assert k == len(want[0]), (variant, k, len(want[0]))
         assert np.array_equal(o1[:k], want[0]) and np.array_equal(o2[:k], want[1]) and np.array_equal(oi[:k], want[2])

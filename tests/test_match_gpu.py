@@ -113,12 +113,14 @@ def test_merge_corres_golden(golden, cuda_device):
     assert len(o1) == 0
 
 
-@pytest.mark.parametrize("n", [1, 5, 1000, 1025, 4096, 5000, 16384, 16385, 40000])
+@pytest.mark.parametrize("n", [1, 5, 1000, 1025, 4096, 5000, 16384, 16385, 40000, 4095, 16383])
 def test_merge_corres_both_sort_variants_vs_numpy(cuda_device, n):
-    """st3r_merge_corres with the one-CTA register sort (lists up to 16384 keys: the default) and with the radix chain
-    (st3r_recip_set_variant(0), also the path of longer lists) against the oracle's np.unique restatement of
-    fast_nn.py:87-106: unique pairs in (idx1, idx2) order and the index of each pair's FIRST occurrence - many
-    duplicates, so the stability of the order is observable."""
+    """st3r_merge_corres with the one-CTA register sort (lists up to 16384 keys; variant 2, the default: 32-bit surrogate
+    words + repair passes, variant 1: the 64-bit words) and with the radix chain (st3r_recip_set_variant(0), also the
+    path of longer lists) against the oracle's np.unique restatement of fast_nn.py:87-106: unique pairs in (idx1, idx2)
+    order and the index of each pair's FIRST occurrence - many duplicates, so the stability of the order is observable.
+    n = 4095: idx1 from five values (the repair passes give up, the 64-bit network finishes); n = 16383: idx1 from a pool
+    of 4000 with unrelated idx2 (runs of ~4 to repair)."""
     from oracle import match_oracle as mo
     from starst3r_b200 import _lib, match
     lib = _lib.load()
@@ -129,15 +131,20 @@ def test_merge_corres_both_sort_variants_vs_numpy(cuda_device, n):
     pick = rng.integers(0, len(pool1), size=n)
     idx1 = pool1[pick].astype(np.int32)
     idx2 = np.where(rng.random(n) < 0.7, pool2[pick], rng.integers(0, hw, size=n)).astype(np.int32)
+    if n == 4095:
+        idx1 = pool1[:5][rng.integers(0, 5, size=n)].astype(np.int32)
+    if n == 16383:
+        idx1 = pool1[:4000][rng.integers(0, 4000, size=n)].astype(np.int32)
+        idx2 = rng.integers(0, hw, size=n).astype(np.int32)
     want = mo.merge_corres(idx1, idx2, ret_xy=False, ret_index=True)
     try:
-        for variant in (1, 0):
+        for variant in (2, 1, 0):
             _lib.check(lib.st3r_recip_set_variant(variant), "st3r_recip_set_variant")
             got = match.merge_corres(idx1, idx2, (512, 512), (512, 512), ret_xy=False, ret_index=True, device=cuda_device)
             for a, b in zip(got, want):
                 assert np.array_equal(a, b), (variant, n)
     finally:
-        _lib.check(lib.st3r_recip_set_variant(1), "st3r_recip_set_variant")
+        _lib.check(lib.st3r_recip_set_variant(2), "st3r_recip_set_variant")
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -153,14 +160,15 @@ def test_extract_correspondences_golden(golden, cuda_device, impl):
     assert np.array_equal(conf.cpu().numpy(), g["conf"])
     from starst3r_b200 import _lib
     lib = _lib.load()
-    try:        # the radix chain instead of the one-CTA sort + unique: identical
-        _lib.check(lib.st3r_recip_set_variant(0), "st3r_recip_set_variant")
-        r = match.extract_correspondences([T(g["f11"]), T(g["f21"]), T(g["f22"]), T(g["f12"])],
-                                          [T(g["q11"]), T(g["q21"]), T(g["q22"]), T(g["q12"])],
-                                          subsample=8, device=cuda_device, impl=impl)
-    finally:
-        _lib.check(lib.st3r_recip_set_variant(1), "st3r_recip_set_variant")
-    assert torch.equal(r[0], xy1) and torch.equal(r[1], xy2) and torch.equal(r[2], conf)
+    for variant in (0, 1):      # the radix chain / the 64-bit one-CTA sort instead of the surrogate-word sort: identical
+        try:
+            _lib.check(lib.st3r_recip_set_variant(variant), "st3r_recip_set_variant")
+            r = match.extract_correspondences([T(g["f11"]), T(g["f21"]), T(g["f22"]), T(g["f12"])],
+                                              [T(g["q11"]), T(g["q21"]), T(g["q22"]), T(g["q12"])],
+                                              subsample=8, device=cuda_device, impl=impl)
+        finally:
+            _lib.check(lib.st3r_recip_set_variant(2), "st3r_recip_set_variant")
+        assert torch.equal(r[0], xy1) and torch.equal(r[1], xy2) and torch.equal(r[2], conf)
 
 
 @pytest.mark.parametrize("impl", IMPLS)
