@@ -19,6 +19,15 @@
 
 namespace {
 
+// A thread projects ONE Gaussian into up to PROJ_CPT consecutive cameras: the 92 B of parameters are read once per
+// group of cameras instead of once per camera (with a thread per (Gaussian, camera) the kernel moved 147 MB of parameter
+// re-reads through L2 at configs[1], more than the 90 MB it writes), and what does not depend on the camera - the 3-D
+// covariance - is computed once (same operations in the same order: identical bits).
+#ifndef ST3R_PROJ_CPT
+#define ST3R_PROJ_CPT 4
+#endif
+constexpr int PROJ_CPT = ST3R_PROJ_CPT;
+
 __global__ void __launch_bounds__(256)
 gs_project_kernel(const float* __restrict__ means, const float* __restrict__ quats,
                   const float* __restrict__ scales, const float* __restrict__ opacities,
@@ -26,41 +35,49 @@ gs_project_kernel(const float* __restrict__ means, const float* __restrict__ qua
                   float W, float H, int tile_size, int tile_w, int tile_h, float eps2d, float near_plane,
                   float far_plane, float radius_clip, int32_t* __restrict__ radii, float4* __restrict__ geomA,
                   float4* __restrict__ geomB, float4* __restrict__ rgb, int32_t* __restrict__ tiles) {
-  __shared__ GsCam cam;
-  const int c = blockIdx.y;
-  if (threadIdx.x < (int)(sizeof(GsCam) / 4)) reinterpret_cast<float*>(&cam)[threadIdx.x] = reinterpret_cast<const float*>(cams + c)[threadIdx.x];
+  __shared__ GsCam cam_s[PROJ_CPT];
+  const int c0 = blockIdx.y * PROJ_CPT, nc = min(PROJ_CPT, C - c0);
+  constexpr int CAMF = (int)(sizeof(GsCam) / 4);
+  for (int i = threadIdx.x; i < nc * CAMF; i += blockDim.x)
+    reinterpret_cast<float*>(cam_s)[i] = reinterpret_cast<const float*>(cams + c0)[i];
   __syncthreads();
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= N) return;
-  const size_t e = (size_t)c * N + g;
   float mean[3] = {means[3 * g], means[3 * g + 1], means[3 * g + 2]};
   float4 q4 = reinterpret_cast<const float4*>(quats)[g];
   float quat[4] = {q4.x, q4.y, q4.z, q4.w};
   float scale[3] = {scales[3 * g], scales[3 * g + 1], scales[3 * g + 2]};
-  GsProj o;
-  GsProjTmp t;
-  bool vis = gs_project(mean, quat, scale, cam, W, H, eps2d, near_plane, far_plane, radius_clip, o, t);
-  int ntiles = 0;
-  if (vis) {
-    const float ts = (float)tile_size;
-    float txc = o.m2x / ts, tyc = o.m2y / ts, tr = (float)o.radius / ts;
-    int x0 = min(max(0, (int)floorf(txc - tr)), tile_w), x1 = min(max(0, (int)ceilf(txc + tr)), tile_w);
-    int y0 = min(max(0, (int)floorf(tyc - tr)), tile_h), y1 = min(max(0, (int)ceilf(tyc + tr)), tile_h);
-    ntiles = (y1 - y0) * (x1 - x0);
-    const float* sh = shN + (size_t)g * sh_stride;
-    float shl[12];
-    const float4* sh4 = reinterpret_cast<const float4*>(sh);
+  const float opac = opacities[g];
+  float shl[12];
+  {
+    const float4* sh4 = reinterpret_cast<const float4*>(shN + (size_t)g * sh_stride);
     float4 s0 = sh4[0], s1 = sh4[1], s2 = sh4[2];
     shl[0] = s0.x; shl[1] = s0.y; shl[2] = s0.z; shl[3] = s0.w; shl[4] = s1.x; shl[5] = s1.y; shl[6] = s1.z;
     shl[7] = s1.w; shl[8] = s2.x; shl[9] = s2.y; shl[10] = s2.z; shl[11] = s2.w;
-    float col[3];
-    gs_sh_color(mean, cam.pos, shl, col, nullptr, nullptr, nullptr);
-    geomA[e] = make_float4(o.m2x, o.m2y, opacities[g], o.depth);
-    geomB[e] = make_float4(o.ca, o.cb, o.cc, 0.f);
-    rgb[e] = make_float4(col[0], col[1], col[2], 0.f);
   }
-  radii[e] = vis ? o.radius : 0;
-  tiles[e] = ntiles;
+#pragma unroll 1
+  for (int ci = 0; ci < nc; ++ci) {
+    const GsCam& cam = cam_s[ci];
+    const size_t e = (size_t)(c0 + ci) * N + g;
+    GsProj o;
+    GsProjTmp t;
+    bool vis = gs_project(mean, quat, scale, cam, W, H, eps2d, near_plane, far_plane, radius_clip, o, t);
+    int ntiles = 0;
+    if (vis) {
+      const float ts = (float)tile_size;
+      float txc = o.m2x / ts, tyc = o.m2y / ts, tr = (float)o.radius / ts;
+      int x0 = min(max(0, (int)floorf(txc - tr)), tile_w), x1 = min(max(0, (int)ceilf(txc + tr)), tile_w);
+      int y0 = min(max(0, (int)floorf(tyc - tr)), tile_h), y1 = min(max(0, (int)ceilf(tyc + tr)), tile_h);
+      ntiles = (y1 - y0) * (x1 - x0);
+      float col[3];
+      gs_sh_color(mean, cam.pos, shl, col, nullptr, nullptr, nullptr);
+      geomA[e] = make_float4(o.m2x, o.m2y, opac, o.depth);
+      geomB[e] = make_float4(o.ca, o.cb, o.cc, 0.f);
+      rgb[e] = make_float4(col[0], col[1], col[2], 0.f);
+    }
+    radii[e] = vis ? o.radius : 0;
+    tiles[e] = ntiles;
+  }
 }
 
 // One thread per entry writes its (key, value) pairs: key = cam << (32 + tile_bits) | tile << 32 | depth bits.
@@ -139,7 +156,7 @@ int st3r_gs_project(const float* means, const float* quats, const float* scales,
   ST3R_CHECK_ARG(((uintptr_t)quats % 16) == 0 && ((uintptr_t)shN % 16) == 0 && (sh_coeffs * 3) % 4 == 0,
                  "st3r_gs_project: quats / shN must be 16-byte aligned");
   const int tile_w = (width + tile_size - 1) / tile_size, tile_h = (height + tile_size - 1) / tile_size;
-  dim3 grid((N + 255) / 256, C);
+  dim3 grid((N + 255) / 256, (C + PROJ_CPT - 1) / PROJ_CPT);
   gs_project_kernel<<<grid, 256, 0, stream>>>(means, quats, scales, opacities, shN, sh_coeffs * 3,
                                               reinterpret_cast<const GsCam*>(cams), N, C, (float)width, (float)height,
                                               tile_size, tile_w, tile_h, eps2d, near_plane, far_plane, radius_clip,
