@@ -30,7 +30,7 @@ N_GAUSS, N_VIEWS, W, H = 200_000, 8, 512, 512
 WORKLOAD = ("8-view 512x512 synthetic scene, 200k Gaussians, 3DGS train step (render fwd + L1/SSIM loss + bwd + Adam), "
             "BASELINE.json configs[1]")
 MATCH_HW = 512
-TF32_PEAK_TFLOPS = 758.8     # cuBLAS TF32 GEMM 8192^3, measured on this pool's B200 (profiles/r02n_match_micro.json; 748.6 in r02ad)
+TF32_PEAK_TFLOPS = 758.8     # cuBLAS TF32 GEMM 8192^3, measured on this pool's B200 (profiles/r02n_match_micro.json; 748.6 / 749.4 in r02ad / r02ao)
 
 
 def peaks():
@@ -494,7 +494,7 @@ def run_ours(args):
                               "alg_flops_per_pair": flops, "query_rows_per_pair": rows,
                               "note": "whole-pair figure: 29 NN calls with shrinking row counts + reciprocal bookkeeping; "
                                       "the kernel alone reaches 293 / 377 / 442 TFLOP/s at M = 4096 / 32768 / 262144 rows "
-                                      "(profiles/r02ad_match_micro.json), 46x the reference's cuBLAS GEMM + max"},
+                                      "(profiles/r02ao_match_micro.json), 46x the reference's cuBLAS GEMM + max"},
                  "e2e_note": "descriptors are born on the device in production (network output); the e2e figure uploads "
                              "105 MB of descriptor maps per pair from pinned host memory and is PCIe-bound at N > 1"}
 
