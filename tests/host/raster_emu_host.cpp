@@ -1,6 +1,6 @@
 // TEST-ONLY: the blend kernels of starst3r_b200/csrc/gs_raster.cu (fragment-pool pair and visit-list pair)
 // compiled for the host and executed thread by thread by the SIMT emulator in simt_emu.h, so that the CPU test-suite
-// runs the kernels' own source - indexing, visit lists, queues, segmented scans, barriers - against the oracle.
+// runs the kernels' own source - indexing, visit lists, fragment pools, block scans, barriers - against the oracle.
 // Never linked into the product library.
 #include "simt_emu.h"
 #define ST3R_HOST_EMU 1
