@@ -290,6 +290,57 @@ def test_adam_layouts_bit_identical(cuda_device):
     run(64, 8, 12, 8, off=2)
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_peer_gradient_kernels_on_one_device(cuda_device, world):
+    """The multi-GPU exchange kernels with every rank's buffer on ONE device (the kernels only see addresses):
+    st3r_adam_step_peers == st3r_adam_step on the rank-ordered sum, bit for bit, for the float4 rows, the strided shN rows
+    and an offset that is not a multiple of 4 floats (scalar peer loads); st3r_grad_reduce_scatter run once per rank
+    leaves that same sum in every rank's `reduced` buffer."""
+    import ctypes
+    from starst3r_b200 import _lib, gs
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(17 + world)
+    N = 501
+    shapes = [(N, 3, 3, 3), (N, 4, 4, 4), (N, 12, 72, 12), (N, 1, 1, 1)]            # rows, cols, ld_param, ld_grad
+    offs, L = [], 0
+    for k, (r, c, ldp, ldg) in enumerate(shapes):
+        if k == 3:
+            L += 1                              # the last segment starts at an odd float: the scalar path
+        offs.append(L)
+        L += (r * ldg + 3) // 4 * 4
+    L = (L + 3) // 4 * 4
+    peers = [torch.randn(L, generator=g).to(cuda_device) for _ in range(world)]
+    gsum = peers[0].clone()
+    for k in range(1, world):
+        gsum = gsum + peers[k]                   # rank order, like the kernels
+    hp = (1e-3, (0.9, 0.999), 1e-8)
+
+    def state():
+        gg = torch.Generator().manual_seed(3)
+        out = []
+        for r, c, ldp, ldg in shapes:
+            out.append((torch.randn(r * ldp, generator=gg).to(cuda_device), torch.zeros(r * ldp, device=cuda_device),
+                        torch.zeros(r * ldp, device=cuda_device)))
+        return out
+    ref, got = state(), state()
+    for step in (1, 2):
+        gs.adam_step([(p, gsum[o:], m, v, r, c, ldp, ldg) for (p, m, v), o, (r, c, ldp, ldg) in zip(ref, offs, shapes)], *hp, step)
+        gs.adam_step_peers([(p, None, m, v, r, c, ldp, ldg) for (p, m, v), (r, c, ldp, ldg) in zip(got, shapes)], offs,
+                           [t.data_ptr() for t in peers], *hp, step)
+    for (pa, ma, va), (pb, mb, vb) in zip(ref, got):
+        assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb)
+    # reduce-scatter + all-gather form: rank r sums its slice and stores it into every rank's `reduced` buffer
+    reduced = [torch.full((L,), float("nan"), device=cuda_device) for _ in range(world)]
+    gp = (ctypes.c_void_p * world)(*[t.data_ptr() for t in peers])
+    rp = (ctypes.c_void_p * world)(*[t.data_ptr() for t in reduced])
+    for rank in range(world):
+        with torch.cuda.device(cuda_device):
+            _lib.check(lib.st3r_grad_reduce_scatter(world, rank, gp, rp, ctypes.c_int64(L), _lib.stream_ptr()),
+                       "st3r_grad_reduce_scatter")
+    for t in reduced:
+        assert torch.equal(t, gsum)
+
+
 # ------------------------------------------------------------------------------------------ full train step
 def test_train_steps_vs_oracle(cuda_device):
     """Three iterations of gs.py:143-161 (render 3 views, loss, backward, Adam): loss, gradients and updated

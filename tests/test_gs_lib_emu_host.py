@@ -41,6 +41,8 @@ def test_loss_and_adam(backend):
     t.test_fused_adam_vs_torch(CPU)
     t.test_adam_step_dev_equals_host_form(CPU)
     t.test_adam_layouts_bit_identical(CPU)
+    for world in (2, 3, 8):
+        t.test_peer_gradient_kernels_on_one_device(CPU, world)
 
 
 def test_train_steps_vs_oracle(backend_bwd):
